@@ -1,0 +1,9 @@
+"""B200-native window scoring for the R2Plus1D-Sync lip-sync detector (hot path only).
+
+Public surface mirrors the reference (`app/models/lip_sync_model.py`, `app/inference/predictor.py`,
+`app/preprocessing/audio.py`) for the window-scoring path; every numeric op runs in the hand-written
+sm_100a CUDA library `csrc/` through its C-ABI (`include/lsd_b200.h`).  There is no CPU fallback.
+"""
+from .state_spec import state_spec, make_synthetic_state_dict, synthetic_windows  # noqa: F401
+
+__all__ = ["state_spec", "make_synthetic_state_dict", "synthetic_windows"]
