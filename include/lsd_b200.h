@@ -1,0 +1,130 @@
+/*
+ * lsd_b200.h — C-ABI of the B200-native window-scoring library (liblsd_b200.so).
+ *
+ * The reference (PRADUMAN-KR/Multimodal-Lip-Sync-Deepfake-Detection-System) is 100 % Python and has no
+ * FFI of its own; its boundary for this path is
+ *   - `LipSyncModel.forward(visual, audio) -> logits`      app/models/lip_sync_model.py:86-136
+ *   - `LipSyncModel.load_state_dict(state, strict=True)`   app/inference/predictor.py:187-194
+ *   - `preprocess_audio(...)` (librosa log-mel)            app/preprocessing/audio.py:47-102
+ *   - `Predictor._run_chunked_inference(...)`              app/inference/predictor.py:554-580
+ *   - `Predictor._align_audio_chunk(...)`                  app/inference/predictor.py:525-552
+ * Each entry point below names the reference interface it replaces.  The Python host layer
+ * (`lipsync_b200`) binds these with ctypes; INTEGRATION.md shows the stub a reference maintainer adds.
+ *
+ * Conventions: plain pointers and sizes only (no torch types).  Every function returns 0 on success
+ * or a negative lsd_status; the message is available from lsd_last_error().  LSD_ERR_SHAPE maps to
+ * Python ValueError (HTTP 400 in the reference, app/api/routes.py:46-48), everything else to
+ * RuntimeError.  All device pointers are caller-owned; work is enqueued asynchronously on `stream`
+ * (a cudaStream_t passed as void*), with no hidden synchronisation and no hidden device allocation in
+ * lsd_forward / lsd_logmel / lsd_score_windows (the caller provides the workspace).  A handle is not
+ * thread-safe; the Python layer serialises access with a lock (the reference can enter forward from
+ * two threads).
+ */
+#ifndef LSD_B200_H
+#define LSD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lsd_handle lsd_handle;
+
+typedef enum {
+  LSD_OK = 0,
+  LSD_ERR_SHAPE = -1,      /* wrong rank / extent            -> ValueError   */
+  LSD_ERR_ARG = -2,        /* null pointer, bad enum         -> RuntimeError */
+  LSD_ERR_WEIGHTS = -3,    /* missing / mis-shaped state_dict entry (strict) */
+  LSD_ERR_CUDA = -4,       /* CUDA runtime / driver error                    */
+  LSD_ERR_WORKSPACE = -5,  /* workspace too small                            */
+  LSD_ERR_UNSUPPORTED = -6 /* e.g. not an sm_100 device                      */
+} lsd_status;
+
+typedef enum { LSD_F32 = 0, LSD_F16 = 1, LSD_BF16 = 2, LSD_U8 = 3, LSD_I64 = 4 } lsd_dtype;
+
+/* video memory layout: NCDHW is what the reference hands over (video.py:552-556 builds (3,T,H,W));
+ * NDHWC is the raw-track layout (N,T,H,W,3) that the window builder produces. */
+typedef enum { LSD_NCDHW = 0, LSD_NDHWC = 1 } lsd_layout;
+
+/* arithmetic of the conv/GEMM stack: FP32 = CUDA-core FFMA path (parity <= 1e-4 rel);
+ * BF16 = tcgen05 tensor-core path with fp32 accumulation (parity <= 2e-2 abs on logits). */
+typedef enum { LSD_PREC_FP32 = 0, LSD_PREC_BF16 = 1 } lsd_precision;
+
+/* One state_dict entry, host memory (replaces torch.load + load_state_dict, predictor.py:187-194). */
+typedef struct {
+  const char* name;   /* reference key, e.g. "visual_encoder.layer1.conv1.0.weight" */
+  int dtype;          /* LSD_F32 (all parameters/buffers) or LSD_I64 (num_batches_tracked, ignored) */
+  int ndim;
+  int64_t shape[8];
+  const void* data;   /* host pointer, contiguous */
+} lsd_tensor;
+
+/* Optional extra outputs of lsd_forward (the `return_aux=True` dict, lip_sync_model.py:130-136).
+ * Any pointer may be NULL.  All fp32, device memory. */
+typedef struct {
+  float* visual_tokens; /* (B, T, 256)        */
+  float* audio_tokens;  /* (B, T_audio_tok, 256), T_audio_tok = lsd_audio_tokens(Ta) */
+  float* fused_tokens;  /* (B, T, 256)        */
+  float* cls_output;    /* (B, 256)           */
+} lsd_aux;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int lsd_create(lsd_handle** out, int device);
+void lsd_destroy(lsd_handle* h);
+const char* lsd_last_error(lsd_handle* h); /* h may be NULL: returns the last create() error */
+int lsd_version(void);
+
+/* ---- weights: replaces LipSyncModel.load_state_dict(strict=True) ----------------------------- */
+/* Consumes the 270-entry reference state_dict (fp32, host), folds eval-mode BatchNorm (+conv bias)
+ * into per-channel scale/shift and repacks every conv/linear weight into the
+ * device layouts the kernels read (fp32 [tap][Cin][Cout]; bf16 UMMA core-matrix tiles). */
+int lsd_load_weights(lsd_handle* h, const lsd_tensor* tensors, int n);
+
+/* ---- forward: replaces LipSyncModel.forward(visual, audio) ----------------------------------- */
+int lsd_audio_tokens(int Ta);     /* audio token count produced by the audio encoder for Ta mel frames */
+size_t lsd_workspace_bytes(lsd_handle* h, int B, int T, int H, int W, int F, int Ta, int precision);
+int lsd_forward(lsd_handle* h,
+                const void* video, int video_dtype, int video_layout, /* device, (B,3,T,H,W) or (B,T,H,W,3) */
+                const void* audio, int audio_dtype,                   /* device, (B,1,F,Ta) */
+                int B, int T, int H, int W, int F, int Ta,
+                int precision,
+                float* logits_out,                                    /* device, B floats */
+                const lsd_aux* aux_or_null,
+                void* workspace, size_t workspace_bytes,
+                void* stream);
+
+/* ---- log-mel front end: replaces preprocess_audio's librosa calls (audio.py:80-91) ----------- */
+/* pcm: device fp32 mono 16 kHz, clips concatenated; clip c spans [clip_offsets[c], clip_offsets[c+1]).
+ * mel_out: device fp32, clip c written as (80, frames_c) row-major at mel_offsets[c] (in floats),
+ * frames_c = 1 + len_c / 160.  ref=max is per clip (two-pass).  scratch: n_clips floats (device). */
+int lsd_logmel_frames(int64_t n_samples);
+int lsd_logmel(lsd_handle* h, const float* pcm, const int64_t* clip_offsets_host, int n_clips,
+               float* mel_out, const int64_t* mel_offsets_host, float* scratch, void* stream);
+
+/* ---- window builder + batched scoring: replaces the serial loop of _run_chunked_inference ---- */
+/* track: device uint8 (n_frames, H, W, 3) mouth crops (video.py:576-588 contract, before the
+ * astype(float32)/255 of video.py:552-556).  starts: host int32 absolute start frame per window,
+ * relative to track frame 0.  mel_full: device fp32 (1, F, Ta_full) clip-level log-mel.
+ * Audio windows follow _align_audio_chunk (predictor.py:525-552) with chunk_a_size = Ta.
+ * Builds the windows on device and runs lsd_forward in batches of `batch`. */
+size_t lsd_score_workspace_bytes(lsd_handle* h, int batch, int T, int H, int W, int F, int Ta, int precision);
+int lsd_score_windows(lsd_handle* h, const uint8_t* track, int n_frames, int H, int W,
+                      const int32_t* starts_host, int n_windows, int T,
+                      const float* mel_full, int F, int Ta_full, int total_v_frames, int Ta,
+                      int precision, int batch, float* logits_out,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- introspection (tests / profiling) ------------------------------------------------------- */
+/* Named intermediate of the last lsd_forward on this handle: byte offset into the workspace. */
+int lsd_stage_info(lsd_handle* h, const char* name, size_t* offset_bytes, int64_t* numel, int* dtype);
+int lsd_stage_count(lsd_handle* h);
+const char* lsd_stage_name(lsd_handle* h, int i);
+/* Number of kernels this library launched on behalf of the handle since creation. */
+int64_t lsd_launch_count(lsd_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSD_B200_H */

@@ -4,6 +4,10 @@ Public surface mirrors the reference (`app/models/lip_sync_model.py`, `app/infer
 `app/preprocessing/audio.py`) for the window-scoring path; every numeric op runs in the hand-written
 sm_100a CUDA library `csrc/` through its C-ABI (`include/lsd_b200.h`).  There is no CPU fallback.
 """
-from .state_spec import state_spec, make_synthetic_state_dict, synthetic_windows  # noqa: F401
+from .state_spec import state_spec, make_synthetic_state_dict, synthetic_windows, BUFFER_SUFFIXES  # noqa: F401
+from .model import LipSyncModel  # noqa: F401
+from .inference import Predictor, partition_windows, gather_logits  # noqa: F401
+from .audio import preprocess_audio, preprocess_audio_pcm, logmel_db, fit_frames  # noqa: F401
 
-__all__ = ["state_spec", "make_synthetic_state_dict", "synthetic_windows"]
+__all__ = ["state_spec", "make_synthetic_state_dict", "synthetic_windows", "LipSyncModel", "Predictor",
+           "partition_windows", "gather_logits", "preprocess_audio", "preprocess_audio_pcm", "logmel_db", "fit_frames"]

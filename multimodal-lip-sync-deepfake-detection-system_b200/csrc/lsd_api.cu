@@ -1,0 +1,685 @@
+// C-ABI of liblsd_b200.so (include/lsd_b200.h): handle, weight packing (BN fold), forward orchestration.
+// Host-side only; every numeric op is a kernel from kernels_f32.cu / logmel.cu / umma_conv.cu.
+#include "../../include/lsd_b200.h"
+#include "lsd_kernels.h"
+#include "lsd_internal.h"
+
+#include <cmath>
+#include <initializer_list>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+using namespace lsd;
+
+static thread_local std::string g_create_error;
+
+int lsd_fail(lsd_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CUDA_OK(h, expr)                                                                              \
+  do {                                                                                                \
+    cudaError_t e_ = (expr);                                                                          \
+    if (e_ != cudaSuccess) return lsd_fail(h, LSD_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+extern "C" int lsd_version(void) { return 100; }
+
+extern "C" const char* lsd_last_error(lsd_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int lsd_create(lsd_handle** out, int device) {
+  if (!out) return lsd_fail(nullptr, LSD_ERR_ARG, "lsd_create: out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return lsd_fail(nullptr, LSD_ERR_CUDA, "lsd_create: no CUDA device (%s); this library has no CPU fallback",
+                    cudaGetErrorString(e));
+  if (device < 0 || device >= count) return lsd_fail(nullptr, LSD_ERR_ARG, "lsd_create: bad device %d", device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return lsd_fail(nullptr, LSD_ERR_CUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10)
+    return lsd_fail(nullptr, LSD_ERR_UNSUPPORTED, "lsd_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                    device, prop.major, prop.minor);
+  lsd_handle* h = new lsd_handle();
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  h->launches0 = kernel_launches();
+  int rc = init_logmel_tables(h);
+  if (rc != 0) { g_create_error = h->err; delete h; return rc; }
+  *out = h;
+  return LSD_OK;
+}
+
+extern "C" void lsd_destroy(lsd_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->warena) cudaFree(h->warena);
+  if (h->barena) cudaFree(h->barena);
+  if (h->mel_tables) cudaFree(h->mel_tables);
+  delete h;
+}
+
+extern "C" int64_t lsd_launch_count(lsd_handle* h) { return h ? kernel_launches() - h->launches0 : 0; }
+
+// ================================================================================================
+// Weights: consume the reference state_dict, fold eval BatchNorm (+conv bias).
+// ================================================================================================
+namespace {
+
+struct HostT {
+  const float* data = nullptr;
+  int ndim = 0;
+  int64_t shape[8] = {0};
+  int64_t numel() const { int64_t n = 1; for (int i = 0; i < ndim; ++i) n *= shape[i]; return n; }
+};
+
+struct Loader {
+  lsd_handle* h;
+  std::map<std::string, HostT> t;
+  std::vector<float> arena;          // fp32 host staging of the packed device arena
+  std::string missing;
+  const HostT* get(const std::string& name, std::initializer_list<int64_t> shape) {
+    auto it = t.find(name);
+    if (it == t.end()) { if (missing.empty()) missing = "missing key " + name; return nullptr; }
+    const HostT& x = it->second;
+    bool ok = x.ndim == (int)shape.size();
+    int i = 0;
+    for (int64_t s : shape) { if (ok && x.shape[i] != s) ok = false; ++i; }
+    if (!ok) { if (missing.empty()) missing = "shape mismatch for " + name; return nullptr; }
+    return &x;
+  }
+  size_t reserve(size_t n) {  // 64-float (256 B) aligned
+    size_t off = (arena.size() + 63) & ~size_t(63);
+    arena.resize(off + n, 0.f);
+    return off;
+  }
+};
+
+// Folded conv / linear: weights [tap][Cin][Cout], per-channel scale/shift.
+//   bn != "" : scale = gamma/sqrt(var+eps), shift = beta - mean*scale + bias*scale   (App. A)
+//   bn == "" : scale = 1 (null), shift = bias
+bool pack_conv(Loader& L, const std::string& key, const std::string& wname, const std::string& bname, const std::string& bn,
+               int Cout, int Cin, int kt, int kh, int kw) {
+  const HostT* w = nullptr;
+  if (kt > 0) w = L.get(wname, {Cout, Cin, kt, kh, kw});
+  else if (kh > 0) { w = L.get(wname, {Cout, Cin, kh, kw}); kt = 1; }
+  else if (kw > 0) { w = L.get(wname, {Cout, Cin, kw}); kt = kh = 1; }
+  else { w = L.get(wname, {Cout, Cin}); kt = kh = kw = 1; }
+  if (!w) return false;
+  const int taps = kt * kh * kw;
+  ConvP c;
+  c.Cin = Cin; c.Cout = Cout; c.kt = kt; c.kh = kh; c.kw = kw;
+  c.w_off = L.reserve((size_t)taps * Cin * Cout);
+  for (int co = 0; co < Cout; ++co)
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int tp = 0; tp < taps; ++tp)
+        L.arena[c.w_off + ((size_t)tp * Cin + ci) * Cout + co] = w->data[((size_t)co * Cin + ci) * taps + tp];
+  const HostT* b = bname.empty() ? nullptr : L.get(bname, {Cout});
+  if (!bname.empty() && !b) return false;
+  c.shift_off = L.reserve(Cout);
+  c.has_scale = !bn.empty();
+  if (c.has_scale) {
+    const HostT *g = L.get(bn + ".weight", {Cout}), *be = L.get(bn + ".bias", {Cout}),
+                *mu = L.get(bn + ".running_mean", {Cout}), *var = L.get(bn + ".running_var", {Cout});
+    if (!g || !be || !mu || !var) return false;
+    if (L.t.find(bn + ".num_batches_tracked") == L.t.end()) { L.missing = "missing key " + bn + ".num_batches_tracked"; return false; }
+    c.scale_off = L.reserve(Cout);
+    for (int i = 0; i < Cout; ++i) {
+      const float sc = g->data[i] / sqrtf(var->data[i] + 1e-5f);
+      L.arena[c.scale_off + i] = sc;
+      L.arena[c.shift_off + i] = be->data[i] - mu->data[i] * sc + (b ? b->data[i] * sc : 0.f);
+    }
+  } else {
+    for (int i = 0; i < Cout; ++i) L.arena[c.shift_off + i] = b ? b->data[i] : 0.f;
+  }
+  L.h->convs[key] = c;
+  return true;
+}
+
+bool pack_vec(Loader& L, const std::string& key, const std::string& name, std::initializer_list<int64_t> shape) {
+  const HostT* v = L.get(name, shape);
+  if (!v) return false;
+  const size_t off = L.reserve((size_t)v->numel());
+  memcpy(&L.arena[off], v->data, sizeof(float) * v->numel());
+  L.h->vecs[key] = off;
+  return true;
+}
+
+// Cross-attention input projections regrouped by *source* tensor so each source needs one GEMM:
+//   from visual tokens: [Q of v2a | K of a2v | V of a2v];  from audio tokens: [Q of a2v | K of v2a | V of v2a]
+bool pack_cross_inproj(Loader& L) {
+  const HostT *w1 = L.get("cross_modal.v2a_attn.in_proj_weight", {768, 256}), *b1 = L.get("cross_modal.v2a_attn.in_proj_bias", {768}),
+              *w2 = L.get("cross_modal.a2v_attn.in_proj_weight", {768, 256}), *b2 = L.get("cross_modal.a2v_attn.in_proj_bias", {768});
+  if (!w1 || !b1 || !w2 || !b2) return false;
+  for (int side = 0; side < 2; ++side) {
+    ConvP c;
+    c.Cin = 256; c.Cout = 768; c.kt = c.kh = c.kw = 1; c.has_scale = false;
+    c.w_off = L.reserve(256 * 768);
+    c.shift_off = L.reserve(768);
+    for (int blk = 0; blk < 3; ++blk) {
+      // side 0 (visual source): Q from v2a, K/V from a2v;  side 1 (audio source): Q from a2v, K/V from v2a
+      const bool from_v2a = (side == 0) ? (blk == 0) : (blk != 0);
+      const HostT* w = from_v2a ? w1 : w2;
+      const HostT* b = from_v2a ? b1 : b2;
+      for (int o = 0; o < 256; ++o) {
+        const int src_row = blk * 256 + o;
+        L.arena[c.shift_off + blk * 256 + o] = b->data[src_row];
+        for (int i = 0; i < 256; ++i) L.arena[c.w_off + (size_t)i * 768 + blk * 256 + o] = w->data[(size_t)src_row * 256 + i];
+      }
+    }
+    L.h->convs[side == 0 ? "cross.in_v" : "cross.in_a"] = c;
+  }
+  return true;
+}
+
+}  // namespace
+
+extern "C" int lsd_load_weights(lsd_handle* h, const lsd_tensor* tensors, int n) {
+  if (!h || !tensors) return lsd_fail(h, LSD_ERR_ARG, "lsd_load_weights: null argument");
+  CUDA_OK(h, cudaSetDevice(h->device));
+  Loader L;
+  L.h = h;
+  h->convs.clear();
+  h->vecs.clear();
+  h->loaded = false;
+  for (int i = 0; i < n; ++i) {
+    const lsd_tensor& s = tensors[i];
+    if (!s.name) return lsd_fail(h, LSD_ERR_ARG, "lsd_load_weights: tensor %d has no name", i);
+    if (s.dtype == LSD_I64) { HostT x; x.ndim = 0; L.t[s.name] = x; continue; }  // num_batches_tracked: presence only
+    if (s.dtype != LSD_F32 || !s.data) return lsd_fail(h, LSD_ERR_WEIGHTS, "lsd_load_weights: %s must be fp32 host data", s.name);
+    HostT x;
+    x.data = reinterpret_cast<const float*>(s.data);
+    x.ndim = s.ndim;
+    for (int d = 0; d < s.ndim && d < 8; ++d) x.shape[d] = s.shape[d];
+    L.t[s.name] = x;
+  }
+  if (n != 270) return lsd_fail(h, LSD_ERR_WEIGHTS, "lsd_load_weights: expected the 270-entry reference state_dict, got %d entries", n);
+  bool ok = true;
+  auto conv3 = [&](const std::string& p, int co, int ci, int kt, int kh, int kw, const std::string& bias = "") {
+    ok = ok && pack_conv(L, p, p + ".0.weight", bias, p + ".1", co, ci, kt, kh, kw);
+  };
+  // visual encoder (visual_encoder.py:113-152)
+  conv3("visual_encoder.stem", 64, 3, 3, 7, 7);
+  const int chans[4][2] = {{64, 64}, {64, 128}, {128, 256}, {256, 256}};
+  for (int l = 0; l < 4; ++l) {
+    const std::string p = "visual_encoder.layer" + std::to_string(l + 1);
+    conv3(p + ".conv1", chans[l][1], chans[l][0], 3, 3, 3);
+    conv3(p + ".conv2", chans[l][1], chans[l][1], 3, 3, 3);
+    if (l > 0) conv3(p + ".downsample", chans[l][1], chans[l][0], 1, 1, 1);
+  }
+  // audio encoder (audio_encoder.py:128-156)
+  conv3("audio_encoder.stem", 64, 1, 0, 7, 7);
+  for (int l = 0; l < 4; ++l) {
+    const std::string p = "audio_encoder.layer" + std::to_string(l + 1);
+    conv3(p + ".conv1", chans[l][1], chans[l][0], 0, 3, 3);
+    conv3(p + ".conv2", chans[l][1], chans[l][1], 0, 3, 3);
+    if (l > 0) conv3(p + ".downsample", chans[l][1], chans[l][0], 0, 1, 1);
+  }
+  auto linear = [&](const std::string& key, const std::string& p, int co, int ci) {
+    ok = ok && pack_conv(L, key, p + ".weight", p + ".bias", "", co, ci, 0, 0, 0);
+  };
+  linear("projection.visual_proj", "projection.visual_proj", 256, 256);
+  linear("projection.audio_proj", "projection.audio_proj", 256, 256);
+  ok = ok && pack_cross_inproj(L);
+  linear("cross.v2a.out", "cross_modal.v2a_attn.out_proj", 256, 256);
+  linear("cross.a2v.out", "cross_modal.a2v_attn.out_proj", 256, 256);
+  linear("cross.gate0", "cross_modal.gate.0", 256, 512);
+  ok = ok && pack_vec(L, "cross.gate2.w", "cross_modal.gate.2.weight", {1, 256});
+  ok = ok && pack_vec(L, "cross.gate2.b", "cross_modal.gate.2.bias", {1});
+  linear("cross.fuse", "cross_modal.fuse.0", 256, 256);
+  // temporal transformer (temporal.py:31-77)
+  ok = ok && pack_vec(L, "temporal.cls", "temporal.cls_token", {1, 1, 256});
+  for (int k : {3, 5, 7}) {
+    const std::string p = "temporal.branch_k" + std::to_string(k);
+    ok = ok && pack_conv(L, p, p + ".0.weight", "", p + ".1", 256, 256, 0, 0, k);
+  }
+  linear("temporal.pre_scale_proj", "temporal.pre_scale_proj", 256, 768);
+  for (int l = 0; l < 4; ++l) {
+    const std::string p = "temporal.transformer.layers." + std::to_string(l);
+    const std::string k = "t" + std::to_string(l);
+    ok = ok && pack_conv(L, k + ".in", p + ".self_attn.in_proj_weight", p + ".self_attn.in_proj_bias", "", 768, 256, 0, 0, 0);
+    linear(k + ".out", p + ".self_attn.out_proj", 256, 256);
+    linear(k + ".ff1", p + ".linear1", 1024, 256);
+    linear(k + ".ff2", p + ".linear2", 256, 1024);
+    ok = ok && pack_vec(L, k + ".ln1.w", p + ".norm1.weight", {256}) && pack_vec(L, k + ".ln1.b", p + ".norm1.bias", {256});
+    ok = ok && pack_vec(L, k + ".ln2.w", p + ".norm2.weight", {256}) && pack_vec(L, k + ".ln2.b", p + ".norm2.bias", {256});
+  }
+  // artifact detector (artifact_detector.py:33-43,74-93,142-147)
+  const std::string td = "artifact_detector.temporal_detector.temporal_conv";
+  ok = ok && pack_conv(L, "art.td0", td + ".0.weight", td + ".0.bias", td + ".1", 128, 256, 3, 3, 3);
+  ok = ok && pack_conv(L, "art.td3", td + ".3.weight", td + ".3.bias", td + ".4", 64, 128, 3, 3, 3);
+  const std::string hf = "artifact_detector.high_freq_detector";
+  ok = ok && pack_conv(L, "art.lap", hf + ".laplacian.weight", "", "", 3, 3, 0, 3, 3);
+  ok = ok && pack_conv(L, "art.hf0", hf + ".conv3d.0.weight", hf + ".conv3d.0.bias", hf + ".conv3d.1", 32, 3, 3, 3, 3);
+  ok = ok && pack_conv(L, "art.hf3", hf + ".conv3d.3.weight", hf + ".conv3d.3.bias", hf + ".conv3d.4", 64, 32, 3, 3, 3);
+  linear("art.fuse0", "artifact_detector.artifact_fusion.0", 256, 448);
+  linear("art.fuse2", "artifact_detector.artifact_fusion.2", 128, 256);
+  // head (classifier.py:14-20)
+  linear("head.fc0", "classifier.net.0", 128, 384);
+  ok = ok && pack_vec(L, "head.ln.w", "classifier.net.3.weight", {128}) && pack_vec(L, "head.ln.b", "classifier.net.3.bias", {128});
+  ok = ok && pack_vec(L, "head.out.w", "classifier.net.4.weight", {1, 128}) && pack_vec(L, "head.out.b", "classifier.net.4.bias", {1});
+  if (!ok) return lsd_fail(h, LSD_ERR_WEIGHTS, "lsd_load_weights: %s", L.missing.empty() ? "pack failed" : L.missing.c_str());
+
+  if (h->warena) { cudaFree(h->warena); h->warena = nullptr; }
+  CUDA_OK(h, cudaMalloc(&h->warena, L.arena.size() * sizeof(float)));
+  CUDA_OK(h, cudaMemcpy(h->warena, L.arena.data(), L.arena.size() * sizeof(float), cudaMemcpyHostToDevice));
+  int rc = pack_bf16_weights(h, L.arena);
+  if (rc != 0) return rc;
+  h->loaded = true;
+  return LSD_OK;
+}
+
+// ================================================================================================
+// Workspace plan
+// ================================================================================================
+namespace {
+
+inline int osz(int i, int k, int s, int p) { return (i + 2 * p - k) / s + 1; }
+
+struct Shapes {
+  int B, T, H, W, F, Ta;
+  int Hs, Ws, H1, W1, H2, W2, H3, W3, H4, W4;          // visual: stem conv, pool(=layer1), layer2..4
+  int Fs, As, F1, A1, F2, A2, F3, A3, F4, A4;          // audio: stem conv, pool(=layer1), layer2..4 (A = time)
+  int Hh, Wh, Hg, Wg;                                  // hf: conv0 out, conv3 out
+  int Td;                                              // delta frames (T-1, or 1 with zeros if T == 1)
+};
+
+int make_shapes(lsd_handle* h, int B, int T, int H, int W, int F, int Ta, Shapes& s) {
+  if (B < 0 || T < 1 || H < 1 || W < 1 || F < 1 || Ta < 1)
+    return lsd_fail(h, LSD_ERR_SHAPE, "expected visual (B,3,T,H,W) and audio (B,1,F,T_a) with positive extents, got B=%d T=%d H=%d W=%d F=%d Ta=%d", B, T, H, W, F, Ta);
+  s.B = B; s.T = T; s.H = H; s.W = W; s.F = F; s.Ta = Ta;
+  s.Hs = osz(H, 7, 2, 3); s.Ws = osz(W, 7, 2, 3);
+  s.H1 = osz(s.Hs, 3, 2, 1); s.W1 = osz(s.Ws, 3, 2, 1);
+  s.H2 = osz(s.H1, 3, 2, 1); s.W2 = osz(s.W1, 3, 2, 1);
+  s.H3 = osz(s.H2, 3, 2, 1); s.W3 = osz(s.W2, 3, 2, 1);
+  s.H4 = osz(s.H3, 3, 2, 1); s.W4 = osz(s.W3, 3, 2, 1);
+  s.Fs = osz(F, 7, 2, 3); s.As = osz(Ta, 7, 2, 3);
+  s.F1 = osz(s.Fs, 3, 2, 1); s.A1 = osz(s.As, 3, 2, 1);
+  s.F2 = osz(s.F1, 3, 2, 1); s.A2 = osz(s.A1, 3, 2, 1);
+  s.F3 = osz(s.F2, 3, 2, 1); s.A3 = s.A2;               // stride (2,1): preserve_audio_temporal (audio_encoder.py:144)
+  s.F4 = osz(s.F3, 3, 2, 1); s.A4 = s.A3;
+  s.Hh = osz(H, 3, 2, 1); s.Wh = osz(W, 3, 2, 1);
+  s.Hg = osz(s.Hh, 3, 2, 1); s.Wg = osz(s.Wh, 3, 2, 1);
+  s.Td = T > 1 ? T - 1 : 1;
+  if (s.H4 < 1 || s.W4 < 1 || s.F4 < 1 || s.A4 < 1 || s.Hg < 1 || s.Wg < 1)
+    return lsd_fail(h, LSD_ERR_SHAPE, "input extents too small for the encoder strides");
+  return 0;
+}
+
+struct Plan {
+  std::vector<Stage> stages;
+  size_t cursor = 0;  // bytes
+  size_t add(const char* name, int64_t numel, int dtype = LSD_F32) {
+    const size_t esz = (dtype == LSD_F32) ? 4 : 2;
+    cursor = (cursor + 255) & ~size_t(255);
+    Stage st; st.name = name; st.offset = cursor; st.numel = numel; st.dtype = dtype;
+    stages.push_back(st);
+    cursor += (size_t)numel * esz;
+    return st.offset;
+  }
+  size_t find(const char* name) const {
+    for (const Stage& s : stages) if (s.name == name) return s.offset;
+    return (size_t)-1;
+  }
+};
+
+void make_plan_f32(const Shapes& s, Plan& p) {
+  const int64_t B = s.B, T = s.T;
+  p.add("vid", B * T * s.H * s.W * 3);
+  p.add("aud", B * s.F * s.Ta);
+  p.add("v_stem_conv", B * T * s.Hs * s.Ws * 64);
+  p.add("v_stem", B * T * s.H1 * s.W1 * 64);
+  p.add("v_l1a", B * T * s.H1 * s.W1 * 64);
+  p.add("v_layer1", B * T * s.H1 * s.W1 * 64);
+  p.add("v_l2a", B * T * s.H2 * s.W2 * 128);
+  p.add("v_l2d", B * T * s.H2 * s.W2 * 128);
+  p.add("v_layer2", B * T * s.H2 * s.W2 * 128);
+  p.add("v_l3a", B * T * s.H3 * s.W3 * 256);
+  p.add("v_l3d", B * T * s.H3 * s.W3 * 256);
+  p.add("v_layer3", B * T * s.H3 * s.W3 * 256);
+  p.add("v_l4a", B * T * s.H4 * s.W4 * 256);
+  p.add("v_l4d", B * T * s.H4 * s.W4 * 256);
+  p.add("v_layer4", B * T * s.H4 * s.W4 * 256);
+  p.add("v_feat", B * T * 256);
+  p.add("a_stem_conv", B * s.Fs * s.As * 64);
+  p.add("a_stem", B * s.F1 * s.A1 * 64);
+  p.add("a_l1a", B * s.F1 * s.A1 * 64);
+  p.add("a_layer1", B * s.F1 * s.A1 * 64);
+  p.add("a_l2a", B * s.F2 * s.A2 * 128);
+  p.add("a_l2d", B * s.F2 * s.A2 * 128);
+  p.add("a_layer2", B * s.F2 * s.A2 * 128);
+  p.add("a_l3a", B * s.F3 * s.A3 * 256);
+  p.add("a_l3d", B * s.F3 * s.A3 * 256);
+  p.add("a_layer3", B * s.F3 * s.A3 * 256);
+  p.add("a_l4a", B * s.F4 * s.A4 * 256);
+  p.add("a_l4d", B * s.F4 * s.A4 * 256);
+  p.add("a_layer4", B * s.F4 * s.A4 * 256);
+  p.add("a_feat", B * s.A4 * 256);
+  p.add("v_emb", B * T * 256);
+  p.add("a_emb", B * s.A4 * 256);
+  p.add("a_int", B * T * 256);
+  p.add("proj_v", B * T * 768);
+  p.add("proj_a", B * T * 768);
+  p.add("att1", B * T * 256);
+  p.add("att2", B * T * 256);
+  p.add("gate_in", B * T * 512);
+  p.add("gate_h", B * T * 256);
+  p.add("blend", B * T * 256);
+  p.add("fused", B * T * 256);
+  p.add("ms_cat", B * T * 768);
+  p.add("tok", B * (T + 1) * 256);
+  p.add("tok_ln", B * (T + 1) * 256);
+  p.add("tok_qkv", B * (T + 1) * 768);
+  p.add("tok_att", B * (T + 1) * 256);
+  p.add("tok_ff", B * (T + 1) * 1024);
+  p.add("t_layer0", B * (T + 1) * 256);
+  p.add("t_layer3", B * (T + 1) * 256);
+  p.add("art_a", B * T * s.H4 * s.W4 * 128);
+  p.add("art_b", B * T * s.H4 * s.W4 * 64);
+  p.add("art_delta", B * s.Td * s.H4 * s.W4 * 256);
+  p.add("hf_lap", B * T * s.H * s.W * 3);
+  p.add("hf_front", B * T * s.Hh * s.Wh * 32);
+  p.add("hf_back", B * T * s.Hg * s.Wg * 64);
+  p.add("comb", B * 448);
+  p.add("art_h", B * 256);
+  p.add("feat", B * 384);
+  p.add("head_h", B * 128);
+}
+
+struct Ctx {
+  lsd_handle* h;
+  char* ws;
+  const Plan* plan;
+  cudaStream_t st;
+  float* buf(const char* name) const { return reinterpret_cast<float*>(ws + plan->find(name)); }
+  const float* W(const ConvP& c) const { return h->warena + c.w_off; }
+};
+
+// one conv/linear launch on the fp32 path
+void conv(const Ctx& c, const char* key, const float* x, int in_ld, int N, int Ti, int Hi, int Wi, int st, int sh, int sw,
+          int pt, int ph, int pw, float* y, int out_ld, int act, const float* res = nullptr, int res_ld = 0,
+          int grp = 0, int grp_stride = 0, int row_off = 0) {
+  const ConvP& w = c.h->convs.at(key);
+  ConvF32 p;
+  p.x = x; p.w = c.h->warena + w.w_off;
+  p.scale = w.has_scale ? c.h->warena + w.scale_off : nullptr;
+  p.shift = c.h->warena + w.shift_off;
+  p.res = res; p.y = y;
+  p.N = N; p.Ti = Ti; p.Hi = Hi; p.Wi = Wi; p.Cin = w.Cin;
+  p.kt = w.kt; p.kh = w.kh; p.kw = w.kw; p.st = st; p.sh = sh; p.sw = sw; p.pt = pt; p.ph = ph; p.pw = pw;
+  p.To = osz(Ti, w.kt, st, pt); p.Ho = osz(Hi, w.kh, sh, ph); p.Wo = osz(Wi, w.kw, sw, pw); p.Cout = w.Cout;
+  p.in_ld = in_ld; p.w_ld = w.Cout; p.out_ld = out_ld; p.res_ld = res_ld; p.act = act;
+  p.grp = grp; p.grp_stride = grp_stride; p.row_off = row_off;
+  launch_conv_f32(p, c.st);
+}
+inline void linear(const Ctx& c, const char* key, const float* x, int in_ld, int rows, float* y, int out_ld, int act,
+                   const float* res = nullptr, int res_ld = 0, int grp = 0, int grp_stride = 0, int row_off = 0) {
+  conv(c, key, x, in_ld, 1, 1, 1, rows, 1, 1, 1, 0, 0, 0, y, out_ld, act, res, res_ld, grp, grp_stride, row_off);
+}
+
+// Residual stage (visual_encoder.py:81-87 / audio_encoder.py:82-89): conv1+BN+ReLU, conv2+BN, (+BN(ds(x)) | +x), ReLU.
+void res_stage(const Ctx& c, const std::string& p, const float* x, int N, int Ti, int Hi, int Wi, int st, int sh, int sw,
+               bool is3d, float* a, float* d, float* y, int Cout) {
+  const int pt = is3d ? 1 : 0;
+  const ConvP& w1 = c.h->convs.at(p + ".conv1");
+  const int To = osz(Ti, w1.kt, st, pt), Ho = osz(Hi, 3, sh, 1), Wo = osz(Wi, 3, sw, 1);
+  conv(c, (p + ".conv1").c_str(), x, w1.Cin, N, Ti, Hi, Wi, st, sh, sw, pt, 1, 1, a, Cout, ACT_RELU);
+  const float* idt = x;
+  if (c.h->convs.count(p + ".downsample")) {
+    conv(c, (p + ".downsample").c_str(), x, w1.Cin, N, Ti, Hi, Wi, st, sh, sw, 0, 0, 0, d, Cout, ACT_NONE);
+    idt = d;
+  }
+  conv(c, (p + ".conv2").c_str(), a, Cout, N, To, Ho, Wo, 1, 1, 1, pt, 1, 1, y, Cout, ACT_RELU, idt, Cout);
+}
+
+int forward_f32(lsd_handle* h, const Shapes& s, const Plan& plan, char* ws, const lsd_aux* aux, float* logits, cudaStream_t st,
+                bool inputs_ready, const void* video, int vdt, int vlayout, const void* audio, int adt) {
+  Ctx c{h, ws, &plan, st};
+  const int B = s.B, T = s.T;
+  float* vid = c.buf("vid");
+  float* aud = c.buf("aud");
+  if (!inputs_ready) {
+    if (vlayout == LSD_NCDHW) launch_video_to_ndhwc(video, vdt, vid, B, 3, T, s.H, s.W, st);
+    else launch_cast_to_f32(video, vdt, vid, (int64_t)B * T * s.H * s.W * 3, vdt == LSD_U8 ? 255.0f : 1.0f, st);
+    launch_cast_to_f32(audio, adt, aud, (int64_t)B * s.F * s.Ta, 1.0f, st);
+  }
+  // ---- visual encoder (visual_encoder.py:166-201)
+  conv(c, "visual_encoder.stem", vid, 3, B, T, s.H, s.W, 1, 2, 2, 1, 3, 3, c.buf("v_stem_conv"), 64, ACT_RELU);
+  launch_maxpool3x3s2(c.buf("v_stem_conv"), c.buf("v_stem"), B * T, s.Hs, s.Ws, 64, st);
+  res_stage(c, "visual_encoder.layer1", c.buf("v_stem"), B, T, s.H1, s.W1, 1, 1, 1, true, c.buf("v_l1a"), nullptr, c.buf("v_layer1"), 64);
+  res_stage(c, "visual_encoder.layer2", c.buf("v_layer1"), B, T, s.H1, s.W1, 1, 2, 2, true, c.buf("v_l2a"), c.buf("v_l2d"), c.buf("v_layer2"), 128);
+  res_stage(c, "visual_encoder.layer3", c.buf("v_layer2"), B, T, s.H2, s.W2, 1, 2, 2, true, c.buf("v_l3a"), c.buf("v_l3d"), c.buf("v_layer3"), 256);
+  res_stage(c, "visual_encoder.layer4", c.buf("v_layer3"), B, T, s.H3, s.W3, 1, 2, 2, true, c.buf("v_l4a"), c.buf("v_l4d"), c.buf("v_layer4"), 256);
+  const float* vmap = c.buf("v_layer4");  // (B,T,H4,W4,256)
+  launch_mean_mid(vmap, c.buf("v_feat"), B * T, s.H4 * s.W4, 256, 256, st);  // (B,T,256) token layout
+  // ---- audio encoder (audio_encoder.py:173-205): (B,1,F,Ta) == channels-last (B,F,Ta,1)
+  conv(c, "audio_encoder.stem", aud, 1, B, 1, s.F, s.Ta, 1, 2, 2, 0, 3, 3, c.buf("a_stem_conv"), 64, ACT_RELU);
+  launch_maxpool3x3s2(c.buf("a_stem_conv"), c.buf("a_stem"), B, s.Fs, s.As, 64, st);
+  res_stage(c, "audio_encoder.layer1", c.buf("a_stem"), B, 1, s.F1, s.A1, 1, 1, 1, false, c.buf("a_l1a"), nullptr, c.buf("a_layer1"), 64);
+  res_stage(c, "audio_encoder.layer2", c.buf("a_layer1"), B, 1, s.F1, s.A1, 1, 2, 2, false, c.buf("a_l2a"), c.buf("a_l2d"), c.buf("a_layer2"), 128);
+  res_stage(c, "audio_encoder.layer3", c.buf("a_layer2"), B, 1, s.F2, s.A2, 1, 2, 1, false, c.buf("a_l3a"), c.buf("a_l3d"), c.buf("a_layer3"), 256);
+  res_stage(c, "audio_encoder.layer4", c.buf("a_layer3"), B, 1, s.F3, s.A3, 1, 2, 1, false, c.buf("a_l4a"), c.buf("a_l4d"), c.buf("a_layer4"), 256);
+  const int TA = s.A4;
+  launch_mean_mid(c.buf("a_layer4"), c.buf("a_feat"), B, s.F4, TA * 256, TA * 256, st);  // mean over F' -> (B,TA,256)
+  // ---- projection (fusion_module.py:108-124)
+  linear(c, "projection.visual_proj", c.buf("v_feat"), 256, B * T, c.buf("v_emb"), 256, ACT_NONE);
+  linear(c, "projection.audio_proj", c.buf("a_feat"), 256, B * TA, c.buf("a_emb"), 256, ACT_NONE);
+  // ---- cross-modal attention + gated fusion (fusion_module.py:54-87)
+  const float* a_int = c.buf("a_emb");
+  if (TA != T) { launch_lerp_tokens(c.buf("a_emb"), c.buf("a_int"), B, TA, T, 256, st); a_int = c.buf("a_int"); }
+  float *pv = c.buf("proj_v"), *pa = c.buf("proj_a"), *gi = c.buf("gate_in");
+  linear(c, "cross.in_v", c.buf("v_emb"), 256, B * T, pv, 768, ACT_NONE);
+  linear(c, "cross.in_a", a_int, 256, B * T, pa, 768, ACT_NONE);
+  launch_mha_core(pv, 768, pa + 256, 768, pa + 512, 768, c.buf("att1"), 256, B, T, T, 8, st);  // v2a: Q=v, K/V=a
+  launch_mha_core(pa, 768, pv + 256, 768, pv + 512, 768, c.buf("att2"), 256, B, T, T, 8, st);  // a2v: Q=a, K/V=v
+  linear(c, "cross.v2a.out", c.buf("att1"), 256, B * T, gi, 512, ACT_NONE, c.buf("v_emb"), 256);       // v_out -> gate_in[:, :256]
+  linear(c, "cross.a2v.out", c.buf("att2"), 256, B * T, gi + 256, 512, ACT_NONE, a_int, 256);          // a_out -> gate_in[:, 256:]
+  linear(c, "cross.gate0", gi, 512, B * T, c.buf("gate_h"), 256, ACT_GELU);
+  launch_gate_blend(c.buf("gate_h"), h->warena + h->vecs.at("cross.gate2.w"), h->warena + h->vecs.at("cross.gate2.b"), gi, 512,
+                    gi + 256, 512, c.buf("blend"), B * T, 256, st);
+  linear(c, "cross.fuse", c.buf("blend"), 256, B * T, c.buf("fused"), 256, ACT_RELU);
+  // ---- temporal transformer (temporal.py:79-111)
+  const float* fused = c.buf("fused");
+  for (int k : {3, 5, 7}) {
+    const std::string key = "temporal.branch_k" + std::to_string(k);
+    conv(c, key.c_str(), fused, 256, B, 1, 1, T, 1, 1, 1, 0, 0, k / 2, c.buf("ms_cat") + (k / 2 - 1) * 256, 768, ACT_GELU);
+  }
+  const int NT = T + 1;
+  float* tok = c.buf("tok");
+  launch_set_cls(h->warena + h->vecs.at("temporal.cls"), tok, B, NT, 256, st);
+  // pre_scale_proj + residual, written straight into token rows 1..T of each window
+  linear(c, "temporal.pre_scale_proj", c.buf("ms_cat"), 768, B * T, tok, 256, ACT_NONE, fused, 256, T, NT, 1);
+  for (int l = 0; l < 4; ++l) {
+    const std::string k = "t" + std::to_string(l);
+    launch_layernorm(tok, 256, h->warena + h->vecs.at(k + ".ln1.w"), h->warena + h->vecs.at(k + ".ln1.b"), c.buf("tok_ln"), 256, B * NT, 256, st);
+    linear(c, (k + ".in").c_str(), c.buf("tok_ln"), 256, B * NT, c.buf("tok_qkv"), 768, ACT_NONE);
+    const float* qkv = c.buf("tok_qkv");
+    launch_mha_core(qkv, 768, qkv + 256, 768, qkv + 512, 768, c.buf("tok_att"), 256, B, NT, NT, 8, st);
+    linear(c, (k + ".out").c_str(), c.buf("tok_att"), 256, B * NT, tok, 256, ACT_NONE, tok, 256);
+    launch_layernorm(tok, 256, h->warena + h->vecs.at(k + ".ln2.w"), h->warena + h->vecs.at(k + ".ln2.b"), c.buf("tok_ln"), 256, B * NT, 256, st);
+    linear(c, (k + ".ff1").c_str(), c.buf("tok_ln"), 256, B * NT, c.buf("tok_ff"), 1024, ACT_GELU);
+    linear(c, (k + ".ff2").c_str(), c.buf("tok_ff"), 1024, B * NT, tok, 256, ACT_NONE, tok, 256);
+    if (l == 0) launch_copy_rows(tok, 256, c.buf("t_layer0"), 256, B * NT, 256, st);
+    if (l == 3) launch_copy_rows(tok, 256, c.buf("t_layer3"), 256, B * NT, 256, st);
+  }
+  // cls = tok[:,0]: no final norm (temporal.py:110-111)
+  float *comb = c.buf("comb"), *feat = c.buf("feat");
+  launch_copy_rows(tok, (int64_t)NT * 256, comb, 448, B, 256, st);
+  launch_copy_rows(tok, (int64_t)NT * 256, feat, 384, B, 256, st);
+  // ---- artifact detector (artifact_detector.py:149-183)
+  conv(c, "art.td0", vmap, 256, B, T, s.H4, s.W4, 1, 1, 1, 1, 1, 1, c.buf("art_a"), 128, ACT_RELU);
+  conv(c, "art.td3", c.buf("art_a"), 128, B, T, s.H4, s.W4, 1, 1, 1, 1, 1, 1, c.buf("art_b"), 64, ACT_RELU);
+  launch_mean_mid(c.buf("art_b"), comb + 256, B, T * s.H4 * s.W4, 64, 448, st);
+  if (T > 1) launch_delta_t(vmap, c.buf("art_delta"), B, T, (int64_t)s.H4 * s.W4 * 256, st);
+  else launch_fill_zero(c.buf("art_delta"), (int64_t)B * s.H4 * s.W4 * 256, st);  // zeros_like (artifact_detector.py:168-171)
+  conv(c, "art.td0", c.buf("art_delta"), 256, B, s.Td, s.H4, s.W4, 1, 1, 1, 1, 1, 1, c.buf("art_a"), 128, ACT_RELU);
+  conv(c, "art.td3", c.buf("art_a"), 128, B, s.Td, s.H4, s.W4, 1, 1, 1, 1, 1, 1, c.buf("art_b"), 64, ACT_RELU);
+  launch_mean_mid(c.buf("art_b"), comb + 320, B, s.Td * s.H4 * s.W4, 64, 448, st);
+  conv(c, "art.lap", vid, 3, B * T, 1, s.H, s.W, 1, 1, 1, 0, 1, 1, c.buf("hf_lap"), 3, ACT_NONE);   // per-frame 3->3 (parameter)
+  conv(c, "art.hf0", c.buf("hf_lap"), 3, B, T, s.H, s.W, 1, 2, 2, 1, 1, 1, c.buf("hf_front"), 32, ACT_RELU);
+  conv(c, "art.hf3", c.buf("hf_front"), 32, B, T, s.Hh, s.Wh, 1, 2, 2, 1, 1, 1, c.buf("hf_back"), 64, ACT_RELU);
+  launch_mean_mid(c.buf("hf_back"), comb + 384, B, T * s.Hg * s.Wg, 64, 448, st);
+  linear(c, "art.fuse0", comb, 448, B, c.buf("art_h"), 256, ACT_RELU);
+  linear(c, "art.fuse2", c.buf("art_h"), 256, B, feat + 256, 384, ACT_RELU);
+  // ---- head (classifier.py:22-34)
+  linear(c, "head.fc0", feat, 384, B, c.buf("head_h"), 128, ACT_GELU);
+  launch_ln_dot(c.buf("head_h"), h->warena + h->vecs.at("head.ln.w"), h->warena + h->vecs.at("head.ln.b"),
+                h->warena + h->vecs.at("head.out.w"), h->warena + h->vecs.at("head.out.b"), logits, B, 128, st);
+  if (aux) {
+    const size_t tb = (size_t)B * T * 256 * sizeof(float);
+    if (aux->visual_tokens) cudaMemcpyAsync(aux->visual_tokens, c.buf("v_emb"), tb, cudaMemcpyDeviceToDevice, st);
+    if (aux->audio_tokens) cudaMemcpyAsync(aux->audio_tokens, c.buf("a_emb"), (size_t)B * TA * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (aux->fused_tokens) cudaMemcpyAsync(aux->fused_tokens, c.buf("fused"), tb, cudaMemcpyDeviceToDevice, st);
+    if (aux->cls_output) launch_copy_rows(tok, (int64_t)NT * 256, aux->cls_output, 256, B, 256, st);
+  }
+  return 0;
+}
+
+int check_dtype(lsd_handle* h, int dt, const char* what) {
+  if (dt < LSD_F32 || dt > LSD_U8) return lsd_fail(h, LSD_ERR_ARG, "%s: unsupported dtype %d", what, dt);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int lsd_audio_tokens(int Ta) {
+  if (Ta < 1) return 0;
+  return osz(osz(osz(Ta, 7, 2, 3), 3, 2, 1), 3, 2, 1);
+}
+
+extern "C" size_t lsd_workspace_bytes(lsd_handle* h, int B, int T, int H, int W, int F, int Ta, int precision) {
+  Shapes s;
+  if (make_shapes(h, B, T, H, W, F, Ta, s) != 0) return 0;
+  Plan p;
+  if (precision == LSD_PREC_BF16) make_plan_bf16(h, s.B, s.T, s.H, s.W, s.F, s.Ta, p.stages, p.cursor);
+  else make_plan_f32(s, p);
+  return p.cursor + 256;
+}
+
+extern "C" int lsd_forward(lsd_handle* h, const void* video, int video_dtype, int video_layout, const void* audio, int audio_dtype,
+                           int B, int T, int H, int W, int F, int Ta, int precision, float* logits_out, const lsd_aux* aux,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return LSD_ERR_ARG;
+  if (!h->loaded) return lsd_fail(h, LSD_ERR_WEIGHTS, "lsd_forward: no weights loaded (call lsd_load_weights first)");
+  Shapes s;
+  int rc = make_shapes(h, B, T, H, W, F, Ta, s);
+  if (rc) return rc;
+  if (B == 0) return LSD_OK;
+  if (!video || !audio || !logits_out || !workspace) return lsd_fail(h, LSD_ERR_ARG, "lsd_forward: null pointer argument");
+  if ((rc = check_dtype(h, video_dtype, "video")) || (rc = check_dtype(h, audio_dtype, "audio"))) return rc;
+  if (audio_dtype == LSD_U8) return lsd_fail(h, LSD_ERR_ARG, "audio: uint8 log-mel is not supported");
+  if (video_layout != LSD_NCDHW && video_layout != LSD_NDHWC) return lsd_fail(h, LSD_ERR_ARG, "bad video layout %d", video_layout);
+  if (precision != LSD_PREC_FP32 && precision != LSD_PREC_BF16) return lsd_fail(h, LSD_ERR_ARG, "bad precision %d", precision);
+  CUDA_OK(h, cudaSetDevice(h->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (precision == LSD_PREC_BF16) {
+    rc = forward_bf16(h, B, T, H, W, F, Ta, video, video_dtype, video_layout, audio, audio_dtype, logits_out, aux,
+                      reinterpret_cast<char*>(workspace), workspace_bytes, st, false);
+    if (rc) return rc;
+  } else {
+    Plan p;
+    make_plan_f32(s, p);
+    if (p.cursor > workspace_bytes) return lsd_fail(h, LSD_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", p.cursor, workspace_bytes);
+    h->stages = p.stages;
+    rc = forward_f32(h, s, p, reinterpret_cast<char*>(workspace), aux, logits_out, st, false, video, video_dtype, video_layout, audio, audio_dtype);
+    if (rc) return rc;
+  }
+  CUDA_OK(h, cudaGetLastError());
+  return LSD_OK;
+}
+
+// ================================================================================================
+// Window builder + batched scoring (replaces the serial loop of Predictor._run_chunked_inference)
+// ================================================================================================
+extern "C" size_t lsd_score_workspace_bytes(lsd_handle* h, int batch, int T, int H, int W, int F, int Ta, int precision) {
+  const size_t fw = lsd_workspace_bytes(h, batch, T, H, W, F, Ta, precision);
+  if (fw == 0) return 0;
+  return fw + 2 * (((size_t)batch * sizeof(int32_t) + 255) & ~size_t(255)) + 256;
+}
+
+extern "C" int lsd_score_windows(lsd_handle* h, const uint8_t* track, int n_frames, int H, int W, const int32_t* starts_host,
+                                 int n_windows, int T, const float* mel_full, int F, int Ta_full, int total_v_frames, int Ta,
+                                 int precision, int batch, float* logits_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return LSD_ERR_ARG;
+  if (!h->loaded) return lsd_fail(h, LSD_ERR_WEIGHTS, "lsd_score_windows: no weights loaded");
+  if (n_windows == 0) return LSD_OK;
+  if (!track || !starts_host || !mel_full || !logits_out || !workspace) return lsd_fail(h, LSD_ERR_ARG, "lsd_score_windows: null pointer argument");
+  if (batch < 1 || n_windows < 0 || n_frames < 1 || Ta_full < 1) return lsd_fail(h, LSD_ERR_SHAPE, "lsd_score_windows: bad extents");
+  if (precision != LSD_PREC_FP32 && precision != LSD_PREC_BF16) return lsd_fail(h, LSD_ERR_ARG, "bad precision %d", precision);
+  Shapes s;
+  int rc = make_shapes(h, batch, T, H, W, F, Ta, s);
+  if (rc) return rc;
+  for (int i = 0; i < n_windows; ++i)
+    if (starts_host[i] < 0 || starts_host[i] + T > n_frames)
+      return lsd_fail(h, LSD_ERR_SHAPE, "window %d [%d,%d) is outside the %d-frame track", i, starts_host[i], starts_host[i] + T, n_frames);
+  CUDA_OK(h, cudaSetDevice(h->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t need = lsd_score_workspace_bytes(h, batch, T, H, W, F, Ta, precision);
+  if (need > workspace_bytes) return lsd_fail(h, LSD_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+  const size_t idx_bytes = ((size_t)batch * sizeof(int32_t) + 255) & ~size_t(255);
+  char* ws = reinterpret_cast<char*>(workspace);
+  int32_t* d_vs = reinterpret_cast<int32_t*>(ws);
+  int32_t* d_as = reinterpret_cast<int32_t*>(ws + idx_bytes);
+  char* fws = ws + 2 * idx_bytes;
+  // all window/audio starts are staged once (pinned-free small copies are ordered on the stream)
+  h->idx_host.resize((size_t)2 * n_windows);
+  const double a_ratio = (double)Ta_full / (double)(total_v_frames > 1 ? total_v_frames : 1);
+  for (int i = 0; i < n_windows; ++i) {
+    // predictor.py:540-547: a_start = int(round(v_start * a_ratio)) (round-half-even), clamped so the chunk ends inside the clip
+    long a_start = (long)nearbyint((double)starts_host[i] * a_ratio);
+    if (a_start + Ta > Ta_full) { a_start = Ta_full - Ta; if (a_start < 0) a_start = 0; }
+    h->idx_host[i] = starts_host[i];
+    h->idx_host[n_windows + i] = (int32_t)a_start;
+  }
+  for (int w0 = 0; w0 < n_windows; w0 += batch) {
+    const int nb = (n_windows - w0) < batch ? (n_windows - w0) : batch;
+    CUDA_OK(h, cudaMemcpyAsync(d_vs, &h->idx_host[w0], nb * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CUDA_OK(h, cudaMemcpyAsync(d_as, &h->idx_host[n_windows + w0], nb * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (precision == LSD_PREC_BF16) {
+      rc = score_batch_bf16(h, track, n_frames, d_vs, d_as, mel_full, Ta_full, nb, T, H, W, F, Ta, logits_out + w0, fws,
+                            workspace_bytes - 2 * idx_bytes, st);
+      if (rc) return rc;
+    } else {
+      Shapes sb;
+      make_shapes(h, nb, T, H, W, F, Ta, sb);
+      Plan pb;
+      make_plan_f32(sb, pb);
+      h->stages = pb.stages;
+      Ctx c{h, fws, &pb, st};
+      launch_gather_windows_u8(track, n_frames, d_vs, c.buf("vid"), nb, T, H * W * 3, st);
+      launch_gather_audio(mel_full, F, Ta_full, d_as, c.buf("aud"), nb, Ta, st);
+      rc = forward_f32(h, sb, pb, fws, nullptr, logits_out + w0, st, true, nullptr, 0, 0, nullptr, 0);
+      if (rc) return rc;
+    }
+  }
+  CUDA_OK(h, cudaGetLastError());
+  return LSD_OK;
+}
+
+// ================================================================================================
+// Introspection
+// ================================================================================================
+extern "C" int lsd_stage_count(lsd_handle* h) { return h ? (int)h->stages.size() : 0; }
+extern "C" const char* lsd_stage_name(lsd_handle* h, int i) {
+  if (!h || i < 0 || i >= (int)h->stages.size()) return nullptr;
+  return h->stages[i].name.c_str();
+}
+extern "C" int lsd_stage_info(lsd_handle* h, const char* name, size_t* offset_bytes, int64_t* numel, int* dtype) {
+  if (!h || !name) return LSD_ERR_ARG;
+  for (const Stage& s : h->stages)
+    if (s.name == name) {
+      if (offset_bytes) *offset_bytes = s.offset;
+      if (numel) *numel = s.numel;
+      if (dtype) *dtype = s.dtype;
+      return LSD_OK;
+    }
+  return lsd_fail(h, LSD_ERR_ARG, "unknown stage %s", name);
+}

@@ -1,0 +1,56 @@
+// Internal host-side state shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+struct ConvP {            // one folded conv / linear in the fp32 device arena (offsets in floats)
+  size_t w_off = 0, scale_off = 0, shift_off = 0;
+  bool has_scale = false;
+  int Cin = 0, Cout = 0, kt = 1, kh = 1, kw = 1;
+};
+
+struct Stage {            // named intermediate of the last forward (byte offset into the caller's workspace)
+  std::string name;
+  size_t offset = 0;
+  int64_t numel = 0;
+  int dtype = 0;
+};
+
+struct Bf16Conv;          // packed UMMA operand description (bf16_path.cu)
+
+struct lsd_handle {
+  int device = 0;
+  int num_sms = 148;
+  std::string err;
+  bool loaded = false;
+  float* warena = nullptr;                 // fp32 packed weights
+  void* barena = nullptr;                  // bf16 UMMA-packed weights
+  std::map<std::string, ConvP> convs;
+  std::map<std::string, size_t> vecs;      // small fp32 vectors (offsets into warena)
+  std::map<std::string, size_t> bconvs;    // byte offsets into barena
+  std::vector<Stage> stages;
+  std::vector<int32_t> idx_host;
+  int64_t launches0 = 0;
+  // log-mel tables (device): hann[400], cos[400], sin[400], melw[80*32], lo[80], cnt[80]
+  void* mel_tables = nullptr;
+  const float *d_hann = nullptr, *d_cos = nullptr, *d_sin = nullptr, *d_melw = nullptr;
+  const int *d_mel_lo = nullptr, *d_mel_cnt = nullptr;
+};
+
+int lsd_fail(lsd_handle* h, int code, const char* fmt, ...);
+int init_logmel_tables(lsd_handle* h);
+
+// bf16 tensor-core path (bf16_path.cu)
+int pack_bf16_weights(lsd_handle* h, const std::vector<float>& f32_arena);
+void make_plan_bf16(lsd_handle* h, int B, int T, int H, int W, int F, int Ta, std::vector<Stage>& stages, size_t& bytes);
+#include "../../include/lsd_b200.h"
+int forward_bf16(lsd_handle* h, int B, int T, int H, int W, int F, int Ta, const void* video, int vdt, int vlayout,
+                 const void* audio, int adt, float* logits, const lsd_aux* aux, char* ws, size_t ws_bytes,
+                 cudaStream_t st, bool inputs_ready);
+int score_batch_bf16(lsd_handle* h, const uint8_t* track, int n_frames, const int32_t* d_vstarts, const int32_t* d_astarts,
+                     const float* mel_full, int Ta_full, int nb, int T, int H, int W, int F, int Ta, float* logits,
+                     char* ws, size_t ws_bytes, cudaStream_t st);

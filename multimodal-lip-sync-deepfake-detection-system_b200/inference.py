@@ -1,0 +1,268 @@
+"""Window-scoring API: the scoring/aggregation subset of the reference `Predictor`
+(app/inference/predictor.py), re-hosted on the batched B200 forward.
+
+Mirrors, with the reference's names, argument meaning and return values:
+  `_infer_confidence`              predictor.py:212-244   (+ batched `_infer_confidences`)
+  `_robust_confidence`             predictor.py:246-260
+  `_speech_weighted_confidence`    predictor.py:262-293
+  `_temporal_smoothed_confidence`  predictor.py:295-331
+  `_align_audio_chunk`             predictor.py:525-552
+  `_run_chunked_inference`         predictor.py:554-580   (serial B=1 loop -> batches of `batch_size` windows)
+New: `score_track` (uint8 track -> device-built windows, C `lsd_score_windows`) and
+`score_windows_sharded` (contiguous block partition over ranks + one all-gather of fp32 logits).
+Video decode, face tracking, VAD and the gate/verdict block of `_predict_long_video` stay reference Python.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .model import LipSyncModel
+
+
+def partition_windows(n_windows: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous block partition of [0, n_windows): rank r owns [lo, hi) with ceil(n/R) windows per rank
+    (contiguous so each rank reads one contiguous span of the track)."""
+    per = -(-n_windows // world_size) if world_size > 0 else n_windows
+    lo = min(n_windows, rank * per)
+    hi = min(n_windows, lo + per)
+    return lo, hi
+
+
+def gather_logits(local: torch.Tensor, n_windows: int, world_size: int, rank: int) -> torch.Tensor:
+    """All-gather per-rank fp32 logits (padded to ceil(n/R)) and strip the padding: the only collective on the path."""
+    import torch.distributed as dist
+
+    per = -(-n_windows // world_size)
+    buf = torch.zeros(per, dtype=torch.float32, device=local.device)
+    buf[: local.numel()] = local.to(torch.float32)
+    if world_size == 1:
+        return buf[:n_windows]
+    out = torch.empty(world_size * per, dtype=torch.float32, device=local.device)
+    if local.is_cuda:
+        dist.all_gather_into_tensor(out, buf)  # NCCL over NVLink: <= 4 B per window
+    else:
+        dist.all_gather(list(out.view(world_size, per).unbind(0)), buf)  # gloo (CPU tests of the host logic)
+    return out[:n_windows]
+
+
+class Predictor:
+    """Scoring half of the reference Predictor.  `model` is a `lipsync_b200.LipSyncModel` already on a CUDA device."""
+
+    def __init__(
+        self,
+        model: LipSyncModel,
+        device: Optional[torch.device] = None,
+        use_half_precision: bool = False,
+        confidence_smoothing: str = "median",
+        trim_ratio: float = 0.1,
+        calibration_method: str = "none",
+        calibration_temperature: float = 1.0,
+        calibration_platt_a: float = 1.0,
+        calibration_platt_b: float = 0.0,
+        isotonic_calibrator=None,
+        chunk_size: int = 32,
+        chunk_stride: int = 8,
+        batch_size: int = 64,
+    ) -> None:
+        self.model = model
+        self.device = device if device is not None else (model._device() if model is not None else torch.device("cpu"))
+        self.use_half_precision = bool(use_half_precision and self.device.type == "cuda")
+        allowed = {"none", "median", "trimmed_mean"}
+        self.confidence_smoothing = confidence_smoothing if confidence_smoothing in allowed else "median"
+        self.trim_ratio = float(min(max(trim_ratio, 0.0), 0.49))
+        _cal_allowed = {"none", "temperature", "platt", "isotonic"}
+        self._cal_method = calibration_method if calibration_method in _cal_allowed else "none"
+        self._cal_temperature = float(max(1e-3, calibration_temperature))
+        self._cal_platt_a = float(calibration_platt_a)
+        self._cal_platt_b = float(calibration_platt_b)
+        self._isotonic_cal = isotonic_calibrator
+        if self._cal_method == "isotonic" and self._isotonic_cal is None:
+            self._cal_method = "none"
+        self.chunk_size = int(chunk_size)
+        self.chunk_stride = int(chunk_stride)
+        self.batch_size = int(max(1, batch_size))
+
+    # ------------------------------------------------------------------ calibration (predictor.py:226-244)
+    def _calibrate(self, logit_val: float) -> float:
+        if self._cal_method == "temperature":
+            return float(torch.sigmoid(torch.tensor(logit_val / self._cal_temperature)).item())
+        if self._cal_method == "platt":
+            return float(torch.sigmoid(torch.tensor(self._cal_platt_a * logit_val + self._cal_platt_b)).item())
+        raw_prob = float(torch.sigmoid(torch.tensor(logit_val, dtype=torch.float32)).item())
+        if self._cal_method == "isotonic" and self._isotonic_cal is not None:
+            cal_prob = float(self._isotonic_cal.predict([[raw_prob]])[0])
+            return float(np.clip(cal_prob, 0.0, 1.0))
+        return raw_prob
+
+    # ------------------------------------------------------------------ scoring
+    def _infer_logits(self, visuals: Sequence[np.ndarray], audios: Sequence[np.ndarray]) -> List[float]:
+        """Batched forward over host windows of one common shape, `batch_size` windows per launch."""
+        out: List[float] = []
+        n = len(visuals)
+        for i0 in range(0, n, self.batch_size):
+            v = torch.from_numpy(np.stack(visuals[i0:i0 + self.batch_size]))
+            a = torch.from_numpy(np.stack(audios[i0:i0 + self.batch_size]))
+            if self.use_half_precision:
+                v, a = v.half(), a.half()
+            v = v.to(self.device, non_blocking=True)
+            a = a.to(self.device, non_blocking=True)
+            logits = self.model(v, a)
+            out.extend(float(x) for x in logits.float().cpu().tolist())
+        return out
+
+    def _infer_confidences(self, visuals: Sequence[np.ndarray], audios: Sequence[np.ndarray]) -> List[float]:
+        return [self._calibrate(l) for l in self._infer_logits(visuals, audios)]
+
+    def _infer_confidence(self, visual_np: np.ndarray, audio_np: np.ndarray) -> float:
+        """Run a single forward pass, apply output calibration, return P(REAL)."""
+        return self._infer_confidences([visual_np], [audio_np])[0]
+
+    # ------------------------------------------------------------------ aggregation helpers (host numpy, as the reference)
+    def _robust_confidence(self, confidences: List[float]) -> float:
+        if not confidences:
+            return 0.5
+        arr = np.asarray(confidences, dtype=np.float32)
+        if self.confidence_smoothing == "none":
+            return float(arr.mean())
+        if self.confidence_smoothing == "median":
+            return float(np.median(arr))
+        n = int(arr.size)
+        k = int(n * self.trim_ratio)
+        if k <= 0 or (2 * k) >= n:
+            return float(arr.mean())
+        arr_sorted = np.sort(arr)
+        return float(arr_sorted[k: n - k].mean())
+
+    def _speech_weighted_confidence(self, confidences: List[float], speaking_scores: List[float],
+                                    vad_weights: Optional[List[float]] = None) -> float:
+        if not confidences:
+            return 0.5
+        if len(confidences) != len(speaking_scores):
+            return self._robust_confidence(confidences)
+        conf = np.asarray(confidences, dtype=np.float32)
+        speech = np.clip(np.asarray(speaking_scores, dtype=np.float32), 0.0, 1.0)
+        if vad_weights is not None and len(vad_weights) == len(confidences):
+            vad_arr = np.clip(np.asarray(vad_weights, dtype=np.float32), 0.0, 1.0)
+            combined_speech = 0.7 * vad_arr + 0.3 * speech
+        else:
+            combined_speech = speech
+        weights = np.clip(0.2 + 0.8 * combined_speech, 0.2, 1.0)
+        denom = float(weights.sum())
+        if denom <= 1e-8:
+            return self._robust_confidence(confidences)
+        return float(np.dot(conf, weights) / denom)
+
+    @staticmethod
+    def _smoothing_windows(t_v: int, t_a: int) -> Tuple[List[Tuple[int, int, int, int]], List[Tuple[int, int]]]:
+        """Window spans of `_temporal_smoothed_confidence` (predictor.py:302-325): (v0, v1, a0, a1) + reported spans."""
+        wins = [(0, t_v, 0, t_a)]
+        spans = [(0, max(1, t_v))]
+        win_v = max(12, t_v // 2)
+        win_a = max(48, t_a // 2)
+        if t_v >= win_v and t_a >= win_a:
+            v_starts = [0, max(0, (t_v - win_v) // 2), max(0, t_v - win_v)]
+            for v_start in v_starts:
+                v_end = min(t_v, v_start + win_v)
+                a_start = int(round(v_start * (t_a / max(1, t_v))))
+                a_end = min(t_a, a_start + win_a)
+                if (v_end - v_start) >= 16 and (a_end - a_start) >= 64:
+                    wins.append((v_start, v_end, a_start, a_end))
+                    spans.append((v_start, v_end))
+        return wins, spans
+
+    def _temporal_smoothed_confidence(self, visual_np: np.ndarray, audio_np: np.ndarray):
+        t_v = int(visual_np.shape[1])
+        t_a = int(audio_np.shape[2])
+        wins, spans = self._smoothing_windows(t_v, t_a)
+        confidences: List[float] = []
+        # full window and the half windows have different shapes: one batch per distinct shape, order preserved
+        by_shape = {}
+        for i, (v0, v1, a0, a1) in enumerate(wins):
+            by_shape.setdefault((v1 - v0, a1 - a0), []).append(i)
+        res = [0.0] * len(wins)
+        for idxs in by_shape.values():
+            vs = [np.ascontiguousarray(visual_np[:, wins[i][0]:wins[i][1]]) for i in idxs]
+            as_ = [np.ascontiguousarray(audio_np[:, :, wins[i][2]:wins[i][3]]) for i in idxs]
+            for i, c in zip(idxs, self._infer_confidences(vs, as_)):
+                res[i] = c
+        confidences = res
+        return self._robust_confidence(confidences), confidences, spans
+
+    @staticmethod
+    def _audio_start(v_start: int, total_a: int, total_v_frames: int, chunk_a_size: int = 128) -> int:
+        a_ratio = total_a / max(1, total_v_frames)
+        a_start = int(round(v_start * a_ratio))
+        if a_start + chunk_a_size > total_a:
+            a_start = max(0, total_a - chunk_a_size)
+        return a_start
+
+    def _align_audio_chunk(self, audio_np_full: np.ndarray, v_start: int, total_v_frames: int, chunk_a_size: int = 128) -> np.ndarray:
+        total_a = int(audio_np_full.shape[2])
+        a_start = self._audio_start(v_start, total_a, total_v_frames, chunk_a_size)
+        a_end = min(total_a, a_start + chunk_a_size)
+        chunk = audio_np_full[:, :, a_start:a_end]
+        if chunk.shape[2] < chunk_a_size:
+            pad = np.repeat(chunk[:, :, -1:], chunk_a_size - chunk.shape[2], axis=2)
+            chunk = np.concatenate([chunk, pad], axis=2)
+        return chunk
+
+    def _run_chunked_inference(self, chunks: List[np.ndarray], chunk_starts: List[int], audio_np_full: np.ndarray,
+                               total_v_frames: int) -> Tuple[float, List[float]]:
+        """Score every chunk of a track (batched) and aggregate; returns (aggregated_confidence, per_chunk_confidences)."""
+        audios = [self._align_audio_chunk(audio_np_full, v_start, total_v_frames) for v_start in chunk_starts]
+        chunk_confs = self._infer_confidences(list(chunks), audios) if len(chunks) else []
+        return self._robust_confidence(chunk_confs), chunk_confs
+
+    # ------------------------------------------------------------------ device-side window builder
+    def score_track_logits(self, track_u8: torch.Tensor, starts: Sequence[int], mel_full: torch.Tensor, total_v_frames: int,
+                           chunk_a_size: int = 128) -> torch.Tensor:
+        """uint8 track `(n_frames,H,W,3)` + window start frames + clip log-mel `(1,F,Ta_full)` (both on the device)
+        -> fp32 logits `(n_windows,)` on the device.  Windows are built on the GPU (`/255`, audio alignment)."""
+        m = self.model
+        dev = m._device()
+        if track_u8.dtype != torch.uint8 or track_u8.dim() != 4 or track_u8.shape[3] != 3:
+            raise ValueError(f"track must be uint8 (n_frames, H, W, 3), got {track_u8.dtype} {tuple(track_u8.shape)}")
+        if mel_full.dim() != 3 or mel_full.shape[0] != 1:
+            raise ValueError(f"mel_full must be (1, F, T_full), got {tuple(mel_full.shape)}")
+        n = len(starts)
+        logits = torch.empty(n, dtype=torch.float32, device=dev)
+        if n == 0:
+            return logits
+        track_u8 = track_u8.contiguous()
+        mel_full = mel_full.to(torch.float32).contiguous()
+        n_frames, H, W = int(track_u8.shape[0]), int(track_u8.shape[1]), int(track_u8.shape[2])
+        F_, Ta_full = int(mel_full.shape[1]), int(mel_full.shape[2])
+        with m._lsd_lock:
+            h = m._ensure_handle(dev)
+            L = _cabi.lib()
+            prec = m._precision()
+            batch = min(self.batch_size, n)
+            need = L.lsd_score_workspace_bytes(h.ptr, batch, self.chunk_size, H, W, F_, chunk_a_size, prec)
+            if need == 0:
+                _cabi.check(h.ptr, _cabi.LSD_ERR_SHAPE)
+            ws = m._workspace(need, dev)
+            st = (C.c_int32 * n)(*[int(s) for s in starts])
+            rc = L.lsd_score_windows(h.ptr, track_u8.data_ptr(), n_frames, H, W, st, n, self.chunk_size, mel_full.data_ptr(),
+                                     F_, Ta_full, int(total_v_frames), chunk_a_size, prec, batch, logits.data_ptr(),
+                                     ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream)
+            _cabi.check(h.ptr, rc)
+        return logits
+
+    def score_track(self, track_u8: torch.Tensor, starts: Sequence[int], mel_full: torch.Tensor, total_v_frames: int):
+        logits = self.score_track_logits(track_u8, starts, mel_full, total_v_frames)
+        confs = [self._calibrate(float(x)) for x in logits.cpu().tolist()]
+        return self._robust_confidence(confs), confs
+
+    # ------------------------------------------------------------------ multi-GPU
+    def score_windows_sharded(self, n_windows: int, score_range: Callable[[int, int], torch.Tensor],
+                              world_size: int, rank: int) -> torch.Tensor:
+        """Each rank scores its contiguous block `[lo,hi)` with `score_range(lo, hi) -> logits`, then one
+        all-gather returns all `n_windows` fp32 logits on every rank (rank 0 runs the host aggregation)."""
+        lo, hi = partition_windows(n_windows, world_size, rank)
+        local = score_range(lo, hi) if hi > lo else torch.empty(0, dtype=torch.float32, device=self.device)
+        return gather_logits(local, n_windows, world_size, rank)

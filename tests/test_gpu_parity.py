@@ -1,0 +1,226 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle and the committed reference goldens.
+Run on a B200: python -m pytest tests -m gpu.  Tolerances follow BASELINE.json: fp32 <= 1e-4 relative on logits,
+bf16 <= 2e-2 absolute on logits, decisions (logit >= 0) identical."""
+import numpy as np
+import pytest
+import torch
+
+import lipsync_b200 as lb
+from oracle import lipsync_oracle as orc
+from oracle import logmel_oracle as lmo
+from tests.golden.make_golden import CASES
+from tests.golden.make_logmel_golden import CASES as MEL_CASES, make_pcm
+
+pytestmark = pytest.mark.gpu
+
+FP32_REL = 1e-4   # north_star: fp32 <= 1e-4 relative
+BF16_ABS = 2e-2   # north_star: bf16 <= 2e-2 absolute on logits
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+    g.build()
+
+
+@pytest.fixture(scope="module")
+def model(built, seed0_sd):
+    m = lb.LipSyncModel()
+    m.load_state_dict(seed0_sd, strict=True)
+    return m.to("cuda:0").eval()
+
+
+def _cl(x):  # oracle (B,C,T,H,W) / (B,C,H,W) -> channels-last flat
+    if x.dim() == 5:
+        return x.permute(0, 2, 3, 4, 1).contiguous().reshape(-1)
+    if x.dim() == 4:
+        return x.permute(0, 2, 3, 1).contiguous().reshape(-1)
+    return x.contiguous().reshape(-1)
+
+
+def _rel(a, b):
+    return float((a - b).abs().max()) / max(1e-12, float(b.abs().max()))
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_fp32_logits_match_reference_golden(model, golden, case):
+    wseed, rescale, iseed, b, t, h, w, f, ta = CASES[case]
+    sd = lb.make_synthetic_state_dict(wseed, rescale_head=rescale)
+    model.load_state_dict(sd, strict=True)
+    model.compute_precision = "fp32"
+    video, audio = lb.synthetic_windows(iseed, b, t, h, w, f, ta)
+    out = model(video.cuda(), audio.cuda()).cpu()
+    ref = torch.from_numpy(golden[f"{case}/logits"])
+    assert out.shape == (b,) and out.dtype == torch.float32
+    assert _rel(out, ref) <= FP32_REL, (out, ref)
+    assert ((out >= 0) == (ref >= 0)).all()
+    model.load_state_dict(lb.make_synthetic_state_dict(0), strict=True)
+
+
+def test_fp32_stages_match_oracle(model, seed0_sd):
+    model.compute_precision = "fp32"
+    video, audio = lb.synthetic_windows(1, 2)
+    inter = {}
+    ref = orc.forward(seed0_sd, video, audio, inter=inter)
+    out, aux = model(video.cuda(), audio.cuda(), return_aux=True)
+    assert _rel(out.cpu(), ref) <= FP32_REL
+    for name in ["v_stem", "v_layer1", "v_layer2", "v_layer3", "v_layer4", "a_stem", "a_layer1", "a_layer2", "a_layer3",
+                 "a_layer4", "hf_front", "fused", "v_emb", "a_emb"]:
+        got = model.stage(name).cpu()
+        exp = _cl(inter[name])
+        assert got.numel() == exp.numel(), name
+        assert _rel(got, exp) <= 5e-5, (name, _rel(got, exp))
+    tok = model.stage("t_layer3").cpu().view(2, 33, 256)
+    assert _rel(tok, inter["t_layer3"]) <= 5e-5
+    comb = model.stage("comb").cpu().view(2, 448)
+    for i, key in enumerate(["art_raw", "art_delta", "art_hf"]):
+        assert _rel(comb[:, 256 + 64 * i: 320 + 64 * i], inter[key]) <= 5e-5, key
+    assert _rel(aux["cls_output"].cpu(), inter["cls"]) <= 5e-5
+    assert _rel(aux["visual_tokens"].cpu(), inter["v_emb"]) <= 5e-5
+    assert _rel(aux["audio_tokens"].cpu(), inter["a_emb"]) <= 5e-5
+    assert _rel(aux["fused_tokens"].cpu(), inter["fused"]) <= 5e-5
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_batch_composition_independence_bitwise(model, prec):
+    """Per-window results must not depend on the batch they ride in (sharding invariance)."""
+    model.compute_precision = prec
+    video, audio = lb.synthetic_windows(5, 3)
+    v, a = video.cuda(), audio.cuda()
+    full = model(v, a).cpu()
+    one = model(v[1:2], a[1:2]).cpu()
+    assert full[1].item() == one[0].item()
+    rep = model(v.repeat(7, 1, 1, 1, 1), a.repeat(7, 1, 1, 1)).cpu()  # B = 21
+    assert torch.equal(rep.view(7, 3), full.expand(7, 3))
+
+
+def test_full_batch_64_property(model, golden):
+    """BASELINE config 2 size (B=64): 16 copies of the 4 canonical windows reproduce the reference logits."""
+    ref = torch.from_numpy(golden["canonical/logits"])
+    video, audio = lb.synthetic_windows(1, 4)
+    v = video.cuda().repeat(16, 1, 1, 1, 1)
+    a = audio.cuda().repeat(16, 1, 1, 1)
+    model.compute_precision = "fp32"
+    out = model(v, a).cpu().view(16, 4)
+    assert _rel(out, ref.expand(16, 4)) <= FP32_REL
+    model.compute_precision = "bf16"
+    out = model(v, a).cpu().view(16, 4)
+    assert float((out - ref.expand(16, 4)).abs().max()) <= BF16_ABS
+    assert ((out >= 0) == (ref.expand(16, 4) >= 0)).all()
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_bf16_logits_within_budget(model, golden, case):
+    wseed, rescale, iseed, b, t, h, w, f, ta = CASES[case]
+    model.load_state_dict(lb.make_synthetic_state_dict(wseed, rescale_head=rescale), strict=True)
+    model.compute_precision = "bf16"
+    video, audio = lb.synthetic_windows(iseed, b, t, h, w, f, ta)
+    out = model(video.cuda(), audio.cuda()).cpu()
+    ref = torch.from_numpy(golden[f"{case}/logits"])
+    model.load_state_dict(lb.make_synthetic_state_dict(0), strict=True)
+    assert float((out - ref).abs().max()) <= BF16_ABS, (out, ref)
+    margin = ref.abs() > BF16_ABS  # decisions must agree wherever the reference is not inside the tolerance band
+    assert ((out >= 0) == (ref >= 0))[margin].all()
+
+
+def test_half_module_runs_tensor_core_path(model, golden):
+    """predictor.py:196-197: model.half() + half inputs -> low-precision path, logits returned in the input dtype."""
+    m = lb.LipSyncModel()
+    m.load_state_dict(lb.make_synthetic_state_dict(0), strict=True)
+    m.half().to("cuda:0").eval()
+    video, audio = lb.synthetic_windows(1, 4)
+    out = m(video.cuda().half(), audio.cuda().half())
+    assert out.dtype == torch.float16
+    ref = torch.from_numpy(golden["canonical/logits"])
+    assert float((out.float().cpu() - ref).abs().max()) <= 3e-2  # bf16 budget + fp16 rounding of inputs/weights
+
+
+def test_input_layouts_and_dtypes(model):
+    model.compute_precision = "fp32"
+    g = torch.Generator().manual_seed(11)
+    u8 = torch.randint(0, 256, (2, 32, 96, 96, 3), generator=g, dtype=torch.uint8)
+    _, audio = lb.synthetic_windows(9, 2)
+    f_ncdhw = (u8.to(torch.float32) / 255.0).permute(0, 4, 1, 2, 3).contiguous()
+    a = model(f_ncdhw.cuda(), audio.cuda()).cpu()
+    b = model(u8.cuda(), audio.cuda(), video_layout="NDHWC").cpu()
+    assert torch.equal(a, b)
+    c = model(u8.permute(0, 4, 1, 2, 3).contiguous().cuda(), audio.cuda()).cpu()
+    assert torch.equal(a, c)
+
+
+def test_shape_errors_on_device(model):
+    with pytest.raises(ValueError):
+        model(torch.zeros(1, 3, 4, 8, 8, device="cuda"), torch.zeros(1, 1, 80, 128, device="cuda"))  # too small for the strides
+    with pytest.raises(ValueError):
+        model(torch.zeros(1, 3, 4, 96, 96, device="cuda"), torch.zeros(2, 1, 80, 128, device="cuda"))
+    out = model(torch.zeros(0, 3, 32, 96, 96, device="cuda"), torch.zeros(0, 1, 80, 128, device="cuda"))
+    assert out.shape == (0,)
+
+
+def test_run_chunked_inference_matches_serial_oracle(model, seed0_sd):
+    """The batched replacement of the serial loop (predictor.py:554-580) returns the same per-chunk confidences."""
+    model.compute_precision = "fp32"
+    g = torch.Generator().manual_seed(21)
+    n_frames, stride = 32 + 8 * 5, 8
+    track = torch.rand((3, n_frames, 96, 96), generator=g).numpy().astype(np.float32)
+    starts = list(range(0, n_frames - 32 + 1, stride))
+    chunks = [np.ascontiguousarray(track[:, s:s + 32]) for s in starts]
+    mel_full = (-80.0 * torch.rand((1, 80, 500), generator=g)).numpy().astype(np.float32)
+    p = lb.Predictor(model, batch_size=4)
+    agg, confs = p._run_chunked_inference(chunks, starts, mel_full, n_frames)
+    ref = []
+    for c, s in zip(chunks, starts):
+        a = p._align_audio_chunk(mel_full, s, n_frames)
+        ref.append(float(torch.sigmoid(orc.forward(seed0_sd, torch.from_numpy(c)[None], torch.from_numpy(a)[None])).item()))
+    assert len(confs) == len(starts) == 6
+    assert np.abs(np.asarray(confs) - np.asarray(ref)).max() <= 2e-5
+    assert abs(agg - float(np.median(np.asarray(ref, dtype=np.float32)))) <= 2e-5
+    # variable-T forwards of _temporal_smoothed_confidence (T=16, Ta=64)
+    r, cs, spans = p._temporal_smoothed_confidence(chunks[0], p._align_audio_chunk(mel_full, 0, n_frames))
+    assert spans == [(0, 32), (0, 16), (8, 24), (16, 32)] and len(cs) == 4
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_score_track_device_window_builder(model, prec):
+    """uint8 track -> device-built windows (lsd_score_windows) equals the host-built windows through forward()."""
+    model.compute_precision = prec
+    g = torch.Generator().manual_seed(31)
+    n_frames = 32 + 8 * 9
+    track = torch.randint(0, 256, (n_frames, 96, 96, 3), generator=g, dtype=torch.uint8)
+    mel = -80.0 * torch.rand((1, 80, 650), generator=g)
+    starts = list(range(0, n_frames - 32 + 1, 8))
+    p = lb.Predictor(model, batch_size=4)  # 10 windows -> batches 4,4,2
+    logits = p.score_track_logits(track.cuda(), starts, mel.cuda(), n_frames).cpu()
+    vis = torch.stack([track[s:s + 32] for s in starts]).cuda()
+    aud = torch.stack([torch.from_numpy(p._align_audio_chunk(mel.numpy(), s, n_frames)) for s in starts]).cuda()
+    ref = model(vis, aud, video_layout="NDHWC").cpu()
+    assert torch.equal(logits, ref)
+    with pytest.raises(ValueError):
+        p.score_track_logits(track.cuda(), [n_frames - 8], mel.cuda(), n_frames)
+
+
+@pytest.mark.parametrize("name", list(MEL_CASES))
+def test_logmel_matches_oracle(built, name):
+    y = make_pcm(name)
+    ref = lmo.preprocess_audio_pcm(y)
+    out = lb.preprocess_audio_pcm(y)
+    assert out.shape == ref.shape and out.dtype == np.float32
+    assert out.max() == 0.0 and out.min() >= -80.0
+    assert np.abs(out - ref).max() <= 2e-3  # dB; fp32 direct DFT vs pocketfft rFFT
+    assert lb.preprocess_audio_pcm(y, target_frames=128).shape == (1, 80, 128)
+
+
+def test_logmel_batched_clips_have_their_own_reference(built):
+    ys = [make_pcm("noise_20480"), 0.01 * make_pcm("long_50000"), make_pcm("short_1000")]
+    outs = lb.logmel_db([torch.from_numpy(y).cuda() for y in ys])
+    for y, o in zip(ys, outs):
+        ref = lmo.preprocess_audio_pcm(y)[0]
+        assert np.abs(o.cpu().numpy() - ref).max() <= 2e-3
+
+
+def test_launch_counter_counts(model):
+    model.compute_precision = "fp32"
+    video, audio = lb.synthetic_windows(1, 1)
+    n0 = model.launch_count()
+    model(video.cuda(), audio.cuda())
+    assert model.launch_count() - n0 > 50

@@ -1,0 +1,136 @@
+"""Host-side logic against known answers produced by the real reference (tests/golden/make_golden.py), the log-mel
+oracle against its independent fixture, and the world_size-2 window sharding over gloo.  CPU only."""
+import json
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+import lipsync_b200 as lb
+from oracle import logmel_oracle as lmo
+from tests.conftest import ROOT
+from tests.golden.make_logmel_golden import CASES as MEL_CASES, make_pcm
+
+
+@pytest.fixture(scope="module")
+def scoring():
+    with open(os.path.join(ROOT, "tests", "golden", "scoring_golden.json")) as fh:
+        return json.load(fh)
+
+
+@pytest.fixture()
+def pred():
+    return lb.Predictor(model=None, device=torch.device("cpu"))
+
+
+def test_align_audio_chunk(scoring, pred):
+    assert scoring["align"]
+    for case in scoring["align"]:
+        full = np.arange(case["total_a"], dtype=np.float32)[None, None, :].repeat(2, axis=1)
+        chunk = pred._align_audio_chunk(full, case["v_start"], case["total_v"])
+        assert chunk.shape == (1, 2, 128)
+        assert chunk[0, 0].astype(int).tolist() == case["cols"]
+        # the device gather uses (a_start, clamp-to-last-column): same columns
+        a0 = pred._audio_start(case["v_start"], case["total_a"], case["total_v"])
+        cols = np.minimum(a0 + np.arange(128), case["total_a"] - 1)
+        assert cols.tolist() == case["cols"]
+
+
+def test_robust_confidence(scoring, pred):
+    for case in scoring["robust"]:
+        pred.confidence_smoothing = case["mode"]
+        pred.trim_ratio = 0.1
+        assert pred._robust_confidence(case["confs"]) == case["out"]
+
+
+def test_speech_weighted_confidence(scoring, pred):
+    for case in scoring["weighted"]:
+        assert pred._speech_weighted_confidence(case["confs"], case["speak"], vad_weights=case["vad"]) == case["out"]
+
+
+def test_temporal_smoothing_spans(scoring, pred):
+    for case in scoring["spans"]:
+        wins, spans = pred._smoothing_windows(case["t_v"], case["t_a"])
+        assert [list(s) for s in spans] == case["spans"]
+        assert [[v1 - v0, a1 - a0] for (v0, v1, a0, a1) in wins] == case["shapes"]
+
+
+def test_calibration_matches_reference_formulas():
+    p = lb.Predictor(model=None, device=torch.device("cpu"), calibration_method="temperature", calibration_temperature=2.0)
+    assert p._calibrate(1.0) == float(torch.sigmoid(torch.tensor(0.5)).item())
+    p = lb.Predictor(model=None, device=torch.device("cpu"), calibration_method="platt", calibration_platt_a=1.5, calibration_platt_b=-0.2)
+    assert p._calibrate(0.4) == float(torch.sigmoid(torch.tensor(1.5 * 0.4 - 0.2)).item())
+    p = lb.Predictor(model=None, device=torch.device("cpu"))
+    assert p._calibrate(0.0) == 0.5
+
+
+def test_partition_covers_everything():
+    for n in (0, 1, 7, 10, 64, 10000):
+        for ws in (1, 2, 3, 4, 8):
+            spans = [lb.partition_windows(n, ws, r) for r in range(ws)]
+            got = [i for lo, hi in spans for i in range(lo, hi)]
+            assert got == list(range(n))
+            assert max(hi - lo for lo, hi in spans) <= -(-n // ws) if n else True
+
+
+def test_fit_frames():
+    x = np.arange(2 * 3 * 5, dtype=np.float32).reshape(1, 6, 5)
+    assert lb.fit_frames(x, None) is x
+    assert lb.fit_frames(x, 3).shape == (1, 6, 3)
+    y = lb.fit_frames(x, 8)
+    assert y.shape == (1, 6, 8) and (y[:, :, 5:] == x[:, :, -1:]).all()
+
+
+@pytest.mark.parametrize("name", list(MEL_CASES))
+def test_logmel_oracle_matches_independent_fixture(name):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "logmel_golden.npz"))
+    db = lmo.preprocess_audio_pcm(make_pcm(name))[0]
+    assert db.shape == tuple(g[name + "/shape"])
+    assert db.max() == 0.0 and db.min() >= -80.0
+    assert np.abs(db.reshape(-1)[g[name + "/idx"]] - g[name + "/val"]).max() <= 1e-3  # dB
+
+
+def test_logmel_filterbank_properties():
+    fb = lmo.mel_filterbank()
+    assert fb.shape == (80, 201) and fb.dtype == np.float32
+    assert int((fb != 0).sum()) == 391
+    assert (fb >= 0).all()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _shard_worker(rank, world, port, n, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    p = lb.Predictor(model=None, device=torch.device("cpu"))
+    # stub scorer: logit of window i is a deterministic function of i (the CUDA scorer is tested with -m gpu)
+    out = p.score_windows_sharded(n, lambda lo, hi: torch.arange(lo, hi, dtype=torch.float32) * 0.5 - 3.0, world, rank)
+    q.put((rank, out.tolist()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [10, 7, 1])
+def test_sharded_scoring_gloo_world2(n):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    expect = (np.arange(n, dtype=np.float32) * 0.5 - 3.0).tolist()
+    assert res[0] == expect and res[1] == expect
