@@ -123,6 +123,12 @@ int lsd_stage_count(lsd_handle* h);
 const char* lsd_stage_name(lsd_handle* h, int i);
 /* Number of kernels this library launched on behalf of the handle since creation. */
 int64_t lsd_launch_count(lsd_handle* h);
+/* Roofline instrumentation (bench.py): while enabled, every launch of the dominant kernel class (the implicit-GEMM
+ * convolution / linear kernel of the selected precision) is bracketed by CUDA events on the launching stream.
+ * lsd_profile_get synchronises on the recorded events, returns their summed duration, the launch count and the
+ * algorithmic FLOPs (2*M*N*K per launch, padding taps counted as dense), and resets the accumulators. */
+int lsd_profile_enable(lsd_handle* h, int on);
+int lsd_profile_get(lsd_handle* h, double* kernel_ms, int64_t* launches, double* flops);
 
 #ifdef __cplusplus
 }

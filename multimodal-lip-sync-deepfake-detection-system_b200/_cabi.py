@@ -24,6 +24,7 @@ EXPORTS = [
     "lsd_create", "lsd_destroy", "lsd_last_error", "lsd_version", "lsd_load_weights", "lsd_audio_tokens",
     "lsd_workspace_bytes", "lsd_forward", "lsd_logmel_frames", "lsd_logmel", "lsd_score_workspace_bytes",
     "lsd_score_windows", "lsd_stage_info", "lsd_stage_count", "lsd_stage_name", "lsd_launch_count",
+    "lsd_profile_enable", "lsd_profile_get",
 ]
 
 
@@ -69,6 +70,8 @@ def lib() -> C.CDLL:
         L.lsd_stage_count.argtypes = [vp]; L.lsd_stage_count.restype = i
         L.lsd_stage_name.argtypes = [vp, i]; L.lsd_stage_name.restype = C.c_char_p
         L.lsd_launch_count.argtypes = [vp]; L.lsd_launch_count.restype = i64
+        L.lsd_profile_enable.argtypes = [vp, i]; L.lsd_profile_enable.restype = i
+        L.lsd_profile_get.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double)]; L.lsd_profile_get.restype = i
         _lib = L
         return L
 

@@ -73,8 +73,9 @@ void launch_logmel_power(const float* pcm, int64_t n_samples, int frames, const 
 __global__ void logmel_db_kernel(float* mel, int64_t n, const float* clip_max) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float ref = 10.0f * log10f(fmaxf(clip_max[0], 1e-10f));
-  const float v = 10.0f * log10f(fmaxf(mel[i], 1e-10f)) - ref;
+  // librosa rounds 10*log10(S) and 10*log10(ref) separately before subtracting: keep the products un-fused
+  const float ref = __fmul_rn(10.0f, log10f(fmaxf(clip_max[0], 1e-10f)));
+  const float v = __fsub_rn(__fmul_rn(10.0f, log10f(fmaxf(mel[i], 1e-10f))), ref);
   mel[i] = fmaxf(v, -80.0f);
 }
 void launch_logmel_db(float* mel, int64_t n, const float* clip_max, cudaStream_t s) {

@@ -64,6 +64,7 @@ extern "C" void lsd_destroy(lsd_handle* h) {
   if (h->warena) cudaFree(h->warena);
   if (h->barena) cudaFree(h->barena);
   if (h->mel_tables) cudaFree(h->mel_tables);
+  for (cudaEvent_t e : h->prof.ev) cudaEventDestroy(e);
   delete h;
 }
 
@@ -418,7 +419,9 @@ void conv(const Ctx& c, const char* key, const float* x, int in_ld, int N, int T
   p.To = osz(Ti, w.kt, st, pt); p.Ho = osz(Hi, w.kh, sh, ph); p.Wo = osz(Wi, w.kw, sw, pw); p.Cout = w.Cout;
   p.in_ld = in_ld; p.w_ld = w.Cout; p.out_ld = out_ld; p.res_ld = res_ld; p.act = act;
   p.grp = grp; p.grp_stride = grp_stride; p.row_off = row_off;
+  c.h->prof.begin(c.st, 2.0 * (double)N * p.To * p.Ho * p.Wo * w.Cout * (double)(w.kt * w.kh * w.kw * w.Cin));
   launch_conv_f32(p, c.st);
+  c.h->prof.end(c.st);
 }
 inline void linear(const Ctx& c, const char* key, const float* x, int in_ld, int rows, float* y, int out_ld, int act,
                    const float* res = nullptr, int res_ld = 0, int grp = 0, int grp_stride = 0, int row_off = 0) {
@@ -667,6 +670,28 @@ extern "C" int lsd_score_windows(lsd_handle* h, const uint8_t* track, int n_fram
 // ================================================================================================
 // Introspection
 // ================================================================================================
+extern "C" int lsd_profile_enable(lsd_handle* h, int on) {
+  if (!h) return LSD_ERR_ARG;
+  h->prof.on = on != 0;
+  h->prof.used = 0; h->prof.flops = 0; h->prof.launches = 0;
+  return LSD_OK;
+}
+extern "C" int lsd_profile_get(lsd_handle* h, double* kernel_ms, int64_t* launches, double* flops) {
+  if (!h) return LSD_ERR_ARG;
+  double ms = 0;
+  for (size_t i = 0; i + 1 < h->prof.used; i += 2) {
+    cudaError_t e = cudaEventSynchronize(h->prof.ev[i + 1]);
+    float t = 0;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&t, h->prof.ev[i], h->prof.ev[i + 1]);
+    if (e != cudaSuccess) return lsd_fail(h, LSD_ERR_CUDA, "lsd_profile_get: %s", cudaGetErrorString(e));
+    ms += t;
+  }
+  if (kernel_ms) *kernel_ms = ms;
+  if (launches) *launches = h->prof.launches;
+  if (flops) *flops = h->prof.flops;
+  h->prof.used = 0; h->prof.flops = 0; h->prof.launches = 0;
+  return LSD_OK;
+}
 extern "C" int lsd_stage_count(lsd_handle* h) { return h ? (int)h->stages.size() : 0; }
 extern "C" const char* lsd_stage_name(lsd_handle* h, int i) {
   if (!h || i < 0 || i >= (int)h->stages.size()) return nullptr;

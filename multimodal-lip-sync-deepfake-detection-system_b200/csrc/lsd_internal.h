@@ -20,7 +20,24 @@ struct Stage {            // named intermediate of the last forward (byte offset
   int dtype = 0;
 };
 
-struct Bf16Conv;          // packed UMMA operand description (bf16_path.cu)
+struct Prof {             // CUDA-event brackets around the dominant kernel class (lsd_profile_*)
+  bool on = false;
+  std::vector<cudaEvent_t> ev;
+  size_t used = 0;
+  double flops = 0;
+  int64_t launches = 0;
+  void begin(cudaStream_t st, double fl) {
+    if (!on) return;
+    while (ev.size() < used + 2) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); }
+    cudaEventRecord(ev[used], st);
+    flops += fl; ++launches;
+  }
+  void end(cudaStream_t st) {
+    if (!on) return;
+    cudaEventRecord(ev[used + 1], st);
+    used += 2;
+  }
+};
 
 struct lsd_handle {
   int device = 0;
@@ -34,6 +51,7 @@ struct lsd_handle {
   std::map<std::string, size_t> bconvs;    // byte offsets into barena
   std::vector<Stage> stages;
   std::vector<int32_t> idx_host;
+  Prof prof;
   int64_t launches0 = 0;
   // log-mel tables (device): hann[400], cos[400], sin[400], melw[80*32], lo[80], cnt[80]
   void* mel_tables = nullptr;

@@ -60,7 +60,7 @@ struct Case { const char* name; int N, K; int variant; bool swap; };
 int main() {
   cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   std::vector<Case> cases = {
-      {"canonical N=64 K=64", 64, 64, 1, false},   {"canonical N=64 K=64 LBO/SBO swapped", 64, 64, 1, true},
+      {"canonical N=64 K=64", 64, 64, 1, false},  // (the LBO/SBO-swapped variant faults: measured once, removed)
       {"canonical N=256 K=128", 256, 128, 1, false}, {"halo-view N=64 K=64 (unaligned start, SBO=160)", 64, 64, 2, false},
       {"halo-view N=128 K=64", 128, 64, 2, false},   {"toeplitz N=64 K=32 (LBO=16, overlapping rows)", 64, 32, 3, false},
       {"halo-view stride-2 groups N=64 K=64 (SBO=320)", 64, 64, 4, false},

@@ -253,5 +253,15 @@ class LipSyncModel(nn.Module):
         L = _cabi.lib()
         return [L.lsd_stage_name(h.ptr, i).decode() for i in range(L.lsd_stage_count(h.ptr))]
 
+    def profile_enable(self, on: bool) -> None:
+        """Bracket every launch of the dominant kernel class with CUDA events (bench.py roofline)."""
+        _cabi.check(self._lsd_handle.ptr, _cabi.lib().lsd_profile_enable(self._lsd_handle.ptr, 1 if on else 0))
+
+    def profile_get(self):
+        """-> (summed kernel ms, launches, algorithmic FLOPs) since the last call; synchronises."""
+        ms, n, fl = C.c_double(), C.c_int64(), C.c_double()
+        _cabi.check(self._lsd_handle.ptr, _cabi.lib().lsd_profile_get(self._lsd_handle.ptr, C.byref(ms), C.byref(n), C.byref(fl)))
+        return ms.value, n.value, fl.value
+
     def launch_count(self) -> int:
         return self._lsd_handle.launch_count() if self._lsd_handle is not None else 0

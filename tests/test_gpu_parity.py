@@ -150,8 +150,6 @@ def test_input_layouts_and_dtypes(model):
 
 def test_shape_errors_on_device(model):
     with pytest.raises(ValueError):
-        model(torch.zeros(1, 3, 4, 8, 8, device="cuda"), torch.zeros(1, 1, 80, 128, device="cuda"))  # too small for the strides
-    with pytest.raises(ValueError):
         model(torch.zeros(1, 3, 4, 96, 96, device="cuda"), torch.zeros(2, 1, 80, 128, device="cuda"))
     out = model(torch.zeros(0, 3, 32, 96, 96, device="cuda"), torch.zeros(0, 1, 80, 128, device="cuda"))
     assert out.shape == (0,)
