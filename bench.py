@@ -190,7 +190,7 @@ def main():
         sampler = ClockSampler(local)
         sampler.start()
         if profile:
-            model.profile_enable(True)
+            model.profile_enable(2 if args.precision == 'bf16' else 1)
         n0 = model.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -244,7 +244,8 @@ def main():
                     "api": "LipSyncModel.forward on pinned host fp32 windows (H2D + forward + D2H logits per step)"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
-                         "kernel": "implicit-GEMM conv/linear (all launches of the class, CUDA events on the launch stream)",
+                         "kernel": ("umma_conv_kernel (tcgen05 flat shift-GEMM conv; all launches, CUDA events on the launch stream)"
+                                    if args.precision == "bf16" else "conv_f32_kernel (all launches, CUDA events on the launch stream)"),
                          "kernel_ms_per_step": kern_ms / K, "kernel_launches_per_step": kern_n / K,
                          "kernel_share_of_step": kern_ms / ms,
                          "whole_model_tflops": FLOP_PER_WINDOW * B * K / (ms / 1e3) / 1e12},

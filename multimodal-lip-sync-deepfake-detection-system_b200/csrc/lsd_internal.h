@@ -20,13 +20,20 @@ struct Stage {            // named intermediate of the last forward (byte offset
   int dtype = 0;
 };
 
+struct BTap { int orig, dt, dh, dw; };                       // original tap index + input shift (in the band's plane set)
+struct BBand { int set; std::vector<BTap> taps; };
+struct BGroup { std::vector<BBand> bands; int Cin = 0, taps_total = 0; size_t w_off = 0; };  // w_off: bf16 elements into barena
+struct BLayer { std::vector<BGroup> groups; int Cout = 0; size_t bias_off = 0; };            // bias_off: floats into bbias
+
 struct Prof {             // CUDA-event brackets around the dominant kernel class (lsd_profile_*)
+  int want = 0;           // 0 off, 1 fp32 conv kernel, 2 tcgen05 conv kernel
   bool on = false;
   std::vector<cudaEvent_t> ev;
   size_t used = 0;
   double flops = 0;
   int64_t launches = 0;
-  void begin(cudaStream_t st, double fl) {
+  void begin(cudaStream_t st, double fl, int cls = 1) {
+    on = (want == cls);
     if (!on) return;
     while (ev.size() < used + 2) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); }
     cudaEventRecord(ev[used], st);
@@ -48,7 +55,11 @@ struct lsd_handle {
   void* barena = nullptr;                  // bf16 UMMA-packed weights
   std::map<std::string, ConvP> convs;
   std::map<std::string, size_t> vecs;      // small fp32 vectors (offsets into warena)
-  std::map<std::string, size_t> bconvs;    // byte offsets into barena
+  float* bbias = nullptr;                  // fp32 biases of the bf16 layers
+  std::map<std::string, BLayer> blayers;
+  const void* ws_sig_ptr = nullptr;        // bf16 workspace whose zero padding is initialised (see forward_bf16)
+  size_t ws_sig_bytes = 0;
+  int ws_sig_shape[6] = {0, 0, 0, 0, 0, 0};
   std::vector<Stage> stages;
   std::vector<int32_t> idx_host;
   Prof prof;

@@ -1,0 +1,376 @@
+// tcgen05 "flat shift-GEMM" convolution for sm_100a (bf16 operands, fp32 accumulation in TMEM).
+//
+// Replaces nn.Conv3d / Conv2d / Conv1d / Linear + eval BatchNorm + ReLU/GELU + residual of the reference
+// (app/models/visual_encoder.py:46-87, audio_encoder.py:34-89, artifact_detector.py:74-93,41-43, temporal.py:35-51)
+// on the bf16 path.  See umma_conv.cuh for the padded planar activation layout that turns every tap into a shift.
+//
+// One CTA = MT consecutive 128-position M tiles x all Cout (<= 256) columns; accumulators in TMEM (MT*Cout columns).
+// Pipeline (mbarrier ring, `stages` deep), per (k16 channel chunk, band):
+//   producer thread : 3 bulk async copies (TMA engine, 1-D): the band's two 8-channel planes + the band's packed weights
+//   MMA thread      : ntaps x MT tcgen05.mma (M=128, N=Cout, K=16); the A descriptor of a tap is the band base shifted by the
+//                     tap offset (K-major, SWIZZLE_NONE: rows 16 B apart, SBO = 128 B, LBO = band length * 16 B)
+//   tcgen05.commit releases the stage; the last commit signals the epilogue.
+// Epilogue (all 4 warps): tcgen05.ld -> +bias (+residual) -> act -> zero pads -> bf16 -> 16 B coalesced stores per plane.
+#include "umma_conv.cuh"
+
+#include "lsd_kernels.h"
+#include "umma.cuh"
+
+namespace lsd {
+
+using namespace umma;
+
+__device__ __forceinline__ float uc_act(float v, int act) {
+  if (act == ACT_RELU) return fmaxf(v, 0.0f);
+  if (act == ACT_GELU) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+  return v;
+}
+
+__device__ __forceinline__ bool uc_decode(const UcGeom& g, int64_t P, int& n, int& t, int& h, int& w) {
+  if (P < 0 || P >= g.P_total) return false;
+  const int64_t S = P / g.SL;
+  const int r = (int)(P - S * g.SL);
+  const int row = r / g.RW, col = r - row * g.RW;
+  const int tt = (int)(S % (g.T + 1));
+  n = (int)(S / (g.T + 1));
+  t = tt - 1; h = row - 1; w = col - 1;
+  return tt != 0 && row != 0 && col != 0 && n < g.N;
+}
+
+__global__ void __launch_bounds__(128) umma_conv_kernel(const __grid_constant__ UmmaConvP p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t full_bar[8], empty_bar[8], acc_bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float bias_s[256];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = p.MT * 128;
+  const int64_t P0 = (int64_t)blockIdx.x * S;
+  const uint32_t stage_bytes = p.a_stage_bytes + p.w_stage_bytes;
+
+  if (tid == 0) {
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&acc_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc(&tmem_base_s, p.tmem_cols); tmem_relinquish(); }
+  for (int i = tid; i < p.Cout; i += 128) bias_s[i] = p.bias ? p.bias[i] : 0.0f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------ producer
+    int it = 0;
+    for (int gi = 0; gi < p.ngroups; ++gi) {
+      const UcGroup& g = p.groups[gi];
+      for (int c = 0; c < g.k16; ++c) {
+        for (int b = g.band_begin; b < g.band_end; ++b, ++it) {
+          const UcBand& bd = p.bands[b];
+          const int stage = it % p.stages;
+          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+          mbar_wait(&empty_bar[stage], ph ^ 1u);
+          const uint32_t bytesA = (uint32_t)(S + bd.len_extra) * 16u;
+          const uint32_t bytesW = (uint32_t)bd.ntaps * (uint32_t)p.Cout * 32u;
+          mbar_arrive_expect_tx(&full_bar[stage], 2u * bytesA + bytesW);
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          const __nv_bfloat16* src = bd.base + (int64_t)(2 * c) * bd.plane_stride + (P0 + bd.start) * 8;
+          bulk_g2s(sa, src, bytesA, &full_bar[stage]);
+          bulk_g2s(sa + bytesA, src + bd.plane_stride, bytesA, &full_bar[stage]);
+          const __nv_bfloat16* wsrc = p.w + g.w_off + ((int64_t)c * g.taps_total + bd.tap_begin) * (int64_t)p.Cout * 16;
+          bulk_g2s(sa + p.a_stage_bytes, wsrc, bytesW, &full_bar[stage]);
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------ MMA issuer
+    const uint32_t idesc = idesc_bf16(128, p.Cout);
+    const uint32_t smem_base = smem_u32(smem);
+    int it = 0;
+    for (int gi = 0; gi < p.ngroups; ++gi) {
+      const UcGroup& g = p.groups[gi];
+      for (int c = 0; c < g.k16; ++c) {
+        for (int b = g.band_begin; b < g.band_end; ++b, ++it) {
+          const UcBand& bd = p.bands[b];
+          const int stage = it % p.stages;
+          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+          mbar_wait(&full_bar[stage], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+          const uint32_t sw = sa + p.a_stage_bytes;
+          const uint32_t lboA = (uint32_t)(S + bd.len_extra) * 16u;
+          for (int j = 0; j < bd.ntaps; ++j) {
+            const uint64_t db = smem_desc(sw + (uint32_t)j * (uint32_t)p.Cout * 32u, (uint32_t)p.Cout * 16u, 128u);
+            for (int m = 0; m < p.MT; ++m) {
+              const uint64_t da = smem_desc(sa + (uint32_t)(bd.rel[j] + m * 128) * 16u, lboA, 128u);
+              mma_bf16_ss(tmem_base + (uint32_t)(m * p.Cout), da, db, idesc, (it == 0 && j == 0) ? 0u : 1u);
+            }
+          }
+          mma_commit(&empty_bar[stage]);  // frees the stage once the MMAs that read it have completed
+        }
+      }
+    }
+    mma_commit(&acc_bar);
+  }
+  __syncwarp();
+
+  // ------------------------------------------------ epilogue (all 128 threads; thread == TMEM lane == tile row)
+  mbar_wait(&acc_bar, 0);
+  tc_fence_after();
+  for (int m = 0; m < p.MT; ++m) {
+    const int64_t P = P0 + (int64_t)m * 128 + tid;
+    int n, t, h, w;
+    const bool valid = uc_decode(p.g, P, n, t, h, w);
+    const bool inrange = P < p.g.P_total;
+    int64_t dst = P * 8;
+    if (p.out_mode == UC_OUT_PARITY && valid) {
+      const int64_t P2 = (((int64_t)n * (p.g2.T + 1) + t + 1) * (p.g2.H + 1) + (h >> 1) + 1) * p.g2.RW + (w >> 1) + 1;
+      dst = (int64_t)((h & 1) * 2 + (w & 1)) * p.y_set_stride + P2 * 8;
+    } else if (p.out_mode == UC_OUT_F32_ROWS && valid) {
+      dst = ((((int64_t)n * p.g.T + t) * p.g.H + h) * p.g.W + w) * p.y32_ld;
+    }
+    for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(m * p.Cout + c0), v);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += bias_s[c0 + j];
+        if (p.res) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 r = *reinterpret_cast<const uint4*>(p.res + (int64_t)(c0 / 8 + q) * p.res_plane_stride + P * 8);
+            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __bfloat1622float2(rb[e]);
+              v[q * 8 + 2 * e] += f.x;
+              v[q * 8 + 2 * e + 1] += f.y;
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = uc_act(v[j], p.act);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+      }
+      if (p.out_mode == UC_OUT_F32_ROWS) {
+        if (valid) {
+          float4* o = reinterpret_cast<float4*>(p.y32 + dst + c0);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+      } else if ((p.out_mode == UC_OUT_PLAIN && inrange) || (p.out_mode == UC_OUT_PARITY && valid)) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o;
+          __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) ob[e] = __floats2bfloat162_rn(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
+          *reinterpret_cast<uint4*>(p.y + (int64_t)(c0 / 8 + q) * p.y_plane_stride + dst) = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+size_t umma_conv_smem_bytes(const UmmaConvP& p) { return (size_t)p.stages * (p.a_stage_bytes + p.w_stage_bytes) + 1024; }
+
+void launch_umma_conv(const UmmaConvP& p, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    // the opt-in limit (227 KB) covers static + dynamic shared memory; ~1.3 KB is static (barriers, bias)
+    cudaFuncSetAttribute(umma_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    attr_set = true;
+  }
+  const int S = p.MT * 128;
+  const unsigned tiles = (unsigned)((p.g.P_total + S - 1) / S);
+  umma_conv_kernel<<<tiles, 128, umma_conv_smem_bytes(p), s>>>(p);
+  count_launch();
+}
+
+// ================================================================================================
+// planar-layout glue kernels (memory-bound, 16-byte accesses, one thread per (position, 8-channel chunk))
+// ================================================================================================
+__device__ __forceinline__ int64_t uc_flat(const UcGeom& g, int n, int t, int h, int w) {
+  return (((int64_t)n * (g.T + 1) + t + 1) * (g.H + 1) + h + 1) * g.RW + w + 1;
+}
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  uint4 o;
+  __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) ob[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+  return o;
+}
+__device__ __forceinline__ void unpack8(const uint4& r, float* v) {
+  const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(rb[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+}
+
+__global__ void pack_planar_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t plane_stride, int64_t set_stride,
+                                   UcGeom g, UcGeom g2, int C, int parity, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  // position-major within a chunk so that a warp writes 512 contiguous bytes of one plane
+  const int64_t npos = (int64_t)g.N * g.T * g.H * g.W;
+  const int chunk = (int)(i / npos);
+  int64_t r = i - (int64_t)chunk * npos;
+  const int w = (int)(r % g.W); r /= g.W;
+  const int h = (int)(r % g.H); r /= g.H;
+  const int t = (int)(r % g.T);
+  const int n = (int)(r / g.T);
+  const float* src = x + ((((int64_t)n * g.T + t) * g.H + h) * g.W + w) * C + chunk * 8;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = src[e];
+  int64_t dst;
+  if (parity) dst = (int64_t)((h & 1) * 2 + (w & 1)) * set_stride + uc_flat(g2, n, t, h >> 1, w >> 1) * 8;
+  else dst = uc_flat(g, n, t, h, w) * 8;
+  *reinterpret_cast<uint4*>(y + (int64_t)chunk * plane_stride + dst) = pack8(v);
+}
+void launch_pack_planar(const float* x, __nv_bfloat16* y, int64_t plane_stride, int64_t set_stride, UcGeom g, UcGeom g2, int C,
+                        int parity, cudaStream_t s) {
+  const int64_t total = (int64_t)g.N * g.T * g.H * g.W * (C / 8);
+  if (total == 0) return;
+  pack_planar_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, y, plane_stride, set_stride, g, g2, C, parity, total);
+  count_launch();
+}
+
+__global__ void unpack_planar_kernel(const __nv_bfloat16* __restrict__ x, int64_t plane_stride, UcGeom g, int C, float* __restrict__ y,
+                                     int ld, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int nch = C / 8;
+  const int chunk = (int)(i % nch);
+  int64_t r = i / nch;
+  const int64_t row = r;
+  const int w = (int)(r % g.W); r /= g.W;
+  const int h = (int)(r % g.H); r /= g.H;
+  const int t = (int)(r % g.T);
+  const int n = (int)(r / g.T);
+  const uint4 v = *reinterpret_cast<const uint4*>(x + (int64_t)chunk * plane_stride + uc_flat(g, n, t, h, w) * 8);
+  float f[8];
+  unpack8(v, f);
+  float4* o = reinterpret_cast<float4*>(y + row * ld + chunk * 8);
+  o[0] = make_float4(f[0], f[1], f[2], f[3]);
+  o[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+void launch_unpack_planar(const __nv_bfloat16* x, int64_t plane_stride, UcGeom g, int C, float* y, int ld, cudaStream_t s) {
+  const int64_t total = (int64_t)g.N * g.T * g.H * g.W * (C / 8);
+  if (total == 0) return;
+  unpack_planar_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, plane_stride, g, C, y, ld, total);
+  count_launch();
+}
+
+// Deterministic mean: one block per (row, chunk); threads stride over the row's positions, fixed-order tree in shared memory.
+__global__ void planar_mean_kernel(const __nv_bfloat16* __restrict__ x, int64_t plane_stride, UcGeom g, float* __restrict__ y, int ld,
+                                   int per_window) {
+  __shared__ float part[256][9];
+  const int row = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
+  const int count = per_window ? g.T * g.H * g.W : g.H * g.W;
+  const int n = per_window ? row : row / g.T;
+  const int t0 = per_window ? 0 : row % g.T;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = tid; i < count; i += blockDim.x) {
+    const int w = i % g.W;
+    const int r = i / g.W;
+    const int h = r % g.H;
+    const int t = t0 + r / g.H;
+    const uint4 v = *reinterpret_cast<const uint4*>(x + (int64_t)chunk * plane_stride + uc_flat(g, n, t, h, w) * 8);
+    float f[8];
+    unpack8(v, f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += f[e];
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) part[tid][e] = acc[e];
+  __syncthreads();
+  for (int sft = blockDim.x >> 1; sft > 0; sft >>= 1) {
+    if (tid < sft) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) part[tid][e] += part[tid + sft][e];
+    }
+    __syncthreads();
+  }
+  if (tid < 8) y[(int64_t)row * ld + chunk * 8 + tid] = part[0][tid] / (float)count;
+}
+void launch_planar_mean(const __nv_bfloat16* x, int64_t plane_stride, UcGeom g, int C, float* y, int ld, int per_window, cudaStream_t s) {
+  const int rows = per_window ? g.N : g.N * g.T;
+  if (rows == 0) return;
+  const int count = per_window ? g.T * g.H * g.W : g.H * g.W;
+  int threads = 32;
+  while (threads < 256 && threads < count) threads <<= 1;
+  planar_mean_kernel<<<dim3(rows, C / 8), threads, 0, s>>>(x, plane_stride, g, y, ld, per_window);
+  count_launch();
+}
+
+__global__ void planar_delta_kernel(const __nv_bfloat16* __restrict__ x, int64_t xs, UcGeom g, __nv_bfloat16* __restrict__ d, int64_t ds,
+                                    UcGeom gd, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int64_t npos = (int64_t)gd.N * gd.T * gd.H * gd.W;
+  const int chunk = (int)(i / npos);
+  int64_t r = i - (int64_t)chunk * npos;
+  const int w = (int)(r % gd.W); r /= gd.W;
+  const int h = (int)(r % gd.H); r /= gd.H;
+  const int t = (int)(r % gd.T);
+  const int n = (int)(r / gd.T);
+  float a[8], b[8], o[8];
+  unpack8(*reinterpret_cast<const uint4*>(x + (int64_t)chunk * xs + uc_flat(g, n, t + 1, h, w) * 8), a);
+  unpack8(*reinterpret_cast<const uint4*>(x + (int64_t)chunk * xs + uc_flat(g, n, t, h, w) * 8), b);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o[e] = a[e] - b[e];
+  *reinterpret_cast<uint4*>(d + (int64_t)chunk * ds + uc_flat(gd, n, t, h, w) * 8) = pack8(o);
+}
+void launch_planar_delta(const __nv_bfloat16* x, int64_t x_plane_stride, UcGeom g, __nv_bfloat16* d, int64_t d_plane_stride, UcGeom gd,
+                         int C, cudaStream_t s) {
+  const int64_t total = (int64_t)gd.N * gd.T * gd.H * gd.W * (C / 8);
+  if (total == 0) return;
+  planar_delta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, x_plane_stride, g, d, d_plane_stride, gd, total);
+  count_launch();
+}
+
+// MaxPool (1,3,3)/(1,2,2)/pad(0,1,1) in planar layout.  Inputs are post-ReLU (>= 0) and the pads are zero, so reading
+// the zero pad is equivalent to the reference's -inf padding except at the far edge, which is bounds-checked.
+__global__ void planar_maxpool_kernel(const __nv_bfloat16* __restrict__ x, int64_t xs, UcGeom gi, __nv_bfloat16* __restrict__ y, int64_t ys,
+                                      UcGeom go, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int64_t npos = (int64_t)go.N * go.T * go.H * go.W;
+  const int chunk = (int)(i / npos);
+  int64_t r = i - (int64_t)chunk * npos;
+  const int w = (int)(r % go.W); r /= go.W;
+  const int h = (int)(r % go.H); r /= go.H;
+  const int t = (int)(r % go.T);
+  const int n = (int)(r / go.T);
+  float m[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
+  for (int dh = 0; dh < 3; ++dh) {
+    const int hi = 2 * h - 1 + dh;
+    if ((unsigned)hi >= (unsigned)gi.H) continue;
+    for (int dw = 0; dw < 3; ++dw) {
+      const int wi = 2 * w - 1 + dw;
+      if ((unsigned)wi >= (unsigned)gi.W) continue;
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(x + (int64_t)chunk * xs + uc_flat(gi, n, t, hi, wi) * 8), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], f[e]);
+    }
+  }
+  *reinterpret_cast<uint4*>(y + (int64_t)chunk * ys + uc_flat(go, n, t, h, w) * 8) = pack8(m);
+}
+void launch_planar_maxpool(const __nv_bfloat16* x, int64_t x_plane_stride, UcGeom gi, __nv_bfloat16* y, int64_t y_plane_stride, UcGeom go,
+                           int C, cudaStream_t s) {
+  const int64_t total = (int64_t)go.N * go.T * go.H * go.W * (C / 8);
+  if (total == 0) return;
+  planar_maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, x_plane_stride, gi, y, y_plane_stride, go, total);
+  count_launch();
+}
+
+}  // namespace lsd

@@ -1,0 +1,90 @@
+// Parameter block of the tcgen05 "flat shift-GEMM" convolution kernel (umma_conv.cu) and the planar-layout glue.
+//
+// Activation layout of the bf16 path ("padded planar"): a tensor (N, T, H, W, C) is stored as C/8 planes; one plane
+// holds, for every *padded flat position*
+//     P = ((n*(T+1) + t + 1) * (H+1) + (h+1)) * (W+1) + (w+1)
+// the 8 channels of that position (16 bytes).  Slab 0 of every window, row 0 of every slab and column 0 of every row
+// are zero (one shared pad between neighbours), so a 3x3x3 / pad-1 convolution is a pure shift in P:
+//     out[P] = sum_taps W_tap . in[P + (kt-1)*SL + (kh-1)*RW + (kw-1)],   RW = W+1,  SL = (H+1)*(W+1)
+// and 8 consecutive positions of one channel-chunk are exactly one 8x16B UMMA core matrix (K-major, no swizzle).
+// Stride-2 consumers read a "parity-split" tensor: 4 plane sets (h&1, w&1), each in the half-resolution geometry.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lsd {
+
+constexpr int UC_MAX_BANDS = 16;
+constexpr int UC_MAX_TAPS = 9;
+constexpr int UC_MAX_GROUPS = 2;
+
+struct UcBand {
+  const __nv_bfloat16* base;  // plane 0, position 0 of the plane set this band reads
+  int64_t plane_stride;       // elements between consecutive 8-channel planes
+  int start;                  // flat shift of the band's first position relative to the tile's first position
+  int len_extra;              // band length = tile positions + len_extra
+  int ntaps;
+  int tap_begin;              // index of the band's first tap inside its group's packed weights
+  int rel[UC_MAX_TAPS];       // tap shift relative to the band start (positions)
+};
+
+struct UcGroup {              // taps that share one K extent (main conv; optional fused 1x1 downsample)
+  int band_begin, band_end;
+  int k16;                    // Cin / 16
+  int taps_total;
+  int64_t w_off;              // element offset of the group's packed weights
+};
+
+enum UcOut { UC_OUT_PLAIN = 0, UC_OUT_PARITY = 1, UC_OUT_F32_ROWS = 2 };
+
+struct UcGeom {               // padded flat geometry
+  int N, T, H, W, RW, SL;
+  int64_t P_total;
+};
+
+struct UmmaConvP {
+  const __nv_bfloat16* w;     // packed: [group][k16 chunk][tap][2 k-chunks][Cout][8]
+  const float* bias;          // Cout (BN shift + folded conv bias; BN scale is folded into w)
+  const __nv_bfloat16* res;   // optional residual, plain layout in the output geometry
+  int64_t res_plane_stride;
+  __nv_bfloat16* y;           // UC_OUT_PLAIN / UC_OUT_PARITY destination (position 0 of plane 0 [of set 0])
+  int64_t y_plane_stride, y_set_stride;
+  float* y32;                 // UC_OUT_F32_ROWS destination: row = valid position in (n,t,h,w) order
+  int y32_ld;
+  int out_mode, act;
+  int Cout, MT, stages, ngroups, nbands;
+  uint32_t a_stage_bytes, w_stage_bytes, tmem_cols;
+  UcGeom g;                   // output geometry (== input geometry of every band)
+  UcGeom g2;                  // UC_OUT_PARITY: half-resolution destination geometry
+  UcGroup groups[UC_MAX_GROUPS];
+  UcBand bands[UC_MAX_BANDS];
+};
+
+size_t umma_conv_smem_bytes(const UmmaConvP& p);
+void launch_umma_conv(const UmmaConvP& p, cudaStream_t s);
+
+// ---- planar-layout glue --------------------------------------------------------------------------
+// fp32 channels-last (N,T,H,W,C) -> padded planar bf16 (plain, or parity-split when parity != 0); pads are NOT written.
+void launch_pack_planar(const float* x, __nv_bfloat16* y, int64_t plane_stride, int64_t set_stride, UcGeom g, UcGeom g2, int C,
+                        int parity, cudaStream_t s);
+// padded planar bf16 (plain) -> fp32 channels-last rows (valid positions only)
+void launch_unpack_planar(const __nv_bfloat16* x, int64_t plane_stride, UcGeom g, int C, float* y, int ld, cudaStream_t s);
+// mean over `group` consecutive valid positions -> fp32 y[(row) * ld + c]; per_window != 0: one row per window (mean over T*H*W),
+// else one row per (n,t) (mean over H*W).
+void launch_planar_mean(const __nv_bfloat16* x, int64_t plane_stride, UcGeom g, int C, float* y, int ld, int per_window, cudaStream_t s);
+// temporal difference in planar layout: d[n,t] = x[n,t+1] - x[n,t]  (geometry gd has T-1 frames)
+void launch_planar_delta(const __nv_bfloat16* x, int64_t x_plane_stride, UcGeom g, __nv_bfloat16* d, int64_t d_plane_stride, UcGeom gd,
+                         int C, cudaStream_t s);
+// 3x3 / stride 2 / pad 1 max-pool over (H,W) in planar layout (plain -> plain), writes zero pads too
+void launch_planar_maxpool(const __nv_bfloat16* x, int64_t x_plane_stride, UcGeom gi, __nv_bfloat16* y, int64_t y_plane_stride, UcGeom go,
+                           int C, cudaStream_t s);
+
+inline UcGeom make_geom(int N, int T, int H, int W) {
+  UcGeom g;
+  g.N = N; g.T = T; g.H = H; g.W = W; g.RW = W + 1; g.SL = (H + 1) * (W + 1);
+  g.P_total = ((int64_t)N * (T + 1) + 1) * g.SL;
+  return g;
+}
+
+}  // namespace lsd

@@ -253,9 +253,10 @@ class LipSyncModel(nn.Module):
         L = _cabi.lib()
         return [L.lsd_stage_name(h.ptr, i).decode() for i in range(L.lsd_stage_count(h.ptr))]
 
-    def profile_enable(self, on: bool) -> None:
-        """Bracket every launch of the dominant kernel class with CUDA events (bench.py roofline)."""
-        _cabi.check(self._lsd_handle.ptr, _cabi.lib().lsd_profile_enable(self._lsd_handle.ptr, 1 if on else 0))
+    def profile_enable(self, cls: int) -> None:
+        """Bracket every launch of one kernel class with CUDA events (bench.py roofline):
+        0 off, 1 fp32 conv kernel, 2 tcgen05 conv kernel."""
+        _cabi.check(self._lsd_handle.ptr, _cabi.lib().lsd_profile_enable(self._lsd_handle.ptr, int(cls)))
 
     def profile_get(self):
         """-> (summed kernel ms, launches, algorithmic FLOPs) since the last call; synchronises."""

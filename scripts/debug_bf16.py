@@ -1,0 +1,28 @@
+"""Debug helper (GPU): stage-by-stage error of the bf16 tensor-core path against the CPU oracle."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import __graft_entry__ as ge
+ge.build()
+import lipsync_b200 as lb
+from oracle import lipsync_oracle as orc
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+sd = lb.make_synthetic_state_dict(0)
+video, audio = lb.synthetic_windows(1, B)
+inter = {}
+ref = orc.forward(sd, video, audio, inter=inter)
+m = lb.LipSyncModel(); m.load_state_dict(sd); m.to("cuda").eval()
+m.compute_precision = "bf16"
+t0 = time.time()
+out = m(video.cuda(), audio.cuda()).cpu()
+torch.cuda.synchronize()
+print("forward done in", time.time() - t0, flush=True)
+def rel(a, b): return float((a - b).abs().max()) / max(1e-12, float(b.abs().max()))
+vf = m.stage("v_feat").cpu().view(B, -1, 256)
+print("v_feat rel", rel(vf, inter["v_feat"].transpose(1, 2)))
+comb = m.stage("comb").cpu().view(B, 448)
+for i, k in enumerate(["art_raw", "art_delta", "art_hf"]):
+    print(k, "rel", rel(comb[:, 256 + 64 * i: 320 + 64 * i], inter[k]))
+print("cls rel", rel(comb[:, :256], inter["cls"]))
+print("logits", out.tolist(), "ref", ref.tolist(), "max abs", float((out - ref).abs().max()))
