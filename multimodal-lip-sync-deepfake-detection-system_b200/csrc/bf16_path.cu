@@ -43,6 +43,34 @@ BGroup make_group(const ConvP& c, int sh, int sw) {
         band->taps.push_back(t);
       }
   g.taps_total = c.kt * c.kh * c.kw;
+  g.k16 = c.Cin / 16;
+  return g;
+}
+
+// Toeplitz group (Cin = 3 convolutions with stride 2 in w, reading bf16 "pixel rows": 4 channels x 2 B per pixel, h-parity
+// split, 2 pixels per 16-byte unit): a "tap" is one (kt, kh) pair, K runs over `kpix` consecutive pixels of the input row
+// starting at pixel 2*wo + kw0 - pad_w (kw0 = -1: one leading zero-weight pixel keeps the start 16-byte aligned).
+BGroup make_group_toeplitz(const ConvP& c, int kpix, int dw_units) {
+  BGroup g;
+  g.Cin = c.Cin;
+  g.toeplitz = 1;
+  g.k16 = kpix * 4 / 16;
+  for (int a = 0; a < c.kt; ++a)
+    for (int b = 0; b < c.kh; ++b) {
+      BTap t;
+      t.orig = a * c.kh + b;
+      t.dt = a - c.kt / 2;
+      const int oh = b - c.kh / 2;
+      const int hp = oh & 1;
+      t.dh = (oh - hp) / 2;
+      t.dw = dw_units;
+      BBand* band = nullptr;
+      for (BBand& bb : g.bands)
+        if (bb.set == hp && bb.taps[0].dt == t.dt) band = &bb;
+      if (!band) { g.bands.push_back(BBand{hp, {}}); band = &g.bands.back(); }
+      band->taps.push_back(t);
+    }
+  g.taps_total = c.kt * c.kh;
   return g;
 }
 
@@ -67,6 +95,32 @@ struct Packer {
                 const float v = W[((size_t)t.orig * c.Cin + ci) * Cout + n] * (sc ? sc[n] : 1.0f);
                 w.push_back(f2bf(v));
               }
+  }
+  // Toeplitz packing: K index k = c*16 + kc*8 + e  <->  pixel j = k/4 of the row window, channel k%4; kw = j - 1.
+  void add_toeplitz(const std::string& name, const std::string& key, int kpix, int dw_units) {
+    const ConvP& c = h->convs.at(key);
+    BLayer L;
+    L.Cout = c.Cout;
+    L.groups.push_back(make_group_toeplitz(c, kpix, dw_units));
+    BGroup& g = L.groups[0];
+    g.w_off = w.size();
+    const float* W = &f32[c.w_off];
+    const float* sc = c.has_scale ? &f32[c.scale_off] : nullptr;
+    for (int ch = 0; ch < g.k16; ++ch)
+      for (const BBand& b : g.bands)
+        for (const BTap& t : b.taps)
+          for (int kc = 0; kc < 2; ++kc)
+            for (int n = 0; n < c.Cout; ++n)
+              for (int e = 0; e < 8; ++e) {
+                const int k = ch * 16 + kc * 8 + e, j = k / 4, ci = k % 4, kw = j - 1;
+                float v = 0.f;
+                if (ci < c.Cin && kw >= 0 && kw < c.kw) v = W[((size_t)(t.orig * c.kw + kw) * c.Cin + ci) * c.Cout + n] * (sc ? sc[n] : 1.0f);
+                w.push_back(f2bf(v));
+              }
+    L.bias_off = bias.size();
+    for (int i = 0; i < c.Cout; ++i) bias.push_back(f32[c.shift_off + i]);
+    while (w.size() % 64) w.push_back(0);
+    h->blayers[name] = L;
   }
   void add(const std::string& name, const std::string& key, int sh, int sw, const std::string& ds_key = "") {
     const ConvP& c = h->convs.at(key);
@@ -101,7 +155,7 @@ constexpr int TILE_MAX = 1024;  // largest MT*128
 PBuf make_pbuf(int C, int sets, UcGeom g) {
   PBuf b;
   b.C = C; b.sets = sets; b.g = g;
-  const int64_t gf = ((int64_t)g.SL + g.RW + 8 + 7) / 8 * 8;
+  const int64_t gf = ((int64_t)g.SL + 3 * g.RW + 16 + 7) / 8 * 8;
   const int64_t gb = gf + TILE_MAX;
   const int64_t plane_pos = (gf + g.P_total + gb + 7) / 8 * 8;
   b.origin = gf * 8;
@@ -131,8 +185,6 @@ void build_plan(const Shapes& s, BPlan& P) {
   // fp32 buffers (names shared with make_plan_f32 so the fw_* helpers work on either plan)
   p.add("vid", B * T * s.H * s.W * 3);
   p.add("aud", B * s.F * s.Ta);
-  p.add("v_stem_conv", B * T * s.Hs * s.Ws * 64);
-  p.add("v_stem", B * T * s.H1 * s.W1 * 64);
   p.add("v_feat", B * T * 256);
   for (const char* n : {"a_stem_conv"}) p.add(n, B * s.Fs * s.As * 64);
   for (const char* n : {"a_stem", "a_l1a", "a_layer1"}) p.add(n, B * s.F1 * s.A1 * 64);
@@ -155,8 +207,6 @@ void build_plan(const Shapes& s, BPlan& P) {
   for (const char* n : {"tok", "tok_ln", "tok_att", "t_layer0", "t_layer3"}) p.add(n, B * (T + 1) * 256);
   p.add("tok_qkv", B * (T + 1) * 768);
   p.add("tok_ff", B * (T + 1) * 1024);
-  p.add("hf_lap", B * T * s.H * s.W * 3);
-  p.add("hf_front", B * T * s.Hh * s.Wh * 32);
   p.add("comb", B * 448);
   p.add("art_h", B * 256);
   p.add("feat", B * 384);
@@ -166,6 +216,11 @@ void build_plan(const Shapes& s, BPlan& P) {
   const int Bn = s.B, Tn = s.T;
   const UcGeom g1 = make_geom(Bn, Tn, s.H1, s.W1), g2 = make_geom(Bn, Tn, s.H2, s.W2), g3 = make_geom(Bn, Tn, s.H3, s.W3),
                g4 = make_geom(Bn, Tn, s.H4, s.W4), gd = make_geom(Bn, s.Td, s.H4, s.W4), gh = make_geom(Bn, Tn, s.Hg, s.Wg);
+  // bf16 pixel rows of the video and of its per-frame 3->3 "laplacian" conv (h-parity split; 16-byte unit = 2 pixels x 4 ch)
+  const UcGeom gs = make_geom_ex(Bn, Tn, s.Hs, s.Ws, 1, 2, 0, 0, 4);
+  P.addp("xs", 8, 2, gs);
+  P.addp("xl", 8, 2, gs);
+  P.addp("s_out", 64, 1, gs);    // stem conv output (stem geometry), before the max-pool
   P.addp("x1", 64, 1, g1);
   P.addp("l1a", 64, 1, g1);
   P.addp("y1", 64, 4, g2);       // parity-split: four half-resolution plane sets
@@ -227,7 +282,7 @@ int run_umma(const BCtx& c, const std::string& name, const PBuf& in, const PBuf*
     const PBuf& src = (gi == 0) ? in : *in_ds;
     UcGroup& ug = p.groups[gi];
     ug.band_begin = nb;
-    ug.k16 = G.Cin / 16;
+    ug.k16 = G.k16;
     ug.taps_total = G.taps_total;
     ug.w_off = (int64_t)G.w_off;
     int tap_begin = 0;
@@ -236,6 +291,8 @@ int run_umma(const BCtx& c, const std::string& name, const PBuf& in, const PBuf*
       UcBand& ub = p.bands[nb++];
       ub.base = c.base(src) + (int64_t)b.set * src.set_stride + src.origin;
       ub.plane_stride = src.plane_stride;
+      ub.toeplitz = G.toeplitz;
+      ub.chunk_stride = G.toeplitz ? 16 : 2 * src.plane_stride;
       int mn = INT32_MAX, mx = INT32_MIN;
       for (const BTap& t : b.taps) {
         const int sft = t.dt * og.SL + t.dh * og.RW + t.dw;
@@ -247,7 +304,7 @@ int run_umma(const BCtx& c, const std::string& name, const PBuf& in, const PBuf*
       ub.tap_begin = tap_begin;
       for (int j = 0; j < ub.ntaps; ++j) ub.rel[j] = b.taps[j].dt * og.SL + b.taps[j].dh * og.RW + b.taps[j].dw - mn;
       tap_begin += ub.ntaps;
-      max_extra = std::max(max_extra, ub.len_extra);
+      max_extra = std::max(max_extra, ub.len_extra + ub.toeplitz);
       max_taps = std::max(max_taps, ub.ntaps);
       // the band must stay inside the guard zones of the source buffer
       if (-(int64_t)ub.start * 8 > src.origin) return lsd_fail(c.h, LSD_ERR_UNSUPPORTED, "%s: front guard too small", name.c_str());
@@ -265,6 +322,7 @@ int run_umma(const BCtx& c, const std::string& name, const PBuf& in, const PBuf*
   p.stages = stages;
   double kflop = 0;
   for (const BGroup& G : L.groups) kflop += (double)G.taps_total * G.Cin;
+  if (L.groups[0].toeplitz) { const ConvP& cp = c.h->convs.at(name); kflop = (double)cp.kt * cp.kh * cp.kw * cp.Cin; }  // algorithmic K, not the padded one
   c.h->prof.begin(c.st, 2.0 * (double)og.N * og.T * og.H * og.W * L.Cout * kflop, 2);
   launch_umma_conv(p, c.st);
   c.h->prof.end(c.st);
@@ -282,6 +340,8 @@ int pack_bf16_weights(lsd_handle* h, const std::vector<float>& f32_arena) {
     P.add(p + ".conv1", p + ".conv1", s, s);
     P.add(p + ".conv2", p + ".conv2", 1, 1, l == 1 ? "" : p + ".downsample");
   }
+  P.add_toeplitz("visual_encoder.stem", "visual_encoder.stem", 8, 0);  // 7 taps in w -> 8-pixel window starting at 2*wo-4
+  P.add_toeplitz("art.hf0", "art.hf0", 4, 1);                          // 3 taps in w -> 4-pixel window starting at 2*wo-2
   P.add("art.td0", "art.td0", 1, 1);
   P.add("art.td3", "art.td3", 1, 1);
   P.add("art.hf3", "art.hf3", 2, 2);
@@ -321,14 +381,17 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   Ctx c{h, ws, &P.f32, st};
   BCtx b{h, ws, &P, st};
   const int B = s.B, T = s.T;
-  if (!inputs_ready) fw_inputs(c, s, video, vdt, vlayout, audio, adt);
+  if (!inputs_ready) launch_cast_to_f32(audio, adt, c.buf("aud"), (int64_t)B * s.F * s.Ta, 1.0f, st);
   auto& pb = P.pb;
   int rc = 0;
-  // ---- stem (fp32 CUDA-core kernel for now) + max-pool, then into the planar layout
-  conv(c, "visual_encoder.stem", c.buf("vid"), 3, B, T, s.H, s.W, 1, 2, 2, 1, 3, 3, c.buf("v_stem_conv"), 64, ACT_RELU);
-  launch_maxpool3x3s2(c.buf("v_stem_conv"), c.buf("v_stem"), B * T, s.Hs, s.Ws, 64, st);
-  const PBuf& x1 = pb["x1"];
-  launch_pack_planar(c.buf("v_stem"), b.base(x1) + x1.origin, x1.plane_stride, x1.set_stride, x1.g, x1.g, 64, 0, st);
+  // ---- video -> bf16 pixel rows (+ per-frame laplacian conv), stem conv on tcgen05 (Toeplitz K), max-pool in planar layout
+  const PBuf &xs = pb["xs"], &xl = pb["xl"], &so = pb["s_out"], &x1 = pb["x1"];
+  if (inputs_ready) launch_video_rows(c.buf("vid"), LSD_F32, LSD_NDHWC, h->warena + h->convs.at("art.lap").w_off, b.base(xs) + xs.origin,
+                                      b.base(xl) + xl.origin, xs.set_stride, xs.g, s.H, s.W, st);
+  else launch_video_rows(video, vdt, vlayout, h->warena + h->convs.at("art.lap").w_off, b.base(xs) + xs.origin, b.base(xl) + xl.origin,
+                         xs.set_stride, xs.g, s.H, s.W, st);
+  if ((rc = run_umma(b, "visual_encoder.stem", xs, nullptr, so, xs.g, ACT_RELU, nullptr))) return rc;
+  launch_planar_maxpool(b.base(so) + so.origin, so.plane_stride, so.g, b.base(x1) + x1.origin, x1.plane_stride, x1.g, 64, st);
   // ---- residual stages on tcgen05 (visual_encoder.py:81-87, 133-152)
   if ((rc = run_umma(b, "visual_encoder.layer1.conv1", x1, nullptr, pb["l1a"], x1.g, ACT_RELU, nullptr))) return rc;
   if ((rc = run_umma(b, "visual_encoder.layer1.conv2", pb["l1a"], nullptr, pb["y1"], x1.g, ACT_RELU, &x1))) return rc;
@@ -354,11 +417,9 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   if ((rc = run_umma(b, "art.td0", dl, nullptr, pb["artd_a"], dl.g, ACT_RELU, nullptr))) return rc;
   if ((rc = run_umma(b, "art.td3", pb["artd_a"], nullptr, pb["artd_b"], dl.g, ACT_RELU, nullptr))) return rc;
   launch_planar_mean(b.base(pb["artd_b"]) + pb["artd_b"].origin, pb["artd_b"].plane_stride, dl.g, 64, comb + 320, 448, 1, st);
-  // high-frequency branch: per-frame 3->3 conv + Conv3d 3->32 on CUDA cores (Cin = 3), Conv3d 32->64 on tcgen05
-  conv(c, "art.lap", c.buf("vid"), 3, B * T, 1, s.H, s.W, 1, 1, 1, 0, 1, 1, c.buf("hf_lap"), 3, ACT_NONE);
-  conv(c, "art.hf0", c.buf("hf_lap"), 3, B, T, s.H, s.W, 1, 2, 2, 1, 1, 1, c.buf("hf_front"), 32, ACT_RELU);
+  // high-frequency branch: Conv3d 3->32 s(1,2,2) on the laplacian pixel rows (Toeplitz K), Conv3d 32->64 s(1,2,2) planar
   const PBuf& hf = pb["hf_f"];
-  launch_pack_planar(c.buf("hf_front"), b.base(hf) + hf.origin, hf.plane_stride, hf.set_stride, make_geom(B, T, s.Hh, s.Wh), hf.g, 32, 1, st);
+  if ((rc = run_umma(b, "art.hf0", xl, nullptr, hf, xl.g, ACT_RELU, nullptr))) return rc;
   if ((rc = run_umma(b, "art.hf3", hf, nullptr, pb["hf_b"], hf.g, ACT_RELU, nullptr))) return rc;
   launch_planar_mean(b.base(pb["hf_b"]) + pb["hf_b"].origin, pb["hf_b"].plane_stride, hf.g, 64, comb + 384, 448, 1, st);
   // ---- fusion MLP + head (fp32)

@@ -31,10 +31,14 @@ __device__ __forceinline__ bool uc_decode(const UcGeom& g, int64_t P, int& n, in
   const int64_t S = P / g.SL;
   const int r = (int)(P - S * g.SL);
   const int row = r / g.RW, col = r - row * g.RW;
-  const int tt = (int)(S % (g.T + 1));
-  n = (int)(S / (g.T + 1));
-  t = tt - 1; h = row - 1; w = col - 1;
-  return tt != 0 && row != 0 && col != 0 && n < g.N;
+  n = (int)(S / g.TS);
+  t = (int)(S - (int64_t)n * g.TS) - g.ot;
+  h = row - g.oh; w = col - g.ow;
+  return (unsigned)t < (unsigned)g.T && (unsigned)h < (unsigned)g.H && (unsigned)w < (unsigned)g.W && n < g.N;
+}
+
+__device__ __forceinline__ int64_t uc_flat(const UcGeom& g, int n, int t, int h, int w) {
+  return (((int64_t)n * g.TS + t + g.ot) * g.HP + h + g.oh) * g.RW + w + g.ow;
 }
 
 __global__ void __launch_bounds__(128) umma_conv_kernel(const __grid_constant__ UmmaConvP p) {
@@ -70,13 +74,14 @@ __global__ void __launch_bounds__(128) umma_conv_kernel(const __grid_constant__ 
           const int stage = it % p.stages;
           const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
           mbar_wait(&empty_bar[stage], ph ^ 1u);
-          const uint32_t bytesA = (uint32_t)(S + bd.len_extra) * 16u;
+          // planar: two 8-channel planes; Toeplitz: one pixel-row region (+1 unit for the overlapping second K chunk)
+          const uint32_t bytesA = (uint32_t)(S + bd.len_extra + bd.toeplitz) * 16u;
           const uint32_t bytesW = (uint32_t)bd.ntaps * (uint32_t)p.Cout * 32u;
-          mbar_arrive_expect_tx(&full_bar[stage], 2u * bytesA + bytesW);
+          mbar_arrive_expect_tx(&full_bar[stage], (bd.toeplitz ? 1u : 2u) * bytesA + bytesW);
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
-          const __nv_bfloat16* src = bd.base + (int64_t)(2 * c) * bd.plane_stride + (P0 + bd.start) * 8;
+          const __nv_bfloat16* src = bd.base + (int64_t)c * bd.chunk_stride + (P0 + bd.start) * 8;
           bulk_g2s(sa, src, bytesA, &full_bar[stage]);
-          bulk_g2s(sa + bytesA, src + bd.plane_stride, bytesA, &full_bar[stage]);
+          if (!bd.toeplitz) bulk_g2s(sa + bytesA, src + bd.plane_stride, bytesA, &full_bar[stage]);
           const __nv_bfloat16* wsrc = p.w + g.w_off + ((int64_t)c * g.taps_total + bd.tap_begin) * (int64_t)p.Cout * 16;
           bulk_g2s(sa + p.a_stage_bytes, wsrc, bytesW, &full_bar[stage]);
         }
@@ -98,7 +103,7 @@ __global__ void __launch_bounds__(128) umma_conv_kernel(const __grid_constant__ 
           tc_fence_after();
           const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
           const uint32_t sw = sa + p.a_stage_bytes;
-          const uint32_t lboA = (uint32_t)(S + bd.len_extra) * 16u;
+          const uint32_t lboA = bd.toeplitz ? 16u : (uint32_t)(S + bd.len_extra) * 16u;
           for (int j = 0; j < bd.ntaps; ++j) {
             const uint64_t db = smem_desc(sw + (uint32_t)j * (uint32_t)p.Cout * 32u, (uint32_t)p.Cout * 16u, 128u);
             for (int m = 0; m < p.MT; ++m) {
@@ -124,8 +129,7 @@ __global__ void __launch_bounds__(128) umma_conv_kernel(const __grid_constant__ 
     const bool inrange = P < p.g.P_total;
     int64_t dst = P * 8;
     if (p.out_mode == UC_OUT_PARITY && valid) {
-      const int64_t P2 = (((int64_t)n * (p.g2.T + 1) + t + 1) * (p.g2.H + 1) + (h >> 1) + 1) * p.g2.RW + (w >> 1) + 1;
-      dst = (int64_t)((h & 1) * 2 + (w & 1)) * p.y_set_stride + P2 * 8;
+      dst = (int64_t)((h & 1) * 2 + (w & 1)) * p.y_set_stride + uc_flat(p.g2, n, t, h >> 1, w >> 1) * 8;
     } else if (p.out_mode == UC_OUT_F32_ROWS && valid) {
       dst = ((((int64_t)n * p.g.T + t) * p.g.H + h) * p.g.W + w) * p.y32_ld;
     }
@@ -196,9 +200,6 @@ void launch_umma_conv(const UmmaConvP& p, cudaStream_t s) {
 // ================================================================================================
 // planar-layout glue kernels (memory-bound, 16-byte accesses, one thread per (position, 8-channel chunk))
 // ================================================================================================
-__device__ __forceinline__ int64_t uc_flat(const UcGeom& g, int n, int t, int h, int w) {
-  return (((int64_t)n * (g.T + 1) + t + 1) * (g.H + 1) + h + 1) * g.RW + w + 1;
-}
 __device__ __forceinline__ uint4 pack8(const float* v) {
   uint4 o;
   __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
@@ -370,6 +371,80 @@ void launch_planar_maxpool(const __nv_bfloat16* x, int64_t x_plane_stride, UcGeo
   const int64_t total = (int64_t)go.N * go.T * go.H * go.W * (C / 8);
   if (total == 0) return;
   planar_maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, x_plane_stride, gi, y, y_plane_stride, go, total);
+  count_launch();
+}
+
+// One thread per pixel pair: loads the 3x4 pixel neighbourhood once, writes the pair to both row buffers.
+__global__ void video_rows_kernel(const void* __restrict__ video, int dtype, int layout, const float* __restrict__ lapw,
+                                  __nv_bfloat16* __restrict__ xs, __nv_bfloat16* __restrict__ xl, int64_t set_stride, UcGeom g, int T, int H,
+                                  int W, int64_t total) {
+  __shared__ float lw[81];
+  if (threadIdx.x < 81) lw[threadIdx.x] = lapw[threadIdx.x];
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int WP = (W + 1) / 2;
+  const int wp = (int)(i % WP);
+  int64_t r = i / WP;
+  const int h = (int)(r % H); r /= H;
+  const int t = (int)(r % T);
+  const int n = (int)(r / T);
+  const int p0 = 2 * wp;
+  const float div = dtype == 3 ? 255.0f : 1.0f;
+  float v[3][4][3];
+#pragma unroll
+  for (int dh = 0; dh < 3; ++dh) {
+    const int hh = h + dh - 1;
+#pragma unroll
+    for (int dp = 0; dp < 4; ++dp) {
+      const int ww = p0 + dp - 1;
+      const bool in = (unsigned)hh < (unsigned)H && (unsigned)ww < (unsigned)W;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float x = 0.f;
+        if (in) {
+          const int64_t idx = layout == 0 ? ((((int64_t)n * 3 + c) * T + t) * H + hh) * W + ww
+                                          : ((((int64_t)n * T + t) * H + hh) * W + ww) * 3 + c;
+          switch (dtype) {
+            case 0: x = reinterpret_cast<const float*>(video)[idx]; break;
+            case 1: x = __half2float(reinterpret_cast<const __half*>(video)[idx]); break;
+            case 2: x = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(video)[idx]); break;
+            default: x = (float)reinterpret_cast<const uint8_t*>(video)[idx]; break;
+          }
+          x /= div;
+        }
+        v[dh][dp][c] = x;
+      }
+    }
+  }
+  float px[8], lp[8];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) px[q * 4 + c] = v[1][1 + q][c];
+    px[q * 4 + 3] = 0.f;
+#pragma unroll
+    for (int co = 0; co < 3; ++co) {
+      float acc = 0.f;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+          for (int ci = 0; ci < 3; ++ci) acc = fmaf(lw[((kh * 3 + kw) * 3 + ci) * 3 + co], v[kh][q + kw][ci], acc);
+      lp[q * 4 + co] = (p0 + q < W) ? acc : 0.f;
+    }
+    lp[q * 4 + 3] = 0.f;
+  }
+  const int64_t dst = (int64_t)(h & 1) * set_stride + uc_flat(g, n, t, h >> 1, 0) * 8 + (int64_t)(p0 + 4) * 4;
+  *reinterpret_cast<uint4*>(xs + dst) = pack8(px);
+  *reinterpret_cast<uint4*>(xl + dst) = pack8(lp);
+}
+void launch_video_rows(const void* video, int dtype, int layout, const float* lapw, __nv_bfloat16* xs, __nv_bfloat16* xl,
+                       int64_t set_stride, UcGeom g, int H, int W, cudaStream_t s) {
+  const int64_t total = (int64_t)g.N * g.T * H * ((W + 1) / 2);
+  if (total == 0) return;
+  video_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(video, dtype, layout, lapw, xs, xl, set_stride, g, g.T, H, W, total);
   count_launch();
 }
 

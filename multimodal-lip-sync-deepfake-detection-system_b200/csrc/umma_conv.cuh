@@ -22,10 +22,12 @@ constexpr int UC_MAX_GROUPS = 2;
 struct UcBand {
   const __nv_bfloat16* base;  // plane 0, position 0 of the plane set this band reads
   int64_t plane_stride;       // elements between consecutive 8-channel planes
+  int64_t chunk_stride;       // elements added per k16 chunk: 2*plane_stride (planar) or 16 (Toeplitz pixel rows)
   int start;                  // flat shift of the band's first position relative to the tile's first position
   int len_extra;              // band length = tile positions + len_extra
   int ntaps;
   int tap_begin;              // index of the band's first tap inside its group's packed weights
+  int toeplitz;               // 1: K runs along the pixel row itself (LBO = 16 B, one region), see bf16_path.cu (stem / hf front)
   int rel[UC_MAX_TAPS];       // tap shift relative to the band start (positions)
 };
 
@@ -38,8 +40,11 @@ struct UcGroup {              // taps that share one K extent (main conv; option
 
 enum UcOut { UC_OUT_PLAIN = 0, UC_OUT_PARITY = 1, UC_OUT_F32_ROWS = 2 };
 
-struct UcGeom {               // padded flat geometry
-  int N, T, H, W, RW, SL;
+// Padded flat geometry:  P = ((n*TS + t + ot)*HP + h + oh)*RW + w + ow,  SL = HP*RW.
+// Standard activation geometry: one shared zero slab / row / column (TS=T+1, ot=1, HP=H+1, oh=1, RW=W+1, ow=1).
+struct UcGeom {
+  int N, T, H, W;
+  int TS, ot, HP, oh, RW, ow, SL;
   int64_t P_total;
 };
 
@@ -76,15 +81,28 @@ void launch_planar_mean(const __nv_bfloat16* x, int64_t plane_stride, UcGeom g, 
 // temporal difference in planar layout: d[n,t] = x[n,t+1] - x[n,t]  (geometry gd has T-1 frames)
 void launch_planar_delta(const __nv_bfloat16* x, int64_t x_plane_stride, UcGeom g, __nv_bfloat16* d, int64_t d_plane_stride, UcGeom gd,
                          int C, cudaStream_t s);
-// 3x3 / stride 2 / pad 1 max-pool over (H,W) in planar layout (plain -> plain), writes zero pads too
+// 3x3 / stride 2 / pad 1 max-pool over (H,W) in planar layout (plain -> plain); valid positions only
 void launch_planar_maxpool(const __nv_bfloat16* x, int64_t x_plane_stride, UcGeom gi, __nv_bfloat16* y, int64_t y_plane_stride, UcGeom go,
                            int C, cudaStream_t s);
 
-inline UcGeom make_geom(int N, int T, int H, int W) {
+// video (any dtype; NCDHW or NDHWC; uint8 scaled by 1/255) -> bf16 pixel rows xs (stem input) and xl = per-frame 3x3 conv 3->3
+// with weights lapw [tap][ci][co] (artifact_detector.py:33-35,55-57).  Row layout: h-parity plane sets, geometry g (units of
+// 2 pixels), pixel p of a row at element offset (p + 4) * 4, channels (r, g, b, 0).
+void launch_video_rows(const void* video, int dtype, int layout, const float* lapw, __nv_bfloat16* xs, __nv_bfloat16* xl,
+                       int64_t set_stride, UcGeom g, int H, int W, cudaStream_t s);
+
+inline UcGeom make_geom_ex(int N, int T, int H, int W, int tpad, int oh, int hp_extra, int ow, int wp_extra) {
   UcGeom g;
-  g.N = N; g.T = T; g.H = H; g.W = W; g.RW = W + 1; g.SL = (H + 1) * (W + 1);
-  g.P_total = ((int64_t)N * (T + 1) + 1) * g.SL;
+  g.N = N; g.T = T; g.H = H; g.W = W;
+  g.TS = T + tpad; g.ot = tpad;
+  g.HP = H + oh + hp_extra; g.oh = oh;
+  g.RW = W + ow + wp_extra; g.ow = ow;
+  g.SL = g.HP * g.RW;
+  g.P_total = ((int64_t)N * g.TS + tpad) * g.SL;
   return g;
 }
+inline UcGeom make_geom(int N, int T, int H, int W) { return make_geom_ex(N, T, H, W, 1, 1, 0, 1, 0); }
+// plain row-major rows (Linear layers): P == row
+inline UcGeom make_geom_rows(int rows) { return make_geom_ex(1, 1, 1, rows, 0, 0, 0, 0, 0); }
 
 }  // namespace lsd
