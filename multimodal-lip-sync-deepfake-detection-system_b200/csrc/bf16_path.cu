@@ -2,6 +2,7 @@
 // orchestration that runs the 3-D residual stages, the artifact-detector convolutions and the high-frequency
 // back end on it.  Host-side only.
 #include "forward_common.h"
+#include "token_kernels.cuh"
 #include "umma_conv.cuh"
 
 #include <algorithm>
@@ -79,28 +80,36 @@ struct Packer {
   const std::vector<float>& f32;
   std::vector<uint16_t> w;
   std::vector<float> bias;
-  // packed order: [k16 chunk][tap in band order][2 k-chunks][Cout][8]
-  void pack_group(BGroup& g, const ConvP& c) {
+  int ds_sh = 2, ds_sw = 2;   // stride of the downsample conv fused by the next add(..., ds_key)
+  // packed order: [Cout slice][k16 chunk][tap in band order][2 k-chunks][ntile][8]
+  // part: 0 = bf16(W*scale) ("hi"), 1 = bf16(W*scale - hi) ("lo")
+  void pack_group(BGroup& g, const ConvP& c, int ntile, int part = 0) {
     g.w_off = w.size();
     const int Cout = c.Cout;
     const float* W = &f32[c.w_off];
     const float* sc = c.has_scale ? &f32[c.scale_off] : nullptr;
-    for (int ch = 0; ch < c.Cin / 16; ++ch)
-      for (const BBand& b : g.bands)
-        for (const BTap& t : b.taps)
-          for (int kc = 0; kc < 2; ++kc)
-            for (int n = 0; n < Cout; ++n)
-              for (int e = 0; e < 8; ++e) {
-                const int ci = ch * 16 + kc * 8 + e;
-                const float v = W[((size_t)t.orig * c.Cin + ci) * Cout + n] * (sc ? sc[n] : 1.0f);
-                w.push_back(f2bf(v));
-              }
+    g.slice_stride = (size_t)(c.Cin / 16) * g.taps_total * ntile * 16;
+    for (int sl = 0; sl < Cout / ntile; ++sl)
+      for (int ch = 0; ch < c.Cin / 16; ++ch)
+        for (const BBand& b : g.bands)
+          for (const BTap& t : b.taps)
+            for (int kc = 0; kc < 2; ++kc)
+              for (int nn = 0; nn < ntile; ++nn)
+                for (int e = 0; e < 8; ++e) {
+                  const int ci = ch * 16 + kc * 8 + e, n = sl * ntile + nn;
+                  const float v = W[((size_t)t.orig * c.Cin + ci) * Cout + n] * (sc ? sc[n] : 1.0f);
+                  const uint16_t hi = f2bf(v);
+                  if (part == 0) w.push_back(hi);
+                  else { uint32_t u = (uint32_t)hi << 16; float hf; memcpy(&hf, &u, 4); w.push_back(f2bf(v - hf)); }
+                }
   }
   // Toeplitz packing: K index k = c*16 + kc*8 + e  <->  pixel j = k/4 of the row window, channel k%4; kw = j - 1.
-  void add_toeplitz(const std::string& name, const std::string& key, int kpix, int dw_units) {
+  // dup_lo: single-channel input stored as (hi, lo) bf16 pair in channels 0/1 -> both channels carry the channel-0 weight
+  void add_toeplitz(const std::string& name, const std::string& key, int kpix, int dw_units, bool dup_lo = false) {
     const ConvP& c = h->convs.at(key);
     BLayer L;
     L.Cout = c.Cout;
+    L.ntile = c.Cout;
     L.groups.push_back(make_group_toeplitz(c, kpix, dw_units));
     BGroup& g = L.groups[0];
     g.w_off = w.size();
@@ -112,30 +121,72 @@ struct Packer {
           for (int kc = 0; kc < 2; ++kc)
             for (int n = 0; n < c.Cout; ++n)
               for (int e = 0; e < 8; ++e) {
-                const int k = ch * 16 + kc * 8 + e, j = k / 4, ci = k % 4, kw = j - 1;
+                const int k = ch * 16 + kc * 8 + e, j = k / 4, kw = j - 1;
+                int ci = k % 4;
+                const bool lo_part = dup_lo && ci == 2;     // channel 2 = x_hi again, multiplied by the low part of W
+                if (dup_lo) ci = ci < 3 ? 0 : 99;
                 float v = 0.f;
                 if (ci < c.Cin && kw >= 0 && kw < c.kw) v = W[((size_t)(t.orig * c.kw + kw) * c.Cin + ci) * c.Cout + n] * (sc ? sc[n] : 1.0f);
-                w.push_back(f2bf(v));
+                const uint16_t hi = f2bf(v);
+                if (!lo_part) w.push_back(hi);
+                else { uint32_t u = (uint32_t)hi << 16; float hf; memcpy(&hf, &u, 4); w.push_back(f2bf(v - hf)); }
               }
     L.bias_off = bias.size();
     for (int i = 0; i < c.Cout; ++i) bias.push_back(f32[c.shift_off + i]);
     while (w.size() % 64) w.push_back(0);
     h->blayers[name] = L;
   }
-  void add(const std::string& name, const std::string& key, int sh, int sw, const std::string& ds_key = "") {
+  // split: every K group is issued three times (hi*hi, lo*hi, hi*lo), see add_split
+  void add(const std::string& name, const std::string& key, int sh, int sw, const std::string& ds_key = "", int ntile = 0, bool split = false) {
     const ConvP& c = h->convs.at(key);
     BLayer L;
     L.Cout = c.Cout;
+    L.ntile = ntile > 0 ? ntile : c.Cout;
     L.groups.push_back(make_group(c, sh, sw));
-    pack_group(L.groups[0], c);
+    pack_group(L.groups[0], c, L.ntile);
+    if (split) {
+      BGroup g1 = L.groups[0]; g1.src = 2;
+      BGroup g2 = make_group(c, sh, sw);
+      pack_group(g2, c, L.ntile, 1);
+      L.groups.push_back(g1);
+      L.groups.push_back(g2);
+    }
     L.bias_off = bias.size();
     for (int i = 0; i < c.Cout; ++i) bias.push_back(f32[c.shift_off + i]);
     if (!ds_key.empty()) {
       const ConvP& d = h->convs.at(ds_key);
-      L.groups.push_back(make_group(d, 2, 2));  // 1x1x1 stride (1,2,2) reads parity set (0,0) with zero shift
-      pack_group(L.groups[1], d);
+      const int sh_ds = ds_sh, sw_ds = ds_sw;
+      BGroup gd = make_group(d, sh_ds, sw_ds);  // 1x1 strided conv reads parity set (0,0) with zero shift
+      gd.src = 1;
+      pack_group(gd, d, L.ntile);
+      L.groups.push_back(gd);
+      if (split) {
+        BGroup g1 = gd; g1.src = 3;
+        BGroup g2 = make_group(d, sh_ds, sw_ds); g2.src = 1;
+        pack_group(g2, d, L.ntile, 1);
+        L.groups.push_back(g1);
+        L.groups.push_back(g2);
+      }
       for (int i = 0; i < c.Cout; ++i) bias[L.bias_off + i] += f32[d.shift_off + i];
     }
+    while (w.size() % 64) w.push_back(0);
+    h->blayers[name] = L;
+  }
+  // Split-bf16 ("bf16x3") layer for the token path: y = Ahi*Whi + Alo*Whi + Ahi*Wlo accumulated in one TMEM tile
+  // (three K groups), which keeps ~16 mantissa bits of both operands; the dropped Alo*Wlo term is ~2^-16 relative.
+  void add_split(const std::string& name, const std::string& key, int ntile) {
+    const ConvP& c = h->convs.at(key);
+    BLayer L;
+    L.Cout = c.Cout;
+    L.ntile = ntile;
+    BGroup g0 = make_group(c, 1, 1);
+    pack_group(g0, c, ntile, 0);
+    BGroup g1 = g0; g1.src = 2;                 // low part of the activations x the same high weights
+    BGroup g2 = make_group(c, 1, 1);
+    pack_group(g2, c, ntile, 1);                // high part of the activations x low weights
+    L.groups = {g0, g1, g2};
+    L.bias_off = bias.size();
+    for (int i = 0; i < c.Cout; ++i) bias.push_back(f32[c.shift_off + i]);
     while (w.size() % 64) w.push_back(0);
     h->blayers[name] = L;
   }
@@ -166,9 +217,10 @@ PBuf make_pbuf(int C, int sets, UcGeom g) {
 
 struct BPlan {
   Shapes s;
-  Plan f32;                               // fp32 buffers shared with the fp32 path's tail (same names)
+  Plan f32;                               // fp32 buffers (stage registry + bump allocator)
   std::map<std::string, PBuf> pb;
   size_t planar_begin = 0, planar_end = 0;
+  UcGeom gt, g33, gta;                    // token geometries: T tokens (+3 pad), T+1 tokens (rows), audio tokens (rows)
   void addp(const char* name, int C, int sets, UcGeom g) {
     PBuf b = make_pbuf(C, sets, g);
     f32.cursor = (f32.cursor + 255) & ~size_t(255);
@@ -181,36 +233,22 @@ struct BPlan {
 void build_plan(const Shapes& s, BPlan& P) {
   P.s = s;
   Plan& p = P.f32;
-  const int64_t B = s.B, T = s.T;
-  // fp32 buffers (names shared with make_plan_f32 so the fw_* helpers work on either plan)
-  p.add("vid", B * T * s.H * s.W * 3);
+  const int64_t B = s.B, T = s.T, TA = s.A4;
+  p.add("vid", B * T * s.H * s.W * 3);     // only used by the uint8-track window builder (lsd_score_windows)
   p.add("aud", B * s.F * s.Ta);
   p.add("v_feat", B * T * 256);
-  for (const char* n : {"a_stem_conv"}) p.add(n, B * s.Fs * s.As * 64);
-  for (const char* n : {"a_stem", "a_l1a", "a_layer1"}) p.add(n, B * s.F1 * s.A1 * 64);
-  for (const char* n : {"a_l2a", "a_l2d", "a_layer2"}) p.add(n, B * s.F2 * s.A2 * 128);
-  for (const char* n : {"a_l3a", "a_l3d", "a_layer3"}) p.add(n, B * s.F3 * s.A3 * 256);
-  for (const char* n : {"a_l4a", "a_l4d", "a_layer4"}) p.add(n, B * s.F4 * s.A4 * 256);
-  p.add("a_feat", B * s.A4 * 256);
+  p.add("a_feat", B * TA * 256);
   p.add("v_emb", B * T * 256);
-  p.add("a_emb", B * s.A4 * 256);
+  p.add("a_emb", B * TA * 256);
   p.add("a_int", B * T * 256);
   p.add("proj_v", B * T * 768);
   p.add("proj_a", B * T * 768);
-  p.add("att1", B * T * 256);
-  p.add("att2", B * T * 256);
   p.add("gate_in", B * T * 512);
   p.add("gate_h", B * T * 256);
-  p.add("blend", B * T * 256);
   p.add("fused", B * T * 256);
-  p.add("ms_cat", B * T * 768);
-  for (const char* n : {"tok", "tok_ln", "tok_att", "t_layer0", "t_layer3"}) p.add(n, B * (T + 1) * 256);
+  p.add("tok", B * (T + 1) * 256);
   p.add("tok_qkv", B * (T + 1) * 768);
-  p.add("tok_ff", B * (T + 1) * 1024);
   p.add("comb", B * 448);
-  p.add("art_h", B * 256);
-  p.add("feat", B * 384);
-  p.add("head_h", B * 128);
   // planar bf16 buffers
   P.planar_begin = (p.cursor + 255) & ~size_t(255);
   const int Bn = s.B, Tn = s.T;
@@ -237,6 +275,38 @@ void build_plan(const Shapes& s, BPlan& P) {
   P.addp("artd_b", 64, 1, gd);
   P.addp("hf_f", 32, 4, gh);
   P.addp("hf_b", 64, 1, gh);
+  // audio encoder: 2-D geometries (one slab per window, no temporal padding)
+  const UcGeom as = make_geom_ex(Bn, 1, s.Fs, s.As, 0, 2, 0, 0, 4);
+  auto g2d = [&](int H, int W) { return make_geom_ex(Bn, 1, H, W, 0, 1, 0, 1, 0); };
+  P.addp("xa", 8, 2, as);
+  for (const char* sfx : {"", "_lo"}) {      // audio activations are (hi, lo) bf16 pairs (split-bf16 convolutions)
+    auto nm = [&](const char* n) { return std::string(n) + sfx; };
+    P.addp(nm("sa_out").c_str(), 64, 1, as);
+    P.addp(nm("a1").c_str(), 64, 1, g2d(s.F1, s.A1));
+    P.addp(nm("a1a").c_str(), 64, 1, g2d(s.F1, s.A1));
+    P.addp(nm("ya1").c_str(), 64, 4, g2d(s.F2, s.A2));
+    P.addp(nm("a2a").c_str(), 128, 1, g2d(s.F2, s.A2));
+    P.addp(nm("ya2").c_str(), 128, 4, g2d(s.F3, s.A3));   // h-parity only (stride (2,1)): sets 0 and 2 are used
+    P.addp(nm("a3a").c_str(), 256, 1, g2d(s.F3, s.A3));
+    P.addp(nm("ya3").c_str(), 256, 4, g2d(s.F4, s.A4));
+    P.addp(nm("a4a").c_str(), 256, 1, g2d(s.F4, s.A4));
+    P.addp(nm("ya4").c_str(), 256, 1, g2d(s.F4, s.A4));
+  }
+  // token path
+  P.gt = make_geom_ex(Bn, 1, 1, Tn, 0, 0, 0, 3, 0);   // 3 zero positions before every window (conv1d k<=7)
+  P.g33 = make_geom_rows(Bn * (Tn + 1));
+  P.gta = make_geom_rows(Bn * (int)TA);
+  // every token-path GEMM operand exists as a (hi, lo) bf16 pair ("<name>" / "<name>_lo")
+  for (const char* sfx : {"", "_lo"}) {
+    auto nm = [&](const char* n) { return std::string(n) + sfx; };
+    P.addp(nm("afeat_p").c_str(), 256, 1, P.gta);
+    for (const char* n : {"vfeat_p", "vemb_p", "aint_p", "att1_p", "att2_p", "blend_p", "fused_p"}) P.addp(nm(n).c_str(), 256, 1, P.gt);
+    P.addp(nm("gatein_p").c_str(), 512, 1, P.gt);
+    P.addp(nm("mscat_p").c_str(), 768, 1, P.gt);
+    P.addp(nm("tokln_p").c_str(), 256, 1, P.g33);
+    P.addp(nm("tokatt_p").c_str(), 256, 1, P.g33);
+    P.addp(nm("tokff_p").c_str(), 1024, 1, P.g33);
+  }
   P.planar_end = p.cursor;
 }
 
@@ -246,50 +316,83 @@ struct BCtx {
   const BPlan* P;
   cudaStream_t st;
   __nv_bfloat16* base(const PBuf& b) const { return reinterpret_cast<__nv_bfloat16*>(ws + b.off); }
+  __nv_bfloat16* org(const PBuf& b) const { return base(b) + b.origin; }
+  float* f(const char* name) const { return reinterpret_cast<float*>(ws + P->f32.find(name)); }
+  const float* W(const char* key) const { return h->warena + h->vecs.at(key); }
 };
 
-// One launch of the tcgen05 kernel: layer `name`, main input `in` (+ `in_ds` for the fused downsample group),
-// output `out` (plain when out.sets == 1, parity-split when 4), optional residual (plain, output geometry).
-int run_umma(const BCtx& c, const std::string& name, const PBuf& in, const PBuf* in_ds, const PBuf& out, UcGeom og, int act,
-             const PBuf* res, float* y32 = nullptr, int y32_ld = 0) {
+struct UArgs {
+  const PBuf* in = nullptr;       // main input (planar, or pixel rows for Toeplitz layers)
+  const PBuf* in_ds = nullptr;    // input of the fused strided 1x1 downsample group
+  const PBuf* in_lo = nullptr;    // low part of the main input (split-bf16 layers)
+  const PBuf* in_ds_lo = nullptr; // low part of the downsample input
+  const PBuf* res_lo = nullptr;   // low part of the residual
+  const PBuf* yp_lo = nullptr;    // low part of the planar destination
+  UcGeom og;                      // output geometry (== flat geometry of every input band)
+  int act = ACT_NONE;
+  const PBuf* yp = nullptr;       // planar bf16 destination (plain when sets == 1, parity-split when 4)
+  int y_plane_off = 0;            // first destination plane (concatenation along channels)
+  int y_mode = -1;                // -1: derive from yp->sets
+  const PBuf* res = nullptr;      // bf16 residual (plain, output geometry)
+  float* y32 = nullptr;           // fp32 row destination
+  int y32_ld = 0, y32_outer_stride = -1, y32_row_off = 0;
+  const float* res32 = nullptr;   // fp32 row residual (compact rows)
+  int res32_ld = 0;
+};
+
+// One launch of the tcgen05 kernel for layer `name`.
+int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
   const BLayer& L = c.h->blayers.at(name);
+  const UcGeom& og = a.og;
   UmmaConvP p;
   memset(&p, 0, sizeof(p));
   p.w = reinterpret_cast<const __nv_bfloat16*>(c.h->barena);
   p.bias = c.h->bbias + L.bias_off;
-  p.Cout = L.Cout;
-  p.act = act;
+  p.Cout = L.ntile;
+  const int slices = L.Cout / L.ntile;
+  p.act = a.act;
   p.g = og;
-  if (y32) {
-    p.out_mode = UC_OUT_F32_ROWS; p.y32 = y32; p.y32_ld = y32_ld;
-  } else {
-    p.out_mode = out.sets == 4 ? UC_OUT_PARITY : UC_OUT_PLAIN;
-    p.y = c.base(out) + out.origin;
-    p.y_plane_stride = out.plane_stride; p.y_set_stride = out.set_stride;
-    p.g2 = out.g;
+  if (a.yp) {
+    p.y_mode = a.y_mode >= 0 ? a.y_mode : (a.yp->sets == 4 ? UC_Y_PARITY : UC_Y_PLAIN);
+    p.y = c.org(*a.yp) + (int64_t)a.y_plane_off * a.yp->plane_stride;
+    p.y_plane_stride = a.yp->plane_stride; p.y_set_stride = a.yp->set_stride;
+    p.g2 = a.yp->g;
+    if (a.yp_lo) p.ylo = c.org(*a.yp_lo) + (int64_t)a.y_plane_off * a.yp_lo->plane_stride;
   }
-  if (res) { p.res = c.base(*res) + res->origin; p.res_plane_stride = res->plane_stride; }
-  // tile shape: all Cout columns x MT M-tiles in TMEM (512 columns)
-  p.MT = L.Cout <= 64 ? 4 : 2;
+  if (a.y32) {
+    p.y32 = a.y32; p.y32_ld = a.y32_ld;
+    p.y32_outer_stride = a.y32_outer_stride >= 0 ? a.y32_outer_stride : og.W;
+    p.y32_row_off = a.y32_row_off;
+  }
+  if (a.res) { p.res = c.org(*a.res); p.res_plane_stride = a.res->plane_stride; }
+  if (a.res_lo) p.res_lo = c.org(*a.res_lo);
+  if (a.res32) { p.res32 = a.res32; p.res32_ld = a.res32_ld; }
+  // tile shape: MT M-tiles x ntile columns in TMEM; shrink MT until the grid fills the SMs
+  p.MT = L.ntile <= 64 ? 4 : 2;
+  const int mt_min = L.ntile > 64 ? 2 : 1;  // wide tiles re-read all weights per CTA: keep two M-tiles per weight load
+  while (p.MT > mt_min && ((og.P_total + p.MT * 128 - 1) / (p.MT * 128)) * slices < c.h->num_sms) p.MT /= 2;
   uint32_t cols = 32;
-  while ((int)cols < p.MT * L.Cout) cols *= 2;
+  while ((int)cols < p.MT * L.ntile) cols *= 2;
   p.tmem_cols = cols;
   const int S = p.MT * 128;
-  int nb = 0, max_extra = 0, max_taps = 0;
+  int nb = 0, max_a = 0, max_taps = 0;
   p.ngroups = (int)L.groups.size();
   for (int gi = 0; gi < p.ngroups; ++gi) {
     const BGroup& G = L.groups[gi];
-    const PBuf& src = (gi == 0) ? in : *in_ds;
+    const PBuf* srcp = G.src == 0 ? a.in : (G.src == 1 ? a.in_ds : (G.src == 2 ? a.in_lo : a.in_ds_lo));
+    if (!srcp) return lsd_fail(c.h, LSD_ERR_ARG, "%s: missing input for group %d", name.c_str(), gi);
+    const PBuf& src = *srcp;
     UcGroup& ug = p.groups[gi];
     ug.band_begin = nb;
     ug.k16 = G.k16;
     ug.taps_total = G.taps_total;
     ug.w_off = (int64_t)G.w_off;
+    ug.slice_stride = (int64_t)G.slice_stride;
     int tap_begin = 0;
     for (const BBand& b : G.bands) {
       if (nb >= UC_MAX_BANDS) return lsd_fail(c.h, LSD_ERR_UNSUPPORTED, "%s: too many bands", name.c_str());
       UcBand& ub = p.bands[nb++];
-      ub.base = c.base(src) + (int64_t)b.set * src.set_stride + src.origin;
+      ub.base = c.org(src) + (int64_t)b.set * src.set_stride;
       ub.plane_stride = src.plane_stride;
       ub.toeplitz = G.toeplitz;
       ub.chunk_stride = G.toeplitz ? 16 : 2 * src.plane_stride;
@@ -304,28 +407,58 @@ int run_umma(const BCtx& c, const std::string& name, const PBuf& in, const PBuf*
       ub.tap_begin = tap_begin;
       for (int j = 0; j < ub.ntaps; ++j) ub.rel[j] = b.taps[j].dt * og.SL + b.taps[j].dh * og.RW + b.taps[j].dw - mn;
       tap_begin += ub.ntaps;
-      max_extra = std::max(max_extra, ub.len_extra + ub.toeplitz);
+      max_a = std::max(max_a, (G.toeplitz ? 1 : 2) * (S + ub.len_extra + ub.toeplitz) * 16);
       max_taps = std::max(max_taps, ub.ntaps);
       // the band must stay inside the guard zones of the source buffer
-      if (-(int64_t)ub.start * 8 > src.origin) return lsd_fail(c.h, LSD_ERR_UNSUPPORTED, "%s: front guard too small", name.c_str());
+      if (-(int64_t)ub.start * 8 > src.origin || (int64_t)(mx + TILE_MAX) * 8 > src.origin + (int64_t)TILE_MAX * 8)
+        return lsd_fail(c.h, LSD_ERR_UNSUPPORTED, "%s: guard zone too small", name.c_str());
     }
     ug.band_end = nb;
   }
   p.nbands = nb;
-  p.a_stage_bytes = ((uint32_t)(2 * (S + max_extra) * 16) + 127u) & ~127u;
-  p.w_stage_bytes = (uint32_t)(max_taps * L.Cout * 32);
+  p.a_stage_bytes = ((uint32_t)max_a + 127u) & ~127u;
+  p.w_stage_bytes = (uint32_t)(max_taps * L.ntile * 32);
   const uint32_t stage = p.a_stage_bytes + p.w_stage_bytes;
   const uint32_t budget = (cols <= 256 ? 110u : 218u) * 1024u;
   int stages = (int)(budget / stage);
-  stages = std::max(2, std::min(stages, 6));
+  stages = std::max(2, std::min(stages, 8));
   if ((size_t)stages * stage + 1024 > 224u * 1024u) return lsd_fail(c.h, LSD_ERR_UNSUPPORTED, "%s: stage of %u bytes does not fit", name.c_str(), stage);
   p.stages = stages;
   double kflop = 0;
   for (const BGroup& G : L.groups) kflop += (double)G.taps_total * G.Cin;
   if (L.groups[0].toeplitz) { const ConvP& cp = c.h->convs.at(name); kflop = (double)cp.kt * cp.kh * cp.kw * cp.Cin; }  // algorithmic K, not the padded one
   c.h->prof.begin(c.st, 2.0 * (double)og.N * og.T * og.H * og.W * L.Cout * kflop, 2);
-  launch_umma_conv(p, c.st);
+  launch_umma_conv(p, slices, c.st);
   c.h->prof.end(c.st);
+  return 0;
+}
+
+#define RUN(name, ...)                            \
+  do {                                            \
+    UArgs a_;                                     \
+    __VA_ARGS__;                                  \
+    if ((rc = run_umma(b, name, a_))) return rc;  \
+  } while (0)
+
+PlanarOut pout(const BCtx& c, const PBuf& p, const PBuf* lo = nullptr, int plane_off = 0) {
+  PlanarOut o;
+  o.y = c.org(p) + (int64_t)plane_off * p.plane_stride;
+  o.ylo = lo ? c.org(*lo) + (int64_t)plane_off * lo->plane_stride : nullptr;
+  o.plane_stride = p.plane_stride;
+  if (p.g.ow > 0 && p.g.HP == 1) { o.grp = p.g.W; o.grp_stride = p.g.RW; o.off = p.g.ow; }   // padded token geometry
+  else { o.grp = 0; o.grp_stride = 0; o.off = 0; }                                            // plain rows
+  return o;
+}
+
+// Residual stage: conv1 (+ReLU) -> conv2 (+fused strided 1x1 downsample | +identity) -> ReLU
+int res_stage_umma(const BCtx& b, const std::string& p, const PBuf& x, const PBuf& mid, const PBuf& y, bool has_ds, int y_mode,
+                   const PBuf* x_lo = nullptr, const PBuf* mid_lo = nullptr, const PBuf* y_lo = nullptr) {
+  int rc = 0;
+  RUN(p + ".conv1", a_.in = &x; a_.in_lo = x_lo; a_.og = mid.g; a_.act = ACT_RELU; a_.yp = &mid; a_.yp_lo = mid_lo);
+  if (has_ds) RUN(p + ".conv2", a_.in = &mid; a_.in_lo = mid_lo; a_.in_ds = &x; a_.in_ds_lo = x_lo; a_.og = mid.g; a_.act = ACT_RELU;
+                  a_.yp = &y; a_.yp_lo = y_lo; a_.y_mode = y_mode);
+  else RUN(p + ".conv2", a_.in = &mid; a_.in_lo = mid_lo; a_.og = mid.g; a_.act = ACT_RELU; a_.yp = &y; a_.yp_lo = y_lo; a_.y_mode = y_mode;
+           a_.res = &x; a_.res_lo = x_lo);
   return 0;
 }
 
@@ -334,10 +467,12 @@ int run_umma(const BCtx& c, const std::string& name, const PBuf& in, const PBuf*
 int pack_bf16_weights(lsd_handle* h, const std::vector<float>& f32_arena) {
   Packer P{h, f32_arena, {}, {}};
   h->blayers.clear();
+  const int vstr[4] = {1, 2, 2, 2};
   for (int l = 1; l <= 4; ++l) {
     const std::string p = "visual_encoder.layer" + std::to_string(l);
-    const int s = l == 1 ? 1 : 2;
+    const int s = vstr[l - 1];
     P.add(p + ".conv1", p + ".conv1", s, s);
+    P.ds_sh = 2; P.ds_sw = 2;
     P.add(p + ".conv2", p + ".conv2", 1, 1, l == 1 ? "" : p + ".downsample");
   }
   P.add_toeplitz("visual_encoder.stem", "visual_encoder.stem", 8, 0);  // 7 taps in w -> 8-pixel window starting at 2*wo-4
@@ -345,6 +480,23 @@ int pack_bf16_weights(lsd_handle* h, const std::vector<float>& f32_arena) {
   P.add("art.td0", "art.td0", 1, 1);
   P.add("art.td3", "art.td3", 1, 1);
   P.add("art.hf3", "art.hf3", 2, 2);
+  // audio encoder (audio_encoder.py:128-156): strides (1,1), (2,2), (2,1), (2,1)
+  P.add_toeplitz("audio_encoder.stem", "audio_encoder.stem", 8, 0, true);
+  const int ash[4] = {1, 2, 2, 2}, asw[4] = {1, 2, 1, 1};
+  for (int l = 1; l <= 4; ++l) {
+    const std::string p = "audio_encoder.layer" + std::to_string(l);
+    // split-bf16: the audio encoder is 1.4 % of the FLOPs but its bf16 rounding dominated the logit error
+    P.add(p + ".conv1", p + ".conv1", ash[l - 1], asw[l - 1], "", 0, true);
+    P.ds_sh = ash[l - 1]; P.ds_sw = asw[l - 1];
+    P.add(p + ".conv2", p + ".conv2", 1, 1, l == 1 ? "" : p + ".downsample", 0, true);
+  }
+  // token path GEMMs: 64-column slices so that the small M (B*T rows) still spreads over the SMs
+  for (const char* k : {"projection.visual_proj", "projection.audio_proj", "cross.in_v", "cross.in_a", "cross.v2a.out", "cross.a2v.out",
+                        "cross.gate0", "cross.fuse", "temporal.branch_k3", "temporal.branch_k5", "temporal.branch_k7",
+                        "temporal.pre_scale_proj"})
+    P.add_split(k, k, 64);
+  for (int l = 0; l < 4; ++l)
+    for (const char* k : {".in", ".out", ".ff1", ".ff2"}) P.add_split("t" + std::to_string(l) + k, "t" + std::to_string(l) + k, 64);
   if (h->barena) { cudaFree(h->barena); h->barena = nullptr; }
   if (h->bbias) { cudaFree(h->bbias); h->bbias = nullptr; }
   cudaError_t e = cudaMalloc(&h->barena, P.w.size() * 2);
@@ -378,52 +530,111 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
     if (e != cudaSuccess) return lsd_fail(h, LSD_ERR_CUDA, "workspace init: %s", cudaGetErrorString(e));
     h->ws_sig_ptr = ws; h->ws_sig_bytes = ws_bytes; memcpy(h->ws_sig_shape, sig, sizeof(sig));
   }
-  Ctx c{h, ws, &P.f32, st};
   BCtx b{h, ws, &P, st};
-  const int B = s.B, T = s.T;
-  if (!inputs_ready) launch_cast_to_f32(audio, adt, c.buf("aud"), (int64_t)B * s.F * s.Ta, 1.0f, st);
+  const int B = s.B, T = s.T, TA = s.A4, NT = T + 1;
   auto& pb = P.pb;
   int rc = 0;
   // ---- video -> bf16 pixel rows (+ per-frame laplacian conv), stem conv on tcgen05 (Toeplitz K), max-pool in planar layout
   const PBuf &xs = pb["xs"], &xl = pb["xl"], &so = pb["s_out"], &x1 = pb["x1"];
-  if (inputs_ready) launch_video_rows(c.buf("vid"), LSD_F32, LSD_NDHWC, h->warena + h->convs.at("art.lap").w_off, b.base(xs) + xs.origin,
-                                      b.base(xl) + xl.origin, xs.set_stride, xs.g, s.H, s.W, st);
-  else launch_video_rows(video, vdt, vlayout, h->warena + h->convs.at("art.lap").w_off, b.base(xs) + xs.origin, b.base(xl) + xl.origin,
-                         xs.set_stride, xs.g, s.H, s.W, st);
-  if ((rc = run_umma(b, "visual_encoder.stem", xs, nullptr, so, xs.g, ACT_RELU, nullptr))) return rc;
-  launch_planar_maxpool(b.base(so) + so.origin, so.plane_stride, so.g, b.base(x1) + x1.origin, x1.plane_stride, x1.g, 64, st);
-  // ---- residual stages on tcgen05 (visual_encoder.py:81-87, 133-152)
-  if ((rc = run_umma(b, "visual_encoder.layer1.conv1", x1, nullptr, pb["l1a"], x1.g, ACT_RELU, nullptr))) return rc;
-  if ((rc = run_umma(b, "visual_encoder.layer1.conv2", pb["l1a"], nullptr, pb["y1"], x1.g, ACT_RELU, &x1))) return rc;
-  if ((rc = run_umma(b, "visual_encoder.layer2.conv1", pb["y1"], nullptr, pb["l2a"], pb["l2a"].g, ACT_RELU, nullptr))) return rc;
-  if ((rc = run_umma(b, "visual_encoder.layer2.conv2", pb["l2a"], &pb["y1"], pb["y2"], pb["l2a"].g, ACT_RELU, nullptr))) return rc;
-  if ((rc = run_umma(b, "visual_encoder.layer3.conv1", pb["y2"], nullptr, pb["l3a"], pb["l3a"].g, ACT_RELU, nullptr))) return rc;
-  if ((rc = run_umma(b, "visual_encoder.layer3.conv2", pb["l3a"], &pb["y2"], pb["y3"], pb["l3a"].g, ACT_RELU, nullptr))) return rc;
-  if ((rc = run_umma(b, "visual_encoder.layer4.conv1", pb["y3"], nullptr, pb["l4a"], pb["l4a"].g, ACT_RELU, nullptr))) return rc;
-  if ((rc = run_umma(b, "visual_encoder.layer4.conv2", pb["l4a"], &pb["y3"], pb["y4"], pb["l4a"].g, ACT_RELU, nullptr))) return rc;
+  const float* lapw = h->warena + h->convs.at("art.lap").w_off;
+  if (inputs_ready) launch_video_rows(b.f("vid"), LSD_F32, LSD_NDHWC, lapw, b.org(xs), b.org(xl), xs.set_stride, xs.g, s.H, s.W, st);
+  else launch_video_rows(video, vdt, vlayout, lapw, b.org(xs), b.org(xl), xs.set_stride, xs.g, s.H, s.W, st);
+  RUN("visual_encoder.stem", a_.in = &xs; a_.og = xs.g; a_.act = ACT_RELU; a_.yp = &so);
+  launch_planar_maxpool(b.org(so), so.plane_stride, so.g, b.org(x1), x1.plane_stride, x1.g, 64, st);
+  // ---- residual stages (visual_encoder.py:81-87, 133-152)
+  if ((rc = res_stage_umma(b, "visual_encoder.layer1", x1, pb["l1a"], pb["y1"], false, UC_Y_PARITY))) return rc;
+  if ((rc = res_stage_umma(b, "visual_encoder.layer2", pb["y1"], pb["l2a"], pb["y2"], true, UC_Y_PARITY))) return rc;
+  if ((rc = res_stage_umma(b, "visual_encoder.layer3", pb["y2"], pb["l3a"], pb["y3"], true, UC_Y_PARITY))) return rc;
+  if ((rc = res_stage_umma(b, "visual_encoder.layer4", pb["y3"], pb["l4a"], pb["y4"], true, UC_Y_PLAIN))) return rc;
   const PBuf& y4 = pb["y4"];
-  launch_planar_mean(b.base(y4) + y4.origin, y4.plane_stride, y4.g, 256, c.buf("v_feat"), 256, 0, st);  // spatial mean -> tokens
-  // ---- audio encoder + token path (fp32 kernels)
-  fw_audio_f32(c, s);
-  fw_tokens_f32(c, s);
-  float* comb = c.buf("comb");
+  // spatial mean -> visual tokens (fp32 stage + planar GEMM input)
+  launch_planar_mean2(b.org(y4), y4.plane_stride, y4.g, 256, b.f("v_feat"), 256, 0, pout(b, pb["vfeat_p"], &pb["vfeat_p_lo"]), st);
+  // ---- audio encoder (audio_encoder.py:173-205) on tcgen05
+  const PBuf &xa = pb["xa"], &sao = pb["sa_out"], &a1 = pb["a1"];
+  if (inputs_ready) launch_audio_rows(b.f("aud"), LSD_F32, b.org(xa), xa.set_stride, xa.g, s.F, s.Ta, st);
+  else launch_audio_rows(audio, adt, b.org(xa), xa.set_stride, xa.g, s.F, s.Ta, st);
+  RUN("audio_encoder.stem", a_.in = &xa; a_.og = xa.g; a_.act = ACT_RELU; a_.yp = &sao; a_.yp_lo = &pb["sa_out_lo"]);
+  launch_planar_maxpool(b.org(sao), sao.plane_stride, sao.g, b.org(a1), a1.plane_stride, a1.g, 64, st, b.org(pb["sa_out_lo"]), b.org(pb["a1_lo"]));
+  if ((rc = res_stage_umma(b, "audio_encoder.layer1", a1, pb["a1a"], pb["ya1"], false, UC_Y_PARITY, &pb["a1_lo"], &pb["a1a_lo"], &pb["ya1_lo"]))) return rc;
+  if ((rc = res_stage_umma(b, "audio_encoder.layer2", pb["ya1"], pb["a2a"], pb["ya2"], true, UC_Y_PARITY_H, &pb["ya1_lo"], &pb["a2a_lo"], &pb["ya2_lo"]))) return rc;
+  if ((rc = res_stage_umma(b, "audio_encoder.layer3", pb["ya2"], pb["a3a"], pb["ya3"], true, UC_Y_PARITY_H, &pb["ya2_lo"], &pb["a3a_lo"], &pb["ya3_lo"]))) return rc;
+  if ((rc = res_stage_umma(b, "audio_encoder.layer4", pb["ya3"], pb["a4a"], pb["ya4"], true, UC_Y_PLAIN, &pb["ya3_lo"], &pb["a4a_lo"], &pb["ya4_lo"]))) return rc;
+  const PBuf& ya4 = pb["ya4"];
+  launch_planar_mean2(b.org(ya4), ya4.plane_stride, ya4.g, 256, b.f("a_feat"), 256, 2, pout(b, pb["afeat_p"], &pb["afeat_p_lo"]), st,
+                      b.org(pb["ya4_lo"]));  // mean over F'
+  // ---- projection (fusion_module.py:108-124)
+  const UcGeom gt = P.gt;
+  RUN("projection.visual_proj", a_.in = &pb["vfeat_p"]; a_.in_lo = &pb["vfeat_p_lo"]; a_.og = gt; a_.yp = &pb["vemb_p"]; a_.yp_lo = &pb["vemb_p_lo"]; a_.y32 = b.f("v_emb"); a_.y32_ld = 256);
+  RUN("projection.audio_proj", a_.in = &pb["afeat_p"]; a_.in_lo = &pb["afeat_p_lo"]; a_.og = P.gta; a_.y32 = b.f("a_emb"); a_.y32_ld = 256);
+  // ---- cross-modal attention + gated fusion (fusion_module.py:54-87)
+  launch_lerp_tokens_p(b.f("a_emb"), b.f("a_int"), B, TA, T, 256, pout(b, pb["aint_p"], &pb["aint_p_lo"]), st);
+  float *pv = b.f("proj_v"), *pa = b.f("proj_a"), *gi = b.f("gate_in");
+  RUN("cross.in_v", a_.in = &pb["vemb_p"]; a_.in_lo = &pb["vemb_p_lo"]; a_.og = gt; a_.y32 = pv; a_.y32_ld = 768);
+  RUN("cross.in_a", a_.in = &pb["aint_p"]; a_.in_lo = &pb["aint_p_lo"]; a_.og = gt; a_.y32 = pa; a_.y32_ld = 768);
+  launch_mha_core_p(pv, 768, pa + 256, 768, pa + 512, 768, B, T, T, 8, pout(b, pb["att1_p"], &pb["att1_p_lo"]), st);  // v2a: Q=v, K/V=a
+  launch_mha_core_p(pa, 768, pv + 256, 768, pv + 512, 768, B, T, T, 8, pout(b, pb["att2_p"], &pb["att2_p_lo"]), st);  // a2v: Q=a, K/V=v
+  RUN("cross.v2a.out", a_.in = &pb["att1_p"]; a_.in_lo = &pb["att1_p_lo"]; a_.og = gt; a_.res32 = b.f("v_emb"); a_.res32_ld = 256; a_.y32 = gi; a_.y32_ld = 512;
+      a_.yp = &pb["gatein_p"]; a_.yp_lo = &pb["gatein_p_lo"]);
+  RUN("cross.a2v.out", a_.in = &pb["att2_p"]; a_.in_lo = &pb["att2_p_lo"]; a_.og = gt; a_.res32 = b.f("a_int"); a_.res32_ld = 256; a_.y32 = gi + 256; a_.y32_ld = 512;
+      a_.yp = &pb["gatein_p"]; a_.yp_lo = &pb["gatein_p_lo"]; a_.y_plane_off = 32);
+  RUN("cross.gate0", a_.in = &pb["gatein_p"]; a_.in_lo = &pb["gatein_p_lo"]; a_.og = gt; a_.act = ACT_GELU; a_.y32 = b.f("gate_h"); a_.y32_ld = 256);
+  launch_gate_blend_p(b.f("gate_h"), b.W("cross.gate2.w"), b.W("cross.gate2.b"), gi, 512, gi + 256, 512, B * T, 256, pout(b, pb["blend_p"], &pb["blend_p_lo"]), st);
+  RUN("cross.fuse", a_.in = &pb["blend_p"]; a_.in_lo = &pb["blend_p_lo"]; a_.og = gt; a_.act = ACT_RELU; a_.y32 = b.f("fused"); a_.y32_ld = 256; a_.yp = &pb["fused_p"]; a_.yp_lo = &pb["fused_p_lo"]);
+  // ---- temporal transformer (temporal.py:79-111)
+  RUN("temporal.branch_k3", a_.in = &pb["fused_p"]; a_.in_lo = &pb["fused_p_lo"]; a_.og = gt; a_.act = ACT_GELU; a_.yp = &pb["mscat_p"]; a_.yp_lo = &pb["mscat_p_lo"]; a_.y_plane_off = 0);
+  RUN("temporal.branch_k5", a_.in = &pb["fused_p"]; a_.in_lo = &pb["fused_p_lo"]; a_.og = gt; a_.act = ACT_GELU; a_.yp = &pb["mscat_p"]; a_.yp_lo = &pb["mscat_p_lo"]; a_.y_plane_off = 32);
+  RUN("temporal.branch_k7", a_.in = &pb["fused_p"]; a_.in_lo = &pb["fused_p_lo"]; a_.og = gt; a_.act = ACT_GELU; a_.yp = &pb["mscat_p"]; a_.yp_lo = &pb["mscat_p_lo"]; a_.y_plane_off = 64);
+  float* tok = b.f("tok");
+  launch_set_cls(b.W("temporal.cls"), tok, B, NT, 256, st);
+  // pre_scale_proj + residual, written straight into token rows 1..T of each window
+  RUN("temporal.pre_scale_proj", a_.in = &pb["mscat_p"]; a_.in_lo = &pb["mscat_p_lo"]; a_.og = gt; a_.res32 = b.f("fused"); a_.res32_ld = 256; a_.y32 = tok; a_.y32_ld = 256;
+      a_.y32_outer_stride = NT; a_.y32_row_off = 1);
+  const UcGeom g33 = P.g33;
+  for (int l = 0; l < 4; ++l) {
+    const std::string k = "t" + std::to_string(l);
+    launch_layernorm_p(tok, 256, b.W((k + ".ln1.w").c_str()), b.W((k + ".ln1.b").c_str()), B * NT, 256, pout(b, pb["tokln_p"], &pb["tokln_p_lo"]), st);
+    RUN(k + ".in", a_.in = &pb["tokln_p"]; a_.in_lo = &pb["tokln_p_lo"]; a_.og = g33; a_.y32 = b.f("tok_qkv"); a_.y32_ld = 768);
+    const float* qkv = b.f("tok_qkv");
+    launch_mha_core_p(qkv, 768, qkv + 256, 768, qkv + 512, 768, B, NT, NT, 8, pout(b, pb["tokatt_p"], &pb["tokatt_p_lo"]), st);
+    RUN(k + ".out", a_.in = &pb["tokatt_p"]; a_.in_lo = &pb["tokatt_p_lo"]; a_.og = g33; a_.res32 = tok; a_.res32_ld = 256; a_.y32 = tok; a_.y32_ld = 256);
+    launch_layernorm_p(tok, 256, b.W((k + ".ln2.w").c_str()), b.W((k + ".ln2.b").c_str()), B * NT, 256, pout(b, pb["tokln_p"], &pb["tokln_p_lo"]), st);
+    RUN(k + ".ff1", a_.in = &pb["tokln_p"]; a_.in_lo = &pb["tokln_p_lo"]; a_.og = g33; a_.act = ACT_GELU; a_.yp = &pb["tokff_p"]; a_.yp_lo = &pb["tokff_p_lo"]);
+    RUN(k + ".ff2", a_.in = &pb["tokff_p"]; a_.in_lo = &pb["tokff_p_lo"]; a_.og = g33; a_.res32 = tok; a_.res32_ld = 256; a_.y32 = tok; a_.y32_ld = 256);
+  }
+  // cls = tok[:,0]: no final norm (temporal.py:110-111)
+  float* comb = b.f("comb");
+  launch_copy_rows(tok, (int64_t)NT * 256, comb, 448, B, 256, st);
   // ---- artifact detector (artifact_detector.py:149-183)
-  if ((rc = run_umma(b, "art.td0", y4, nullptr, pb["art_a"], y4.g, ACT_RELU, nullptr))) return rc;
-  if ((rc = run_umma(b, "art.td3", pb["art_a"], nullptr, pb["art_b"], y4.g, ACT_RELU, nullptr))) return rc;
-  launch_planar_mean(b.base(pb["art_b"]) + pb["art_b"].origin, pb["art_b"].plane_stride, y4.g, 64, comb + 256, 448, 1, st);
+  PlanarOut none{nullptr, nullptr, 0, 0, 0, 0};
+  RUN("art.td0", a_.in = &y4; a_.og = y4.g; a_.act = ACT_RELU; a_.yp = &pb["art_a"]);
+  RUN("art.td3", a_.in = &pb["art_a"]; a_.og = y4.g; a_.act = ACT_RELU; a_.yp = &pb["art_b"]);
+  launch_planar_mean2(b.org(pb["art_b"]), pb["art_b"].plane_stride, y4.g, 64, comb + 256, 448, 1, none, st);
   const PBuf& dl = pb["delta"];
-  if (T > 1) launch_planar_delta(b.base(y4) + y4.origin, y4.plane_stride, y4.g, b.base(dl) + dl.origin, dl.plane_stride, dl.g, 256, st);
+  if (T > 1) launch_planar_delta(b.org(y4), y4.plane_stride, y4.g, b.org(dl), dl.plane_stride, dl.g, 256, st);
   // (T == 1: the delta map is all zeros — the buffer is never written and keeps its zero initialisation)
-  if ((rc = run_umma(b, "art.td0", dl, nullptr, pb["artd_a"], dl.g, ACT_RELU, nullptr))) return rc;
-  if ((rc = run_umma(b, "art.td3", pb["artd_a"], nullptr, pb["artd_b"], dl.g, ACT_RELU, nullptr))) return rc;
-  launch_planar_mean(b.base(pb["artd_b"]) + pb["artd_b"].origin, pb["artd_b"].plane_stride, dl.g, 64, comb + 320, 448, 1, st);
+  RUN("art.td0", a_.in = &dl; a_.og = dl.g; a_.act = ACT_RELU; a_.yp = &pb["artd_a"]);
+  RUN("art.td3", a_.in = &pb["artd_a"]; a_.og = dl.g; a_.act = ACT_RELU; a_.yp = &pb["artd_b"]);
+  launch_planar_mean2(b.org(pb["artd_b"]), pb["artd_b"].plane_stride, dl.g, 64, comb + 320, 448, 1, none, st);
   // high-frequency branch: Conv3d 3->32 s(1,2,2) on the laplacian pixel rows (Toeplitz K), Conv3d 32->64 s(1,2,2) planar
   const PBuf& hf = pb["hf_f"];
-  if ((rc = run_umma(b, "art.hf0", xl, nullptr, hf, xl.g, ACT_RELU, nullptr))) return rc;
-  if ((rc = run_umma(b, "art.hf3", hf, nullptr, pb["hf_b"], hf.g, ACT_RELU, nullptr))) return rc;
-  launch_planar_mean(b.base(pb["hf_b"]) + pb["hf_b"].origin, pb["hf_b"].plane_stride, hf.g, 64, comb + 384, 448, 1, st);
-  // ---- fusion MLP + head (fp32)
-  fw_head_f32(c, s, logits, aux);
+  RUN("art.hf0", a_.in = &xl; a_.og = xl.g; a_.act = ACT_RELU; a_.yp = &hf);
+  RUN("art.hf3", a_.in = &hf; a_.og = hf.g; a_.act = ACT_RELU; a_.yp = &pb["hf_b"]);
+  launch_planar_mean2(b.org(pb["hf_b"]), pb["hf_b"].plane_stride, hf.g, 64, comb + 384, 448, 1, none, st);
+  // ---- artifact fusion MLP + classification head, fused, fp32 (artifact_detector.py:142-147,180-181; classifier.py:14-34)
+  HeadW hw;
+  auto cw = [&](const char* key) { return h->warena + h->convs.at(key).w_off; };
+  auto cb = [&](const char* key) { return h->warena + h->convs.at(key).shift_off; };
+  hw.w0 = cw("art.fuse0"); hw.b0 = cb("art.fuse0"); hw.w2 = cw("art.fuse2"); hw.b2 = cb("art.fuse2");
+  hw.wc = cw("head.fc0"); hw.bc = cb("head.fc0");
+  hw.lng = b.W("head.ln.w"); hw.lnb = b.W("head.ln.b"); hw.wo = b.W("head.out.w"); hw.bo = b.W("head.out.b");
+  launch_head(comb, hw, logits, B, st);
+  if (aux) {
+    const size_t tb = (size_t)B * T * 256 * sizeof(float);
+    if (aux->visual_tokens) cudaMemcpyAsync(aux->visual_tokens, b.f("v_emb"), tb, cudaMemcpyDeviceToDevice, st);
+    if (aux->audio_tokens) cudaMemcpyAsync(aux->audio_tokens, b.f("a_emb"), (size_t)B * TA * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (aux->fused_tokens) cudaMemcpyAsync(aux->fused_tokens, b.f("fused"), tb, cudaMemcpyDeviceToDevice, st);
+    if (aux->cls_output) launch_copy_rows(tok, (int64_t)NT * 256, aux->cls_output, 256, B, 256, st);
+  }
   return 0;
 }
 
@@ -445,8 +656,8 @@ int score_batch_bf16(lsd_handle* h, const uint8_t* track, int n_frames, const in
   BPlan P;
   build_plan(s, P);
   if (P.f32.cursor > ws_bytes) return lsd_fail(h, LSD_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", P.f32.cursor, ws_bytes);
-  Ctx c{h, ws, &P.f32, st};
-  launch_gather_windows_u8(track, n_frames, d_vstarts, c.buf("vid"), nb, T, H * W * 3, st);
-  launch_gather_audio(mel_full, F, Ta_full, d_astarts, c.buf("aud"), nb, Ta, st);
+  BCtx b{h, ws, &P, st};
+  launch_gather_windows_u8(track, n_frames, d_vstarts, b.f("vid"), nb, T, H * W * 3, st);
+  launch_gather_audio(mel_full, F, Ta_full, d_astarts, b.f("aud"), nb, Ta, st);
   return forward_bf16_impl(h, s, logits, nullptr, ws, ws_bytes, st, true, nullptr, 0, 0, nullptr, 0);
 }

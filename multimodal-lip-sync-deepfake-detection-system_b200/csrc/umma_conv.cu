@@ -12,6 +12,7 @@
 //   tcgen05.commit releases the stage; the last commit signals the epilogue.
 // Epilogue (all 4 warps): tcgen05.ld -> +bias (+residual) -> act -> zero pads -> bf16 -> 16 B coalesced stores per plane.
 #include "umma_conv.cuh"
+#include "token_kernels.cuh"
 
 #include "lsd_kernels.h"
 #include "umma.cuh"
@@ -57,7 +58,8 @@ __global__ void __launch_bounds__(128) umma_conv_kernel(const __grid_constant__ 
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc(&tmem_base_s, p.tmem_cols); tmem_relinquish(); }
-  for (int i = tid; i < p.Cout; i += 128) bias_s[i] = p.bias ? p.bias[i] : 0.0f;
+  const int slice = blockIdx.y, ch0 = slice * p.Cout;
+  for (int i = tid; i < p.Cout; i += 128) bias_s[i] = p.bias ? p.bias[ch0 + i] : 0.0f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -82,7 +84,8 @@ __global__ void __launch_bounds__(128) umma_conv_kernel(const __grid_constant__ 
           const __nv_bfloat16* src = bd.base + (int64_t)c * bd.chunk_stride + (P0 + bd.start) * 8;
           bulk_g2s(sa, src, bytesA, &full_bar[stage]);
           if (!bd.toeplitz) bulk_g2s(sa + bytesA, src + bd.plane_stride, bytesA, &full_bar[stage]);
-          const __nv_bfloat16* wsrc = p.w + g.w_off + ((int64_t)c * g.taps_total + bd.tap_begin) * (int64_t)p.Cout * 16;
+          const __nv_bfloat16* wsrc = p.w + g.w_off + (int64_t)slice * g.slice_stride +
+                                      ((int64_t)c * g.taps_total + bd.tap_begin) * (int64_t)p.Cout * 16;
           bulk_g2s(sa + p.a_stage_bytes, wsrc, bytesW, &full_bar[stage]);
         }
       }
@@ -127,12 +130,13 @@ __global__ void __launch_bounds__(128) umma_conv_kernel(const __grid_constant__ 
     int n, t, h, w;
     const bool valid = uc_decode(p.g, P, n, t, h, w);
     const bool inrange = P < p.g.P_total;
+    const int64_t outer = valid ? ((int64_t)n * p.g.T + t) * p.g.H + h : 0;
     int64_t dst = P * 8;
-    if (p.out_mode == UC_OUT_PARITY && valid) {
+    if (valid && p.y_mode == UC_Y_PARITY)
       dst = (int64_t)((h & 1) * 2 + (w & 1)) * p.y_set_stride + uc_flat(p.g2, n, t, h >> 1, w >> 1) * 8;
-    } else if (p.out_mode == UC_OUT_F32_ROWS && valid) {
-      dst = ((((int64_t)n * p.g.T + t) * p.g.H + h) * p.g.W + w) * p.y32_ld;
-    }
+    else if (valid && p.y_mode == UC_Y_PARITY_H)
+      dst = (int64_t)((h & 1) * 2) * p.y_set_stride + uc_flat(p.g2, n, t, h >> 1, w) * 8;
+    const bool store_planar = (p.y_mode == UC_Y_PLAIN && inrange) || (p.y_mode >= UC_Y_PARITY && valid);
     for (int c0 = 0; c0 < p.Cout; c0 += 32) {
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(m * p.Cout + c0), v);
@@ -143,7 +147,7 @@ __global__ void __launch_bounds__(128) umma_conv_kernel(const __grid_constant__ 
         if (p.res) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint4 r = *reinterpret_cast<const uint4*>(p.res + (int64_t)(c0 / 8 + q) * p.res_plane_stride + P * 8);
+            const uint4 r = *reinterpret_cast<const uint4*>(p.res + (int64_t)((ch0 + c0) / 8 + q) * p.res_plane_stride + P * 8);
             const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&r);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -151,28 +155,55 @@ __global__ void __launch_bounds__(128) umma_conv_kernel(const __grid_constant__ 
               v[q * 8 + 2 * e] += f.x;
               v[q * 8 + 2 * e + 1] += f.y;
             }
+            if (p.res_lo) {
+              const uint4 rl = *reinterpret_cast<const uint4*>(p.res_lo + (int64_t)((ch0 + c0) / 8 + q) * p.res_plane_stride + P * 8);
+              const __nv_bfloat162* rlb = reinterpret_cast<const __nv_bfloat162*>(&rl);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(rlb[e]);
+                v[q * 8 + 2 * e] += f.x;
+                v[q * 8 + 2 * e + 1] += f.y;
+              }
+            }
+          }
+        }
+        if (p.res32) {
+          const float4* r4 = reinterpret_cast<const float4*>(p.res32 + (outer * p.g.W + w) * p.res32_ld + ch0 + c0);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 f = r4[q];
+            v[4 * q] += f.x; v[4 * q + 1] += f.y; v[4 * q + 2] += f.z; v[4 * q + 3] += f.w;
           }
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = uc_act(v[j], p.act);
+        if (p.y32) {
+          float4* o = reinterpret_cast<float4*>(p.y32 + (outer * p.y32_outer_stride + w + p.y32_row_off) * p.y32_ld + ch0 + c0);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.0f;
       }
-      if (p.out_mode == UC_OUT_F32_ROWS) {
-        if (valid) {
-          float4* o = reinterpret_cast<float4*>(p.y32 + dst + c0);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        }
-      } else if ((p.out_mode == UC_OUT_PLAIN && inrange) || (p.out_mode == UC_OUT_PARITY && valid)) {
+      if (store_planar) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint4 o;
           __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
           for (int e = 0; e < 4; ++e) ob[e] = __floats2bfloat162_rn(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
-          *reinterpret_cast<uint4*>(p.y + (int64_t)(c0 / 8 + q) * p.y_plane_stride + dst) = o;
+          *reinterpret_cast<uint4*>(p.y + (int64_t)((ch0 + c0) / 8 + q) * p.y_plane_stride + dst) = o;
+          if (p.ylo) {
+            uint4 l;
+            __nv_bfloat162* lb = reinterpret_cast<__nv_bfloat162*>(&l);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 hf2 = __bfloat1622float2(ob[e]);
+              lb[e] = __floats2bfloat162_rn(v[q * 8 + 2 * e] - hf2.x, v[q * 8 + 2 * e + 1] - hf2.y);
+            }
+            *reinterpret_cast<uint4*>(p.ylo + (int64_t)((ch0 + c0) / 8 + q) * p.y_plane_stride + dst) = l;
+          }
         }
       }
     }
@@ -184,7 +215,7 @@ __global__ void __launch_bounds__(128) umma_conv_kernel(const __grid_constant__ 
 
 size_t umma_conv_smem_bytes(const UmmaConvP& p) { return (size_t)p.stages * (p.a_stage_bytes + p.w_stage_bytes) + 1024; }
 
-void launch_umma_conv(const UmmaConvP& p, cudaStream_t s) {
+void launch_umma_conv(const UmmaConvP& p, int n_slices, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
     // the opt-in limit (227 KB) covers static + dynamic shared memory; ~1.3 KB is static (barriers, bias)
@@ -193,7 +224,7 @@ void launch_umma_conv(const UmmaConvP& p, cudaStream_t s) {
   }
   const int S = p.MT * 128;
   const unsigned tiles = (unsigned)((p.g.P_total + S - 1) / S);
-  umma_conv_kernel<<<tiles, 128, umma_conv_smem_bytes(p), s>>>(p);
+  umma_conv_kernel<<<dim3(tiles, n_slices), 128, umma_conv_smem_bytes(p), s>>>(p);
   count_launch();
 }
 
@@ -339,7 +370,7 @@ void launch_planar_delta(const __nv_bfloat16* x, int64_t x_plane_stride, UcGeom 
 // MaxPool (1,3,3)/(1,2,2)/pad(0,1,1) in planar layout.  Inputs are post-ReLU (>= 0) and the pads are zero, so reading
 // the zero pad is equivalent to the reference's -inf padding except at the far edge, which is bounds-checked.
 __global__ void planar_maxpool_kernel(const __nv_bfloat16* __restrict__ x, int64_t xs, UcGeom gi, __nv_bfloat16* __restrict__ y, int64_t ys,
-                                      UcGeom go, int64_t total) {
+                                      UcGeom go, int64_t total, const __nv_bfloat16* __restrict__ xlo, __nv_bfloat16* __restrict__ ylo) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int64_t npos = (int64_t)go.N * go.T * go.H * go.W;
@@ -359,18 +390,34 @@ __global__ void planar_maxpool_kernel(const __nv_bfloat16* __restrict__ x, int64
       const int wi = 2 * w - 1 + dw;
       if ((unsigned)wi >= (unsigned)gi.W) continue;
       float f[8];
-      unpack8(*reinterpret_cast<const uint4*>(x + (int64_t)chunk * xs + uc_flat(gi, n, t, hi, wi) * 8), f);
+      const int64_t src = (int64_t)chunk * xs + uc_flat(gi, n, t, hi, wi) * 8;
+      unpack8(*reinterpret_cast<const uint4*>(x + src), f);
+      if (xlo) {
+        float fl[8];
+        unpack8(*reinterpret_cast<const uint4*>(xlo + src), fl);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] += fl[e];
+      }
 #pragma unroll
       for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], f[e]);
     }
   }
-  *reinterpret_cast<uint4*>(y + (int64_t)chunk * ys + uc_flat(go, n, t, h, w) * 8) = pack8(m);
+  const int64_t dst = (int64_t)chunk * ys + uc_flat(go, n, t, h, w) * 8;
+  const uint4 hi4 = pack8(m);
+  *reinterpret_cast<uint4*>(y + dst) = hi4;
+  if (ylo) {
+    float hf[8], lo[8];
+    unpack8(hi4, hf);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) lo[e] = m[e] - hf[e];
+    *reinterpret_cast<uint4*>(ylo + dst) = pack8(lo);
+  }
 }
 void launch_planar_maxpool(const __nv_bfloat16* x, int64_t x_plane_stride, UcGeom gi, __nv_bfloat16* y, int64_t y_plane_stride, UcGeom go,
-                           int C, cudaStream_t s) {
+                           int C, cudaStream_t s, const __nv_bfloat16* xlo, __nv_bfloat16* ylo) {
   const int64_t total = (int64_t)go.N * go.T * go.H * go.W * (C / 8);
   if (total == 0) return;
-  planar_maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, x_plane_stride, gi, y, y_plane_stride, go, total);
+  planar_maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, x_plane_stride, gi, y, y_plane_stride, go, total, xlo, ylo);
   count_launch();
 }
 
@@ -445,6 +492,66 @@ void launch_video_rows(const void* video, int dtype, int layout, const float* la
   const int64_t total = (int64_t)g.N * g.T * H * ((W + 1) / 2);
   if (total == 0) return;
   video_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(video, dtype, layout, lapw, xs, xl, set_stride, g, g.T, H, W, total);
+  count_launch();
+}
+
+// Generalised deterministic mean (see token_kernels.cuh): fp32 rows and/or planar bf16 rows out.
+__global__ void planar_mean2_kernel(const __nv_bfloat16* __restrict__ x, int64_t plane_stride, UcGeom g, float* __restrict__ y32, int ld,
+                                    int mode, PlanarOut po, const __nv_bfloat16* __restrict__ xlo) {
+  __shared__ float part[256][9];
+  const int row = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
+  const int count = mode == 1 ? g.T * g.H * g.W : (mode == 0 ? g.H * g.W : g.H);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = tid; i < count; i += blockDim.x) {
+    int n, t, h, w;
+    if (mode == 2) { n = row / g.W; w = row % g.W; t = 0; h = i; }
+    else {
+      n = mode == 1 ? row : row / g.T;
+      w = i % g.W;
+      const int r = i / g.W;
+      h = r % g.H;
+      t = (mode == 1 ? 0 : row % g.T) + r / g.H;
+    }
+    float f[8];
+    const int64_t src = (int64_t)chunk * plane_stride + uc_flat(g, n, t, h, w) * 8;
+    unpack8(*reinterpret_cast<const uint4*>(x + src), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += f[e];
+    if (xlo) {
+      unpack8(*reinterpret_cast<const uint4*>(xlo + src), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += f[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) part[tid][e] = acc[e];
+  __syncthreads();
+  for (int sft = blockDim.x >> 1; sft > 0; sft >>= 1) {
+    if (tid < sft) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) part[tid][e] += part[tid + sft][e];
+    }
+    __syncthreads();
+  }
+  if (tid < 8) {
+    const float m = part[0][tid] / (float)count;
+    if (y32) y32[(int64_t)row * ld + chunk * 8 + tid] = m;
+    if (po.y) {
+      const int64_t pos = po.grp > 0 ? ((int64_t)row / po.grp) * po.grp_stride + (row % po.grp) + po.off : (int64_t)row + po.off;
+      const __nv_bfloat16 hi = __float2bfloat16_rn(m);
+      po.y[(int64_t)chunk * po.plane_stride + pos * 8 + tid] = hi;
+      if (po.ylo) po.ylo[(int64_t)chunk * po.plane_stride + pos * 8 + tid] = __float2bfloat16_rn(m - __bfloat162float(hi));
+    }
+  }
+}
+void launch_planar_mean2(const __nv_bfloat16* x, int64_t plane_stride, UcGeom g, int C, float* y32, int ld, int mode, PlanarOut po, cudaStream_t s,
+                         const __nv_bfloat16* xlo) {
+  const int rows = mode == 1 ? g.N : (mode == 0 ? g.N * g.T : g.N * g.W);
+  if (rows == 0) return;
+  const int count = mode == 1 ? g.T * g.H * g.W : (mode == 0 ? g.H * g.W : g.H);
+  int threads = 32;
+  while (threads < 256 && threads < count) threads <<= 1;
+  planar_mean2_kernel<<<dim3(rows, C / 8), threads, 0, s>>>(x, plane_stride, g, y32, ld, mode, po, xlo);
   count_launch();
 }
 

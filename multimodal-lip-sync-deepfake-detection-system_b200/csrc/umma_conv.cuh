@@ -17,7 +17,7 @@ namespace lsd {
 
 constexpr int UC_MAX_BANDS = 16;
 constexpr int UC_MAX_TAPS = 9;
-constexpr int UC_MAX_GROUPS = 2;
+constexpr int UC_MAX_GROUPS = 6;
 
 struct UcBand {
   const __nv_bfloat16* base;  // plane 0, position 0 of the plane set this band reads
@@ -36,9 +36,11 @@ struct UcGroup {              // taps that share one K extent (main conv; option
   int k16;                    // Cin / 16
   int taps_total;
   int64_t w_off;              // element offset of the group's packed weights
+  int64_t slice_stride;       // elements between consecutive Cout slices (grid.y) of the packed weights
 };
 
-enum UcOut { UC_OUT_PLAIN = 0, UC_OUT_PARITY = 1, UC_OUT_F32_ROWS = 2 };
+// bf16 planar output modes (an fp32 row output can be produced in addition to, or instead of, the planar one)
+enum UcOut { UC_Y_NONE = 0, UC_Y_PLAIN = 1, UC_Y_PARITY = 2, UC_Y_PARITY_H = 3 };
 
 // Padded flat geometry:  P = ((n*TS + t + ot)*HP + h + oh)*RW + w + ow,  SL = HP*RW.
 // Standard activation geometry: one shared zero slab / row / column (TS=T+1, ot=1, HP=H+1, oh=1, RW=W+1, ow=1).
@@ -49,25 +51,33 @@ struct UcGeom {
 };
 
 struct UmmaConvP {
-  const __nv_bfloat16* w;     // packed: [group][k16 chunk][tap][2 k-chunks][Cout][8]
-  const float* bias;          // Cout (BN shift + folded conv bias; BN scale is folded into w)
-  const __nv_bfloat16* res;   // optional residual, plain layout in the output geometry
+  const __nv_bfloat16* w;     // packed: [group][Cout slice][k16 chunk][tap][2 k-chunks][Cout][8]
+  const float* bias;          // all slices (BN shift + folded conv bias; BN scale is folded into w)
+  const __nv_bfloat16* res;   // optional bf16 residual, plain layout in the output geometry
+  const __nv_bfloat16* res_lo; // optional low part of the residual (split-bf16 activations)
   int64_t res_plane_stride;
-  __nv_bfloat16* y;           // UC_OUT_PLAIN / UC_OUT_PARITY destination (position 0 of plane 0 [of set 0])
+  const float* res32;         // optional fp32 residual rows: res32[(outer*W + w) * res32_ld + channel]
+  int res32_ld;
+  __nv_bfloat16* y;           // planar destination (position 0 of plane 0 [of set 0]); y_mode selects the layout
+  __nv_bfloat16* ylo;         // optional second planar destination receiving bf16(v - bf16(v)) (split-bf16 operands of the
+                              //   token-path GEMMs: x ~ hi + lo keeps ~16 mantissa bits through the tensor cores)
   int64_t y_plane_stride, y_set_stride;
-  float* y32;                 // UC_OUT_F32_ROWS destination: row = valid position in (n,t,h,w) order
-  int y32_ld;
-  int out_mode, act;
-  int Cout, MT, stages, ngroups, nbands;
+  int y_mode;
+  float* y32;                 // optional fp32 rows: y32[(outer*y32_outer_stride + w + y32_row_off) * y32_ld + channel],
+  int y32_ld;                 //   outer = (n*T + t)*H + h  (valid positions only)
+  int y32_outer_stride, y32_row_off;
+  int act;
+  int Cout;                   // columns per CTA (one slice); grid.y = number of slices
+  int MT, stages, ngroups, nbands;
   uint32_t a_stage_bytes, w_stage_bytes, tmem_cols;
   UcGeom g;                   // output geometry (== input geometry of every band)
-  UcGeom g2;                  // UC_OUT_PARITY: half-resolution destination geometry
+  UcGeom g2;                  // UC_Y_PARITY*: destination geometry of each parity plane set
   UcGroup groups[UC_MAX_GROUPS];
   UcBand bands[UC_MAX_BANDS];
 };
 
 size_t umma_conv_smem_bytes(const UmmaConvP& p);
-void launch_umma_conv(const UmmaConvP& p, cudaStream_t s);
+void launch_umma_conv(const UmmaConvP& p, int n_slices, cudaStream_t s);
 
 // ---- planar-layout glue --------------------------------------------------------------------------
 // fp32 channels-last (N,T,H,W,C) -> padded planar bf16 (plain, or parity-split when parity != 0); pads are NOT written.
@@ -83,7 +93,7 @@ void launch_planar_delta(const __nv_bfloat16* x, int64_t x_plane_stride, UcGeom 
                          int C, cudaStream_t s);
 // 3x3 / stride 2 / pad 1 max-pool over (H,W) in planar layout (plain -> plain); valid positions only
 void launch_planar_maxpool(const __nv_bfloat16* x, int64_t x_plane_stride, UcGeom gi, __nv_bfloat16* y, int64_t y_plane_stride, UcGeom go,
-                           int C, cudaStream_t s);
+                           int C, cudaStream_t s, const __nv_bfloat16* xlo = nullptr, __nv_bfloat16* ylo = nullptr);
 
 // video (any dtype; NCDHW or NDHWC; uint8 scaled by 1/255) -> bf16 pixel rows xs (stem input) and xl = per-frame 3x3 conv 3->3
 // with weights lapw [tap][ci][co] (artifact_detector.py:33-35,55-57).  Row layout: h-parity plane sets, geometry g (units of

@@ -25,4 +25,10 @@ comb = m.stage("comb").cpu().view(B, 448)
 for i, k in enumerate(["art_raw", "art_delta", "art_hf"]):
     print(k, "rel", rel(comb[:, 256 + 64 * i: 320 + 64 * i], inter[k]))
 print("cls rel", rel(comb[:, :256], inter["cls"]))
+TA = inter["a_emb"].shape[1]
+print("a_feat rel", rel(m.stage("a_feat").cpu().view(B, TA, 256), inter["a_feat"].transpose(1, 2)))
+print("v_emb rel", rel(m.stage("v_emb").cpu().view(B, -1, 256), inter["v_emb"]))
+print("a_emb rel", rel(m.stage("a_emb").cpu().view(B, TA, 256), inter["a_emb"]))
+print("fused rel", rel(m.stage("fused").cpu().view(B, -1, 256), inter["fused"]))
+print("t_preconv rel", rel(m.stage("tok").cpu().view(B, 33, 256)[:, 1:], inter["t_layer3"][:, 1:]), "(tok final vs t_layer3)")
 print("logits", out.tolist(), "ref", ref.tolist(), "max abs", float((out - ref).abs().max()))
