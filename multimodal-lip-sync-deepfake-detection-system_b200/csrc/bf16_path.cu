@@ -375,7 +375,8 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
   while ((int)cols < p.MT * L.ntile) cols *= 2;
   p.tmem_cols = cols;
   const int S = p.MT * 128;
-  int nb = 0, max_a = 0, max_taps = 0;
+  int nb = 0, max_a = 0, max_taps = 0, min_k16 = 1 << 30;
+  bool any_toeplitz = false;
   p.ngroups = (int)L.groups.size();
   for (int gi = 0; gi < p.ngroups; ++gi) {
     const BGroup& G = L.groups[gi];
@@ -407,8 +408,10 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
       ub.tap_begin = tap_begin;
       for (int j = 0; j < ub.ntaps; ++j) ub.rel[j] = b.taps[j].dt * og.SL + b.taps[j].dh * og.RW + b.taps[j].dw - mn;
       tap_begin += ub.ntaps;
-      max_a = std::max(max_a, (G.toeplitz ? 1 : 2) * (S + ub.len_extra + ub.toeplitz) * 16);
+      max_a = std::max(max_a, G.toeplitz ? (S + ub.len_extra + 1 + 2 * (G.k16 - 1)) * 16 : 2 * (S + ub.len_extra) * 16);
       max_taps = std::max(max_taps, ub.ntaps);
+      min_k16 = std::min(min_k16, G.k16);
+      any_toeplitz = any_toeplitz || G.toeplitz;
       // the band must stay inside the guard zones of the source buffer
       if (-(int64_t)ub.start * 8 > src.origin || (int64_t)(mx + TILE_MAX) * 8 > src.origin + (int64_t)TILE_MAX * 8)
         return lsd_fail(c.h, LSD_ERR_UNSUPPORTED, "%s: guard zone too small", name.c_str());
@@ -416,8 +419,12 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
     ug.band_end = nb;
   }
   p.nbands = nb;
-  p.a_stage_bytes = ((uint32_t)max_a + 127u) & ~127u;
-  p.w_stage_bytes = (uint32_t)(max_taps * L.ntile * 32);
+  // K chunks per stage: Toeplitz layers share one row region for all chunks; small planar stages are packed up to ~24 KB
+  const int w_chunk = max_taps * L.ntile * 32;
+  if (any_toeplitz) p.kpack = min_k16;
+  else p.kpack = std::max(1, std::min(std::min(8, min_k16), (24 * 1024) / (max_a + w_chunk)));
+  p.a_stage_bytes = ((uint32_t)(any_toeplitz ? max_a : max_a * p.kpack) + 127u) & ~127u;
+  p.w_stage_bytes = (uint32_t)(w_chunk * p.kpack);
   const uint32_t stage = p.a_stage_bytes + p.w_stage_bytes;
   const uint32_t budget = (cols <= 256 ? 110u : 218u) * 1024u;
   int stages = (int)(budget / stage);

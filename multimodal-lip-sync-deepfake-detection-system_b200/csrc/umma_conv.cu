@@ -65,60 +65,106 @@ __global__ void __launch_bounds__(128) umma_conv_kernel(const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp == 0 && lane == 0) {
-    // ------------------------------------------------ producer
-    int it = 0;
+  if (warp == 0) {
+    // ------------------------------------------------ producer (whole warp runs the loop; one elected lane issues)
+    int stage = 0;
+    uint32_t ph = 0;
     for (int gi = 0; gi < p.ngroups; ++gi) {
       const UcGroup& g = p.groups[gi];
-      for (int c = 0; c < g.k16; ++c) {
-        for (int b = g.band_begin; b < g.band_end; ++b, ++it) {
+      for (int c0 = 0; c0 < g.k16; c0 += p.kpack) {
+        const int nc = min(p.kpack, g.k16 - c0);
+        for (int b = g.band_begin; b < g.band_end; ++b) {
           const UcBand& bd = p.bands[b];
-          const int stage = it % p.stages;
-          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
           mbar_wait(&empty_bar[stage], ph ^ 1u);
-          // planar: two 8-channel planes; Toeplitz: one pixel-row region (+1 unit for the overlapping second K chunk)
-          const uint32_t bytesA = (uint32_t)(S + bd.len_extra + bd.toeplitz) * 16u;
+          if (elect_one()) {
           const uint32_t bytesW = (uint32_t)bd.ntaps * (uint32_t)p.Cout * 32u;
-          mbar_arrive_expect_tx(&full_bar[stage], (bd.toeplitz ? 1u : 2u) * bytesA + bytesW);
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
-          const __nv_bfloat16* src = bd.base + (int64_t)c * bd.chunk_stride + (P0 + bd.start) * 8;
-          bulk_g2s(sa, src, bytesA, &full_bar[stage]);
-          if (!bd.toeplitz) bulk_g2s(sa + bytesA, src + bd.plane_stride, bytesA, &full_bar[stage]);
-          const __nv_bfloat16* wsrc = p.w + g.w_off + (int64_t)slice * g.slice_stride +
-                                      ((int64_t)c * g.taps_total + bd.tap_begin) * (int64_t)p.Cout * 16;
-          bulk_g2s(sa + p.a_stage_bytes, wsrc, bytesW, &full_bar[stage]);
+          uint8_t* sw = sa + p.a_stage_bytes;
+          const __nv_bfloat16* src = bd.base + (int64_t)c0 * bd.chunk_stride + (P0 + bd.start) * 8;
+          if (bd.toeplitz) {
+            // pixel rows: the K chunks are 32-byte shifts of one region -> one copy serves all chunks of the stage
+            const uint32_t bytesA = (uint32_t)(S + bd.len_extra + 1 + 2 * (nc - 1)) * 16u;
+            mbar_arrive_expect_tx(&full_bar[stage], bytesA + (uint32_t)nc * bytesW);
+            bulk_g2s(sa, src, bytesA, &full_bar[stage]);
+          } else {
+            // planar: two 8-channel planes per K chunk
+            const uint32_t bytesA = (uint32_t)(S + bd.len_extra) * 16u;
+            mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)nc * (2u * bytesA + bytesW));
+            for (int j = 0; j < nc; ++j) {
+              const __nv_bfloat16* sj = src + (int64_t)j * bd.chunk_stride;
+              bulk_g2s(sa + (size_t)j * 2u * bytesA, sj, bytesA, &full_bar[stage]);
+              bulk_g2s(sa + (size_t)j * 2u * bytesA + bytesA, sj + bd.plane_stride, bytesA, &full_bar[stage]);
+            }
+          }
+          for (int j = 0; j < nc; ++j) {
+            const __nv_bfloat16* wsrc = p.w + g.w_off + (int64_t)slice * g.slice_stride +
+                                        ((int64_t)(c0 + j) * g.taps_total + bd.tap_begin) * (int64_t)p.Cout * 16;
+            bulk_g2s(sw + (size_t)j * bytesW, wsrc, bytesW, &full_bar[stage]);
+          }
+          }
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; ph ^= 1u; }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------ MMA issuer
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer (whole warp runs the loop; one elected lane issues)
+    // One thread feeds the tensor core: keep the per-instruction work to a few 32-bit adds.  A descriptor is
+    // (constant high part) | (start address >> 4); tap / M-tile / K-chunk offsets are added in 16-byte units.
     const uint32_t idesc = idesc_bf16(128, p.Cout);
     const uint32_t smem_base = smem_u32(smem);
-    int it = 0;
+    const uint64_t desc_hi = ((uint64_t)8 << 32) | ((uint64_t)1 << 46);            // SBO = 128 B, descriptor version 1
+    const uint64_t db_hi = desc_hi | ((uint64_t)(uint32_t)p.Cout << 16);           // LBO(B) = Cout * 16 B
+    const uint32_t tap_w = (uint32_t)p.Cout * 2u;                                  // Cout * 32 B per tap, in 16 B units
+    int stage = 0;
+    uint32_t ph = 0, acc = 0;
     for (int gi = 0; gi < p.ngroups; ++gi) {
       const UcGroup& g = p.groups[gi];
-      for (int c = 0; c < g.k16; ++c) {
-        for (int b = g.band_begin; b < g.band_end; ++b, ++it) {
+      for (int c0 = 0; c0 < g.k16; c0 += p.kpack) {
+        const int nc = min(p.kpack, g.k16 - c0);
+        for (int b = g.band_begin; b < g.band_end; ++b) {
           const UcBand& bd = p.bands[b];
-          const int stage = it % p.stages;
-          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+          const int ntaps = bd.ntaps;
+          uint32_t rel[UC_MAX_TAPS];
+#pragma unroll
+          for (int tp = 0; tp < UC_MAX_TAPS; ++tp) rel[tp] = tp < ntaps ? (uint32_t)bd.rel[tp] : 0u;
+          const uint32_t unitsA = (uint32_t)(S + bd.len_extra);
+          const uint64_t da_hi = desc_hi | ((uint64_t)(bd.toeplitz ? 1u : unitsA) << 16);
+          const uint32_t a_chunk = bd.toeplitz ? 2u : 2u * unitsA;
+          const uint32_t w_chunk = (uint32_t)ntaps * tap_w;
           mbar_wait(&full_bar[stage], ph);
           tc_fence_after();
-          const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
-          const uint32_t sw = sa + p.a_stage_bytes;
-          const uint32_t lboA = bd.toeplitz ? 16u : (uint32_t)(S + bd.len_extra) * 16u;
-          for (int j = 0; j < bd.ntaps; ++j) {
-            const uint64_t db = smem_desc(sw + (uint32_t)j * (uint32_t)p.Cout * 32u, (uint32_t)p.Cout * 16u, 128u);
-            for (int m = 0; m < p.MT; ++m) {
-              const uint64_t da = smem_desc(sa + (uint32_t)(bd.rel[j] + m * 128) * 16u, lboA, 128u);
-              mma_bf16_ss(tmem_base + (uint32_t)(m * p.Cout), da, db, idesc, (it == 0 && j == 0) ? 0u : 1u);
+          const uint32_t sa = (smem_base + (uint32_t)stage * stage_bytes) >> 4;
+          const uint32_t sw = sa + (p.a_stage_bytes >> 4);
+          if (elect_one()) {
+          uint32_t accl = acc;   // 0 only for the very first MMA of each accumulator
+          for (int j = 0; j < nc; ++j) {
+            const uint32_t aj = sa + (uint32_t)j * a_chunk, wj = sw + (uint32_t)j * w_chunk;
+#pragma unroll
+            for (int tp = 0; tp < UC_MAX_TAPS; ++tp) {
+              if (tp < ntaps) {
+                const uint64_t db = db_hi | (uint64_t)(wj + (uint32_t)tp * tap_w);
+                const uint32_t at = aj + rel[tp];
+                mma_bf16_ss(tmem_base, da_hi | (uint64_t)at, db, idesc, accl);
+                if (p.MT > 1) mma_bf16_ss(tmem_base + (uint32_t)p.Cout, da_hi | (uint64_t)(at + 128u), db, idesc, accl);
+                if (p.MT > 2) {
+                  mma_bf16_ss(tmem_base + 2u * (uint32_t)p.Cout, da_hi | (uint64_t)(at + 256u), db, idesc, accl);
+                  mma_bf16_ss(tmem_base + 3u * (uint32_t)p.Cout, da_hi | (uint64_t)(at + 384u), db, idesc, accl);
+                }
+                accl = 1u;
+              }
             }
           }
           mma_commit(&empty_bar[stage]);  // frees the stage once the MMAs that read it have completed
+          }
+          acc = 1u;
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; ph ^= 1u; }
         }
       }
     }
-    mma_commit(&acc_bar);
+    if (elect_one()) mma_commit(&acc_bar);
+    __syncwarp();
   }
   __syncwarp();
 
@@ -421,77 +467,82 @@ void launch_planar_maxpool(const __nv_bfloat16* x, int64_t x_plane_stride, UcGeo
   count_launch();
 }
 
-// One thread per pixel pair: loads the 3x4 pixel neighbourhood once, writes the pair to both row buffers.
-__global__ void video_rows_kernel(const void* __restrict__ video, int dtype, int layout, const float* __restrict__ lapw,
-                                  __nv_bfloat16* __restrict__ xs, __nv_bfloat16* __restrict__ xl, int64_t set_stride, UcGeom g, int T, int H,
-                                  int W, int64_t total) {
+// One thread per 8 consecutive pixels of a row: loads the 3x10 pixel neighbourhood once (sliding window in registers),
+// writes four 16-byte units to each row buffer.
+template <typename T, int LAYOUT>
+__global__ void __launch_bounds__(128) video_rows_kernel(const T* __restrict__ video, const float* __restrict__ lapw,
+                                                         __nv_bfloat16* __restrict__ xs, __nv_bfloat16* __restrict__ xl, int64_t set_stride,
+                                                         UcGeom g, int Tn, int H, int W, int64_t total, float div) {
   __shared__ float lw[81];
   if (threadIdx.x < 81) lw[threadIdx.x] = lapw[threadIdx.x];
   __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int WP = (W + 1) / 2;
-  const int wp = (int)(i % WP);
-  int64_t r = i / WP;
+  const int WG = (W + 7) / 8;
+  const int wg = (int)(i % WG);
+  int64_t r = i / WG;
   const int h = (int)(r % H); r /= H;
-  const int t = (int)(r % T);
-  const int n = (int)(r / T);
-  const int p0 = 2 * wp;
-  const float div = dtype == 3 ? 255.0f : 1.0f;
-  float v[3][4][3];
+  const int t = (int)(r % Tn);
+  const int n = (int)(r / Tn);
+  const int p0 = 8 * wg;
+  float v[3][10][3];
 #pragma unroll
   for (int dh = 0; dh < 3; ++dh) {
     const int hh = h + dh - 1;
+    const bool rowin = (unsigned)hh < (unsigned)H;
 #pragma unroll
-    for (int dp = 0; dp < 4; ++dp) {
-      const int ww = p0 + dp - 1;
-      const bool in = (unsigned)hh < (unsigned)H && (unsigned)ww < (unsigned)W;
+    for (int c = 0; c < 3; ++c) {
+      const T* rp = LAYOUT == 0 ? video + ((((int64_t)n * 3 + c) * Tn + t) * H + (rowin ? hh : 0)) * W
+                                : video + ((((int64_t)n * Tn + t) * H + (rowin ? hh : 0)) * W) * 3 + c;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
+      for (int dp = 0; dp < 10; ++dp) {
+        const int ww = p0 + dp - 1;
         float x = 0.f;
-        if (in) {
-          const int64_t idx = layout == 0 ? ((((int64_t)n * 3 + c) * T + t) * H + hh) * W + ww
-                                          : ((((int64_t)n * T + t) * H + hh) * W + ww) * 3 + c;
-          switch (dtype) {
-            case 0: x = reinterpret_cast<const float*>(video)[idx]; break;
-            case 1: x = __half2float(reinterpret_cast<const __half*>(video)[idx]); break;
-            case 2: x = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(video)[idx]); break;
-            default: x = (float)reinterpret_cast<const uint8_t*>(video)[idx]; break;
-          }
-          x /= div;
-        }
+        if (rowin && (unsigned)ww < (unsigned)W) x = (float)rp[LAYOUT == 0 ? ww : ww * 3] / div;
         v[dh][dp][c] = x;
       }
     }
   }
-  float px[8], lp[8];
+  const int64_t dst0 = (int64_t)(h & 1) * set_stride + uc_flat(g, n, t, h >> 1, 0) * 8 + (int64_t)(p0 + 4) * 4;
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
+  for (int u = 0; u < 4; ++u) {
+    if (p0 + 2 * u >= W) break;
+    float px[8], lp[8];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) px[q * 4 + c] = v[1][1 + q][c];
-    px[q * 4 + 3] = 0.f;
+    for (int q = 0; q < 2; ++q) {
+      const int j = 2 * u + q;   // pixel p0 + j, centre column index j + 1
 #pragma unroll
-    for (int co = 0; co < 3; ++co) {
-      float acc = 0.f;
+      for (int c = 0; c < 3; ++c) px[q * 4 + c] = v[1][j + 1][c];
+      px[q * 4 + 3] = 0.f;
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh)
+      for (int co = 0; co < 3; ++co) {
+        float acc = 0.f;
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw)
+        for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-          for (int ci = 0; ci < 3; ++ci) acc = fmaf(lw[((kh * 3 + kw) * 3 + ci) * 3 + co], v[kh][q + kw][ci], acc);
-      lp[q * 4 + co] = (p0 + q < W) ? acc : 0.f;
+          for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) acc = fmaf(lw[((kh * 3 + kw) * 3 + ci) * 3 + co], v[kh][j + kw][ci], acc);
+        lp[q * 4 + co] = (p0 + j < W) ? acc : 0.f;
+      }
+      lp[q * 4 + 3] = 0.f;
     }
-    lp[q * 4 + 3] = 0.f;
+    *reinterpret_cast<uint4*>(xs + dst0 + u * 8) = pack8(px);
+    *reinterpret_cast<uint4*>(xl + dst0 + u * 8) = pack8(lp);
   }
-  const int64_t dst = (int64_t)(h & 1) * set_stride + uc_flat(g, n, t, h >> 1, 0) * 8 + (int64_t)(p0 + 4) * 4;
-  *reinterpret_cast<uint4*>(xs + dst) = pack8(px);
-  *reinterpret_cast<uint4*>(xl + dst) = pack8(lp);
 }
 void launch_video_rows(const void* video, int dtype, int layout, const float* lapw, __nv_bfloat16* xs, __nv_bfloat16* xl,
                        int64_t set_stride, UcGeom g, int H, int W, cudaStream_t s) {
-  const int64_t total = (int64_t)g.N * g.T * H * ((W + 1) / 2);
+  const int64_t total = (int64_t)g.N * g.T * H * ((W + 7) / 8);
   if (total == 0) return;
-  video_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(video, dtype, layout, lapw, xs, xl, set_stride, g, g.T, H, W, total);
+  const unsigned grid = (unsigned)((total + 127) / 128);
+#define VR(TT, LL, DIV) video_rows_kernel<TT, LL><<<grid, 128, 0, s>>>(reinterpret_cast<const TT*>(video), lapw, xs, xl, set_stride, g, g.T, H, W, total, DIV)
+  if (layout == 0) {
+    if (dtype == 0) VR(float, 0, 1.0f); else if (dtype == 1) VR(__half, 0, 1.0f); else if (dtype == 2) VR(__nv_bfloat16, 0, 1.0f); else VR(uint8_t, 0, 255.0f);
+  } else {
+    if (dtype == 0) VR(float, 1, 1.0f); else if (dtype == 1) VR(__half, 1, 1.0f); else if (dtype == 2) VR(__nv_bfloat16, 1, 1.0f); else VR(uint8_t, 1, 255.0f);
+  }
+#undef VR
   count_launch();
 }
 

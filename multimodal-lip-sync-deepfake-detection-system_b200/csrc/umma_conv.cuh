@@ -69,6 +69,7 @@ struct UmmaConvP {
   int act;
   int Cout;                   // columns per CTA (one slice); grid.y = number of slices
   int MT, stages, ngroups, nbands;
+  int kpack;                  // k16 chunks per pipeline stage (small-K-step layers amortise the mbarrier round trip)
   uint32_t a_stage_bytes, w_stage_bytes, tmem_cols;
   UcGeom g;                   // output geometry (== input geometry of every band)
   UcGeom g2;                  // UC_Y_PARITY*: destination geometry of each parity plane set
