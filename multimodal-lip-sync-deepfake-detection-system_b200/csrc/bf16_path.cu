@@ -141,7 +141,7 @@ struct Packer {
     const ConvP& c = h->convs.at(key);
     BLayer L;
     L.Cout = c.Cout;
-    L.ntile = ntile > 0 ? ntile : c.Cout;
+    L.ntile = ntile > 0 ? ntile : std::min(c.Cout, 128);   // <= 128 columns per CTA: 2 M-tiles x 2 TMEM buffers
     L.groups.push_back(make_group(c, sh, sw));
     pack_group(L.groups[0], c, L.ntile);
     if (split) {
@@ -344,6 +344,7 @@ struct UArgs {
 int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
   const BLayer& L = c.h->blayers.at(name);
   const UcGeom& og = a.og;
+  if (og.P_total >= (int64_t)1 << 31) return lsd_fail(c.h, LSD_ERR_SHAPE, "%s: more than 2^31 padded positions in one launch (reduce the batch)", name.c_str());
   UmmaConvP p;
   memset(&p, 0, sizeof(p));
   p.w = reinterpret_cast<const __nv_bfloat16*>(c.h->barena);
@@ -367,12 +368,13 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
   if (a.res) { p.res = c.org(*a.res); p.res_plane_stride = a.res->plane_stride; }
   if (a.res_lo) p.res_lo = c.org(*a.res_lo);
   if (a.res32) { p.res32 = a.res32; p.res32_ld = a.res32_ld; }
-  // tile shape: MT M-tiles x ntile columns in TMEM; shrink MT until the grid fills the SMs
-  p.MT = L.ntile <= 64 ? 4 : 2;
-  const int mt_min = L.ntile > 64 ? 2 : 1;  // wide tiles re-read all weights per CTA: keep two M-tiles per weight load
-  while (p.MT > mt_min && ((og.P_total + p.MT * 128 - 1) / (p.MT * 128)) * slices < c.h->num_sms) p.MT /= 2;
+  // tile shape: MT M-tiles x ntile columns per accumulator buffer, two buffers in TMEM (<= 512 columns);
+  // shrink MT while the tile count cannot keep every SM busy
+  p.MT = std::max(1, 256 / L.ntile);
+  if (p.MT > 4) p.MT = 4;
+  while (p.MT > 1 && ((og.P_total + p.MT * 128 - 1) / (p.MT * 128)) * slices < c.h->num_sms) p.MT /= 2;
   uint32_t cols = 32;
-  while ((int)cols < p.MT * L.ntile) cols *= 2;
+  while ((int)cols < 2 * p.MT * L.ntile) cols *= 2;
   p.tmem_cols = cols;
   const int S = p.MT * 128;
   int nb = 0, max_a = 0, max_taps = 0, min_k16 = 1 << 30;
@@ -426,7 +428,7 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
   p.a_stage_bytes = ((uint32_t)(any_toeplitz ? max_a : max_a * p.kpack) + 127u) & ~127u;
   p.w_stage_bytes = (uint32_t)(w_chunk * p.kpack);
   const uint32_t stage = p.a_stage_bytes + p.w_stage_bytes;
-  const uint32_t budget = (cols <= 256 ? 110u : 218u) * 1024u;
+  const uint32_t budget = 212u * 1024u;   // one persistent CTA per SM owns the whole shared memory
   int stages = (int)(budget / stage);
   stages = std::max(2, std::min(stages, 8));
   if ((size_t)stages * stage + 1024 > 224u * 1024u) return lsd_fail(c.h, LSD_ERR_UNSUPPORTED, "%s: stage of %u bytes does not fit", name.c_str(), stage);

@@ -27,13 +27,15 @@ __device__ __forceinline__ float uc_act(float v, int act) {
   return v;
 }
 
+// (P_total < 2^31 is enforced on the host: 32-bit divisions only)
 __device__ __forceinline__ bool uc_decode(const UcGeom& g, int64_t P, int& n, int& t, int& h, int& w) {
   if (P < 0 || P >= g.P_total) return false;
-  const int64_t S = P / g.SL;
-  const int r = (int)(P - S * g.SL);
+  const uint32_t Pu = (uint32_t)P;
+  const uint32_t S = Pu / (uint32_t)g.SL;
+  const int r = (int)(Pu - S * (uint32_t)g.SL);
   const int row = r / g.RW, col = r - row * g.RW;
-  n = (int)(S / g.TS);
-  t = (int)(S - (int64_t)n * g.TS) - g.ot;
+  n = (int)(S / (uint32_t)g.TS);
+  t = (int)(S - (uint32_t)n * (uint32_t)g.TS) - g.ot;
   h = row - g.oh; w = col - g.ow;
   return (unsigned)t < (unsigned)g.T && (unsigned)h < (unsigned)g.H && (unsigned)w < (unsigned)g.W && n < g.N;
 }
@@ -42,24 +44,34 @@ __device__ __forceinline__ int64_t uc_flat(const UcGeom& g, int n, int t, int h,
   return (((int64_t)n * g.TS + t + g.ot) * g.HP + h + g.oh) * g.RW + w + g.ow;
 }
 
-__global__ void __launch_bounds__(128) umma_conv_kernel(const __grid_constant__ UmmaConvP p) {
+// Persistent, warp-specialised: warp 0 = bulk-copy producer, warps 1 and 2 = MMA issuers (each owns half of the tile's
+// M-tiles: a single thread cannot issue N<=128 instructions as fast as the tensor core retires them), warps 3-10 = epilogue
+// (two warps per TMEM lane quarter, each handling every other 32-column chunk).
+// Each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the accumulators are double-buffered in TMEM so the
+// epilogue of tile i overlaps the main loop of tile i+1, and the smem ring keeps streaming across tile boundaries.
+constexpr int UC_THREADS = 352;
+constexpr int UC_EPI_WARP0 = 3, UC_EPI_WARPS = 8;
+
+__global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_constant__ UmmaConvP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t full_bar[8], empty_bar[8], acc_bar;
+  __shared__ uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float bias_s[256];
+  __shared__ __align__(16) float bias_s[256];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = p.MT * 128;
-  const int64_t P0 = (int64_t)blockIdx.x * S;
   const uint32_t stage_bytes = p.a_stage_bytes + p.w_stage_bytes;
+  const int num_tiles = (int)((p.g.P_total + S - 1) / S);
+  const int slice = blockIdx.y, ch0 = slice * p.Cout;
+  const uint32_t buf_cols = (uint32_t)(p.MT * p.Cout);
 
+  const int n_issuers = p.MT > 1 ? 2 : 1;   // MMA-issuing warps (M-tiles are independent accumulators)
   if (tid == 0) {
-    for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    mbar_init(&acc_bar, 1);
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], n_issuers); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], n_issuers); mbar_init(&tempty_bar[i], UC_EPI_WARPS); }
     fence_barrier_init();
   }
-  if (warp == 2) { tmem_alloc(&tmem_base_s, p.tmem_cols); tmem_relinquish(); }
-  const int slice = blockIdx.y, ch0 = slice * p.Cout;
-  for (int i = tid; i < p.Cout; i += 128) bias_s[i] = p.bias ? p.bias[ch0 + i] : 0.0f;
+  if (warp == UC_EPI_WARP0) { tmem_alloc(&tmem_base_s, p.tmem_cols); tmem_relinquish(); }
+  for (int i = tid; i < p.Cout; i += UC_THREADS) bias_s[i] = p.bias ? p.bias[ch0 + i] : 0.0f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -69,46 +81,52 @@ __global__ void __launch_bounds__(128) umma_conv_kernel(const __grid_constant__ 
     // ------------------------------------------------ producer (whole warp runs the loop; one elected lane issues)
     int stage = 0;
     uint32_t ph = 0;
-    for (int gi = 0; gi < p.ngroups; ++gi) {
-      const UcGroup& g = p.groups[gi];
-      for (int c0 = 0; c0 < g.k16; c0 += p.kpack) {
-        const int nc = min(p.kpack, g.k16 - c0);
-        for (int b = g.band_begin; b < g.band_end; ++b) {
-          const UcBand& bd = p.bands[b];
-          mbar_wait(&empty_bar[stage], ph ^ 1u);
-          if (elect_one()) {
-          const uint32_t bytesW = (uint32_t)bd.ntaps * (uint32_t)p.Cout * 32u;
-          uint8_t* sa = smem + (size_t)stage * stage_bytes;
-          uint8_t* sw = sa + p.a_stage_bytes;
-          const __nv_bfloat16* src = bd.base + (int64_t)c0 * bd.chunk_stride + (P0 + bd.start) * 8;
-          if (bd.toeplitz) {
-            // pixel rows: the K chunks are 32-byte shifts of one region -> one copy serves all chunks of the stage
-            const uint32_t bytesA = (uint32_t)(S + bd.len_extra + 1 + 2 * (nc - 1)) * 16u;
-            mbar_arrive_expect_tx(&full_bar[stage], bytesA + (uint32_t)nc * bytesW);
-            bulk_g2s(sa, src, bytesA, &full_bar[stage]);
-          } else {
-            // planar: two 8-channel planes per K chunk
-            const uint32_t bytesA = (uint32_t)(S + bd.len_extra) * 16u;
-            mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)nc * (2u * bytesA + bytesW));
-            for (int j = 0; j < nc; ++j) {
-              const __nv_bfloat16* sj = src + (int64_t)j * bd.chunk_stride;
-              bulk_g2s(sa + (size_t)j * 2u * bytesA, sj, bytesA, &full_bar[stage]);
-              bulk_g2s(sa + (size_t)j * 2u * bytesA + bytesA, sj + bd.plane_stride, bytesA, &full_bar[stage]);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int64_t P0 = (int64_t)tile * S;
+      for (int gi = 0; gi < p.ngroups; ++gi) {
+        const UcGroup& g = p.groups[gi];
+        for (int c0 = 0; c0 < g.k16; c0 += p.kpack) {
+          const int nc = min(p.kpack, g.k16 - c0);
+          for (int b = g.band_begin; b < g.band_end; ++b) {
+            const UcBand& bd = p.bands[b];
+            mbar_wait(&empty_bar[stage], ph ^ 1u);
+            if (elect_one()) {
+              const uint32_t bytesW = (uint32_t)bd.ntaps * (uint32_t)p.Cout * 32u;
+              uint8_t* sa = smem + (size_t)stage * stage_bytes;
+              uint8_t* sw = sa + p.a_stage_bytes;
+              const __nv_bfloat16* src = bd.base + (int64_t)c0 * bd.chunk_stride + (P0 + bd.start) * 8;
+              if (bd.toeplitz) {
+                // pixel rows: the K chunks are 32-byte shifts of one region -> one copy serves all chunks of the stage
+                const uint32_t bytesA = (uint32_t)(S + bd.len_extra + 1 + 2 * (nc - 1)) * 16u;
+                mbar_arrive_expect_tx(&full_bar[stage], bytesA + (uint32_t)nc * bytesW);
+                bulk_g2s(sa, src, bytesA, &full_bar[stage]);
+              } else {
+                // planar: two 8-channel planes per K chunk
+                const uint32_t bytesA = (uint32_t)(S + bd.len_extra) * 16u;
+                mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)nc * (2u * bytesA + bytesW));
+                for (int j = 0; j < nc; ++j) {
+                  const __nv_bfloat16* sj = src + (int64_t)j * bd.chunk_stride;
+                  bulk_g2s(sa + (size_t)j * 2u * bytesA, sj, bytesA, &full_bar[stage]);
+                  bulk_g2s(sa + (size_t)j * 2u * bytesA + bytesA, sj + bd.plane_stride, bytesA, &full_bar[stage]);
+                }
+              }
+              for (int j = 0; j < nc; ++j) {
+                const __nv_bfloat16* wsrc = p.w + g.w_off + (int64_t)slice * g.slice_stride +
+                                            ((int64_t)(c0 + j) * g.taps_total + bd.tap_begin) * (int64_t)p.Cout * 16;
+                bulk_g2s(sw + (size_t)j * bytesW, wsrc, bytesW, &full_bar[stage]);
+              }
             }
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; ph ^= 1u; }
           }
-          for (int j = 0; j < nc; ++j) {
-            const __nv_bfloat16* wsrc = p.w + g.w_off + (int64_t)slice * g.slice_stride +
-                                        ((int64_t)(c0 + j) * g.taps_total + bd.tap_begin) * (int64_t)p.Cout * 16;
-            bulk_g2s(sw + (size_t)j * bytesW, wsrc, bytesW, &full_bar[stage]);
-          }
-          }
-          __syncwarp();
-          if (++stage == p.stages) { stage = 0; ph ^= 1u; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer (whole warp runs the loop; one elected lane issues)
+  } else if (warp == 1 || warp == 2) {
+    // ------------------------------------------------ MMA issuers (whole warp runs the loop; one elected lane issues)
+    if (warp == 2 && n_issuers == 1) goto done;
+    const int mt_lo = (warp == 1) ? 0 : p.MT / 2;                         // this warp's M-tiles: [mt_lo, mt_lo + mt_n)
+    const int mt_n = n_issuers == 1 ? p.MT : p.MT / 2;
     // One thread feeds the tensor core: keep the per-instruction work to a few 32-bit adds.  A descriptor is
     // (constant high part) | (start address >> 4); tap / M-tile / K-chunk offsets are added in 16-byte units.
     const uint32_t idesc = idesc_bf16(128, p.Cout);
@@ -116,147 +134,173 @@ __global__ void __launch_bounds__(128) umma_conv_kernel(const __grid_constant__ 
     const uint64_t desc_hi = ((uint64_t)8 << 32) | ((uint64_t)1 << 46);            // SBO = 128 B, descriptor version 1
     const uint64_t db_hi = desc_hi | ((uint64_t)(uint32_t)p.Cout << 16);           // LBO(B) = Cout * 16 B
     const uint32_t tap_w = (uint32_t)p.Cout * 2u;                                  // Cout * 32 B per tap, in 16 B units
-    int stage = 0;
-    uint32_t ph = 0, acc = 0;
-    for (int gi = 0; gi < p.ngroups; ++gi) {
-      const UcGroup& g = p.groups[gi];
-      for (int c0 = 0; c0 < g.k16; c0 += p.kpack) {
-        const int nc = min(p.kpack, g.k16 - c0);
-        for (int b = g.band_begin; b < g.band_end; ++b) {
-          const UcBand& bd = p.bands[b];
-          const int ntaps = bd.ntaps;
-          uint32_t rel[UC_MAX_TAPS];
+    int stage = 0, lt = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      const uint32_t tb = tmem_base + (uint32_t)buf * buf_cols + (uint32_t)(mt_lo * p.Cout);
+      mbar_wait(&tempty_bar[buf], (((uint32_t)lt >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator buffer
+      tc_fence_after();
+      uint32_t acc = 0;
+      for (int gi = 0; gi < p.ngroups; ++gi) {
+        const UcGroup& g = p.groups[gi];
+        for (int c0 = 0; c0 < g.k16; c0 += p.kpack) {
+          const int nc = min(p.kpack, g.k16 - c0);
+          for (int b = g.band_begin; b < g.band_end; ++b) {
+            const UcBand& bd = p.bands[b];
+            const int ntaps = bd.ntaps;
+            uint32_t rel[UC_MAX_TAPS];
 #pragma unroll
-          for (int tp = 0; tp < UC_MAX_TAPS; ++tp) rel[tp] = tp < ntaps ? (uint32_t)bd.rel[tp] : 0u;
-          const uint32_t unitsA = (uint32_t)(S + bd.len_extra);
-          const uint64_t da_hi = desc_hi | ((uint64_t)(bd.toeplitz ? 1u : unitsA) << 16);
-          const uint32_t a_chunk = bd.toeplitz ? 2u : 2u * unitsA;
-          const uint32_t w_chunk = (uint32_t)ntaps * tap_w;
-          mbar_wait(&full_bar[stage], ph);
-          tc_fence_after();
-          const uint32_t sa = (smem_base + (uint32_t)stage * stage_bytes) >> 4;
-          const uint32_t sw = sa + (p.a_stage_bytes >> 4);
-          if (elect_one()) {
-          uint32_t accl = acc;   // 0 only for the very first MMA of each accumulator
-          for (int j = 0; j < nc; ++j) {
-            const uint32_t aj = sa + (uint32_t)j * a_chunk, wj = sw + (uint32_t)j * w_chunk;
+            for (int tp = 0; tp < UC_MAX_TAPS; ++tp) rel[tp] = tp < ntaps ? (uint32_t)bd.rel[tp] : 0u;
+            const uint32_t unitsA = (uint32_t)(S + bd.len_extra);
+            const uint64_t da_hi = desc_hi | ((uint64_t)(bd.toeplitz ? 1u : unitsA) << 16);
+            const uint32_t a_chunk = bd.toeplitz ? 2u : 2u * unitsA;
+            const uint32_t w_chunk = (uint32_t)ntaps * tap_w;
+            mbar_wait(&full_bar[stage], ph);
+            tc_fence_after();
+            const uint32_t sa = (smem_base + (uint32_t)stage * stage_bytes) >> 4;
+            const uint32_t sw = sa + (p.a_stage_bytes >> 4);
+            if (elect_one()) {
+              uint32_t accl = acc;   // 0 only for the very first MMA of each accumulator
+              for (int j = 0; j < nc; ++j) {
+                const uint32_t aj = sa + (uint32_t)j * a_chunk, wj = sw + (uint32_t)j * w_chunk;
 #pragma unroll
-            for (int tp = 0; tp < UC_MAX_TAPS; ++tp) {
-              if (tp < ntaps) {
-                const uint64_t db = db_hi | (uint64_t)(wj + (uint32_t)tp * tap_w);
-                const uint32_t at = aj + rel[tp];
-                mma_bf16_ss(tmem_base, da_hi | (uint64_t)at, db, idesc, accl);
-                if (p.MT > 1) mma_bf16_ss(tmem_base + (uint32_t)p.Cout, da_hi | (uint64_t)(at + 128u), db, idesc, accl);
-                if (p.MT > 2) {
-                  mma_bf16_ss(tmem_base + 2u * (uint32_t)p.Cout, da_hi | (uint64_t)(at + 256u), db, idesc, accl);
-                  mma_bf16_ss(tmem_base + 3u * (uint32_t)p.Cout, da_hi | (uint64_t)(at + 384u), db, idesc, accl);
+                for (int tp = 0; tp < UC_MAX_TAPS; ++tp) {
+                  if (tp < ntaps) {
+                    const uint64_t db = db_hi | (uint64_t)(wj + (uint32_t)tp * tap_w);
+                    const uint32_t at = aj + rel[tp] + (uint32_t)mt_lo * 128u;
+                    mma_bf16_ss(tb, da_hi | (uint64_t)at, db, idesc, accl);
+                    if (mt_n > 1) mma_bf16_ss(tb + (uint32_t)p.Cout, da_hi | (uint64_t)(at + 128u), db, idesc, accl);
+                    accl = 1u;
+                  }
                 }
-                accl = 1u;
+              }
+              mma_commit(&empty_bar[stage]);  // frees the stage once the MMAs that read it have completed
+            }
+            acc = 1u;
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; ph ^= 1u; }
+          }
+        }
+      }
+      if (elect_one()) mma_commit(&tfull_bar[buf]);   // accumulator of this tile complete -> epilogue
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------ epilogue warps (TMEM lane quarter = warp % 4; thread == tile row)
+    const int quarter = warp & 3;
+    const int half = (warp - UC_EPI_WARP0) >> 2;                 // which 32-column chunks this warp handles (even / odd)
+    const float act_lo = p.act == ACT_RELU ? 0.0f : -INFINITY;   // ReLU as one FMNMX; GELU (token GEMMs only) branches once per chunk
+    const int rowt = quarter * 32 + lane;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      const uint32_t tb = tmem_base + (uint32_t)buf * buf_cols + ((uint32_t)(quarter * 32) << 16);
+      const int64_t P0 = (int64_t)tile * S;
+      mbar_wait(&tfull_bar[buf], ((uint32_t)lt >> 1) & 1u);
+      tc_fence_after();
+      for (int m = 0; m < p.MT; ++m) {
+        const int64_t P = P0 + (int64_t)m * 128 + rowt;
+        int n, t, h, w;
+        const bool valid = uc_decode(p.g, P, n, t, h, w);
+        const bool inrange = P < p.g.P_total;
+        const int64_t outer = valid ? ((int64_t)n * p.g.T + t) * p.g.H + h : 0;
+        int64_t dst = P * 8;
+        if (valid && p.y_mode == UC_Y_PARITY)
+          dst = (int64_t)((h & 1) * 2 + (w & 1)) * p.y_set_stride + uc_flat(p.g2, n, t, h >> 1, w >> 1) * 8;
+        else if (valid && p.y_mode == UC_Y_PARITY_H)
+          dst = (int64_t)((h & 1) * 2) * p.y_set_stride + uc_flat(p.g2, n, t, h >> 1, w) * 8;
+        const bool store_planar = (p.y_mode == UC_Y_PLAIN && inrange) || (p.y_mode >= UC_Y_PARITY && valid);
+#pragma unroll 1
+        for (int c0 = half * 32; c0 < p.Cout; c0 += 64) {
+          float v[32];
+          tmem_ld32(tb + (uint32_t)(m * p.Cout + c0), v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 b4 = *reinterpret_cast<const float4*>(&bias_s[c0 + 4 * q]);
+              v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
+            }
+            if (p.res) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 r = *reinterpret_cast<const uint4*>(p.res + (int64_t)((ch0 + c0) / 8 + q) * p.res_plane_stride + P * 8);
+                const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __bfloat1622float2(rb[e]);
+                  v[q * 8 + 2 * e] += f.x;
+                  v[q * 8 + 2 * e + 1] += f.y;
+                }
+                if (p.res_lo) {
+                  const uint4 rl = *reinterpret_cast<const uint4*>(p.res_lo + (int64_t)((ch0 + c0) / 8 + q) * p.res_plane_stride + P * 8);
+                  const __nv_bfloat162* rlb = reinterpret_cast<const __nv_bfloat162*>(&rl);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = __bfloat1622float2(rlb[e]);
+                    v[q * 8 + 2 * e] += f.x;
+                    v[q * 8 + 2 * e + 1] += f.y;
+                  }
+                }
+              }
+            }
+            if (p.res32) {
+              const float4* r4 = reinterpret_cast<const float4*>(p.res32 + (outer * p.g.W + w) * p.res32_ld + ch0 + c0);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 f = r4[q];
+                v[4 * q] += f.x; v[4 * q + 1] += f.y; v[4 * q + 2] += f.z; v[4 * q + 3] += f.w;
+              }
+            }
+            if (p.act == ACT_GELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752f));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], act_lo);
+            }
+            if (p.y32) {
+              float4* o = reinterpret_cast<float4*>(p.y32 + (outer * p.y32_outer_stride + w + p.y32_row_off) * p.y32_ld + ch0 + c0);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+          }
+          if (store_planar) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 o;
+              __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) ob[e] = __floats2bfloat162_rn(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
+              *reinterpret_cast<uint4*>(p.y + (int64_t)((ch0 + c0) / 8 + q) * p.y_plane_stride + dst) = o;
+              if (p.ylo) {
+                uint4 l;
+                __nv_bfloat162* lb = reinterpret_cast<__nv_bfloat162*>(&l);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 hf2 = __bfloat1622float2(ob[e]);
+                  lb[e] = __floats2bfloat162_rn(v[q * 8 + 2 * e] - hf2.x, v[q * 8 + 2 * e + 1] - hf2.y);
+                }
+                *reinterpret_cast<uint4*>(p.ylo + (int64_t)((ch0 + c0) / 8 + q) * p.y_plane_stride + dst) = l;
               }
             }
           }
-          mma_commit(&empty_bar[stage]);  // frees the stage once the MMAs that read it have completed
-          }
-          acc = 1u;
-          __syncwarp();
-          if (++stage == p.stages) { stage = 0; ph ^= 1u; }
         }
       }
-    }
-    if (elect_one()) mma_commit(&acc_bar);
-    __syncwarp();
-  }
-  __syncwarp();
-
-  // ------------------------------------------------ epilogue (all 128 threads; thread == TMEM lane == tile row)
-  mbar_wait(&acc_bar, 0);
-  tc_fence_after();
-  for (int m = 0; m < p.MT; ++m) {
-    const int64_t P = P0 + (int64_t)m * 128 + tid;
-    int n, t, h, w;
-    const bool valid = uc_decode(p.g, P, n, t, h, w);
-    const bool inrange = P < p.g.P_total;
-    const int64_t outer = valid ? ((int64_t)n * p.g.T + t) * p.g.H + h : 0;
-    int64_t dst = P * 8;
-    if (valid && p.y_mode == UC_Y_PARITY)
-      dst = (int64_t)((h & 1) * 2 + (w & 1)) * p.y_set_stride + uc_flat(p.g2, n, t, h >> 1, w >> 1) * 8;
-    else if (valid && p.y_mode == UC_Y_PARITY_H)
-      dst = (int64_t)((h & 1) * 2) * p.y_set_stride + uc_flat(p.g2, n, t, h >> 1, w) * 8;
-    const bool store_planar = (p.y_mode == UC_Y_PLAIN && inrange) || (p.y_mode >= UC_Y_PARITY && valid);
-    for (int c0 = 0; c0 < p.Cout; c0 += 32) {
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(m * p.Cout + c0), v);
-      tmem_ld_wait();
-      if (valid) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += bias_s[c0 + j];
-        if (p.res) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 r = *reinterpret_cast<const uint4*>(p.res + (int64_t)((ch0 + c0) / 8 + q) * p.res_plane_stride + P * 8);
-            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&r);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = __bfloat1622float2(rb[e]);
-              v[q * 8 + 2 * e] += f.x;
-              v[q * 8 + 2 * e + 1] += f.y;
-            }
-            if (p.res_lo) {
-              const uint4 rl = *reinterpret_cast<const uint4*>(p.res_lo + (int64_t)((ch0 + c0) / 8 + q) * p.res_plane_stride + P * 8);
-              const __nv_bfloat162* rlb = reinterpret_cast<const __nv_bfloat162*>(&rl);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __bfloat1622float2(rlb[e]);
-                v[q * 8 + 2 * e] += f.x;
-                v[q * 8 + 2 * e + 1] += f.y;
-              }
-            }
-          }
-        }
-        if (p.res32) {
-          const float4* r4 = reinterpret_cast<const float4*>(p.res32 + (outer * p.g.W + w) * p.res32_ld + ch0 + c0);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 f = r4[q];
-            v[4 * q] += f.x; v[4 * q + 1] += f.y; v[4 * q + 2] += f.z; v[4 * q + 3] += f.w;
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = uc_act(v[j], p.act);
-        if (p.y32) {
-          float4* o = reinterpret_cast<float4*>(p.y32 + (outer * p.y32_outer_stride + w + p.y32_row_off) * p.y32_ld + ch0 + c0);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.0f;
-      }
-      if (store_planar) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 o;
-          __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) ob[e] = __floats2bfloat162_rn(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
-          *reinterpret_cast<uint4*>(p.y + (int64_t)((ch0 + c0) / 8 + q) * p.y_plane_stride + dst) = o;
-          if (p.ylo) {
-            uint4 l;
-            __nv_bfloat162* lb = reinterpret_cast<__nv_bfloat162*>(&l);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 hf2 = __bfloat1622float2(ob[e]);
-              lb[e] = __floats2bfloat162_rn(v[q * 8 + 2 * e] - hf2.x, v[q * 8 + 2 * e + 1] - hf2.y);
-            }
-            *reinterpret_cast<uint4*>(p.ylo + (int64_t)((ch0 + c0) / 8 + q) * p.y_plane_stride + dst) = l;
-          }
-        }
-      }
+      // all TMEM reads of this warp are complete (wait::ld above): hand the buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
     }
   }
+done:
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
+  if (warp == UC_EPI_WARP0) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
 size_t umma_conv_smem_bytes(const UmmaConvP& p) { return (size_t)p.stages * (p.a_stage_bytes + p.w_stage_bytes) + 1024; }
@@ -269,8 +313,13 @@ void launch_umma_conv(const UmmaConvP& p, int n_slices, cudaStream_t s) {
     attr_set = true;
   }
   const int S = p.MT * 128;
-  const unsigned tiles = (unsigned)((p.g.P_total + S - 1) / S);
-  umma_conv_kernel<<<dim3(tiles, n_slices), 128, umma_conv_smem_bytes(p), s>>>(p);
+  const int tiles = (int)((p.g.P_total + S - 1) / S);
+  static int num_sms = 0;
+  if (num_sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+  // persistent grid: one CTA per SM (per Cout slice), each walking tiles with stride gridDim.x
+  int gx = (num_sms + n_slices - 1) / n_slices;
+  gx = gx < 1 ? 1 : (gx > tiles ? tiles : gx);
+  umma_conv_kernel<<<dim3(gx, n_slices), UC_THREADS, umma_conv_smem_bytes(p), s>>>(p);
   count_launch();
 }
 
