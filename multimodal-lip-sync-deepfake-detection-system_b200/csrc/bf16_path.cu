@@ -6,6 +6,8 @@
 #include "umma_conv.cuh"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 using namespace lsd;
@@ -23,7 +25,9 @@ uint16_t f2bf(float f) {
 
 // Tap/band structure of a k_t x k_h x k_w convolution with stride (1, sh, sw) and "same" padding k/2 over the padded
 // planar layout: taps that read the same parity plane set and the same temporal offset form one band.
-BGroup make_group(const ConvP& c, int sh, int sw) {
+// merge_kt: taps of all temporal offsets that read the same parity set share one band (small maps: the three temporal
+// slabs of a tile are close together, so one region covers them and the stage carries up to 12 taps).
+BGroup make_group(const ConvP& c, int sh, int sw, bool merge_kt = false) {
   BGroup g;
   g.Cin = c.Cin;
   for (int a = 0; a < c.kt; ++a)
@@ -39,7 +43,7 @@ BGroup make_group(const ConvP& c, int sh, int sw) {
         const int set = hp * 2 + wp;
         BBand* band = nullptr;
         for (BBand& bb : g.bands)
-          if (bb.set == set && bb.taps[0].dt == t.dt && (int)bb.taps.size() < UC_MAX_TAPS) band = &bb;
+          if (bb.set == set && (merge_kt || bb.taps[0].dt == t.dt) && (int)bb.taps.size() < UC_MAX_TAPS) band = &bb;
         if (!band) { g.bands.push_back(BBand{set, {}}); band = &g.bands.back(); }
         band->taps.push_back(t);
       }
@@ -137,16 +141,17 @@ struct Packer {
     h->blayers[name] = L;
   }
   // split: every K group is issued three times (hi*hi, lo*hi, hi*lo), see add_split
-  void add(const std::string& name, const std::string& key, int sh, int sw, const std::string& ds_key = "", int ntile = 0, bool split = false) {
+  void add(const std::string& name, const std::string& key, int sh, int sw, const std::string& ds_key = "", int ntile = 0, bool split = false,
+           bool merge_kt = false) {
     const ConvP& c = h->convs.at(key);
     BLayer L;
     L.Cout = c.Cout;
-    L.ntile = ntile > 0 ? ntile : std::min(c.Cout, 128);   // <= 128 columns per CTA: 2 M-tiles x 2 TMEM buffers
-    L.groups.push_back(make_group(c, sh, sw));
+    L.ntile = ntile > 0 ? ntile : c.Cout;
+    L.groups.push_back(make_group(c, sh, sw, merge_kt));
     pack_group(L.groups[0], c, L.ntile);
     if (split) {
       BGroup g1 = L.groups[0]; g1.src = 2;
-      BGroup g2 = make_group(c, sh, sw);
+      BGroup g2 = make_group(c, sh, sw, merge_kt);
       pack_group(g2, c, L.ntile, 1);
       L.groups.push_back(g1);
       L.groups.push_back(g2);
@@ -368,13 +373,15 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
   if (a.res) { p.res = c.org(*a.res); p.res_plane_stride = a.res->plane_stride; }
   if (a.res_lo) p.res_lo = c.org(*a.res_lo);
   if (a.res32) { p.res32 = a.res32; p.res32_ld = a.res32_ld; }
-  // tile shape: MT M-tiles x ntile columns per accumulator buffer, two buffers in TMEM (<= 512 columns);
-  // shrink MT while the tile count cannot keep every SM busy
-  p.MT = std::max(1, 256 / L.ntile);
-  if (p.MT > 4) p.MT = 4;
+  // Tile shape.  The kernel is bound by shared-memory bandwidth (operand reads of the MMAs + the fills of the ring), so
+  // the fills per MMA are minimised: wide layers (>= 128 columns) give all 512 TMEM columns to one tile (more M-tiles per
+  // weight stage; their K loop is so long that the un-overlapped epilogue is a few %), narrow layers keep two
+  // accumulator buffers so that the epilogue overlaps the next tile.  MT shrinks while the tiles cannot fill the SMs.
+  p.nbuf = L.ntile >= 128 ? 1 : 2;
+  p.MT = std::max(1, std::min(4, 512 / (p.nbuf * L.ntile)));
   while (p.MT > 1 && ((og.P_total + p.MT * 128 - 1) / (p.MT * 128)) * slices < c.h->num_sms) p.MT /= 2;
   uint32_t cols = 32;
-  while ((int)cols < 2 * p.MT * L.ntile) cols *= 2;
+  while ((int)cols < p.nbuf * p.MT * L.ntile) cols *= 2;
   p.tmem_cols = cols;
   const int S = p.MT * 128;
   int nb = 0, max_a = 0, max_taps = 0, min_k16 = 1 << 30;
@@ -392,31 +399,38 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
     ug.w_off = (int64_t)G.w_off;
     ug.slice_stride = (int64_t)G.slice_stride;
     int tap_begin = 0;
+    const int tmax = std::max(1, std::min(UC_MAX_TAPS, (40 * 1024) / (L.ntile * 32)));   // keep a weight stage <= ~40 KB
     for (const BBand& b : G.bands) {
-      if (nb >= UC_MAX_BANDS) return lsd_fail(c.h, LSD_ERR_UNSUPPORTED, "%s: too many bands", name.c_str());
-      UcBand& ub = p.bands[nb++];
-      ub.base = c.org(src) + (int64_t)b.set * src.set_stride;
-      ub.plane_stride = src.plane_stride;
-      ub.toeplitz = G.toeplitz;
-      ub.chunk_stride = G.toeplitz ? 16 : 2 * src.plane_stride;
-      int mn = INT32_MAX, mx = INT32_MIN;
-      for (const BTap& t : b.taps) {
-        const int sft = t.dt * og.SL + t.dh * og.RW + t.dw;
-        mn = std::min(mn, sft); mx = std::max(mx, sft);
+      const int nt = (int)b.taps.size();
+      const int pieces = (nt + tmax - 1) / tmax, per = (nt + pieces - 1) / pieces;
+      for (int t0 = 0; t0 < nt; t0 += per) {
+        const int t1 = std::min(nt, t0 + per);
+        if (nb >= UC_MAX_BANDS) return lsd_fail(c.h, LSD_ERR_UNSUPPORTED, "%s: too many bands", name.c_str());
+        UcBand& ub = p.bands[nb++];
+        ub.base = c.org(src) + (int64_t)b.set * src.set_stride;
+        ub.plane_stride = src.plane_stride;
+        ub.toeplitz = G.toeplitz;
+        ub.chunk_stride = G.toeplitz ? 16 : 2 * src.plane_stride;
+        int mn = INT32_MAX, mx = INT32_MIN;
+        for (int j = t0; j < t1; ++j) {
+          const BTap& t = b.taps[j];
+          const int sft = t.dt * og.SL + t.dh * og.RW + t.dw;
+          mn = std::min(mn, sft); mx = std::max(mx, sft);
+        }
+        ub.start = mn;
+        ub.len_extra = mx - mn;
+        ub.ntaps = t1 - t0;
+        ub.tap_begin = tap_begin;
+        for (int j = t0; j < t1; ++j) ub.rel[j - t0] = b.taps[j].dt * og.SL + b.taps[j].dh * og.RW + b.taps[j].dw - mn;
+        tap_begin += ub.ntaps;
+        max_a = std::max(max_a, G.toeplitz ? (S + ub.len_extra + 1 + 2 * (G.k16 - 1)) * 16 : 2 * (S + ub.len_extra) * 16);
+        max_taps = std::max(max_taps, ub.ntaps);
+        min_k16 = std::min(min_k16, G.k16);
+        any_toeplitz = any_toeplitz || G.toeplitz;
+        // the band must stay inside the guard zones of the source buffer
+        if (-(int64_t)ub.start * 8 > src.origin || (int64_t)mx * 8 > src.origin)
+          return lsd_fail(c.h, LSD_ERR_UNSUPPORTED, "%s: guard zone too small", name.c_str());
       }
-      ub.start = mn;
-      ub.len_extra = mx - mn;
-      ub.ntaps = (int)b.taps.size();
-      ub.tap_begin = tap_begin;
-      for (int j = 0; j < ub.ntaps; ++j) ub.rel[j] = b.taps[j].dt * og.SL + b.taps[j].dh * og.RW + b.taps[j].dw - mn;
-      tap_begin += ub.ntaps;
-      max_a = std::max(max_a, G.toeplitz ? (S + ub.len_extra + 1 + 2 * (G.k16 - 1)) * 16 : 2 * (S + ub.len_extra) * 16);
-      max_taps = std::max(max_taps, ub.ntaps);
-      min_k16 = std::min(min_k16, G.k16);
-      any_toeplitz = any_toeplitz || G.toeplitz;
-      // the band must stay inside the guard zones of the source buffer
-      if (-(int64_t)ub.start * 8 > src.origin || (int64_t)(mx + TILE_MAX) * 8 > src.origin + (int64_t)TILE_MAX * 8)
-        return lsd_fail(c.h, LSD_ERR_UNSUPPORTED, "%s: guard zone too small", name.c_str());
     }
     ug.band_end = nb;
   }
@@ -436,6 +450,28 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
   double kflop = 0;
   for (const BGroup& G : L.groups) kflop += (double)G.taps_total * G.Cin;
   if (L.groups[0].toeplitz) { const ConvP& cp = c.h->convs.at(name); kflop = (double)cp.kt * cp.kh * cp.kw * cp.Cin; }  // algorithmic K, not the padded one
+  if (const char* e = getenv("LSD_UMMA_TRACE")) {
+    // debug: per-launch phase timestamps of CTA (0,0); prints after a sync (never enabled in timed runs)
+    static long long* dbuf = nullptr;
+    if (!dbuf) cudaMalloc(&dbuf, 512);
+    cudaMemsetAsync(dbuf, 0, 512, c.st);
+    p.dbg = dbuf;
+    launch_umma_conv(p, slices, c.st);
+    long long hv[64];
+    cudaMemcpyAsync(hv, dbuf, 512, cudaMemcpyDeviceToHost, c.st);
+    cudaStreamSynchronize(c.st);
+    if (atoi(e) > 0)
+      fprintf(stderr, "[umma] %-34s MT=%d N=%d slices=%d stages=%d kpack=%d tiles=%lld | prologue %lld, first-data %lld, mma-issued %lld, acc-done %lld, epi-done %lld, total %lld cycles\n",
+              name.c_str(), p.MT, p.Cout, slices, p.stages, p.kpack, hv[7], hv[1] - hv[0], hv[2] - hv[0], hv[3] - hv[0], hv[4] - hv[0], hv[5] - hv[0], hv[6] - hv[0]);
+    if (atoi(e) > 1) {
+      fprintf(stderr, "        full-wait done at:");
+      for (int i = 0; i < 24 && hv[8 + i]; ++i) fprintf(stderr, " %lld", hv[8 + i] - hv[0]);
+      fprintf(stderr, "\n        producer issue at:");
+      for (int i = 0; i < 24 && hv[32 + i]; ++i) fprintf(stderr, " %lld", hv[32 + i] - hv[0]);
+      fprintf(stderr, "\n");
+    }
+    return 0;
+  }
   c.h->prof.begin(c.st, 2.0 * (double)og.N * og.T * og.H * og.W * L.Cout * kflop, 2);
   launch_umma_conv(p, slices, c.st);
   c.h->prof.end(c.st);
@@ -480,7 +516,7 @@ int pack_bf16_weights(lsd_handle* h, const std::vector<float>& f32_arena) {
   for (int l = 1; l <= 4; ++l) {
     const std::string p = "visual_encoder.layer" + std::to_string(l);
     const int s = vstr[l - 1];
-    P.add(p + ".conv1", p + ".conv1", s, s);
+    P.add(p + ".conv1", p + ".conv1", s, s, "", 0, false, /*merge_kt=*/l >= 2);   // 12x12 / 6x6 / 3x3 maps: one band per parity set
     P.ds_sh = 2; P.ds_sw = 2;
     P.add(p + ".conv2", p + ".conv2", 1, 1, l == 1 ? "" : p + ".downsample");
   }

@@ -44,13 +44,29 @@ __device__ __forceinline__ int64_t uc_flat(const UcGeom& g, int n, int t, int h,
   return (((int64_t)n * g.TS + t + g.ot) * g.HP + h + g.oh) * g.RW + w + g.ow;
 }
 
-// Persistent, warp-specialised: warp 0 = bulk-copy producer, warps 1 and 2 = MMA issuers (each owns half of the tile's
-// M-tiles: a single thread cannot issue N<=128 instructions as fast as the tensor core retires them), warps 3-10 = epilogue
-// (two warps per TMEM lane quarter, each handling every other 32-column chunk).
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  uint4 o;
+  __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) ob[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+  return o;
+}
+__device__ __forceinline__ void unpack8(const uint4& r, float* v) {
+  const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(rb[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+}
+
+// Persistent, warp-specialised (14 warps):
+//   warps 0-3  bulk-copy producers (measured on B200: one warp sustains only ~1 cp.async.bulk per ~100-130 cycles whatever the
+//              number of active lanes, and the rate scales with the number of issuing warps -> the copies of a stage are
+//              dealt round-robin to four warps),
+//   warps 4-5  MMA issuers (each owns half of the tile's M-tiles),
+//   warps 6-13 epilogue (two warps per TMEM lane quarter, each handling every other 32-column chunk).
 // Each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the accumulators are double-buffered in TMEM so the
 // epilogue of tile i overlaps the main loop of tile i+1, and the smem ring keeps streaming across tile boundaries.
-constexpr int UC_THREADS = 352;
-constexpr int UC_EPI_WARP0 = 3, UC_EPI_WARPS = 8;
+constexpr int UC_THREADS = 448;
+constexpr int UC_PROD_WARPS = 4, UC_MMA_WARP0 = 4, UC_EPI_WARP0 = 6, UC_EPI_WARPS = 8;
 
 __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_constant__ UmmaConvP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -58,6 +74,8 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_s[256];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+  if (dbg && tid == 0) p.dbg[0] = clock64();
   const int S = p.MT * 128;
   const uint32_t stage_bytes = p.a_stage_bytes + p.w_stage_bytes;
   const int num_tiles = (int)((p.g.P_total + S - 1) / S);
@@ -76,10 +94,11 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  if (dbg && tid == 0) p.dbg[1] = clock64();   // prologue done
 
-  if (warp == 0) {
-    // ------------------------------------------------ producer (whole warp runs the loop; one elected lane issues)
-    int stage = 0;
+  if (warp < UC_PROD_WARPS) {
+    // ------------------------------------------------ producers (every warp runs the loop; lane 0 of each issues its share)
+    int stage = 0, dbg_it = 0;
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int64_t P0 = (int64_t)tile * S;
@@ -90,30 +109,28 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
           for (int b = g.band_begin; b < g.band_end; ++b) {
             const UcBand& bd = p.bands[b];
             mbar_wait(&empty_bar[stage], ph ^ 1u);
-            if (elect_one()) {
+            if (dbg && warp == 0 && lane == 0 && dbg_it < 24 && tile == (int)blockIdx.x) p.dbg[32 + dbg_it++] = clock64();
+            if (lane == 0) {
               const uint32_t bytesW = (uint32_t)bd.ntaps * (uint32_t)p.Cout * 32u;
               uint8_t* sa = smem + (size_t)stage * stage_bytes;
               uint8_t* sw = sa + p.a_stage_bytes;
               const __nv_bfloat16* src = bd.base + (int64_t)c0 * bd.chunk_stride + (P0 + bd.start) * 8;
-              if (bd.toeplitz) {
-                // pixel rows: the K chunks are 32-byte shifts of one region -> one copy serves all chunks of the stage
-                const uint32_t bytesA = (uint32_t)(S + bd.len_extra + 1 + 2 * (nc - 1)) * 16u;
-                mbar_arrive_expect_tx(&full_bar[stage], bytesA + (uint32_t)nc * bytesW);
-                bulk_g2s(sa, src, bytesA, &full_bar[stage]);
-              } else {
-                // planar: two 8-channel planes per K chunk
-                const uint32_t bytesA = (uint32_t)(S + bd.len_extra) * 16u;
-                mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)nc * (2u * bytesA + bytesW));
-                for (int j = 0; j < nc; ++j) {
-                  const __nv_bfloat16* sj = src + (int64_t)j * bd.chunk_stride;
-                  bulk_g2s(sa + (size_t)j * 2u * bytesA, sj, bytesA, &full_bar[stage]);
-                  bulk_g2s(sa + (size_t)j * 2u * bytesA + bytesA, sj + bd.plane_stride, bytesA, &full_bar[stage]);
+              const uint32_t bytesA = bd.toeplitz ? (uint32_t)(S + bd.len_extra + 1 + 2 * (nc - 1)) * 16u : (uint32_t)(S + bd.len_extra) * 16u;
+              const int n_a = bd.toeplitz ? 1 : 2 * nc;   // Toeplitz: the K chunks are 32-byte shifts of one row region
+              // single-band groups (Linear layers): the weights of consecutive K chunks are contiguous -> one copy
+              const bool w_merged = (g.band_end - g.band_begin) == 1;
+              const int n_w = w_merged ? 1 : nc;
+              if (warp == 0) mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)n_a * bytesA + (uint32_t)nc * bytesW);
+              for (int idx = warp; idx < n_a + n_w; idx += UC_PROD_WARPS) {
+                if (idx < n_a) {
+                  const int j = idx >> 1, pl = idx & 1;     // K chunk j, plane pl (planar); idx == 0 only for Toeplitz
+                  bulk_g2s(sa + (size_t)idx * bytesA, src + (int64_t)j * bd.chunk_stride + (int64_t)pl * bd.plane_stride, bytesA, &full_bar[stage]);
+                } else {
+                  const int j = idx - n_a;
+                  const __nv_bfloat16* wsrc = p.w + g.w_off + (int64_t)slice * g.slice_stride +
+                                              ((int64_t)(c0 + j) * g.taps_total + bd.tap_begin) * (int64_t)p.Cout * 16;
+                  bulk_g2s(sw + (size_t)j * bytesW, wsrc, w_merged ? (uint32_t)nc * bytesW : bytesW, &full_bar[stage]);
                 }
-              }
-              for (int j = 0; j < nc; ++j) {
-                const __nv_bfloat16* wsrc = p.w + g.w_off + (int64_t)slice * g.slice_stride +
-                                            ((int64_t)(c0 + j) * g.taps_total + bd.tap_begin) * (int64_t)p.Cout * 16;
-                bulk_g2s(sw + (size_t)j * bytesW, wsrc, bytesW, &full_bar[stage]);
               }
             }
             __syncwarp();
@@ -122,10 +139,10 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
         }
       }
     }
-  } else if (warp == 1 || warp == 2) {
+  } else if (warp == UC_MMA_WARP0 || warp == UC_MMA_WARP0 + 1) {
     // ------------------------------------------------ MMA issuers (whole warp runs the loop; one elected lane issues)
-    if (warp == 2 && n_issuers == 1) goto done;
-    const int mt_lo = (warp == 1) ? 0 : p.MT / 2;                         // this warp's M-tiles: [mt_lo, mt_lo + mt_n)
+    if (warp == UC_MMA_WARP0 + 1 && n_issuers == 1) goto done;
+    const int mt_lo = (warp == UC_MMA_WARP0) ? 0 : p.MT / 2;                         // this warp's M-tiles: [mt_lo, mt_lo + mt_n)
     const int mt_n = n_issuers == 1 ? p.MT : p.MT / 2;
     // One thread feeds the tensor core: keep the per-instruction work to a few 32-bit adds.  A descriptor is
     // (constant high part) | (start address >> 4); tap / M-tile / K-chunk offsets are added in 16-byte units.
@@ -134,12 +151,13 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
     const uint64_t desc_hi = ((uint64_t)8 << 32) | ((uint64_t)1 << 46);            // SBO = 128 B, descriptor version 1
     const uint64_t db_hi = desc_hi | ((uint64_t)(uint32_t)p.Cout << 16);           // LBO(B) = Cout * 16 B
     const uint32_t tap_w = (uint32_t)p.Cout * 2u;                                  // Cout * 32 B per tap, in 16 B units
-    int stage = 0, lt = 0;
+    int stage = 0, lt = 0, dbg_it = 0;
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-      const int buf = lt & 1;
+      const int buf = p.nbuf == 2 ? (lt & 1) : 0;
+      const uint32_t use = p.nbuf == 2 ? ((uint32_t)lt >> 1) : (uint32_t)lt;   // how many times this buffer was used before
       const uint32_t tb = tmem_base + (uint32_t)buf * buf_cols + (uint32_t)(mt_lo * p.Cout);
-      mbar_wait(&tempty_bar[buf], (((uint32_t)lt >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator buffer
+      mbar_wait(&tempty_bar[buf], (use & 1u) ^ 1u);   // epilogue has drained this accumulator buffer
       tc_fence_after();
       uint32_t acc = 0;
       for (int gi = 0; gi < p.ngroups; ++gi) {
@@ -149,30 +167,27 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
           for (int b = g.band_begin; b < g.band_end; ++b) {
             const UcBand& bd = p.bands[b];
             const int ntaps = bd.ntaps;
-            uint32_t rel[UC_MAX_TAPS];
-#pragma unroll
-            for (int tp = 0; tp < UC_MAX_TAPS; ++tp) rel[tp] = tp < ntaps ? (uint32_t)bd.rel[tp] : 0u;
             const uint32_t unitsA = (uint32_t)(S + bd.len_extra);
             const uint64_t da_hi = desc_hi | ((uint64_t)(bd.toeplitz ? 1u : unitsA) << 16);
             const uint32_t a_chunk = bd.toeplitz ? 2u : 2u * unitsA;
             const uint32_t w_chunk = (uint32_t)ntaps * tap_w;
             mbar_wait(&full_bar[stage], ph);
             tc_fence_after();
+            if (dbg && warp == UC_MMA_WARP0 && lane == 0 && acc == 0 && lt == 0) p.dbg[2] = clock64();   // first stage landed
+            if (dbg && warp == UC_MMA_WARP0 && lane == 0 && lt == 0 && dbg_it < 24) p.dbg[8 + dbg_it++] = clock64();
             const uint32_t sa = (smem_base + (uint32_t)stage * stage_bytes) >> 4;
             const uint32_t sw = sa + (p.a_stage_bytes >> 4);
             if (elect_one()) {
               uint32_t accl = acc;   // 0 only for the very first MMA of each accumulator
               for (int j = 0; j < nc; ++j) {
                 const uint32_t aj = sa + (uint32_t)j * a_chunk, wj = sw + (uint32_t)j * w_chunk;
-#pragma unroll
-                for (int tp = 0; tp < UC_MAX_TAPS; ++tp) {
-                  if (tp < ntaps) {
-                    const uint64_t db = db_hi | (uint64_t)(wj + (uint32_t)tp * tap_w);
-                    const uint32_t at = aj + rel[tp] + (uint32_t)mt_lo * 128u;
-                    mma_bf16_ss(tb, da_hi | (uint64_t)at, db, idesc, accl);
-                    if (mt_n > 1) mma_bf16_ss(tb + (uint32_t)p.Cout, da_hi | (uint64_t)(at + 128u), db, idesc, accl);
-                    accl = 1u;
-                  }
+#pragma unroll 1
+                for (int tp = 0; tp < ntaps; ++tp) {   // (not unrolled: the kernel must stay inside the instruction cache)
+                  const uint64_t db = db_hi | (uint64_t)(wj + (uint32_t)tp * tap_w);
+                  const uint32_t at = aj + (uint32_t)bd.rel[tp] + (uint32_t)mt_lo * 128u;
+                  mma_bf16_ss(tb, da_hi | (uint64_t)at, db, idesc, accl);
+                  if (mt_n > 1) mma_bf16_ss(tb + (uint32_t)p.Cout, da_hi | (uint64_t)(at + 128u), db, idesc, accl);
+                  accl = 1u;
                 }
               }
               mma_commit(&empty_bar[stage]);  // frees the stage once the MMAs that read it have completed
@@ -185,6 +200,7 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
       }
       if (elect_one()) mma_commit(&tfull_bar[buf]);   // accumulator of this tile complete -> epilogue
       __syncwarp();
+      if (dbg && warp == UC_MMA_WARP0 && lane == 0 && lt == 0) p.dbg[3] = clock64();   // all MMAs of the first tile issued
     }
   } else {
     // ------------------------------------------------ epilogue warps (TMEM lane quarter = warp % 4; thread == tile row)
@@ -194,11 +210,13 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
     const int rowt = quarter * 32 + lane;
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-      const int buf = lt & 1;
+      const int buf = p.nbuf == 2 ? (lt & 1) : 0;
+      const uint32_t use = p.nbuf == 2 ? ((uint32_t)lt >> 1) : (uint32_t)lt;
       const uint32_t tb = tmem_base + (uint32_t)buf * buf_cols + ((uint32_t)(quarter * 32) << 16);
       const int64_t P0 = (int64_t)tile * S;
-      mbar_wait(&tfull_bar[buf], ((uint32_t)lt >> 1) & 1u);
+      mbar_wait(&tfull_bar[buf], use & 1u);
       tc_fence_after();
+      if (dbg && warp == UC_EPI_WARP0 && lane == 0 && lt == 0) p.dbg[4] = clock64();   // first accumulator complete
       for (int m = 0; m < p.MT; ++m) {
         const int64_t P = P0 + (int64_t)m * 128 + rowt;
         int n, t, h, w;
@@ -213,79 +231,58 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
         const bool store_planar = (p.y_mode == UC_Y_PLAIN && inrange) || (p.y_mode >= UC_Y_PARITY && valid);
 #pragma unroll 1
         for (int c0 = half * 32; c0 < p.Cout; c0 += 64) {
-          float v[32];
-          tmem_ld32(tb + (uint32_t)(m * p.Cout + c0), v);
-          tmem_ld_wait();
-          if (valid) {
+#pragma unroll 1
+          for (int q = 0; q < 4; ++q) {   // 8 columns per step keeps the epilogue code small (instruction cache)
+            const int c = c0 + 8 * q;
+            float v[8];
+            tmem_ld8(tb + (uint32_t)(m * p.Cout + c), v);
+            tmem_ld_wait();
+            if (valid) {
+              const float4 b0 = *reinterpret_cast<const float4*>(&bias_s[c]);
+              const float4 b1 = *reinterpret_cast<const float4*>(&bias_s[c + 4]);
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              if (p.res) {
+                float f[8];
+                unpack8(*reinterpret_cast<const uint4*>(p.res + (int64_t)((ch0 + c) >> 3) * p.res_plane_stride + P * 8), f);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 b4 = *reinterpret_cast<const float4*>(&bias_s[c0 + 4 * q]);
-              v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
-            }
-            if (p.res) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint4 r = *reinterpret_cast<const uint4*>(p.res + (int64_t)((ch0 + c0) / 8 + q) * p.res_plane_stride + P * 8);
-                const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&r);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = __bfloat1622float2(rb[e]);
-                  v[q * 8 + 2 * e] += f.x;
-                  v[q * 8 + 2 * e + 1] += f.y;
-                }
+                for (int e = 0; e < 8; ++e) v[e] += f[e];
                 if (p.res_lo) {
-                  const uint4 rl = *reinterpret_cast<const uint4*>(p.res_lo + (int64_t)((ch0 + c0) / 8 + q) * p.res_plane_stride + P * 8);
-                  const __nv_bfloat162* rlb = reinterpret_cast<const __nv_bfloat162*>(&rl);
+                  unpack8(*reinterpret_cast<const uint4*>(p.res_lo + (int64_t)((ch0 + c) >> 3) * p.res_plane_stride + P * 8), f);
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float2 f = __bfloat1622float2(rlb[e]);
-                    v[q * 8 + 2 * e] += f.x;
-                    v[q * 8 + 2 * e + 1] += f.y;
-                  }
+                  for (int e = 0; e < 8; ++e) v[e] += f[e];
                 }
               }
-            }
-            if (p.res32) {
-              const float4* r4 = reinterpret_cast<const float4*>(p.res32 + (outer * p.g.W + w) * p.res32_ld + ch0 + c0);
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 f = r4[q];
-                v[4 * q] += f.x; v[4 * q + 1] += f.y; v[4 * q + 2] += f.z; v[4 * q + 3] += f.w;
+              if (p.res32) {
+                const float4* r4 = reinterpret_cast<const float4*>(p.res32 + (outer * p.g.W + w) * p.res32_ld + ch0 + c);
+                const float4 r0 = r4[0], r1 = r4[1];
+                v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
               }
-            }
-            if (p.act == ACT_GELU) {
+              if (p.act == ACT_GELU) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752f));
+                for (int e = 0; e < 8; ++e) v[e] = 0.5f * v[e] * (1.0f + erff(v[e] * 0.70710678118654752f));
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], act_lo);
+              }
+              if (p.y32) {
+                float4* o = reinterpret_cast<float4*>(p.y32 + (outer * p.y32_outer_stride + w + p.y32_row_off) * p.y32_ld + ch0 + c);
+                o[0] = make_float4(v[0], v[1], v[2], v[3]);
+                o[1] = make_float4(v[4], v[5], v[6], v[7]);
+              }
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], act_lo);
+              for (int e = 0; e < 8; ++e) v[e] = 0.0f;
             }
-            if (p.y32) {
-              float4* o = reinterpret_cast<float4*>(p.y32 + (outer * p.y32_outer_stride + w + p.y32_row_off) * p.y32_ld + ch0 + c0);
-#pragma unroll
-              for (int q = 0; q < 8; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.0f;
-          }
-          if (store_planar) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 o;
-              __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) ob[e] = __floats2bfloat162_rn(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
-              *reinterpret_cast<uint4*>(p.y + (int64_t)((ch0 + c0) / 8 + q) * p.y_plane_stride + dst) = o;
+            if (store_planar) {
+              const uint4 hi4 = pack8(v);
+              const int64_t off = (int64_t)((ch0 + c) >> 3) * p.y_plane_stride + dst;
+              *reinterpret_cast<uint4*>(p.y + off) = hi4;
               if (p.ylo) {
-                uint4 l;
-                __nv_bfloat162* lb = reinterpret_cast<__nv_bfloat162*>(&l);
+                float hf[8];
+                unpack8(hi4, hf);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 hf2 = __bfloat1622float2(ob[e]);
-                  lb[e] = __floats2bfloat162_rn(v[q * 8 + 2 * e] - hf2.x, v[q * 8 + 2 * e + 1] - hf2.y);
-                }
-                *reinterpret_cast<uint4*>(p.ylo + (int64_t)((ch0 + c0) / 8 + q) * p.y_plane_stride + dst) = l;
+                for (int e = 0; e < 8; ++e) hf[e] = v[e] - hf[e];
+                *reinterpret_cast<uint4*>(p.ylo + off) = pack8(hf);
               }
             }
           }
@@ -295,12 +292,14 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      if (dbg && warp == UC_EPI_WARP0 && lane == 0 && lt == 0) p.dbg[5] = clock64();   // first epilogue done
     }
   }
 done:
   tc_fence_before();
   __syncthreads();
   if (warp == UC_EPI_WARP0) tmem_dealloc(tmem_base, p.tmem_cols);
+  if (dbg && tid == 0) { p.dbg[6] = clock64(); p.dbg[7] = num_tiles; }
 }
 
 size_t umma_conv_smem_bytes(const UmmaConvP& p) { return (size_t)p.stages * (p.a_stage_bytes + p.w_stage_bytes) + 1024; }
@@ -326,19 +325,6 @@ void launch_umma_conv(const UmmaConvP& p, int n_slices, cudaStream_t s) {
 // ================================================================================================
 // planar-layout glue kernels (memory-bound, 16-byte accesses, one thread per (position, 8-channel chunk))
 // ================================================================================================
-__device__ __forceinline__ uint4 pack8(const float* v) {
-  uint4 o;
-  __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-  for (int e = 0; e < 4; ++e) ob[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-  return o;
-}
-__device__ __forceinline__ void unpack8(const uint4& r, float* v) {
-  const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&r);
-#pragma unroll
-  for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(rb[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
-}
-
 __global__ void pack_planar_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t plane_stride, int64_t set_stride,
                                    UcGeom g, UcGeom g2, int C, int parity, int64_t total) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

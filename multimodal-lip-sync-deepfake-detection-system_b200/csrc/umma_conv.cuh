@@ -16,7 +16,7 @@
 namespace lsd {
 
 constexpr int UC_MAX_BANDS = 16;
-constexpr int UC_MAX_TAPS = 9;
+constexpr int UC_MAX_TAPS = 12;
 constexpr int UC_MAX_GROUPS = 6;
 
 struct UcBand {
@@ -69,6 +69,8 @@ struct UmmaConvP {
   int act;
   int Cout;                   // columns per CTA (one slice); grid.y = number of slices
   int MT, stages, ngroups, nbands;
+  int nbuf;                   // TMEM accumulator buffers: 2 = epilogue overlaps the next tile, 1 = all 512 columns for one tile
+  long long* dbg;             // optional: CTA (0,0) writes clock64 phase timestamps (debug builds of the bench only)
   int kpack;                  // k16 chunks per pipeline stage (small-K-step layers amortise the mbarrier round trip)
   uint32_t a_stage_bytes, w_stage_bytes, tmem_cols;
   UcGeom g;                   // output geometry (== input geometry of every band)
