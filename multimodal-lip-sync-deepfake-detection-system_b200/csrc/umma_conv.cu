@@ -502,76 +502,107 @@ void launch_planar_maxpool(const __nv_bfloat16* x, int64_t x_plane_stride, UcGeo
   count_launch();
 }
 
-// One thread per 8 consecutive pixels of a row: loads the 3x10 pixel neighbourhood once (sliding window in registers),
-// writes four 16-byte units to each row buffer.
+// One block (32 x 8 threads) per (n, t, band of VR_ROWS image rows): the band (+1 halo row/column on every side) is staged
+// in shared memory with coalesced, batched loads and no integer divisions, and each thread
+// produces pixel pairs (16-byte units) of both row buffers.
+constexpr int VR_ROWS = 8;
+// uint8 crops are scaled exactly like the reference: astype(float32) / 255.0 (video.py:552-556)
+template <typename T> __device__ __forceinline__ float vr_norm(float x) { return x; }
+template <> __device__ __forceinline__ float vr_norm<uint8_t>(float x) { return x / 255.0f; }
 template <typename T, int LAYOUT>
-__global__ void __launch_bounds__(128) video_rows_kernel(const T* __restrict__ video, const float* __restrict__ lapw,
+__global__ void __launch_bounds__(256) video_rows_kernel(const T* __restrict__ video, const float* __restrict__ lapw,
                                                          __nv_bfloat16* __restrict__ xs, __nv_bfloat16* __restrict__ xl, int64_t set_stride,
-                                                         UcGeom g, int Tn, int H, int W, int64_t total, float div) {
+                                                         UcGeom g, int Tn, int H, int W, int bands, float inv_div) {
+  extern __shared__ float tile[];   // [3][VR_ROWS + 2][W + 2]
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int WP2 = W + 2, per_c = (VR_ROWS + 2) * WP2;
+  const int band = blockIdx.x % bands;
+  const int nt = blockIdx.x / bands;            // n * Tn + t
+  const int t = nt % Tn, n = nt / Tn;
+  const int h0 = band * VR_ROWS;
   __shared__ float lw[81];
-  if (threadIdx.x < 81) lw[threadIdx.x] = lapw[threadIdx.x];
-  __syncthreads();
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int WG = (W + 7) / 8;
-  const int wg = (int)(i % WG);
-  int64_t r = i / WG;
-  const int h = (int)(r % H); r /= H;
-  const int t = (int)(r % Tn);
-  const int n = (int)(r / Tn);
-  const int p0 = 8 * wg;
-  float v[3][10][3];
+  if (ty == 0 && tx < 27) { lw[tx] = lapw[tx]; lw[tx + 27] = lapw[tx + 27]; lw[tx + 54] = lapw[tx + 54]; }
+  // tile fill: all loads of a row are issued before the first shared-memory store (the kernel is latency-bound otherwise)
+  for (int r = ty; r < VR_ROWS + 2; r += 8) {
+    const int hh = h0 + r - 1;
+    const bool rin = (unsigned)hh < (unsigned)H;
+    if (LAYOUT == 0) {
+      const T* rp0 = video + ((((int64_t)n * 3) * Tn + t) * H + (rin ? hh : 0)) * W;
+      const int64_t cstride = (int64_t)Tn * H * W;
+      for (int col0 = 0; col0 < WP2; col0 += 128) {
+        float vals[3][4];
 #pragma unroll
-  for (int dh = 0; dh < 3; ++dh) {
-    const int hh = h + dh - 1;
-    const bool rowin = (unsigned)hh < (unsigned)H;
+        for (int c = 0; c < 3; ++c)
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const T* rp = LAYOUT == 0 ? video + ((((int64_t)n * 3 + c) * Tn + t) * H + (rowin ? hh : 0)) * W
-                                : video + ((((int64_t)n * Tn + t) * H + (rowin ? hh : 0)) * W) * 3 + c;
+          for (int k = 0; k < 4; ++k) {
+            const int ww = col0 + tx + 32 * k - 1;
+            vals[c][k] = (rin && (unsigned)ww < (unsigned)W) ? vr_norm<T>((float)rp0[c * cstride + ww]) : 0.f;
+          }
 #pragma unroll
-      for (int dp = 0; dp < 10; ++dp) {
-        const int ww = p0 + dp - 1;
-        float x = 0.f;
-        if (rowin && (unsigned)ww < (unsigned)W) x = (float)rp[LAYOUT == 0 ? ww : ww * 3] / div;
-        v[dh][dp][c] = x;
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int col = col0 + tx + 32 * k;
+            if (col < WP2) tile[c * per_c + r * WP2 + col] = vals[c][k];
+          }
+      }
+    } else {
+      const T* rp = video + (((int64_t)nt * H + (rin ? hh : 0)) * W) * 3;
+      for (int e0 = 0; e0 < 3 * WP2; e0 += 256) {
+        float vals[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int e = e0 + tx + 32 * k, col = e / 3, c = e - col * 3, ww = col - 1;
+          vals[k] = (rin && e < 3 * WP2 && (unsigned)ww < (unsigned)W) ? vr_norm<T>((float)rp[ww * 3 + c]) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int e = e0 + tx + 32 * k, col = e / 3, c = e - col * 3;
+          if (e < 3 * WP2) tile[c * per_c + r * WP2 + col] = vals[k];
+        }
       }
     }
   }
-  const int64_t dst0 = (int64_t)(h & 1) * set_stride + uc_flat(g, n, t, h >> 1, 0) * 8 + (int64_t)(p0 + 4) * 4;
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    if (p0 + 2 * u >= W) break;
+  __syncthreads();
+  const int h = h0 + ty;
+  if (h >= H) return;
+  const int WP = (W + 1) / 2;
+  const int64_t row_dst = (int64_t)(h & 1) * set_stride + uc_flat(g, n, t, h >> 1, 0) * 8 + 16;
+  for (int wp = tx; wp < WP; wp += 32) {
+    const int p0 = 2 * wp;
     float px[8], lp[8];
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-      const int j = 2 * u + q;   // pixel p0 + j, centre column index j + 1
+      const int pc = p0 + q;   // pixel column; tile column = pc + 1
+      const bool in = pc < W;
+      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) px[q * 4 + c] = v[1][j + 1][c];
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+          for (int ci = 0; ci < 3; ++ci) {
+            const float x = in ? tile[ci * per_c + (ty + kh) * WP2 + pc + kw] : 0.f;
+            if (kh == 1 && kw == 1) px[q * 4 + ci] = x;
+            const int wi = ((kh * 3 + kw) * 3 + ci) * 3;
+            acc0 = fmaf(lw[wi], x, acc0);
+            acc1 = fmaf(lw[wi + 1], x, acc1);
+            acc2 = fmaf(lw[wi + 2], x, acc2);
+          }
       px[q * 4 + 3] = 0.f;
-#pragma unroll
-      for (int co = 0; co < 3; ++co) {
-        float acc = 0.f;
-#pragma unroll
-        for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-          for (int kw = 0; kw < 3; ++kw)
-#pragma unroll
-            for (int ci = 0; ci < 3; ++ci) acc = fmaf(lw[((kh * 3 + kw) * 3 + ci) * 3 + co], v[kh][j + kw][ci], acc);
-        lp[q * 4 + co] = (p0 + j < W) ? acc : 0.f;
-      }
-      lp[q * 4 + 3] = 0.f;
+      lp[q * 4 + 0] = acc0; lp[q * 4 + 1] = acc1; lp[q * 4 + 2] = acc2; lp[q * 4 + 3] = 0.f;
     }
-    *reinterpret_cast<uint4*>(xs + dst0 + u * 8) = pack8(px);
-    *reinterpret_cast<uint4*>(xl + dst0 + u * 8) = pack8(lp);
+    *reinterpret_cast<uint4*>(xs + row_dst + (int64_t)p0 * 4) = pack8(px);
+    *reinterpret_cast<uint4*>(xl + row_dst + (int64_t)p0 * 4) = pack8(lp);
   }
 }
 void launch_video_rows(const void* video, int dtype, int layout, const float* lapw, __nv_bfloat16* xs, __nv_bfloat16* xl,
                        int64_t set_stride, UcGeom g, int H, int W, cudaStream_t s) {
-  const int64_t total = (int64_t)g.N * g.T * H * ((W + 7) / 8);
-  if (total == 0) return;
-  const unsigned grid = (unsigned)((total + 127) / 128);
-#define VR(TT, LL, DIV) video_rows_kernel<TT, LL><<<grid, 128, 0, s>>>(reinterpret_cast<const TT*>(video), lapw, xs, xl, set_stride, g, g.T, H, W, total, DIV)
+  const int bands = (H + VR_ROWS - 1) / VR_ROWS;
+  const int64_t blocks = (int64_t)g.N * g.T * bands;
+  if (blocks == 0) return;
+  const size_t smem = (size_t)3 * (VR_ROWS + 2) * (W + 2) * sizeof(float);
+#define VR(TT, LL, DIV) video_rows_kernel<TT, LL><<<(unsigned)blocks, dim3(32, 8), smem, s>>>(reinterpret_cast<const TT*>(video), lapw, xs, xl, set_stride, g, g.T, H, W, bands, 1.0f / (DIV))
   if (layout == 0) {
     if (dtype == 0) VR(float, 0, 1.0f); else if (dtype == 1) VR(__half, 0, 1.0f); else if (dtype == 2) VR(__nv_bfloat16, 0, 1.0f); else VR(uint8_t, 0, 255.0f);
   } else {
