@@ -102,18 +102,53 @@ class Predictor:
     # ------------------------------------------------------------------ scoring
     def _infer_logits(self, visuals: Sequence[np.ndarray], audios: Sequence[np.ndarray]) -> List[float]:
         """Batched forward over host windows of one common shape, `batch_size` windows per launch."""
-        out: List[float] = []
         n = len(visuals)
-        for i0 in range(0, n, self.batch_size):
-            v = torch.from_numpy(np.stack(visuals[i0:i0 + self.batch_size]))
-            a = torch.from_numpy(np.stack(audios[i0:i0 + self.batch_size]))
-            if self.use_half_precision:
-                v, a = v.half(), a.half()
-            v = v.to(self.device, non_blocking=True)
-            a = a.to(self.device, non_blocking=True)
-            logits = self.model(v, a)
-            out.extend(float(x) for x in logits.float().cpu().tolist())
+
+        def gen():
+            for i0 in range(0, n, self.batch_size):
+                v = torch.from_numpy(np.stack(visuals[i0:i0 + self.batch_size])).pin_memory()
+                a = torch.from_numpy(np.stack(audios[i0:i0 + self.batch_size])).pin_memory()
+                yield v, a
+
+        out: List[float] = []
+        for t in self.score_batches(gen()):
+            out.extend(float(x) for x in t.tolist())
         return out
+
+    def score_batches(self, batches) -> List[torch.Tensor]:
+        """Pipelined scoring of a sequence of HOST batches `(visual (B,3,T,H,W), audio (B,1,F,Ta))` (torch CPU tensors, ideally
+        pinned): the H2D copy of batch k+1 runs on a copy stream while batch k is scored, logits come back through pinned
+        memory.  Returns one fp32 CPU tensor of logits per batch.  Same numerics as calling the model batch by batch."""
+        dev = self.device
+        m = self.model
+        comp = torch.cuda.current_stream(dev)
+        copy = getattr(self, "_copy_stream", None)
+        if copy is None:
+            copy = self._copy_stream = torch.cuda.Stream(dev)
+        slots = [None, None]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        free = [torch.cuda.Event(), torch.cuda.Event()]
+        outs: List[torch.Tensor] = []
+        for k, (vh, ah) in enumerate(batches):
+            s = k & 1
+            if self.use_half_precision:
+                vh, ah = vh.half(), ah.half()
+            if slots[s] is None or slots[s][0].shape != vh.shape or slots[s][0].dtype != vh.dtype or slots[s][1].shape != ah.shape:
+                slots[s] = (torch.empty(vh.shape, dtype=vh.dtype, device=dev), torch.empty(ah.shape, dtype=ah.dtype, device=dev))
+                free[s].record(comp)
+            with torch.cuda.stream(copy):
+                copy.wait_event(free[s])          # the forward that last read this slot has finished
+                slots[s][0].copy_(vh, non_blocking=True)
+                slots[s][1].copy_(ah, non_blocking=True)
+                ready[s].record(copy)
+            comp.wait_event(ready[s])
+            logits = m(slots[s][0], slots[s][1])
+            free[s].record(comp)
+            host = torch.empty(logits.shape, dtype=torch.float32, pin_memory=True)
+            host.copy_(logits.float(), non_blocking=True)
+            outs.append(host)
+        comp.synchronize()
+        return outs
 
     def _infer_confidences(self, visuals: Sequence[np.ndarray], audios: Sequence[np.ndarray]) -> List[float]:
         return [self._calibrate(l) for l in self._infer_logits(visuals, audios)]
