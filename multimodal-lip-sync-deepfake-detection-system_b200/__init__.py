@@ -7,7 +7,8 @@ sm_100a CUDA library `csrc/` through its C-ABI (`include/lsd_b200.h`).  There is
 from .state_spec import state_spec, make_synthetic_state_dict, synthetic_windows, BUFFER_SUFFIXES  # noqa: F401
 from .model import LipSyncModel  # noqa: F401
 from .inference import Predictor, partition_windows, gather_logits  # noqa: F401
+from .aggregate import aggregate_long_video, select_windows_by_time  # noqa: F401
 from .audio import preprocess_audio, preprocess_audio_pcm, logmel_db, fit_frames  # noqa: F401
 
 __all__ = ["state_spec", "make_synthetic_state_dict", "synthetic_windows", "LipSyncModel", "Predictor",
-           "partition_windows", "gather_logits", "preprocess_audio", "preprocess_audio_pcm", "logmel_db", "fit_frames"]
+           "partition_windows", "gather_logits", "aggregate_long_video", "select_windows_by_time", "preprocess_audio", "preprocess_audio_pcm", "logmel_db", "fit_frames"]

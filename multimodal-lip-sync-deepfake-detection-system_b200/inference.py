@@ -293,6 +293,13 @@ class Predictor:
         confs = [self._calibrate(float(x)) for x in logits.cpu().tolist()]
         return self._robust_confidence(confs), confs
 
+    # ------------------------------------------------------------------ decision (predictor.py:856-1155, :1235)
+    def aggregate_long_video(self, window_confs, window_speaking, window_vad_weights=None, mouth_check_result: str = "no_data", **gates):
+        """Final `real` / `fake` / `uncertain` decision from per-window confidences; see `lipsync_b200.aggregate`."""
+        from .aggregate import aggregate_long_video
+        return aggregate_long_video(window_confs, window_speaking, window_vad_weights, mouth_check_result,
+                                    confidence_smoothing=self.confidence_smoothing, trim_ratio=self.trim_ratio, **gates)
+
     # ------------------------------------------------------------------ multi-GPU (SURVEY.md §8e)
     def score_windows_sharded(self, n_windows: int, score_range: Callable[[int, int], torch.Tensor],
                               world_size: int, rank: int) -> torch.Tensor:

@@ -197,6 +197,33 @@ def test_score_track_device_window_builder(model, prec):
         p.score_track_logits(track.cuda(), [n_frames - 8], mel.cuda(), n_frames)
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_long_video_decision_matches_oracle(model, seed0_sd, prec):
+    """Decision level: per-window confidences from the CUDA scorer and from the CPU oracle lead to the same
+    real / fake / uncertain verdict through the (reference-pinned) aggregation and gate block."""
+    model.compute_precision = prec
+    g = torch.Generator().manual_seed(41)
+    n_win = 12
+    n_frames = 32 + 8 * (n_win - 1)
+    track = torch.randint(0, 256, (n_frames, 96, 96, 3), generator=g, dtype=torch.uint8)
+    mel = -80.0 * torch.rand((1, 80, int(n_frames / 15 * 100)), generator=g)
+    starts = list(range(0, n_frames - 32 + 1, 8))
+    speaking = torch.rand(n_win, generator=g).tolist()
+    vad = torch.rand(n_win, generator=g).tolist()
+    p = lb.Predictor(model, batch_size=8)
+    _, confs = p.score_track(track.cuda(), starts, mel.cuda(), n_frames)
+    vis = torch.stack([track[s:s + 32] for s in starts]).permute(0, 4, 1, 2, 3).float() / 255.0
+    aud = torch.stack([torch.from_numpy(p._align_audio_chunk(mel.numpy(), s, n_frames)) for s in starts])
+    ref_confs = torch.sigmoid(orc.forward(seed0_sd, vis, aud)).tolist()
+    tol = 1e-4 if prec == "fp32" else 5e-3   # on probabilities (sigmoid slope <= 1/4 of the logit tolerance)
+    assert np.abs(np.asarray(confs) - np.asarray(ref_confs)).max() <= tol
+    for gate in (0.15, 0.10):
+        a = p.aggregate_long_video(confs, speaking, vad, "no_issue", fake_vote_gate=gate)
+        b = p.aggregate_long_video(ref_confs, speaking, vad, "no_issue", fake_vote_gate=gate)
+        assert a["verdict"] == b["verdict"] and a["override_reason"] == b["override_reason"]
+        assert abs(a["confidence"] - b["confidence"]) <= 2 * tol
+
+
 @pytest.mark.parametrize("name", list(MEL_CASES))
 def test_logmel_matches_oracle(built, name):
     y = make_pcm(name)
