@@ -127,7 +127,8 @@ int64_t lsd_launch_count(lsd_handle* h);
  * convolution / linear kernel of the selected precision) is bracketed by CUDA events on the launching stream.
  * lsd_profile_get synchronises on the recorded events, returns their summed duration, the launch count and the
  * algorithmic FLOPs (2*M*N*K per launch, padding taps counted as dense), and resets the accumulators. */
-int lsd_profile_enable(lsd_handle* h, int kernel_class); /* 0 off, 1 fp32 conv kernel, 2 tcgen05 conv kernel */
+int lsd_profile_enable(lsd_handle* h, int kernel_class); /* 0 off, 1 fp32 conv kernel, 2 tcgen05 kernel: 3-D conv visual encoder launches,
+                                                             3 tcgen05 kernel: all other launches (audio encoder, token GEMMs, artifact branch) */
 int lsd_profile_get(lsd_handle* h, double* kernel_ms, int64_t* launches, double* flops);
 
 #ifdef __cplusplus

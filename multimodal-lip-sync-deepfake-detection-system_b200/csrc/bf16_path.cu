@@ -320,6 +320,7 @@ struct BCtx {
   char* ws;
   const BPlan* P;
   cudaStream_t st;
+  int max_ctas = 0;        // > 0: persistent grids of this context are limited (side stream shares the GPU with the main one)
   __nv_bfloat16* base(const PBuf& b) const { return reinterpret_cast<__nv_bfloat16*>(ws + b.off); }
   __nv_bfloat16* org(const PBuf& b) const { return base(b) + b.origin; }
   float* f(const char* name) const { return reinterpret_cast<float*>(ws + P->f32.find(name)); }
@@ -456,7 +457,7 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
     if (!dbuf) cudaMalloc(&dbuf, 512);
     cudaMemsetAsync(dbuf, 0, 512, c.st);
     p.dbg = dbuf;
-    launch_umma_conv(p, slices, c.st);
+    launch_umma_conv(p, slices, c.st, c.max_ctas);
     long long hv[64];
     cudaMemcpyAsync(hv, dbuf, 512, cudaMemcpyDeviceToHost, c.st);
     cudaStreamSynchronize(c.st);
@@ -472,8 +473,10 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
     }
     return 0;
   }
-  c.h->prof.begin(c.st, 2.0 * (double)og.N * og.T * og.H * og.W * L.Cout * kflop, 2);
-  launch_umma_conv(p, slices, c.st);
+  // profile classes: 2 = 3-D conv visual encoder (stem + residual stages, 86 % of the FLOPs, runs alone on the GPU),
+  //                  3 = every other tcgen05 launch (audio encoder, token GEMMs, artifact branch on the side stream)
+  c.h->prof.begin(c.st, 2.0 * (double)og.N * og.T * og.H * og.W * L.Cout * kflop, name.rfind("visual_encoder.", 0) == 0 ? 2 : 3);
+  launch_umma_conv(p, slices, c.st, c.max_ctas);
   c.h->prof.end(c.st);
   return 0;
 }
@@ -483,6 +486,13 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
     UArgs a_;                                     \
     __VA_ARGS__;                                  \
     if ((rc = run_umma(b, name, a_))) return rc;  \
+  } while (0)
+
+#define RUNS(name, ...)                            \
+  do {                                             \
+    UArgs a_;                                      \
+    __VA_ARGS__;                                   \
+    if ((rc = run_umma(bs, name, a_))) return rc;  \
   } while (0)
 
 PlanarOut pout(const BCtx& c, const PBuf& p, const PBuf* lo = nullptr, int plane_off = 0) {
@@ -594,6 +604,36 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   const PBuf& y4 = pb["y4"];
   // spatial mean -> visual tokens (fp32 stage + planar GEMM input)
   launch_planar_mean2(b.org(y4), y4.plane_stride, y4.g, 256, b.f("v_feat"), 256, 0, pout(b, pb["vfeat_p"], &pb["vfeat_p_lo"]), st);
+  // ---- artifact detector (artifact_detector.py:149-183) on a side stream: its convolutions (hf front/back on the laplacian
+  // rows, temporal-inconsistency convs on the feature map and on its temporal delta) only need the visual encoder's
+  // output, so they run concurrently with the audio encoder + token path, whose small grids leave most SMs idle.
+  if (!h->side_stream) {
+    if (cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess)
+      return lsd_fail(h, LSD_ERR_CUDA, "side stream creation failed");
+  }
+  cudaStream_t sst = h->side_stream;
+  BCtx bs{h, ws, &P, sst};
+  bs.max_ctas = (h->num_sms * 5) / 8;
+  cudaEventRecord(h->ev_fork, st);
+  cudaStreamWaitEvent(sst, h->ev_fork, 0);
+  float* comb = b.f("comb");
+  PlanarOut none{nullptr, nullptr, 0, 0, 0, 0};
+  RUNS("art.td0", a_.in = &y4; a_.og = y4.g; a_.act = ACT_RELU; a_.yp = &pb["art_a"]);
+  RUNS("art.td3", a_.in = &pb["art_a"]; a_.og = y4.g; a_.act = ACT_RELU; a_.yp = &pb["art_b"]);
+  launch_planar_mean2(bs.org(pb["art_b"]), pb["art_b"].plane_stride, y4.g, 64, comb + 256, 448, 1, none, sst);
+  const PBuf& dl = pb["delta"];
+  if (T > 1) launch_planar_delta(bs.org(y4), y4.plane_stride, y4.g, bs.org(dl), dl.plane_stride, dl.g, 256, sst);
+  // (T == 1: the delta map is all zeros — the buffer is never written and keeps its zero initialisation)
+  RUNS("art.td0", a_.in = &dl; a_.og = dl.g; a_.act = ACT_RELU; a_.yp = &pb["artd_a"]);
+  RUNS("art.td3", a_.in = &pb["artd_a"]; a_.og = dl.g; a_.act = ACT_RELU; a_.yp = &pb["artd_b"]);
+  launch_planar_mean2(bs.org(pb["artd_b"]), pb["artd_b"].plane_stride, dl.g, 64, comb + 320, 448, 1, none, sst);
+  // high-frequency branch: Conv3d 3->32 s(1,2,2) on the laplacian pixel rows (Toeplitz K), Conv3d 32->64 s(1,2,2) planar
+  const PBuf& hf = pb["hf_f"];
+  RUNS("art.hf0", a_.in = &xl; a_.og = xl.g; a_.act = ACT_RELU; a_.yp = &hf);
+  RUNS("art.hf3", a_.in = &hf; a_.og = hf.g; a_.act = ACT_RELU; a_.yp = &pb["hf_b"]);
+  launch_planar_mean2(bs.org(pb["hf_b"]), pb["hf_b"].plane_stride, hf.g, 64, comb + 384, 448, 1, none, sst);
+  cudaEventRecord(h->ev_join, sst);
   // ---- audio encoder (audio_encoder.py:173-205) on tcgen05
   const PBuf &xa = pb["xa"], &sao = pb["sa_out"], &a1 = pb["a1"];
   if (inputs_ready) launch_audio_rows(b.f("aud"), LSD_F32, b.org(xa), xa.set_stride, xa.g, s.F, s.Ta, st);
@@ -647,24 +687,8 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
     RUN(k + ".ff2", a_.in = &pb["tokff_p"]; a_.in_lo = &pb["tokff_p_lo"]; a_.og = g33; a_.res32 = tok; a_.res32_ld = 256; a_.y32 = tok; a_.y32_ld = 256);
   }
   // cls = tok[:,0]: no final norm (temporal.py:110-111)
-  float* comb = b.f("comb");
   launch_copy_rows(tok, (int64_t)NT * 256, comb, 448, B, 256, st);
-  // ---- artifact detector (artifact_detector.py:149-183)
-  PlanarOut none{nullptr, nullptr, 0, 0, 0, 0};
-  RUN("art.td0", a_.in = &y4; a_.og = y4.g; a_.act = ACT_RELU; a_.yp = &pb["art_a"]);
-  RUN("art.td3", a_.in = &pb["art_a"]; a_.og = y4.g; a_.act = ACT_RELU; a_.yp = &pb["art_b"]);
-  launch_planar_mean2(b.org(pb["art_b"]), pb["art_b"].plane_stride, y4.g, 64, comb + 256, 448, 1, none, st);
-  const PBuf& dl = pb["delta"];
-  if (T > 1) launch_planar_delta(b.org(y4), y4.plane_stride, y4.g, b.org(dl), dl.plane_stride, dl.g, 256, st);
-  // (T == 1: the delta map is all zeros — the buffer is never written and keeps its zero initialisation)
-  RUN("art.td0", a_.in = &dl; a_.og = dl.g; a_.act = ACT_RELU; a_.yp = &pb["artd_a"]);
-  RUN("art.td3", a_.in = &pb["artd_a"]; a_.og = dl.g; a_.act = ACT_RELU; a_.yp = &pb["artd_b"]);
-  launch_planar_mean2(b.org(pb["artd_b"]), pb["artd_b"].plane_stride, dl.g, 64, comb + 320, 448, 1, none, st);
-  // high-frequency branch: Conv3d 3->32 s(1,2,2) on the laplacian pixel rows (Toeplitz K), Conv3d 32->64 s(1,2,2) planar
-  const PBuf& hf = pb["hf_f"];
-  RUN("art.hf0", a_.in = &xl; a_.og = xl.g; a_.act = ACT_RELU; a_.yp = &hf);
-  RUN("art.hf3", a_.in = &hf; a_.og = hf.g; a_.act = ACT_RELU; a_.yp = &pb["hf_b"]);
-  launch_planar_mean2(b.org(pb["hf_b"]), pb["hf_b"].plane_stride, hf.g, 64, comb + 384, 448, 1, none, st);
+  cudaStreamWaitEvent(st, h->ev_join, 0);   // artifact features (comb[:, 256:448]) are complete
   // ---- artifact fusion MLP + classification head, fused, fp32 (artifact_detector.py:142-147,180-181; classifier.py:14-34)
   HeadW hw;
   auto cw = [&](const char* key) { return h->warena + h->convs.at(key).w_off; };

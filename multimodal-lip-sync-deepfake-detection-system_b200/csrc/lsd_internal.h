@@ -63,6 +63,8 @@ struct lsd_handle {
   std::vector<Stage> stages;
   std::vector<int32_t> idx_host;
   Prof prof;
+  cudaStream_t side_stream = nullptr;      // artifact branch runs here, concurrently with the token path
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int64_t launches0 = 0;
   // log-mel tables (device): hann[400], cos[400], sin[400], melw[80*32], lo[80], cnt[80]
   void* mel_tables = nullptr;

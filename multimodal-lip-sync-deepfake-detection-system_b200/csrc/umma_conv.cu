@@ -229,10 +229,22 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
         else if (valid && p.y_mode == UC_Y_PARITY_H)
           dst = (int64_t)((h & 1) * 2) * p.y_set_stride + uc_flat(p.g2, n, t, h >> 1, w) * 8;
         const bool store_planar = (p.y_mode == UC_Y_PLAIN && inrange) || (p.y_mode >= UC_Y_PARITY && valid);
+        // this warp's columns: [half*Cout/2, (half+1)*Cout/2), in chunks of up to 32 (4 steps of 8 columns)
+        const int cbeg = half * (p.Cout >> 1), cend = cbeg + (p.Cout >> 1);
 #pragma unroll 1
-        for (int c0 = half * 32; c0 < p.Cout; c0 += 64) {
+        for (int c0 = cbeg; c0 < cend; c0 += 32) {
+          const int nq = min(4, (cend - c0) >> 3);
+          // residual prefetch for the whole chunk: the global-load latency is paid once, not once per 8-column step
+          uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = r0;
+          if (valid && p.res) {
+            const __nv_bfloat16* rp = p.res + (int64_t)((ch0 + c0) >> 3) * p.res_plane_stride + P * 8;
+            r0 = *reinterpret_cast<const uint4*>(rp);
+            if (nq > 1) r1 = *reinterpret_cast<const uint4*>(rp + p.res_plane_stride);
+            if (nq > 2) r2 = *reinterpret_cast<const uint4*>(rp + 2 * p.res_plane_stride);
+            if (nq > 3) r3 = *reinterpret_cast<const uint4*>(rp + 3 * p.res_plane_stride);
+          }
 #pragma unroll 1
-          for (int q = 0; q < 4; ++q) {   // 8 columns per step keeps the epilogue code small (instruction cache)
+          for (int q = 0; q < nq; ++q) {   // 8 columns per step keeps the epilogue code small (instruction cache)
             const int c = c0 + 8 * q;
             float v[8];
             tmem_ld8(tb + (uint32_t)(m * p.Cout + c), v);
@@ -243,7 +255,8 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
               v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
               if (p.res) {
                 float f[8];
-                unpack8(*reinterpret_cast<const uint4*>(p.res + (int64_t)((ch0 + c) >> 3) * p.res_plane_stride + P * 8), f);
+                const uint4 rr = q == 0 ? r0 : (q == 1 ? r1 : (q == 2 ? r2 : r3));
+                unpack8(rr, f);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] += f[e];
                 if (p.res_lo) {
@@ -254,8 +267,8 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
               }
               if (p.res32) {
                 const float4* r4 = reinterpret_cast<const float4*>(p.res32 + (outer * p.g.W + w) * p.res32_ld + ch0 + c);
-                const float4 r0 = r4[0], r1 = r4[1];
-                v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+                const float4 q0 = r4[0], q1 = r4[1];
+                v[0] += q0.x; v[1] += q0.y; v[2] += q0.z; v[3] += q0.w; v[4] += q1.x; v[5] += q1.y; v[6] += q1.z; v[7] += q1.w;
               }
               if (p.act == ACT_GELU) {
 #pragma unroll
@@ -304,7 +317,7 @@ done:
 
 size_t umma_conv_smem_bytes(const UmmaConvP& p) { return (size_t)p.stages * (p.a_stage_bytes + p.w_stage_bytes) + 1024; }
 
-void launch_umma_conv(const UmmaConvP& p, int n_slices, cudaStream_t s) {
+void launch_umma_conv(const UmmaConvP& p, int n_slices, cudaStream_t s, int max_ctas) {
   static bool attr_set = false;
   if (!attr_set) {
     // the opt-in limit (227 KB) covers static + dynamic shared memory; ~1.3 KB is static (barriers, bias)
@@ -316,7 +329,8 @@ void launch_umma_conv(const UmmaConvP& p, int n_slices, cudaStream_t s) {
   static int num_sms = 0;
   if (num_sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
   // persistent grid: one CTA per SM (per Cout slice), each walking tiles with stride gridDim.x
-  int gx = (num_sms + n_slices - 1) / n_slices;
+  const int budget = (max_ctas > 0 && max_ctas < num_sms) ? max_ctas : num_sms;   // side-stream launches leave SMs to the main stream
+  int gx = (budget + n_slices - 1) / n_slices;
   gx = gx < 1 ? 1 : (gx > tiles ? tiles : gx);
   umma_conv_kernel<<<dim3(gx, n_slices), UC_THREADS, umma_conv_smem_bytes(p), s>>>(p);
   count_launch();

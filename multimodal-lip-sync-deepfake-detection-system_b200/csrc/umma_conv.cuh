@@ -80,7 +80,7 @@ struct UmmaConvP {
 };
 
 size_t umma_conv_smem_bytes(const UmmaConvP& p);
-void launch_umma_conv(const UmmaConvP& p, int n_slices, cudaStream_t s);
+void launch_umma_conv(const UmmaConvP& p, int n_slices, cudaStream_t s, int max_ctas = 0);
 
 // ---- planar-layout glue --------------------------------------------------------------------------
 // fp32 channels-last (N,T,H,W,C) -> padded planar bf16 (plain, or parity-split when parity != 0); pads are NOT written.
