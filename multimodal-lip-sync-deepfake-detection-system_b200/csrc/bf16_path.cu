@@ -378,9 +378,15 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
   // the fills per MMA are minimised: wide layers (>= 128 columns) give all 512 TMEM columns to one tile (more M-tiles per
   // weight stage; their K loop is so long that the un-overlapped epilogue is a few %), narrow layers keep two
   // accumulator buffers so that the epilogue overlaps the next tile.  MT shrinks while the tiles cannot fill the SMs.
-  p.nbuf = L.ntile >= 128 ? 1 : 2;
-  p.MT = std::max(1, std::min(4, 512 / (p.nbuf * L.ntile)));
+  const int mt2 = std::max(1, std::min(4, 256 / L.ntile));   // M-tiles per tile with two accumulator buffers
+  p.MT = std::max(1, std::min(4, 512 / L.ntile));             // ... with one
   while (p.MT > 1 && ((og.P_total + p.MT * 128 - 1) / (p.MT * 128)) * slices < c.h->num_sms) p.MT /= 2;
+  p.nbuf = (p.MT <= mt2 && 2 * p.MT * L.ntile <= 512) ? 2 : 1;  // single buffering only when it buys a larger tile
+  if (const char* e = getenv("LSD_UMMA_NBUF")) {               // tuning knob
+    const int v = atoi(e);
+    if (v == 1) p.nbuf = 1;
+    if (v == 2 && 2 * L.ntile <= 512) { p.nbuf = 2; p.MT = std::min(p.MT, mt2); }
+  }
   uint32_t cols = 32;
   while ((int)cols < p.nbuf * p.MT * L.ntile) cols *= 2;
   p.tmem_cols = cols;
