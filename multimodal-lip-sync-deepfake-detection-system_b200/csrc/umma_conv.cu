@@ -580,34 +580,56 @@ __global__ void __launch_bounds__(256) video_rows_kernel(const T* __restrict__ v
   __syncthreads();
   const int h = h0 + ty;
   if (h >= H) return;
-  const int WP = (W + 1) / 2;
+  // each thread produces strips of 4 consecutive pixels (two 16-byte units): the 3x6 neighbourhood and every laplacian
+  // weight are read from shared memory once per strip instead of once per pixel
   const int64_t row_dst = (int64_t)(h & 1) * set_stride + uc_flat(g, n, t, h >> 1, 0) * 8 + 16;
-  for (int wp = tx; wp < WP; wp += 32) {
-    const int p0 = 2 * wp;
-    float px[8], lp[8];
+  for (int p0 = 4 * tx; p0 < W; p0 += 128) {
+    float acc[4][3];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int pc = p0 + q;   // pixel column; tile column = pc + 1
-      const bool in = pc < W;
-      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+    for (int q = 0; q < 4; ++q) acc[q][0] = acc[q][1] = acc[q][2] = 0.f;
+    float ctr[4][3];
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh)
+    for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw)
+      for (int ci = 0; ci < 3; ++ci) {
+        float x[6];
+        const float* trow = &tile[ci * per_c + (ty + kh) * WP2 + p0];
 #pragma unroll
-          for (int ci = 0; ci < 3; ++ci) {
-            const float x = in ? tile[ci * per_c + (ty + kh) * WP2 + pc + kw] : 0.f;
-            if (kh == 1 && kw == 1) px[q * 4 + ci] = x;
-            const int wi = ((kh * 3 + kw) * 3 + ci) * 3;
-            acc0 = fmaf(lw[wi], x, acc0);
-            acc1 = fmaf(lw[wi + 1], x, acc1);
-            acc2 = fmaf(lw[wi + 2], x, acc2);
+        for (int j = 0; j < 6; ++j) x[j] = (p0 + j < WP2) ? trow[j] : 0.f;   // tile columns p0 .. p0+5 <-> pixels p0-1 .. p0+4
+        if (kh == 1) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) ctr[q][ci] = x[q + 1];
+        }
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int wi = ((kh * 3 + kw) * 3 + ci) * 3;
+          const float w0 = lw[wi], w1 = lw[wi + 1], w2 = lw[wi + 2];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            acc[q][0] = fmaf(w0, x[q + kw], acc[q][0]);
+            acc[q][1] = fmaf(w1, x[q + kw], acc[q][1]);
+            acc[q][2] = fmaf(w2, x[q + kw], acc[q][2]);
           }
-      px[q * 4 + 3] = 0.f;
-      lp[q * 4 + 0] = acc0; lp[q * 4 + 1] = acc1; lp[q * 4 + 2] = acc2; lp[q * 4 + 3] = 0.f;
+        }
+      }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (p0 + 2 * u >= W) break;
+      float px[8], lp[8];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const bool in = p0 + 2 * u + q < W;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          px[q * 4 + c] = in ? ctr[2 * u + q][c] : 0.f;
+          lp[q * 4 + c] = in ? acc[2 * u + q][c] : 0.f;
+        }
+        px[q * 4 + 3] = 0.f;
+        lp[q * 4 + 3] = 0.f;
+      }
+      *reinterpret_cast<uint4*>(xs + row_dst + (int64_t)(p0 + 2 * u) * 4) = pack8(px);
+      *reinterpret_cast<uint4*>(xl + row_dst + (int64_t)(p0 + 2 * u) * 4) = pack8(lp);
     }
-    *reinterpret_cast<uint4*>(xs + row_dst + (int64_t)p0 * 4) = pack8(px);
-    *reinterpret_cast<uint4*>(xl + row_dst + (int64_t)p0 * 4) = pack8(lp);
   }
 }
 void launch_video_rows(const void* video, int dtype, int layout, const float* lapw, __nv_bfloat16* xs, __nv_bfloat16* xl,
