@@ -68,6 +68,10 @@ __device__ __forceinline__ void unpack8(const uint4& r, float* v) {
 constexpr int UC_THREADS = 448;
 constexpr int UC_PROD_WARPS = 4, UC_MMA_WARP0 = 4, UC_EPI_WARP0 = 6, UC_EPI_WARPS = 8;
 
+// GENERIC = false: lean epilogue of the convolution layers (bias, ReLU/none, optional bf16 residual, planar / parity-split bf16
+// store).  GENERIC = true: everything (fp32 rows in/out, split-bf16 hi/lo outputs and residuals, GELU) for the audio encoder and
+// the token-path GEMMs.  Two instantiations keep each one small enough for the instruction cache.
+template <bool GENERIC>
 __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_constant__ UmmaConvP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2];
@@ -229,8 +233,33 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
         else if (valid && p.y_mode == UC_Y_PARITY_H)
           dst = (int64_t)((h & 1) * 2) * p.y_set_stride + uc_flat(p.g2, n, t, h >> 1, w) * 8;
         const bool store_planar = (p.y_mode == UC_Y_PLAIN && inrange) || (p.y_mode >= UC_Y_PARITY && valid);
-        // this warp's columns: [half*Cout/2, (half+1)*Cout/2), in chunks of up to 32 (4 steps of 8 columns)
+        // this warp's columns: [half*Cout/2, (half+1)*Cout/2)
         const int cbeg = half * (p.Cout >> 1), cend = cbeg + (p.Cout >> 1);
+        if constexpr (!GENERIC) {
+          // lean path: 8 columns (one 16-byte plane entry) per step, pointers advanced by one plane per step
+          __nv_bfloat16* yp = p.y + (int64_t)((ch0 + cbeg) >> 3) * p.y_plane_stride + dst;
+          const __nv_bfloat16* rp = p.res + (int64_t)((ch0 + cbeg) >> 3) * p.res_plane_stride + P * 8;
+          const bool has_res = p.res != nullptr && valid;
+          const float* bp = &bias_s[cbeg];
+          uint32_t ta = tb + (uint32_t)(m * p.Cout + cbeg);
+#pragma unroll 1
+          for (int c = cbeg; c < cend; c += 8, yp += p.y_plane_stride, rp += p.res_plane_stride, bp += 8, ta += 8) {
+            float v[8];
+            tmem_ld8(ta, v);
+            uint4 rr = make_uint4(0, 0, 0, 0);
+            if (has_res) rr = *reinterpret_cast<const uint4*>(rp);   // overlaps the TMEM load
+            const float4 b0 = *reinterpret_cast<const float4*>(bp);
+            const float4 b1 = *reinterpret_cast<const float4*>(bp + 4);
+            tmem_ld_wait();
+            float f[8];
+            unpack8(rr, f);
+            v[0] = fmaxf(v[0] + b0.x + f[0], act_lo); v[1] = fmaxf(v[1] + b0.y + f[1], act_lo);
+            v[2] = fmaxf(v[2] + b0.z + f[2], act_lo); v[3] = fmaxf(v[3] + b0.w + f[3], act_lo);
+            v[4] = fmaxf(v[4] + b1.x + f[4], act_lo); v[5] = fmaxf(v[5] + b1.y + f[5], act_lo);
+            v[6] = fmaxf(v[6] + b1.z + f[6], act_lo); v[7] = fmaxf(v[7] + b1.w + f[7], act_lo);
+            if (store_planar) *reinterpret_cast<uint4*>(yp) = valid ? pack8(v) : make_uint4(0, 0, 0, 0);
+          }
+        } else {
 #pragma unroll 1
         for (int c0 = cbeg; c0 < cend; c0 += 32) {
           const int nq = min(4, (cend - c0) >> 3);
@@ -300,6 +329,7 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
             }
           }
         }
+        }
       }
       // all TMEM reads of this warp are complete (wait::ld above): hand the buffer back to the MMA warp
       tc_fence_before();
@@ -321,7 +351,8 @@ void launch_umma_conv(const UmmaConvP& p, int n_slices, cudaStream_t s, int max_
   static bool attr_set = false;
   if (!attr_set) {
     // the opt-in limit (227 KB) covers static + dynamic shared memory; ~1.3 KB is static (barriers, bias)
-    cudaFuncSetAttribute(umma_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    cudaFuncSetAttribute(umma_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    cudaFuncSetAttribute(umma_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     attr_set = true;
   }
   const int S = p.MT * 128;
@@ -332,7 +363,9 @@ void launch_umma_conv(const UmmaConvP& p, int n_slices, cudaStream_t s, int max_
   const int budget = (max_ctas > 0 && max_ctas < num_sms) ? max_ctas : num_sms;   // side-stream launches leave SMs to the main stream
   int gx = (budget + n_slices - 1) / n_slices;
   gx = gx < 1 ? 1 : (gx > tiles ? tiles : gx);
-  umma_conv_kernel<<<dim3(gx, n_slices), UC_THREADS, umma_conv_smem_bytes(p), s>>>(p);
+  const bool generic = p.y32 || p.res32 || p.ylo || p.res_lo || p.act == ACT_GELU || p.y_mode == UC_Y_NONE;
+  if (generic) umma_conv_kernel<true><<<dim3(gx, n_slices), UC_THREADS, umma_conv_smem_bytes(p), s>>>(p);
+  else umma_conv_kernel<false><<<dim3(gx, n_slices), UC_THREADS, umma_conv_smem_bytes(p), s>>>(p);
   count_launch();
 }
 
