@@ -95,6 +95,19 @@ int lsd_forward(lsd_handle* h,
                 void* workspace, size_t workspace_bytes,
                 void* stream);
 
+/* ---- sub-paths of the forward (tensor-core route; same kernels and numerics as inside lsd_forward) ------- */
+/* AudioEncoder.forward (app/models/audio_encoder.py:173-205): log-mel windows (B,1,F,Ta), device, any float dtype
+ * -> feats_out (B, lsd_audio_tokens(Ta), 256) fp32 device rows (the reference returns the transpose (B,256,T')). */
+size_t lsd_audio_encoder_workspace_bytes(lsd_handle* h, int B, int F, int Ta);
+int lsd_audio_encoder(lsd_handle* h, const void* audio, int audio_dtype, int B, int F, int Ta, float* feats_out,
+                      void* workspace, size_t workspace_bytes, void* stream);
+/* CrossModalAttention.forward (app/models/fusion_module.py:54-87) followed by TemporalTransformer.forward
+ * (app/models/temporal.py:79-111): projected embeddings v_emb (B,T,256), a_emb (B,Ta_tokens,256), fp32 device
+ * -> fused_out (B,T,256) and/or cls_out (B,256), fp32 device (either may be NULL). */
+size_t lsd_token_path_workspace_bytes(lsd_handle* h, int B, int T, int Ta_tokens);
+int lsd_token_path(lsd_handle* h, const float* v_emb, const float* a_emb, int B, int T, int Ta_tokens,
+                   float* fused_out, float* cls_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- log-mel front end: replaces preprocess_audio's librosa calls (audio.py:80-91) ----------- */
 /* pcm: device fp32 mono 16 kHz, clips concatenated; clip c spans [clip_offsets[c], clip_offsets[c+1]).
  * mel_out: device fp32, clip c written as (80, frames_c) row-major at mel_offsets[c] (in floats),
@@ -111,10 +124,13 @@ int lsd_logmel(lsd_handle* h, const float* pcm, const int64_t* clip_offsets_host
  * Builds the windows on device and runs lsd_forward in batches of `batch`. */
 size_t lsd_score_workspace_bytes(lsd_handle* h, int batch, int T, int H, int W, int F, int Ta, int precision);
 int lsd_score_windows(lsd_handle* h, const uint8_t* track, int n_frames, int H, int W,
-                      const int32_t* starts_host, int n_windows, int T,
+                      const int32_t* starts_host, const int32_t* audio_starts_host_or_null, int n_windows, int T,
                       const float* mel_full, int F, int Ta_full, int total_v_frames, int Ta,
                       int precision, int batch, float* logits_out,
                       void* workspace, size_t workspace_bytes, void* stream);
+/* audio_starts_host_or_null: explicit first mel column per window (clamped like _align_audio_chunk).  A rank that holds
+ * only its own span of a sharded track passes span-relative `starts` and the audio starts computed from the absolute frame
+ * indices; NULL = computed here from `starts` as predictor.py:540-547 does. */
 
 /* ---- introspection (tests / profiling) ------------------------------------------------------- */
 /* Named intermediate of the last lsd_forward on this handle: byte offset into the workspace. */

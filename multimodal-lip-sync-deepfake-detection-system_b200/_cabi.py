@@ -25,6 +25,7 @@ EXPORTS = [
     "lsd_workspace_bytes", "lsd_forward", "lsd_logmel_frames", "lsd_logmel", "lsd_score_workspace_bytes",
     "lsd_score_windows", "lsd_stage_info", "lsd_stage_count", "lsd_stage_name", "lsd_launch_count",
     "lsd_profile_enable", "lsd_profile_get",
+    "lsd_audio_encoder_workspace_bytes", "lsd_audio_encoder", "lsd_token_path_workspace_bytes", "lsd_token_path",
 ]
 
 
@@ -64,7 +65,7 @@ def lib() -> C.CDLL:
         L.lsd_logmel_frames.argtypes = [i64]; L.lsd_logmel_frames.restype = i
         L.lsd_logmel.argtypes = [vp, vp, C.POINTER(i64), i, vp, C.POINTER(i64), vp, vp]; L.lsd_logmel.restype = i
         L.lsd_score_workspace_bytes.argtypes = [vp, i, i, i, i, i, i, i]; L.lsd_score_workspace_bytes.restype = sz
-        L.lsd_score_windows.argtypes = [vp, vp, i, i, i, C.POINTER(C.c_int32), i, i, vp, i, i, i, i, i, i, vp, vp, sz, vp]
+        L.lsd_score_windows.argtypes = [vp, vp, i, i, i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), i, i, vp, i, i, i, i, i, i, vp, vp, sz, vp]
         L.lsd_score_windows.restype = i
         L.lsd_stage_info.argtypes = [vp, C.c_char_p, C.POINTER(sz), C.POINTER(i64), C.POINTER(i)]; L.lsd_stage_info.restype = i
         L.lsd_stage_count.argtypes = [vp]; L.lsd_stage_count.restype = i
@@ -72,6 +73,10 @@ def lib() -> C.CDLL:
         L.lsd_launch_count.argtypes = [vp]; L.lsd_launch_count.restype = i64
         L.lsd_profile_enable.argtypes = [vp, i]; L.lsd_profile_enable.restype = i
         L.lsd_profile_get.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double)]; L.lsd_profile_get.restype = i
+        L.lsd_audio_encoder_workspace_bytes.argtypes = [vp, i, i, i]; L.lsd_audio_encoder_workspace_bytes.restype = sz
+        L.lsd_audio_encoder.argtypes = [vp, vp, i, i, i, i, vp, vp, sz, vp]; L.lsd_audio_encoder.restype = i
+        L.lsd_token_path_workspace_bytes.argtypes = [vp, i, i, i]; L.lsd_token_path_workspace_bytes.restype = sz
+        L.lsd_token_path.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp, sz, vp]; L.lsd_token_path.restype = i
         _lib = L
         return L
 

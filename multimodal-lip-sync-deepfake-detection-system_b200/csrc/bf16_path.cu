@@ -406,7 +406,9 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
     ug.w_off = (int64_t)G.w_off;
     ug.slice_stride = (int64_t)G.slice_stride;
     int tap_begin = 0;
-    const int tmax = std::max(1, std::min(UC_MAX_TAPS, (40 * 1024) / (L.ntile * 32)));   // keep a weight stage <= ~40 KB
+    int wkb = 40;                                                                        // keep a weight stage <= ~40 KB
+    if (const char* e = getenv("LSD_UMMA_WKB")) wkb = std::max(8, atoi(e));               // tuning knob
+    const int tmax = std::max(1, std::min(UC_MAX_TAPS, (wkb * 1024) / (L.ntile * 32)));
     for (const BBand& b : G.bands) {
       const int nt = (int)b.taps.size();
       const int pieces = (nt + tmax - 1) / tmax, per = (nt + pieces - 1) / pieces;
@@ -449,14 +451,21 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
   p.a_stage_bytes = ((uint32_t)(any_toeplitz ? max_a : max_a * p.kpack) + 127u) & ~127u;
   p.w_stage_bytes = (uint32_t)(w_chunk * p.kpack);
   const uint32_t stage = p.a_stage_bytes + p.w_stage_bytes;
-  const uint32_t budget = 212u * 1024u;   // one persistent CTA per SM owns the whole shared memory
-  int stages = (int)(budget / stage);
+  // stage program (one 64-byte descriptor per ring stage of a tile) lives behind the ring in shared memory
+  p.nst_tile = 0;
+  for (int gi = 0; gi < p.ngroups; ++gi)
+    p.nst_tile += ((p.groups[gi].k16 + p.kpack - 1) / p.kpack) * (p.groups[gi].band_end - p.groups[gi].band_begin);
+  const uint32_t prog_bytes = (uint32_t)p.nst_tile * (uint32_t)umma_conv_stage_desc_bytes();
+  const uint32_t budget = 211u * 1024u;   // one persistent CTA per SM owns the whole shared memory
+  if (prog_bytes + 2 * stage > budget) return lsd_fail(c.h, LSD_ERR_UNSUPPORTED, "%s: stage program of %u bytes does not fit", name.c_str(), prog_bytes);
+  int stages = (int)((budget - prog_bytes) / stage);
   stages = std::max(2, std::min(stages, 8));
-  if ((size_t)stages * stage + 1024 > 224u * 1024u) return lsd_fail(c.h, LSD_ERR_UNSUPPORTED, "%s: stage of %u bytes does not fit", name.c_str(), stage);
+  if ((size_t)stages * stage + prog_bytes + 1024 > 223u * 1024u) return lsd_fail(c.h, LSD_ERR_UNSUPPORTED, "%s: stage of %u bytes does not fit", name.c_str(), stage);
   p.stages = stages;
   double kflop = 0;
   for (const BGroup& G : L.groups) kflop += (double)G.taps_total * G.Cin;
   if (L.groups[0].toeplitz) { const ConvP& cp = c.h->convs.at(name); kflop = (double)cp.kt * cp.kh * cp.kw * cp.Cin; }  // algorithmic K, not the padded one
+  if (const char* e = getenv("LSD_UMMA_SKIP")) p.skip = atoi(e);
   if (const char* e = getenv("LSD_UMMA_TRACE")) {
     // debug: per-launch phase timestamps of CTA (0,0); prints after a sync (never enabled in timed runs)
     static long long* dbuf = nullptr;
@@ -475,6 +484,8 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
       for (int i = 0; i < 24 && hv[8 + i]; ++i) fprintf(stderr, " %lld", hv[8 + i] - hv[0]);
       fprintf(stderr, "\n        producer issue at:");
       for (int i = 0; i < 24 && hv[32 + i]; ++i) fprintf(stderr, " %lld", hv[32 + i] - hv[0]);
+      fprintf(stderr, "\n        copies issued at: ");
+      for (int i = 0; i < 8 && hv[56 + i]; ++i) fprintf(stderr, " %lld", hv[56 + i] - hv[0]);
       fprintf(stderr, "\n");
     }
     return 0;
@@ -532,9 +543,13 @@ int pack_bf16_weights(lsd_handle* h, const std::vector<float>& f32_arena) {
   for (int l = 1; l <= 4; ++l) {
     const std::string p = "visual_encoder.layer" + std::to_string(l);
     const int s = vstr[l - 1];
-    P.add(p + ".conv1", p + ".conv1", s, s, "", 0, false, /*merge_kt=*/l >= 2);   // 12x12 / 6x6 / 3x3 maps: one band per parity set
+    // Cout slice width per CTA (0 = all columns).  256-column layers run as two 128-column slices: a 128-column stage carries
+    // twice the MMA time per refill (4 M-tiles per weight stage instead of 2), measured 15-18 % faster than one 256-column slice.
+    int nt = l >= 3 ? 128 : 0;
+    if (const char* e = getenv(l == 3 ? "LSD_UMMA_NT3" : (l == 4 ? "LSD_UMMA_NT4" : "LSD_UMMA_NTX"))) nt = atoi(e);   // tuning knob
+    P.add(p + ".conv1", p + ".conv1", s, s, "", nt, false, /*merge_kt=*/l >= 2);   // 12x12 / 6x6 / 3x3 maps: one band per parity set
     P.ds_sh = 2; P.ds_sw = 2;
-    P.add(p + ".conv2", p + ".conv2", 1, 1, l == 1 ? "" : p + ".downsample");
+    P.add(p + ".conv2", p + ".conv2", 1, 1, l == 1 ? "" : p + ".downsample", nt);
   }
   P.add_toeplitz("visual_encoder.stem", "visual_encoder.stem", 8, 0);  // 7 taps in w -> 8-pixel window starting at 2*wo-4
   P.add_toeplitz("art.hf0", "art.hf0", 4, 1);                          // 3 taps in w -> 4-pixel window starting at 2*wo-2
@@ -551,13 +566,18 @@ int pack_bf16_weights(lsd_handle* h, const std::vector<float>& f32_arena) {
     P.ds_sh = ash[l - 1]; P.ds_sw = asw[l - 1];
     P.add(p + ".conv2", p + ".conv2", 1, 1, l == 1 ? "" : p + ".downsample", 0, true);
   }
-  // token path GEMMs: 64-column slices so that the small M (B*T rows) still spreads over the SMs
-  for (const char* k : {"projection.visual_proj", "projection.audio_proj", "cross.in_v", "cross.in_a", "cross.v2a.out", "cross.a2v.out",
+  // token path GEMMs: 64-column slices so that the small M (B*T rows) still spreads over the SMs; the wide ones (768 / 1024
+  // columns) use 128-column slices, which keeps B = 64 (17 M-tiles) inside one wave of CTAs
+  int wide = 128;
+  if (const char* e = getenv("LSD_UMMA_NTW")) wide = atoi(e);   // tuning knob
+  for (const char* k : {"projection.visual_proj", "projection.audio_proj", "cross.v2a.out", "cross.a2v.out",
                         "cross.gate0", "cross.fuse", "temporal.branch_k3", "temporal.branch_k5", "temporal.branch_k7",
                         "temporal.pre_scale_proj"})
     P.add_split(k, k, 64);
+  for (const char* k : {"cross.in_v", "cross.in_a"}) P.add_split(k, k, wide);
   for (int l = 0; l < 4; ++l)
-    for (const char* k : {".in", ".out", ".ff1", ".ff2"}) P.add_split("t" + std::to_string(l) + k, "t" + std::to_string(l) + k, 64);
+    for (const char* k : {".in", ".out", ".ff1", ".ff2"})
+      P.add_split("t" + std::to_string(l) + k, "t" + std::to_string(l) + k, (k[1] == 'i' || (k[1] == 'f' && k[3] == '1')) ? wide : 64);
   if (h->barena) { cudaFree(h->barena); h->barena = nullptr; }
   if (h->bbias) { cudaFree(h->bbias); h->bbias = nullptr; }
   cudaError_t e = cudaMalloc(&h->barena, P.w.size() * 2);
@@ -577,8 +597,78 @@ void make_plan_bf16(lsd_handle* h, int B, int T, int H, int W, int F, int Ta, st
   bytes = P.f32.cursor;
 }
 
+// AudioEncoder.forward (audio_encoder.py:173-205) on tcgen05: log-mel windows -> a_feat (B, A4, 256) fp32 + planar (hi, lo) copy
+static int audio_encoder_bf16(const BCtx& b, const Shapes& s, bool inputs_ready, const void* audio, int adt) {
+  const BPlan& P = *b.P;
+  auto pbf = [&](const char* n) -> const PBuf& { return P.pb.at(n); };
+  cudaStream_t st = b.st;
+  int rc = 0;
+  // ---- audio encoder (audio_encoder.py:173-205) on tcgen05
+  const PBuf &xa = pbf("xa"), &sao = pbf("sa_out"), &a1 = pbf("a1");
+  if (inputs_ready) launch_audio_rows(b.f("aud"), LSD_F32, b.org(xa), xa.set_stride, xa.g, s.F, s.Ta, st);
+  else launch_audio_rows(audio, adt, b.org(xa), xa.set_stride, xa.g, s.F, s.Ta, st);
+  RUN("audio_encoder.stem", a_.in = &xa; a_.og = xa.g; a_.act = ACT_RELU; a_.yp = &sao; a_.yp_lo = &pbf("sa_out_lo"));
+  launch_planar_maxpool(b.org(sao), sao.plane_stride, sao.g, b.org(a1), a1.plane_stride, a1.g, 64, st, b.org(pbf("sa_out_lo")), b.org(pbf("a1_lo")));
+  if ((rc = res_stage_umma(b, "audio_encoder.layer1", a1, pbf("a1a"), pbf("ya1"), false, UC_Y_PARITY, &pbf("a1_lo"), &pbf("a1a_lo"), &pbf("ya1_lo")))) return rc;
+  if ((rc = res_stage_umma(b, "audio_encoder.layer2", pbf("ya1"), pbf("a2a"), pbf("ya2"), true, UC_Y_PARITY_H, &pbf("ya1_lo"), &pbf("a2a_lo"), &pbf("ya2_lo")))) return rc;
+  if ((rc = res_stage_umma(b, "audio_encoder.layer3", pbf("ya2"), pbf("a3a"), pbf("ya3"), true, UC_Y_PARITY_H, &pbf("ya2_lo"), &pbf("a3a_lo"), &pbf("ya3_lo")))) return rc;
+  if ((rc = res_stage_umma(b, "audio_encoder.layer4", pbf("ya3"), pbf("a4a"), pbf("ya4"), true, UC_Y_PLAIN, &pbf("ya3_lo"), &pbf("a4a_lo"), &pbf("ya4_lo")))) return rc;
+  const PBuf& ya4 = pbf("ya4");
+  launch_planar_mean2(b.org(ya4), ya4.plane_stride, ya4.g, 256, b.f("a_feat"), 256, 2, pout(b, pbf("afeat_p"), &pbf("afeat_p_lo")), st,
+                      b.org(pbf("ya4_lo")));  // mean over F'
+  return 0;
+}
+
+// CrossModalAttention.forward + TemporalTransformer.forward (fusion_module.py:54-87, temporal.py:79-111): expects v_emb / a_emb
+// (fp32 rows) and vemb_p (planar hi, lo) in the workspace; leaves the fused tokens in "fused" and the transformer tokens in "tok".
+static int token_path_bf16(const BCtx& b, const Shapes& s) {
+  const BPlan& P = *b.P;
+  auto pbf = [&](const char* n) -> const PBuf& { return P.pb.at(n); };
+  cudaStream_t st = b.st;
+  const int B = s.B, T = s.T, TA = s.A4, NT = T + 1;
+  const UcGeom gt = P.gt;
+  int rc = 0;
+  // ---- cross-modal attention + gated fusion (fusion_module.py:54-87)
+  launch_lerp_tokens_p(b.f("a_emb"), b.f("a_int"), B, TA, T, 256, pout(b, pbf("aint_p"), &pbf("aint_p_lo")), st);
+  float *pv = b.f("proj_v"), *pa = b.f("proj_a"), *gi = b.f("gate_in");
+  RUN("cross.in_v", a_.in = &pbf("vemb_p"); a_.in_lo = &pbf("vemb_p_lo"); a_.og = gt; a_.y32 = pv; a_.y32_ld = 768);
+  RUN("cross.in_a", a_.in = &pbf("aint_p"); a_.in_lo = &pbf("aint_p_lo"); a_.og = gt; a_.y32 = pa; a_.y32_ld = 768);
+  launch_mha_core_p(pv, 768, pa + 256, 768, pa + 512, 768, B, T, T, 8, pout(b, pbf("att1_p"), &pbf("att1_p_lo")), st);  // v2a: Q=v, K/V=a
+  launch_mha_core_p(pa, 768, pv + 256, 768, pv + 512, 768, B, T, T, 8, pout(b, pbf("att2_p"), &pbf("att2_p_lo")), st);  // a2v: Q=a, K/V=v
+  RUN("cross.v2a.out", a_.in = &pbf("att1_p"); a_.in_lo = &pbf("att1_p_lo"); a_.og = gt; a_.res32 = b.f("v_emb"); a_.res32_ld = 256; a_.y32 = gi; a_.y32_ld = 512;
+      a_.yp = &pbf("gatein_p"); a_.yp_lo = &pbf("gatein_p_lo"));
+  RUN("cross.a2v.out", a_.in = &pbf("att2_p"); a_.in_lo = &pbf("att2_p_lo"); a_.og = gt; a_.res32 = b.f("a_int"); a_.res32_ld = 256; a_.y32 = gi + 256; a_.y32_ld = 512;
+      a_.yp = &pbf("gatein_p"); a_.yp_lo = &pbf("gatein_p_lo"); a_.y_plane_off = 32);
+  RUN("cross.gate0", a_.in = &pbf("gatein_p"); a_.in_lo = &pbf("gatein_p_lo"); a_.og = gt; a_.act = ACT_GELU; a_.y32 = b.f("gate_h"); a_.y32_ld = 256);
+  launch_gate_blend_p(b.f("gate_h"), b.W("cross.gate2.w"), b.W("cross.gate2.b"), gi, 512, gi + 256, 512, B * T, 256, pout(b, pbf("blend_p"), &pbf("blend_p_lo")), st);
+  RUN("cross.fuse", a_.in = &pbf("blend_p"); a_.in_lo = &pbf("blend_p_lo"); a_.og = gt; a_.act = ACT_RELU; a_.y32 = b.f("fused"); a_.y32_ld = 256; a_.yp = &pbf("fused_p"); a_.yp_lo = &pbf("fused_p_lo"));
+  // ---- temporal transformer (temporal.py:79-111)
+  RUN("temporal.branch_k3", a_.in = &pbf("fused_p"); a_.in_lo = &pbf("fused_p_lo"); a_.og = gt; a_.act = ACT_GELU; a_.yp = &pbf("mscat_p"); a_.yp_lo = &pbf("mscat_p_lo"); a_.y_plane_off = 0);
+  RUN("temporal.branch_k5", a_.in = &pbf("fused_p"); a_.in_lo = &pbf("fused_p_lo"); a_.og = gt; a_.act = ACT_GELU; a_.yp = &pbf("mscat_p"); a_.yp_lo = &pbf("mscat_p_lo"); a_.y_plane_off = 32);
+  RUN("temporal.branch_k7", a_.in = &pbf("fused_p"); a_.in_lo = &pbf("fused_p_lo"); a_.og = gt; a_.act = ACT_GELU; a_.yp = &pbf("mscat_p"); a_.yp_lo = &pbf("mscat_p_lo"); a_.y_plane_off = 64);
+  float* tok = b.f("tok");
+  launch_set_cls(b.W("temporal.cls"), tok, B, NT, 256, st);
+  // pre_scale_proj + residual, written straight into token rows 1..T of each window
+  RUN("temporal.pre_scale_proj", a_.in = &pbf("mscat_p"); a_.in_lo = &pbf("mscat_p_lo"); a_.og = gt; a_.res32 = b.f("fused"); a_.res32_ld = 256; a_.y32 = tok; a_.y32_ld = 256;
+      a_.y32_outer_stride = NT; a_.y32_row_off = 1);
+  const UcGeom g33 = P.g33;
+  for (int l = 0; l < 4; ++l) {
+    const std::string k = "t" + std::to_string(l);
+    launch_layernorm_p(tok, 256, b.W((k + ".ln1.w").c_str()), b.W((k + ".ln1.b").c_str()), B * NT, 256, pout(b, pbf("tokln_p"), &pbf("tokln_p_lo")), st);
+    RUN(k + ".in", a_.in = &pbf("tokln_p"); a_.in_lo = &pbf("tokln_p_lo"); a_.og = g33; a_.y32 = b.f("tok_qkv"); a_.y32_ld = 768);
+    const float* qkv = b.f("tok_qkv");
+    launch_mha_core_p(qkv, 768, qkv + 256, 768, qkv + 512, 768, B, NT, NT, 8, pout(b, pbf("tokatt_p"), &pbf("tokatt_p_lo")), st);
+    RUN(k + ".out", a_.in = &pbf("tokatt_p"); a_.in_lo = &pbf("tokatt_p_lo"); a_.og = g33; a_.res32 = tok; a_.res32_ld = 256; a_.y32 = tok; a_.y32_ld = 256);
+    launch_layernorm_p(tok, 256, b.W((k + ".ln2.w").c_str()), b.W((k + ".ln2.b").c_str()), B * NT, 256, pout(b, pbf("tokln_p"), &pbf("tokln_p_lo")), st);
+    RUN(k + ".ff1", a_.in = &pbf("tokln_p"); a_.in_lo = &pbf("tokln_p_lo"); a_.og = g33; a_.act = ACT_GELU; a_.yp = &pbf("tokff_p"); a_.yp_lo = &pbf("tokff_p_lo"));
+    RUN(k + ".ff2", a_.in = &pbf("tokff_p"); a_.in_lo = &pbf("tokff_p_lo"); a_.og = g33; a_.res32 = tok; a_.res32_ld = 256; a_.y32 = tok; a_.y32_ld = 256);
+  }
+  return 0;
+}
+
 static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, const lsd_aux* aux, char* ws, size_t ws_bytes,
-                             cudaStream_t st, bool inputs_ready, const void* video, int vdt, int vlayout, const void* audio, int adt) {
+                             cudaStream_t st, bool inputs_ready, const void* video, int vdt, int vlayout, const void* audio, int adt,
+                             const int32_t* vstarts = nullptr, int n_frames = 0) {
   BPlan P;
   build_plan(s, P);
   if (P.f32.cursor > ws_bytes) return lsd_fail(h, LSD_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", P.f32.cursor, ws_bytes);
@@ -598,7 +688,9 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   // ---- video -> bf16 pixel rows (+ per-frame laplacian conv), stem conv on tcgen05 (Toeplitz K), max-pool in planar layout
   const PBuf &xs = pb["xs"], &xl = pb["xl"], &so = pb["s_out"], &x1 = pb["x1"];
   const float* lapw = h->warena + h->convs.at("art.lap").w_off;
-  if (inputs_ready) launch_video_rows(b.f("vid"), LSD_F32, LSD_NDHWC, lapw, b.org(xs), b.org(xl), xs.set_stride, xs.g, s.H, s.W, st);
+  // (vstarts: the uint8 track is read in place, window n = frames vstarts[n] .. vstarts[n]+T-1 — no fp32 window copy)
+  if (vstarts) launch_video_rows(video, vdt, vlayout, lapw, b.org(xs), b.org(xl), xs.set_stride, xs.g, s.H, s.W, st, vstarts, n_frames);
+  else if (inputs_ready) launch_video_rows(b.f("vid"), LSD_F32, LSD_NDHWC, lapw, b.org(xs), b.org(xl), xs.set_stride, xs.g, s.H, s.W, st);
   else launch_video_rows(video, vdt, vlayout, lapw, b.org(xs), b.org(xl), xs.set_stride, xs.g, s.H, s.W, st);
   RUN("visual_encoder.stem", a_.in = &xs; a_.og = xs.g; a_.act = ACT_RELU; a_.yp = &so);
   launch_planar_maxpool(b.org(so), so.plane_stride, so.g, b.org(x1), x1.plane_stride, x1.g, 64, st);
@@ -640,58 +732,13 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   RUNS("art.hf3", a_.in = &hf; a_.og = hf.g; a_.act = ACT_RELU; a_.yp = &pb["hf_b"]);
   launch_planar_mean2(bs.org(pb["hf_b"]), pb["hf_b"].plane_stride, hf.g, 64, comb + 384, 448, 1, none, sst);
   cudaEventRecord(h->ev_join, sst);
-  // ---- audio encoder (audio_encoder.py:173-205) on tcgen05
-  const PBuf &xa = pb["xa"], &sao = pb["sa_out"], &a1 = pb["a1"];
-  if (inputs_ready) launch_audio_rows(b.f("aud"), LSD_F32, b.org(xa), xa.set_stride, xa.g, s.F, s.Ta, st);
-  else launch_audio_rows(audio, adt, b.org(xa), xa.set_stride, xa.g, s.F, s.Ta, st);
-  RUN("audio_encoder.stem", a_.in = &xa; a_.og = xa.g; a_.act = ACT_RELU; a_.yp = &sao; a_.yp_lo = &pb["sa_out_lo"]);
-  launch_planar_maxpool(b.org(sao), sao.plane_stride, sao.g, b.org(a1), a1.plane_stride, a1.g, 64, st, b.org(pb["sa_out_lo"]), b.org(pb["a1_lo"]));
-  if ((rc = res_stage_umma(b, "audio_encoder.layer1", a1, pb["a1a"], pb["ya1"], false, UC_Y_PARITY, &pb["a1_lo"], &pb["a1a_lo"], &pb["ya1_lo"]))) return rc;
-  if ((rc = res_stage_umma(b, "audio_encoder.layer2", pb["ya1"], pb["a2a"], pb["ya2"], true, UC_Y_PARITY_H, &pb["ya1_lo"], &pb["a2a_lo"], &pb["ya2_lo"]))) return rc;
-  if ((rc = res_stage_umma(b, "audio_encoder.layer3", pb["ya2"], pb["a3a"], pb["ya3"], true, UC_Y_PARITY_H, &pb["ya2_lo"], &pb["a3a_lo"], &pb["ya3_lo"]))) return rc;
-  if ((rc = res_stage_umma(b, "audio_encoder.layer4", pb["ya3"], pb["a4a"], pb["ya4"], true, UC_Y_PLAIN, &pb["ya3_lo"], &pb["a4a_lo"], &pb["ya4_lo"]))) return rc;
-  const PBuf& ya4 = pb["ya4"];
-  launch_planar_mean2(b.org(ya4), ya4.plane_stride, ya4.g, 256, b.f("a_feat"), 256, 2, pout(b, pb["afeat_p"], &pb["afeat_p_lo"]), st,
-                      b.org(pb["ya4_lo"]));  // mean over F'
+  if ((rc = audio_encoder_bf16(b, s, inputs_ready, audio, adt))) return rc;
   // ---- projection (fusion_module.py:108-124)
   const UcGeom gt = P.gt;
   RUN("projection.visual_proj", a_.in = &pb["vfeat_p"]; a_.in_lo = &pb["vfeat_p_lo"]; a_.og = gt; a_.yp = &pb["vemb_p"]; a_.yp_lo = &pb["vemb_p_lo"]; a_.y32 = b.f("v_emb"); a_.y32_ld = 256);
   RUN("projection.audio_proj", a_.in = &pb["afeat_p"]; a_.in_lo = &pb["afeat_p_lo"]; a_.og = P.gta; a_.y32 = b.f("a_emb"); a_.y32_ld = 256);
-  // ---- cross-modal attention + gated fusion (fusion_module.py:54-87)
-  launch_lerp_tokens_p(b.f("a_emb"), b.f("a_int"), B, TA, T, 256, pout(b, pb["aint_p"], &pb["aint_p_lo"]), st);
-  float *pv = b.f("proj_v"), *pa = b.f("proj_a"), *gi = b.f("gate_in");
-  RUN("cross.in_v", a_.in = &pb["vemb_p"]; a_.in_lo = &pb["vemb_p_lo"]; a_.og = gt; a_.y32 = pv; a_.y32_ld = 768);
-  RUN("cross.in_a", a_.in = &pb["aint_p"]; a_.in_lo = &pb["aint_p_lo"]; a_.og = gt; a_.y32 = pa; a_.y32_ld = 768);
-  launch_mha_core_p(pv, 768, pa + 256, 768, pa + 512, 768, B, T, T, 8, pout(b, pb["att1_p"], &pb["att1_p_lo"]), st);  // v2a: Q=v, K/V=a
-  launch_mha_core_p(pa, 768, pv + 256, 768, pv + 512, 768, B, T, T, 8, pout(b, pb["att2_p"], &pb["att2_p_lo"]), st);  // a2v: Q=a, K/V=v
-  RUN("cross.v2a.out", a_.in = &pb["att1_p"]; a_.in_lo = &pb["att1_p_lo"]; a_.og = gt; a_.res32 = b.f("v_emb"); a_.res32_ld = 256; a_.y32 = gi; a_.y32_ld = 512;
-      a_.yp = &pb["gatein_p"]; a_.yp_lo = &pb["gatein_p_lo"]);
-  RUN("cross.a2v.out", a_.in = &pb["att2_p"]; a_.in_lo = &pb["att2_p_lo"]; a_.og = gt; a_.res32 = b.f("a_int"); a_.res32_ld = 256; a_.y32 = gi + 256; a_.y32_ld = 512;
-      a_.yp = &pb["gatein_p"]; a_.yp_lo = &pb["gatein_p_lo"]; a_.y_plane_off = 32);
-  RUN("cross.gate0", a_.in = &pb["gatein_p"]; a_.in_lo = &pb["gatein_p_lo"]; a_.og = gt; a_.act = ACT_GELU; a_.y32 = b.f("gate_h"); a_.y32_ld = 256);
-  launch_gate_blend_p(b.f("gate_h"), b.W("cross.gate2.w"), b.W("cross.gate2.b"), gi, 512, gi + 256, 512, B * T, 256, pout(b, pb["blend_p"], &pb["blend_p_lo"]), st);
-  RUN("cross.fuse", a_.in = &pb["blend_p"]; a_.in_lo = &pb["blend_p_lo"]; a_.og = gt; a_.act = ACT_RELU; a_.y32 = b.f("fused"); a_.y32_ld = 256; a_.yp = &pb["fused_p"]; a_.yp_lo = &pb["fused_p_lo"]);
-  // ---- temporal transformer (temporal.py:79-111)
-  RUN("temporal.branch_k3", a_.in = &pb["fused_p"]; a_.in_lo = &pb["fused_p_lo"]; a_.og = gt; a_.act = ACT_GELU; a_.yp = &pb["mscat_p"]; a_.yp_lo = &pb["mscat_p_lo"]; a_.y_plane_off = 0);
-  RUN("temporal.branch_k5", a_.in = &pb["fused_p"]; a_.in_lo = &pb["fused_p_lo"]; a_.og = gt; a_.act = ACT_GELU; a_.yp = &pb["mscat_p"]; a_.yp_lo = &pb["mscat_p_lo"]; a_.y_plane_off = 32);
-  RUN("temporal.branch_k7", a_.in = &pb["fused_p"]; a_.in_lo = &pb["fused_p_lo"]; a_.og = gt; a_.act = ACT_GELU; a_.yp = &pb["mscat_p"]; a_.yp_lo = &pb["mscat_p_lo"]; a_.y_plane_off = 64);
+  if ((rc = token_path_bf16(b, s))) return rc;
   float* tok = b.f("tok");
-  launch_set_cls(b.W("temporal.cls"), tok, B, NT, 256, st);
-  // pre_scale_proj + residual, written straight into token rows 1..T of each window
-  RUN("temporal.pre_scale_proj", a_.in = &pb["mscat_p"]; a_.in_lo = &pb["mscat_p_lo"]; a_.og = gt; a_.res32 = b.f("fused"); a_.res32_ld = 256; a_.y32 = tok; a_.y32_ld = 256;
-      a_.y32_outer_stride = NT; a_.y32_row_off = 1);
-  const UcGeom g33 = P.g33;
-  for (int l = 0; l < 4; ++l) {
-    const std::string k = "t" + std::to_string(l);
-    launch_layernorm_p(tok, 256, b.W((k + ".ln1.w").c_str()), b.W((k + ".ln1.b").c_str()), B * NT, 256, pout(b, pb["tokln_p"], &pb["tokln_p_lo"]), st);
-    RUN(k + ".in", a_.in = &pb["tokln_p"]; a_.in_lo = &pb["tokln_p_lo"]; a_.og = g33; a_.y32 = b.f("tok_qkv"); a_.y32_ld = 768);
-    const float* qkv = b.f("tok_qkv");
-    launch_mha_core_p(qkv, 768, qkv + 256, 768, qkv + 512, 768, B, NT, NT, 8, pout(b, pb["tokatt_p"], &pb["tokatt_p_lo"]), st);
-    RUN(k + ".out", a_.in = &pb["tokatt_p"]; a_.in_lo = &pb["tokatt_p_lo"]; a_.og = g33; a_.res32 = tok; a_.res32_ld = 256; a_.y32 = tok; a_.y32_ld = 256);
-    launch_layernorm_p(tok, 256, b.W((k + ".ln2.w").c_str()), b.W((k + ".ln2.b").c_str()), B * NT, 256, pout(b, pb["tokln_p"], &pb["tokln_p_lo"]), st);
-    RUN(k + ".ff1", a_.in = &pb["tokln_p"]; a_.in_lo = &pb["tokln_p_lo"]; a_.og = g33; a_.act = ACT_GELU; a_.yp = &pb["tokff_p"]; a_.yp_lo = &pb["tokff_p_lo"]);
-    RUN(k + ".ff2", a_.in = &pb["tokff_p"]; a_.in_lo = &pb["tokff_p_lo"]; a_.og = g33; a_.res32 = tok; a_.res32_ld = 256; a_.y32 = tok; a_.y32_ld = 256);
-  }
   // cls = tok[:,0]: no final norm (temporal.py:110-111)
   launch_copy_rows(tok, (int64_t)NT * 256, comb, 448, B, 256, st);
   cudaStreamWaitEvent(st, h->ev_join, 0);   // artifact features (comb[:, 256:448]) are complete
@@ -710,6 +757,68 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
     if (aux->fused_tokens) cudaMemcpyAsync(aux->fused_tokens, b.f("fused"), tb, cudaMemcpyDeviceToDevice, st);
     if (aux->cls_output) launch_copy_rows(tok, (int64_t)NT * 256, aux->cls_output, 256, B, 256, st);
   }
+  return 0;
+}
+
+// ---- sub-paths behind the C-ABI (lsd_audio_encoder / lsd_token_path): the same functions the full forward runs, on a plan
+// whose unused video extents are minimal (16x16, one frame), so the audits of BASELINE.json configs 3 and 4 can sweep the batch.
+static int subpath_begin(lsd_handle* h, const Shapes& s, BPlan& P, char* ws, size_t ws_bytes, cudaStream_t st) {
+  build_plan(s, P);
+  if (P.f32.cursor > ws_bytes) return lsd_fail(h, LSD_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", P.f32.cursor, ws_bytes);
+  h->stages = P.f32.stages;
+  const int sig[6] = {s.B, s.T, s.H, s.W, s.F, s.Ta};
+  if (h->ws_sig_ptr != ws || h->ws_sig_bytes != ws_bytes || memcmp(h->ws_sig_shape, sig, sizeof(sig)) != 0) {
+    cudaError_t e = cudaMemsetAsync(ws + P.planar_begin, 0, P.planar_end - P.planar_begin, st);
+    if (e != cudaSuccess) return lsd_fail(h, LSD_ERR_CUDA, "workspace init: %s", cudaGetErrorString(e));
+    h->ws_sig_ptr = ws; h->ws_sig_bytes = ws_bytes; memcpy(h->ws_sig_shape, sig, sizeof(sig));
+  }
+  return 0;
+}
+
+size_t audio_encoder_bf16_bytes(lsd_handle* h, int B, int F, int Ta) {
+  Shapes s;
+  if (make_shapes(h, B, 1, 16, 16, F, Ta, s) != 0) return 0;
+  BPlan P;
+  build_plan(s, P);
+  return P.f32.cursor + 256;
+}
+
+int audio_encoder_bf16_run(lsd_handle* h, int B, int F, int Ta, const void* audio, int adt, float* feats_out, char* ws, size_t ws_bytes,
+                           cudaStream_t st) {
+  Shapes s;
+  int rc = make_shapes(h, B, 1, 16, 16, F, Ta, s);
+  if (rc) return rc;
+  BPlan P;
+  if ((rc = subpath_begin(h, s, P, ws, ws_bytes, st))) return rc;
+  BCtx b{h, ws, &P, st};
+  if ((rc = audio_encoder_bf16(b, s, false, audio, adt))) return rc;
+  cudaMemcpyAsync(feats_out, b.f("a_feat"), (size_t)B * s.A4 * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  return 0;
+}
+
+size_t token_path_bf16_bytes(lsd_handle* h, int B, int T, int TA) {
+  Shapes s;
+  if (make_shapes(h, B, T, 16, 16, 16, 8 * TA, s) != 0) return 0;
+  BPlan P;
+  build_plan(s, P);
+  return P.f32.cursor + 256;
+}
+
+int token_path_bf16_run(lsd_handle* h, int B, int T, int TA, const float* v_emb, const float* a_emb, float* fused_out, float* cls_out,
+                        char* ws, size_t ws_bytes, cudaStream_t st) {
+  Shapes s;
+  int rc = make_shapes(h, B, T, 16, 16, 16, 8 * TA, s);
+  if (rc) return rc;
+  if (s.A4 != TA) return lsd_fail(h, LSD_ERR_SHAPE, "lsd_token_path: unsupported audio token count %d", TA);
+  BPlan P;
+  if ((rc = subpath_begin(h, s, P, ws, ws_bytes, st))) return rc;
+  BCtx b{h, ws, &P, st};
+  // projected embeddings arrive as fp32 rows; the planar (hi, lo) copy of v_emb is what projection.visual_proj's epilogue writes
+  cudaMemcpyAsync(b.f("a_emb"), a_emb, (size_t)B * TA * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  launch_lerp_tokens_p(v_emb, b.f("v_emb"), B, T, T, 256, pout(b, P.pb.at("vemb_p"), &P.pb.at("vemb_p_lo")), st);
+  if ((rc = token_path_bf16(b, s))) return rc;
+  if (fused_out) cudaMemcpyAsync(fused_out, b.f("fused"), (size_t)B * T * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  if (cls_out) launch_copy_rows(b.f("tok"), (int64_t)(T + 1) * 256, cls_out, 256, B, 256, st);
   return 0;
 }
 
@@ -732,7 +841,9 @@ int score_batch_bf16(lsd_handle* h, const uint8_t* track, int n_frames, const in
   build_plan(s, P);
   if (P.f32.cursor > ws_bytes) return lsd_fail(h, LSD_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", P.f32.cursor, ws_bytes);
   BCtx b{h, ws, &P, st};
-  launch_gather_windows_u8(track, n_frames, d_vstarts, b.f("vid"), nb, T, H * W * 3, st);
   launch_gather_audio(mel_full, F, Ta_full, d_astarts, b.f("aud"), nb, Ta, st);
+  if (video_rows_bulk_ok(track, LSD_U8, LSD_NDHWC, W))
+    return forward_bf16_impl(h, s, logits, nullptr, ws, ws_bytes, st, true, track, LSD_U8, LSD_NDHWC, nullptr, 0, d_vstarts, n_frames);
+  launch_gather_windows_u8(track, n_frames, d_vstarts, b.f("vid"), nb, T, H * W * 3, st);
   return forward_bf16_impl(h, s, logits, nullptr, ws, ws_bytes, st, true, nullptr, 0, 0, nullptr, 0);
 }

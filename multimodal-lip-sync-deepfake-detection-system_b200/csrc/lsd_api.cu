@@ -353,7 +353,7 @@ extern "C" size_t lsd_score_workspace_bytes(lsd_handle* h, int batch, int T, int
 }
 
 extern "C" int lsd_score_windows(lsd_handle* h, const uint8_t* track, int n_frames, int H, int W, const int32_t* starts_host,
-                                 int n_windows, int T, const float* mel_full, int F, int Ta_full, int total_v_frames, int Ta,
+                                 const int32_t* audio_starts_host, int n_windows, int T, const float* mel_full, int F, int Ta_full, int total_v_frames, int Ta,
                                  int precision, int batch, float* logits_out, void* workspace, size_t workspace_bytes, void* stream) {
   if (!h) return LSD_ERR_ARG;
   if (!h->loaded) return lsd_fail(h, LSD_ERR_WEIGHTS, "lsd_score_windows: no weights loaded");
@@ -381,8 +381,9 @@ extern "C" int lsd_score_windows(lsd_handle* h, const uint8_t* track, int n_fram
   const double a_ratio = (double)Ta_full / (double)(total_v_frames > 1 ? total_v_frames : 1);
   for (int i = 0; i < n_windows; ++i) {
     // predictor.py:540-547: a_start = int(round(v_start * a_ratio)) (round-half-even), clamped so the chunk ends inside the clip
-    long a_start = (long)nearbyint((double)starts_host[i] * a_ratio);
+    long a_start = audio_starts_host ? (long)audio_starts_host[i] : (long)nearbyint((double)starts_host[i] * a_ratio);
     if (a_start + Ta > Ta_full) { a_start = Ta_full - Ta; if (a_start < 0) a_start = 0; }
+    if (a_start < 0) a_start = 0;
     h->idx_host[i] = starts_host[i];
     h->idx_host[n_windows + i] = (int32_t)a_start;
   }
@@ -408,6 +409,47 @@ extern "C" int lsd_score_windows(lsd_handle* h, const uint8_t* track, int n_fram
       if (rc) return rc;
     }
   }
+  CUDA_OK(h, cudaGetLastError());
+  return LSD_OK;
+}
+
+// ================================================================================================
+// Sub-paths (tensor-core route): AudioEncoder.forward and CrossModalAttention + TemporalTransformer
+// ================================================================================================
+extern "C" size_t lsd_audio_encoder_workspace_bytes(lsd_handle* h, int B, int F, int Ta) {
+  return h ? audio_encoder_bf16_bytes(h, B, F, Ta) : 0;
+}
+extern "C" int lsd_audio_encoder(lsd_handle* h, const void* audio, int audio_dtype, int B, int F, int Ta, float* feats_out,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return LSD_ERR_ARG;
+  if (!h->loaded) return lsd_fail(h, LSD_ERR_WEIGHTS, "lsd_audio_encoder: no weights loaded");
+  if (B < 0 || F < 1 || Ta < 1) return lsd_fail(h, LSD_ERR_SHAPE, "expected audio (B,1,F,T_a) with positive extents, got B=%d F=%d Ta=%d", B, F, Ta);
+  if (B == 0) return LSD_OK;
+  if (!audio || !feats_out || !workspace) return lsd_fail(h, LSD_ERR_ARG, "lsd_audio_encoder: null pointer argument");
+  int rc = check_dtype(h, audio_dtype, "audio");
+  if (rc) return rc;
+  if (audio_dtype == LSD_U8) return lsd_fail(h, LSD_ERR_ARG, "audio: uint8 log-mel is not supported");
+  CUDA_OK(h, cudaSetDevice(h->device));
+  rc = audio_encoder_bf16_run(h, B, F, Ta, audio, audio_dtype, feats_out, reinterpret_cast<char*>(workspace), workspace_bytes,
+                              reinterpret_cast<cudaStream_t>(stream));
+  if (rc) return rc;
+  CUDA_OK(h, cudaGetLastError());
+  return LSD_OK;
+}
+extern "C" size_t lsd_token_path_workspace_bytes(lsd_handle* h, int B, int T, int Ta_tokens) {
+  return h ? token_path_bf16_bytes(h, B, T, Ta_tokens) : 0;
+}
+extern "C" int lsd_token_path(lsd_handle* h, const float* v_emb, const float* a_emb, int B, int T, int Ta_tokens, float* fused_out,
+                              float* cls_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return LSD_ERR_ARG;
+  if (!h->loaded) return lsd_fail(h, LSD_ERR_WEIGHTS, "lsd_token_path: no weights loaded");
+  if (B < 0 || T < 1 || Ta_tokens < 1) return lsd_fail(h, LSD_ERR_SHAPE, "expected v_emb (B,T,256) and a_emb (B,T_a,256), got B=%d T=%d T_a=%d", B, T, Ta_tokens);
+  if (B == 0) return LSD_OK;
+  if (!v_emb || !a_emb || !workspace || (!fused_out && !cls_out)) return lsd_fail(h, LSD_ERR_ARG, "lsd_token_path: null pointer argument");
+  CUDA_OK(h, cudaSetDevice(h->device));
+  int rc = token_path_bf16_run(h, B, T, Ta_tokens, v_emb, a_emb, fused_out, cls_out, reinterpret_cast<char*>(workspace), workspace_bytes,
+                               reinterpret_cast<cudaStream_t>(stream));
+  if (rc) return rc;
   CUDA_OK(h, cudaGetLastError());
   return LSD_OK;
 }

@@ -82,6 +82,12 @@ void make_plan_bf16(lsd_handle* h, int B, int T, int H, int W, int F, int Ta, st
 int forward_bf16(lsd_handle* h, int B, int T, int H, int W, int F, int Ta, const void* video, int vdt, int vlayout,
                  const void* audio, int adt, float* logits, const lsd_aux* aux, char* ws, size_t ws_bytes,
                  cudaStream_t st, bool inputs_ready);
+size_t audio_encoder_bf16_bytes(lsd_handle* h, int B, int F, int Ta);
+int audio_encoder_bf16_run(lsd_handle* h, int B, int F, int Ta, const void* audio, int adt, float* feats_out, char* ws, size_t ws_bytes,
+                           cudaStream_t st);
+size_t token_path_bf16_bytes(lsd_handle* h, int B, int T, int TA);
+int token_path_bf16_run(lsd_handle* h, int B, int T, int TA, const float* v_emb, const float* a_emb, float* fused_out, float* cls_out,
+                        char* ws, size_t ws_bytes, cudaStream_t st);
 int score_batch_bf16(lsd_handle* h, const uint8_t* track, int n_frames, const int32_t* d_vstarts, const int32_t* d_astarts,
                      const float* mel_full, int Ta_full, int nb, int T, int H, int W, int F, int Ta, float* logits,
                      char* ws, size_t ws_bytes, cudaStream_t st);

@@ -92,10 +92,60 @@ __global__ void mha_core_p_kernel(const float* q, int q_ld, const float* k, int 
     pstore(o, pmap(o, (int64_t)n * Tq + i), h * 32 + lane, acc / den);
   }
 }
+// Register-resident variant for Tk <= 64 (every shape of this model: 16/17/32/33 keys): K and V of one (window, head) are
+// staged in shared memory with coalesced loads; lane j keeps key rows j and j+32 in registers, a query row is broadcast from
+// shared memory (LDS.128), so Q.K^T costs one FMA per (key, dim) with no shuffles; softmax statistics by warp reduction;
+// P.V broadcasts p_j by shuffle against V rows in shared memory (lane = output dim).
+__global__ void __launch_bounds__(128) mha_core_p64_kernel(const float* __restrict__ q, int q_ld, const float* __restrict__ k, int k_ld,
+                                                           const float* __restrict__ v, int v_ld, int Tq, int Tk, int heads, PlanarOut o) {
+  extern __shared__ __align__(16) float sm[];
+  float* Qs = sm;                                // [Tq][32], pre-scaled (first: rows stay 16-byte aligned for LDS.128)
+  float* Ks = Qs + (size_t)Tq * 32;              // [Tk][33]
+  float* Vs = Ks + (size_t)Tk * 33;              // [Tk][33]
+  const int n = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const float scale = 0.17677669529663688f;  // 1/sqrt(32)
+  for (int j = warp; j < Tk; j += nwarps) {
+    Ks[j * 33 + lane] = k[((int64_t)n * Tk + j) * k_ld + h * 32 + lane];
+    Vs[j * 33 + lane] = v[((int64_t)n * Tk + j) * v_ld + h * 32 + lane];
+  }
+  for (int i = warp; i < Tq; i += nwarps) Qs[i * 32 + lane] = q[((int64_t)n * Tq + i) * q_ld + h * 32 + lane] * scale;
+  __syncthreads();
+  const bool two = Tk > 32;
+  const bool v0 = lane < Tk, v1 = lane + 32 < Tk;
+  float k0[32], k1[32];
+#pragma unroll
+  for (int d = 0; d < 32; ++d) {
+    k0[d] = v0 ? Ks[lane * 33 + d] : 0.f;
+    k1[d] = v1 ? Ks[(lane + 32) * 33 + d] : 0.f;
+  }
+  for (int i = warp; i < Tq; i += nwarps) {
+    float d0 = 0.f, d1 = 0.f;
+    const float4* qr = reinterpret_cast<const float4*>(Qs + i * 32);
+#pragma unroll
+    for (int d4 = 0; d4 < 8; ++d4) {
+      const float4 qv = qr[d4];
+      d0 = fmaf(qv.x, k0[4 * d4], d0); d0 = fmaf(qv.y, k0[4 * d4 + 1], d0); d0 = fmaf(qv.z, k0[4 * d4 + 2], d0); d0 = fmaf(qv.w, k0[4 * d4 + 3], d0);
+      if (two) { d1 = fmaf(qv.x, k1[4 * d4], d1); d1 = fmaf(qv.y, k1[4 * d4 + 1], d1); d1 = fmaf(qv.z, k1[4 * d4 + 2], d1); d1 = fmaf(qv.w, k1[4 * d4 + 3], d1); }
+    }
+    const float mx = tk_warp_max(fmaxf(v0 ? d0 : -INFINITY, v1 ? d1 : -INFINITY));
+    const float p0 = v0 ? expf(d0 - mx) : 0.f, p1 = v1 ? expf(d1 - mx) : 0.f;
+    // fixed summation order (the same as the generic kernel: tile 0 then tile 1)
+    const float den = tk_warp_sum(p0) + (two ? tk_warp_sum(p1) : 0.f);
+    float acc = 0.f;
+    const int c0 = min(32, Tk);
+    for (int j = 0; j < c0; ++j) acc = fmaf(__shfl_sync(0xffffffffu, p0, j), Vs[j * 33 + lane], acc);
+    for (int j = 32; j < Tk; ++j) acc = fmaf(__shfl_sync(0xffffffffu, p1, j - 32), Vs[j * 33 + lane], acc);
+    pstore(o, pmap(o, (int64_t)n * Tq + i), h * 32 + lane, acc / den);
+  }
+}
 void launch_mha_core_p(const float* q, int q_ld, const float* k, int k_ld, const float* v, int v_ld, int N, int Tq, int Tk, int heads,
                        PlanarOut o, cudaStream_t s) {
   if (N == 0) return;
-  mha_core_p_kernel<<<N * heads, 128, (size_t)Tk * 33 * 2 * sizeof(float), s>>>(q, q_ld, k, k_ld, v, v_ld, Tq, Tk, heads, o);
+  if (Tk <= 64)
+    mha_core_p64_kernel<<<N * heads, 128, ((size_t)Tk * 33 * 2 + (size_t)Tq * 32) * sizeof(float), s>>>(q, q_ld, k, k_ld, v, v_ld, Tq, Tk, heads, o);
+  else
+    mha_core_p_kernel<<<N * heads, 128, (size_t)Tk * 33 * 2 * sizeof(float), s>>>(q, q_ld, k, k_ld, v, v_ld, Tq, Tk, heads, o);
   count_launch();
 }
 
@@ -199,6 +249,7 @@ __global__ void __launch_bounds__(256) head_kernel(const float* comb, HeadW w, f
   __syncthreads();
   {
     float acc = w.b0[tid];
+#pragma unroll 16   // 16 independent weight loads in flight per thread (the loop is L2-latency-bound otherwise); same summation order
     for (int k = 0; k < 448; ++k) acc = fmaf(x[k], w.w0[k * 256 + tid], acc);
     h1[tid] = fmaxf(acc, 0.f);
   }
@@ -206,6 +257,7 @@ __global__ void __launch_bounds__(256) head_kernel(const float* comb, HeadW w, f
   __syncthreads();
   if (tid < 128) {
     float acc = w.b2[tid];
+#pragma unroll 16
     for (int k = 0; k < 256; ++k) acc = fmaf(h1[k], w.w2[k * 128 + tid], acc);
     f[256 + tid] = fmaxf(acc, 0.f);
   }
@@ -213,6 +265,7 @@ __global__ void __launch_bounds__(256) head_kernel(const float* comb, HeadW w, f
   float hv = 0.f;
   if (tid < 128) {
     float acc = w.bc[tid];
+#pragma unroll 16
     for (int k = 0; k < 384; ++k) acc = fmaf(f[k], w.wc[k * 128 + tid], acc);
     hv = tk_gelu(acc);
     h2[tid] = hv;

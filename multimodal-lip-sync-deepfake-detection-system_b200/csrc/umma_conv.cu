@@ -14,6 +14,10 @@
 #include "umma_conv.cuh"
 #include "token_kernels.cuh"
 
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
 #include "lsd_kernels.h"
 #include "umma.cuh"
 
@@ -67,16 +71,79 @@ __device__ __forceinline__ void unpack8(const uint4& r, float* v) {
 // epilogue of tile i overlaps the main loop of tile i+1, and the smem ring keeps streaming across tile boundaries.
 constexpr int UC_THREADS = 448;
 constexpr int UC_PROD_WARPS = 4, UC_MMA_WARP0 = 4, UC_EPI_WARP0 = 6, UC_EPI_WARPS = 8;
+// issuing one cp.async.bulk occupies the issuing thread for ~330 cycles; the cost overlaps across warps and (partly) across the
+// lanes of a warp (probe/bulk_issue.cu: 16 issuers = 4 warps x 4 lanes sustain one 2 KB copy per ~26 cycles per SM), so the
+// copies of a stage are dealt to 16 issuing threads: stages made of many small copies (token-path GEMMs) are issue-bound otherwise
+constexpr int UC_PROD_LANES = 8;   // 32 issuers >= copies per stage (2 * kpack A planes + up to kpack weight pieces; kpack <= 8 checked on the host)
 
 // GENERIC = false: lean epilogue of the convolution layers (bias, ReLU/none, optional bf16 residual, planar / parity-split bf16
 // store).  GENERIC = true: everything (fp32 rows in/out, split-bf16 hi/lo outputs and residuals, GELU) for the audio encoder and
 // the token-path GEMMs.  Two instantiations keep each one small enough for the instruction cache.
+// Per-tile "stage program" of the producers.  The sequence of ring stages (group, K-chunk block, band) is the same for every
+// tile; only the tile's first position P0 shifts the A sources.  Computing a stage's copy operands from the parameter block
+// costs ~150 dependent instructions (indexed constant loads + 64-bit multiplies), i.e. ~1200 cycles for the single issuing
+// warp — more than the MMA time of a stage for every layer with few taps per stage (token GEMMs, audio encoder, N = 256
+// tiles), which made those launches producer-latency-bound.  The program is therefore expanded ONCE per CTA in the prologue
+// (all 448 threads, one stage each) into shared memory and the producer loop only reads 64-byte descriptors.
+struct __align__(16) UcStageDesc {
+  uint64_t a_src;            // global byte address of the stage's first A piece for P0 = 0
+  uint64_t w_src;            // global byte address of the stage's first weight piece (slice included)
+  uint64_t chunk_stride_b;   // bytes between consecutive K-chunk pairs of planes
+  uint64_t plane_stride_b;   // bytes between the two 8-channel planes of a K chunk
+  uint32_t bytesA;           // bytes of one A piece
+  uint32_t w_copy_bytes;     // bytes of one weight copy
+  uint32_t w_dst_step;       // shared-memory distance between weight pieces
+  uint32_t tx_bytes;         // bytes the stage's full barrier expects
+  uint32_t n_a, n_w;         // number of A / weight copies
+  uint32_t pad0;             // global distance between weight pieces of consecutive K chunks
+  uint32_t pad1;             // band index | (K chunks in this stage << 8)
+};
+static_assert(sizeof(UcStageDesc) == 64, "UcStageDesc must be 64 bytes");
+
+__device__ __forceinline__ void uc_build_stage(const UmmaConvP& p, const UcGroup* groups, const UcBand* bands, int s, int S, int slice,
+                                               UcStageDesc* out) {
+  int cnt = 0, gi = 0, c0 = 0, b = 0;
+  for (; gi < p.ngroups; ++gi) {
+    const UcGroup& g = groups[gi];
+    const int nb = g.band_end - g.band_begin;
+    const int n = ((g.k16 + p.kpack - 1) / p.kpack) * nb;
+    if (s < cnt + n) { const int r = s - cnt; c0 = (r / nb) * p.kpack; b = g.band_begin + r % nb; break; }
+    cnt += n;
+  }
+  const UcGroup& g = groups[gi];
+  const UcBand& bd = bands[b];
+  const int nc = min(p.kpack, g.k16 - c0);
+  UcStageDesc d;
+  const uint32_t bytesW = (uint32_t)bd.ntaps * (uint32_t)p.Cout * 32u;
+  d.bytesA = bd.toeplitz ? (uint32_t)(S + bd.len_extra + 1 + 2 * (nc - 1)) * 16u : (uint32_t)(S + bd.len_extra) * 16u;
+  d.n_a = bd.toeplitz ? 1u : 2u * (uint32_t)nc;   // Toeplitz: the K chunks are 32-byte shifts of one row region
+  // single-band groups (Linear layers): the weights of consecutive K chunks are contiguous -> one copy
+  const bool w_merged = (g.band_end - g.band_begin) == 1;
+  d.n_w = w_merged ? 1u : (uint32_t)nc;
+  d.w_copy_bytes = w_merged ? (uint32_t)nc * bytesW : bytesW;
+  d.w_dst_step = bytesW;
+  // (p.skip: timing experiments only — bit 0 drops the A copies, bit 1 the W copies; results are then garbage)
+  if (p.skip & 1) d.n_a = 0;
+  if (p.skip & 2) d.n_w = 0;
+  d.tx_bytes = d.n_a * d.bytesA + (d.n_w ? (uint32_t)nc * bytesW : 0u);
+  d.a_src = reinterpret_cast<uint64_t>(bd.base + (int64_t)c0 * bd.chunk_stride + (int64_t)bd.start * 8);
+  d.chunk_stride_b = (uint64_t)bd.chunk_stride * 2u;
+  d.plane_stride_b = (uint64_t)bd.plane_stride * 2u;
+  // weight piece j of the stage is the packed block [chunk c0 + j][taps of this band]: pieces are taps_total * Cout * 32 B apart
+  d.w_src = reinterpret_cast<uint64_t>(p.w + g.w_off + (int64_t)slice * g.slice_stride + ((int64_t)c0 * g.taps_total + bd.tap_begin) * (int64_t)p.Cout * 16);
+  d.pad0 = (uint32_t)g.taps_total * (uint32_t)p.Cout * 32u;   // global distance between weight pieces of consecutive K chunks
+  d.pad1 = (uint32_t)b | ((uint32_t)nc << 8);                // band index and K chunks of the stage (MMA issuers)
+  *out = d;
+}
+
 template <bool GENERIC>
 __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_constant__ UmmaConvP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_s[256];
+  __shared__ __align__(16) UcBand bands_s[UC_MAX_BANDS];
+  __shared__ __align__(16) UcGroup groups_s[UC_MAX_GROUPS];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
   if (dbg && tid == 0) p.dbg[0] = clock64();
@@ -94,6 +161,19 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
   }
   if (warp == UC_EPI_WARP0) { tmem_alloc(&tmem_base_s, p.tmem_cols); tmem_relinquish(); }
   for (int i = tid; i < p.Cout; i += UC_THREADS) bias_s[i] = p.bias ? p.bias[ch0 + i] : 0.0f;
+  // band / group tables: parameter (constant) bank -> shared memory, one word per thread (indexed constant loads are slow and
+  // the loops below would chain them)
+  {
+    const uint32_t* bsrc = reinterpret_cast<const uint32_t*>(p.bands);
+    uint32_t* bdst = reinterpret_cast<uint32_t*>(bands_s);
+    for (int i = tid; i < p.nbands * (int)(sizeof(UcBand) / 4); i += UC_THREADS) bdst[i] = bsrc[i];
+    const uint32_t* gsrc = reinterpret_cast<const uint32_t*>(p.groups);
+    uint32_t* gdst = reinterpret_cast<uint32_t*>(groups_s);
+    for (int i = tid; i < p.ngroups * (int)(sizeof(UcGroup) / 4); i += UC_THREADS) gdst[i] = gsrc[i];
+  }
+  __syncthreads();
+  UcStageDesc* prog = reinterpret_cast<UcStageDesc*>(smem + (size_t)p.stages * stage_bytes);
+  for (int i = tid; i < p.nst_tile; i += UC_THREADS) uc_build_stage(p, groups_s, bands_s, i, S, slice, &prog[i]);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -104,43 +184,30 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
     // ------------------------------------------------ producers (every warp runs the loop; lane 0 of each issues its share)
     int stage = 0, dbg_it = 0;
     uint32_t ph = 0;
+    const int idx0 = lane * UC_PROD_WARPS + warp;          // this lane's copy slot within a stage
+    const uint32_t smem_base = smem_u32(smem);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int64_t P0 = (int64_t)tile * S;
-      for (int gi = 0; gi < p.ngroups; ++gi) {
-        const UcGroup& g = p.groups[gi];
-        for (int c0 = 0; c0 < g.k16; c0 += p.kpack) {
-          const int nc = min(p.kpack, g.k16 - c0);
-          for (int b = g.band_begin; b < g.band_end; ++b) {
-            const UcBand& bd = p.bands[b];
-            mbar_wait(&empty_bar[stage], ph ^ 1u);
-            if (dbg && warp == 0 && lane == 0 && dbg_it < 24 && tile == (int)blockIdx.x) p.dbg[32 + dbg_it++] = clock64();
-            if (lane == 0) {
-              const uint32_t bytesW = (uint32_t)bd.ntaps * (uint32_t)p.Cout * 32u;
-              uint8_t* sa = smem + (size_t)stage * stage_bytes;
-              uint8_t* sw = sa + p.a_stage_bytes;
-              const __nv_bfloat16* src = bd.base + (int64_t)c0 * bd.chunk_stride + (P0 + bd.start) * 8;
-              const uint32_t bytesA = bd.toeplitz ? (uint32_t)(S + bd.len_extra + 1 + 2 * (nc - 1)) * 16u : (uint32_t)(S + bd.len_extra) * 16u;
-              const int n_a = bd.toeplitz ? 1 : 2 * nc;   // Toeplitz: the K chunks are 32-byte shifts of one row region
-              // single-band groups (Linear layers): the weights of consecutive K chunks are contiguous -> one copy
-              const bool w_merged = (g.band_end - g.band_begin) == 1;
-              const int n_w = w_merged ? 1 : nc;
-              if (warp == 0) mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)n_a * bytesA + (uint32_t)nc * bytesW);
-              for (int idx = warp; idx < n_a + n_w; idx += UC_PROD_WARPS) {
-                if (idx < n_a) {
-                  const int j = idx >> 1, pl = idx & 1;     // K chunk j, plane pl (planar); idx == 0 only for Toeplitz
-                  bulk_g2s(sa + (size_t)idx * bytesA, src + (int64_t)j * bd.chunk_stride + (int64_t)pl * bd.plane_stride, bytesA, &full_bar[stage]);
-                } else {
-                  const int j = idx - n_a;
-                  const __nv_bfloat16* wsrc = p.w + g.w_off + (int64_t)slice * g.slice_stride +
-                                              ((int64_t)(c0 + j) * g.taps_total + bd.tap_begin) * (int64_t)p.Cout * 16;
-                  bulk_g2s(sw + (size_t)j * bytesW, wsrc, w_merged ? (uint32_t)nc * bytesW : bytesW, &full_bar[stage]);
-                }
-              }
-            }
-            __syncwarp();
-            if (++stage == p.stages) { stage = 0; ph ^= 1u; }
-          }
-        }
+      const uint64_t p0_bytes = (uint64_t)tile * (uint64_t)S * 16u;
+      for (int si = 0; si < p.nst_tile; ++si) {
+        // operands of this lane's copy, from the stage program (computed before waiting for the stage to drain)
+        const UcStageDesc& d = prog[si];
+        const uint32_t n_a = d.n_a, n_all = n_a + d.n_w;
+        const bool is_a = (uint32_t)idx0 < n_a;
+        const bool mine = lane < UC_PROD_LANES && (uint32_t)idx0 < n_all;
+        const uint32_t j = is_a ? ((uint32_t)idx0 >> 1) : ((uint32_t)idx0 - n_a);   // K chunk (planar A: plane idx & 1)
+        const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+        const uint64_t gsrc = is_a ? d.a_src + p0_bytes + (uint64_t)j * d.chunk_stride_b + (uint64_t)(idx0 & 1) * d.plane_stride_b
+                                   : d.w_src + (uint64_t)j * (uint64_t)d.pad0;
+        const uint32_t dst = is_a ? sa + (uint32_t)idx0 * d.bytesA : sa + p.a_stage_bytes + j * d.w_dst_step;
+        const uint32_t nbytes = is_a ? d.bytesA : d.w_copy_bytes;
+        const uint32_t tx_bytes = d.tx_bytes;
+        mbar_wait(&empty_bar[stage], ph ^ 1u);
+        if (dbg && warp == 0 && lane == 0 && dbg_it < 24 && tile == (int)blockIdx.x) p.dbg[32 + dbg_it++] = clock64();
+        if (warp == 0 && lane == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+        if (mine) bulk_s2(dst, reinterpret_cast<const void*>(gsrc), nbytes, &full_bar[stage]);
+        __syncwarp();
+        if (dbg && warp == 0 && lane == 0 && dbg_it <= 8 && tile == (int)blockIdx.x) p.dbg[56 + dbg_it - 1] = clock64();   // copies issued
+        if (++stage == p.stages) { stage = 0; ph ^= 1u; }
       }
     }
   } else if (warp == UC_MMA_WARP0 || warp == UC_MMA_WARP0 + 1) {
@@ -164,43 +231,43 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
       mbar_wait(&tempty_bar[buf], (use & 1u) ^ 1u);   // epilogue has drained this accumulator buffer
       tc_fence_after();
       uint32_t acc = 0;
-      for (int gi = 0; gi < p.ngroups; ++gi) {
-        const UcGroup& g = p.groups[gi];
-        for (int c0 = 0; c0 < g.k16; c0 += p.kpack) {
-          const int nc = min(p.kpack, g.k16 - c0);
-          for (int b = g.band_begin; b < g.band_end; ++b) {
-            const UcBand& bd = p.bands[b];
-            const int ntaps = bd.ntaps;
-            const uint32_t unitsA = (uint32_t)(S + bd.len_extra);
-            const uint64_t da_hi = desc_hi | ((uint64_t)(bd.toeplitz ? 1u : unitsA) << 16);
-            const uint32_t a_chunk = bd.toeplitz ? 2u : 2u * unitsA;
-            const uint32_t w_chunk = (uint32_t)ntaps * tap_w;
-            mbar_wait(&full_bar[stage], ph);
-            tc_fence_after();
-            if (dbg && warp == UC_MMA_WARP0 && lane == 0 && acc == 0 && lt == 0) p.dbg[2] = clock64();   // first stage landed
-            if (dbg && warp == UC_MMA_WARP0 && lane == 0 && lt == 0 && dbg_it < 24) p.dbg[8 + dbg_it++] = clock64();
-            const uint32_t sa = (smem_base + (uint32_t)stage * stage_bytes) >> 4;
-            const uint32_t sw = sa + (p.a_stage_bytes >> 4);
-            if (elect_one()) {
-              uint32_t accl = acc;   // 0 only for the very first MMA of each accumulator
-              for (int j = 0; j < nc; ++j) {
-                const uint32_t aj = sa + (uint32_t)j * a_chunk, wj = sw + (uint32_t)j * w_chunk;
+      for (int si = 0; si < p.nst_tile; ++si) {
+        const uint32_t bn = prog[si].pad1;
+        const int nc = (int)(bn >> 8);
+        const UcBand& bd = bands_s[bn & 0xffu];
+        const int ntaps = bd.ntaps;
+        const uint32_t unitsA = (uint32_t)(S + bd.len_extra);
+        const uint64_t da_hi = desc_hi | ((uint64_t)(bd.toeplitz ? 1u : unitsA) << 16);
+        const uint32_t a_chunk = bd.toeplitz ? 2u : 2u * unitsA;
+        const uint32_t w_chunk = (uint32_t)ntaps * tap_w;
+        const uint32_t rel0 = (uint32_t)bd.rel[0];
+        mbar_wait(&full_bar[stage], ph);
+        tc_fence_after();
+        if (dbg && warp == UC_MMA_WARP0 && lane == 0 && acc == 0 && lt == 0) p.dbg[2] = clock64();   // first stage landed
+        if (dbg && warp == UC_MMA_WARP0 && lane == 0 && lt == 0 && dbg_it < 24) p.dbg[8 + dbg_it++] = clock64();
+        const uint32_t sa = (smem_base + (uint32_t)stage * stage_bytes) >> 4;
+        const uint32_t sw = sa + (p.a_stage_bytes >> 4);
+        if (elect_one()) {
+          uint32_t accl = acc;   // 0 only for the very first MMA of each accumulator
+          for (int j = 0; j < nc; ++j) {
+            const uint32_t aj = sa + (uint32_t)j * a_chunk + (uint32_t)mt_lo * 128u, wj = sw + (uint32_t)j * w_chunk;
+            uint32_t rel = rel0;
 #pragma unroll 1
-                for (int tp = 0; tp < ntaps; ++tp) {   // (not unrolled: the kernel must stay inside the instruction cache)
-                  const uint64_t db = db_hi | (uint64_t)(wj + (uint32_t)tp * tap_w);
-                  const uint32_t at = aj + (uint32_t)bd.rel[tp] + (uint32_t)mt_lo * 128u;
-                  mma_bf16_ss(tb, da_hi | (uint64_t)at, db, idesc, accl);
-                  if (mt_n > 1) mma_bf16_ss(tb + (uint32_t)p.Cout, da_hi | (uint64_t)(at + 128u), db, idesc, accl);
-                  accl = 1u;
-                }
-              }
-              mma_commit(&empty_bar[stage]);  // frees the stage once the MMAs that read it have completed
+            for (int tp = 0; tp < ntaps; ++tp) {   // (not unrolled: the kernel must stay inside the instruction cache)
+              const uint32_t rel_next = (uint32_t)bd.rel[tp + 1 < ntaps ? tp + 1 : tp];   // shared-memory load overlaps the issue
+              const uint64_t db = db_hi | (uint64_t)(wj + (uint32_t)tp * tap_w);
+              const uint32_t at = aj + rel;
+              mma_bf16_ss(tb, da_hi | (uint64_t)at, db, idesc, accl);
+              if (mt_n > 1) mma_bf16_ss(tb + (uint32_t)p.Cout, da_hi | (uint64_t)(at + 128u), db, idesc, accl);
+              accl = 1u;
+              rel = rel_next;
             }
-            acc = 1u;
-            __syncwarp();
-            if (++stage == p.stages) { stage = 0; ph ^= 1u; }
           }
+          mma_commit(&empty_bar[stage]);  // frees the stage once the MMAs that read it have completed
         }
+        acc = 1u;
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; ph ^= 1u; }
       }
       if (elect_one()) mma_commit(&tfull_bar[buf]);   // accumulator of this tile complete -> epilogue
       __syncwarp();
@@ -345,16 +412,20 @@ done:
   if (dbg && tid == 0) { p.dbg[6] = clock64(); p.dbg[7] = num_tiles; }
 }
 
-size_t umma_conv_smem_bytes(const UmmaConvP& p) { return (size_t)p.stages * (p.a_stage_bytes + p.w_stage_bytes) + 1024; }
+size_t umma_conv_smem_bytes(const UmmaConvP& p) {
+  return (size_t)p.stages * (p.a_stage_bytes + p.w_stage_bytes) + (size_t)p.nst_tile * sizeof(UcStageDesc) + 1024;
+}
+int umma_conv_stage_desc_bytes() { return (int)sizeof(UcStageDesc); }
 
 void launch_umma_conv(const UmmaConvP& p, int n_slices, cudaStream_t s, int max_ctas) {
   static bool attr_set = false;
   if (!attr_set) {
-    // the opt-in limit (227 KB) covers static + dynamic shared memory; ~1.3 KB is static (barriers, bias)
-    cudaFuncSetAttribute(umma_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-    cudaFuncSetAttribute(umma_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    // the opt-in limit (227 KB) covers static + dynamic shared memory; ~3.7 KB is static (barriers, bias, band / group tables)
+    cudaFuncSetAttribute(umma_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024);
+    cudaFuncSetAttribute(umma_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024);
     attr_set = true;
   }
+  if (2 * p.kpack + p.kpack > UC_PROD_WARPS * UC_PROD_LANES) { fprintf(stderr, "umma_conv: kpack %d exceeds the issuer count\n", p.kpack); abort(); }
   const int S = p.MT * 128;
   const int tiles = (int)((p.g.P_total + S - 1) / S);
   static int num_sms = 0;
@@ -497,55 +568,84 @@ void launch_planar_delta(const __nv_bfloat16* x, int64_t x_plane_stride, UcGeom 
 
 // MaxPool (1,3,3)/(1,2,2)/pad(0,1,1) in planar layout.  Inputs are post-ReLU (>= 0) and the pads are zero, so reading
 // the zero pad is equivalent to the reference's -inf padding except at the far edge, which is bounds-checked.
-__global__ void planar_maxpool_kernel(const __nv_bfloat16* __restrict__ x, int64_t xs, UcGeom gi, __nv_bfloat16* __restrict__ y, int64_t ys,
-                                      UcGeom go, int64_t total, const __nv_bfloat16* __restrict__ xlo, __nv_bfloat16* __restrict__ ylo) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int64_t npos = (int64_t)go.N * go.T * go.H * go.W;
-  const int chunk = (int)(i / npos);
-  int64_t r = i - (int64_t)chunk * npos;
-  const int w = (int)(r % go.W); r /= go.W;
-  const int h = (int)(r % go.H); r /= go.H;
-  const int t = (int)(r % go.T);
-  const int n = (int)(r / go.T);
-  float m[8];
+__global__ void __launch_bounds__(256) planar_maxpool_kernel(const __nv_bfloat16* __restrict__ x, int64_t xs, UcGeom gi, __nv_bfloat16* __restrict__ y,
+                                                             int64_t ys, UcGeom go, const __nv_bfloat16* __restrict__ xlo,
+                                                             __nv_bfloat16* __restrict__ ylo) {
+  // One block per (frame, 8-channel plane); a warp takes (output row, 32-column input segment) pairs.  Lane l loads input
+  // column seg*32 + l of the three rows — a warp reads 512 contiguous bytes per row, every 32-byte sector fully used (the
+  // per-output 16-byte gathers of the first versions made the kernel L1-bound: 12x sector amplification) — and keeps the
+  // column's vertical maximum; the 16 outputs of the segment combine columns 2w-1, 2w, 2w+1 by shuffle.
+  // All index arithmetic is 32-bit relative to the frame origin.
+  const int frame = blockIdx.x, chunk = blockIdx.y;
+  const int n = frame / go.T, t = frame - n * go.T;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const __nv_bfloat16* xc = x + (int64_t)chunk * xs + uc_flat(gi, n, t, 0, 0) * 8;      // input pixel (0,0) of this frame
+  const __nv_bfloat16* xlc = xlo ? xlo + (int64_t)chunk * xs + uc_flat(gi, n, t, 0, 0) * 8 : nullptr;
+  __nv_bfloat16* yc = y + (int64_t)chunk * ys + uc_flat(go, n, t, 0, 0) * 8;
+  __nv_bfloat16* ylc = ylo ? ylo + (int64_t)chunk * ys + uc_flat(go, n, t, 0, 0) * 8 : nullptr;
+  auto ld = [&](int pos, float* f) {
+    unpack8(*reinterpret_cast<const uint4*>(xc + pos * 8), f);
+    if (xlc) {
+      float fl[8];
+      unpack8(*reinterpret_cast<const uint4*>(xlc + pos * 8), fl);
 #pragma unroll
-  for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
-  for (int dh = 0; dh < 3; ++dh) {
-    const int hi = 2 * h - 1 + dh;
-    if ((unsigned)hi >= (unsigned)gi.H) continue;
-    for (int dw = 0; dw < 3; ++dw) {
-      const int wi = 2 * w - 1 + dw;
-      if ((unsigned)wi >= (unsigned)gi.W) continue;
-      float f[8];
-      const int64_t src = (int64_t)chunk * xs + uc_flat(gi, n, t, hi, wi) * 8;
-      unpack8(*reinterpret_cast<const uint4*>(x + src), f);
-      if (xlo) {
-        float fl[8];
-        unpack8(*reinterpret_cast<const uint4*>(xlo + src), fl);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] += fl[e];
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], f[e]);
+      for (int e = 0; e < 8; ++e) f[e] += fl[e];
     }
-  }
-  const int64_t dst = (int64_t)chunk * ys + uc_flat(go, n, t, h, w) * 8;
-  const uint4 hi4 = pack8(m);
-  *reinterpret_cast<uint4*>(y + dst) = hi4;
-  if (ylo) {
-    float hf[8], lo[8];
-    unpack8(hi4, hf);
+  };
+  const int nseg = (gi.W + 31) >> 5;
+  const int npairs = go.H * nseg;
+  for (int pair = warp; pair < npairs; pair += nwarps) {
+    const int h = pair / nseg, seg = pair - h * nseg;
+    const int c = seg * 32 + lane;                         // this lane's input column
+    float mv[8], ml[8];                                    // vertical max of column c; of column seg*32 - 1 (lane 0 only)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) lo[e] = m[e] - hf[e];
-    *reinterpret_cast<uint4*>(ylo + dst) = pack8(lo);
+    for (int e = 0; e < 8; ++e) mv[e] = ml[e] = -INFINITY;
+    const bool extra_left = lane == 0 && seg > 0;
+#pragma unroll
+    for (int dh = 0; dh < 3; ++dh) {
+      const int hi = 2 * h - 1 + dh;
+      if ((unsigned)hi >= (unsigned)gi.H) continue;
+      float f[8];
+      if (c < gi.W) {
+        ld(hi * gi.RW + c, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) mv[e] = fmaxf(mv[e], f[e]);
+      }
+      if (extra_left) {
+        ld(hi * gi.RW + c - 1, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ml[e] = fmaxf(ml[e], f[e]);
+      }
+    }
+    const int w = seg * 16 + lane;                         // output column of lanes 0..15
+    float m[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float a = __shfl_sync(0xffffffffu, mv[e], (2 * lane) & 31);
+      const float b = __shfl_sync(0xffffffffu, mv[e], (2 * lane + 1) & 31);
+      const float cl = __shfl_sync(0xffffffffu, mv[e], (2 * lane - 1) & 31);
+      const float left = lane == 0 ? ml[e] : cl;           // (seg == 0: ml stays -inf = the reference's padding)
+      m[e] = fmaxf(fmaxf(a, b), left);
+    }
+    if (lane < 16 && w < go.W) {
+      const int dst = (h * go.RW + w) * 8;
+      const uint4 hi4 = pack8(m);
+      *reinterpret_cast<uint4*>(yc + dst) = hi4;
+      if (ylc) {
+        float hf[8], lo[8];
+        unpack8(hi4, hf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) lo[e] = m[e] - hf[e];
+        *reinterpret_cast<uint4*>(ylc + dst) = pack8(lo);
+      }
+    }
   }
 }
 void launch_planar_maxpool(const __nv_bfloat16* x, int64_t x_plane_stride, UcGeom gi, __nv_bfloat16* y, int64_t y_plane_stride, UcGeom go,
                            int C, cudaStream_t s, const __nv_bfloat16* xlo, __nv_bfloat16* ylo) {
-  const int64_t total = (int64_t)go.N * go.T * go.H * go.W * (C / 8);
-  if (total == 0) return;
-  planar_maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, x_plane_stride, gi, y, y_plane_stride, go, total, xlo, ylo);
+  const int frames = go.N * go.T;
+  if (frames == 0 || go.H * go.W == 0) return;
+  planar_maxpool_kernel<<<dim3((unsigned)frames, (unsigned)(C / 8)), 256, 0, s>>>(x, x_plane_stride, gi, y, y_plane_stride, go, xlo, ylo);
   count_launch();
 }
 
@@ -665,8 +765,217 @@ __global__ void __launch_bounds__(256) video_rows_kernel(const T* __restrict__ v
     }
   }
 }
+
+// ---- bulk-copy (TMA engine) version --------------------------------------------------------------------------------------
+// The register-heavy strip computation above leaves only two blocks per SM, too few to keep HBM busy with ordinary loads.
+// Here the loads are asynchronous: persistent blocks walk (frame, band of VR2_ROWS rows) tiles, one elected thread streams
+// the raw bytes of the next tiles (band + halo rows; one contiguous piece per channel plane, or one piece for interleaved
+// layouts) into a VR2_STAGES-deep shared-memory ring with cp.async.bulk, completion on mbarriers; the 256 threads convert
+// (uint8: /255) and compute from shared memory.  Column halos and rows outside the image are predicated, not staged.
+// `starts` (optional, interleaved uint8 tracks): window n reads frames starts[n] .. starts[n]+T-1 of the track directly
+// (the window builder of lsd_score_windows, video.py:552-556 + predictor.py:566-572, without materialising fp32 windows).
+constexpr int VR2_ROWS = 16, VR2_STAGES = 3, VR2_THREADS = 256;
+template <typename T> __device__ __forceinline__ void vr_load4(const T* p, float* o);
+template <> __device__ __forceinline__ void vr_load4<float>(const float* p, float* o) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+template <> __device__ __forceinline__ void vr_load4<__half>(const __half* p, float* o) {
+  const uint2 v = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+template <> __device__ __forceinline__ void vr_load4<__nv_bfloat16>(const __nv_bfloat16* p, float* o) {
+  const uint2 v = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+template <> __device__ __forceinline__ void vr_load4<uint8_t>(const uint8_t* p, float* o) {
+  const uint32_t v = *reinterpret_cast<const uint32_t*>(p);
+  o[0] = (float)(v & 0xffu) / 255.0f; o[1] = (float)((v >> 8) & 0xffu) / 255.0f;
+  o[2] = (float)((v >> 16) & 0xffu) / 255.0f; o[3] = (float)(v >> 24) / 255.0f;
+}
+
+template <typename T, int LAYOUT>
+__global__ void __launch_bounds__(VR2_THREADS, 2) video_rows_tma_kernel(const T* __restrict__ video, const int32_t* __restrict__ starts, int n_frames,
+                                                                    const float* __restrict__ lapw, __nv_bfloat16* __restrict__ xs,
+                                                                    __nv_bfloat16* __restrict__ xl, int64_t set_stride, UcGeom g, int Tn, int H, int W,
+                                                                    int bands, int num_tiles) {
+  extern __shared__ __align__(128) uint8_t vr_smem[];
+  __shared__ uint64_t full_bar[VR2_STAGES];
+  __shared__ float lw[81];
+  const int tid = threadIdx.x;
+  const int row_elems = LAYOUT == 0 ? W : 3 * W;                       // elements of one image row in one staged piece
+  const int plane_elems = (VR2_ROWS + 2) * row_elems;                  // one staged piece (all rows of the band + halo)
+  const uint32_t stage_bytes = (uint32_t)((LAYOUT == 0 ? 3 : 1) * plane_elems * (int)sizeof(T));
+  const uint32_t stage_pitch = (stage_bytes + 127u) & ~127u;
+  if (tid < 81) lw[tid] = lapw[tid];
+  if (tid == 0) {
+    for (int i = 0; i < VR2_STAGES; ++i) mbar_init(&full_bar[i], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int k) {   // thread 0: stream tile k of this block into stage k % VR2_STAGES
+    const int tile = blockIdx.x + k * gridDim.x;
+    if (tile >= num_tiles) return;
+    const int band = tile % bands, nt = tile / bands;
+    const int h0 = band * VR2_ROWS;
+    const int r_lo = h0 == 0 ? 1 : 0;                                    // first staged tile row (tile row r <-> image row h0-1+r)
+    const int r_hi = min(VR2_ROWS + 2, H - h0 + 1);                      // one past the last staged tile row
+    const uint32_t bytes = (uint32_t)((r_hi - r_lo) * row_elems * (int)sizeof(T));
+    uint8_t* dst = vr_smem + (size_t)(k % VR2_STAGES) * stage_pitch + (size_t)r_lo * row_elems * sizeof(T);
+    uint64_t* bar = &full_bar[k % VR2_STAGES];
+    if (LAYOUT == 0) {
+      const int n = nt / Tn, t = nt - n * Tn;
+      mbar_arrive_expect_tx(bar, 3u * bytes);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const T* src = video + ((((int64_t)n * 3 + c) * Tn + t) * H + (h0 - 1 + r_lo)) * W;
+        bulk_g2s(dst + (size_t)c * plane_elems * sizeof(T), src, bytes, bar);
+      }
+    } else {
+      int64_t frame = nt;
+      if (starts) {
+        const int n = nt / Tn, t = nt - n * Tn;
+        int f = starts[n] + t;
+        frame = f < 0 ? 0 : (f >= n_frames ? n_frames - 1 : f);
+      }
+      mbar_arrive_expect_tx(bar, bytes);
+      bulk_g2s(dst, video + (frame * H + (h0 - 1 + r_lo)) * (int64_t)row_elems, bytes, bar);
+    }
+  };
+  if (tid == 0)
+    for (int k = 0; k < VR2_STAGES - 1; ++k) issue(k);
+
+  const int nstrips = W >> 2;
+  const int ntasks = VR2_ROWS * nstrips;
+  for (int k = 0;; ++k) {
+    const int tile = blockIdx.x + k * gridDim.x;
+    if (tile >= num_tiles) break;
+    if (tid == 0) issue(k + VR2_STAGES - 1);      // its stage was drained before the barrier that ended iteration k-1
+    mbar_wait(&full_bar[k % VR2_STAGES], (uint32_t)(k / VR2_STAGES) & 1u);
+    const T* st = reinterpret_cast<const T*>(vr_smem + (size_t)(k % VR2_STAGES) * stage_pitch);
+    const int band = tile % bands, nt = tile / bands;
+    const int n = nt / Tn, t = nt - n * Tn;
+    const int h0 = band * VR2_ROWS;
+    for (int task = tid; task < ntasks; task += VR2_THREADS) {
+      const int ty = task / nstrips, p0 = (task - ty * nstrips) << 2;
+      const int h = h0 + ty;
+      if (h >= H) break;
+      float acc[4][3], ctr[4][3];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q][0] = acc[q][1] = acc[q][2] = 0.f;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int hh = h - 1 + kh;
+        float x[3][6];   // channel, pixels p0-1 .. p0+4
+        if ((unsigned)hh < (unsigned)H) {
+          const T* trow = st + (size_t)(ty + kh) * row_elems;
+          if (LAYOUT == 0) {
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+              const T* pr = trow + (size_t)ci * plane_elems + p0;
+              vr_load4<T>(pr, &x[ci][1]);
+              x[ci][0] = p0 > 0 ? vr_norm<T>((float)pr[-1]) : 0.f;
+              x[ci][5] = p0 + 4 < W ? vr_norm<T>((float)pr[4]) : 0.f;
+            }
+          } else {
+            const T* pr = trow + 3 * p0;
+            float e[12];
+            vr_load4<T>(pr, e); vr_load4<T>(pr + 4, e + 4); vr_load4<T>(pr + 8, e + 8);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+              for (int ci = 0; ci < 3; ++ci) x[ci][q + 1] = e[q * 3 + ci];
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+              x[ci][0] = p0 > 0 ? vr_norm<T>((float)pr[ci - 3]) : 0.f;
+              x[ci][5] = p0 + 4 < W ? vr_norm<T>((float)pr[12 + ci]) : 0.f;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+            for (int j = 0; j < 6; ++j) x[ci][j] = 0.f;
+        }
+        if (kh == 1) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) ctr[q][ci] = x[ci][q + 1];
+        }
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const int wi = ((kh * 3 + kw) * 3 + ci) * 3;
+            const float w0 = lw[wi], w1 = lw[wi + 1], w2 = lw[wi + 2];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              acc[q][0] = fmaf(w0, x[ci][q + kw], acc[q][0]);
+              acc[q][1] = fmaf(w1, x[ci][q + kw], acc[q][1]);
+              acc[q][2] = fmaf(w2, x[ci][q + kw], acc[q][2]);
+            }
+          }
+      }
+      const int64_t dst = (int64_t)(h & 1) * set_stride + uc_flat(g, n, t, h >> 1, 0) * 8 + 16 + (int64_t)p0 * 4;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        float px[8], lp[8];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { px[q * 4 + c] = ctr[2 * u + q][c]; lp[q * 4 + c] = acc[2 * u + q][c]; }
+          px[q * 4 + 3] = 0.f; lp[q * 4 + 3] = 0.f;
+        }
+        *reinterpret_cast<uint4*>(xs + dst + u * 8) = pack8(px);
+        *reinterpret_cast<uint4*>(xl + dst + u * 8) = pack8(lp);
+      }
+    }
+    __syncthreads();   // every thread is done with this stage before it is refilled (issue(k + STAGES) at iteration k + 1)
+  }
+}
+
+bool video_rows_bulk_ok(const void* video, int dtype, int layout, int W) {
+  const size_t esz = dtype == 0 ? 4 : (dtype == 3 ? 1 : 2);
+  const size_t row_bytes = (size_t)W * esz * (layout == 0 ? 1 : 3);
+  const size_t stage = (((layout == 0 ? 3 : 1) * (size_t)(VR2_ROWS + 2) * row_bytes) + 127) & ~size_t(127);
+  return (W % 4 == 0) && (row_bytes % 16 == 0) && (reinterpret_cast<uintptr_t>(video) % 16 == 0) && stage * VR2_STAGES <= 96 * 1024;
+}
+
 void launch_video_rows(const void* video, int dtype, int layout, const float* lapw, __nv_bfloat16* xs, __nv_bfloat16* xl,
-                       int64_t set_stride, UcGeom g, int H, int W, cudaStream_t s) {
+                       int64_t set_stride, UcGeom g, int H, int W, cudaStream_t s, const int32_t* starts, int n_frames) {
+  const size_t esz = dtype == 0 ? 4 : (dtype == 3 ? 1 : 2);
+  const size_t row_bytes = (size_t)W * esz * (layout == 0 ? 1 : 3);
+  const size_t stage = (((layout == 0 ? 3 : 1) * (size_t)(VR2_ROWS + 2) * row_bytes) + 127) & ~size_t(127);
+  if (video_rows_bulk_ok(video, dtype, layout, W)) {
+    const int bands = (H + VR2_ROWS - 1) / VR2_ROWS;
+    const int64_t tiles = (int64_t)g.N * g.T * bands;
+    if (tiles == 0) return;
+    static int num_sms = 0;
+    if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+    const size_t smem = stage * VR2_STAGES;
+    const int64_t per_sm = 2;   // 128 registers x 256 threads: two resident blocks per SM
+    const unsigned grid = (unsigned)std::min<int64_t>(tiles, per_sm * num_sms);
+#define VRT(TT, LL)                                                                                                             \
+  do {                                                                                                                          \
+    static bool attr = false;                                                                                                   \
+    if (!attr) { cudaFuncSetAttribute(video_rows_tma_kernel<TT, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; } \
+    video_rows_tma_kernel<TT, LL><<<grid, VR2_THREADS, smem, s>>>(reinterpret_cast<const TT*>(video), starts, n_frames, lapw, xs, xl,    \
+                                                                  set_stride, g, g.T, H, W, bands, (int)tiles);               \
+  } while (0)
+    if (layout == 0) {
+      if (dtype == 0) VRT(float, 0); else if (dtype == 1) VRT(__half, 0); else if (dtype == 2) VRT(__nv_bfloat16, 0); else VRT(uint8_t, 0);
+    } else {
+      if (dtype == 0) VRT(float, 1); else if (dtype == 1) VRT(__half, 1); else if (dtype == 2) VRT(__nv_bfloat16, 1); else VRT(uint8_t, 1);
+    }
+#undef VRT
+    count_launch();
+    return;
+  }
+  // fallback (unaligned rows / odd widths): direct loads; a start table is not supported here (the caller gathers first)
   const int bands = (H + VR_ROWS - 1) / VR_ROWS;
   const int64_t blocks = (int64_t)g.N * g.T * bands;
   if (blocks == 0) return;
@@ -730,11 +1039,65 @@ __global__ void planar_mean2_kernel(const __nv_bfloat16* __restrict__ x, int64_t
     }
   }
 }
+// Short means (<= 32 positions: the 3x3 spatial mean of the visual tokens, the mean over F' = 3 of the audio tokens): one
+// THREAD per (row, 8-channel chunk) summing serially — the block-per-row tree above launched 65k one-warp blocks for 9 values.
+__global__ void __launch_bounds__(256) planar_mean2_small_kernel(const __nv_bfloat16* __restrict__ x, int64_t plane_stride, UcGeom g,
+                                                                 float* __restrict__ y32, int ld, int mode, PlanarOut po,
+                                                                 const __nv_bfloat16* __restrict__ xlo, int rows, int nchunks) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * nchunks) return;
+  const int chunk = i / rows, row = i - chunk * rows;      // consecutive threads -> consecutive rows of one plane
+  const int count = mode == 0 ? g.H * g.W : g.H;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int k = 0; k < count; ++k) {
+    int n, t, h, w;
+    if (mode == 2) { n = row / g.W; w = row - n * g.W; t = 0; h = k; }
+    else { n = row / g.T; t = row - n * g.T; h = k / g.W; w = k - h * g.W; }
+    const int64_t off = (int64_t)chunk * plane_stride + uc_flat(g, n, t, h, w) * 8;
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + off), f);
+    if (xlo) {
+      float fl[8];
+      unpack8(*reinterpret_cast<const uint4*>(xlo + off), fl);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] += fl[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += f[e];
+  }
+  float m[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) m[e] = acc[e] / (float)count;
+  if (y32) {
+    float4* o = reinterpret_cast<float4*>(y32 + (int64_t)row * ld + chunk * 8);
+    o[0] = make_float4(m[0], m[1], m[2], m[3]);
+    o[1] = make_float4(m[4], m[5], m[6], m[7]);
+  }
+  if (po.y) {
+    const int64_t pos = po.grp > 0 ? ((int64_t)row / po.grp) * po.grp_stride + (row % po.grp) + po.off : (int64_t)row + po.off;
+    const uint4 hi4 = pack8(m);
+    *reinterpret_cast<uint4*>(po.y + (int64_t)chunk * po.plane_stride + pos * 8) = hi4;
+    if (po.ylo) {
+      float hf[8], lo[8];
+      unpack8(hi4, hf);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) lo[e] = m[e] - hf[e];
+      *reinterpret_cast<uint4*>(po.ylo + (int64_t)chunk * po.plane_stride + pos * 8) = pack8(lo);
+    }
+  }
+}
+
 void launch_planar_mean2(const __nv_bfloat16* x, int64_t plane_stride, UcGeom g, int C, float* y32, int ld, int mode, PlanarOut po, cudaStream_t s,
                          const __nv_bfloat16* xlo) {
   const int rows = mode == 1 ? g.N : (mode == 0 ? g.N * g.T : g.N * g.W);
   if (rows == 0) return;
   const int count = mode == 1 ? g.T * g.H * g.W : (mode == 0 ? g.H * g.W : g.H);
+  if (mode != 1 && count <= 32 && (ld % 4) == 0 && (!y32 || reinterpret_cast<uintptr_t>(y32) % 16 == 0)) {
+    const int total = rows * (C / 8);
+    planar_mean2_small_kernel<<<(total + 255) / 256, 256, 0, s>>>(x, plane_stride, g, y32, ld, mode, po, xlo, rows, C / 8);
+    count_launch();
+    return;
+  }
   int threads = 32;
   while (threads < 256 && threads < count) threads <<= 1;
   planar_mean2_kernel<<<dim3(rows, C / 8), threads, 0, s>>>(x, plane_stride, g, y32, ld, mode, po, xlo);

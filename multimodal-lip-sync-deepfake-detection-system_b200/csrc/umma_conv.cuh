@@ -71,6 +71,8 @@ struct UmmaConvP {
   int MT, stages, ngroups, nbands;
   int nbuf;                   // TMEM accumulator buffers: 2 = epilogue overlaps the next tile, 1 = all 512 columns for one tile
   long long* dbg;             // optional: CTA (0,0) writes clock64 phase timestamps (debug builds of the bench only)
+  int nst_tile;               // ring stages per tile (sum over groups of ceil(k16 / kpack) * bands): length of the stage program
+  int skip;                   // debug (LSD_UMMA_SKIP): bit 0 = no A copies, bit 1 = no W copies — timing experiments only
   int kpack;                  // k16 chunks per pipeline stage (small-K-step layers amortise the mbarrier round trip)
   uint32_t a_stage_bytes, w_stage_bytes, tmem_cols;
   UcGeom g;                   // output geometry (== input geometry of every band)
@@ -80,6 +82,7 @@ struct UmmaConvP {
 };
 
 size_t umma_conv_smem_bytes(const UmmaConvP& p);
+int umma_conv_stage_desc_bytes();
 void launch_umma_conv(const UmmaConvP& p, int n_slices, cudaStream_t s, int max_ctas = 0);
 
 // ---- planar-layout glue --------------------------------------------------------------------------
@@ -101,8 +104,11 @@ void launch_planar_maxpool(const __nv_bfloat16* x, int64_t x_plane_stride, UcGeo
 // video (any dtype; NCDHW or NDHWC; uint8 scaled by 1/255) -> bf16 pixel rows xs (stem input) and xl = per-frame 3x3 conv 3->3
 // with weights lapw [tap][ci][co] (artifact_detector.py:33-35,55-57).  Row layout: h-parity plane sets, geometry g (units of
 // 2 pixels), pixel p of a row at element offset (p + 4) * 4, channels (r, g, b, 0).
+// starts != nullptr (interleaved tracks, bulk-copy path only — check video_rows_bulk_ok): window n reads frames
+// starts[n] .. starts[n]+T-1 of an n_frames-long track instead of frames n*T .. n*T+T-1.
 void launch_video_rows(const void* video, int dtype, int layout, const float* lapw, __nv_bfloat16* xs, __nv_bfloat16* xl,
-                       int64_t set_stride, UcGeom g, int H, int W, cudaStream_t s);
+                       int64_t set_stride, UcGeom g, int H, int W, cudaStream_t s, const int32_t* starts = nullptr, int n_frames = 0);
+bool video_rows_bulk_ok(const void* video, int dtype, int layout, int W);
 
 inline UcGeom make_geom_ex(int N, int T, int H, int W, int tpad, int oh, int hp_extra, int ow, int wp_extra) {
   UcGeom g;

@@ -255,9 +255,11 @@ class Predictor:
 
     # ------------------------------------------------------------------ device-side window builder
     def score_track_logits(self, track_u8: torch.Tensor, starts: Sequence[int], mel_full: torch.Tensor, total_v_frames: int,
-                           chunk_a_size: int = 128) -> torch.Tensor:
+                           chunk_a_size: int = 128, audio_starts_from: Optional[Sequence[int]] = None) -> torch.Tensor:
         """uint8 track `(n_frames,H,W,3)` + window start frames + clip log-mel `(1,F,Ta_full)` (both on the device)
-        -> fp32 logits `(n_windows,)` on the device.  Windows are built on the GPU (`/255`, audio alignment)."""
+        -> fp32 logits `(n_windows,)` on the device.  Windows are built on the GPU (`/255`, audio alignment).
+        `audio_starts_from`: absolute start frames used for the audio alignment when `track_u8` is only a rank-local span
+        of the full track and `starts` are relative to that span (sharded long videos)."""
         m = self.model
         dev = m._device()
         if track_u8.dtype != torch.uint8 or track_u8.dim() != 4 or track_u8.shape[3] != 3:
@@ -282,7 +284,12 @@ class Predictor:
                 _cabi.check(h.ptr, _cabi.LSD_ERR_SHAPE)
             ws = m._workspace(need, dev)
             st = (C.c_int32 * n)(*[int(s) for s in starts])
-            rc = L.lsd_score_windows(h.ptr, track_u8.data_ptr(), n_frames, H, W, st, n, self.chunk_size, mel_full.data_ptr(),
+            ast = None
+            if audio_starts_from is not None:
+                if len(audio_starts_from) != n:
+                    raise ValueError("audio_starts_from must have one entry per window")
+                ast = (C.c_int32 * n)(*[self._audio_start(int(v), Ta_full, int(total_v_frames), chunk_a_size) for v in audio_starts_from])
+            rc = L.lsd_score_windows(h.ptr, track_u8.data_ptr(), n_frames, H, W, st, ast, n, self.chunk_size, mel_full.data_ptr(),
                                      F_, Ta_full, int(total_v_frames), chunk_a_size, prec, batch, logits.data_ptr(),
                                      ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream)
             _cabi.check(h.ptr, rc)

@@ -238,6 +238,59 @@ class LipSyncModel(nn.Module):
         self.eval()
         return self.forward(visual, audio)
 
+    # ------------------------------------------------------------------ sub-paths (tensor-core route)
+    def encode_audio(self, audio: Tensor) -> Tensor:
+        """`AudioEncoder.forward` (audio_encoder.py:173-205) alone: log-mel `(B,1,F,T_a)` -> `(B, 256, T_a')` fp32."""
+        if audio.dim() != 4 or audio.shape[1] != 1:
+            raise ValueError(f"AudioEncoder expected input of shape (B, 1, F, T), got {tuple(audio.shape)}")
+        dev = self._device()
+        if audio.device != dev or audio.dtype not in _DTYPES or audio.dtype == torch.uint8:
+            raise RuntimeError(f"audio must be a float tensor on {dev}")
+        B, F_, Ta = int(audio.shape[0]), int(audio.shape[2]), int(audio.shape[3])
+        with self._lsd_lock:
+            h = self._ensure_handle(dev)
+            L = _cabi.lib()
+            tok = L.lsd_audio_tokens(Ta)
+            out = torch.empty(B, tok, 256, dtype=torch.float32, device=dev)
+            if B == 0:
+                return out.transpose(1, 2)
+            need = L.lsd_audio_encoder_workspace_bytes(h.ptr, B, F_, Ta)
+            if need == 0:
+                _cabi.check(h.ptr, _cabi.LSD_ERR_SHAPE)
+            ws = self._workspace(need, dev)
+            audio = audio.contiguous()
+            rc = L.lsd_audio_encoder(h.ptr, audio.data_ptr(), _DTYPES[audio.dtype], B, F_, Ta, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                     torch.cuda.current_stream(dev).cuda_stream)
+            _cabi.check(h.ptr, rc)
+        return out.transpose(1, 2)
+
+    def fuse_tokens(self, v_emb: Tensor, a_emb: Tensor) -> Tuple[Tensor, Tensor]:
+        """`CrossModalAttention.forward` + `TemporalTransformer.forward` (fusion_module.py:54-87, temporal.py:79-111):
+        projected embeddings `(B,T,256)`, `(B,T_a,256)` -> `(fused (B,T,256), cls (B,256))`, fp32."""
+        if v_emb.dim() != 3 or a_emb.dim() != 3 or v_emb.shape[2] != 256 or a_emb.shape[2] != 256 or v_emb.shape[0] != a_emb.shape[0]:
+            raise ValueError(f"expected v_emb (B,T,256) and a_emb (B,T_a,256), got {tuple(v_emb.shape)}, {tuple(a_emb.shape)}")
+        dev = self._device()
+        if v_emb.device != dev or a_emb.device != dev:
+            raise RuntimeError(f"inputs must live on the module's device {dev}")
+        B, T, TA = int(v_emb.shape[0]), int(v_emb.shape[1]), int(a_emb.shape[1])
+        v_emb = v_emb.to(torch.float32).contiguous()
+        a_emb = a_emb.to(torch.float32).contiguous()
+        fused = torch.empty(B, T, 256, dtype=torch.float32, device=dev)
+        cls = torch.empty(B, 256, dtype=torch.float32, device=dev)
+        if B == 0:
+            return fused, cls
+        with self._lsd_lock:
+            h = self._ensure_handle(dev)
+            L = _cabi.lib()
+            need = L.lsd_token_path_workspace_bytes(h.ptr, B, T, TA)
+            if need == 0:
+                _cabi.check(h.ptr, _cabi.LSD_ERR_SHAPE)
+            ws = self._workspace(need, dev)
+            rc = L.lsd_token_path(h.ptr, v_emb.data_ptr(), a_emb.data_ptr(), B, T, TA, fused.data_ptr(), cls.data_ptr(), ws.data_ptr(),
+                                  ws.numel(), torch.cuda.current_stream(dev).cuda_stream)
+            _cabi.check(h.ptr, rc)
+        return fused, cls
+
     # ------------------------------------------------------------------ introspection (tests / profiling)
     def stage(self, name: str) -> Tensor:
         """Flat fp32/bf16 view of a named intermediate of the last forward (lives in the workspace)."""

@@ -3,9 +3,9 @@ import csv, sys
 path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/launches.csv"
 with open(path) as f:
     lines = [l for l in f if not l.startswith("==")]
-rows = list(csv.DictReader(lines))
-names = [(r["Kernel Name"], float(r["Metric Value"].replace(",", "")), r["Grid Size"]) for r in rows]
-idx = [i for i, (n, _, _) in enumerate(names) if n.startswith("void lsd::video_rows") or n.startswith("video_rows") or "video_rows_kernel" in n]
+rows = [r for r in csv.DictReader(lines) if r["Metric Name"] == "gpu__time_duration.sum"]
+names = [(r["Kernel Name"], float(r["Metric Value"].replace(",", "")) * {"ns": 1, "us": 1e3, "ms": 1e6}.get(r["Metric Unit"], 1), r["Grid Size"]) for r in rows]
+idx = [i for i, (n, _, _) in enumerate(names) if "video_rows" in n]
 start = idx[-1]
 tot = 0
 agg = {}

@@ -249,3 +249,54 @@ def test_launch_counter_counts(model):
     n0 = model.launch_count()
     model(video.cuda(), audio.cuda())
     assert model.launch_count() - n0 > 50
+
+
+def test_audio_encoder_subpath(model, seed0_sd):
+    """lsd_audio_encoder == the audio branch of the full forward (bitwise) and == AudioEncoder.forward of the oracle
+    (audio_encoder.py:173-205) within the bf16-route budget (split-bf16 operands: ~1e-4 relative)."""
+    model.compute_precision = "bf16"
+    video, audio = lb.synthetic_windows(1, 3)
+    inter = {}
+    orc.forward(seed0_sd, video, audio, inter=inter)
+    _, aux = model(video.cuda(), audio.cuda(), return_aux=True)
+    full = model.stage("a_feat").clone().view(3, -1, 256)
+    got = model.encode_audio(audio.cuda())                    # (B, 256, T')
+    assert got.shape == (3, 256, 16)
+    assert torch.equal(got.transpose(1, 2).contiguous(), full)
+    assert _rel(got.cpu(), orc.audio_encoder(seed0_sd, audio)) <= 2e-3
+    # ragged / batch extremes of the sweep (BASELINE.json configs[2]): B = 1 and a non-multiple-of-tile batch
+    for b in (1, 5):
+        _, a = lb.synthetic_windows(7, b)
+        o = model.encode_audio(a.cuda())
+        assert o.shape == (b, 256, 16) and torch.isfinite(o).all()
+    assert model.encode_audio(audio.cuda()[:0]).shape == (0, 256, 16)
+    with pytest.raises(ValueError):
+        model.encode_audio(audio.cuda()[:, 0])
+
+
+def test_token_path_subpath(model, seed0_sd):
+    """lsd_token_path (CrossModalAttention + TemporalTransformer, fusion_module.py:54-87 / temporal.py:79-111) fed with the
+    projected embeddings of a full forward reproduces that forward's fused tokens and CLS output bitwise, and matches the
+    oracle's `fused` / `cls` within the bf16-route budget."""
+    model.compute_precision = "bf16"
+    video, audio = lb.synthetic_windows(1, 3)
+    inter = {}
+    orc.forward(seed0_sd, video, audio, inter=inter)
+    _, aux = model(video.cuda(), audio.cuda(), return_aux=True)
+    fused, cls = model.fuse_tokens(aux["visual_tokens"], aux["audio_tokens"])
+    assert torch.equal(fused, aux["fused_tokens"])
+    assert torch.equal(cls, aux["cls_output"])
+    f2, c2 = model.fuse_tokens(inter["v_emb"].cuda(), inter["a_emb"].cuda())
+    assert _rel(f2.cpu(), inter["fused"]) <= 2e-3
+    assert _rel(c2.cpu(), inter["cls"]) <= 2e-3
+    # half windows (T=16, 8 audio tokens) and a large batch (BASELINE.json configs[3]: B=256)
+    g = torch.Generator().manual_seed(4)
+    v = torch.randn(256, 32, 256, generator=g).cuda()
+    a = torch.randn(256, 16, 256, generator=g).cuda()
+    fb, cb = model.fuse_tokens(v, a)
+    f1, c1 = model.fuse_tokens(v[:5], a[:5])
+    assert torch.equal(fb[:5], f1) and torch.equal(cb[:5], c1)      # batch-composition independence
+    fh, ch = model.fuse_tokens(v[:4, :16], a[:4, :8])
+    assert fh.shape == (4, 16, 256) and ch.shape == (4, 256) and torch.isfinite(ch).all()
+    with pytest.raises(ValueError):
+        model.fuse_tokens(v[:, :, :128], a)
