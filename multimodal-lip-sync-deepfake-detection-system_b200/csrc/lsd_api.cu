@@ -66,6 +66,7 @@ extern "C" void lsd_destroy(lsd_handle* h) {
   if (h->barena) cudaFree(h->barena);
   if (h->bbias) cudaFree(h->bbias);
   if (h->mel_tables) cudaFree(h->mel_tables);
+  if (h->prog_arena) cudaFree(h->prog_arena);
   for (cudaEvent_t e : h->prof.ev) cudaEventDestroy(e);
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);

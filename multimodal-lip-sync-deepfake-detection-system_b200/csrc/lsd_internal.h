@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <map>
+#include <unordered_map>
 #include <string>
 #include <vector>
 
@@ -66,6 +67,10 @@ struct lsd_handle {
   cudaStream_t side_stream = nullptr;      // artifact branch runs here, concurrently with the token path
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int64_t launches0 = 0;
+  // stage programs of the tcgen05 launches (umma_conv.cuh): built on the host once per (layer, shapes, workspace), cached here
+  char* prog_arena = nullptr;
+  size_t prog_cap = 0, prog_cursor = 0;
+  std::unordered_map<uint64_t, const void*> prog_cache;
   // log-mel tables (device): hann[400], cos[400], sin[400], melw[80*32], lo[80], cnt[80]
   void* mel_tables = nullptr;
   const float *d_hann = nullptr, *d_cos = nullptr, *d_sin = nullptr, *d_melw = nullptr;

@@ -79,71 +79,12 @@ constexpr int UC_PROD_LANES = 8;   // 32 issuers >= copies per stage (2 * kpack 
 // GENERIC = false: lean epilogue of the convolution layers (bias, ReLU/none, optional bf16 residual, planar / parity-split bf16
 // store).  GENERIC = true: everything (fp32 rows in/out, split-bf16 hi/lo outputs and residuals, GELU) for the audio encoder and
 // the token-path GEMMs.  Two instantiations keep each one small enough for the instruction cache.
-// Per-tile "stage program" of the producers.  The sequence of ring stages (group, K-chunk block, band) is the same for every
-// tile; only the tile's first position P0 shifts the A sources.  Computing a stage's copy operands from the parameter block
-// costs ~150 dependent instructions (indexed constant loads + 64-bit multiplies), i.e. ~1200 cycles for the single issuing
-// warp — more than the MMA time of a stage for every layer with few taps per stage (token GEMMs, audio encoder, N = 256
-// tiles), which made those launches producer-latency-bound.  The program is therefore expanded ONCE per CTA in the prologue
-// (all 448 threads, one stage each) into shared memory and the producer loop only reads 64-byte descriptors.
-struct __align__(16) UcStageDesc {
-  uint64_t a_src;            // global byte address of the stage's first A piece for P0 = 0
-  uint64_t w_src;            // global byte address of the stage's first weight piece (slice included)
-  uint64_t chunk_stride_b;   // bytes between consecutive K-chunk pairs of planes
-  uint64_t plane_stride_b;   // bytes between the two 8-channel planes of a K chunk
-  uint32_t bytesA;           // bytes of one A piece
-  uint32_t w_copy_bytes;     // bytes of one weight copy
-  uint32_t w_dst_step;       // shared-memory distance between weight pieces
-  uint32_t tx_bytes;         // bytes the stage's full barrier expects
-  uint32_t n_a, n_w;         // number of A / weight copies
-  uint32_t pad0;             // global distance between weight pieces of consecutive K chunks
-  uint32_t pad1;             // band index | (K chunks in this stage << 8)
-};
-static_assert(sizeof(UcStageDesc) == 64, "UcStageDesc must be 64 bytes");
-
-__device__ __forceinline__ void uc_build_stage(const UmmaConvP& p, const UcGroup* groups, const UcBand* bands, int s, int S, int slice,
-                                               UcStageDesc* out) {
-  int cnt = 0, gi = 0, c0 = 0, b = 0;
-  for (; gi < p.ngroups; ++gi) {
-    const UcGroup& g = groups[gi];
-    const int nb = g.band_end - g.band_begin;
-    const int n = ((g.k16 + p.kpack - 1) / p.kpack) * nb;
-    if (s < cnt + n) { const int r = s - cnt; c0 = (r / nb) * p.kpack; b = g.band_begin + r % nb; break; }
-    cnt += n;
-  }
-  const UcGroup& g = groups[gi];
-  const UcBand& bd = bands[b];
-  const int nc = min(p.kpack, g.k16 - c0);
-  UcStageDesc d;
-  const uint32_t bytesW = (uint32_t)bd.ntaps * (uint32_t)p.Cout * 32u;
-  d.bytesA = bd.toeplitz ? (uint32_t)(S + bd.len_extra + 1 + 2 * (nc - 1)) * 16u : (uint32_t)(S + bd.len_extra) * 16u;
-  d.n_a = bd.toeplitz ? 1u : 2u * (uint32_t)nc;   // Toeplitz: the K chunks are 32-byte shifts of one row region
-  // single-band groups (Linear layers): the weights of consecutive K chunks are contiguous -> one copy
-  const bool w_merged = (g.band_end - g.band_begin) == 1;
-  d.n_w = w_merged ? 1u : (uint32_t)nc;
-  d.w_copy_bytes = w_merged ? (uint32_t)nc * bytesW : bytesW;
-  d.w_dst_step = bytesW;
-  // (p.skip: timing experiments only — bit 0 drops the A copies, bit 1 the W copies; results are then garbage)
-  if (p.skip & 1) d.n_a = 0;
-  if (p.skip & 2) d.n_w = 0;
-  d.tx_bytes = d.n_a * d.bytesA + (d.n_w ? (uint32_t)nc * bytesW : 0u);
-  d.a_src = reinterpret_cast<uint64_t>(bd.base + (int64_t)c0 * bd.chunk_stride + (int64_t)bd.start * 8);
-  d.chunk_stride_b = (uint64_t)bd.chunk_stride * 2u;
-  d.plane_stride_b = (uint64_t)bd.plane_stride * 2u;
-  // weight piece j of the stage is the packed block [chunk c0 + j][taps of this band]: pieces are taps_total * Cout * 32 B apart
-  d.w_src = reinterpret_cast<uint64_t>(p.w + g.w_off + (int64_t)slice * g.slice_stride + ((int64_t)c0 * g.taps_total + bd.tap_begin) * (int64_t)p.Cout * 16);
-  d.pad0 = (uint32_t)g.taps_total * (uint32_t)p.Cout * 32u;   // global distance between weight pieces of consecutive K chunks
-  d.pad1 = (uint32_t)b | ((uint32_t)nc << 8);                // band index and K chunks of the stage (MMA issuers)
-  *out = d;
-}
-
 template <bool GENERIC>
 __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_constant__ UmmaConvP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_s[256];
-  __shared__ __align__(16) UcBand bands_s[UC_MAX_BANDS];
-  __shared__ __align__(16) UcGroup groups_s[UC_MAX_GROUPS];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
   if (dbg && tid == 0) p.dbg[0] = clock64();
@@ -161,19 +102,13 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
   }
   if (warp == UC_EPI_WARP0) { tmem_alloc(&tmem_base_s, p.tmem_cols); tmem_relinquish(); }
   for (int i = tid; i < p.Cout; i += UC_THREADS) bias_s[i] = p.bias ? p.bias[ch0 + i] : 0.0f;
-  // band / group tables: parameter (constant) bank -> shared memory, one word per thread (indexed constant loads are slow and
-  // the loops below would chain them)
-  {
-    const uint32_t* bsrc = reinterpret_cast<const uint32_t*>(p.bands);
-    uint32_t* bdst = reinterpret_cast<uint32_t*>(bands_s);
-    for (int i = tid; i < p.nbands * (int)(sizeof(UcBand) / 4); i += UC_THREADS) bdst[i] = bsrc[i];
-    const uint32_t* gsrc = reinterpret_cast<const uint32_t*>(p.groups);
-    uint32_t* gdst = reinterpret_cast<uint32_t*>(groups_s);
-    for (int i = tid; i < p.ngroups * (int)(sizeof(UcGroup) / 4); i += UC_THREADS) gdst[i] = gsrc[i];
-  }
-  __syncthreads();
+  // stage program -> shared memory (one 16-byte piece per thread)
   UcStageDesc* prog = reinterpret_cast<UcStageDesc*>(smem + (size_t)p.stages * stage_bytes);
-  for (int i = tid; i < p.nst_tile; i += UC_THREADS) uc_build_stage(p, groups_s, bands_s, i, S, slice, &prog[i]);
+  {
+    const uint4* psrc = reinterpret_cast<const uint4*>(p.prog);
+    uint4* pdst = reinterpret_cast<uint4*>(prog);
+    for (int i = tid; i < p.nst_tile * 4; i += UC_THREADS) pdst[i] = psrc[i];
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -184,30 +119,42 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
     // ------------------------------------------------ producers (every warp runs the loop; lane 0 of each issues its share)
     int stage = 0, dbg_it = 0;
     uint32_t ph = 0;
-    const int idx0 = lane * UC_PROD_WARPS + warp;          // this lane's copy slot within a stage
+    // Stage k of the CTA's stream (k counts across tiles) belongs to producer warp k % npw: the per-stage work (descriptor reads,
+    // address arithmetic, barrier wait, ~330-cycle bulk-copy issue) then overlaps across the four warps.  Lane l issues the
+    // stage's copy l, all issuing lanes in ONE converged cp.async.bulk.
+    // (Parity waits cannot alias as long as a warp is never two uses of a slot ahead of the consumer: a warp reaches stage k
+    // only after stage k - npw - stages completed, which covers stage k - 2*stages iff stages >= npw.)
+    const int npw = min(UC_PROD_WARPS, p.stages);
+    if (warp >= npw) goto done;
     const uint32_t smem_base = smem_u32(smem);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const uint64_t slice64 = (uint64_t)slice;
+    int k = 0;                                              // global stage counter at the start of the tile
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, k += p.nst_tile) {
       const uint64_t p0_bytes = (uint64_t)tile * (uint64_t)S * 16u;
-      for (int si = 0; si < p.nst_tile; ++si) {
-        // operands of this lane's copy, from the stage program (computed before waiting for the stage to drain)
+      // first stage of this tile owned by this warp: si = (warp - k) mod 4
+      for (int si = ((warp - k) % npw + npw) % npw; si < p.nst_tile; si += npw) {
+        const int kk = k + si;
+        const int stage = kk % p.stages;
+        const uint32_t ph = (uint32_t)(kk / p.stages) & 1u;
         const UcStageDesc& d = prog[si];
-        const uint32_t n_a = d.n_a, n_all = n_a + d.n_w;
-        const bool is_a = (uint32_t)idx0 < n_a;
-        const bool mine = lane < UC_PROD_LANES && (uint32_t)idx0 < n_all;
-        const uint32_t j = is_a ? ((uint32_t)idx0 >> 1) : ((uint32_t)idx0 - n_a);   // K chunk (planar A: plane idx & 1)
+        const uint32_t counts = d.counts;
+        const uint32_t n_a = counts & 0xffu, n_all = n_a + ((counts >> 8) & 0xffu);
+        const bool is_a = (uint32_t)lane < n_a;
+        const bool mine = (uint32_t)lane < n_all;
+        const uint32_t j = is_a ? ((uint32_t)lane >> 1) : ((uint32_t)lane - n_a);   // K chunk (planar A: plane lane & 1)
         const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
-        const uint64_t gsrc = is_a ? d.a_src + p0_bytes + (uint64_t)j * d.chunk_stride_b + (uint64_t)(idx0 & 1) * d.plane_stride_b
-                                   : d.w_src + (uint64_t)j * (uint64_t)d.pad0;
-        const uint32_t dst = is_a ? sa + (uint32_t)idx0 * d.bytesA : sa + p.a_stage_bytes + j * d.w_dst_step;
+        const uint64_t gsrc = is_a ? d.a_src + p0_bytes + (uint64_t)j * d.chunk_stride_b + (uint64_t)(lane & 1) * d.plane_stride_b
+                                   : d.w_src + slice64 * d.w_slice_stride_b + (uint64_t)j * (uint64_t)d.w_src_step;
+        const uint32_t dst = is_a ? sa + (uint32_t)lane * d.bytesA : sa + p.a_stage_bytes + j * d.w_dst_step;
         const uint32_t nbytes = is_a ? d.bytesA : d.w_copy_bytes;
         const uint32_t tx_bytes = d.tx_bytes;
         mbar_wait(&empty_bar[stage], ph ^ 1u);
-        if (dbg && warp == 0 && lane == 0 && dbg_it < 24 && tile == (int)blockIdx.x) p.dbg[32 + dbg_it++] = clock64();
-        if (warp == 0 && lane == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+        if (dbg && lane == 0 && tile == (int)blockIdx.x && si < 24) p.dbg[32 + si] = clock64();
+        if (lane == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+        __syncwarp();                                        // the expectation is registered before any completion can arrive
         if (mine) bulk_s2(dst, reinterpret_cast<const void*>(gsrc), nbytes, &full_bar[stage]);
         __syncwarp();
-        if (dbg && warp == 0 && lane == 0 && dbg_it <= 8 && tile == (int)blockIdx.x) p.dbg[56 + dbg_it - 1] = clock64();   // copies issued
-        if (++stage == p.stages) { stage = 0; ph ^= 1u; }
+        if (dbg && lane == 0 && tile == (int)blockIdx.x && si < 8) p.dbg[56 + si] = clock64();   // copies issued
       }
     }
   } else if (warp == UC_MMA_WARP0 || warp == UC_MMA_WARP0 + 1) {
@@ -219,9 +166,10 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
     // (constant high part) | (start address >> 4); tap / M-tile / K-chunk offsets are added in 16-byte units.
     const uint32_t idesc = idesc_bf16(128, p.Cout);
     const uint32_t smem_base = smem_u32(smem);
-    const uint64_t desc_hi = ((uint64_t)8 << 32) | ((uint64_t)1 << 46);            // SBO = 128 B, descriptor version 1
-    const uint64_t db_hi = desc_hi | ((uint64_t)(uint32_t)p.Cout << 16);           // LBO(B) = Cout * 16 B
+    const uint64_t desc_hi64 = ((uint64_t)8 << 32) | ((uint64_t)1 << 46);          // high word: SBO = 128 B, descriptor version 1
+    const uint32_t b_lbo = (uint32_t)p.Cout << 16;                                 // LBO(B) = Cout * 16 B
     const uint32_t tap_w = (uint32_t)p.Cout * 2u;                                  // Cout * 32 B per tap, in 16 B units
+    const uint32_t leader = elect_one() ? 1u : 0u;                                 // the lane that issues (fixed for the whole kernel)
     int stage = 0, lt = 0, dbg_it = 0;
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
@@ -231,46 +179,45 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
       mbar_wait(&tempty_bar[buf], (use & 1u) ^ 1u);   // epilogue has drained this accumulator buffer
       tc_fence_after();
       uint32_t acc = 0;
-      for (int si = 0; si < p.nst_tile; ++si) {
-        const uint32_t bn = prog[si].pad1;
-        const int nc = (int)(bn >> 8);
-        const UcBand& bd = bands_s[bn & 0xffu];
-        const int ntaps = bd.ntaps;
-        const uint32_t unitsA = (uint32_t)(S + bd.len_extra);
-        const uint64_t da_hi = desc_hi | ((uint64_t)(bd.toeplitz ? 1u : unitsA) << 16);
-        const uint32_t a_chunk = bd.toeplitz ? 2u : 2u * unitsA;
-        const uint32_t w_chunk = (uint32_t)ntaps * tap_w;
-        const uint32_t rel0 = (uint32_t)bd.rel[0];
-        mbar_wait(&full_bar[stage], ph);
-        tc_fence_after();
-        if (dbg && warp == UC_MMA_WARP0 && lane == 0 && acc == 0 && lt == 0) p.dbg[2] = clock64();   // first stage landed
-        if (dbg && warp == UC_MMA_WARP0 && lane == 0 && lt == 0 && dbg_it < 24) p.dbg[8 + dbg_it++] = clock64();
-        const uint32_t sa = (smem_base + (uint32_t)stage * stage_bytes) >> 4;
-        const uint32_t sw = sa + (p.a_stage_bytes >> 4);
-        if (elect_one()) {
-          uint32_t accl = acc;   // 0 only for the very first MMA of each accumulator
-          for (int j = 0; j < nc; ++j) {
-            const uint32_t aj = sa + (uint32_t)j * a_chunk + (uint32_t)mt_lo * 128u, wj = sw + (uint32_t)j * w_chunk;
-            uint32_t rel = rel0;
+      // The loop nest reads the parameter block with warp-uniform indices (uniform constant loads) and runs on every lane;
+      // only the MMA / commit instructions are predicated on the elected lane, so the descriptor arithmetic stays in uniform
+      // registers instead of being moved there (R2UR) for every instruction.
+      for (int gi = 0; gi < p.ngroups; ++gi) {
+        const int k16 = p.groups[gi].k16, b0 = p.groups[gi].band_begin, b1 = p.groups[gi].band_end;
+        for (int c0 = 0; c0 < k16; c0 += p.kpack) {
+          const int nc = min(p.kpack, k16 - c0);
+          for (int b = b0; b < b1; ++b) {
+            const UcBand& bd = p.bands[b];
+            const int ntaps = bd.ntaps;
+            const uint32_t unitsA = (uint32_t)(S + bd.len_extra);
+            const uint32_t a_lbo = (bd.toeplitz ? 1u : unitsA) << 16;     // low descriptor word = LBO << 16 | start address >> 4
+            const uint32_t a_chunk = bd.toeplitz ? 2u : 2u * unitsA;
+            const uint32_t w_chunk = (uint32_t)ntaps * tap_w;
+            mbar_wait(&full_bar[stage], ph);
+            tc_fence_after();
+            if (dbg && warp == UC_MMA_WARP0 && lane == 0 && acc == 0 && lt == 0) p.dbg[2] = clock64();   // first stage landed
+            if (dbg && warp == UC_MMA_WARP0 && lane == 0 && lt == 0 && dbg_it < 24) p.dbg[8 + dbg_it++] = clock64();
+            const uint32_t sa = ((smem_base + (uint32_t)stage * stage_bytes) >> 4) + (uint32_t)mt_lo * 128u;
+            const uint32_t sw = ((smem_base + (uint32_t)stage * stage_bytes + p.a_stage_bytes) >> 4) | b_lbo;
+            for (int j = 0; j < nc; ++j) {
+              const uint32_t aj = (sa + (uint32_t)j * a_chunk) | a_lbo;
+              uint32_t wj = sw + (uint32_t)j * w_chunk;
 #pragma unroll 1
-            for (int tp = 0; tp < ntaps; ++tp) {   // (not unrolled: the kernel must stay inside the instruction cache)
-              const uint32_t rel_next = (uint32_t)bd.rel[tp + 1 < ntaps ? tp + 1 : tp];   // shared-memory load overlaps the issue
-              const uint64_t db = db_hi | (uint64_t)(wj + (uint32_t)tp * tap_w);
-              const uint32_t at = aj + rel;
-              mma_bf16_ss(tb, da_hi | (uint64_t)at, db, idesc, accl);
-              if (mt_n > 1) mma_bf16_ss(tb + (uint32_t)p.Cout, da_hi | (uint64_t)(at + 128u), db, idesc, accl);
-              accl = 1u;
-              rel = rel_next;
+              for (int tp = 0; tp < ntaps; ++tp) {   // (not unrolled: the kernel must stay inside the instruction cache)
+                const uint32_t at = aj + (uint32_t)bd.rel[tp];
+                const uint64_t da = desc_hi64 | (uint64_t)at, db = desc_hi64 | (uint64_t)wj;
+                mma_bf16_ss_pred(tb, da, db, idesc, acc, leader);
+                if (mt_n > 1) mma_bf16_ss_pred(tb + (uint32_t)p.Cout, da + 128u, db, idesc, acc, leader);
+                acc = 1u;
+                wj += tap_w;
+              }
             }
+            mma_commit_pred(&empty_bar[stage], leader);  // frees the stage once the MMAs that read it have completed
+            if (++stage == p.stages) { stage = 0; ph ^= 1u; }
           }
-          mma_commit(&empty_bar[stage]);  // frees the stage once the MMAs that read it have completed
         }
-        acc = 1u;
-        __syncwarp();
-        if (++stage == p.stages) { stage = 0; ph ^= 1u; }
       }
-      if (elect_one()) mma_commit(&tfull_bar[buf]);   // accumulator of this tile complete -> epilogue
-      __syncwarp();
+      mma_commit_pred(&tfull_bar[buf], leader);   // accumulator of this tile complete -> epilogue
       if (dbg && warp == UC_MMA_WARP0 && lane == 0 && lt == 0) p.dbg[3] = clock64();   // all MMAs of the first tile issued
     }
   } else {
@@ -412,6 +359,42 @@ done:
   if (dbg && tid == 0) { p.dbg[6] = clock64(); p.dbg[7] = num_tiles; }
 }
 
+void umma_conv_build_program(const UmmaConvP& p, UcStageDesc* out) {
+  const int S = p.MT * 128;
+  int s = 0;
+  for (int gi = 0; gi < p.ngroups; ++gi) {
+    const UcGroup& g = p.groups[gi];
+    for (int c0 = 0; c0 < g.k16; c0 += p.kpack) {
+      const int nc = std::min(p.kpack, g.k16 - c0);
+      for (int b = g.band_begin; b < g.band_end; ++b, ++s) {
+        const UcBand& bd = p.bands[b];
+        UcStageDesc d;
+        const uint32_t bytesW = (uint32_t)bd.ntaps * (uint32_t)p.Cout * 32u;
+        d.bytesA = bd.toeplitz ? (uint32_t)(S + bd.len_extra + 1 + 2 * (nc - 1)) * 16u : (uint32_t)(S + bd.len_extra) * 16u;
+        uint32_t n_a = bd.toeplitz ? 1u : 2u * (uint32_t)nc;   // Toeplitz: the K chunks are 32-byte shifts of one row region
+        // single-band groups (Linear layers): the weights of consecutive K chunks are contiguous -> one copy
+        const bool w_merged = (g.band_end - g.band_begin) == 1;
+        uint32_t n_w = w_merged ? 1u : (uint32_t)nc;
+        d.w_copy_bytes = w_merged ? (uint32_t)nc * bytesW : bytesW;
+        d.w_dst_step = bytesW;
+        // (p.skip: timing experiments only — bit 0 drops the A copies, bit 1 the W copies; results are then garbage)
+        if (p.skip & 1) n_a = 0;
+        if (p.skip & 2) n_w = 0;
+        d.tx_bytes = n_a * d.bytesA + (n_w ? (uint32_t)nc * bytesW : 0u);
+        d.a_src = reinterpret_cast<uint64_t>(bd.base + (int64_t)c0 * bd.chunk_stride + (int64_t)bd.start * 8);
+        d.chunk_stride_b = (uint64_t)bd.chunk_stride * 2u;
+        d.plane_stride_b = (uint64_t)bd.plane_stride * 2u;
+        // weight piece j of the stage is the packed block [chunk c0 + j][taps of this band]: pieces are taps_total * Cout * 32 B apart
+        d.w_src = reinterpret_cast<uint64_t>(p.w + g.w_off + ((int64_t)c0 * g.taps_total + bd.tap_begin) * (int64_t)p.Cout * 16);
+        d.w_slice_stride_b = (uint64_t)g.slice_stride * 2u;
+        d.w_src_step = (uint32_t)g.taps_total * (uint32_t)p.Cout * 32u;
+        d.counts = n_a | (n_w << 8) | ((uint32_t)b << 16) | ((uint32_t)nc << 24);
+        out[s] = d;
+      }
+    }
+  }
+}
+
 size_t umma_conv_smem_bytes(const UmmaConvP& p) {
   return (size_t)p.stages * (p.a_stage_bytes + p.w_stage_bytes) + (size_t)p.nst_tile * sizeof(UcStageDesc) + 1024;
 }
@@ -425,7 +408,7 @@ void launch_umma_conv(const UmmaConvP& p, int n_slices, cudaStream_t s, int max_
     cudaFuncSetAttribute(umma_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024);
     attr_set = true;
   }
-  if (2 * p.kpack + p.kpack > UC_PROD_WARPS * UC_PROD_LANES) { fprintf(stderr, "umma_conv: kpack %d exceeds the issuer count\n", p.kpack); abort(); }
+  if (2 * p.kpack + p.kpack > 32) { fprintf(stderr, "umma_conv: kpack %d exceeds the issuer count\n", p.kpack); abort(); }
   const int S = p.MT * 128;
   const int tiles = (int)((p.g.P_total + S - 1) / S);
   static int num_sms = 0;

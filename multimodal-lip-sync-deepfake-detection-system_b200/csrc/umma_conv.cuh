@@ -50,6 +50,27 @@ struct UcGeom {
   int64_t P_total;
 };
 
+// One ring stage of a tile, as the producers and MMA issuers consume it ("stage program").  The sequence of stages
+// (group, K-chunk block, band) is identical for every tile — only the tile's first position shifts the A sources — so the host
+// expands it once per (layer, shapes, workspace), keeps it in device memory (lsd_handle::prog_*) and every CTA copies it into
+// shared memory in its prologue.  Computing the same operands in the kernel from the parameter block cost ~150 dependent
+// instructions (indexed constant loads, 64-bit multiplies) = ~1200 cycles per stage for the single issuing warp, more than the
+// MMA time of a stage for every layer with few taps per stage (token GEMMs, audio encoder, 256-column tiles).
+struct alignas(16) UcStageDesc {
+  uint64_t a_src;            // global byte address of the stage's first A piece for tile position 0
+  uint64_t w_src;            // global byte address of the stage's first weight piece, Cout slice 0
+  uint64_t chunk_stride_b;   // bytes between consecutive K-chunk pairs of planes
+  uint64_t plane_stride_b;   // bytes between the two 8-channel planes of a K chunk
+  uint64_t w_slice_stride_b; // bytes between consecutive Cout slices of the packed weights
+  uint32_t bytesA;           // bytes of one A piece
+  uint32_t w_copy_bytes;     // bytes of one weight copy
+  uint32_t w_dst_step;       // shared-memory distance between weight pieces
+  uint32_t w_src_step;       // global distance between the weight pieces of consecutive K chunks
+  uint32_t tx_bytes;         // bytes the stage's full barrier expects
+  uint32_t counts;           // n_a | n_w << 8 | band index << 16 | K chunks in this stage << 24
+};
+static_assert(sizeof(UcStageDesc) == 64, "UcStageDesc must be 64 bytes");
+
 struct UmmaConvP {
   const __nv_bfloat16* w;     // packed: [group][Cout slice][k16 chunk][tap][2 k-chunks][Cout][8]
   const float* bias;          // all slices (BN shift + folded conv bias; BN scale is folded into w)
@@ -71,6 +92,7 @@ struct UmmaConvP {
   int MT, stages, ngroups, nbands;
   int nbuf;                   // TMEM accumulator buffers: 2 = epilogue overlaps the next tile, 1 = all 512 columns for one tile
   long long* dbg;             // optional: CTA (0,0) writes clock64 phase timestamps (debug builds of the bench only)
+  const UcStageDesc* prog;    // device memory: the stage program (nst_tile entries)
   int nst_tile;               // ring stages per tile (sum over groups of ceil(k16 / kpack) * bands): length of the stage program
   int skip;                   // debug (LSD_UMMA_SKIP): bit 0 = no A copies, bit 1 = no W copies — timing experiments only
   int kpack;                  // k16 chunks per pipeline stage (small-K-step layers amortise the mbarrier round trip)
@@ -83,6 +105,8 @@ struct UmmaConvP {
 
 size_t umma_conv_smem_bytes(const UmmaConvP& p);
 int umma_conv_stage_desc_bytes();
+// host: expand the stage program of a launch (same arithmetic the kernel used to do per stage)
+void umma_conv_build_program(const UmmaConvP& p, UcStageDesc* out);
 void launch_umma_conv(const UmmaConvP& p, int n_slices, cudaStream_t s, int max_ctas = 0);
 
 // ---- planar-layout glue --------------------------------------------------------------------------
