@@ -30,7 +30,9 @@ def _handle(dev: torch.device) -> _cabi.Handle:
 
 def logmel_db(pcm: Union[torch.Tensor, Sequence[torch.Tensor]]):
     """fp32 mono 16 kHz PCM on a CUDA device -> log-mel dB `(80, 1 + n//160)` in [-80, 0], `ref=max` per clip.
-    A list of clips is processed in one call (clips concatenated; one maximum per clip)."""
+    A list of clips (or a 2-D `(B, n)` tensor of equal-length clips) is processed in one call; one maximum per clip."""
+    if isinstance(pcm, torch.Tensor) and pcm.dim() == 2:
+        return _logmel_db_equal(pcm)
     single = isinstance(pcm, torch.Tensor)
     clips = [pcm] if single else list(pcm)
     if not clips:
@@ -62,6 +64,31 @@ def logmel_db(pcm: Union[torch.Tensor, Sequence[torch.Tensor]]):
         _cabi.check(h.ptr, rc)
     mels = [out[moffs[i]:moffs[i + 1]].view(N_MELS, frames[i]) for i in range(len(clips))]
     return mels[0] if single else mels
+
+
+def _logmel_db_equal(pcm: torch.Tensor) -> torch.Tensor:
+    """`(B, n)` equal-length clips -> `(B, 80, 1 + n//160)`; one launch pair for the whole batch, no per-clip host work
+    beyond the offset table."""
+    if pcm.device.type != "cuda":
+        raise RuntimeError("logmel_db needs PCM on an sm_100 CUDA device; there is no CPU fallback")
+    B, n = int(pcm.shape[0]), int(pcm.shape[1])
+    if n == 0:
+        raise ValueError("Empty audio signal")
+    L = _cabi.lib()
+    fr = L.lsd_logmel_frames(n)
+    out = torch.empty(B, N_MELS, fr, dtype=torch.float32, device=pcm.device)
+    if B == 0:
+        return out
+    flat = pcm.to(torch.float32).contiguous()
+    scratch = torch.empty(B, dtype=torch.float32, device=pcm.device)
+    co = (C.c_int64 * (B + 1))(*range(0, (B + 1) * n, n))
+    mo = (C.c_int64 * (B + 1))(*range(0, (B + 1) * N_MELS * fr, N_MELS * fr))
+    h = _handle(pcm.device)
+    with h.lock:
+        rc = L.lsd_logmel(h.ptr, flat.data_ptr(), co, B, out.data_ptr(), mo, scratch.data_ptr(),
+                          torch.cuda.current_stream(pcm.device).cuda_stream)
+        _cabi.check(h.ptr, rc)
+    return out
 
 
 def fit_frames(mel_db: np.ndarray, target_frames: Optional[int]) -> np.ndarray:

@@ -51,7 +51,7 @@ int init_logmel_tables(lsd_handle* h) {
     lo[i] = first; cnt[i] = last - first + 1;
     for (int k = first; k <= last; ++k) melw[(size_t)i * MELW_MAX + (k - first)] = row[k];
   }
-  const size_t nf = 3 * NFFT + (size_t)NMEL * MELW_MAX;
+  const size_t nf = 3 * NFFT + (size_t)NMEL * MELW_MAX + 2 * NFFT;   // ... + interleaved (cos, -sin) twiddles of the FFT kernel
   const size_t bytes = nf * sizeof(float) + 2 * NMEL * sizeof(int);
   cudaError_t e = cudaSetDevice(h->device);
   if (e == cudaSuccess) e = cudaMalloc(&h->mel_tables, bytes);
@@ -60,13 +60,16 @@ int init_logmel_tables(lsd_handle* h) {
   float* f = reinterpret_cast<float*>(host.data());
   memcpy(f, hann.data(), NFFT * 4); memcpy(f + NFFT, tc.data(), NFFT * 4); memcpy(f + 2 * NFFT, ts.data(), NFFT * 4);
   memcpy(f + 3 * NFFT, melw.data(), melw.size() * 4);
+  for (int n = 0; n < NFFT; ++n) { f[3 * NFFT + melw.size() + 2 * n] = tc[n]; f[3 * NFFT + melw.size() + 2 * n + 1] = ts[n]; }
   int* ip = reinterpret_cast<int*>(f + nf);
   memcpy(ip, lo.data(), NMEL * 4); memcpy(ip + NMEL, cnt.data(), NMEL * 4);
   e = cudaMemcpy(h->mel_tables, host.data(), bytes, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) return lsd_fail(h, LSD_ERR_CUDA, "log-mel tables copy: %s", cudaGetErrorString(e));
   const float* d = reinterpret_cast<const float*>(h->mel_tables);
   h->d_hann = d; h->d_cos = d + NFFT; h->d_sin = d + 2 * NFFT; h->d_melw = d + 3 * NFFT;
+  h->d_w400 = d + 3 * NFFT + (size_t)NMEL * MELW_MAX;
   h->d_mel_lo = reinterpret_cast<const int*>(d + nf); h->d_mel_cnt = h->d_mel_lo + NMEL;
+  lsd::init_logmel_fft_constants();
   return 0;
 }
 
@@ -81,15 +84,32 @@ extern "C" int lsd_logmel(lsd_handle* h, const float* pcm, const int64_t* clip_o
   cudaError_t e = cudaSetDevice(h->device);
   if (e == cudaSuccess) e = cudaMemsetAsync(scratch, 0, sizeof(float) * n_clips, st);
   if (e != cudaSuccess) return lsd_fail(h, LSD_ERR_CUDA, "lsd_logmel: %s", cudaGetErrorString(e));
+  if (n_clips > 65535) return lsd_fail(h, LSD_ERR_SHAPE, "lsd_logmel: at most 65535 clips per call");
+  // clip table (device): built on the host, uploaded on the stream; the device buffer is owned by the handle and grows on demand
+  const int fb = lsd::logmel_frames_per_block();
+  h->lm_clips_host.resize((size_t)n_clips * sizeof(lsd::LmClip));
+  lsd::LmClip* tab = reinterpret_cast<lsd::LmClip*>(h->lm_clips_host.data());
+  long long blocks = 0;
+  int max_frames = 0;
   for (int c = 0; c < n_clips; ++c) {
     const int64_t n = clip_offsets_host[c + 1] - clip_offsets_host[c];
     if (n < 0) return lsd_fail(h, LSD_ERR_SHAPE, "lsd_logmel: clip %d has negative length", c);
     const int frames = lsd_logmel_frames(n);
-    float* out = mel_out + mel_offsets_host[c];
-    lsd::launch_logmel_power(pcm + clip_offsets_host[c], n, frames, h->d_hann, h->d_cos, h->d_sin, h->d_melw, h->d_mel_lo,
-                             h->d_mel_cnt, out, scratch + c, st);
-    lsd::launch_logmel_db(out, (int64_t)NMEL * frames, scratch + c, st);
+    tab[c].pcm_off = clip_offsets_host[c]; tab[c].n_samples = n; tab[c].mel_off = mel_offsets_host[c];
+    tab[c].frames = frames; tab[c].block0 = (int)blocks;
+    blocks += (frames + fb - 1) / fb;
+    if (frames > max_frames) max_frames = frames;
   }
+  if (blocks > 0x7fffffffLL) return lsd_fail(h, LSD_ERR_SHAPE, "lsd_logmel: too many frames in one call");
+  if (h->lm_clips_cap < h->lm_clips_host.size()) {
+    if (h->lm_clips) { cudaStreamSynchronize(st); cudaFree(h->lm_clips); h->lm_clips = nullptr; }
+    h->lm_clips_cap = h->lm_clips_host.size() * 2;
+    if (cudaMalloc(&h->lm_clips, h->lm_clips_cap) != cudaSuccess) { h->lm_clips_cap = 0; return lsd_fail(h, LSD_ERR_CUDA, "lsd_logmel: clip table allocation failed"); }
+  }
+  e = cudaMemcpyAsync(h->lm_clips, tab, h->lm_clips_host.size(), cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return lsd_fail(h, LSD_ERR_CUDA, "lsd_logmel: %s", cudaGetErrorString(e));
+  lsd::launch_logmel_fft(pcm, reinterpret_cast<const lsd::LmClip*>(h->lm_clips), n_clips, (int)blocks, max_frames, h->d_hann,
+                         reinterpret_cast<const float2*>(h->d_w400), h->d_melw, h->d_mel_lo, h->d_mel_cnt, mel_out, scratch, st);
   e = cudaGetLastError();
   if (e != cudaSuccess) return lsd_fail(h, LSD_ERR_CUDA, "lsd_logmel: %s", cudaGetErrorString(e));
   return LSD_OK;

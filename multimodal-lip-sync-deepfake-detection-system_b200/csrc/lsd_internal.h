@@ -75,6 +75,10 @@ struct lsd_handle {
   void* mel_tables = nullptr;
   const float *d_hann = nullptr, *d_cos = nullptr, *d_sin = nullptr, *d_melw = nullptr;
   const int *d_mel_lo = nullptr, *d_mel_cnt = nullptr;
+  const void* d_w400 = nullptr;            // float2[400]: exp(-2*pi*i*m/400)
+  void* lm_clips = nullptr;                // device clip table of the batched log-mel kernel (grows on demand)
+  size_t lm_clips_cap = 0;
+  std::vector<char> lm_clips_host;
 };
 
 int lsd_fail(lsd_handle* h, int code, const char* fmt, ...);

@@ -67,6 +67,15 @@ void launch_logmel_power(const float* pcm, int64_t n_samples, int frames, const 
                          const float* twid_sin, const float* melw, const int* mel_lo, const int* mel_cnt,
                          float* mel_power, float* clip_max, cudaStream_t s);
 void launch_logmel_db(float* mel, int64_t n, const float* clip_max, cudaStream_t s);
+// batched FFT version (product path): clip table in device memory, one launch for all clips + one dB pass
+struct LmClip { long long pcm_off, n_samples, mel_off; int frames, block0; };
+size_t logmel_fft_smem_bytes();
+int logmel_frames_per_block();
+void init_logmel_fft_constants();
+void launch_logmel_fft(const float* pcm, const LmClip* clips, int n_clips, int total_blocks, int max_frames, const float* hann,
+                       const float2* w400, const float* melw, const int* mel_lo, const int* mel_cnt, float* mel_out, float* clip_max,
+                       cudaStream_t s);
+
 
 int64_t kernel_launches();   // process-wide count of kernels launched by this library
 void count_launch(int n = 1);

@@ -242,57 +242,72 @@ void launch_audio_rows(const void* audio, int dtype, __nv_bfloat16* y, int64_t s
 
 // ---- fused head: artifact fusion MLP (448->256 ReLU ->128 ReLU), cat[cls|artifact], Linear 384->128, GELU, LayerNorm(128),
 // Linear 128->1.  One block (256 threads) per window, everything in fp32, weights [Cin][Cout] from the fp32 arena.
-__global__ void __launch_bounds__(256) head_kernel(const float* comb, HeadW w, float* logits) {
-  __shared__ float x[448], h1[256], f[384], h2[128], red[8];
+// 512 threads: every layer splits its K range over 2 (448 -> 256) or 4 (256 -> 128, 384 -> 128) thread groups and keeps 16
+// independent weight loads in flight per thread — the kernel is L2-latency-bound (0.9 MB of fp32 weights per window, one
+// window per SM); partial sums are combined in a fixed order.
+__global__ void __launch_bounds__(512) head_kernel(const float* __restrict__ comb, HeadW w, float* __restrict__ logits) {
+  __shared__ float x[448], h1[256], f[384], part[512], red[4];
   const int n = blockIdx.x, tid = threadIdx.x;
-  for (int i = tid; i < 448; i += 256) x[i] = comb[(int64_t)n * 448 + i];
+  for (int i = tid; i < 448; i += 512) x[i] = comb[(int64_t)n * 448 + i];
   __syncthreads();
   {
-    float acc = w.b0[tid];
-#pragma unroll 16   // 16 independent weight loads in flight per thread (the loop is L2-latency-bound otherwise); same summation order
-    for (int k = 0; k < 448; ++k) acc = fmaf(x[k], w.w0[k * 256 + tid], acc);
-    h1[tid] = fmaxf(acc, 0.f);
-  }
-  f[tid] = x[tid];  // cls
-  __syncthreads();
-  if (tid < 128) {
-    float acc = w.b2[tid];
+    const int o = tid & 255, half = tid >> 8;                 // K split: [0,224) and [224,448)
+    const float* wp = w.w0 + (size_t)half * 224 * 256 + o;
+    const float* xp = x + half * 224;
+    float acc = 0.f;
 #pragma unroll 16
-    for (int k = 0; k < 256; ++k) acc = fmaf(h1[k], w.w2[k * 128 + tid], acc);
-    f[256 + tid] = fmaxf(acc, 0.f);
+    for (int k = 0; k < 224; ++k) acc = fmaf(xp[k], wp[(size_t)k * 256], acc);
+    part[tid] = acc;
+  }
+  __syncthreads();
+  if (tid < 256) { h1[tid] = fmaxf(w.b0[tid] + part[tid] + part[tid + 256], 0.f); f[tid] = x[tid]; }   // f[0:256] = cls
+  __syncthreads();
+  {
+    const int o = tid & 127, q = tid >> 7;                    // K split: 4 x 64
+    const float* wp = w.w2 + (size_t)q * 64 * 128 + o;
+    const float* xp = h1 + q * 64;
+    float acc = 0.f;
+#pragma unroll 16
+    for (int k = 0; k < 64; ++k) acc = fmaf(xp[k], wp[(size_t)k * 128], acc);
+    part[tid] = acc;
+  }
+  __syncthreads();
+  if (tid < 128) f[256 + tid] = fmaxf(w.b2[tid] + ((part[tid] + part[tid + 128]) + (part[tid + 256] + part[tid + 384])), 0.f);
+  __syncthreads();
+  {
+    const int o = tid & 127, q = tid >> 7;                    // K split: 4 x 96
+    const float* wp = w.wc + (size_t)q * 96 * 128 + o;
+    const float* xp = f + q * 96;
+    float acc = 0.f;
+#pragma unroll 16
+    for (int k = 0; k < 96; ++k) acc = fmaf(xp[k], wp[(size_t)k * 128], acc);
+    part[tid] = acc;
   }
   __syncthreads();
   float hv = 0.f;
-  if (tid < 128) {
-    float acc = w.bc[tid];
-#pragma unroll 16
-    for (int k = 0; k < 384; ++k) acc = fmaf(f[k], w.wc[k * 128 + tid], acc);
-    hv = tk_gelu(acc);
-    h2[tid] = hv;
-  }
-  __syncthreads();
-  // LayerNorm(128) + dot, fixed-order reductions
+  if (tid < 128) hv = tk_gelu(w.bc[tid] + ((part[tid] + part[tid + 128]) + (part[tid + 256] + part[tid + 384])));
+  // LayerNorm(128) + dot, fixed-order reductions over the first four warps
   float s = (tid < 128) ? hv : 0.f;
   s = tk_warp_sum(s);
-  if ((tid & 31) == 0) red[tid >> 5] = s;
+  if (tid < 128 && (tid & 31) == 0) red[tid >> 5] = s;
   __syncthreads();
   const float mu = (red[0] + red[1] + red[2] + red[3]) / 128.0f;
   __syncthreads();
   float d = (tid < 128) ? (hv - mu) * (hv - mu) : 0.f;
   d = tk_warp_sum(d);
-  if ((tid & 31) == 0) red[tid >> 5] = d;
+  if (tid < 128 && (tid & 31) == 0) red[tid >> 5] = d;
   __syncthreads();
   const float rstd = 1.0f / sqrtf((red[0] + red[1] + red[2] + red[3]) / 128.0f + 1e-5f);
   __syncthreads();
   float o = (tid < 128) ? ((hv - mu) * rstd * w.lng[tid] + w.lnb[tid]) * w.wo[tid] : 0.f;
   o = tk_warp_sum(o);
-  if ((tid & 31) == 0) red[tid >> 5] = o;
+  if (tid < 128 && (tid & 31) == 0) red[tid >> 5] = o;
   __syncthreads();
   if (tid == 0) logits[n] = red[0] + red[1] + red[2] + red[3] + w.bo[0];
 }
 void launch_head(const float* comb, const HeadW& w, float* logits, int B, cudaStream_t s) {
   if (B == 0) return;
-  head_kernel<<<B, 256, 0, s>>>(comb, w, logits);
+  head_kernel<<<B, 512, 0, s>>>(comb, w, logits);
   count_launch();
 }
 

@@ -624,11 +624,60 @@ __global__ void __launch_bounds__(256) planar_maxpool_kernel(const __nv_bfloat16
     }
   }
 }
+// Same mapping, plain bf16 tensors (no hi/lo split): the maximum is taken on packed bf16 pairs (HMNMX2) — the maximum of bf16
+// values is exact in bf16, so no unpack / repack and half the shuffles; the float version above was instruction-issue-bound.
+__global__ void __launch_bounds__(256) planar_maxpool_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t xs, UcGeom gi,
+                                                                  __nv_bfloat16* __restrict__ y, int64_t ys, UcGeom go) {
+  const int frame = blockIdx.x, chunk = blockIdx.y;
+  const int n = frame / go.T, t = frame - n * go.T;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const uint4* xc = reinterpret_cast<const uint4*>(x + (int64_t)chunk * xs + uc_flat(gi, n, t, 0, 0) * 8);
+  uint4* yc = reinterpret_cast<uint4*>(y + (int64_t)chunk * ys + uc_flat(go, n, t, 0, 0) * 8);
+  const uint32_t NINF2 = 0xFF80FF80u;                                   // (-inf, -inf) in bf16
+  auto mx4 = [](uint4 a, uint4 b) {
+    uint4 r;
+    __nv_bfloat162 t0 = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a.x), *reinterpret_cast<__nv_bfloat162*>(&b.x));
+    __nv_bfloat162 t1 = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a.y), *reinterpret_cast<__nv_bfloat162*>(&b.y));
+    __nv_bfloat162 t2 = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a.z), *reinterpret_cast<__nv_bfloat162*>(&b.z));
+    __nv_bfloat162 t3 = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a.w), *reinterpret_cast<__nv_bfloat162*>(&b.w));
+    r.x = *reinterpret_cast<uint32_t*>(&t0); r.y = *reinterpret_cast<uint32_t*>(&t1);
+    r.z = *reinterpret_cast<uint32_t*>(&t2); r.w = *reinterpret_cast<uint32_t*>(&t3);
+    return r;
+  };
+  const int nseg = (gi.W + 31) >> 5;
+  const int npairs = go.H * nseg;
+  for (int pair = warp; pair < npairs; pair += nwarps) {
+    const int h = pair / nseg, seg = pair - h * nseg;
+    const int c = seg * 32 + lane;                         // this lane's input column
+    uint4 mv = make_uint4(NINF2, NINF2, NINF2, NINF2), ml = mv;
+    const bool extra_left = lane == 0 && seg > 0;
+#pragma unroll
+    for (int dh = 0; dh < 3; ++dh) {
+      const int hi = 2 * h - 1 + dh;
+      if ((unsigned)hi >= (unsigned)gi.H) continue;
+      if (c < gi.W) mv = mx4(mv, xc[hi * gi.RW + c]);
+      if (extra_left) ml = mx4(ml, xc[hi * gi.RW + c - 1]);
+    }
+    const int sa = (2 * lane) & 31, sb = (2 * lane + 1) & 31, sc = (2 * lane - 1) & 31;
+    uint4 a, b, cl;
+    a.x = __shfl_sync(0xffffffffu, mv.x, sa); a.y = __shfl_sync(0xffffffffu, mv.y, sa);
+    a.z = __shfl_sync(0xffffffffu, mv.z, sa); a.w = __shfl_sync(0xffffffffu, mv.w, sa);
+    b.x = __shfl_sync(0xffffffffu, mv.x, sb); b.y = __shfl_sync(0xffffffffu, mv.y, sb);
+    b.z = __shfl_sync(0xffffffffu, mv.z, sb); b.w = __shfl_sync(0xffffffffu, mv.w, sb);
+    cl.x = __shfl_sync(0xffffffffu, mv.x, sc); cl.y = __shfl_sync(0xffffffffu, mv.y, sc);
+    cl.z = __shfl_sync(0xffffffffu, mv.z, sc); cl.w = __shfl_sync(0xffffffffu, mv.w, sc);
+    if (lane == 0) cl = ml;                                // (seg == 0: ml stays -inf = the reference's padding)
+    const int w = seg * 16 + lane;
+    if (lane < 16 && w < go.W) yc[h * go.RW + w] = mx4(mx4(a, b), cl);
+  }
+}
+
 void launch_planar_maxpool(const __nv_bfloat16* x, int64_t x_plane_stride, UcGeom gi, __nv_bfloat16* y, int64_t y_plane_stride, UcGeom go,
                            int C, cudaStream_t s, const __nv_bfloat16* xlo, __nv_bfloat16* ylo) {
   const int frames = go.N * go.T;
   if (frames == 0 || go.H * go.W == 0) return;
-  planar_maxpool_kernel<<<dim3((unsigned)frames, (unsigned)(C / 8)), 256, 0, s>>>(x, x_plane_stride, gi, y, y_plane_stride, go, xlo, ylo);
+  if (!xlo && !ylo) planar_maxpool_bf16_kernel<<<dim3((unsigned)frames, (unsigned)(C / 8)), 256, 0, s>>>(x, x_plane_stride, gi, y, y_plane_stride, go);
+  else planar_maxpool_kernel<<<dim3((unsigned)frames, (unsigned)(C / 8)), 256, 0, s>>>(x, x_plane_stride, gi, y, y_plane_stride, go, xlo, ylo);
   count_launch();
 }
 

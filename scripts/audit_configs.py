@@ -61,12 +61,12 @@ def config3(args):
     m = make_model(dev)
     g = torch.Generator().manual_seed(3)
     pcm_all = (0.1 * torch.randn(512, 20480, generator=g)).to(dev)
-    for B in [1, 2, 4, 8, 16, 32, 64, 128, 256, 512]:
-        clips = [pcm_all[i] for i in range(B)]
+    for B in args.batches:
+        clips = pcm_all[:B]
         iters = 20 if B <= 64 else 5
         ms_mel = timed(lambda: lb.logmel_db(clips), iters)
-        mels = lb.logmel_db(clips)
-        audio = torch.stack([x[:, :128] for x in mels]).unsqueeze(1).contiguous()      # (B,1,80,128): target_frames=128
+        mels = lb.logmel_db(clips)                                                     # (B,80,129)
+        audio = mels[:, :, :128].unsqueeze(1).contiguous()                             # (B,1,80,128): target_frames=128
         ms_enc = timed(lambda: m.encode_audio(audio), iters)
         out = m.encode_audio(audio)
         assert out.shape == (B, 256, 16) and bool(torch.isfinite(out).all())
@@ -184,6 +184,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", required=True)
     ap.add_argument("--windows", type=int, default=10000)
+    ap.add_argument("--batches", type=lambda v: [int(x) for x in v.split(",")], default=[1, 2, 4, 8, 16, 32, 64, 128, 256, 512])
     a = ap.parse_args()
     import __graft_entry__ as ge
     if int(os.environ.get("RANK", "0")) == 0:

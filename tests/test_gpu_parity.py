@@ -243,6 +243,20 @@ def test_logmel_batched_clips_have_their_own_reference(built):
         assert np.abs(o.cpu().numpy() - ref).max() <= 2e-3
 
 
+def test_logmel_equal_length_batch_matches_per_clip(built):
+    """2-D `(B, n)` fast path == per-clip results, including clips whose PCM offset is not 16-byte aligned (n odd)."""
+    g = torch.Generator().manual_seed(3)
+    for n in (20480, 4001):
+        pcm = (0.1 * torch.randn(5, n, generator=g)).cuda()
+        pcm[2] *= 0.01
+        batch = lb.logmel_db(pcm)
+        assert batch.shape == (5, 80, 1 + n // 160)
+        for i in range(5):
+            ref = lmo.preprocess_audio_pcm(pcm[i].cpu().numpy())[0]
+            assert np.abs(batch[i].cpu().numpy() - ref).max() <= 2e-3
+            assert torch.equal(batch[i], lb.logmel_db(pcm[i].clone()))
+
+
 def test_launch_counter_counts(model):
     model.compute_precision = "fp32"
     video, audio = lb.synthetic_windows(1, 1)
