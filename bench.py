@@ -221,10 +221,47 @@ def main():
             ms = float(t.item())
         return ms, launches, prof, sampler.result()
 
+    # uint8-track variant of the end-to-end path: per step the host hands over the uint8 mouth-crop span of
+    # the step's 64 windows (stride 8: 536 frames, 14.8 MB instead of 226 MB of fp32 windows) from pinned memory, the windows
+    # are built on the device (lsd_score_windows), and the logits come back to the host.
+    n_tf = 8 * (B - 1) + 32
+    gt = torch.Generator().manual_seed(200 + rank)
+    track_h = torch.randint(0, 256, (n_tf, 96, 96, 3), dtype=torch.uint8, generator=gt).pin_memory()
+    mel_h = (-80.0 * torch.rand(1, 80, int(n_tf / 15 * 100), generator=gt)).pin_memory()
+    starts = [8 * i for i in range(B)]
+    track_slots = [torch.empty_like(track_h, device=dev) for _ in range(2)]
+    mel_slots = [torch.empty_like(mel_h, device=dev) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(dev)
+
+    def run_e2e_track(steps):
+        comp = torch.cuda.current_stream(dev)
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        free = [torch.cuda.Event(), torch.cuda.Event()]
+        for e in free:
+            e.record(comp)
+        host_out = []
+        for k in range(steps):
+            sl = k & 1
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(free[sl])
+                track_slots[sl].copy_(track_h, non_blocking=True)
+                mel_slots[sl].copy_(mel_h, non_blocking=True)
+                ready[sl].record(copy_stream)
+            comp.wait_event(ready[sl])
+            lg = pred.score_track_logits(track_slots[sl], starts, mel_slots[sl], n_tf)
+            free[sl].record(comp)
+            ho = torch.empty(B, dtype=torch.float32, pin_memory=True)
+            ho.copy_(lg, non_blocking=True)
+            host_out.append(ho)
+        comp.synchronize()
+        return host_out[-1]
+
     ms, launches, prof, clocks = timed(step_resident, K, profile=True)
     ms_e2e, _, _, _ = timed(run_e2e, K, whole=True)
+    ms_trk, _, _, _ = timed(run_e2e_track, K, whole=True)
     value = ws * B * K / (ms / 1e3)
     e2e = ws * B * K / (ms_e2e / 1e3)
+    e2e_trk = ws * B * K / (ms_trk / 1e3)
 
     if rank == 0:
         peaks, peak_src = _peaks()
@@ -249,6 +286,9 @@ def main():
             "e2e": {"value": e2e, "unit": "windows/s", "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": vh.numel() * 4 + ah.numel() * 4, "d2h_bytes_per_step": (ws if ws > 1 else 1) * B * 4,
                     "api": "Predictor.score_batches on pinned host fp32 windows (per step: H2D of the windows on a copy stream, forward, D2H of the logits)"},
+            "e2e_track_u8": {"value": e2e_trk, "unit": "windows/s", "ms_per_step": ms_trk / K,
+                             "h2d_bytes_per_step": track_h.numel() + mel_h.numel() * 4, "d2h_bytes_per_step": B * 4,
+                             "api": "Predictor.score_track_logits on a pinned host uint8 mouth-crop track (windows built on the device, lsd_score_windows)"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
                          "kernel": ("umma_conv_kernel, the 9 launches of the 3-D conv visual encoder (stem + layer1-4: 26.77 of the 31.29 "

@@ -132,6 +132,25 @@ int lsd_score_windows(lsd_handle* h, const uint8_t* track, int n_frames, int H, 
  * only its own span of a sharded track passes span-relative `starts` and the audio starts computed from the absolute frame
  * indices; NULL = computed here from `starts` as predictor.py:540-547 does. */
 
+/* ---- speaking alignment / mouth motion: the per-window numpy loops of _predict_long_video ------------------ */
+/* Frame-difference energies of a track (Predictor._speaking_alignment_score, app/inference/predictor.py:339-345, and
+ * _mouth_motion_energy_check, :395-402): for every frame pair f in [0, n_frames-1)
+ *   motion_full[f] = mean_{h,w} |gray[f+1]-gray[f]|,  motion_low[f] = the same over the lower half rows (h >= H/2),
+ * gray = channel mean of the crop scaled to [0,1].  video: device uint8 (n_frames,H,W,3) track (LSD_U8, LSD_NDHWC) or a
+ * device float32 (3,n_frames,H,W) window (LSD_F32, LSD_NCDHW: the reference's visual_np). */
+int lsd_track_motion(lsd_handle* h, const void* video, int dtype, int layout, int n_frames, int H, int W,
+                     float* motion_full, float* motion_low, void* stream);
+/* Per window (start frame starts_host[i], T frames; audio slice as in lsd_score_windows):
+ *   speaking_out[i]     = Predictor._speaking_alignment_score(window, mel slice)      predictor.py:333-370
+ *   mouth_motion_out[i] = mean lower-face motion, audio_energy_out[i] = mean mel dB     predictor.py:395-402
+ * (the likely_fake / uncertain / no_issue thresholds of :403-413 are applied by the host layer).
+ * idx_scratch: device, 2*n_windows int32.  T, Ta <= 128. */
+int lsd_speech_stats(lsd_handle* h, const float* motion_full, const float* motion_low, int n_frames,
+                     const int32_t* starts_host, const int32_t* audio_starts_host_or_null, int n_windows, int T,
+                     const float* mel_full, int F, int Ta_full, int total_v_frames, int Ta,
+                     float* speaking_out, float* mouth_motion_out, float* audio_energy_out,
+                     int32_t* idx_scratch, void* stream);
+
 /* ---- introspection (tests / profiling) ------------------------------------------------------- */
 /* Named intermediate of the last lsd_forward on this handle: byte offset into the workspace. */
 int lsd_stage_info(lsd_handle* h, const char* name, size_t* offset_bytes, int64_t* numel, int* dtype);

@@ -26,6 +26,7 @@ EXPORTS = [
     "lsd_score_windows", "lsd_stage_info", "lsd_stage_count", "lsd_stage_name", "lsd_launch_count",
     "lsd_profile_enable", "lsd_profile_get",
     "lsd_audio_encoder_workspace_bytes", "lsd_audio_encoder", "lsd_token_path_workspace_bytes", "lsd_token_path",
+    "lsd_track_motion", "lsd_speech_stats",
 ]
 
 
@@ -77,6 +78,9 @@ def lib() -> C.CDLL:
         L.lsd_audio_encoder.argtypes = [vp, vp, i, i, i, i, vp, vp, sz, vp]; L.lsd_audio_encoder.restype = i
         L.lsd_token_path_workspace_bytes.argtypes = [vp, i, i, i]; L.lsd_token_path_workspace_bytes.restype = sz
         L.lsd_token_path.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp, sz, vp]; L.lsd_token_path.restype = i
+        L.lsd_track_motion.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp]; L.lsd_track_motion.restype = i
+        L.lsd_speech_stats.argtypes = [vp, vp, vp, i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), i, i, vp, i, i, i, i, vp, vp, vp, vp, vp]
+        L.lsd_speech_stats.restype = i
         _lib = L
         return L
 

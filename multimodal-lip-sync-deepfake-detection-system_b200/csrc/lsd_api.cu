@@ -457,6 +457,54 @@ extern "C" int lsd_token_path(lsd_handle* h, const float* v_emb, const float* a_
 }
 
 // ================================================================================================
+// Speaking alignment / mouth motion statistics (host numpy loops of predictor.py:333-419, per window)
+// ================================================================================================
+extern "C" int lsd_track_motion(lsd_handle* h, const void* video, int dtype, int layout, int n_frames, int H, int W,
+                                float* motion_full, float* motion_low, void* stream) {
+  if (!h) return LSD_ERR_ARG;
+  if (n_frames < 1 || H < 2 || W < 1) return lsd_fail(h, LSD_ERR_SHAPE, "lsd_track_motion: bad extents n_frames=%d H=%d W=%d", n_frames, H, W);
+  if (n_frames < 2) return LSD_OK;
+  if (!video || !motion_full || !motion_low) return lsd_fail(h, LSD_ERR_ARG, "lsd_track_motion: null pointer argument");
+  if (!((dtype == LSD_U8 && layout == LSD_NDHWC) || (dtype == LSD_F32 && layout == LSD_NCDHW)))
+    return lsd_fail(h, LSD_ERR_ARG, "lsd_track_motion: supported inputs are a uint8 (n,H,W,3) track or a float32 (3,T,H,W) window");
+  CUDA_OK(h, cudaSetDevice(h->device));
+  lsd::launch_track_motion(video, layout == LSD_NDHWC ? 1 : 0, n_frames, H, W, motion_full, motion_low, reinterpret_cast<cudaStream_t>(stream));
+  CUDA_OK(h, cudaGetLastError());
+  return LSD_OK;
+}
+
+extern "C" int lsd_speech_stats(lsd_handle* h, const float* motion_full, const float* motion_low, int n_frames, const int32_t* starts_host,
+                                const int32_t* audio_starts_host, int n_windows, int T, const float* mel_full, int F, int Ta_full,
+                                int total_v_frames, int Ta, float* speaking_out, float* mouth_motion_out, float* audio_energy_out,
+                                int32_t* idx_scratch, void* stream) {
+  if (!h) return LSD_ERR_ARG;
+  if (n_windows == 0) return LSD_OK;
+  if (!motion_full || !motion_low || !starts_host || !mel_full || !speaking_out || !mouth_motion_out || !audio_energy_out || !idx_scratch)
+    return lsd_fail(h, LSD_ERR_ARG, "lsd_speech_stats: null pointer argument");
+  if (n_windows < 0 || T < 1 || Ta < 1 || F < 1 || Ta_full < 1 || T > lsd::speech_stats_max() || Ta > lsd::speech_stats_max())
+    return lsd_fail(h, LSD_ERR_SHAPE, "lsd_speech_stats: bad extents (T and Ta must be in [1, %d])", lsd::speech_stats_max());
+  for (int i = 0; i < n_windows; ++i)
+    if (starts_host[i] < 0 || starts_host[i] + T > n_frames)
+      return lsd_fail(h, LSD_ERR_SHAPE, "window %d [%d,%d) is outside the %d-frame track", i, starts_host[i], starts_host[i] + T, n_frames);
+  CUDA_OK(h, cudaSetDevice(h->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  h->idx_host.resize((size_t)2 * n_windows);
+  const double a_ratio = (double)Ta_full / (double)(total_v_frames > 1 ? total_v_frames : 1);
+  for (int i = 0; i < n_windows; ++i) {
+    long a_start = audio_starts_host ? (long)audio_starts_host[i] : (long)nearbyint((double)starts_host[i] * a_ratio);   // predictor.py:540-547
+    if (a_start + Ta > Ta_full) { a_start = Ta_full - Ta; }
+    if (a_start < 0) a_start = 0;
+    h->idx_host[i] = starts_host[i];
+    h->idx_host[n_windows + i] = (int32_t)a_start;
+  }
+  CUDA_OK(h, cudaMemcpyAsync(idx_scratch, h->idx_host.data(), (size_t)2 * n_windows * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  lsd::launch_speech_stats(motion_full, motion_low, idx_scratch, idx_scratch + n_windows, n_windows, T, mel_full, F, Ta_full, Ta, speaking_out,
+                           mouth_motion_out, audio_energy_out, st);
+  CUDA_OK(h, cudaGetLastError());
+  return LSD_OK;
+}
+
+// ================================================================================================
 // Introspection
 // ================================================================================================
 extern "C" int lsd_profile_enable(lsd_handle* h, int on) {

@@ -80,4 +80,11 @@ void launch_logmel_fft(const float* pcm, const LmClip* clips, int n_clips, int t
 int64_t kernel_launches();   // process-wide count of kernels launched by this library
 void count_launch(int n = 1);
 
+// ---- speaking alignment / mouth motion (speech_stats.cu) ---------------------------------------------------
+void launch_track_motion(const void* video, int layout, int n_frames, int H, int W, float* motion_full, float* motion_low, cudaStream_t s);
+int speech_stats_max();
+void launch_speech_stats(const float* motion_full, const float* motion_low, const int32_t* v_starts, const int32_t* a_starts, int n_windows,
+                         int T, const float* mel, int F, int Ta_full, int Ta, float* score, float* mouth_motion, float* audio_energy,
+                         cudaStream_t s);
+
 }  // namespace lsd

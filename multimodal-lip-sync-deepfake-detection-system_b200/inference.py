@@ -300,6 +300,117 @@ class Predictor:
         confs = [self._calibrate(float(x)) for x in logits.cpu().tolist()]
         return self._robust_confidence(confs), confs
 
+    # ------------------------------------------------------------------ speaking alignment / mouth motion
+    def window_speech_stats(self, track_u8: torch.Tensor, starts: Sequence[int], mel_full: torch.Tensor, total_v_frames: int,
+                            chunk_a_size: int = 128, audio_starts_from: Optional[Sequence[int]] = None):
+        """Per-window `(speaking_alignment, mouth_motion_energy, audio_energy)` fp32 device tensors for the windows of a
+        uint8 track: the statistics `_predict_long_video` computes per window with `_speaking_alignment_score`
+        (predictor.py:333-370) and `_mouth_motion_energy_check` (:374-419).  Frame-difference energies are computed once
+        per frame pair of the track (`lsd_track_motion`), then combined per window (`lsd_speech_stats`)."""
+        m = self.model
+        dev = m._device()
+        if track_u8.dtype != torch.uint8 or track_u8.dim() != 4 or track_u8.shape[3] != 3:
+            raise ValueError(f"track must be uint8 (n_frames, H, W, 3), got {track_u8.dtype} {tuple(track_u8.shape)}")
+        if mel_full.dim() != 3 or mel_full.shape[0] != 1:
+            raise ValueError(f"mel_full must be (1, F, T_full), got {tuple(mel_full.shape)}")
+        n = len(starts)
+        out = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(3)]
+        if n == 0:
+            return tuple(out)
+        track_u8 = track_u8.contiguous()
+        mel_full = mel_full.to(torch.float32).contiguous()
+        n_frames, H, W = int(track_u8.shape[0]), int(track_u8.shape[1]), int(track_u8.shape[2])
+        F_, Ta_full = int(mel_full.shape[1]), int(mel_full.shape[2])
+        motion = torch.zeros(2, max(1, n_frames - 1), dtype=torch.float32, device=dev)
+        idx = torch.empty(2 * n, dtype=torch.int32, device=dev)
+        with m._lsd_lock:
+            h = m._ensure_handle(dev)
+            L = _cabi.lib()
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _cabi.check(h.ptr, L.lsd_track_motion(h.ptr, track_u8.data_ptr(), _cabi.LSD_U8, _cabi.LSD_NDHWC, n_frames, H, W,
+                                                  motion[0].data_ptr(), motion[1].data_ptr(), stream))
+            st = (C.c_int32 * n)(*[int(s) for s in starts])
+            ast = None
+            if audio_starts_from is not None:
+                ast = (C.c_int32 * n)(*[self._audio_start(int(v), Ta_full, int(total_v_frames), chunk_a_size) for v in audio_starts_from])
+            rc = L.lsd_speech_stats(h.ptr, motion[0].data_ptr(), motion[1].data_ptr(), n_frames, st, ast, n, self.chunk_size,
+                                    mel_full.data_ptr(), F_, Ta_full, int(total_v_frames), chunk_a_size, out[0].data_ptr(),
+                                    out[1].data_ptr(), out[2].data_ptr(), idx.data_ptr(), stream)
+            _cabi.check(h.ptr, rc)
+        return tuple(out)
+
+    def _speaking_alignment_score(self, visual_np: np.ndarray, audio_np: np.ndarray) -> float:
+        """Same contract as the reference static method (predictor.py:333-370): `(3,T,H,W)` float32 crop in [0,1] +
+        `(1,F,T_a)` log-mel -> score in [0,1]; computed on the device."""
+        m = self.model
+        dev = m._device()
+        v = torch.from_numpy(np.ascontiguousarray(visual_np, dtype=np.float32)).to(dev)
+        a = torch.from_numpy(np.ascontiguousarray(audio_np, dtype=np.float32)).to(dev)
+        T, H, W = int(v.shape[1]), int(v.shape[2]), int(v.shape[3])
+        Ta = int(a.shape[2])
+        if T < 2 or Ta < 2:
+            return 0.5
+        motion = torch.zeros(2, T - 1, dtype=torch.float32, device=dev)
+        out = torch.empty(3, dtype=torch.float32, device=dev)
+        idx = torch.empty(2, dtype=torch.int32, device=dev)
+        with m._lsd_lock:
+            h = m._ensure_handle(dev)
+            L = _cabi.lib()
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _cabi.check(h.ptr, L.lsd_track_motion(h.ptr, v.data_ptr(), _cabi.LSD_F32, _cabi.LSD_NCDHW, T, H, W,
+                                                  motion[0].data_ptr(), motion[1].data_ptr(), stream))
+            st = (C.c_int32 * 1)(0)
+            rc = L.lsd_speech_stats(h.ptr, motion[0].data_ptr(), motion[1].data_ptr(), T, st, st, 1, T, a.data_ptr(), int(a.shape[1]), Ta,
+                                    T, Ta, out[0:1].data_ptr(), out[1:2].data_ptr(), out[2:3].data_ptr(), idx.data_ptr(), stream)
+            _cabi.check(h.ptr, rc)
+        return float(out[0].item())
+
+    def mouth_motion_checks(self, mouth_motion: Sequence[float], audio_energy: Sequence[float], mouth_motion_low_threshold: float = 0.015,
+                            audio_energy_high_threshold: float = -25.0, audio_energy_low_threshold: float = -50.0) -> List[dict]:
+        """Decision logic of `_mouth_motion_energy_check` (predictor.py:403-419) on the per-window statistics."""
+        res = []
+        for motion, energy in zip(mouth_motion, audio_energy):
+            motion, energy = float(motion), float(energy)
+            if energy > audio_energy_high_threshold and motion < mouth_motion_low_threshold:
+                r = "likely_fake"
+            elif energy < audio_energy_low_threshold and motion < mouth_motion_low_threshold:
+                r = "uncertain"
+            else:
+                r = "no_issue"
+            res.append({"audio_energy": round(energy, 4), "mouth_motion_energy": round(motion, 6), "check_result": r})
+        return res
+
+    @staticmethod
+    def aggregate_mouth_motion_checks(checks: Sequence[dict], max_samples: int = 5) -> dict:
+        """`_aggregate_mouth_motion_check` (predictor.py:463-523): sample up to `max_samples` evenly spaced windows (always the
+        last one), majority vote with the conservative `uncertain` rule."""
+        n = len(checks)
+        if n == 0:
+            return {"check_result": "no_data", "audio_energy": 0.0, "mouth_motion_energy": 0.0, "samples_checked": 0}
+        if n <= max_samples:
+            indices = list(range(n))
+        else:
+            step = n / max_samples
+            indices = [int(i * step) for i in range(max_samples)]
+            if (n - 1) not in indices:
+                indices[-1] = n - 1
+        counts = {"likely_fake": 0, "uncertain": 0, "no_issue": 0}
+        energies, motions = [], []
+        for i in indices:
+            c = checks[i]
+            counts[c["check_result"]] = counts.get(c["check_result"], 0) + 1
+            energies.append(float(c["audio_energy"]))
+            motions.append(float(c["mouth_motion_energy"]))
+        k = len(indices)
+        if counts["uncertain"] > k // 2:
+            agg = "uncertain"
+        elif counts["likely_fake"] > counts["uncertain"] + counts["no_issue"]:
+            agg = "likely_fake"
+        else:
+            agg = "no_issue"
+        return {"check_result": agg, "audio_energy": round(float(np.median(energies)), 4),
+                "mouth_motion_energy": round(float(np.median(motions)), 6), "samples_checked": k, "counts": counts}
+
     # ------------------------------------------------------------------ decision (predictor.py:856-1155, :1235)
     def aggregate_long_video(self, window_confs, window_speaking, window_vad_weights=None, mouth_check_result: str = "no_data", **gates):
         """Final `real` / `fake` / `uncertain` decision from per-window confidences; see `lipsync_b200.aggregate`."""

@@ -314,3 +314,32 @@ def test_token_path_subpath(model, seed0_sd):
     assert fh.shape == (4, 16, 256) and ch.shape == (4, 256) and torch.isfinite(ch).all()
     with pytest.raises(ValueError):
         model.fuse_tokens(v[:, :, :128], a)
+
+
+@pytest.mark.parametrize("name", ["random_motion_random_audio", "static_face_loud_audio", "static_face_silent_audio",
+                                  "speech_like_correlated", "slow_drift_anticorrelated", "short_audio_clamped_tail"])
+def test_speech_stats_match_reference_golden(model, name):
+    """Device speaking-alignment scores / mouth-motion statistics (lsd_track_motion + lsd_speech_stats) against the REAL
+    reference functions (predictor.py:333-419) on the same synthetic tracks: score <= 2e-5 absolute, motion / energy at the
+    reference's rounding (1e-6 / 1e-4), identical check results and aggregate."""
+    import json, os
+    from tests.golden.make_speech_golden import make_case
+    with open(os.path.join(os.path.dirname(__file__), "golden", "speech_golden.json")) as fh:
+        gold = json.load(fh)[name]
+    track, starts, mel, n_frames = make_case(name)
+    pred = lb.Predictor(model, batch_size=8)
+    sp, mm, ae = pred.window_speech_stats(torch.from_numpy(track).cuda(), starts, torch.from_numpy(mel).cuda(), n_frames)
+    assert np.abs(sp.cpu().numpy() - np.asarray(gold["speaking"], dtype=np.float64)).max() <= 2e-5
+    checks = pred.mouth_motion_checks(mm.cpu().tolist(), ae.cpu().tolist())
+    for got, exp in zip(checks, gold["mouth"]):
+        assert abs(got["mouth_motion_energy"] - exp["mouth_motion_energy"]) <= 2e-6
+        assert abs(got["audio_energy"] - exp["audio_energy"]) <= 2e-4
+        assert got["check_result"] == exp["check_result"]
+    agg = pred.aggregate_mouth_motion_checks(checks)
+    assert agg["check_result"] == gold["aggregate"]["check_result"] and agg["samples_checked"] == gold["aggregate"]["samples_checked"]
+    assert agg["counts"] == gold["aggregate"]["counts"]
+    # single-window entry with the reference's own argument types: float32 (3,T,H,W) crop + (1,F,Ta) mel slice
+    s0 = starts[1]
+    visual = np.ascontiguousarray(track[s0:s0 + 32].transpose(3, 0, 1, 2)).astype(np.float32) / 255.0
+    audio = pred._align_audio_chunk(mel, s0, n_frames)
+    assert abs(pred._speaking_alignment_score(visual, audio) - gold["speaking"][1]) <= 2e-5

@@ -134,3 +134,22 @@ def test_sharded_scoring_gloo_world2(n):
         assert pr.exitcode == 0
     expect = (np.arange(n, dtype=np.float32) * 0.5 - 3.0).tolist()
     assert res[0] == expect and res[1] == expect
+
+
+def test_mouth_motion_decision_and_aggregate_mirror_reference_golden():
+    """`mouth_motion_checks` (predictor.py:403-419) and `aggregate_mouth_motion_checks` (:463-523) on the statistics the real
+    reference computed (tests/golden/speech_golden.json): same per-window results, same aggregate."""
+    import json
+    import os
+    import lipsync_b200 as lb
+    with open(os.path.join(os.path.dirname(__file__), "golden", "speech_golden.json")) as fh:
+        gold = json.load(fh)
+    pred = lb.Predictor(None, batch_size=4)
+    for name, g in gold.items():
+        checks = pred.mouth_motion_checks([c["mouth_motion_energy"] for c in g["mouth"]], [c["audio_energy"] for c in g["mouth"]])
+        assert [c["check_result"] for c in checks] == [c["check_result"] for c in g["mouth"]], name
+        agg = lb.Predictor.aggregate_mouth_motion_checks(checks)
+        assert agg["check_result"] == g["aggregate"]["check_result"], name
+        assert agg["counts"] == g["aggregate"]["counts"] and agg["samples_checked"] == g["aggregate"]["samples_checked"]
+        assert abs(agg["audio_energy"] - g["aggregate"]["audio_energy"]) < 1e-9
+    assert lb.Predictor.aggregate_mouth_motion_checks([])["check_result"] == "no_data"
