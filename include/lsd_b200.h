@@ -151,6 +151,14 @@ int lsd_speech_stats(lsd_handle* h, const float* motion_full, const float* motio
                      float* speaking_out, float* mouth_motion_out, float* audio_energy_out,
                      int32_t* idx_scratch, void* stream);
 
+/* ---- energy VAD: the per-frame loops of detect_voice_activity (app/preprocessing/audio.py:178-230) ---------- */
+/* energy_out[i] = mean(y[160 i : min(160 i + 400, n)]^2) for i < lsd_vad_frames(n) = ceil(n / 160)   (audio.py:182-192);
+ * mask_out[i] = OR_{j in [i-1,i+1]} (energy[j] >= threshold)                                         (audio.py:214-221).
+ * The threshold (median / 20th percentile / torchaudio VAD energy, audio.py:196-212) is computed by the host layer. */
+int lsd_vad_frames(int64_t n_samples);
+int lsd_frame_energy(lsd_handle* h, const float* pcm, int64_t n_samples, float* energy_out, void* stream);
+int lsd_vad_mask(lsd_handle* h, const float* energy, int n_frames, float threshold, uint8_t* mask_out, void* stream);
+
 /* ---- introspection (tests / profiling) ------------------------------------------------------- */
 /* Named intermediate of the last lsd_forward on this handle: byte offset into the workspace. */
 int lsd_stage_info(lsd_handle* h, const char* name, size_t* offset_bytes, int64_t* numel, int* dtype);

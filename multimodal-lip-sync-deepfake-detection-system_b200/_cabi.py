@@ -26,7 +26,7 @@ EXPORTS = [
     "lsd_score_windows", "lsd_stage_info", "lsd_stage_count", "lsd_stage_name", "lsd_launch_count",
     "lsd_profile_enable", "lsd_profile_get",
     "lsd_audio_encoder_workspace_bytes", "lsd_audio_encoder", "lsd_token_path_workspace_bytes", "lsd_token_path",
-    "lsd_track_motion", "lsd_speech_stats",
+    "lsd_track_motion", "lsd_speech_stats", "lsd_vad_frames", "lsd_frame_energy", "lsd_vad_mask",
 ]
 
 
@@ -81,6 +81,9 @@ def lib() -> C.CDLL:
         L.lsd_track_motion.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp]; L.lsd_track_motion.restype = i
         L.lsd_speech_stats.argtypes = [vp, vp, vp, i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), i, i, vp, i, i, i, i, vp, vp, vp, vp, vp]
         L.lsd_speech_stats.restype = i
+        L.lsd_vad_frames.argtypes = [i64]; L.lsd_vad_frames.restype = i
+        L.lsd_frame_energy.argtypes = [vp, vp, i64, vp, vp]; L.lsd_frame_energy.restype = i
+        L.lsd_vad_mask.argtypes = [vp, vp, i, C.c_float, vp, vp]; L.lsd_vad_mask.restype = i
         _lib = L
         return L
 

@@ -128,3 +128,39 @@ def preprocess_audio(path: Path, sr: int = 16000, n_mels: int = 80, hop_length: 
     if y.size == 0:
         raise ValueError(f"Empty audio signal for {path}")
     return preprocess_audio_pcm(y, target_frames)
+
+
+def detect_voice_activity_pcm(y: np.ndarray, sr: int = 16000, trigger_level: float = 7.0, trigger_time: float = 0.25,
+                              search_time: float = 1.0, allowed_gap: float = 0.25, device: str = "cuda"):
+    """`detect_voice_activity` (app/preprocessing/audio.py:105-245) on decoded samples: `(voice_mask bool (ceil(n/160),),
+    duration_sec)`.  Frame energies, thresholding and the 3-frame smoothing run on the device (`lsd_frame_energy`,
+    `lsd_vad_mask`); the threshold follows audio.py:196-212 — numpy median / 20th percentile of the energies and, as in the
+    reference, the energy of `torchaudio.functional.vad`'s trimmed waveform (library call on the host, used only as a cap)."""
+    y = np.asarray(y, dtype=np.float32).reshape(-1)
+    if y.size == 0:
+        return np.ones(1, dtype=bool), 0.0
+    duration_sec = len(y) / sr
+    dev = torch.device(device)
+    L = _cabi.lib()
+    n_frames = L.lsd_vad_frames(y.size)
+    pcm = torch.from_numpy(y).to(dev)
+    energy = torch.empty(n_frames, dtype=torch.float32, device=dev)
+    mask = torch.empty(n_frames, dtype=torch.uint8, device=dev)
+    h = _handle(pcm.device)
+    stream = torch.cuda.current_stream(pcm.device).cuda_stream
+    with h.lock:
+        _cabi.check(h.ptr, L.lsd_frame_energy(h.ptr, pcm.data_ptr(), y.size, energy.data_ptr(), stream))
+    frame_energies = energy.cpu().numpy()
+    energy_median = np.median(frame_energies)
+    energy_p20 = np.percentile(frame_energies, 20)
+    threshold = min(energy_p20, energy_median * 0.05)
+    threshold = max(1e-8, threshold)
+    import torchaudio.functional as AF
+    vad_waveform = AF.vad(waveform=torch.from_numpy(y).float().unsqueeze(0), sample_rate=sr, trigger_level=trigger_level,
+                          trigger_time=trigger_time, search_time=search_time, allowed_gap=allowed_gap)
+    if vad_waveform.numel() > 0:
+        vad_energy = float(torch.mean(vad_waveform ** 2))
+        threshold = min(threshold, max(1e-8, vad_energy * 0.05))
+    with h.lock:
+        _cabi.check(h.ptr, L.lsd_vad_mask(h.ptr, energy.data_ptr(), n_frames, float(threshold), mask.data_ptr(), stream))
+    return mask.cpu().numpy().astype(bool), duration_sec

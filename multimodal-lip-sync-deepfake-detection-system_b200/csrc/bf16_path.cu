@@ -744,6 +744,7 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   cudaStream_t sst = h->side_stream;
   BCtx bs{h, ws, &P, sst};
   bs.max_ctas = (h->num_sms * 5) / 8;
+  if (const char* e = getenv("LSD_SIDE_CTAS")) bs.max_ctas = atoi(e);   // tuning knob: SMs the artifact branch may occupy
   cudaEventRecord(h->ev_fork, st);
   cudaStreamWaitEvent(sst, h->ev_fork, 0);
   float* comb = b.f("comb");

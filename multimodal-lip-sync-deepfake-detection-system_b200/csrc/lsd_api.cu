@@ -505,6 +505,31 @@ extern "C" int lsd_speech_stats(lsd_handle* h, const float* motion_full, const f
 }
 
 // ================================================================================================
+// Energy VAD (detect_voice_activity, app/preprocessing/audio.py:178-230)
+// ================================================================================================
+extern "C" int lsd_vad_frames(int64_t n_samples) { return n_samples <= 0 ? 0 : (int)((n_samples + 159) / 160); }
+extern "C" int lsd_frame_energy(lsd_handle* h, const float* pcm, int64_t n_samples, float* energy_out, void* stream) {
+  if (!h) return LSD_ERR_ARG;
+  if (n_samples < 0) return lsd_fail(h, LSD_ERR_SHAPE, "lsd_frame_energy: negative length");
+  if (n_samples == 0) return LSD_OK;
+  if (!pcm || !energy_out) return lsd_fail(h, LSD_ERR_ARG, "lsd_frame_energy: null pointer argument");
+  CUDA_OK(h, cudaSetDevice(h->device));
+  lsd::launch_frame_energy(pcm, n_samples, lsd_vad_frames(n_samples), energy_out, reinterpret_cast<cudaStream_t>(stream));
+  CUDA_OK(h, cudaGetLastError());
+  return LSD_OK;
+}
+extern "C" int lsd_vad_mask(lsd_handle* h, const float* energy, int n_frames, float threshold, uint8_t* mask_out, void* stream) {
+  if (!h) return LSD_ERR_ARG;
+  if (n_frames < 0) return lsd_fail(h, LSD_ERR_SHAPE, "lsd_vad_mask: negative length");
+  if (n_frames == 0) return LSD_OK;
+  if (!energy || !mask_out) return lsd_fail(h, LSD_ERR_ARG, "lsd_vad_mask: null pointer argument");
+  CUDA_OK(h, cudaSetDevice(h->device));
+  lsd::launch_vad_mask(energy, n_frames, threshold, mask_out, reinterpret_cast<cudaStream_t>(stream));
+  CUDA_OK(h, cudaGetLastError());
+  return LSD_OK;
+}
+
+// ================================================================================================
 // Introspection
 // ================================================================================================
 extern "C" int lsd_profile_enable(lsd_handle* h, int on) {

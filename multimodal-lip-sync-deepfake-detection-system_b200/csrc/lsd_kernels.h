@@ -87,4 +87,7 @@ void launch_speech_stats(const float* motion_full, const float* motion_low, cons
                          int T, const float* mel, int F, int Ta_full, int Ta, float* score, float* mouth_motion, float* audio_energy,
                          cudaStream_t s);
 
+void launch_frame_energy(const float* pcm, long long n, int n_frames, float* energy, cudaStream_t s);
+void launch_vad_mask(const float* energy, int n_frames, float threshold, uint8_t* mask, cudaStream_t s);
+
 }  // namespace lsd

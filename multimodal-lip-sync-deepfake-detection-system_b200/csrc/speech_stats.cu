@@ -198,3 +198,45 @@ void launch_speech_stats(const float* motion_full, const float* motion_low, cons
 }
 
 }  // namespace lsd
+
+// ================================================================================================
+// Energy VAD: the per-frame Python loops of detect_voice_activity
+// (app/preprocessing/audio.py:178-230).  frame i = samples [160 i, min(160 i + 400, n)); energy = mean of squares; the mask is
+// energy >= threshold, then OR-smoothed over [i-1, i+1].  The two order statistics behind the threshold (median, 20th
+// percentile) are taken on the host from the energies, with numpy, exactly as the reference does.
+// ================================================================================================
+namespace lsd {
+
+__global__ void __launch_bounds__(128) frame_energy_kernel(const float* __restrict__ pcm, long long n, int n_frames, float* __restrict__ energy) {
+  // one warp per frame: 400 samples, float64 accumulation, rounded once (numpy: pairwise float32 mean of y*y)
+  const int f = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (f >= n_frames) return;
+  const long long a = (long long)f * 160, b = a + 400 < n ? a + 400 : n;
+  double s = 0.0;
+  for (long long i = a + lane; i < b; i += 32) { const float v = pcm[i]; s += (double)__fmul_rn(v, v); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) energy[f] = (float)(s / (double)(b - a));
+}
+
+__global__ void vad_mask_kernel(const float* __restrict__ energy, int n_frames, float threshold, uint8_t* __restrict__ mask) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_frames) return;
+  bool v = energy[i] >= threshold;
+  if (i > 0) v = v || energy[i - 1] >= threshold;
+  if (i + 1 < n_frames) v = v || energy[i + 1] >= threshold;
+  mask[i] = v ? 1 : 0;
+}
+
+void launch_frame_energy(const float* pcm, long long n, int n_frames, float* energy, cudaStream_t s) {
+  if (n_frames <= 0) return;
+  frame_energy_kernel<<<(n_frames + 3) / 4, 128, 0, s>>>(pcm, n, n_frames, energy);
+  count_launch();
+}
+void launch_vad_mask(const float* energy, int n_frames, float threshold, uint8_t* mask, cudaStream_t s) {
+  if (n_frames <= 0) return;
+  vad_mask_kernel<<<(n_frames + 255) / 256, 256, 0, s>>>(energy, n_frames, threshold, mask);
+  count_launch();
+}
+
+}  // namespace lsd

@@ -343,3 +343,18 @@ def test_speech_stats_match_reference_golden(model, name):
     visual = np.ascontiguousarray(track[s0:s0 + 32].transpose(3, 0, 1, 2)).astype(np.float32) / 255.0
     audio = pred._align_audio_chunk(mel, s0, n_frames)
     assert abs(pred._speaking_alignment_score(visual, audio) - gold["speaking"][1]) <= 2e-5
+
+
+@pytest.mark.parametrize("name", ["speech_bursts", "continuous_noise", "near_silence", "short_clip", "loud_then_quiet"])
+def test_vad_mask_matches_reference_golden(built, name):
+    """Energy VAD (lsd_frame_energy + lsd_vad_mask + the reference's threshold rule) against the REAL
+    `detect_voice_activity` (audio.py:105-245) on the same synthetic PCM: identical masks."""
+    import json, os
+    from tests.golden.make_vad_golden import make_pcm as vad_pcm
+    with open(os.path.join(os.path.dirname(__file__), "golden", "vad_golden.json")) as fh:
+        gold = json.load(fh)[name]
+    mask, dur = lb.detect_voice_activity_pcm(vad_pcm(name))
+    exp = np.asarray([c == "1" for c in gold["mask"]])
+    assert mask.dtype == bool and mask.shape == exp.shape
+    assert int((mask != exp).sum()) == 0
+    assert abs(dur - gold["duration_sec"]) < 1e-9
