@@ -123,6 +123,9 @@ int lsd_logmel(lsd_handle* h, const float* pcm, const int64_t* clip_offsets_host
  * Audio windows follow _align_audio_chunk (predictor.py:525-552) with chunk_a_size = Ta.
  * Builds the windows on device and runs lsd_forward in batches of `batch`. */
 size_t lsd_score_workspace_bytes(lsd_handle* h, int batch, int T, int H, int W, int F, int Ta, int precision);
+/* Passing a workspace of at least TWICE lsd_score_workspace_bytes() lets lsd_score_windows (tensor-core route, more than one
+ * batch) alternate batches between its two halves and overlap the latency-bound tail of batch k (audio encoder, token path,
+ * head, artifact branch: internal streams) with the visual encoder of batch k+1; results are bit-identical either way. */
 int lsd_score_windows(lsd_handle* h, const uint8_t* track, int n_frames, int H, int W,
                       const int32_t* starts_host, const int32_t* audio_starts_host_or_null, int n_windows, int T,
                       const float* mel_full, int F, int Ta_full, int total_v_frames, int Ta,

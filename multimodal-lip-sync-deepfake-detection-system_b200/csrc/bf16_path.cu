@@ -697,9 +697,11 @@ static int token_path_bf16(const BCtx& b, const Shapes& s) {
   return 0;
 }
 
+// pipe_parity >= 0 (lsd_score_windows with a double workspace): everything after the visual encoder is enqueued on
+// h->tail_stream, ordered after the encoder by ev_front[parity]; ev_tail_done[parity] marks the batch's logits complete.
 static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, const lsd_aux* aux, char* ws, size_t ws_bytes,
                              cudaStream_t st, bool inputs_ready, const void* video, int vdt, int vlayout, const void* audio, int adt,
-                             const int32_t* vstarts = nullptr, int n_frames = 0) {
+                             const int32_t* vstarts = nullptr, int n_frames = 0, int pipe_parity = -1) {
   BPlan P;
   build_plan(s, P);
   if (P.f32.cursor > ws_bytes) return lsd_fail(h, LSD_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", P.f32.cursor, ws_bytes);
@@ -707,10 +709,13 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   // Zero padding of the planar buffers lives in the workspace across calls: (re)initialise when the workspace or the
   // shapes change.  Kernels only ever write valid positions (or zeros at pad positions), so the padding stays intact.
   const int sig[6] = {s.B, s.T, s.H, s.W, s.F, s.Ta};
-  if (h->ws_sig_ptr != ws || h->ws_sig_bytes != ws_bytes || memcmp(h->ws_sig_shape, sig, sizeof(sig)) != 0) {
+  const bool known1 = h->ws_sig_ptr == ws && h->ws_sig_bytes == ws_bytes && memcmp(h->ws_sig_shape, sig, sizeof(sig)) == 0;
+  const bool known2 = h->ws_sig2_ptr == ws && h->ws_sig2_bytes == ws_bytes && memcmp(h->ws_sig2_shape, sig, sizeof(sig)) == 0;
+  if (!known1 && !known2) {
     cudaError_t e = cudaMemsetAsync(ws + P.planar_begin, 0, P.planar_end - P.planar_begin, st);
     if (e != cudaSuccess) return lsd_fail(h, LSD_ERR_CUDA, "workspace init: %s", cudaGetErrorString(e));
-    h->ws_sig_ptr = ws; h->ws_sig_bytes = ws_bytes; memcpy(h->ws_sig_shape, sig, sizeof(sig));
+    if (pipe_parity == 1) { h->ws_sig2_ptr = ws; h->ws_sig2_bytes = ws_bytes; memcpy(h->ws_sig2_shape, sig, sizeof(sig)); }
+    else { h->ws_sig_ptr = ws; h->ws_sig_bytes = ws_bytes; memcpy(h->ws_sig_shape, sig, sizeof(sig)); }
   }
   BCtx b{h, ws, &P, st};
   const int B = s.B, T = s.T, TA = s.A4, NT = T + 1;
@@ -743,7 +748,7 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   }
   cudaStream_t sst = h->side_stream;
   BCtx bs{h, ws, &P, sst};
-  bs.max_ctas = (h->num_sms * 5) / 8;
+  bs.max_ctas = h->num_sms / 2;   // measured at B=64: 56 / 74 / 92 / 110 / 128 SMs -> 4.07 / 3.93 / 3.99 / 4.01 / 4.10 ms per step
   if (const char* e = getenv("LSD_SIDE_CTAS")) bs.max_ctas = atoi(e);   // tuning knob: SMs the artifact branch may occupy
   cudaEventRecord(h->ev_fork, st);
   cudaStreamWaitEvent(sst, h->ev_fork, 0);
@@ -764,6 +769,17 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   RUNS("art.hf3", a_.in = &hf; a_.og = hf.g; a_.act = ACT_RELU; a_.yp = &pb["hf_b"]);
   launch_planar_mean2(bs.org(pb["hf_b"]), pb["hf_b"].plane_stride, hf.g, 64, comb + 384, 448, 1, none, sst);
   cudaEventRecord(h->ev_join, sst);
+  // ---- everything below is the latency-bound tail (small grids): on the caller's stream, or on the tail stream when batches
+  // are pipelined (the main stream then goes straight on to the next batch's visual encoder)
+  cudaStream_t tst = st;
+  if (pipe_parity >= 0) {
+    cudaEventRecord(h->ev_front[pipe_parity], st);
+    cudaStreamWaitEvent(h->tail_stream, h->ev_front[pipe_parity], 0);
+    tst = h->tail_stream;
+  }
+  {
+  BCtx b{h, ws, &P, tst};
+  cudaStream_t st = tst;
   if ((rc = audio_encoder_bf16(b, s, inputs_ready, audio, adt))) return rc;
   // ---- projection (fusion_module.py:108-124)
   const UcGeom gt = P.gt;
@@ -789,6 +805,18 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
     if (aux->fused_tokens) cudaMemcpyAsync(aux->fused_tokens, b.f("fused"), tb, cudaMemcpyDeviceToDevice, st);
     if (aux->cls_output) launch_copy_rows(tok, (int64_t)NT * 256, aux->cls_output, 256, B, 256, st);
   }
+  if (pipe_parity >= 0) cudaEventRecord(h->ev_tail_done[pipe_parity], st);
+  }
+  return 0;
+}
+
+int ensure_pipeline(lsd_handle* h) {
+  if (h->tail_stream) return 0;
+  if (cudaStreamCreateWithFlags(&h->tail_stream, cudaStreamNonBlocking) != cudaSuccess) return lsd_fail(h, LSD_ERR_CUDA, "tail stream creation failed");
+  for (int i = 0; i < 2; ++i)
+    if (cudaEventCreateWithFlags(&h->ev_front[i], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_tail_done[i], cudaEventDisableTiming) != cudaSuccess)
+      return lsd_fail(h, LSD_ERR_CUDA, "pipeline event creation failed");
   return 0;
 }
 
@@ -865,7 +893,7 @@ int forward_bf16(lsd_handle* h, int B, int T, int H, int W, int F, int Ta, const
 
 int score_batch_bf16(lsd_handle* h, const uint8_t* track, int n_frames, const int32_t* d_vstarts, const int32_t* d_astarts,
                      const float* mel_full, int Ta_full, int nb, int T, int H, int W, int F, int Ta, float* logits, char* ws,
-                     size_t ws_bytes, cudaStream_t st) {
+                     size_t ws_bytes, cudaStream_t st, int pipe_parity) {
   Shapes s;
   int rc = make_shapes(h, nb, T, H, W, F, Ta, s);
   if (rc) return rc;
@@ -875,7 +903,7 @@ int score_batch_bf16(lsd_handle* h, const uint8_t* track, int n_frames, const in
   BCtx b{h, ws, &P, st};
   launch_gather_audio(mel_full, F, Ta_full, d_astarts, b.f("aud"), nb, Ta, st);
   if (video_rows_bulk_ok(track, LSD_U8, LSD_NDHWC, W))
-    return forward_bf16_impl(h, s, logits, nullptr, ws, ws_bytes, st, true, track, LSD_U8, LSD_NDHWC, nullptr, 0, d_vstarts, n_frames);
+    return forward_bf16_impl(h, s, logits, nullptr, ws, ws_bytes, st, true, track, LSD_U8, LSD_NDHWC, nullptr, 0, d_vstarts, n_frames, pipe_parity);
   launch_gather_windows_u8(track, n_frames, d_vstarts, b.f("vid"), nb, T, H * W * 3, st);
-  return forward_bf16_impl(h, s, logits, nullptr, ws, ws_bytes, st, true, nullptr, 0, 0, nullptr, 0);
+  return forward_bf16_impl(h, s, logits, nullptr, ws, ws_bytes, st, true, nullptr, 0, 0, nullptr, 0, nullptr, 0, pipe_parity);
 }

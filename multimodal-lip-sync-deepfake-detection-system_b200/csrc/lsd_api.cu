@@ -70,6 +70,8 @@ extern "C" void lsd_destroy(lsd_handle* h) {
   if (h->lm_clips) cudaFree(h->lm_clips);
   for (cudaEvent_t e : h->prof.ev) cudaEventDestroy(e);
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
+  if (h->tail_stream) cudaStreamDestroy(h->tail_stream);
+  for (int i = 0; i < 2; ++i) { if (h->ev_front[i]) cudaEventDestroy(h->ev_front[i]); if (h->ev_tail_done[i]) cudaEventDestroy(h->ev_tail_done[i]); }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;
@@ -337,7 +339,7 @@ extern "C" int lsd_forward(lsd_handle* h, const void* video, int video_dtype, in
     make_plan_f32(s, p);
     if (p.cursor > workspace_bytes) return lsd_fail(h, LSD_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", p.cursor, workspace_bytes);
     h->stages = p.stages;
-    h->ws_sig_ptr = nullptr;  // the fp32 plan overwrites any bf16 zero padding kept in this workspace
+    h->ws_sig_ptr = nullptr; h->ws_sig2_ptr = nullptr;  // the fp32 plan overwrites any bf16 zero padding kept in this workspace
     rc = forward_f32(h, s, p, reinterpret_cast<char*>(workspace), aux, logits_out, st, false, video, video_dtype, video_layout, audio, audio_dtype);
     if (rc) return rc;
   }
@@ -389,13 +391,25 @@ extern "C" int lsd_score_windows(lsd_handle* h, const uint8_t* track, int n_fram
     h->idx_host[i] = starts_host[i];
     h->idx_host[n_windows + i] = (int32_t)a_start;
   }
-  for (int w0 = 0; w0 < n_windows; w0 += batch) {
+  // Cross-batch pipelining (tensor-core route, more than one batch, workspace >= 2 x lsd_score_workspace_bytes): batches
+  // alternate between the two halves of the workspace; the tail of batch k (audio encoder, token path, head, artifact branch)
+  // runs on side streams while this stream continues with the visual encoder of batch k+1.
+  const size_t fw_bytes = ((lsd_workspace_bytes(h, batch, T, H, W, F, Ta, precision) + 255) & ~size_t(255));
+  const bool pipelined = precision == LSD_PREC_BF16 && n_windows > batch && workspace_bytes >= 2 * idx_bytes + 2 * fw_bytes &&
+                         getenv("LSD_NO_PIPELINE") == nullptr;
+  if (pipelined && (rc = ensure_pipeline(h))) return rc;
+  int k = 0;
+  for (int w0 = 0; w0 < n_windows; w0 += batch, ++k) {
     const int nb = (n_windows - w0) < batch ? (n_windows - w0) : batch;
+    const int parity = k & 1;
+    if (pipelined && k >= 2) CUDA_OK(h, cudaStreamWaitEvent(st, h->ev_tail_done[parity], 0));   // this half of the workspace is free again
     CUDA_OK(h, cudaMemcpyAsync(d_vs, &h->idx_host[w0], nb * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CUDA_OK(h, cudaMemcpyAsync(d_as, &h->idx_host[n_windows + w0], nb * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     if (precision == LSD_PREC_BF16) {
-      rc = score_batch_bf16(h, track, n_frames, d_vs, d_as, mel_full, Ta_full, nb, T, H, W, F, Ta, logits_out + w0, fws,
-                            workspace_bytes - 2 * idx_bytes, st);
+      if (pipelined) rc = score_batch_bf16(h, track, n_frames, d_vs, d_as, mel_full, Ta_full, nb, T, H, W, F, Ta, logits_out + w0,
+                                           fws + (size_t)parity * fw_bytes, fw_bytes, st, parity);
+      else rc = score_batch_bf16(h, track, n_frames, d_vs, d_as, mel_full, Ta_full, nb, T, H, W, F, Ta, logits_out + w0, fws,
+                                 workspace_bytes - 2 * idx_bytes, st);
       if (rc) return rc;
     } else {
       Shapes sb;
@@ -403,13 +417,17 @@ extern "C" int lsd_score_windows(lsd_handle* h, const uint8_t* track, int n_fram
       Plan pb;
       make_plan_f32(sb, pb);
       h->stages = pb.stages;
-      h->ws_sig_ptr = nullptr;
+      h->ws_sig_ptr = nullptr; h->ws_sig2_ptr = nullptr;
       Ctx c{h, fws, &pb, st};
       launch_gather_windows_u8(track, n_frames, d_vs, c.buf("vid"), nb, T, H * W * 3, st);
       launch_gather_audio(mel_full, F, Ta_full, d_as, c.buf("aud"), nb, Ta, st);
       rc = forward_f32(h, sb, pb, fws, nullptr, logits_out + w0, st, true, nullptr, 0, 0, nullptr, 0);
       if (rc) return rc;
     }
+  }
+  if (pipelined) {   // the caller's stream sees every batch's logits
+    CUDA_OK(h, cudaStreamWaitEvent(st, h->ev_tail_done[0], 0));
+    if (k >= 2) CUDA_OK(h, cudaStreamWaitEvent(st, h->ev_tail_done[1], 0));
   }
   CUDA_OK(h, cudaGetLastError());
   return LSD_OK;

@@ -61,6 +61,13 @@ struct lsd_handle {
   const void* ws_sig_ptr = nullptr;        // bf16 workspace whose zero padding is initialised (see forward_bf16)
   size_t ws_sig_bytes = 0;
   int ws_sig_shape[6] = {0, 0, 0, 0, 0, 0};
+  const void* ws_sig2_ptr = nullptr;       // second remembered workspace (the two halves of a pipelined lsd_score_windows call)
+  size_t ws_sig2_bytes = 0;
+  int ws_sig2_shape[6] = {0, 0, 0, 0, 0, 0};
+  // cross-batch pipelining of lsd_score_windows: the tail of batch k (audio encoder, token path, head; artifact branch on the
+  // side stream) runs on tail_stream while the main stream already runs the visual encoder of batch k+1
+  cudaStream_t tail_stream = nullptr;
+  cudaEvent_t ev_front[2] = {nullptr, nullptr}, ev_tail_done[2] = {nullptr, nullptr};
   std::vector<Stage> stages;
   std::vector<int32_t> idx_host;
   Prof prof;
@@ -99,4 +106,5 @@ int token_path_bf16_run(lsd_handle* h, int B, int T, int TA, const float* v_emb,
                         char* ws, size_t ws_bytes, cudaStream_t st);
 int score_batch_bf16(lsd_handle* h, const uint8_t* track, int n_frames, const int32_t* d_vstarts, const int32_t* d_astarts,
                      const float* mel_full, int Ta_full, int nb, int T, int H, int W, int F, int Ta, float* logits,
-                     char* ws, size_t ws_bytes, cudaStream_t st);
+                     char* ws, size_t ws_bytes, cudaStream_t st, int pipe_parity = -1);
+int ensure_pipeline(lsd_handle* h);

@@ -62,19 +62,19 @@ __device__ __forceinline__ void unpack8(const uint4& r, float* v) {
 }
 
 // Persistent, warp-specialised (14 warps):
-//   warps 0-3  bulk-copy producers (measured on B200: one warp sustains only ~1 cp.async.bulk per ~100-130 cycles whatever the
-//              number of active lanes, and the rate scales with the number of issuing warps -> the copies of a stage are
-//              dealt round-robin to four warps),
-//   warps 4-5  MMA issuers (each owns half of the tile's M-tiles),
-//   warps 6-13 epilogue (two warps per TMEM lane quarter, each handling every other 32-column chunk).
-// Each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the accumulators are double-buffered in TMEM so the
-// epilogue of tile i overlaps the main loop of tile i+1, and the smem ring keeps streaming across tile boundaries.
+//   warps 0-3  bulk-copy producers: ring stage k of the CTA's stream belongs to warp k % 4, whose lanes issue the stage's
+//              copies (2 planes per K chunk + the weight pieces) in one converged cp.async.bulk; operands come from the
+//              stage program in shared memory (see UcStageDesc in umma_conv.cuh),
+//   warps 4-5  MMA issuers (each owns half of the tile's M-tiles); the loop nest runs warp-uniformly, only the
+//              tcgen05.mma / tcgen05.commit are predicated on one elected lane,
+//   warps 6-13 epilogue (two warps per TMEM lane quarter, each handling half of the columns).
+// Each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the accumulators are double-buffered in TMEM when they fit so
+// that the epilogue of tile i overlaps the main loop of tile i+1, and the smem ring keeps streaming across tile boundaries.
 constexpr int UC_THREADS = 448;
 constexpr int UC_PROD_WARPS = 4, UC_MMA_WARP0 = 4, UC_EPI_WARP0 = 6, UC_EPI_WARPS = 8;
-// issuing one cp.async.bulk occupies the issuing thread for ~330 cycles; the cost overlaps across warps and (partly) across the
-// lanes of a warp (probe/bulk_issue.cu: 16 issuers = 4 warps x 4 lanes sustain one 2 KB copy per ~26 cycles per SM), so the
-// copies of a stage are dealt to 16 issuing threads: stages made of many small copies (token-path GEMMs) are issue-bound otherwise
-constexpr int UC_PROD_LANES = 8;   // 32 issuers >= copies per stage (2 * kpack A planes + up to kpack weight pieces; kpack <= 8 checked on the host)
+// (issuing one cp.async.bulk occupies the issuing thread for ~330 cycles; the cost overlaps across warps and partly across the
+// lanes of a warp — probe/bulk_issue.cu — hence one stage per warp and one copy per lane; a stage has at most 3 * kpack <= 24
+// copies, checked on the host)
 
 // GENERIC = false: lean epilogue of the convolution layers (bias, ReLU/none, optional bf16 residual, planar / parity-split bf16
 // store).  GENERIC = true: everything (fp32 rows in/out, split-bf16 hi/lo outputs and residuals, GELU) for the audio encoder and

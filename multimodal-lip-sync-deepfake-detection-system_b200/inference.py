@@ -282,6 +282,8 @@ class Predictor:
             need = L.lsd_score_workspace_bytes(h.ptr, batch, self.chunk_size, H, W, F_, chunk_a_size, prec)
             if need == 0:
                 _cabi.check(h.ptr, _cabi.LSD_ERR_SHAPE)
+            if n > batch and prec == _cabi.LSD_PREC_BF16:
+                need = 2 * need      # a double workspace lets lsd_score_windows overlap the tail of batch k with the encoder of batch k+1
             ws = m._workspace(need, dev)
             st = (C.c_int32 * n)(*[int(s) for s in starts])
             ast = None

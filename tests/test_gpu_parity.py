@@ -358,3 +358,21 @@ def test_vad_mask_matches_reference_golden(built, name):
     assert mask.dtype == bool and mask.shape == exp.shape
     assert int((mask != exp).sum()) == 0
     assert abs(dur - gold["duration_sec"]) < 1e-9
+
+
+def test_score_track_pipelined_batches_bitwise(model):
+    """lsd_score_windows with a double workspace pipelines batches (tail of batch k on side streams while the main stream runs
+    the encoder of batch k+1): logits must equal the single-batch result bit for bit, also when the two workspace halves are
+    reused (5 batches) and when the last batch is ragged."""
+    model.compute_precision = "bf16"
+    g = torch.Generator().manual_seed(9)
+    n_win = 19
+    track = torch.randint(0, 256, (32 + 8 * (n_win - 1), 96, 96, 3), dtype=torch.uint8, generator=g).cuda()
+    mel = (-80.0 * torch.rand(1, 80, 900, generator=g)).cuda()
+    starts = [8 * i for i in range(n_win)]
+    one = lb.Predictor(model, batch_size=32).score_track_logits(track, starts, mel, track.shape[0]).clone()
+    for bs in (4, 8):
+        piped = lb.Predictor(model, batch_size=bs).score_track_logits(track, starts, mel, track.shape[0]).clone()
+        assert torch.equal(piped, one), bs
+    again = lb.Predictor(model, batch_size=4).score_track_logits(track, starts, mel, track.shape[0])
+    assert torch.equal(again, one)
