@@ -721,6 +721,25 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   const int B = s.B, T = s.T, TA = s.A4, NT = T + 1;
   auto& pb = P.pb;
   int rc = 0;
+  if (!h->side_stream) {
+    if (cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_audio, cudaEventDisableTiming) != cudaSuccess)
+      return lsd_fail(h, LSD_ERR_CUDA, "side stream creation failed");
+  }
+  cudaStream_t sst = h->side_stream;
+  BCtx bs{h, ws, &P, sst};
+  bs.max_ctas = h->num_sms / 2;   // measured at B=64: 56 / 74 / 92 / 110 / 128 SMs -> 4.07 / 3.93 / 3.99 / 4.01 / 4.10 ms per step
+  if (const char* e = getenv("LSD_SIDE_CTAS")) bs.max_ctas = atoi(e);   // tuning knob: SMs the side stream may occupy
+  // ---- audio encoder (independent of the video): on the side stream from the very start, so that its latency-bound chain of
+  // small launches hides behind the visual encoder instead of heading the tail
+  const bool audio_early = getenv("LSD_AUDIO_LATE") == nullptr;
+  if (audio_early) {
+    cudaEventRecord(h->ev_start, st);
+    cudaStreamWaitEvent(sst, h->ev_start, 0);
+    if ((rc = audio_encoder_bf16(bs, s, inputs_ready, audio, adt))) return rc;
+    cudaEventRecord(h->ev_audio, sst);
+  }
   // ---- video -> bf16 pixel rows (+ per-frame laplacian conv), stem conv on tcgen05 (Toeplitz K), max-pool in planar layout
   const PBuf &xs = pb["xs"], &xl = pb["xl"], &so = pb["s_out"], &x1 = pb["x1"];
   const float* lapw = h->warena + h->convs.at("art.lap").w_off;
@@ -741,15 +760,6 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   // ---- artifact detector (artifact_detector.py:149-183) on a side stream: its convolutions (hf front/back on the laplacian
   // rows, temporal-inconsistency convs on the feature map and on its temporal delta) only need the visual encoder's
   // output, so they run concurrently with the audio encoder + token path, whose small grids leave most SMs idle.
-  if (!h->side_stream) {
-    if (cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess)
-      return lsd_fail(h, LSD_ERR_CUDA, "side stream creation failed");
-  }
-  cudaStream_t sst = h->side_stream;
-  BCtx bs{h, ws, &P, sst};
-  bs.max_ctas = h->num_sms / 2;   // measured at B=64: 56 / 74 / 92 / 110 / 128 SMs -> 4.07 / 3.93 / 3.99 / 4.01 / 4.10 ms per step
-  if (const char* e = getenv("LSD_SIDE_CTAS")) bs.max_ctas = atoi(e);   // tuning knob: SMs the artifact branch may occupy
   cudaEventRecord(h->ev_fork, st);
   cudaStreamWaitEvent(sst, h->ev_fork, 0);
   float* comb = b.f("comb");
@@ -780,10 +790,11 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   {
   BCtx b{h, ws, &P, tst};
   cudaStream_t st = tst;
-  if ((rc = audio_encoder_bf16(b, s, inputs_ready, audio, adt))) return rc;
+  if (!audio_early) { if ((rc = audio_encoder_bf16(b, s, inputs_ready, audio, adt))) return rc; }
   // ---- projection (fusion_module.py:108-124)
   const UcGeom gt = P.gt;
   RUN("projection.visual_proj", a_.in = &pb["vfeat_p"]; a_.in_lo = &pb["vfeat_p_lo"]; a_.og = gt; a_.yp = &pb["vemb_p"]; a_.yp_lo = &pb["vemb_p_lo"]; a_.y32 = b.f("v_emb"); a_.y32_ld = 256);
+  if (audio_early) cudaStreamWaitEvent(st, h->ev_audio, 0);   // audio features (a_feat / afeat_p) are complete
   RUN("projection.audio_proj", a_.in = &pb["afeat_p"]; a_.in_lo = &pb["afeat_p_lo"]; a_.og = P.gta; a_.y32 = b.f("a_emb"); a_.y32_ld = 256);
   if ((rc = token_path_bf16(b, s))) return rc;
   float* tok = b.f("tok");

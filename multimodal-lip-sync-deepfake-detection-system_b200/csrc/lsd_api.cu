@@ -74,6 +74,8 @@ extern "C" void lsd_destroy(lsd_handle* h) {
   for (int i = 0; i < 2; ++i) { if (h->ev_front[i]) cudaEventDestroy(h->ev_front[i]); if (h->ev_tail_done[i]) cudaEventDestroy(h->ev_tail_done[i]); }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->ev_start) cudaEventDestroy(h->ev_start);
+  if (h->ev_audio) cudaEventDestroy(h->ev_audio);
   delete h;
 }
 

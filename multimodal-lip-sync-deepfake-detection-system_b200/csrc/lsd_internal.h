@@ -72,7 +72,7 @@ struct lsd_handle {
   std::vector<int32_t> idx_host;
   Prof prof;
   cudaStream_t side_stream = nullptr;      // artifact branch runs here, concurrently with the token path
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_start = nullptr, ev_audio = nullptr;
   int64_t launches0 = 0;
   // stage programs of the tcgen05 launches (umma_conv.cuh): built on the host once per (layer, shapes, workspace), cached here
   char* prog_arena = nullptr;

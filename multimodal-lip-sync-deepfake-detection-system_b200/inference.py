@@ -117,20 +117,23 @@ class Predictor:
 
     def score_batches(self, batches) -> List[torch.Tensor]:
         """Pipelined scoring of a sequence of HOST batches `(visual (B,3,T,H,W), audio (B,1,F,Ta))` (torch CPU tensors, ideally
-        pinned): the H2D copy of batch k+1 runs on a copy stream while batch k is scored, logits come back through pinned
-        memory.  Returns one fp32 CPU tensor of logits per batch.  Same numerics as calling the model batch by batch."""
+        pinned): the H2D copies of the next batches run on a copy stream while batch k is scored, logits come back through
+        pinned memory.  Returns one fp32 CPU tensor of logits per batch.  Same numerics as calling the model batch by batch."""
         dev = self.device
         m = self.model
         comp = torch.cuda.current_stream(dev)
         copy = getattr(self, "_copy_stream", None)
         if copy is None:
             copy = self._copy_stream = torch.cuda.Stream(dev)
-        slots = [None, None]
-        ready = [torch.cuda.Event(), torch.cuda.Event()]
-        free = [torch.cuda.Event(), torch.cuda.Event()]
+        # three device slots: the copy stream stays busy back to back (copy and forward take about the same time at B=64 —
+        # 4.1 ms of PCIe vs 3.9 ms of compute — so two slots leave bubbles whenever either one jitters)
+        NS = 3
+        slots = [None] * NS
+        ready = [torch.cuda.Event() for _ in range(NS)]
+        free = [torch.cuda.Event() for _ in range(NS)]
         outs: List[torch.Tensor] = []
         for k, (vh, ah) in enumerate(batches):
-            s = k & 1
+            s = k % NS
             if self.use_half_precision:
                 vh, ah = vh.half(), ah.half()
             if slots[s] is None or slots[s][0].shape != vh.shape or slots[s][0].dtype != vh.dtype or slots[s][1].shape != ah.shape:

@@ -376,3 +376,22 @@ def test_score_track_pipelined_batches_bitwise(model):
         assert torch.equal(piped, one), bs
     again = lb.Predictor(model, batch_size=4).score_track_logits(track, starts, mel, track.shape[0])
     assert torch.equal(again, one)
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 72, 72, 80, 128), (1, 6, 50, 50, 40, 64), (3, 5, 100, 36, 80, 72)])
+def test_bf16_odd_shapes_against_oracle(model, seed0_sd, shape):
+    """Shapes that leave the fast paths: H not a multiple of the 16-row bands of the bulk-copy row kernel (72, 100), widths
+    that are not multiples of 4 (50: direct-load fallback), odd stem widths (25: -inf edge of the max-pool), ragged T / Ta.
+    bf16 budget on logits, same decisions unless the oracle logit is inside the budget of zero."""
+    b, t, h, w, f, ta = shape
+    model.compute_precision = "bf16"
+    video, audio = lb.synthetic_windows(21, b, t, h, w, f, ta)
+    ref = orc.forward(seed0_sd, video, audio)
+    out = model(video.cuda(), audio.cuda()).float().cpu()
+    assert float((out - ref).abs().max()) <= BF16_ABS, (out, ref)
+    sure = ref.abs() > BF16_ABS
+    assert ((out >= 0) == (ref >= 0))[sure].all()
+    u8 = (video * 255).round().to(torch.uint8)
+    out_u8 = model(u8.permute(0, 2, 3, 4, 1).contiguous().cuda(), audio.cuda(), video_layout="NDHWC").float().cpu()
+    ref_u8 = orc.forward(seed0_sd, u8.float() / 255.0, audio)
+    assert float((out_u8 - ref_u8).abs().max()) <= BF16_ABS
