@@ -387,6 +387,11 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
     if (v == 1) p.nbuf = 1;
     if (v == 2 && 2 * L.ntile <= 512) { p.nbuf = 2; p.MT = std::min(p.MT, mt2); }
   }
+  // One issue-loop iteration (one tap: descriptor arithmetic + R2UR moves + the MMAs) costs an issuing warp 150-260 cycles,
+  // more than the tensor time of the MMAs it carries for narrow tiles, so the M-tiles of a tap are spread over as many
+  // issuing warps as there are M-tiles.
+  p.issuers = p.MT;   // (measured: one issuer for MT = 4 is 6-15 % slower than two on every layer)
+  if (const char* e = getenv("LSD_UMMA_ISSUERS")) { const int v = atoi(e); if (v >= 1 && v <= p.MT && p.MT % v == 0) p.issuers = v; }   // tuning knob
   uint32_t cols = 32;
   while ((int)cols < p.nbuf * p.MT * L.ntile) cols *= 2;
   p.tmem_cols = cols;

@@ -61,17 +61,17 @@ __device__ __forceinline__ void unpack8(const uint4& r, float* v) {
   for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(rb[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
 }
 
-// Persistent, warp-specialised (14 warps):
+// Persistent, warp-specialised (16 warps):
 //   warps 0-3  bulk-copy producers: ring stage k of the CTA's stream belongs to warp k % 4, whose lanes issue the stage's
 //              copies (2 planes per K chunk + the weight pieces) in one converged cp.async.bulk; operands come from the
 //              stage program in shared memory (see UcStageDesc in umma_conv.cuh),
-//   warps 4-5  MMA issuers (each owns half of the tile's M-tiles); the loop nest runs warp-uniformly, only the
-//              tcgen05.mma / tcgen05.commit are predicated on one elected lane,
-//   warps 6-13 epilogue (two warps per TMEM lane quarter, each handling half of the columns).
+//   warps 4-7  MMA issuers (1, 2 or 4 active; each owns an equal share of the tile's M-tiles); the loop nest runs
+//              warp-uniformly, only the tcgen05.mma / tcgen05.commit are predicated on one elected lane,
+//   warps 8-15 epilogue (two warps per TMEM lane quarter, each handling half of the columns).
 // Each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the accumulators are double-buffered in TMEM when they fit so
 // that the epilogue of tile i overlaps the main loop of tile i+1, and the smem ring keeps streaming across tile boundaries.
-constexpr int UC_THREADS = 448;
-constexpr int UC_PROD_WARPS = 4, UC_MMA_WARP0 = 4, UC_EPI_WARP0 = 6, UC_EPI_WARPS = 8;
+constexpr int UC_THREADS = 512;
+constexpr int UC_PROD_WARPS = 4, UC_MMA_WARP0 = 4, UC_MMA_WARPS = 4, UC_EPI_WARP0 = 8, UC_EPI_WARPS = 8;
 // (issuing one cp.async.bulk occupies the issuing thread for ~330 cycles; the cost overlaps across warps and partly across the
 // lanes of a warp — probe/bulk_issue.cu — hence one stage per warp and one copy per lane; a stage has at most 3 * kpack <= 24
 // copies, checked on the host)
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
   const int slice = blockIdx.y, ch0 = slice * p.Cout;
   const uint32_t buf_cols = (uint32_t)(p.MT * p.Cout);
 
-  const int n_issuers = p.MT > 1 ? 2 : 1;   // MMA-issuing warps (M-tiles are independent accumulators)
+  const int n_issuers = p.issuers;          // MMA-issuing warps (M-tiles are independent accumulators), chosen on the host
   if (tid == 0) {
     for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], n_issuers); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], n_issuers); mbar_init(&tempty_bar[i], UC_EPI_WARPS); }
@@ -157,11 +157,11 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
         if (dbg && lane == 0 && tile == (int)blockIdx.x && si < 8) p.dbg[56 + si] = clock64();   // copies issued
       }
     }
-  } else if (warp == UC_MMA_WARP0 || warp == UC_MMA_WARP0 + 1) {
+  } else if (warp < UC_MMA_WARP0 + UC_MMA_WARPS) {
     // ------------------------------------------------ MMA issuers (whole warp runs the loop; one elected lane issues)
-    if (warp == UC_MMA_WARP0 + 1 && n_issuers == 1) goto done;
-    const int mt_lo = (warp == UC_MMA_WARP0) ? 0 : p.MT / 2;                         // this warp's M-tiles: [mt_lo, mt_lo + mt_n)
-    const int mt_n = n_issuers == 1 ? p.MT : p.MT / 2;
+    if (warp - UC_MMA_WARP0 >= n_issuers) goto done;
+    const int mt_n = p.MT / n_issuers;                                               // this warp's M-tiles: [mt_lo, mt_lo + mt_n)
+    const int mt_lo = (warp - UC_MMA_WARP0) * mt_n;
     // One thread feeds the tensor core: keep the per-instruction work to a few 32-bit adds.  A descriptor is
     // (constant high part) | (start address >> 4); tap / M-tile / K-chunk offsets are added in 16-byte units.
     const uint32_t idesc = idesc_bf16(128, p.Cout);
@@ -208,6 +208,10 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
                 const uint64_t da = desc_hi64 | (uint64_t)at, db = desc_hi64 | (uint64_t)wj;
                 mma_bf16_ss_pred(tb, da, db, idesc, acc, leader);
                 if (mt_n > 1) mma_bf16_ss_pred(tb + (uint32_t)p.Cout, da + 128u, db, idesc, acc, leader);
+                if (mt_n > 2) {
+                  mma_bf16_ss_pred(tb + 2u * (uint32_t)p.Cout, da + 256u, db, idesc, acc, leader);
+                  mma_bf16_ss_pred(tb + 3u * (uint32_t)p.Cout, da + 384u, db, idesc, acc, leader);
+                }
                 acc = 1u;
                 wj += tap_w;
               }

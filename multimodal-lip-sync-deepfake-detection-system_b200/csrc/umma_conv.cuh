@@ -90,6 +90,7 @@ struct UmmaConvP {
   int act;
   int Cout;                   // columns per CTA (one slice); grid.y = number of slices
   int MT, stages, ngroups, nbands;
+  int issuers;                // MMA-issuing warps (1, 2 or 4; divides MT): each issues MT / issuers M-tiles per tap
   int nbuf;                   // TMEM accumulator buffers: 2 = epilogue overlaps the next tile, 1 = all 512 columns for one tile
   long long* dbg;             // optional: CTA (0,0) writes clock64 phase timestamps (debug builds of the bench only)
   const UcStageDesc* prog;    // device memory: the stage program (nst_tile entries)
