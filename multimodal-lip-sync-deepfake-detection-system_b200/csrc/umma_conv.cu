@@ -199,6 +199,17 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
             if (dbg && warp == UC_MMA_WARP0 && lane == 0 && lt == 0 && dbg_it < 24) p.dbg[8 + dbg_it++] = clock64();
             const uint32_t sa = ((smem_base + (uint32_t)stage * stage_bytes) >> 4) + (uint32_t)mt_lo * 128u;
             const uint32_t sw = ((smem_base + (uint32_t)stage * stage_bytes + p.a_stage_bytes) >> 4) | b_lbo;
+            if (ntaps == 1) {
+              // Linear layers (one tap per band): one MMA per K chunk, descriptors advance by constant steps
+              uint32_t at = (sa | a_lbo) + (uint32_t)bd.rel[0], wj = sw;
+#pragma unroll 1
+              for (int j = 0; j < nc; ++j, at += a_chunk, wj += w_chunk) {
+                const uint64_t da = desc_hi64 | (uint64_t)at, db = desc_hi64 | (uint64_t)wj;
+                mma_bf16_ss_pred(tb, da, db, idesc, acc, leader);
+                if (mt_n > 1) mma_bf16_ss_pred(tb + (uint32_t)p.Cout, da + 128u, db, idesc, acc, leader);
+                acc = 1u;
+              }
+            } else
             for (int j = 0; j < nc; ++j) {
               const uint32_t aj = (sa + (uint32_t)j * a_chunk) | a_lbo;
               uint32_t wj = sw + (uint32_t)j * w_chunk;
