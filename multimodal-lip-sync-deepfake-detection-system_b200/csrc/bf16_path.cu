@@ -734,7 +734,7 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   }
   cudaStream_t sst = h->side_stream;
   BCtx bs{h, ws, &P, sst};
-  bs.max_ctas = h->num_sms / 2;   // measured at B=64: 56 / 74 / 92 / 110 / 128 SMs -> 4.07 / 3.93 / 3.99 / 4.01 / 4.10 ms per step
+  bs.max_ctas = (h->num_sms * 2) / 3;   // measured at B=64: 74 / 92 / 110 / 128 / 148 SMs -> 3.58 / 3.49 / 3.49 / 3.53 / 3.61 ms per step
   if (const char* e = getenv("LSD_SIDE_CTAS")) bs.max_ctas = atoi(e);   // tuning knob: SMs the side stream may occupy
   // ---- audio encoder (independent of the video): on the side stream from the very start, so that its latency-bound chain of
   // small launches hides behind the visual encoder instead of heading the tail
