@@ -252,8 +252,8 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
       if (dbg && warp == UC_EPI_WARP0 && lane == 0 && lt == 0) p.dbg[4] = clock64();   // first accumulator complete
       for (int m = 0; m < p.MT; ++m) {
         const int64_t P = P0 + (int64_t)m * 128 + rowt;
-        int n, t, h, w;
-        const bool valid = uc_decode(p.g, P, n, t, h, w);
+        int n = 0, t = 0, h = 0, w = 0;
+        const bool valid = (p.skip & 8) ? true : uc_decode(p.g, P, n, t, h, w);   // (skip bit 3: timing experiment)
         const bool inrange = P < p.g.P_total;
         const int64_t outer = valid ? ((int64_t)n * p.g.T + t) * p.g.H + h : 0;
         int64_t dst = P * 8;
@@ -261,32 +261,47 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
           dst = (int64_t)((h & 1) * 2 + (w & 1)) * p.y_set_stride + uc_flat(p.g2, n, t, h >> 1, w >> 1) * 8;
         else if (valid && p.y_mode == UC_Y_PARITY_H)
           dst = (int64_t)((h & 1) * 2) * p.y_set_stride + uc_flat(p.g2, n, t, h >> 1, w) * 8;
-        const bool store_planar = (p.y_mode == UC_Y_PLAIN && inrange) || (p.y_mode >= UC_Y_PARITY && valid);
+        const bool store_planar = ((p.y_mode == UC_Y_PLAIN && inrange) || (p.y_mode >= UC_Y_PARITY && valid)) && !(p.skip & 4);   // (skip bit 2: timing experiment)
         // this warp's columns: [half*Cout/2, (half+1)*Cout/2)
         const int cbeg = half * (p.Cout >> 1), cend = cbeg + (p.Cout >> 1);
         if constexpr (!GENERIC) {
-          // lean path: 8 columns (one 16-byte plane entry) per step, pointers advanced by one plane per step
+          // lean path: up to 32 columns per step — the four TMEM loads of a step are issued back to back and waited for once
+          // (with one load + wait per 8 columns the TMEM round trip made the stem and the hf front convolution epilogue-bound:
+          // 10 k cycles of epilogue per 512-position tile against 8.4 k cycles of MMAs), residuals are prefetched before the wait
           __nv_bfloat16* yp = p.y + (int64_t)((ch0 + cbeg) >> 3) * p.y_plane_stride + dst;
           const __nv_bfloat16* rp = p.res + (int64_t)((ch0 + cbeg) >> 3) * p.res_plane_stride + P * 8;
           const bool has_res = p.res != nullptr && valid;
           const float* bp = &bias_s[cbeg];
           uint32_t ta = tb + (uint32_t)(m * p.Cout + cbeg);
 #pragma unroll 1
-          for (int c = cbeg; c < cend; c += 8, yp += p.y_plane_stride, rp += p.res_plane_stride, bp += 8, ta += 8) {
-            float v[8];
-            tmem_ld8(ta, v);
-            uint4 rr = make_uint4(0, 0, 0, 0);
-            if (has_res) rr = *reinterpret_cast<const uint4*>(rp);   // overlaps the TMEM load
-            const float4 b0 = *reinterpret_cast<const float4*>(bp);
-            const float4 b1 = *reinterpret_cast<const float4*>(bp + 4);
+          for (int c = cbeg; c < cend; c += 32, yp += 4 * p.y_plane_stride, rp += 4 * p.res_plane_stride, bp += 32, ta += 32) {
+            const int nq = min(4, (cend - c) >> 3);
+            float v[4][8];
+            uint4 rr[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              rr[q] = make_uint4(0, 0, 0, 0);
+              if (q < nq) {
+                tmem_ld8(ta + 8 * q, v[q]);
+                if (has_res) rr[q] = *reinterpret_cast<const uint4*>(rp + (int64_t)q * p.res_plane_stride);
+              }
+            }
             tmem_ld_wait();
-            float f[8];
-            unpack8(rr, f);
-            v[0] = fmaxf(v[0] + b0.x + f[0], act_lo); v[1] = fmaxf(v[1] + b0.y + f[1], act_lo);
-            v[2] = fmaxf(v[2] + b0.z + f[2], act_lo); v[3] = fmaxf(v[3] + b0.w + f[3], act_lo);
-            v[4] = fmaxf(v[4] + b1.x + f[4], act_lo); v[5] = fmaxf(v[5] + b1.y + f[5], act_lo);
-            v[6] = fmaxf(v[6] + b1.z + f[6], act_lo); v[7] = fmaxf(v[7] + b1.w + f[7], act_lo);
-            if (store_planar) *reinterpret_cast<uint4*>(yp) = valid ? pack8(v) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (q < nq) {
+                const float4 b0 = *reinterpret_cast<const float4*>(bp + 8 * q);
+                const float4 b1 = *reinterpret_cast<const float4*>(bp + 8 * q + 4);
+                float f[8];
+                unpack8(rr[q], f);
+                float* w8 = v[q];
+                w8[0] = fmaxf(w8[0] + b0.x + f[0], act_lo); w8[1] = fmaxf(w8[1] + b0.y + f[1], act_lo);
+                w8[2] = fmaxf(w8[2] + b0.z + f[2], act_lo); w8[3] = fmaxf(w8[3] + b0.w + f[3], act_lo);
+                w8[4] = fmaxf(w8[4] + b1.x + f[4], act_lo); w8[5] = fmaxf(w8[5] + b1.y + f[5], act_lo);
+                w8[6] = fmaxf(w8[6] + b1.z + f[6], act_lo); w8[7] = fmaxf(w8[7] + b1.w + f[7], act_lo);
+                if (store_planar) *reinterpret_cast<uint4*>(yp + (int64_t)q * p.y_plane_stride) = valid ? pack8(w8) : make_uint4(0, 0, 0, 0);
+              }
+            }
           }
         } else {
 #pragma unroll 1
