@@ -857,6 +857,15 @@ template <> __device__ __forceinline__ void vr_load4<uint8_t>(const uint8_t* p, 
   o[0] = (float)(v & 0xffu) / 255.0f; o[1] = (float)((v >> 8) & 0xffu) / 255.0f;
   o[2] = (float)((v >> 16) & 0xffu) / 255.0f; o[3] = (float)(v >> 24) / 255.0f;
 }
+// uint8 through a 256-entry table of i / 255.0f (exactly the reference's astype(float32) / 255.0): twelve IEEE divisions per
+// strip row made the uint8 variant ALU-bound and slower than the fp32 one although it reads a quarter of the bytes
+template <typename T> __device__ __forceinline__ void vr_load4_lut(const T* p, float* o, const float*) { vr_load4<T>(p, o); }
+template <> __device__ __forceinline__ void vr_load4_lut<uint8_t>(const uint8_t* p, float* o, const float* lut) {
+  const uint32_t v = *reinterpret_cast<const uint32_t*>(p);
+  o[0] = lut[v & 0xffu]; o[1] = lut[(v >> 8) & 0xffu]; o[2] = lut[(v >> 16) & 0xffu]; o[3] = lut[v >> 24];
+}
+template <typename T> __device__ __forceinline__ float vr_norm_lut(T x, const float*) { return vr_norm<T>((float)x); }
+template <> __device__ __forceinline__ float vr_norm_lut<uint8_t>(uint8_t x, const float* lut) { return lut[x]; }
 
 template <typename T, int LAYOUT>
 __global__ void __launch_bounds__(VR2_THREADS, 2) video_rows_tma_kernel(const T* __restrict__ video, const int32_t* __restrict__ starts, int n_frames,
@@ -866,7 +875,9 @@ __global__ void __launch_bounds__(VR2_THREADS, 2) video_rows_tma_kernel(const T*
   extern __shared__ __align__(128) uint8_t vr_smem[];
   __shared__ uint64_t full_bar[VR2_STAGES];
   __shared__ float lw[81];
+  __shared__ float lut[256];
   const int tid = threadIdx.x;
+  if (sizeof(T) == 1) lut[tid] = (float)tid / 255.0f;   // VR2_THREADS == 256
   const int row_elems = LAYOUT == 0 ? W : 3 * W;                       // elements of one image row in one staged piece
   const int plane_elems = (VR2_ROWS + 2) * row_elems;                  // one staged piece (all rows of the band + halo)
   const uint32_t stage_bytes = (uint32_t)((LAYOUT == 0 ? 3 : 1) * plane_elems * (int)sizeof(T));
@@ -938,22 +949,22 @@ __global__ void __launch_bounds__(VR2_THREADS, 2) video_rows_tma_kernel(const T*
 #pragma unroll
             for (int ci = 0; ci < 3; ++ci) {
               const T* pr = trow + (size_t)ci * plane_elems + p0;
-              vr_load4<T>(pr, &x[ci][1]);
-              x[ci][0] = p0 > 0 ? vr_norm<T>((float)pr[-1]) : 0.f;
-              x[ci][5] = p0 + 4 < W ? vr_norm<T>((float)pr[4]) : 0.f;
+              vr_load4_lut<T>(pr, &x[ci][1], lut);
+              x[ci][0] = p0 > 0 ? vr_norm_lut<T>(pr[-1], lut) : 0.f;
+              x[ci][5] = p0 + 4 < W ? vr_norm_lut<T>(pr[4], lut) : 0.f;
             }
           } else {
             const T* pr = trow + 3 * p0;
             float e[12];
-            vr_load4<T>(pr, e); vr_load4<T>(pr + 4, e + 4); vr_load4<T>(pr + 8, e + 8);
+            vr_load4_lut<T>(pr, e, lut); vr_load4_lut<T>(pr + 4, e + 4, lut); vr_load4_lut<T>(pr + 8, e + 8, lut);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
               for (int ci = 0; ci < 3; ++ci) x[ci][q + 1] = e[q * 3 + ci];
 #pragma unroll
             for (int ci = 0; ci < 3; ++ci) {
-              x[ci][0] = p0 > 0 ? vr_norm<T>((float)pr[ci - 3]) : 0.f;
-              x[ci][5] = p0 + 4 < W ? vr_norm<T>((float)pr[12 + ci]) : 0.f;
+              x[ci][0] = p0 > 0 ? vr_norm_lut<T>(pr[ci - 3], lut) : 0.f;
+              x[ci][5] = p0 + 4 < W ? vr_norm_lut<T>(pr[12 + ci], lut) : 0.f;
             }
           }
         } else {
