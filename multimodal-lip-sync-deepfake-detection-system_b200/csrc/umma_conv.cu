@@ -250,7 +250,10 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
       mbar_wait(&tfull_bar[buf], use & 1u);
       tc_fence_after();
       if (dbg && warp == UC_EPI_WARP0 && lane == 0 && lt == 0) p.dbg[4] = clock64();   // first accumulator complete
-      for (int m = 0; m < p.MT; ++m) {
+      // Lean path with several M-tiles per tile: the two warps of a TMEM lane quarter take alternate M-tiles and all columns
+      // (one position decode per M-tile and thread instead of two); otherwise they split the columns.
+      const bool split_m = !GENERIC && p.MT >= 2;
+      for (int m = split_m ? half : 0; m < p.MT; m += split_m ? 2 : 1) {
         const int64_t P = P0 + (int64_t)m * 128 + rowt;
         int n = 0, t = 0, h = 0, w = 0;
         const bool valid = (p.skip & 8) ? true : uc_decode(p.g, P, n, t, h, w);   // (skip bit 3: timing experiment)
@@ -262,8 +265,8 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
         else if (valid && p.y_mode == UC_Y_PARITY_H)
           dst = (int64_t)((h & 1) * 2) * p.y_set_stride + uc_flat(p.g2, n, t, h >> 1, w) * 8;
         const bool store_planar = ((p.y_mode == UC_Y_PLAIN && inrange) || (p.y_mode >= UC_Y_PARITY && valid)) && !(p.skip & 4);   // (skip bit 2: timing experiment)
-        // this warp's columns: [half*Cout/2, (half+1)*Cout/2)
-        const int cbeg = half * (p.Cout >> 1), cend = cbeg + (p.Cout >> 1);
+        // this warp's columns: [half*Cout/2, (half+1)*Cout/2), or all of them when the warps split the M-tiles
+        const int cbeg = split_m ? 0 : half * (p.Cout >> 1), cend = split_m ? p.Cout : cbeg + (p.Cout >> 1);
         if constexpr (!GENERIC) {
           // lean path: up to 32 columns per step — the four TMEM loads of a step are issued back to back and waited for once
           // (with one load + wait per 8 columns the TMEM round trip made the stem and the hf front convolution epilogue-bound:
@@ -287,6 +290,22 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
               }
             }
             tmem_ld_wait();
+            if (p.res == nullptr) {   // (warp-uniform) no residual: bias + activation only
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (q < nq) {
+                  const float4 b0 = *reinterpret_cast<const float4*>(bp + 8 * q);
+                  const float4 b1 = *reinterpret_cast<const float4*>(bp + 8 * q + 4);
+                  float* w8 = v[q];
+                  w8[0] = fmaxf(w8[0] + b0.x, act_lo); w8[1] = fmaxf(w8[1] + b0.y, act_lo);
+                  w8[2] = fmaxf(w8[2] + b0.z, act_lo); w8[3] = fmaxf(w8[3] + b0.w, act_lo);
+                  w8[4] = fmaxf(w8[4] + b1.x, act_lo); w8[5] = fmaxf(w8[5] + b1.y, act_lo);
+                  w8[6] = fmaxf(w8[6] + b1.z, act_lo); w8[7] = fmaxf(w8[7] + b1.w, act_lo);
+                  if (store_planar) *reinterpret_cast<uint4*>(yp + (int64_t)q * p.y_plane_stride) = valid ? pack8(w8) : make_uint4(0, 0, 0, 0);
+                }
+              }
+              continue;
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               if (q < nq) {
