@@ -350,7 +350,7 @@ struct UArgs {
 int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
   const BLayer& L = c.h->blayers.at(name);
   const UcGeom& og = a.og;
-  if (og.P_total >= (int64_t)1 << 31) return lsd_fail(c.h, LSD_ERR_SHAPE, "%s: more than 2^31 padded positions in one launch (reduce the batch)", name.c_str());
+  if (og.P_total >= ((int64_t)1 << 31) - 1024) return lsd_fail(c.h, LSD_ERR_SHAPE, "%s: more than 2^31 padded positions in one launch (reduce the batch)", name.c_str());
   UmmaConvP p;
   memset(&p, 0, sizeof(p));
   p.w = reinterpret_cast<const __nv_bfloat16*>(c.h->barena);

@@ -31,14 +31,15 @@ __device__ __forceinline__ float uc_act(float v, int act) {
   return v;
 }
 
-// (P_total < 2^31 is enforced on the host: 32-bit divisions only)
+// (P_total < 2^31 is enforced on the host: the three divisions are multiply + shift with the geometry's magic numbers)
+__device__ __forceinline__ uint32_t uc_div(uint32_t n, uint32_t m, int s) { return (uint32_t)(((uint64_t)n * m) >> (31 + s)); }
 __device__ __forceinline__ bool uc_decode(const UcGeom& g, int64_t P, int& n, int& t, int& h, int& w) {
   if (P < 0 || P >= g.P_total) return false;
   const uint32_t Pu = (uint32_t)P;
-  const uint32_t S = Pu / (uint32_t)g.SL;
+  const uint32_t S = uc_div(Pu, g.mSL, g.sSL);
   const int r = (int)(Pu - S * (uint32_t)g.SL);
-  const int row = r / g.RW, col = r - row * g.RW;
-  n = (int)(S / (uint32_t)g.TS);
+  const int row = (int)uc_div((uint32_t)r, g.mRW, g.sRW), col = r - row * g.RW;
+  n = (int)uc_div(S, g.mTS, g.sTS);
   t = (int)(S - (uint32_t)n * (uint32_t)g.TS) - g.ot;
   h = row - g.oh; w = col - g.ow;
   return (unsigned)t < (unsigned)g.T && (unsigned)h < (unsigned)g.H && (unsigned)w < (unsigned)g.W && n < g.N;
@@ -53,6 +54,14 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
   __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
   for (int e = 0; e < 4; ++e) ob[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+  return o;
+}
+// same with the ReLU folded into the conversion (cvt.rn.relu.bf16x2.f32: negative inputs and -0 give +0)
+__device__ __forceinline__ uint4 pack8_relu(const float* v) {
+  uint4 o;
+  uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(ow[e]) : "f"(v[2 * e + 1]), "f"(v[2 * e]));
   return o;
 }
 __device__ __forceinline__ void unpack8(const uint4& r, float* v) {
@@ -253,7 +262,11 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
       // Lean path with several M-tiles per tile: the two warps of a TMEM lane quarter take alternate M-tiles and all columns
       // (one position decode per M-tile and thread instead of two); otherwise they split the columns.
       const bool split_m = !GENERIC && p.MT >= 2;
-      for (int m = split_m ? half : 0; m < p.MT; m += split_m ? 2 : 1) {
+      // (the lean epilogue works in 32-column steps: with a single M-tile the columns are split only if both halves are whole
+      // steps, otherwise the first warp of the quarter takes all of them)
+      const bool split_c = !split_m && (GENERIC || (p.Cout & 63) == 0);
+      const int m_end = (!split_m && !split_c && half == 1) ? 0 : p.MT;
+      for (int m = split_m ? half : 0; m < m_end; m += split_m ? 2 : 1) {
         const int64_t P = P0 + (int64_t)m * 128 + rowt;
         int n = 0, t = 0, h = 0, w = 0;
         const bool valid = (p.skip & 8) ? true : uc_decode(p.g, P, n, t, h, w);   // (skip bit 3: timing experiment)
@@ -266,59 +279,50 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
           dst = (int64_t)((h & 1) * 2) * p.y_set_stride + uc_flat(p.g2, n, t, h >> 1, w) * 8;
         const bool store_planar = ((p.y_mode == UC_Y_PLAIN && inrange) || (p.y_mode >= UC_Y_PARITY && valid)) && !(p.skip & 4);   // (skip bit 2: timing experiment)
         // this warp's columns: [half*Cout/2, (half+1)*Cout/2), or all of them when the warps split the M-tiles
-        const int cbeg = split_m ? 0 : half * (p.Cout >> 1), cend = split_m ? p.Cout : cbeg + (p.Cout >> 1);
+        const int cbeg = split_c ? half * (p.Cout >> 1) : 0, cend = split_c ? cbeg + (p.Cout >> 1) : p.Cout;
         if constexpr (!GENERIC) {
-          // lean path: up to 32 columns per step — the four TMEM loads of a step are issued back to back and waited for once
-          // (with one load + wait per 8 columns the TMEM round trip made the stem and the hf front convolution epilogue-bound:
-          // 10 k cycles of epilogue per 512-position tile against 8.4 k cycles of MMAs), residuals are prefetched before the wait
-          __nv_bfloat16* yp = p.y + (int64_t)((ch0 + cbeg) >> 3) * p.y_plane_stride + dst;
-          const __nv_bfloat16* rp = p.res + (int64_t)((ch0 + cbeg) >> 3) * p.res_plane_stride + P * 8;
-          const bool has_res = p.res != nullptr && valid;
+          // lean path (Cout % 32 == 0, checked on the host): 32 columns per step.  One 32-column TMEM load, the bias (shared
+          // memory) and the residual (global) are fetched before the single wait, the activation rides on the bf16 conversion
+          // (cvt.rn.relu), pads are zeroed by a mask on the packed words.  ~110 instructions per step instead of ~450: the stem and
+          // the hf front convolution were bound by the instruction issue of these eight warps, not by the tensor pipe.
+          char* yp = reinterpret_cast<char*>(p.y + (int64_t)((ch0 + cbeg) >> 3) * p.y_plane_stride + dst);
+          const char* rp = reinterpret_cast<const char*>(p.res + (int64_t)((ch0 + cbeg) >> 3) * p.res_plane_stride + P * 8);
+          const int64_t yps = p.y_plane_stride * 2, rps = p.res_plane_stride * 2;
+          const bool has_res = p.res != nullptr;   // (warp-uniform)
+          const bool relu = p.act == ACT_RELU;
+          const uint32_t vmask = valid ? 0xffffffffu : 0u;
           const float* bp = &bias_s[cbeg];
           uint32_t ta = tb + (uint32_t)(m * p.Cout + cbeg);
 #pragma unroll 1
-          for (int c = cbeg; c < cend; c += 32, yp += 4 * p.y_plane_stride, rp += 4 * p.res_plane_stride, bp += 32, ta += 32) {
-            const int nq = min(4, (cend - c) >> 3);
-            float v[4][8];
+          for (int c = cbeg; c < cend; c += 32, yp += 4 * yps, rp += 4 * rps, bp += 32, ta += 32) {
+            float v[32];
+            float4 b[8];
             uint4 rr[4];
+            tmem_ld32(ta, v);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              rr[q] = make_uint4(0, 0, 0, 0);
-              if (q < nq) {
-                tmem_ld8(ta + 8 * q, v[q]);
-                if (has_res) rr[q] = *reinterpret_cast<const uint4*>(rp + (int64_t)q * p.res_plane_stride);
-              }
+            for (int q = 0; q < 8; ++q) b[q] = *reinterpret_cast<const float4*>(bp + 4 * q);
+            if (has_res) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) rr[q] = valid ? *reinterpret_cast<const uint4*>(rp + q * rps) : make_uint4(0, 0, 0, 0);
             }
             tmem_ld_wait();
-            if (p.res == nullptr) {   // (warp-uniform) no residual: bias + activation only
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { v[4 * q] += b[q].x; v[4 * q + 1] += b[q].y; v[4 * q + 2] += b[q].z; v[4 * q + 3] += b[q].w; }
+            if (has_res) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                if (q < nq) {
-                  const float4 b0 = *reinterpret_cast<const float4*>(bp + 8 * q);
-                  const float4 b1 = *reinterpret_cast<const float4*>(bp + 8 * q + 4);
-                  float* w8 = v[q];
-                  w8[0] = fmaxf(w8[0] + b0.x, act_lo); w8[1] = fmaxf(w8[1] + b0.y, act_lo);
-                  w8[2] = fmaxf(w8[2] + b0.z, act_lo); w8[3] = fmaxf(w8[3] + b0.w, act_lo);
-                  w8[4] = fmaxf(w8[4] + b1.x, act_lo); w8[5] = fmaxf(w8[5] + b1.y, act_lo);
-                  w8[6] = fmaxf(w8[6] + b1.z, act_lo); w8[7] = fmaxf(w8[7] + b1.w, act_lo);
-                  if (store_planar) *reinterpret_cast<uint4*>(yp + (int64_t)q * p.y_plane_stride) = valid ? pack8(w8) : make_uint4(0, 0, 0, 0);
-                }
-              }
-              continue;
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (q < nq) {
-                const float4 b0 = *reinterpret_cast<const float4*>(bp + 8 * q);
-                const float4 b1 = *reinterpret_cast<const float4*>(bp + 8 * q + 4);
                 float f[8];
                 unpack8(rr[q], f);
-                float* w8 = v[q];
-                w8[0] = fmaxf(w8[0] + b0.x + f[0], act_lo); w8[1] = fmaxf(w8[1] + b0.y + f[1], act_lo);
-                w8[2] = fmaxf(w8[2] + b0.z + f[2], act_lo); w8[3] = fmaxf(w8[3] + b0.w + f[3], act_lo);
-                w8[4] = fmaxf(w8[4] + b1.x + f[4], act_lo); w8[5] = fmaxf(w8[5] + b1.y + f[5], act_lo);
-                w8[6] = fmaxf(w8[6] + b1.z + f[6], act_lo); w8[7] = fmaxf(w8[7] + b1.w + f[7], act_lo);
-                if (store_planar) *reinterpret_cast<uint4*>(yp + (int64_t)q * p.y_plane_stride) = valid ? pack8(w8) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[8 * q + e] += f[e];
+              }
+            }
+            if (store_planar) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 o = relu ? pack8_relu(v + 8 * q) : pack8(v + 8 * q);
+                o.x &= vmask; o.y &= vmask; o.z &= vmask; o.w &= vmask;
+                *reinterpret_cast<uint4*>(yp + q * yps) = o;
               }
             }
           }
@@ -466,7 +470,7 @@ void launch_umma_conv(const UmmaConvP& p, int n_slices, cudaStream_t s, int max_
   const int budget = (max_ctas > 0 && max_ctas < num_sms) ? max_ctas : num_sms;   // side-stream launches leave SMs to the main stream
   int gx = (budget + n_slices - 1) / n_slices;
   gx = gx < 1 ? 1 : (gx > tiles ? tiles : gx);
-  const bool generic = p.y32 || p.res32 || p.ylo || p.res_lo || p.act == ACT_GELU || p.y_mode == UC_Y_NONE;
+  const bool generic = p.y32 || p.res32 || p.ylo || p.res_lo || p.act == ACT_GELU || p.y_mode == UC_Y_NONE || (p.Cout & 31);   // (the lean epilogue works in 32-column steps)
   if (generic) umma_conv_kernel<true><<<dim3(gx, n_slices), UC_THREADS, umma_conv_smem_bytes(p), s>>>(p);
   else umma_conv_kernel<false><<<dim3(gx, n_slices), UC_THREADS, umma_conv_smem_bytes(p), s>>>(p);
   count_launch();

@@ -48,7 +48,18 @@ struct UcGeom {
   int N, T, H, W;
   int TS, ot, HP, oh, RW, ow, SL;
   int64_t P_total;
+  // division by SL / RW / TS as multiply + shift (numerators < 2^31): q = (n * m) >> (31 + s), see uc_magic
+  uint32_t mSL, mRW, mTS;
+  int sSL, sRW, sTS;
 };
+
+// Round-up magic number for dividing numerators n < 2^31 by d >= 1: s = ceil(log2 d), m = floor(2^(31+s) / d) + 1 < 2^32;
+// m*d = 2^(31+s) + e with 0 < e <= d <= 2^s, so n*e < 2^(31+s) and floor(n*m / 2^(31+s)) == floor(n / d).
+inline void uc_magic(uint32_t d, uint32_t& m, int& s) {
+  s = 0;
+  while (((uint64_t)1 << s) < d) ++s;
+  m = (uint32_t)((((uint64_t)1 << (31 + s)) / d) + 1);
+}
 
 // One ring stage of a tile, as the producers and MMA issuers consume it ("stage program").  The sequence of stages
 // (group, K-chunk block, band) is identical for every tile — only the tile's first position shifts the A sources — so the host
@@ -143,6 +154,9 @@ inline UcGeom make_geom_ex(int N, int T, int H, int W, int tpad, int oh, int hp_
   g.RW = W + ow + wp_extra; g.ow = ow;
   g.SL = g.HP * g.RW;
   g.P_total = ((int64_t)N * g.TS + tpad) * g.SL;
+  uc_magic((uint32_t)g.SL, g.mSL, g.sSL);
+  uc_magic((uint32_t)g.RW, g.mRW, g.sRW);
+  uc_magic((uint32_t)g.TS, g.mTS, g.sTS);
   return g;
 }
 inline UcGeom make_geom(int N, int T, int H, int W) { return make_geom_ex(N, T, H, W, 1, 1, 0, 1, 0); }
