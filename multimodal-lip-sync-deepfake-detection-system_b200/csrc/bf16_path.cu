@@ -502,6 +502,24 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
     }
     p.prog = reinterpret_cast<const UcStageDesc*>(it->second);
   }
+  // tile counters of this layer (dynamic tile scheduling, LSD_UMMA_DYNAMIC=1).  Off by default: measured at B=64 it shortens the
+  // visual encoder by ~20 us per forward (CTAs delayed by the side stream's kernels take fewer tiles) but every one-tile
+  // token-path launch pays the claim + counter re-arm (~1 us each), a net +2 % per step.
+  static const bool dyn_tiles = getenv("LSD_UMMA_DYNAMIC") != nullptr;
+  if (dyn_tiles) {
+    constexpr int kMaxLayers = 512;
+    if (!c.h->tile_ctr_arena) {
+      if (cudaMalloc(&c.h->tile_ctr_arena, kMaxLayers * 16 * sizeof(unsigned)) != cudaSuccess ||
+          cudaMemset(c.h->tile_ctr_arena, 0, kMaxLayers * 16 * sizeof(unsigned)) != cudaSuccess)
+        return lsd_fail(c.h, LSD_ERR_CUDA, "tile counter allocation failed");
+    }
+    auto it = c.h->tile_ctr_idx.find(name);
+    if (it == c.h->tile_ctr_idx.end()) {
+      if ((int)c.h->tile_ctr_idx.size() >= kMaxLayers) return lsd_fail(c.h, LSD_ERR_UNSUPPORTED, "too many tcgen05 layers");
+      it = c.h->tile_ctr_idx.emplace(name, (int)c.h->tile_ctr_idx.size()).first;
+    }
+    p.tile_ctr = c.h->tile_ctr_arena + (size_t)it->second * 16;
+  }
   if (const char* e = getenv("LSD_UMMA_TRACE")) {
     // debug: per-launch phase timestamps of CTA (0,0); prints after a sync (never enabled in timed runs)
     static long long* dbuf = nullptr;
@@ -606,14 +624,16 @@ int pack_bf16_weights(lsd_handle* h, const std::vector<float>& f32_arena) {
   // columns) use 128-column slices, which keeps B = 64 (17 M-tiles) inside one wave of CTAs
   int wide = 128;
   if (const char* e = getenv("LSD_UMMA_NTW")) wide = atoi(e);   // tuning knob
+  int narrow = 64;
+  if (const char* e = getenv("LSD_UMMA_NTN")) narrow = atoi(e);   // tuning knob
   for (const char* k : {"projection.visual_proj", "projection.audio_proj", "cross.v2a.out", "cross.a2v.out",
                         "cross.gate0", "cross.fuse", "temporal.branch_k3", "temporal.branch_k5", "temporal.branch_k7",
                         "temporal.pre_scale_proj"})
-    P.add_split(k, k, 64);
+    P.add_split(k, k, narrow);
   for (const char* k : {"cross.in_v", "cross.in_a"}) P.add_split(k, k, wide);
   for (int l = 0; l < 4; ++l)
     for (const char* k : {".in", ".out", ".ff1", ".ff2"})
-      P.add_split("t" + std::to_string(l) + k, "t" + std::to_string(l) + k, (k[1] == 'i' || (k[1] == 'f' && k[3] == '1')) ? wide : 64);
+      P.add_split("t" + std::to_string(l) + k, "t" + std::to_string(l) + k, (k[1] == 'i' || (k[1] == 'f' && k[3] == '1')) ? wide : narrow);
   if (h->barena) { cudaFree(h->barena); h->barena = nullptr; }
   if (h->bbias) { cudaFree(h->bbias); h->bbias = nullptr; }
   cudaError_t e = cudaMalloc(&h->barena, P.w.size() * 2);
@@ -632,6 +652,28 @@ void make_plan_bf16(lsd_handle* h, int B, int T, int H, int W, int F, int Ta, st
   stages = P.f32.stages;
   bytes = P.f32.cursor;
 }
+
+// Debug timeline (LSD_TIMELINE=1, never in timed runs): timestamps of the phases of one forward on all of its streams, relative to
+// the start of the forward; printed to stderr after a device synchronisation.
+struct Timeline {
+  bool on = false;
+  std::vector<std::pair<std::string, cudaEvent_t>> marks;
+  void mark(cudaStream_t st, const char* name) {
+    if (!on) return;
+    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st);
+    marks.emplace_back(name, e);
+  }
+  void dump() {
+    if (!on || marks.empty()) return;
+    cudaDeviceSynchronize();
+    fprintf(stderr, "[timeline]");
+    for (auto& m : marks) { float ms = 0; cudaEventElapsedTime(&ms, marks[0].second, m.second); fprintf(stderr, " %s=%.0f", m.first.c_str(), ms * 1000.0f); }
+    fprintf(stderr, " (us)\n");
+    for (auto& m : marks) cudaEventDestroy(m.second);
+    marks.clear();
+  }
+};
+static Timeline g_tl;
 
 // AudioEncoder.forward (audio_encoder.py:173-205) on tcgen05: log-mel windows -> a_feat (B, A4, 256) fp32 + planar (hi, lo) copy
 static int audio_encoder_bf16(const BCtx& b, const Shapes& s, bool inputs_ready, const void* audio, int adt) {
@@ -679,6 +721,7 @@ static int token_path_bf16(const BCtx& b, const Shapes& s) {
   launch_gate_blend_p(b.f("gate_h"), b.W("cross.gate2.w"), b.W("cross.gate2.b"), gi, 512, gi + 256, 512, B * T, 256, pout(b, pbf("blend_p"), &pbf("blend_p_lo")), st);
   RUN("cross.fuse", a_.in = &pbf("blend_p"); a_.in_lo = &pbf("blend_p_lo"); a_.og = gt; a_.act = ACT_RELU; a_.y32 = b.f("fused"); a_.y32_ld = 256; a_.yp = &pbf("fused_p"); a_.yp_lo = &pbf("fused_p_lo"));
   // ---- temporal transformer (temporal.py:79-111)
+  g_tl.mark(st, "T:cross");
   RUN("temporal.branch_k3", a_.in = &pbf("fused_p"); a_.in_lo = &pbf("fused_p_lo"); a_.og = gt; a_.act = ACT_GELU; a_.yp = &pbf("mscat_p"); a_.yp_lo = &pbf("mscat_p_lo"); a_.y_plane_off = 0);
   RUN("temporal.branch_k5", a_.in = &pbf("fused_p"); a_.in_lo = &pbf("fused_p_lo"); a_.og = gt; a_.act = ACT_GELU; a_.yp = &pbf("mscat_p"); a_.yp_lo = &pbf("mscat_p_lo"); a_.y_plane_off = 32);
   RUN("temporal.branch_k7", a_.in = &pbf("fused_p"); a_.in_lo = &pbf("fused_p_lo"); a_.og = gt; a_.act = ACT_GELU; a_.yp = &pbf("mscat_p"); a_.yp_lo = &pbf("mscat_p_lo"); a_.y_plane_off = 64);
@@ -701,6 +744,7 @@ static int token_path_bf16(const BCtx& b, const Shapes& s) {
   }
   return 0;
 }
+
 
 // pipe_parity >= 0 (lsd_score_windows with a double workspace): everything after the visual encoder is enqueued on
 // h->tail_stream, ordered after the encoder by ev_front[parity]; ev_tail_done[parity] marks the batch's logits complete.
@@ -739,10 +783,13 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   // ---- audio encoder (independent of the video): on the side stream from the very start, so that its latency-bound chain of
   // small launches hides behind the visual encoder instead of heading the tail
   const bool audio_early = getenv("LSD_AUDIO_LATE") == nullptr;
+  g_tl.on = getenv("LSD_TIMELINE") != nullptr;
+  g_tl.mark(st, "start");
   if (audio_early) {
     cudaEventRecord(h->ev_start, st);
     cudaStreamWaitEvent(sst, h->ev_start, 0);
     if ((rc = audio_encoder_bf16(bs, s, inputs_ready, audio, adt))) return rc;
+    g_tl.mark(sst, "S:audio_enc");
     cudaEventRecord(h->ev_audio, sst);
   }
   // ---- video -> bf16 pixel rows (+ per-frame laplacian conv), stem conv on tcgen05 (Toeplitz K), max-pool in planar layout
@@ -752,13 +799,34 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   if (vstarts) launch_video_rows(video, vdt, vlayout, lapw, b.org(xs), b.org(xl), xs.set_stride, xs.g, s.H, s.W, st, vstarts, n_frames);
   else if (inputs_ready) launch_video_rows(b.f("vid"), LSD_F32, LSD_NDHWC, lapw, b.org(xs), b.org(xl), xs.set_stride, xs.g, s.H, s.W, st);
   else launch_video_rows(video, vdt, vlayout, lapw, b.org(xs), b.org(xl), xs.set_stride, xs.g, s.H, s.W, st);
+  g_tl.mark(st, "M:video_rows");
+  // The high-frequency branch only needs the laplacian rows: LSD_HF_EARLY=1 (tuning knob) runs it on the side stream right after the
+  // audio encoder, next to the visual encoder, instead of in the tail.
+  const bool hf_early = getenv("LSD_HF_EARLY") != nullptr;
+  float* comb = b.f("comb");
+  PlanarOut none{nullptr, nullptr, 0, 0, 0, 0};
+  const PBuf& hf = pb["hf_f"];
+  if (hf_early) {
+    cudaEventRecord(h->ev_fork, st);
+    cudaStreamWaitEvent(sst, h->ev_fork, 0);
+    RUNS("art.hf0", a_.in = &xl; a_.og = xl.g; a_.act = ACT_RELU; a_.yp = &hf);
+    RUNS("art.hf3", a_.in = &hf; a_.og = hf.g; a_.act = ACT_RELU; a_.yp = &pb["hf_b"]);
+    launch_planar_mean2(bs.org(pb["hf_b"]), pb["hf_b"].plane_stride, hf.g, 64, comb + 384, 448, 1, none, sst);
+    g_tl.mark(sst, "S:hf3");
+  }
   RUN("visual_encoder.stem", a_.in = &xs; a_.og = xs.g; a_.act = ACT_RELU; a_.yp = &so);
+  g_tl.mark(st, "M:stem");
   launch_planar_maxpool(b.org(so), so.plane_stride, so.g, b.org(x1), x1.plane_stride, x1.g, 64, st);
+  g_tl.mark(st, "M:maxpool");
   // ---- residual stages (visual_encoder.py:81-87, 133-152)
   if ((rc = res_stage_umma(b, "visual_encoder.layer1", x1, pb["l1a"], pb["y1"], false, UC_Y_PARITY))) return rc;
+  g_tl.mark(st, "M:layer1");
   if ((rc = res_stage_umma(b, "visual_encoder.layer2", pb["y1"], pb["l2a"], pb["y2"], true, UC_Y_PARITY))) return rc;
+  g_tl.mark(st, "M:layer2");
   if ((rc = res_stage_umma(b, "visual_encoder.layer3", pb["y2"], pb["l3a"], pb["y3"], true, UC_Y_PARITY))) return rc;
+  g_tl.mark(st, "M:layer3");
   if ((rc = res_stage_umma(b, "visual_encoder.layer4", pb["y3"], pb["l4a"], pb["y4"], true, UC_Y_PLAIN))) return rc;
+  g_tl.mark(st, "M:layer4");
   const PBuf& y4 = pb["y4"];
   // spatial mean -> visual tokens (fp32 stage + planar GEMM input)
   launch_planar_mean2(b.org(y4), y4.plane_stride, y4.g, 256, b.f("v_feat"), 256, 0, pout(b, pb["vfeat_p"], &pb["vfeat_p_lo"]), st);
@@ -767,22 +835,28 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   // output, so they run concurrently with the audio encoder + token path, whose small grids leave most SMs idle.
   cudaEventRecord(h->ev_fork, st);
   cudaStreamWaitEvent(sst, h->ev_fork, 0);
-  float* comb = b.f("comb");
-  PlanarOut none{nullptr, nullptr, 0, 0, 0, 0};
+  const bool skip_art = getenv("LSD_SKIP_ART") != nullptr;   // timing experiment only (garbage logits)
+  if (!skip_art) {
   RUNS("art.td0", a_.in = &y4; a_.og = y4.g; a_.act = ACT_RELU; a_.yp = &pb["art_a"]);
   RUNS("art.td3", a_.in = &pb["art_a"]; a_.og = y4.g; a_.act = ACT_RELU; a_.yp = &pb["art_b"]);
   launch_planar_mean2(bs.org(pb["art_b"]), pb["art_b"].plane_stride, y4.g, 64, comb + 256, 448, 1, none, sst);
+  g_tl.mark(sst, "S:td_feat");
   const PBuf& dl = pb["delta"];
   if (T > 1) launch_planar_delta(bs.org(y4), y4.plane_stride, y4.g, bs.org(dl), dl.plane_stride, dl.g, 256, sst);
   // (T == 1: the delta map is all zeros — the buffer is never written and keeps its zero initialisation)
   RUNS("art.td0", a_.in = &dl; a_.og = dl.g; a_.act = ACT_RELU; a_.yp = &pb["artd_a"]);
   RUNS("art.td3", a_.in = &pb["artd_a"]; a_.og = dl.g; a_.act = ACT_RELU; a_.yp = &pb["artd_b"]);
   launch_planar_mean2(bs.org(pb["artd_b"]), pb["artd_b"].plane_stride, dl.g, 64, comb + 320, 448, 1, none, sst);
+  g_tl.mark(sst, "S:td_delta");
   // high-frequency branch: Conv3d 3->32 s(1,2,2) on the laplacian pixel rows (Toeplitz K), Conv3d 32->64 s(1,2,2) planar
-  const PBuf& hf = pb["hf_f"];
-  RUNS("art.hf0", a_.in = &xl; a_.og = xl.g; a_.act = ACT_RELU; a_.yp = &hf);
-  RUNS("art.hf3", a_.in = &hf; a_.og = hf.g; a_.act = ACT_RELU; a_.yp = &pb["hf_b"]);
-  launch_planar_mean2(bs.org(pb["hf_b"]), pb["hf_b"].plane_stride, hf.g, 64, comb + 384, 448, 1, none, sst);
+  if (!hf_early) {
+    RUNS("art.hf0", a_.in = &xl; a_.og = xl.g; a_.act = ACT_RELU; a_.yp = &hf);
+    g_tl.mark(sst, "S:hf0");
+    RUNS("art.hf3", a_.in = &hf; a_.og = hf.g; a_.act = ACT_RELU; a_.yp = &pb["hf_b"]);
+    launch_planar_mean2(bs.org(pb["hf_b"]), pb["hf_b"].plane_stride, hf.g, 64, comb + 384, 448, 1, none, sst);
+    g_tl.mark(sst, "S:hf3");
+  }
+  }
   cudaEventRecord(h->ev_join, sst);
   // ---- everything below is the latency-bound tail (small grids): on the caller's stream, or on the tail stream when batches
   // are pipelined (the main stream then goes straight on to the next batch's visual encoder)
@@ -801,8 +875,10 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   RUN("projection.visual_proj", a_.in = &pb["vfeat_p"]; a_.in_lo = &pb["vfeat_p_lo"]; a_.og = gt; a_.yp = &pb["vemb_p"]; a_.yp_lo = &pb["vemb_p_lo"]; a_.y32 = b.f("v_emb"); a_.y32_ld = 256);
   if (audio_early) cudaStreamWaitEvent(st, h->ev_audio, 0);   // audio features (a_feat / afeat_p) are complete
   RUN("projection.audio_proj", a_.in = &pb["afeat_p"]; a_.in_lo = &pb["afeat_p_lo"]; a_.og = P.gta; a_.y32 = b.f("a_emb"); a_.y32_ld = 256);
+  g_tl.mark(st, "T:proj");
   if ((rc = token_path_bf16(b, s))) return rc;
   float* tok = b.f("tok");
+  g_tl.mark(st, "T:tokens");
   // cls = tok[:,0]: no final norm (temporal.py:110-111)
   launch_copy_rows(tok, (int64_t)NT * 256, comb, 448, B, 256, st);
   cudaStreamWaitEvent(st, h->ev_join, 0);   // artifact features (comb[:, 256:448]) are complete
@@ -814,6 +890,8 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   hw.wc = cw("head.fc0"); hw.bc = cb("head.fc0");
   hw.lng = b.W("head.ln.w"); hw.lnb = b.W("head.ln.b"); hw.wo = b.W("head.out.w"); hw.bo = b.W("head.out.b");
   launch_head(comb, hw, logits, B, st);
+  g_tl.mark(st, "T:head");
+  g_tl.dump();
   if (aux) {
     const size_t tb = (size_t)B * T * 256 * sizeof(float);
     if (aux->visual_tokens) cudaMemcpyAsync(aux->visual_tokens, b.f("v_emb"), tb, cudaMemcpyDeviceToDevice, st);

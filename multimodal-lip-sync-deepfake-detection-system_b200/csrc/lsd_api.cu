@@ -67,6 +67,7 @@ extern "C" void lsd_destroy(lsd_handle* h) {
   if (h->bbias) cudaFree(h->bbias);
   if (h->mel_tables) cudaFree(h->mel_tables);
   if (h->prog_arena) cudaFree(h->prog_arena);
+  if (h->tile_ctr_arena) cudaFree(h->tile_ctr_arena);
   if (h->lm_clips) cudaFree(h->lm_clips);
   for (cudaEvent_t e : h->prof.ev) cudaEventDestroy(e);
   if (h->side_stream) cudaStreamDestroy(h->side_stream);

@@ -78,6 +78,10 @@ struct lsd_handle {
   char* prog_arena = nullptr;
   size_t prog_cap = 0, prog_cursor = 0;
   std::unordered_map<uint64_t, const void*> prog_cache;
+  // tile counters of the tcgen05 launches (dynamic tile scheduling): 16 words per layer name, zero whenever the layer is not
+  // running (the last CTA of a launch resets them); launches of one layer are always ordered on one stream
+  unsigned* tile_ctr_arena = nullptr;
+  std::map<std::string, int> tile_ctr_idx;
   // log-mel tables (device): hann[400], cos[400], sin[400], melw[80*32], lo[80], cnt[80]
   void* mel_tables = nullptr;
   const float *d_hann = nullptr, *d_cos = nullptr, *d_sin = nullptr, *d_melw = nullptr;

@@ -25,6 +25,14 @@ namespace lsd {
 
 using namespace umma;
 
+struct F8 { float v[8]; };
+// exact (erf) GELU of 8 values, kept out of line (register ABI) so that the unrolled epilogue step holds one copy of erff
+__device__ __noinline__ F8 gelu8(F8 x) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) x.v[e] = 0.5f * x.v[e] * (1.0f + erff(x.v[e] * 0.70710678118654752f));
+  return x;
+}
+
 __device__ __forceinline__ float uc_act(float v, int act) {
   if (act == ACT_RELU) return fmaxf(v, 0.0f);
   if (act == ACT_GELU) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
@@ -79,6 +87,13 @@ __device__ __forceinline__ void unpack8(const uint4& r, float* v) {
 //   warps 8-15 epilogue (two warps per TMEM lane quarter, each handling half of the columns).
 // Each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the accumulators are double-buffered in TMEM when they fit so
 // that the epilogue of tile i overlaps the main loop of tile i+1, and the smem ring keeps streaming across tile boundaries.
+// Tiles are handed out dynamically: the first tile of a CTA is blockIdx.x, every further one is claimed from a per-slice global
+// counter (p.tile_ctr) by producer warp 0 — one tile ahead, so the atomic's latency hides behind the current tile — and published
+// to the other warps through a small shared-memory queue (tq_*).  A CTA that starts late because another stream's kernel still
+// held its SM then simply takes fewer tiles; with the static stride every concurrent side-stream kernel delayed the whole launch
+// by its own duration.  The last CTA to finish resets the counters for the layer's next launch.
+constexpr int UC_TQ = 8;
+constexpr int UC_CTR_DONE = 8;   // p.tile_ctr[0..7]: claims per Cout slice, [8]: finished CTAs
 constexpr int UC_THREADS = 512;
 constexpr int UC_PROD_WARPS = 4, UC_MMA_WARP0 = 4, UC_MMA_WARPS = 4, UC_EPI_WARP0 = 8, UC_EPI_WARPS = 8;
 // (issuing one cp.async.bulk occupies the issuing thread for ~330 cycles; the cost overlaps across warps and partly across the
@@ -92,6 +107,8 @@ template <bool GENERIC>
 __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_constant__ UmmaConvP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2];
+  __shared__ uint64_t tq_full[UC_TQ], tq_empty[UC_TQ];   // tile queue (dynamic tile scheduling, see below)
+  __shared__ int tq_tile[UC_TQ];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_s[256];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -107,6 +124,8 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
   if (tid == 0) {
     for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], n_issuers); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], n_issuers); mbar_init(&tempty_bar[i], UC_EPI_WARPS); }
+    // queue readers: the producer warps other than warp 0, the MMA issuers, the epilogue warps
+    for (int i = 0; i < UC_TQ; ++i) { mbar_init(&tq_full[i], 1); mbar_init(&tq_empty[i], (uint32_t)(min(UC_PROD_WARPS, p.stages) - 1 + n_issuers + UC_EPI_WARPS)); }
     fence_barrier_init();
   }
   if (warp == UC_EPI_WARP0) { tmem_alloc(&tmem_base_s, p.tmem_cols); tmem_relinquish(); }
@@ -123,6 +142,16 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   if (dbg && tid == 0) p.dbg[1] = clock64();   // prologue done
+  const bool dyn = p.tile_ctr != nullptr;
+  // tile number seq (>= 1) of this CTA, as published by producer warp 0 (whole warp calls this); -1 = no more tiles
+  auto tq_read = [&](int seq) -> int {
+    const int slot = (seq - 1) % UC_TQ;
+    mbar_wait(&tq_full[slot], (uint32_t)((seq - 1) / UC_TQ) & 1u);
+    const int t = *reinterpret_cast<volatile int*>(&tq_tile[slot]);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tq_empty[slot]);
+    return t;
+  };
 
   if (warp < UC_PROD_WARPS) {
     // ------------------------------------------------ producers (every warp runs the loop; lane 0 of each issues its share)
@@ -138,7 +167,10 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
     const uint32_t smem_base = smem_u32(smem);
     const uint64_t slice64 = (uint64_t)slice;
     int k = 0;                                              // global stage counter at the start of the tile
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, k += p.nst_tile) {
+    int seq = 0;
+    for (int tile = blockIdx.x; tile >= 0; k += p.nst_tile) {
+      unsigned claim = 0;
+      if (dyn && warp == 0 && lane == 0) claim = atomicAdd(p.tile_ctr + slice, 1u);   // (consumed after this tile's stages are issued)
       const uint64_t p0_bytes = (uint64_t)tile * (uint64_t)S * 16u;
       // first stage of this tile owned by this warp: si = (warp - k) mod 4
       for (int si = ((warp - k) % npw + npw) % npw; si < p.nst_tile; si += npw) {
@@ -165,6 +197,25 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
         __syncwarp();
         if (dbg && lane == 0 && tile == (int)blockIdx.x && si < 8) p.dbg[56 + si] = clock64();   // copies issued
       }
+      // next tile
+      ++seq;
+      if (!dyn) {
+        tile += gridDim.x;
+        if (tile >= num_tiles) tile = -1;
+      } else if (warp == 0) {
+        int nt = 0;
+        if (lane == 0) {
+          nt = (int)gridDim.x + (int)claim;
+          if (nt >= num_tiles) nt = -1;
+          const int slot = (seq - 1) % UC_TQ;
+          mbar_wait(&tq_empty[slot], ((uint32_t)((seq - 1) / UC_TQ) & 1u) ^ 1u);
+          *reinterpret_cast<volatile int*>(&tq_tile[slot]) = nt;
+          mbar_arrive(&tq_full[slot]);
+        }
+        tile = __shfl_sync(0xffffffffu, nt, 0);
+      } else {
+        tile = tq_read(seq);
+      }
     }
   } else if (warp < UC_MMA_WARP0 + UC_MMA_WARPS) {
     // ------------------------------------------------ MMA issuers (whole warp runs the loop; one elected lane issues)
@@ -181,7 +232,9 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
     const uint32_t leader = elect_one() ? 1u : 0u;                                 // the lane that issues (fixed for the whole kernel)
     int stage = 0, lt = 0, dbg_it = 0;
     uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+    // (the loop must stay provably warp-uniform for the descriptor arithmetic to live in uniform registers: "another tile?" is
+    // taken from a warp vote, which ptxas treats as uniform, not from the per-thread value read from the queue)
+    for (int tile = blockIdx.x; tile < num_tiles; ++lt, tile = dyn ? (__any_sync(0xffffffffu, tq_read(lt) >= 0) ? 0 : num_tiles) : tile + (int)gridDim.x) {
       const int buf = p.nbuf == 2 ? (lt & 1) : 0;
       const uint32_t use = p.nbuf == 2 ? ((uint32_t)lt >> 1) : (uint32_t)lt;   // how many times this buffer was used before
       const uint32_t tb = tmem_base + (uint32_t)buf * buf_cols + (uint32_t)(mt_lo * p.Cout);
@@ -251,7 +304,7 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
     const float act_lo = p.act == ACT_RELU ? 0.0f : -INFINITY;   // ReLU as one FMNMX; GELU (token GEMMs only) branches once per chunk
     const int rowt = quarter * 32 + lane;
     int lt = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+    for (int tile = blockIdx.x; tile >= 0; ++lt, tile = dyn ? tq_read(lt) : (tile + (int)gridDim.x < num_tiles ? tile + (int)gridDim.x : -1)) {
       const int buf = p.nbuf == 2 ? (lt & 1) : 0;
       const uint32_t use = p.nbuf == 2 ? ((uint32_t)lt >> 1) : (uint32_t)lt;
       const uint32_t tb = tmem_base + (uint32_t)buf * buf_cols + ((uint32_t)(quarter * 32) << 16);
@@ -327,70 +380,79 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
             }
           }
         } else {
+        // generic path (Cout % 64 == 0, at most one kind of residual — checked on the host): 32 columns per step.  One 32-column
+        // TMEM load; the step's residuals (bf16 hi [+ lo] planes, or fp32 rows) are fetched before the single wait, so the
+        // global-load latency and the TMEM round trip are paid once per step instead of once per 8 columns.
+        const float* r32row = p.res32 ? p.res32 + (outer * p.g.W + w) * p.res32_ld + ch0 : nullptr;
+        float* y32row = p.y32 ? p.y32 + (outer * p.y32_outer_stride + w + p.y32_row_off) * p.y32_ld + ch0 : nullptr;
+        const bool use_res = valid && p.res != nullptr, use_lo = use_res && p.res_lo != nullptr, use_r32 = valid && p.res32 != nullptr;
 #pragma unroll 1
         for (int c0 = cbeg; c0 < cend; c0 += 32) {
-          const int nq = min(4, (cend - c0) >> 3);
-          // residual prefetch for the whole chunk: the global-load latency is paid once, not once per 8-column step
-          uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = r0;
-          if (valid && p.res) {
-            const __nv_bfloat16* rp = p.res + (int64_t)((ch0 + c0) >> 3) * p.res_plane_stride + P * 8;
-            r0 = *reinterpret_cast<const uint4*>(rp);
-            if (nq > 1) r1 = *reinterpret_cast<const uint4*>(rp + p.res_plane_stride);
-            if (nq > 2) r2 = *reinterpret_cast<const uint4*>(rp + 2 * p.res_plane_stride);
-            if (nq > 3) r3 = *reinterpret_cast<const uint4*>(rp + 3 * p.res_plane_stride);
+          float v[32];
+          uint4 pre[8];
+          tmem_ld32(tb + (uint32_t)(m * p.Cout + c0), v);
+          if (use_res) {
+            const int64_t roff = (int64_t)((ch0 + c0) >> 3) * p.res_plane_stride + P * 8;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pre[q] = *reinterpret_cast<const uint4*>(p.res + roff + (int64_t)q * p.res_plane_stride);
+            if (use_lo) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) pre[4 + q] = *reinterpret_cast<const uint4*>(p.res_lo + roff + (int64_t)q * p.res_plane_stride);
+            }
+          } else if (use_r32) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) pre[q] = *reinterpret_cast<const uint4*>(r32row + c0 + 4 * q);
           }
-#pragma unroll 1
-          for (int q = 0; q < nq; ++q) {   // 8 columns per step keeps the epilogue code small (instruction cache)
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
             const int c = c0 + 8 * q;
-            float v[8];
-            tmem_ld8(tb + (uint32_t)(m * p.Cout + c), v);
-            tmem_ld_wait();
+            F8 x;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x.v[e] = v[8 * q + e];
             if (valid) {
               const float4 b0 = *reinterpret_cast<const float4*>(&bias_s[c]);
               const float4 b1 = *reinterpret_cast<const float4*>(&bias_s[c + 4]);
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-              if (p.res) {
+              x.v[0] += b0.x; x.v[1] += b0.y; x.v[2] += b0.z; x.v[3] += b0.w; x.v[4] += b1.x; x.v[5] += b1.y; x.v[6] += b1.z; x.v[7] += b1.w;
+              if (use_res) {
                 float f[8];
-                const uint4 rr = q == 0 ? r0 : (q == 1 ? r1 : (q == 2 ? r2 : r3));
-                unpack8(rr, f);
+                unpack8(pre[q], f);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] += f[e];
-                if (p.res_lo) {
-                  unpack8(*reinterpret_cast<const uint4*>(p.res_lo + (int64_t)((ch0 + c) >> 3) * p.res_plane_stride + P * 8), f);
+                for (int e = 0; e < 8; ++e) x.v[e] += f[e];
+                if (use_lo) {
+                  unpack8(pre[4 + q], f);
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) v[e] += f[e];
+                  for (int e = 0; e < 8; ++e) x.v[e] += f[e];
                 }
-              }
-              if (p.res32) {
-                const float4* r4 = reinterpret_cast<const float4*>(p.res32 + (outer * p.g.W + w) * p.res32_ld + ch0 + c);
-                const float4 q0 = r4[0], q1 = r4[1];
-                v[0] += q0.x; v[1] += q0.y; v[2] += q0.z; v[3] += q0.w; v[4] += q1.x; v[5] += q1.y; v[6] += q1.z; v[7] += q1.w;
+              } else if (use_r32) {
+                const uint4 q0 = pre[2 * q], q1 = pre[2 * q + 1];
+                x.v[0] += __uint_as_float(q0.x); x.v[1] += __uint_as_float(q0.y); x.v[2] += __uint_as_float(q0.z); x.v[3] += __uint_as_float(q0.w);
+                x.v[4] += __uint_as_float(q1.x); x.v[5] += __uint_as_float(q1.y); x.v[6] += __uint_as_float(q1.z); x.v[7] += __uint_as_float(q1.w);
               }
               if (p.act == ACT_GELU) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = 0.5f * v[e] * (1.0f + erff(v[e] * 0.70710678118654752f));
+                x = gelu8(x);   // (out of line: 32 inlined erff per step would not fit the instruction cache)
               } else {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], act_lo);
+                for (int e = 0; e < 8; ++e) x.v[e] = fmaxf(x.v[e], act_lo);
               }
-              if (p.y32) {
-                float4* o = reinterpret_cast<float4*>(p.y32 + (outer * p.y32_outer_stride + w + p.y32_row_off) * p.y32_ld + ch0 + c);
-                o[0] = make_float4(v[0], v[1], v[2], v[3]);
-                o[1] = make_float4(v[4], v[5], v[6], v[7]);
+              if (y32row) {
+                float4* o = reinterpret_cast<float4*>(y32row + c);
+                o[0] = make_float4(x.v[0], x.v[1], x.v[2], x.v[3]);
+                o[1] = make_float4(x.v[4], x.v[5], x.v[6], x.v[7]);
               }
             } else {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = 0.0f;
+              for (int e = 0; e < 8; ++e) x.v[e] = 0.0f;
             }
             if (store_planar) {
-              const uint4 hi4 = pack8(v);
+              const uint4 hi4 = pack8(x.v);
               const int64_t off = (int64_t)((ch0 + c) >> 3) * p.y_plane_stride + dst;
               *reinterpret_cast<uint4*>(p.y + off) = hi4;
               if (p.ylo) {
                 float hf[8];
                 unpack8(hi4, hf);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) hf[e] = v[e] - hf[e];
+                for (int e = 0; e < 8; ++e) hf[e] = x.v[e] - hf[e];
                 *reinterpret_cast<uint4*>(p.ylo + off) = pack8(hf);
               }
             }
@@ -409,6 +471,16 @@ done:
   tc_fence_before();
   __syncthreads();
   if (warp == UC_EPI_WARP0) tmem_dealloc(tmem_base, p.tmem_cols);
+  if (dyn && tid == 0) {
+    // every claim of this CTA has completed (its queue saw the end marker): the last CTA of the launch re-arms the counters
+    __threadfence();
+    const unsigned n_ctas = gridDim.x * gridDim.y;
+    if (atomicAdd(p.tile_ctr + UC_CTR_DONE, 1u) == n_ctas - 1) {
+      for (unsigned y = 0; y < gridDim.y; ++y) p.tile_ctr[y] = 0;
+      p.tile_ctr[UC_CTR_DONE] = 0;
+      __threadfence();
+    }
+  }
   if (dbg && tid == 0) { p.dbg[6] = clock64(); p.dbg[7] = num_tiles; }
 }
 
@@ -462,6 +534,7 @@ void launch_umma_conv(const UmmaConvP& p, int n_slices, cudaStream_t s, int max_
     attr_set = true;
   }
   if (2 * p.kpack + p.kpack > 32) { fprintf(stderr, "umma_conv: kpack %d exceeds the issuer count\n", p.kpack); abort(); }
+  if (p.res && p.res32) { fprintf(stderr, "umma_conv: bf16 and fp32 residuals are mutually exclusive\n"); abort(); }
   const int S = p.MT * 128;
   const int tiles = (int)((p.g.P_total + S - 1) / S);
   static int num_sms = 0;
@@ -471,6 +544,7 @@ void launch_umma_conv(const UmmaConvP& p, int n_slices, cudaStream_t s, int max_
   int gx = (budget + n_slices - 1) / n_slices;
   gx = gx < 1 ? 1 : (gx > tiles ? tiles : gx);
   const bool generic = p.y32 || p.res32 || p.ylo || p.res_lo || p.act == ACT_GELU || p.y_mode == UC_Y_NONE || (p.Cout & 31);   // (the lean epilogue works in 32-column steps)
+  if (generic && (p.Cout & 63)) { fprintf(stderr, "umma_conv: the generic epilogue needs Cout %% 64 == 0 (got %d)\n", p.Cout); abort(); }
   if (generic) umma_conv_kernel<true><<<dim3(gx, n_slices), UC_THREADS, umma_conv_smem_bytes(p), s>>>(p);
   else umma_conv_kernel<false><<<dim3(gx, n_slices), UC_THREADS, umma_conv_smem_bytes(p), s>>>(p);
   count_launch();

@@ -104,6 +104,7 @@ struct UmmaConvP {
   int issuers;                // MMA-issuing warps (1, 2 or 4; divides MT): each issues MT / issuers M-tiles per tap
   int nbuf;                   // TMEM accumulator buffers: 2 = epilogue overlaps the next tile, 1 = all 512 columns for one tile
   long long* dbg;             // optional: CTA (0,0) writes clock64 phase timestamps (debug builds of the bench only)
+  unsigned* tile_ctr;         // device memory, 16 words, zero between launches: dynamic tile scheduling (nullptr: static stride)
   const UcStageDesc* prog;    // device memory: the stage program (nst_tile entries)
   int nst_tile;               // ring stages per tile (sum over groups of ceil(k16 / kpack) * bands): length of the stage program
   int skip;                   // debug (LSD_UMMA_SKIP): bit 0 = no A copies, bit 1 = no W copies — timing experiments only
