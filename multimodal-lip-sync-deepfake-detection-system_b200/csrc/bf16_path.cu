@@ -778,7 +778,7 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   }
   cudaStream_t sst = h->side_stream;
   BCtx bs{h, ws, &P, sst};
-  bs.max_ctas = (h->num_sms * 2) / 3;   // measured at B=64: 74 / 92 / 110 / 128 / 148 SMs -> 3.58 / 3.49 / 3.49 / 3.53 / 3.61 ms per step
+  bs.max_ctas = h->num_sms / 2;   // measured at B=64 (re-tuned after the epilogue rewrite): 60 / 74 / 98 / 120 / 148 SMs -> 3.53 / 3.30 / 3.36 / 3.37 / 3.43 ms per step
   if (const char* e = getenv("LSD_SIDE_CTAS")) bs.max_ctas = atoi(e);   // tuning knob: SMs the side stream may occupy
   // ---- audio encoder (independent of the video): on the side stream from the very start, so that its latency-bound chain of
   // small launches hides behind the visual encoder instead of heading the tail

@@ -155,8 +155,6 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
 
   if (warp < UC_PROD_WARPS) {
     // ------------------------------------------------ producers (every warp runs the loop; lane 0 of each issues its share)
-    int stage = 0, dbg_it = 0;
-    uint32_t ph = 0;
     // Stage k of the CTA's stream (k counts across tiles) belongs to producer warp k % npw: the per-stage work (descriptor reads,
     // address arithmetic, barrier wait, ~330-cycle bulk-copy issue) then overlaps across the four warps.  Lane l issues the
     // stage's copy l, all issuing lanes in ONE converged cp.async.bulk.
