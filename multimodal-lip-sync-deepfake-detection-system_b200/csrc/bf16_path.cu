@@ -780,6 +780,8 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   BCtx bs{h, ws, &P, sst};
   bs.max_ctas = h->num_sms / 2;   // measured at B=64 (re-tuned after the epilogue rewrite): 60 / 74 / 98 / 120 / 148 SMs -> 3.53 / 3.30 / 3.36 / 3.37 / 3.43 ms per step
   if (const char* e = getenv("LSD_SIDE_CTAS")) bs.max_ctas = atoi(e);   // tuning knob: SMs the side stream may occupy
+  int art_ctas = bs.max_ctas;                                           // ... and during the artifact branch (tail phase)
+  if (const char* e = getenv("LSD_ART_CTAS")) art_ctas = atoi(e);
   // ---- audio encoder (independent of the video): on the side stream from the very start, so that its latency-bound chain of
   // small launches hides behind the visual encoder instead of heading the tail
   const bool audio_early = getenv("LSD_AUDIO_LATE") == nullptr;
@@ -836,6 +838,7 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   cudaEventRecord(h->ev_fork, st);
   cudaStreamWaitEvent(sst, h->ev_fork, 0);
   const bool skip_art = getenv("LSD_SKIP_ART") != nullptr;   // timing experiment only (garbage logits)
+  bs.max_ctas = art_ctas;
   if (!skip_art) {
   RUNS("art.td0", a_.in = &y4; a_.og = y4.g; a_.act = ACT_RELU; a_.yp = &pb["art_a"]);
   RUNS("art.td3", a_.in = &pb["art_a"]; a_.og = y4.g; a_.act = ACT_RELU; a_.yp = &pb["art_b"]);

@@ -218,8 +218,11 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
   } else if (warp < UC_MMA_WARP0 + UC_MMA_WARPS) {
     // ------------------------------------------------ MMA issuers (whole warp runs the loop; one elected lane issues)
     if (warp - UC_MMA_WARP0 >= n_issuers) goto done;
+    // (the warp index as a value ptxas knows to be warp-uniform: everything derived from it — TMEM column, M-tile offset of the A
+    // descriptor — then lives in uniform registers; derived from threadIdx.x it cost an R2UR.BROADCAST per operand per MMA)
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
     const int mt_n = p.MT / n_issuers;                                               // this warp's M-tiles: [mt_lo, mt_lo + mt_n)
-    const int mt_lo = (warp - UC_MMA_WARP0) * mt_n;
+    const int mt_lo = (warp_u - UC_MMA_WARP0) * mt_n;
     // One thread feeds the tensor core: keep the per-instruction work to a few 32-bit adds.  A descriptor is
     // (constant high part) | (start address >> 4); tap / M-tile / K-chunk offsets are added in 16-byte units.
     const uint32_t idesc = idesc_bf16(128, p.Cout);
@@ -1165,18 +1168,9 @@ __global__ void planar_mean2_kernel(const __nv_bfloat16* __restrict__ x, int64_t
   const int row = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
   const int count = mode == 1 ? g.T * g.H * g.W : (mode == 0 ? g.H * g.W : g.H);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int i = tid; i < count; i += blockDim.x) {
-    int n, t, h, w;
-    if (mode == 2) { n = row / g.W; w = row % g.W; t = 0; h = i; }
-    else {
-      n = mode == 1 ? row : row / g.T;
-      w = i % g.W;
-      const int r = i / g.W;
-      h = r % g.H;
-      t = (mode == 1 ? 0 : row % g.T) + r / g.H;
-    }
+  auto add = [&](int64_t pos) {
     float f[8];
-    const int64_t src = (int64_t)chunk * plane_stride + uc_flat(g, n, t, h, w) * 8;
+    const int64_t src = (int64_t)chunk * plane_stride + pos * 8;
     unpack8(*reinterpret_cast<const uint4*>(x + src), f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] += f[e];
@@ -1184,6 +1178,21 @@ __global__ void planar_mean2_kernel(const __nv_bfloat16* __restrict__ x, int64_t
       unpack8(*reinterpret_cast<const uint4*>(xlo + src), f);
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] += f[e];
+    }
+  };
+  if (mode == 2) {
+    const int n = row / g.W, w = row % g.W;
+    for (int i = tid; i < count; i += blockDim.x) add(uc_flat(g, n, 0, i, w));
+  } else {
+    // one image row (t, h) per warp and step, lanes along w: the positions of a row are contiguous, and the per-element
+    // divisions of a flat index (four per 16-byte load) no longer bound the kernel
+    const int n = mode == 1 ? row : row / g.T, t0 = mode == 1 ? 0 : row % g.T;
+    const int n_rows = (mode == 1 ? g.T : 1) * g.H;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    for (int rr = warp; rr < n_rows; rr += nwarps) {
+      const int tt = rr / g.H, h = rr - tt * g.H;
+      const int64_t base = uc_flat(g, n, t0 + tt, h, 0);
+      for (int w = lane; w < g.W; w += 32) add(base + w);
     }
   }
 #pragma unroll
