@@ -380,7 +380,10 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
   // accumulator buffers so that the epilogue overlaps the next tile.  MT shrinks while the tiles cannot fill the SMs.
   const int mt2 = std::max(1, std::min(4, 256 / L.ntile));   // M-tiles per tile with two accumulator buffers
   p.MT = std::max(1, std::min(4, 512 / L.ntile));             // ... with one
-  while (p.MT > 1 && ((og.P_total + p.MT * 128 - 1) / (p.MT * 128)) * slices < c.h->num_sms) p.MT /= 2;
+  // (the CTAs this launch may use: side-stream launches are capped, and a cap of 74 with 265 one-M-tile tiles meant four waves of
+  // single-issuer tiles where two waves of two-M-tile tiles do — the artifact convolutions on the 3x3 maps)
+  const int cta_budget = (c.max_ctas > 0 && c.max_ctas < c.h->num_sms) ? c.max_ctas : c.h->num_sms;
+  while (p.MT > 1 && ((og.P_total + p.MT * 128 - 1) / (p.MT * 128)) * slices < cta_budget) p.MT /= 2;
   p.nbuf = (p.MT <= mt2 && 2 * p.MT * L.ntile <= 512) ? 2 : 1;  // single buffering only when it buys a larger tile
   if (const char* e = getenv("LSD_UMMA_NBUF")) {               // tuning knob
     const int v = atoi(e);
@@ -782,12 +785,15 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   if (const char* e = getenv("LSD_SIDE_CTAS")) bs.max_ctas = atoi(e);   // tuning knob: SMs the side stream may occupy
   int art_ctas = bs.max_ctas;                                           // ... and during the artifact branch (tail phase)
   if (const char* e = getenv("LSD_ART_CTAS")) art_ctas = atoi(e);
+  // LSD_MAIN_CTAS (tuning knob): cap the visual-encoder launches and give the audio encoder exactly the SMs they leave free
+  if (const char* e = getenv("LSD_MAIN_CTAS")) { b.max_ctas = atoi(e); bs.max_ctas = h->num_sms - b.max_ctas; }
   // ---- audio encoder (independent of the video): on the side stream from the very start, so that its latency-bound chain of
   // small launches hides behind the visual encoder instead of heading the tail
   const bool audio_early = getenv("LSD_AUDIO_LATE") == nullptr;
   g_tl.on = getenv("LSD_TIMELINE") != nullptr;
   g_tl.mark(st, "start");
-  if (audio_early) {
+  const bool audio_after_rows = getenv("LSD_AUDIO_AFTER_ROWS") != nullptr;   // tuning knob, see below
+  if (audio_early && !audio_after_rows) {
     cudaEventRecord(h->ev_start, st);
     cudaStreamWaitEvent(sst, h->ev_start, 0);
     if ((rc = audio_encoder_bf16(bs, s, inputs_ready, audio, adt))) return rc;
@@ -802,6 +808,16 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   else if (inputs_ready) launch_video_rows(b.f("vid"), LSD_F32, LSD_NDHWC, lapw, b.org(xs), b.org(xl), xs.set_stride, xs.g, s.H, s.W, st);
   else launch_video_rows(video, vdt, vlayout, lapw, b.org(xs), b.org(xl), xs.set_stride, xs.g, s.H, s.W, st);
   g_tl.mark(st, "M:video_rows");
+  // (LSD_AUDIO_AFTER_ROWS=1 forks the audio encoder after video_rows instead: that kernel then takes 158 us instead of 262 — it
+  // walks its tiles with a static stride, so side-stream kernels holding SMs at its start delay it — but the audio encoder's chain of
+  // 15 launches, which only gets SMs at the main stream's kernel boundaries, then ends after the visual encoder: no net gain)
+  if (audio_early && audio_after_rows) {
+    cudaEventRecord(h->ev_start, st);
+    cudaStreamWaitEvent(sst, h->ev_start, 0);
+    if ((rc = audio_encoder_bf16(bs, s, inputs_ready, audio, adt))) return rc;
+    g_tl.mark(sst, "S:audio_enc");
+    cudaEventRecord(h->ev_audio, sst);
+  }
   // The high-frequency branch only needs the laplacian rows: LSD_HF_EARLY=1 (tuning knob) runs it on the side stream right after the
   // audio encoder, next to the visual encoder, instead of in the tail.
   const bool hf_early = getenv("LSD_HF_EARLY") != nullptr;
@@ -829,6 +845,7 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   g_tl.mark(st, "M:layer3");
   if ((rc = res_stage_umma(b, "visual_encoder.layer4", pb["y3"], pb["l4a"], pb["y4"], true, UC_Y_PLAIN))) return rc;
   g_tl.mark(st, "M:layer4");
+  b.max_ctas = 0;
   const PBuf& y4 = pb["y4"];
   // spatial mean -> visual tokens (fp32 stage + planar GEMM input)
   launch_planar_mean2(b.org(y4), y4.plane_stride, y4.g, 256, b.f("v_feat"), 256, 0, pout(b, pb["vfeat_p"], &pb["vfeat_p_lo"]), st);
