@@ -395,3 +395,24 @@ def test_bf16_odd_shapes_against_oracle(model, seed0_sd, shape):
     out_u8 = model(u8.permute(0, 2, 3, 4, 1).contiguous().cuda(), audio.cuda(), video_layout="NDHWC").float().cpu()
     ref_u8 = orc.forward(seed0_sd, u8.float() / 255.0, audio)
     assert float((out_u8 - ref_u8).abs().max()) <= BF16_ABS
+
+
+def test_scheduling_knobs_do_not_change_logits(model):
+    """The scheduling variants of the tcgen05 kernel (dynamic tile claims, side-stream SM share, artifact branch placement, audio
+    fork point) only move work between CTAs and streams: logits must be bit-identical to the default schedule.  The knobs are read
+    from the environment inside the library (the first one once per process), so each variant runs in a fresh interpreter."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import torch, hashlib, lipsync_b200 as lb\n"
+            "m = lb.LipSyncModel(); m.load_state_dict(lb.make_synthetic_state_dict(0)); m.to('cuda:0').eval(); m.compute_precision = 'bf16'\n"
+            "v, a = lb.synthetic_windows(33, 5)\n"
+            "out = m(v.cuda(), a.cuda()).float().cpu()\n"
+            "print('DIGEST', hashlib.sha256(out.numpy().tobytes()).hexdigest())\n") % root
+    digests = {}
+    for name, env in {"default": {}, "dynamic_tiles": {"LSD_UMMA_DYNAMIC": "1"}, "side_all_sms": {"LSD_SIDE_CTAS": "148"},
+                      "hf_early": {"LSD_HF_EARLY": "1"}, "audio_after_rows": {"LSD_AUDIO_AFTER_ROWS": "1"}}.items():
+        r = subprocess.run([sys.executable, "-c", code], env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, (name, r.stderr[-2000:])
+        digests[name] = [l for l in r.stdout.splitlines() if l.startswith("DIGEST")][-1]
+    assert len(set(digests.values())) == 1, digests
