@@ -378,8 +378,11 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
   // the fills per MMA are minimised: wide layers (>= 128 columns) give all 512 TMEM columns to one tile (more M-tiles per
   // weight stage; their K loop is so long that the un-overlapped epilogue is a few %), narrow layers keep two
   // accumulator buffers so that the epilogue overlaps the next tile.  MT shrinks while the tiles cannot fill the SMs.
-  const int mt2 = std::max(1, std::min(4, 256 / L.ntile));   // M-tiles per tile with two accumulator buffers
-  p.MT = std::max(1, std::min(4, 512 / L.ntile));             // ... with one
+  // (32-column layers — the hf front convolution — take 8 M-tiles: their stages carry one MMA per M-tile, so an issuing warp's
+  // per-stage cost, ~300 cycles of barrier / descriptor bookkeeping, is what bounds them; two M-tiles per issuer halve it)
+  const int mt_cap = L.ntile <= 32 ? 8 : 4;
+  const int mt2 = std::max(1, std::min(mt_cap, 256 / L.ntile));   // M-tiles per tile with two accumulator buffers
+  p.MT = std::max(1, std::min(mt_cap, 512 / L.ntile));             // ... with one
   // (the CTAs this launch may use: side-stream launches are capped, and a cap of 74 with 265 one-M-tile tiles meant four waves of
   // single-issuer tiles where two waves of two-M-tile tiles do — the artifact convolutions on the 3x3 maps)
   const int cta_budget = (c.max_ctas > 0 && c.max_ctas < c.h->num_sms) ? c.max_ctas : c.h->num_sms;
@@ -393,8 +396,8 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
   // One issue-loop iteration (one tap: descriptor arithmetic + R2UR moves + the MMAs) costs an issuing warp 150-260 cycles,
   // more than the tensor time of the MMAs it carries for narrow tiles, so the M-tiles of a tap are spread over as many
   // issuing warps as there are M-tiles.
-  p.issuers = p.MT;   // (measured: one issuer for MT = 4 is 6-15 % slower than two on every layer)
-  if (const char* e = getenv("LSD_UMMA_ISSUERS")) { const int v = atoi(e); if (v >= 1 && v <= p.MT && p.MT % v == 0) p.issuers = v; }   // tuning knob
+  p.issuers = std::min(p.MT, 4);   // (measured: one issuer for MT = 4 is 6-15 % slower than two on every layer)
+  if (const char* e = getenv("LSD_UMMA_ISSUERS")) { const int v = atoi(e); if (v >= 1 && v <= 4 && v <= p.MT && p.MT % v == 0 && p.MT / v <= 4) p.issuers = v; }   // tuning knob
   uint32_t cols = 32;
   while ((int)cols < p.nbuf * p.MT * L.ntile) cols *= 2;
   p.tmem_cols = cols;
@@ -562,6 +565,13 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
     if ((rc = run_umma(b, name, a_))) return rc;  \
   } while (0)
 
+#define RUNC(ctx, name, ...)                        \
+  do {                                              \
+    UArgs a_;                                       \
+    __VA_ARGS__;                                    \
+    if ((rc = run_umma(ctx, name, a_))) return rc;  \
+  } while (0)
+
 #define RUNS(name, ...)                            \
   do {                                             \
     UArgs a_;                                      \
@@ -709,27 +719,48 @@ static int token_path_bf16(const BCtx& b, const Shapes& s) {
   const int B = s.B, T = s.T, TA = s.A4, NT = T + 1;
   const UcGeom gt = P.gt;
   int rc = 0;
+  // Independent pieces run side by side on two helper streams (LSD_TOK_SERIAL=1 keeps everything on one stream): the token path is
+  // a chain of latency-bound launches, each far too small to fill the SMs it gets.
+  lsd_handle* h = b.h;
+  const bool par = getenv("LSD_TOK_SERIAL") == nullptr;
+  if (par && !h->tok_stream[0]) {
+    for (int i = 0; i < 2; ++i)
+      if (cudaStreamCreateWithFlags(&h->tok_stream[i], cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&h->ev_tok_join[i], cudaEventDisableTiming) != cudaSuccess)
+        return lsd_fail(h, LSD_ERR_CUDA, "token helper stream creation failed");
+    if (cudaEventCreateWithFlags(&h->ev_tok_fork, cudaEventDisableTiming) != cudaSuccess) return lsd_fail(h, LSD_ERR_CUDA, "token helper event creation failed");
+  }
+  BCtx b1 = b, b2 = b;                      // helper-stream contexts (same workspace and plan)
+  if (par) { b1.st = h->tok_stream[0]; b2.st = h->tok_stream[1]; }
+  auto fork = [&](int n) { if (par) { cudaEventRecord(h->ev_tok_fork, st); for (int i = 0; i < n; ++i) cudaStreamWaitEvent(h->tok_stream[i], h->ev_tok_fork, 0); } };
+  auto join = [&](int n) { if (par) for (int i = 0; i < n; ++i) { cudaEventRecord(h->ev_tok_join[i], h->tok_stream[i]); cudaStreamWaitEvent(st, h->ev_tok_join[i], 0); } };
   // ---- cross-modal attention + gated fusion (fusion_module.py:54-87)
-  launch_lerp_tokens_p(b.f("a_emb"), b.f("a_int"), B, TA, T, 256, pout(b, pbf("aint_p"), &pbf("aint_p_lo")), st);
   float *pv = b.f("proj_v"), *pa = b.f("proj_a"), *gi = b.f("gate_in");
+  fork(1);
+  launch_lerp_tokens_p(b.f("a_emb"), b.f("a_int"), B, TA, T, 256, pout(b, pbf("aint_p"), &pbf("aint_p_lo")), b1.st);
+  RUNC(b1, "cross.in_a", a_.in = &pbf("aint_p"); a_.in_lo = &pbf("aint_p_lo"); a_.og = gt; a_.y32 = pa; a_.y32_ld = 768);
   RUN("cross.in_v", a_.in = &pbf("vemb_p"); a_.in_lo = &pbf("vemb_p_lo"); a_.og = gt; a_.y32 = pv; a_.y32_ld = 768);
-  RUN("cross.in_a", a_.in = &pbf("aint_p"); a_.in_lo = &pbf("aint_p_lo"); a_.og = gt; a_.y32 = pa; a_.y32_ld = 768);
+  join(1);
+  fork(1);
   launch_mha_core_p(pv, 768, pa + 256, 768, pa + 512, 768, B, T, T, 8, pout(b, pbf("att1_p"), &pbf("att1_p_lo")), st);  // v2a: Q=v, K/V=a
-  launch_mha_core_p(pa, 768, pv + 256, 768, pv + 512, 768, B, T, T, 8, pout(b, pbf("att2_p"), &pbf("att2_p_lo")), st);  // a2v: Q=a, K/V=v
   RUN("cross.v2a.out", a_.in = &pbf("att1_p"); a_.in_lo = &pbf("att1_p_lo"); a_.og = gt; a_.res32 = b.f("v_emb"); a_.res32_ld = 256; a_.y32 = gi; a_.y32_ld = 512;
       a_.yp = &pbf("gatein_p"); a_.yp_lo = &pbf("gatein_p_lo"));
-  RUN("cross.a2v.out", a_.in = &pbf("att2_p"); a_.in_lo = &pbf("att2_p_lo"); a_.og = gt; a_.res32 = b.f("a_int"); a_.res32_ld = 256; a_.y32 = gi + 256; a_.y32_ld = 512;
+  launch_mha_core_p(pa, 768, pv + 256, 768, pv + 512, 768, B, T, T, 8, pout(b, pbf("att2_p"), &pbf("att2_p_lo")), b1.st);  // a2v: Q=a, K/V=v
+  RUNC(b1, "cross.a2v.out", a_.in = &pbf("att2_p"); a_.in_lo = &pbf("att2_p_lo"); a_.og = gt; a_.res32 = b.f("a_int"); a_.res32_ld = 256; a_.y32 = gi + 256; a_.y32_ld = 512;
       a_.yp = &pbf("gatein_p"); a_.yp_lo = &pbf("gatein_p_lo"); a_.y_plane_off = 32);
+  join(1);
   RUN("cross.gate0", a_.in = &pbf("gatein_p"); a_.in_lo = &pbf("gatein_p_lo"); a_.og = gt; a_.act = ACT_GELU; a_.y32 = b.f("gate_h"); a_.y32_ld = 256);
   launch_gate_blend_p(b.f("gate_h"), b.W("cross.gate2.w"), b.W("cross.gate2.b"), gi, 512, gi + 256, 512, B * T, 256, pout(b, pbf("blend_p"), &pbf("blend_p_lo")), st);
   RUN("cross.fuse", a_.in = &pbf("blend_p"); a_.in_lo = &pbf("blend_p_lo"); a_.og = gt; a_.act = ACT_RELU; a_.y32 = b.f("fused"); a_.y32_ld = 256; a_.yp = &pbf("fused_p"); a_.yp_lo = &pbf("fused_p_lo"));
   // ---- temporal transformer (temporal.py:79-111)
   g_tl.mark(st, "T:cross");
-  RUN("temporal.branch_k3", a_.in = &pbf("fused_p"); a_.in_lo = &pbf("fused_p_lo"); a_.og = gt; a_.act = ACT_GELU; a_.yp = &pbf("mscat_p"); a_.yp_lo = &pbf("mscat_p_lo"); a_.y_plane_off = 0);
-  RUN("temporal.branch_k5", a_.in = &pbf("fused_p"); a_.in_lo = &pbf("fused_p_lo"); a_.og = gt; a_.act = ACT_GELU; a_.yp = &pbf("mscat_p"); a_.yp_lo = &pbf("mscat_p_lo"); a_.y_plane_off = 32);
-  RUN("temporal.branch_k7", a_.in = &pbf("fused_p"); a_.in_lo = &pbf("fused_p_lo"); a_.og = gt; a_.act = ACT_GELU; a_.yp = &pbf("mscat_p"); a_.yp_lo = &pbf("mscat_p_lo"); a_.y_plane_off = 64);
   float* tok = b.f("tok");
-  launch_set_cls(b.W("temporal.cls"), tok, B, NT, 256, st);
+  fork(2);
+  RUNC(b1, "temporal.branch_k5", a_.in = &pbf("fused_p"); a_.in_lo = &pbf("fused_p_lo"); a_.og = gt; a_.act = ACT_GELU; a_.yp = &pbf("mscat_p"); a_.yp_lo = &pbf("mscat_p_lo"); a_.y_plane_off = 32);
+  RUNC(b2, "temporal.branch_k3", a_.in = &pbf("fused_p"); a_.in_lo = &pbf("fused_p_lo"); a_.og = gt; a_.act = ACT_GELU; a_.yp = &pbf("mscat_p"); a_.yp_lo = &pbf("mscat_p_lo"); a_.y_plane_off = 0);
+  launch_set_cls(b.W("temporal.cls"), tok, B, NT, 256, b2.st);
+  RUN("temporal.branch_k7", a_.in = &pbf("fused_p"); a_.in_lo = &pbf("fused_p_lo"); a_.og = gt; a_.act = ACT_GELU; a_.yp = &pbf("mscat_p"); a_.yp_lo = &pbf("mscat_p_lo"); a_.y_plane_off = 64);
+  join(2);
   // pre_scale_proj + residual, written straight into token rows 1..T of each window
   RUN("temporal.pre_scale_proj", a_.in = &pbf("mscat_p"); a_.in_lo = &pbf("mscat_p_lo"); a_.og = gt; a_.res32 = b.f("fused"); a_.res32_ld = 256; a_.y32 = tok; a_.y32_ld = 256;
       a_.y32_outer_stride = NT; a_.y32_row_off = 1);

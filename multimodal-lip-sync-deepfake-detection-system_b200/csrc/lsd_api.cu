@@ -71,6 +71,11 @@ extern "C" void lsd_destroy(lsd_handle* h) {
   if (h->lm_clips) cudaFree(h->lm_clips);
   for (cudaEvent_t e : h->prof.ev) cudaEventDestroy(e);
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (h->tok_stream[i]) cudaStreamDestroy(h->tok_stream[i]);
+    if (h->ev_tok_join[i]) cudaEventDestroy(h->ev_tok_join[i]);
+  }
+  if (h->ev_tok_fork) cudaEventDestroy(h->ev_tok_fork);
   if (h->tail_stream) cudaStreamDestroy(h->tail_stream);
   for (int i = 0; i < 2; ++i) { if (h->ev_front[i]) cudaEventDestroy(h->ev_front[i]); if (h->ev_tail_done[i]) cudaEventDestroy(h->ev_tail_done[i]); }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);

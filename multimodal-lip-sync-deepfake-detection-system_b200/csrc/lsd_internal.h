@@ -73,6 +73,9 @@ struct lsd_handle {
   Prof prof;
   cudaStream_t side_stream = nullptr;      // artifact branch runs here, concurrently with the token path
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_start = nullptr, ev_audio = nullptr;
+  // independent pieces of the token path (the two attention directions, the three multi-scale branches) run side by side
+  cudaStream_t tok_stream[2] = {nullptr, nullptr};
+  cudaEvent_t ev_tok_fork = nullptr, ev_tok_join[2] = {nullptr, nullptr};
   int64_t launches0 = 0;
   // stage programs of the tcgen05 launches (umma_conv.cuh): built on the host once per (layer, shapes, workspace), cached here
   char* prog_arena = nullptr;
