@@ -1189,6 +1189,32 @@ __global__ void planar_mean2_kernel(const __nv_bfloat16* __restrict__ x, int64_t
     const int n = mode == 1 ? row : row / g.T, t0 = mode == 1 ? 0 : row % g.T;
     const int n_rows = (mode == 1 ? g.T : 1) * g.H;
     const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    if (g.W <= 32 && !xlo) {
+      // rows of at most one warp width: four rows in flight per warp (the loads are issued before the first dependent add; the
+      // summation order is the sequential one)
+      const bool act = lane < g.W;
+      const __nv_bfloat16* xc = x + (int64_t)chunk * plane_stride;
+      int rr = warp;
+      for (; rr + 3 * nwarps < n_rows; rr += 4 * nwarps) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = rr + u * nwarps, tt = r / g.H, h = r - tt * g.H;
+          v[u] = act ? *reinterpret_cast<const uint4*>(xc + (uc_flat(g, n, t0 + tt, h, 0) + lane) * 8) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float f[8];
+          unpack8(v[u], f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] += f[e];
+        }
+      }
+      for (; rr < n_rows; rr += nwarps) {
+        const int tt = rr / g.H, h = rr - tt * g.H;
+        if (act) add(uc_flat(g, n, t0 + tt, h, 0) + lane);
+      }
+    } else
     for (int rr = warp; rr < n_rows; rr += nwarps) {
       const int tt = rr / g.H, h = rr - tt * g.H;
       const int64_t base = uc_flat(g, n, t0 + tt, h, 0);
