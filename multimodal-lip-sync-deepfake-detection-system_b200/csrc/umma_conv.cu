@@ -958,12 +958,22 @@ template <> __device__ __forceinline__ void vr_load4<uint8_t>(const uint8_t* p, 
 // uint8 through a 256-entry table of i / 255.0f (exactly the reference's astype(float32) / 255.0): twelve IEEE divisions per
 // strip row made the uint8 variant ALU-bound and slower than the fp32 one although it reads a quarter of the bytes
 template <typename T> __device__ __forceinline__ void vr_load4_lut(const T* p, float* o, const float*) { vr_load4<T>(p, o); }
+// i / 255.0f for i in 0..255 without a division or a table: q = i * (1/255), one Newton step on the residual r = i - 255 q
+// (both fused).  Bit-identical to the IEEE division for all 256 inputs (checked exhaustively against the division on the host,
+// tests/test_host_logic.py, and by the uint8-vs-fp32 input equality test on the device).
+__device__ __forceinline__ float vr_u8_norm(float x) {
+  const float c = 1.0f / 255.0f;
+  const float q = x * c;
+  return fmaf(fmaf(-255.0f, q, x), c, q);
+}
 template <> __device__ __forceinline__ void vr_load4_lut<uint8_t>(const uint8_t* p, float* o, const float* lut) {
   const uint32_t v = *reinterpret_cast<const uint32_t*>(p);
-  o[0] = lut[v & 0xffu]; o[1] = lut[(v >> 8) & 0xffu]; o[2] = lut[(v >> 16) & 0xffu]; o[3] = lut[v >> 24];
+  if (lut) { o[0] = lut[v & 0xffu]; o[1] = lut[(v >> 8) & 0xffu]; o[2] = lut[(v >> 16) & 0xffu]; o[3] = lut[v >> 24]; return; }
+  o[0] = vr_u8_norm((float)(v & 0xffu)); o[1] = vr_u8_norm((float)((v >> 8) & 0xffu));
+  o[2] = vr_u8_norm((float)((v >> 16) & 0xffu)); o[3] = vr_u8_norm((float)(v >> 24));
 }
 template <typename T> __device__ __forceinline__ float vr_norm_lut(T x, const float*) { return vr_norm<T>((float)x); }
-template <> __device__ __forceinline__ float vr_norm_lut<uint8_t>(uint8_t x, const float* lut) { return lut[x]; }
+template <> __device__ __forceinline__ float vr_norm_lut<uint8_t>(uint8_t x, const float* lut) { return lut ? lut[x] : vr_u8_norm((float)x); }
 
 template <typename T, int LAYOUT>
 __global__ void __launch_bounds__(VR2_THREADS, 2) video_rows_tma_kernel(const T* __restrict__ video, const int32_t* __restrict__ starts, int n_frames,
@@ -973,9 +983,8 @@ __global__ void __launch_bounds__(VR2_THREADS, 2) video_rows_tma_kernel(const T*
   extern __shared__ __align__(128) uint8_t vr_smem[];
   __shared__ uint64_t full_bar[VR2_STAGES];
   __shared__ float lw[81];
-  __shared__ float lut[256];
+  const float* lut = nullptr;   // (the table variant — 256 entries of i / 255.0f in shared memory — was bank-conflict-bound)
   const int tid = threadIdx.x;
-  if (sizeof(T) == 1) lut[tid] = (float)tid / 255.0f;   // VR2_THREADS == 256
   const int row_elems = LAYOUT == 0 ? W : 3 * W;                       // elements of one image row in one staged piece
   const int plane_elems = (VR2_ROWS + 2) * row_elems;                  // one staged piece (all rows of the band + halo)
   const uint32_t stage_bytes = (uint32_t)((LAYOUT == 0 ? 3 : 1) * plane_elems * (int)sizeof(T));

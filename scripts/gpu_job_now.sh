@@ -1,11 +1,6 @@
 T="timeout 400"
 $T python -m pytest tests -m gpu -q -x 2>&1 | tail -3
-TAG="mean unrolled" $T python scripts/exp_knobs.py 2>&1 | tail -1
-$T ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"planar_mean2|mha_core|layernorm|maxpool|video_rows" -c 60 --csv --log-file gpurun_out/launches_small.csv python scripts/run_forward_b64.py > /dev/null 2>&1
-python - <<'PY'
-import csv
-lines=[l for l in open('gpurun_out/launches_small.csv') if not l.startswith('==')]
-rows=[r for r in csv.DictReader(lines)]
-for r in rows[-20:]:
-    print(r['Kernel Name'][:40], r['Grid Size'], r['Metric Value'], r['Metric Unit'])
-PY
+$T python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -n 1 > gpurun_out/bench_now.json
+python -c "
+import json; d=json.load(open('gpurun_out/bench_now.json')); print(d['value'], d['e2e']['value'], d['e2e_track_u8']['value'])"
+$T python scripts/audit_configs.py --config 5 2>/dev/null | tail -1 | cut -c1-120

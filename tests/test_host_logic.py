@@ -153,3 +153,17 @@ def test_mouth_motion_decision_and_aggregate_mirror_reference_golden():
         assert agg["counts"] == g["aggregate"]["counts"] and agg["samples_checked"] == g["aggregate"]["samples_checked"]
         assert abs(agg["audio_energy"] - g["aggregate"]["audio_energy"]) < 1e-9
     assert lb.Predictor.aggregate_mouth_motion_checks([])["check_result"] == "no_data"
+
+
+def test_u8_normalisation_formula_is_exact():
+    """video_rows normalises uint8 pixels as q = i * (1/255); q += (i - 255 q) * (1/255) with fused multiply-adds
+    (csrc/umma_conv.cu: vr_u8_norm).  That must equal the reference's astype(float32) / 255.0 (video.py:552-556) bit for bit
+    for every byte value; the fused operations are emulated in float64, which is exact for these magnitudes."""
+    import numpy as np
+    i = np.arange(256, dtype=np.float32)
+    ref = i / np.float32(255.0)
+    c = np.float32(1.0) / np.float32(255.0)
+    q = (i * c).astype(np.float32)
+    r = (np.float64(-255.0) * q.astype(np.float64) + i.astype(np.float64)).astype(np.float32)          # fmaf(-255, q, i)
+    out = (r.astype(np.float64) * np.float64(c) + q.astype(np.float64)).astype(np.float32)              # fmaf(r, c, q)
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
