@@ -458,7 +458,18 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
   // K chunks per stage: Toeplitz layers share one row region for all chunks; small planar stages are packed up to ~24 KB
   const int w_chunk = max_taps * L.ntile * 32;
   if (any_toeplitz) p.kpack = min_k16;
-  else p.kpack = std::max(1, std::min(std::min(8, min_k16), (24 * 1024) / (max_a + w_chunk)));
+  else {
+    // A stage costs its issuing warp ~300-450 cycles of barrier / descriptor bookkeeping whatever it carries: with 24 KB stages the
+    // one-tap token GEMMs issued 4 MMAs per stage, ~145 cycles per MMA against 48 of tensor time (measured per step at B=64 with
+    // 24 / 36 / 48 / 64 KB stages everywhere: 3.140 / 3.101 / 3.107 / 3.068 ms).  Only single-band layers (Linear) get the large
+    // stages: with several bands the K accumulation order is (chunk block, band, chunk, tap), i.e. it depends on kpack, kpack
+    // depends on the tile size and the tile size on the batch — logits must not depend on the batch composition bit for bit.
+    bool single_band = true;
+    for (int gi = 0; gi < p.ngroups; ++gi) single_band = single_band && (p.groups[gi].band_end - p.groups[gi].band_begin) == 1;
+    int stage_kb = single_band ? 64 : 24;
+    if (const char* e = getenv("LSD_UMMA_STAGE_KB")) stage_kb = std::max(8, atoi(e));   // tuning knob
+    p.kpack = std::max(1, std::min(std::min(8, min_k16), (stage_kb * 1024) / (max_a + w_chunk)));
+  }
   p.a_stage_bytes = ((uint32_t)(any_toeplitz ? max_a : max_a * p.kpack) + 127u) & ~127u;
   p.w_stage_bytes = (uint32_t)(w_chunk * p.kpack);
   const uint32_t stage = p.a_stage_bytes + p.w_stage_bytes;
