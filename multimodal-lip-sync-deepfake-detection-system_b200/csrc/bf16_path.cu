@@ -488,6 +488,7 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
   for (const BGroup& G : L.groups) kflop += (double)G.taps_total * G.Cin;
   if (L.groups[0].toeplitz) { const ConvP& cp = c.h->convs.at(name); kflop = (double)cp.kt * cp.kh * cp.kw * cp.Cin; }  // algorithmic K, not the padded one
   if (const char* e = getenv("LSD_UMMA_SKIP")) p.skip = atoi(e);
+  if (const char* why = umma_conv_config_error(p)) return lsd_fail(c.h, LSD_ERR_UNSUPPORTED, "%s: %s", name.c_str(), why);
   // stage program: expanded on the host, cached in device memory under a hash of the complete parameter block (pointers,
   // strides, geometry, tile shape), so steady-state forwards only look it up
   {

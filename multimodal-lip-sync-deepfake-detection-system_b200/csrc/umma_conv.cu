@@ -526,6 +526,17 @@ size_t umma_conv_smem_bytes(const UmmaConvP& p) {
 }
 int umma_conv_stage_desc_bytes() { return (int)sizeof(UcStageDesc); }
 
+static bool uc_is_generic(const UmmaConvP& p) {
+  return p.y32 || p.res32 || p.ylo || p.res_lo || p.act == ACT_GELU || p.y_mode == UC_Y_NONE || (p.Cout & 31);   // (the lean epilogue works in 32-column steps)
+}
+const char* umma_conv_config_error(const UmmaConvP& p) {
+  if (2 * p.kpack + p.kpack > 32) return "K chunks per stage exceed the producer lanes";
+  if (p.res && p.res32) return "bf16 and fp32 residuals are mutually exclusive";
+  if (uc_is_generic(p) && (p.Cout & 63)) return "the generic epilogue needs a column slice that is a multiple of 64";
+  if (p.MT / p.issuers > 4 || p.MT % p.issuers) return "unsupported M-tiles per issuing warp";
+  return nullptr;
+}
+
 void launch_umma_conv(const UmmaConvP& p, int n_slices, cudaStream_t s, int max_ctas) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -534,8 +545,7 @@ void launch_umma_conv(const UmmaConvP& p, int n_slices, cudaStream_t s, int max_
     cudaFuncSetAttribute(umma_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024);
     attr_set = true;
   }
-  if (2 * p.kpack + p.kpack > 32) { fprintf(stderr, "umma_conv: kpack %d exceeds the issuer count\n", p.kpack); abort(); }
-  if (p.res && p.res32) { fprintf(stderr, "umma_conv: bf16 and fp32 residuals are mutually exclusive\n"); abort(); }
+  if (const char* why = umma_conv_config_error(p)) { fprintf(stderr, "umma_conv: %s\n", why); abort(); }   // (callers check first)
   const int S = p.MT * 128;
   const int tiles = (int)((p.g.P_total + S - 1) / S);
   static int num_sms = 0;
@@ -544,8 +554,7 @@ void launch_umma_conv(const UmmaConvP& p, int n_slices, cudaStream_t s, int max_
   const int budget = (max_ctas > 0 && max_ctas < num_sms) ? max_ctas : num_sms;   // side-stream launches leave SMs to the main stream
   int gx = (budget + n_slices - 1) / n_slices;
   gx = gx < 1 ? 1 : (gx > tiles ? tiles : gx);
-  const bool generic = p.y32 || p.res32 || p.ylo || p.res_lo || p.act == ACT_GELU || p.y_mode == UC_Y_NONE || (p.Cout & 31);   // (the lean epilogue works in 32-column steps)
-  if (generic && (p.Cout & 63)) { fprintf(stderr, "umma_conv: the generic epilogue needs Cout %% 64 == 0 (got %d)\n", p.Cout); abort(); }
+  const bool generic = uc_is_generic(p);
   if (generic) umma_conv_kernel<true><<<dim3(gx, n_slices), UC_THREADS, umma_conv_smem_bytes(p), s>>>(p);
   else umma_conv_kernel<false><<<dim3(gx, n_slices), UC_THREADS, umma_conv_smem_bytes(p), s>>>(p);
   count_launch();

@@ -120,6 +120,8 @@ size_t umma_conv_smem_bytes(const UmmaConvP& p);
 int umma_conv_stage_desc_bytes();
 // host: expand the stage program of a launch (same arithmetic the kernel used to do per stage)
 void umma_conv_build_program(const UmmaConvP& p, UcStageDesc* out);
+// nullptr if the kernel supports this parameter block, else the reason (callers turn it into an error code instead of launching)
+const char* umma_conv_config_error(const UmmaConvP& p);
 void launch_umma_conv(const UmmaConvP& p, int n_slices, cudaStream_t s, int max_ctas = 0);
 
 // ---- planar-layout glue --------------------------------------------------------------------------
