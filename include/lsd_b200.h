@@ -95,6 +95,14 @@ int lsd_forward(lsd_handle* h,
                 void* workspace, size_t workspace_bytes,
                 void* stream);
 
+/* Workspace contract (tensor-core route): the zero padding of the planar activation buffers is written once per
+ * (workspace pointer, size, shapes) and then kept inside the workspace between calls — the library remembers the last
+ * workspace it initialised and skips the memset when the same one comes back.  The caller must therefore not modify the
+ * workspace between calls that reuse it; after writing into it, or after freeing it (a later allocation may return the
+ * same address), call lsd_workspace_invalidate() before the next forward.  Calls through the library itself (other
+ * shapes, the fp32 route, lsd_score_windows halves) are tracked internally. */
+int lsd_workspace_invalidate(lsd_handle* h);
+
 /* ---- sub-paths of the forward (tensor-core route; same kernels and numerics as inside lsd_forward) ------- */
 /* AudioEncoder.forward (app/models/audio_encoder.py:173-205): log-mel windows (B,1,F,Ta), device, any float dtype
  * -> feats_out (B, lsd_audio_tokens(Ta), 256) fp32 device rows (the reference returns the transpose (B,256,T')). */

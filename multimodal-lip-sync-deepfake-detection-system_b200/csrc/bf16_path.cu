@@ -2,8 +2,11 @@
 // orchestration that runs the 3-D residual stages, the artifact-detector convolutions and the high-frequency
 // back end on it.  Host-side only.
 #include "forward_common.h"
+#include "tok_fused.cuh"
 #include "token_kernels.cuh"
 #include "umma_conv.cuh"
+
+#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -512,8 +515,9 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
       std::vector<UcStageDesc> host((size_t)p.nst_tile);
       umma_conv_build_program(p, host.data());
       char* dst = c.h->prog_arena + c.h->prog_cursor;
-      // (pageable source: the runtime stages the bytes before returning, so `host` may go out of scope)
-      cudaError_t e = cudaMemcpyAsync(dst, host.data(), bytes, cudaMemcpyHostToDevice, c.st);
+      // Cache miss only (first forward of a shape): a blocking copy, so the program is visible to every stream that later
+      // launches this layer (the cache is shared by the main, side, tail and helper streams).
+      cudaError_t e = cudaMemcpy(dst, host.data(), bytes, cudaMemcpyHostToDevice);
       if (e != cudaSuccess) return lsd_fail(c.h, LSD_ERR_CUDA, "%s: stage program upload: %s", name.c_str(), cudaGetErrorString(e));
       c.h->prog_cursor += (bytes + 255) & ~size_t(255);
       it = c.h->prog_cache.emplace(hkey, dst).first;
@@ -544,7 +548,7 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
     if (!dbuf) cudaMalloc(&dbuf, 512);
     cudaMemsetAsync(dbuf, 0, 512, c.st);
     p.dbg = dbuf;
-    launch_umma_conv(p, slices, c.st, c.max_ctas);
+    launch_umma_conv(p, slices, c.st, c.h->num_sms, c.max_ctas);
     long long hv[64];
     cudaMemcpyAsync(hv, dbuf, 512, cudaMemcpyDeviceToHost, c.st);
     cudaStreamSynchronize(c.st);
@@ -565,7 +569,7 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
   // profile classes: 2 = 3-D conv visual encoder (stem + residual stages, 86 % of the FLOPs, runs alone on the GPU),
   //                  3 = every other tcgen05 launch (audio encoder, token GEMMs, artifact branch on the side stream)
   c.h->prof.begin(c.st, 2.0 * (double)og.N * og.T * og.H * og.W * L.Cout * kflop, name.rfind("visual_encoder.", 0) == 0 ? 2 : 3);
-  launch_umma_conv(p, slices, c.st, c.max_ctas);
+  launch_umma_conv(p, slices, c.st, c.h->num_sms, c.max_ctas);
   c.h->prof.end(c.st);
   return 0;
 }
@@ -614,6 +618,65 @@ int res_stage_umma(const BCtx& b, const std::string& p, const PBuf& x, const PBu
 }
 
 }  // namespace
+
+// Weight stream, stage table and small vectors of the fused temporal-transformer kernel (tok_fused.cu).
+static int pack_tok_fused(lsd_handle* h, const std::vector<float>& f32) {
+  std::vector<TfBlock> blocks;
+  tf_layer_blocks(blocks);
+  std::vector<uint32_t> stage_bytes;
+  for (const TfBlock& b : blocks)
+    for (int k0 = 0; k0 < b.k16; k0 += b.kps) stage_bytes.push_back((uint32_t)b.kps * (uint32_t)b.N * 32u);
+  std::vector<__half> w;
+  std::vector<float> vec((size_t)TF_LAYERS * TF_VEC_LAYER + (size_t)(2 * TF_LAYERS + 1) * TF_D, 0.f);
+  std::vector<float> cum(TF_D, 0.f);
+  float* cum_out = vec.data() + (size_t)TF_LAYERS * TF_VEC_LAYER;
+  for (int l = 0; l < TF_LAYERS; ++l) {
+    const std::string k = "t" + std::to_string(l);
+    const ConvP &cin = h->convs.at(k + ".in"), &cout = h->convs.at(k + ".out"), &cf1 = h->convs.at(k + ".ff1"), &cf2 = h->convs.at(k + ".ff2");
+    const size_t w0 = w.size();
+    for (const TfBlock& b : blocks) {
+      const ConvP& c = b.kind == 0 ? cin : (b.kind == 1 ? cout : (b.kind == 2 ? cf1 : cf2));
+      for (int k16 = 0; k16 < b.k16; ++k16)
+        for (int pl = 0; pl < 2; ++pl)
+          for (int n = 0; n < b.N; ++n)
+            for (int e = 0; e < 8; ++e) {
+              const int kk = k16 * 16 + pl * 8 + e;
+              int co, ci;
+              if (b.kind == 0) { co = ((n % 96) / 32) * 256 + (2 * b.idx + n / 96) * 32 + (n % 32); ci = kk; }
+              else if (b.kind == 1) { co = n; ci = 64 * b.idx + kk; }
+              else if (b.kind == 2) { co = 128 * b.idx + n; ci = kk; }
+              else { co = n; ci = 128 * b.idx + kk; }
+              w.push_back(__float2half_rn(f32[c.w_off + (size_t)ci * c.Cout + co]));
+            }
+    }
+    if (l == 0) h->tokf_layer_bytes = (uint32_t)((w.size() - w0) * sizeof(__half));
+    float* lv = vec.data() + (size_t)l * TF_VEC_LAYER;
+    const char* names[4] = {".ln1.w", ".ln1.b", ".ln2.w", ".ln2.b"};
+    for (int i = 0; i < 4; ++i) memcpy(lv + 256 * i, &f32[h->vecs.at(k + names[i])], 256 * sizeof(float));
+    for (int n = 0; n < 768; ++n) {   // packed order: [head pair][head in pair][Q|K|V][32]
+      const int hp = n / 192, r = n % 192;
+      lv[1024 + n] = f32[cin.shift_off + ((r % 96) / 32) * 256 + (2 * hp + r / 96) * 32 + (r % 32)];
+    }
+    memcpy(lv + 1024 + 768, &f32[cf1.shift_off], 1024 * sizeof(float));
+    // cumulative biases of the GEMMs that accumulate straight into the residual stream
+    memcpy(cum_out + (size_t)(2 * l) * TF_D, cum.data(), TF_D * sizeof(float));
+    for (int i = 0; i < TF_D; ++i) cum[i] += f32[cout.shift_off + i];
+    memcpy(cum_out + (size_t)(2 * l + 1) * TF_D, cum.data(), TF_D * sizeof(float));
+    for (int i = 0; i < TF_D; ++i) cum[i] += f32[cf2.shift_off + i];
+  }
+  memcpy(cum_out + (size_t)(2 * TF_LAYERS) * TF_D, cum.data(), TF_D * sizeof(float));
+  h->tokf_n_stage = (int)stage_bytes.size();
+  for (void* q : {(void*)h->tokf_w, (void*)h->tokf_stage_bytes, (void*)h->tokf_vec}) if (q) cudaFree(q);
+  h->tokf_w = nullptr; h->tokf_stage_bytes = nullptr; h->tokf_vec = nullptr;
+  cudaError_t e = cudaMalloc(&h->tokf_w, w.size() * sizeof(__half));
+  if (e == cudaSuccess) e = cudaMemcpy(h->tokf_w, w.data(), w.size() * sizeof(__half), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&h->tokf_stage_bytes, stage_bytes.size() * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMemcpy(h->tokf_stage_bytes, stage_bytes.data(), stage_bytes.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&h->tokf_vec, vec.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(h->tokf_vec, vec.data(), vec.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return lsd_fail(h, LSD_ERR_CUDA, "pack_tok_fused: %s", cudaGetErrorString(e));
+  return 0;
+}
 
 int pack_bf16_weights(lsd_handle* h, const std::vector<float>& f32_arena) {
   Packer P{h, f32_arena, {}, {}};
@@ -666,7 +729,7 @@ int pack_bf16_weights(lsd_handle* h, const std::vector<float>& f32_arena) {
   if (e == cudaSuccess) e = cudaMalloc(&h->bbias, P.bias.size() * 4);
   if (e == cudaSuccess) e = cudaMemcpy(h->bbias, P.bias.data(), P.bias.size() * 4, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) return lsd_fail(h, LSD_ERR_CUDA, "pack_bf16_weights: %s", cudaGetErrorString(e));
-  return 0;
+  return pack_tok_fused(h, f32_arena);
 }
 
 void make_plan_bf16(lsd_handle* h, int B, int T, int H, int W, int F, int Ta, std::vector<Stage>& stages, size_t& bytes) {
@@ -776,6 +839,24 @@ static int token_path_bf16(const BCtx& b, const Shapes& s) {
   // pre_scale_proj + residual, written straight into token rows 1..T of each window
   RUN("temporal.pre_scale_proj", a_.in = &pbf("mscat_p"); a_.in_lo = &pbf("mscat_p_lo"); a_.og = gt; a_.res32 = b.f("fused"); a_.res32_ld = 256; a_.y32 = tok; a_.y32_ld = 256;
       a_.y32_outer_stride = NT; a_.y32_row_off = 1);
+  // ---- the four encoder layers: one fused launch (tok_fused.cu); LSD_TOK_FUSED=0 (debug / A-B tests) or more than 64 tokens per
+  // window fall back to the layer-by-layer GEMM chain
+  const char* fused_env = getenv("LSD_TOK_FUSED");
+  const bool fused_off = fused_env && atoi(fused_env) == 0;
+  if (!fused_off && tok_fused_supported(NT)) {
+    TokFusedP fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.tok = tok;
+    fp.w = reinterpret_cast<const __half*>(h->tokf_w);
+    fp.stage_bytes = h->tokf_stage_bytes;
+    fp.n_stage_layer = h->tokf_n_stage;
+    fp.layer_bytes = h->tokf_layer_bytes;
+    fp.vec = h->tokf_vec;
+    fp.B = B; fp.NT = NT;
+    tok_fused_geometry(NT, fp.SL, fp.G);
+    launch_tok_fused(fp, st);
+    return 0;
+  }
   const UcGeom g33 = P.g33;
   for (int l = 0; l < 4; ++l) {
     const std::string k = "t" + std::to_string(l);
@@ -792,6 +873,27 @@ static int token_path_bf16(const BCtx& b, const Shapes& s) {
 }
 
 
+// Zero padding of the planar buffers lives in the workspace across calls: kernels only ever write valid positions (or zeros at
+// pad positions), so a workspace whose padding was initialised for these shapes is reused as is.  Two (pointer, bytes, shapes)
+// signatures are remembered — slot 1 belongs to the second half of a pipelined lsd_score_windows call, slot 0 to everything
+// else.  A call invalidates the OTHER slot whenever its byte range overlaps this call's workspace (a forward with other shapes
+// through the same memory overwrites that half's padding), and lsd_workspace_invalidate() drops both (the caller reused or
+// freed the memory between calls).
+static int ws_prepare(lsd_handle* h, const Shapes& s, const BPlan& P, char* ws, size_t ws_bytes, cudaStream_t st, int slot) {
+  const int sig[6] = {s.B, s.T, s.H, s.W, s.F, s.Ta};
+  WsSig& mine = h->ws_sig[slot];
+  WsSig& other = h->ws_sig[slot ^ 1];
+  if (other.ptr) {
+    const char* o0 = reinterpret_cast<const char*>(other.ptr);
+    if (o0 < ws + ws_bytes && ws < o0 + other.bytes) other.ptr = nullptr;
+  }
+  if (mine.ptr == ws && mine.bytes == ws_bytes && memcmp(mine.shape, sig, sizeof(sig)) == 0) return 0;
+  cudaError_t e = cudaMemsetAsync(ws + P.planar_begin, 0, P.planar_end - P.planar_begin, st);
+  if (e != cudaSuccess) return lsd_fail(h, LSD_ERR_CUDA, "workspace init: %s", cudaGetErrorString(e));
+  mine.ptr = ws; mine.bytes = ws_bytes; memcpy(mine.shape, sig, sizeof(sig));
+  return 0;
+}
+
 // pipe_parity >= 0 (lsd_score_windows with a double workspace): everything after the visual encoder is enqueued on
 // h->tail_stream, ordered after the encoder by ev_front[parity]; ev_tail_done[parity] marks the batch's logits complete.
 static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, const lsd_aux* aux, char* ws, size_t ws_bytes,
@@ -801,17 +903,8 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   build_plan(s, P);
   if (P.f32.cursor > ws_bytes) return lsd_fail(h, LSD_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", P.f32.cursor, ws_bytes);
   h->stages = P.f32.stages;
-  // Zero padding of the planar buffers lives in the workspace across calls: (re)initialise when the workspace or the
-  // shapes change.  Kernels only ever write valid positions (or zeros at pad positions), so the padding stays intact.
-  const int sig[6] = {s.B, s.T, s.H, s.W, s.F, s.Ta};
-  const bool known1 = h->ws_sig_ptr == ws && h->ws_sig_bytes == ws_bytes && memcmp(h->ws_sig_shape, sig, sizeof(sig)) == 0;
-  const bool known2 = h->ws_sig2_ptr == ws && h->ws_sig2_bytes == ws_bytes && memcmp(h->ws_sig2_shape, sig, sizeof(sig)) == 0;
-  if (!known1 && !known2) {
-    cudaError_t e = cudaMemsetAsync(ws + P.planar_begin, 0, P.planar_end - P.planar_begin, st);
-    if (e != cudaSuccess) return lsd_fail(h, LSD_ERR_CUDA, "workspace init: %s", cudaGetErrorString(e));
-    if (pipe_parity == 1) { h->ws_sig2_ptr = ws; h->ws_sig2_bytes = ws_bytes; memcpy(h->ws_sig2_shape, sig, sizeof(sig)); }
-    else { h->ws_sig_ptr = ws; h->ws_sig_bytes = ws_bytes; memcpy(h->ws_sig_shape, sig, sizeof(sig)); }
-  }
+  int rc0 = 0;
+  if ((rc0 = ws_prepare(h, s, P, ws, ws_bytes, st, pipe_parity == 1 ? 1 : 0))) return rc0;
   BCtx b{h, ws, &P, st};
   const int B = s.B, T = s.T, TA = s.A4, NT = T + 1;
   auto& pb = P.pb;
@@ -847,9 +940,9 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   const PBuf &xs = pb["xs"], &xl = pb["xl"], &so = pb["s_out"], &x1 = pb["x1"];
   const float* lapw = h->warena + h->convs.at("art.lap").w_off;
   // (vstarts: the uint8 track is read in place, window n = frames vstarts[n] .. vstarts[n]+T-1 — no fp32 window copy)
-  if (vstarts) launch_video_rows(video, vdt, vlayout, lapw, b.org(xs), b.org(xl), xs.set_stride, xs.g, s.H, s.W, st, vstarts, n_frames);
-  else if (inputs_ready) launch_video_rows(b.f("vid"), LSD_F32, LSD_NDHWC, lapw, b.org(xs), b.org(xl), xs.set_stride, xs.g, s.H, s.W, st);
-  else launch_video_rows(video, vdt, vlayout, lapw, b.org(xs), b.org(xl), xs.set_stride, xs.g, s.H, s.W, st);
+  if (vstarts) launch_video_rows(video, vdt, vlayout, lapw, b.org(xs), b.org(xl), xs.set_stride, xs.g, s.H, s.W, st, h->num_sms, vstarts, n_frames);
+  else if (inputs_ready) launch_video_rows(b.f("vid"), LSD_F32, LSD_NDHWC, lapw, b.org(xs), b.org(xl), xs.set_stride, xs.g, s.H, s.W, st, h->num_sms);
+  else launch_video_rows(video, vdt, vlayout, lapw, b.org(xs), b.org(xl), xs.set_stride, xs.g, s.H, s.W, st, h->num_sms);
   g_tl.mark(st, "M:video_rows");
   // (LSD_AUDIO_AFTER_ROWS=1 forks the audio encoder after video_rows instead: that kernel then takes 158 us instead of 262 — it
   // walks its tiles with a static stride, so side-stream kernels holding SMs at its start delay it — but the audio encoder's chain of
@@ -983,12 +1076,7 @@ static int subpath_begin(lsd_handle* h, const Shapes& s, BPlan& P, char* ws, siz
   build_plan(s, P);
   if (P.f32.cursor > ws_bytes) return lsd_fail(h, LSD_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", P.f32.cursor, ws_bytes);
   h->stages = P.f32.stages;
-  const int sig[6] = {s.B, s.T, s.H, s.W, s.F, s.Ta};
-  if (h->ws_sig_ptr != ws || h->ws_sig_bytes != ws_bytes || memcmp(h->ws_sig_shape, sig, sizeof(sig)) != 0) {
-    cudaError_t e = cudaMemsetAsync(ws + P.planar_begin, 0, P.planar_end - P.planar_begin, st);
-    if (e != cudaSuccess) return lsd_fail(h, LSD_ERR_CUDA, "workspace init: %s", cudaGetErrorString(e));
-    h->ws_sig_ptr = ws; h->ws_sig_bytes = ws_bytes; memcpy(h->ws_sig_shape, sig, sizeof(sig));
-  }
+  if (int rc = ws_prepare(h, s, P, ws, ws_bytes, st, 0)) return rc;
   return 0;
 }
 

@@ -267,9 +267,8 @@ __global__ void logmel_db_batched_kernel(float* __restrict__ mel, const LmClip* 
 size_t logmel_fft_smem_bytes() { return (size_t)LM_SEG_PAD * 4 + (size_t)2 * LM_PAIRS * NFFT * sizeof(float2); }
 int logmel_frames_per_block() { return LM_FB; }
 
+// __constant__ twiddles and function attributes are per device: called from lsd_create with the handle's device current
 void init_logmel_fft_constants() {
-  static bool done = false;
-  if (done) return;
   float2 w16[16], w25[25], w5[5];
   const double PI = 3.14159265358979323846;
   for (int k = 0; k < 16; ++k) w16[k] = make_float2((float)cos(2.0 * PI * k / 16), (float)-sin(2.0 * PI * k / 16));
@@ -279,7 +278,6 @@ void init_logmel_fft_constants() {
   cudaMemcpyToSymbol(c_w25, w25, sizeof(w25));
   cudaMemcpyToSymbol(c_w5, w5, sizeof(w5));
   cudaFuncSetAttribute(logmel_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)logmel_fft_smem_bytes());
-  done = true;
 }
 
 void launch_logmel_fft(const float* pcm, const LmClip* clips, int n_clips, int total_blocks, int max_frames, const float* hann,

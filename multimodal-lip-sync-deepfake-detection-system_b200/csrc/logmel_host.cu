@@ -81,7 +81,10 @@ extern "C" int lsd_logmel(lsd_handle* h, const float* pcm, const int64_t* clip_o
   if (n_clips == 0) return LSD_OK;
   if (!pcm || !clip_offsets_host || !mel_out || !mel_offsets_host || !scratch) return lsd_fail(h, LSD_ERR_ARG, "lsd_logmel: null pointer argument");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaSetDevice(h->device);
+  int prev_dev = -1;
+  cudaGetDevice(&prev_dev);
+  struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev != h->device ? prev_dev : -1};
+  cudaError_t e = prev_dev != h->device ? cudaSetDevice(h->device) : cudaSuccess;
   if (e == cudaSuccess) e = cudaMemsetAsync(scratch, 0, sizeof(float) * n_clips, st);
   if (e != cudaSuccess) return lsd_fail(h, LSD_ERR_CUDA, "lsd_logmel: %s", cudaGetErrorString(e));
   if (n_clips > 65535) return lsd_fail(h, LSD_ERR_SHAPE, "lsd_logmel: at most 65535 clips per call");
@@ -106,10 +109,17 @@ extern "C" int lsd_logmel(lsd_handle* h, const float* pcm, const int64_t* clip_o
     h->lm_clips_cap = h->lm_clips_host.size() * 2;
     if (cudaMalloc(&h->lm_clips, h->lm_clips_cap) != cudaSuccess) { h->lm_clips_cap = 0; return lsd_fail(h, LSD_ERR_CUDA, "lsd_logmel: clip table allocation failed"); }
   }
+  // the clip table is shared by all calls on this handle: the upload waits for the kernels of the previous call (which may have
+  // run on another stream) before it overwrites the table
+  if (!h->ev_lm_clips && cudaEventCreateWithFlags(&h->ev_lm_clips, cudaEventDisableTiming) != cudaSuccess)
+    return lsd_fail(h, LSD_ERR_CUDA, "lsd_logmel: event creation failed");
+  if (h->lm_clips_used) cudaStreamWaitEvent(st, h->ev_lm_clips, 0);
   e = cudaMemcpyAsync(h->lm_clips, tab, h->lm_clips_host.size(), cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return lsd_fail(h, LSD_ERR_CUDA, "lsd_logmel: %s", cudaGetErrorString(e));
   lsd::launch_logmel_fft(pcm, reinterpret_cast<const lsd::LmClip*>(h->lm_clips), n_clips, (int)blocks, max_frames, h->d_hann,
                          reinterpret_cast<const float2*>(h->d_w400), h->d_melw, h->d_mel_lo, h->d_mel_cnt, mel_out, scratch, st);
+  cudaEventRecord(h->ev_lm_clips, st);
+  h->lm_clips_used = true;
   e = cudaGetLastError();
   if (e != cudaSuccess) return lsd_fail(h, LSD_ERR_CUDA, "lsd_logmel: %s", cudaGetErrorString(e));
   return LSD_OK;

@@ -11,6 +11,8 @@
 #include <cstring>
 
 #include "forward_common.h"
+#include "tok_fused.cuh"
+#include "umma_conv.cuh"
 using namespace lsd;
 
 static thread_local std::string g_create_error;
@@ -31,7 +33,25 @@ int lsd_fail(lsd_handle* h, int code, const char* fmt, ...) {
     if (e_ != cudaSuccess) return lsd_fail(h, LSD_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
   } while (0)
 
-extern "C" int lsd_version(void) { return 100; }
+// Every entry point makes the handle's device current for its own work and restores the caller's device on return
+// (torch reads the current device from the runtime: switching it behind the caller's back would misplace later allocations).
+namespace {
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) err = cudaSetDevice(dev);
+    else prev = -1;   // nothing to restore
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+}  // namespace
+#define ENTER_DEVICE(h)                 \
+  DeviceGuard dev_guard_((h)->device);  \
+  CUDA_OK(h, dev_guard_.err)
+
+extern "C" int lsd_version(void) { return 200; }
 
 extern "C" const char* lsd_last_error(lsd_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
@@ -53,7 +73,16 @@ extern "C" int lsd_create(lsd_handle** out, int device) {
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
   h->launches0 = kernel_launches();
+  DeviceGuard guard(device);
+  if (guard.err != cudaSuccess) { delete h; return lsd_fail(nullptr, LSD_ERR_CUDA, "lsd_create: cudaSetDevice(%d): %s", device, cudaGetErrorString(guard.err)); }
+  // per-device state (opt-in shared-memory limits, __constant__ twiddles) is set up for every handle: cheap, and correct
+  // when one process holds handles on several devices
   int rc = init_logmel_tables(h);
+  if (rc == 0) {
+    cudaError_t ce = lsd::umma_conv_device_init();
+    if (ce == cudaSuccess) ce = lsd::tok_fused_device_init();
+    if (ce != cudaSuccess) rc = lsd_fail(h, LSD_ERR_CUDA, "lsd_create: kernel attribute setup: %s", cudaGetErrorString(ce));
+  }
   if (rc != 0) { g_create_error = h->err; delete h; return rc; }
   *out = h;
   return LSD_OK;
@@ -61,14 +90,18 @@ extern "C" int lsd_create(lsd_handle** out, int device) {
 
 extern "C" void lsd_destroy(lsd_handle* h) {
   if (!h) return;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   if (h->warena) cudaFree(h->warena);
   if (h->barena) cudaFree(h->barena);
   if (h->bbias) cudaFree(h->bbias);
+  if (h->tokf_w) cudaFree(h->tokf_w);
+  if (h->tokf_stage_bytes) cudaFree(h->tokf_stage_bytes);
+  if (h->tokf_vec) cudaFree(h->tokf_vec);
   if (h->mel_tables) cudaFree(h->mel_tables);
   if (h->prog_arena) cudaFree(h->prog_arena);
   if (h->tile_ctr_arena) cudaFree(h->tile_ctr_arena);
   if (h->lm_clips) cudaFree(h->lm_clips);
+  if (h->ev_lm_clips) cudaEventDestroy(h->ev_lm_clips);
   for (cudaEvent_t e : h->prof.ev) cudaEventDestroy(e);
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
   for (int i = 0; i < 2; ++i) {
@@ -202,7 +235,7 @@ bool pack_cross_inproj(Loader& L) {
 
 extern "C" int lsd_load_weights(lsd_handle* h, const lsd_tensor* tensors, int n) {
   if (!h || !tensors) return lsd_fail(h, LSD_ERR_ARG, "lsd_load_weights: null argument");
-  CUDA_OK(h, cudaSetDevice(h->device));
+  ENTER_DEVICE(h);
   Loader L;
   L.h = h;
   h->convs.clear();
@@ -336,7 +369,7 @@ extern "C" int lsd_forward(lsd_handle* h, const void* video, int video_dtype, in
   if (audio_dtype == LSD_U8) return lsd_fail(h, LSD_ERR_ARG, "audio: uint8 log-mel is not supported");
   if (video_layout != LSD_NCDHW && video_layout != LSD_NDHWC) return lsd_fail(h, LSD_ERR_ARG, "bad video layout %d", video_layout);
   if (precision != LSD_PREC_FP32 && precision != LSD_PREC_BF16) return lsd_fail(h, LSD_ERR_ARG, "bad precision %d", precision);
-  CUDA_OK(h, cudaSetDevice(h->device));
+  ENTER_DEVICE(h);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (precision == LSD_PREC_BF16) {
     rc = forward_bf16(h, B, T, H, W, F, Ta, video, video_dtype, video_layout, audio, audio_dtype, logits_out, aux,
@@ -347,7 +380,7 @@ extern "C" int lsd_forward(lsd_handle* h, const void* video, int video_dtype, in
     make_plan_f32(s, p);
     if (p.cursor > workspace_bytes) return lsd_fail(h, LSD_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", p.cursor, workspace_bytes);
     h->stages = p.stages;
-    h->ws_sig_ptr = nullptr; h->ws_sig2_ptr = nullptr;  // the fp32 plan overwrites any bf16 zero padding kept in this workspace
+    h->ws_sig[0].ptr = nullptr; h->ws_sig[1].ptr = nullptr;  // the fp32 plan overwrites any bf16 zero padding kept in this workspace
     rc = forward_f32(h, s, p, reinterpret_cast<char*>(workspace), aux, logits_out, st, false, video, video_dtype, video_layout, audio, audio_dtype);
     if (rc) return rc;
   }
@@ -379,7 +412,7 @@ extern "C" int lsd_score_windows(lsd_handle* h, const uint8_t* track, int n_fram
   for (int i = 0; i < n_windows; ++i)
     if (starts_host[i] < 0 || starts_host[i] + T > n_frames)
       return lsd_fail(h, LSD_ERR_SHAPE, "window %d [%d,%d) is outside the %d-frame track", i, starts_host[i], starts_host[i] + T, n_frames);
-  CUDA_OK(h, cudaSetDevice(h->device));
+  ENTER_DEVICE(h);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t need = lsd_score_workspace_bytes(h, batch, T, H, W, F, Ta, precision);
   if (need > workspace_bytes) return lsd_fail(h, LSD_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
@@ -425,7 +458,7 @@ extern "C" int lsd_score_windows(lsd_handle* h, const uint8_t* track, int n_fram
       Plan pb;
       make_plan_f32(sb, pb);
       h->stages = pb.stages;
-      h->ws_sig_ptr = nullptr; h->ws_sig2_ptr = nullptr;
+      h->ws_sig[0].ptr = nullptr; h->ws_sig[1].ptr = nullptr;
       Ctx c{h, fws, &pb, st};
       launch_gather_windows_u8(track, n_frames, d_vs, c.buf("vid"), nb, T, H * W * 3, st);
       launch_gather_audio(mel_full, F, Ta_full, d_as, c.buf("aud"), nb, Ta, st);
@@ -457,7 +490,7 @@ extern "C" int lsd_audio_encoder(lsd_handle* h, const void* audio, int audio_dty
   int rc = check_dtype(h, audio_dtype, "audio");
   if (rc) return rc;
   if (audio_dtype == LSD_U8) return lsd_fail(h, LSD_ERR_ARG, "audio: uint8 log-mel is not supported");
-  CUDA_OK(h, cudaSetDevice(h->device));
+  ENTER_DEVICE(h);
   rc = audio_encoder_bf16_run(h, B, F, Ta, audio, audio_dtype, feats_out, reinterpret_cast<char*>(workspace), workspace_bytes,
                               reinterpret_cast<cudaStream_t>(stream));
   if (rc) return rc;
@@ -474,7 +507,7 @@ extern "C" int lsd_token_path(lsd_handle* h, const float* v_emb, const float* a_
   if (B < 0 || T < 1 || Ta_tokens < 1) return lsd_fail(h, LSD_ERR_SHAPE, "expected v_emb (B,T,256) and a_emb (B,T_a,256), got B=%d T=%d T_a=%d", B, T, Ta_tokens);
   if (B == 0) return LSD_OK;
   if (!v_emb || !a_emb || !workspace || (!fused_out && !cls_out)) return lsd_fail(h, LSD_ERR_ARG, "lsd_token_path: null pointer argument");
-  CUDA_OK(h, cudaSetDevice(h->device));
+  ENTER_DEVICE(h);
   int rc = token_path_bf16_run(h, B, T, Ta_tokens, v_emb, a_emb, fused_out, cls_out, reinterpret_cast<char*>(workspace), workspace_bytes,
                                reinterpret_cast<cudaStream_t>(stream));
   if (rc) return rc;
@@ -493,7 +526,7 @@ extern "C" int lsd_track_motion(lsd_handle* h, const void* video, int dtype, int
   if (!video || !motion_full || !motion_low) return lsd_fail(h, LSD_ERR_ARG, "lsd_track_motion: null pointer argument");
   if (!((dtype == LSD_U8 && layout == LSD_NDHWC) || (dtype == LSD_F32 && layout == LSD_NCDHW)))
     return lsd_fail(h, LSD_ERR_ARG, "lsd_track_motion: supported inputs are a uint8 (n,H,W,3) track or a float32 (3,T,H,W) window");
-  CUDA_OK(h, cudaSetDevice(h->device));
+  ENTER_DEVICE(h);
   lsd::launch_track_motion(video, layout == LSD_NDHWC ? 1 : 0, n_frames, H, W, motion_full, motion_low, reinterpret_cast<cudaStream_t>(stream));
   CUDA_OK(h, cudaGetLastError());
   return LSD_OK;
@@ -512,7 +545,7 @@ extern "C" int lsd_speech_stats(lsd_handle* h, const float* motion_full, const f
   for (int i = 0; i < n_windows; ++i)
     if (starts_host[i] < 0 || starts_host[i] + T > n_frames)
       return lsd_fail(h, LSD_ERR_SHAPE, "window %d [%d,%d) is outside the %d-frame track", i, starts_host[i], starts_host[i] + T, n_frames);
-  CUDA_OK(h, cudaSetDevice(h->device));
+  ENTER_DEVICE(h);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   h->idx_host.resize((size_t)2 * n_windows);
   const double a_ratio = (double)Ta_full / (double)(total_v_frames > 1 ? total_v_frames : 1);
@@ -539,7 +572,7 @@ extern "C" int lsd_frame_energy(lsd_handle* h, const float* pcm, int64_t n_sampl
   if (n_samples < 0) return lsd_fail(h, LSD_ERR_SHAPE, "lsd_frame_energy: negative length");
   if (n_samples == 0) return LSD_OK;
   if (!pcm || !energy_out) return lsd_fail(h, LSD_ERR_ARG, "lsd_frame_energy: null pointer argument");
-  CUDA_OK(h, cudaSetDevice(h->device));
+  ENTER_DEVICE(h);
   lsd::launch_frame_energy(pcm, n_samples, lsd_vad_frames(n_samples), energy_out, reinterpret_cast<cudaStream_t>(stream));
   CUDA_OK(h, cudaGetLastError());
   return LSD_OK;
@@ -549,7 +582,7 @@ extern "C" int lsd_vad_mask(lsd_handle* h, const float* energy, int n_frames, fl
   if (n_frames < 0) return lsd_fail(h, LSD_ERR_SHAPE, "lsd_vad_mask: negative length");
   if (n_frames == 0) return LSD_OK;
   if (!energy || !mask_out) return lsd_fail(h, LSD_ERR_ARG, "lsd_vad_mask: null pointer argument");
-  CUDA_OK(h, cudaSetDevice(h->device));
+  ENTER_DEVICE(h);
   lsd::launch_vad_mask(energy, n_frames, threshold, mask_out, reinterpret_cast<cudaStream_t>(stream));
   CUDA_OK(h, cudaGetLastError());
   return LSD_OK;
@@ -558,6 +591,12 @@ extern "C" int lsd_vad_mask(lsd_handle* h, const float* energy, int n_frames, fl
 // ================================================================================================
 // Introspection
 // ================================================================================================
+extern "C" int lsd_workspace_invalidate(lsd_handle* h) {
+  if (!h) return LSD_ERR_ARG;
+  h->ws_sig[0].ptr = nullptr; h->ws_sig[1].ptr = nullptr;
+  return LSD_OK;
+}
+
 extern "C" int lsd_profile_enable(lsd_handle* h, int on) {
   if (!h) return LSD_ERR_ARG;
   h->prof.want = on;   // 1: fp32 conv kernel class, 2: tcgen05 conv kernel class

@@ -47,6 +47,8 @@ struct Prof {             // CUDA-event brackets around the dominant kernel clas
   }
 };
 
+struct WsSig { const void* ptr = nullptr; size_t bytes = 0; int shape[6] = {0, 0, 0, 0, 0, 0}; };
+
 struct lsd_handle {
   int device = 0;
   int num_sms = 148;
@@ -57,13 +59,14 @@ struct lsd_handle {
   std::map<std::string, ConvP> convs;
   std::map<std::string, size_t> vecs;      // small fp32 vectors (offsets into warena)
   float* bbias = nullptr;                  // fp32 biases of the bf16 layers
+  // fused temporal-transformer kernel (tok_fused.cu): fp16 weight stream, per-layer stage sizes, small fp32 vectors
+  void* tokf_w = nullptr;
+  uint32_t* tokf_stage_bytes = nullptr;
+  float* tokf_vec = nullptr;
+  int tokf_n_stage = 0;
+  uint32_t tokf_layer_bytes = 0;
   std::map<std::string, BLayer> blayers;
-  const void* ws_sig_ptr = nullptr;        // bf16 workspace whose zero padding is initialised (see forward_bf16)
-  size_t ws_sig_bytes = 0;
-  int ws_sig_shape[6] = {0, 0, 0, 0, 0, 0};
-  const void* ws_sig2_ptr = nullptr;       // second remembered workspace (the two halves of a pipelined lsd_score_windows call)
-  size_t ws_sig2_bytes = 0;
-  int ws_sig2_shape[6] = {0, 0, 0, 0, 0, 0};
+  WsSig ws_sig[2];                         // bf16 workspaces whose zero padding is initialised (see ws_prepare in bf16_path.cu)
   // cross-batch pipelining of lsd_score_windows: the tail of batch k (audio encoder, token path, head; artifact branch on the
   // side stream) runs on tail_stream while the main stream already runs the visual encoder of batch k+1
   cudaStream_t tail_stream = nullptr;
@@ -93,6 +96,8 @@ struct lsd_handle {
   void* lm_clips = nullptr;                // device clip table of the batched log-mel kernel (grows on demand)
   size_t lm_clips_cap = 0;
   std::vector<char> lm_clips_host;
+  cudaEvent_t ev_lm_clips = nullptr;       // recorded after the kernels that read lm_clips; the next upload waits on it
+  bool lm_clips_used = false;
 };
 
 int lsd_fail(lsd_handle* h, int code, const char* fmt, ...);

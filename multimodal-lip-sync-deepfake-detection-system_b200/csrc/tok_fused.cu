@@ -1,0 +1,429 @@
+// Fused temporal transformer for sm_100a: the four pre-norm encoder layers of TemporalTransformer.forward
+// (app/models/temporal.py:64-77: LN -> MHA(8 heads, hd 32) -> +res -> LN -> Linear 256->1024 -> GELU -> Linear 1024->256 -> +res)
+// in one launch.  Replaces 28 launches per forward (4 x [LN, in-proj GEMM, attention core, out-proj GEMM, LN, FF1 GEMM, FF2 GEMM]).
+//
+// One CTA owns G windows (rows = tokens; every window gets a slot of SL = 32 or 64 rows of the 128-row tile, so a warp's 32
+// rows never straddle windows and a window's keys start on a K16 boundary: a window's result does not depend on its slot or
+// on its co-tenants, bit for bit).  Everything a layer touches stays on the SM:
+//   * the residual stream X (128 x 256 fp32) lives in TMEM columns 0..255 for the whole kernel; the out-projection and the
+//     second FFN GEMM accumulate straight into it (tcgen05.mma with accumulate), their biases are carried as a cumulative
+//     vector added wherever X is read (LayerNorm, final store);
+//   * TMEM columns 256..511 hold the transient accumulators: Q|K|V of a head pair (192 columns), the two score tiles
+//     S = Q K^T (2 x 112), the two P V products (2 x 32), an FF1 chunk (128);
+//   * GEMM operands are fp16 in shared memory, K-major core-matrix layout (planes of 8 channels, rows 16 B apart, no swizzle):
+//     LayerNorm output (K = 256), Q / K / V^T of the head pair, the un-normalised probabilities P (flash-style: the row sum is
+//     kept in a register and applied to P V), the attention output of the head pair (K = 64), a GELU'd FF chunk (K = 128);
+//   * weights (fp16, 1.5 MB per layer) stream from L2 through a 3-slot ring of bulk async copies (TMA engine) in exactly the
+//     order the MMA warp consumes them (tok_fused.cuh: tf_layer_blocks).
+// fp16 operands with fp32 accumulation: one MMA pass instead of the three of the split-bf16 GEMMs this replaces (logit
+// deviation from the fp32 reference arithmetic measured on the CPU: 2.8e-3, tests hold the bf16-route budget of 2e-2).
+//
+// Warp roles (320 threads): warps 0-7 compute (warp w: TMEM lane quarter w % 4, thread = row; the two warps of a quarter split
+// columns, or take one head each in the attention phases), warp 8 streams weights, warp 9 issues every tcgen05.mma.
+// Compute and MMA phases alternate strictly (two mbarriers): simple to reason about, and the only latency it exposes is the
+// hand-over (~1 us per phase pair; 22 pairs per layer).
+#include "tok_fused.cuh"
+
+#include <cstdio>
+
+#include "lsd_kernels.h"
+#include "umma.cuh"
+
+namespace lsd {
+
+using namespace umma;
+
+namespace {
+
+constexpr int TF_THREADS = 320;
+constexpr int TF_RING = 3;
+constexpr uint32_t PLANE = 2048;                     // one 8-channel plane of a 128-row operand
+constexpr uint32_t OFF_ALN = 0;                      // LayerNorm output, K = 256: 32 planes
+constexpr uint32_t OFF_QK = 65536;                   // Q0 K0 Q1 K1: 4 planes each (hd = 32); aliased by ATT (K = 64: 8 planes) after S
+constexpr uint32_t OFF_VT = OFF_QK + 32768;          // V^T of the two heads: [key plane (14)][32 hd rows][8 keys], 8 KB per head
+constexpr uint32_t OFF_P = OFF_VT + 16384;           // P of the two heads, K = 112 keys: 14 planes each; aliased by the FF chunk (K = 128)
+constexpr uint32_t P_HEAD = 14 * PLANE;
+constexpr uint32_t OFF_RING = OFF_P + 2 * P_HEAD;
+constexpr uint32_t TF_SMEM = OFF_RING + TF_RING * TF_SLOT_BYTES;
+static_assert(2 * P_HEAD >= 16 * PLANE, "the FF chunk operand must fit in the P region");
+static_assert(TF_SMEM <= 225 * 1024, "shared-memory budget");
+constexpr int KEYS = 112;                            // key extent of S / P / V^T (7 K16 steps)
+constexpr uint32_t X_COL = 0, ACC_COL = 256;
+
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);   // D = f32, A = B = f16, K-major, dense
+}
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+      "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+      "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void st_shared_u16(uint32_t addr, unsigned short v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory"); }
+// 8 consecutive fp32 -> one 16-byte fp16 row piece of a plane
+__device__ __forceinline__ void st_plane8(uint32_t addr, const float* v) {
+  st_shared_v4(addr, pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+}  // namespace
+
+__global__ void __launch_bounds__(TF_THREADS, 1) tok_fused_kernel(const __grid_constant__ TokFusedP p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t w_full[TF_RING], w_empty[TF_RING], bar_mma, bar_cmp;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+
+  if (tid == 0) {
+    for (int i = 0; i < TF_RING; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    mbar_init(&bar_mma, 1);
+    mbar_init(&bar_cmp, 8);
+    fence_barrier_init();
+  }
+  if (warp == 9) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ weight producer (one lane)
+    if (lane == 0) {
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w);
+      int s = 0;
+      for (int l = 0; l < TF_LAYERS; ++l) {
+        const uint8_t* ls = src + (size_t)l * p.layer_bytes;
+        uint32_t off = 0;
+        for (int i = 0; i < p.n_stage_layer; ++i, ++s) {
+          const int slot = s % TF_RING;
+          const uint32_t ph = (uint32_t)(s / TF_RING) & 1u;
+          const uint32_t bytes = __ldg(p.stage_bytes + i);
+          mbar_wait(&w_empty[slot], ph ^ 1u);
+          mbar_arrive_expect_tx(&w_full[slot], bytes);
+          bulk_s2(sbase + OFF_RING + (uint32_t)slot * TF_SLOT_BYTES, ls + off, bytes, &w_full[slot]);
+          off += bytes;
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp runs the loop, one lane issues)
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    const uint64_t desc_hi = ((uint64_t)8 << 32) | ((uint64_t)1 << 46);   // SBO = 128 B, descriptor version 1
+    uint32_t par_c = 0;
+    int ws = 0;                                                           // weight stages consumed so far
+    auto wait_cmp = [&]() { mbar_wait(&bar_cmp, par_c); par_c ^= 1u; tc_fence_after(); };
+    auto done = [&]() { mma_commit_pred(&bar_mma, leader); };
+    auto desc = [&](uint32_t byte_addr, uint32_t lbo_bytes) -> uint64_t {
+      return desc_hi | (uint64_t)(((lbo_bytes >> 4) & 0x3FFFu) << 16) | (uint64_t)((byte_addr >> 4) & 0x3FFFu);
+    };
+    // D[tmem_d] (+)= A[a_addr: planes of 128 rows] * W^T, W = (N x 16*k16) streamed through the ring in stages of kps K16 steps
+    auto gemm_w = [&](uint32_t a_addr, int N, int k16, int kps, uint32_t tmem_d, uint32_t acc) {
+      const uint32_t idesc = idesc_f16(128, N);
+      for (int k0 = 0; k0 < k16; k0 += kps, ++ws) {
+        const int slot = ws % TF_RING;
+        mbar_wait(&w_full[slot], (uint32_t)(ws / TF_RING) & 1u);
+        tc_fence_after();
+        const uint32_t wb = sbase + OFF_RING + (uint32_t)slot * TF_SLOT_BYTES;
+#pragma unroll 1
+        for (int j = 0; j < kps; ++j) {
+          const uint64_t da = desc(a_addr + (uint32_t)(k0 + j) * 2u * PLANE, PLANE);
+          const uint64_t db = desc(wb + (uint32_t)j * (uint32_t)N * 32u, (uint32_t)N * 16u);
+          mma_bf16_ss_pred(tmem_d, da, db, idesc, acc, leader);
+          acc = 1u;
+        }
+        mma_commit_pred(&w_empty[slot], leader);
+      }
+    };
+    const uint32_t X = tmem + X_COL, ACC = tmem + ACC_COL;
+    // S_h = Q_h K_h^T for the two heads of the pair (hd = 32: two K16 steps), 112 key columns each
+    auto mma_scores = [&]() {
+      const uint32_t idesc = idesc_f16(128, KEYS);
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h)
+#pragma unroll 1
+        for (int j = 0; j < 2; ++j) {
+          const uint64_t da = desc(sbase + OFF_QK + (uint32_t)(2 * h) * 8192u + (uint32_t)j * 2u * PLANE, PLANE);
+          const uint64_t db = desc(sbase + OFF_QK + (uint32_t)(2 * h + 1) * 8192u + (uint32_t)j * 2u * PLANE, PLANE);
+          mma_bf16_ss_pred(ACC + (uint32_t)h * 128u, da, db, idesc, j ? 1u : 0u, leader);
+        }
+    };
+    // O_h = P_h V_h (K = 112 keys: seven K16 steps), B = V^T: [key plane][32 hd rows][8 keys]
+    auto mma_pv = [&]() {
+      const uint32_t idesc = idesc_f16(128, 32);
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h)
+#pragma unroll 1
+        for (int j = 0; j < KEYS / 16; ++j) {
+          const uint64_t da = desc(sbase + OFF_P + (uint32_t)h * P_HEAD + (uint32_t)j * 2u * PLANE, PLANE);
+          const uint64_t db = desc(sbase + OFF_VT + (uint32_t)h * 8192u + (uint32_t)j * 1024u, 512u);
+          mma_bf16_ss_pred(ACC + (uint32_t)h * 32u, da, db, idesc, j ? 1u : 0u, leader);
+        }
+    };
+    for (int l = 0; l < TF_LAYERS; ++l) {
+      for (int hp = 0; hp < 4; ++hp) {
+        wait_cmp();                                                       // LN1 output (hp = 0) / attention output of pair hp-1
+        if (hp > 0) gemm_w(sbase + OFF_QK, 256, 4, 2, X, 1u);             // X += att_{hp-1} @ Wo[:, 64(hp-1) : 64hp]^T
+        gemm_w(sbase + OFF_ALN, 192, 16, 2, ACC, 0u);                     // Q|K|V of heads 2hp, 2hp+1
+        done();
+        wait_cmp();                                                       // Q, K, V^T in shared memory
+        mma_scores();
+        done();
+        wait_cmp();                                                       // P in shared memory
+        mma_pv();
+        done();
+      }
+      wait_cmp();                                                         // attention output of the last pair
+      gemm_w(sbase + OFF_QK, 256, 4, 2, X, 1u);
+      done();
+      // ---- FFN: chunks of 128 hidden channels
+      for (int c = 0; c < 8; ++c) {
+        wait_cmp();                                                       // LN2 output (c = 0) / GELU'd chunk c-1
+        if (c > 0) gemm_w(sbase + OFF_P, 256, 8, 2, X, 1u);               // X += h_{c-1} @ W2[:, 128(c-1) : 128c]^T
+        gemm_w(sbase + OFF_ALN, 128, 16, 4, ACC, 0u);                     // h_c = LN2 @ W1[128c : 128c+128]^T
+        done();
+      }
+      wait_cmp();
+      gemm_w(sbase + OFF_P, 256, 8, 2, X, 1u);
+      done();
+    }
+  } else {
+    // ------------------------------------------------------------------ compute warps
+    const int q = warp & 3, hf = warp >> 2;
+    const int row = q * 32 + lane;
+    const int slot = (q * 32) / p.SL;
+    const int lrow = row - slot * p.SL;
+    const int win = blockIdx.x * p.G + slot;
+    const bool valid = slot < p.G && win < p.B && lrow < p.NT;
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    const uint32_t X = lane_base + X_COL, ACC = lane_base + ACC_COL;
+    const uint32_t row16 = (uint32_t)row * 16u;
+    float* grow = p.tok + ((size_t)(valid ? win : 0) * p.NT + (valid ? lrow : 0)) * TF_D;
+    uint32_t par_m = 0;
+    auto wait_mma = [&]() { mbar_wait(&bar_mma, par_m); par_m ^= 1u; tc_fence_after(); };
+    auto done = [&]() {
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_cmp);
+    };
+    const float* cum_all = p.vec + (size_t)TF_LAYERS * TF_VEC_LAYER;
+
+    // X <- tok rows (this warp's half of the columns); rows outside the batch are zero
+    for (int c0 = hf * 128; c0 < hf * 128 + 128; c0 += 32) {
+      float v[32];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float4 t = valid ? *reinterpret_cast<const float4*>(grow + c0 + 4 * e) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[4 * e] = t.x; v[4 * e + 1] = t.y; v[4 * e + 2] = t.z; v[4 * e + 3] = t.w;
+      }
+      tmem_st32(X + (uint32_t)c0, v);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    // both warps of a lane quarter must have stored their halves before either reads full rows
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    tc_fence_after();
+
+    // LayerNorm of (X + cum) -> A_ln (fp16 planes); both warps of a quarter compute the row statistics, each writes its half
+    auto layer_norm = [&](const float* cum, const float* g, const float* b) {
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < TF_D; c0 += 32) {
+        float v[32];
+        tmem_ld32(X + (uint32_t)c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) sum += v[e] + __ldg(cum + c0 + e);
+      }
+      const float mu = sum * (1.0f / TF_D);
+      float var = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < TF_D; c0 += 32) {
+        float v[32];
+        tmem_ld32(X + (uint32_t)c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) { const float d = v[e] + __ldg(cum + c0 + e) - mu; var = fmaf(d, d, var); }
+      }
+      const float rstd = 1.0f / sqrtf(var * (1.0f / TF_D) + 1e-5f);
+#pragma unroll 1
+      for (int c0 = hf * 128; c0 < hf * 128 + 128; c0 += 32) {
+        float v[32];
+        tmem_ld32(X + (uint32_t)c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = valid ? (v[e] + __ldg(cum + c0 + e) - mu) * rstd * __ldg(g + c0 + e) + __ldg(b + c0 + e) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) st_plane8(sbase + OFF_ALN + (uint32_t)(c0 / 8 + j) * PLANE + row16, v + 8 * j);
+      }
+    };
+
+    for (int l = 0; l < TF_LAYERS; ++l) {
+      const float* lv = p.vec + (size_t)l * TF_VEC_LAYER;
+      if (l > 0) wait_mma();                                              // FF2 of the previous layer complete
+      layer_norm(cum_all + (size_t)(2 * l) * TF_D, lv, lv + 256);
+      done();
+      const float* qkv_b = lv + 1024;
+      for (int hp = 0; hp < 4; ++hp) {
+        // ---- Q|K|V epilogue of head 2hp + hf: +bias, Q scaled by 1/sqrt(32), fp16 planes; V transposed (B operand of P V)
+        wait_mma();
+        {
+          const float* hb = qkv_b + hp * 192 + hf * 96;
+#pragma unroll 1
+          for (int part = 0; part < 3; ++part) {
+            float v[32];
+            tmem_ld32(ACC + (uint32_t)(hf * 96 + part * 32), v);
+            tmem_ld_wait();
+            const float sc = part == 0 ? 0.17677669529663688f : 1.0f;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = valid ? (v[e] + __ldg(hb + part * 32 + e)) * sc : 0.f;
+            if (part < 2) {
+              const uint32_t base = sbase + OFF_QK + (uint32_t)(2 * hf + part) * 8192u + row16;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) st_plane8(base + (uint32_t)j * PLANE, v + 8 * j);
+            } else if (row < KEYS) {
+              const uint32_t base = sbase + OFF_VT + (uint32_t)hf * 8192u + (uint32_t)(row >> 3) * 512u + (uint32_t)(row & 7) * 2u;
+#pragma unroll
+              for (int d = 0; d < 32; ++d) st_shared_u16(base + (uint32_t)d * 16u, __half_as_ushort(__float2half_rn(v[d])));
+            }
+          }
+        }
+        done();
+        // ---- softmax over this window's keys (columns slot*SL .. +NT of the score tile), un-normalised P -> fp16 planes
+        wait_mma();
+        float inv_sum = 0.f;
+        {
+          const uint32_t S = ACC + (uint32_t)(hf * 128 + slot * p.SL);
+          float mx = -INFINITY;
+#pragma unroll 1
+          for (int c0 = 0; c0 < p.NT; c0 += 32) {
+            float v[32];
+            tmem_ld32(S + (uint32_t)c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) if (c0 + e < p.NT) mx = fmaxf(mx, v[e]);
+          }
+          float sum = 0.f;
+          const uint32_t pbase = sbase + OFF_P + (uint32_t)hf * P_HEAD + row16;
+          const int kp0 = (slot * p.SL) >> 3;                             // first key plane of this window
+          int written_lo = kp0, written_hi = kp0;
+#pragma unroll 1
+          for (int c0 = 0; c0 < p.NT; c0 += 32) {
+            float v[32];
+            tmem_ld32(S + (uint32_t)c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const float pe = (valid && c0 + e < p.NT) ? __expf(v[e] - mx) : 0.f;
+              // the row sum is taken over the fp16-rounded probabilities the tensor core will multiply with V
+              const float pr = __half2float(__float2half_rn(pe));
+              sum += pr;
+              v[e] = pr;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int kp = kp0 + (c0 >> 3) + j;
+              if (kp < KEYS / 8) st_plane8(pbase + (uint32_t)kp * PLANE, v + 8 * j);
+            }
+            written_hi = kp0 + (c0 >> 3) + 4;
+          }
+          const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          for (int kp = 0; kp < KEYS / 8; ++kp)
+            if (kp < written_lo || kp >= written_hi) st_plane8(pbase + (uint32_t)kp * PLANE, z);
+          inv_sum = (valid && sum > 0.f) ? 1.0f / sum : 0.f;
+        }
+        done();
+        // ---- attention output of head 2hp + hf: (P V) / rowsum -> planes 4hf..4hf+3 of the K = 64 operand (aliases Q/K)
+        wait_mma();
+        {
+          float v[32];
+          tmem_ld32(ACC + (uint32_t)(hf * 32), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] *= inv_sum;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) st_plane8(sbase + OFF_QK + (uint32_t)(4 * hf + j) * PLANE + row16, v + 8 * j);
+        }
+        done();
+      }
+      // ---- LN2 (X now includes the attention update; its bias rides in the cumulative vector)
+      wait_mma();
+      layer_norm(cum_all + (size_t)(2 * l + 1) * TF_D, lv + 512, lv + 768);
+      done();
+      // ---- FFN chunks: GELU(acc + b1) -> fp16 planes of the K = 128 operand (this warp: 64 of the 128 columns)
+      const float* b1 = lv + 1024 + 768;
+      for (int c = 0; c < 8; ++c) {
+        wait_mma();
+#pragma unroll 1
+        for (int c0 = hf * 64; c0 < hf * 64 + 64; c0 += 32) {
+          float v[32];
+          tmem_ld32(ACC + (uint32_t)c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = valid ? gelu_erf(v[e] + __ldg(b1 + c * 128 + c0 + e)) : 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) st_plane8(sbase + OFF_P + (uint32_t)(c0 / 8 + j) * PLANE + row16, v + 8 * j);
+        }
+        done();
+      }
+    }
+    // ---- tok <- X + total bias
+    wait_mma();
+    {
+      const float* cum = cum_all + (size_t)(2 * TF_LAYERS) * TF_D;
+#pragma unroll 1
+      for (int c0 = hf * 128; c0 < hf * 128 + 128; c0 += 32) {
+        float v[32];
+        tmem_ld32(X + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            *reinterpret_cast<float4*>(grow + c0 + 4 * e) = make_float4(v[4 * e] + __ldg(cum + c0 + 4 * e), v[4 * e + 1] + __ldg(cum + c0 + 4 * e + 1),
+                                                                        v[4 * e + 2] + __ldg(cum + c0 + 4 * e + 2), v[4 * e + 3] + __ldg(cum + c0 + 4 * e + 3));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem, 512);
+}
+
+cudaError_t tok_fused_device_init() {
+  return cudaFuncSetAttribute(tok_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TF_SMEM);
+}
+
+// Row slot per window: a multiple of 32 (a warp's rows belong to one window) and of 16 (a window's keys start on a K16 step).
+// The key extent of the score tile is KEYS = 112 columns: (G - 1) * SL + NT must fit.
+void tok_fused_geometry(int NT, int& SL, int& G) {
+  SL = NT <= 32 ? 32 : 64;
+  G = 128 / SL;
+  while (G > 1 && (G - 1) * SL + NT > KEYS) --G;
+}
+bool tok_fused_supported(int NT) { return NT >= 1 && NT <= 64; }
+
+void launch_tok_fused(const TokFusedP& p, cudaStream_t s) {
+  const int grid = (p.B + p.G - 1) / p.G;
+  if (grid <= 0) return;
+  tok_fused_kernel<<<grid, TF_THREADS, TF_SMEM, s>>>(p);
+  count_launch();
+}
+
+}  // namespace lsd

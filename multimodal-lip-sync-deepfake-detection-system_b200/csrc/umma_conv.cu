@@ -537,19 +537,19 @@ const char* umma_conv_config_error(const UmmaConvP& p) {
   return nullptr;
 }
 
-void launch_umma_conv(const UmmaConvP& p, int n_slices, cudaStream_t s, int max_ctas) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    // the opt-in limit (227 KB) covers static + dynamic shared memory; ~3.7 KB is static (barriers, bias, band / group tables)
-    cudaFuncSetAttribute(umma_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024);
-    cudaFuncSetAttribute(umma_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024);
-    attr_set = true;
-  }
+// Function attributes are per device: lsd_create calls this once with the handle's device current.
+cudaError_t umma_conv_device_init() {
+  // the opt-in limit (227 KB) covers static + dynamic shared memory; ~3.7 KB is static (barriers, bias, band / group tables)
+  cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024);
+  if (e == cudaSuccess) e = video_rows_device_init();
+  return e;
+}
+
+void launch_umma_conv(const UmmaConvP& p, int n_slices, cudaStream_t s, int num_sms, int max_ctas) {
   if (const char* why = umma_conv_config_error(p)) { fprintf(stderr, "umma_conv: %s\n", why); abort(); }   // (callers check first)
   const int S = p.MT * 128;
   const int tiles = (int)((p.g.P_total + S - 1) / S);
-  static int num_sms = 0;
-  if (num_sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
   // persistent grid: one CTA per SM (per Cout slice), each walking tiles with stride gridDim.x
   const int budget = (max_ctas > 0 && max_ctas < num_sms) ? max_ctas : num_sms;   // side-stream launches leave SMs to the main stream
   int gx = (budget + n_slices - 1) / n_slices;
@@ -1127,6 +1127,15 @@ __global__ void __launch_bounds__(VR2_THREADS, 2) video_rows_tma_kernel(const T*
   }
 }
 
+cudaError_t video_rows_device_init() {
+  cudaError_t e = cudaSuccess;
+#define VRA(TT, LL) if (e == cudaSuccess) e = cudaFuncSetAttribute(video_rows_tma_kernel<TT, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)
+  VRA(float, 0); VRA(__half, 0); VRA(__nv_bfloat16, 0); VRA(uint8_t, 0);
+  VRA(float, 1); VRA(__half, 1); VRA(__nv_bfloat16, 1); VRA(uint8_t, 1);
+#undef VRA
+  return e;
+}
+
 bool video_rows_bulk_ok(const void* video, int dtype, int layout, int W) {
   const size_t esz = dtype == 0 ? 4 : (dtype == 3 ? 1 : 2);
   const size_t row_bytes = (size_t)W * esz * (layout == 0 ? 1 : 3);
@@ -1135,7 +1144,7 @@ bool video_rows_bulk_ok(const void* video, int dtype, int layout, int W) {
 }
 
 void launch_video_rows(const void* video, int dtype, int layout, const float* lapw, __nv_bfloat16* xs, __nv_bfloat16* xl,
-                       int64_t set_stride, UcGeom g, int H, int W, cudaStream_t s, const int32_t* starts, int n_frames) {
+                       int64_t set_stride, UcGeom g, int H, int W, cudaStream_t s, int num_sms, const int32_t* starts, int n_frames) {
   const size_t esz = dtype == 0 ? 4 : (dtype == 3 ? 1 : 2);
   const size_t row_bytes = (size_t)W * esz * (layout == 0 ? 1 : 3);
   const size_t stage = (((layout == 0 ? 3 : 1) * (size_t)(VR2_ROWS + 2) * row_bytes) + 127) & ~size_t(127);
@@ -1143,15 +1152,11 @@ void launch_video_rows(const void* video, int dtype, int layout, const float* la
     const int bands = (H + VR2_ROWS - 1) / VR2_ROWS;
     const int64_t tiles = (int64_t)g.N * g.T * bands;
     if (tiles == 0) return;
-    static int num_sms = 0;
-    if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
     const size_t smem = stage * VR2_STAGES;
     const int64_t per_sm = 2;   // 128 registers x 256 threads: two resident blocks per SM
     const unsigned grid = (unsigned)std::min<int64_t>(tiles, per_sm * num_sms);
 #define VRT(TT, LL)                                                                                                             \
   do {                                                                                                                          \
-    static bool attr = false;                                                                                                   \
-    if (!attr) { cudaFuncSetAttribute(video_rows_tma_kernel<TT, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; } \
     video_rows_tma_kernel<TT, LL><<<grid, VR2_THREADS, smem, s>>>(reinterpret_cast<const TT*>(video), starts, n_frames, lapw, xs, xl,    \
                                                                   set_stride, g, g.T, H, W, bands, (int)tiles);               \
   } while (0)

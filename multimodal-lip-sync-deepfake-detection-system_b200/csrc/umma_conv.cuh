@@ -122,7 +122,10 @@ int umma_conv_stage_desc_bytes();
 void umma_conv_build_program(const UmmaConvP& p, UcStageDesc* out);
 // nullptr if the kernel supports this parameter block, else the reason (callers turn it into an error code instead of launching)
 const char* umma_conv_config_error(const UmmaConvP& p);
-void launch_umma_conv(const UmmaConvP& p, int n_slices, cudaStream_t s, int max_ctas = 0);
+void launch_umma_conv(const UmmaConvP& p, int n_slices, cudaStream_t s, int num_sms, int max_ctas = 0);
+// per-device one-time setup (opt-in shared-memory limits of the tcgen05 and video_rows kernels); call with the device current
+cudaError_t umma_conv_device_init();
+cudaError_t video_rows_device_init();
 
 // ---- planar-layout glue --------------------------------------------------------------------------
 // fp32 channels-last (N,T,H,W,C) -> padded planar bf16 (plain, or parity-split when parity != 0); pads are NOT written.
@@ -146,7 +149,7 @@ void launch_planar_maxpool(const __nv_bfloat16* x, int64_t x_plane_stride, UcGeo
 // starts != nullptr (interleaved tracks, bulk-copy path only — check video_rows_bulk_ok): window n reads frames
 // starts[n] .. starts[n]+T-1 of an n_frames-long track instead of frames n*T .. n*T+T-1.
 void launch_video_rows(const void* video, int dtype, int layout, const float* lapw, __nv_bfloat16* xs, __nv_bfloat16* xl,
-                       int64_t set_stride, UcGeom g, int H, int W, cudaStream_t s, const int32_t* starts = nullptr, int n_frames = 0);
+                       int64_t set_stride, UcGeom g, int H, int W, cudaStream_t s, int num_sms, const int32_t* starts = nullptr, int n_frames = 0);
 bool video_rows_bulk_ok(const void* video, int dtype, int layout, int W);
 
 inline UcGeom make_geom_ex(int N, int T, int H, int W, int tpad, int oh, int hp_extra, int ow, int wp_extra) {

@@ -166,6 +166,9 @@ class LipSyncModel(nn.Module):
         if self._lsd_ws is None or self._lsd_ws.device != device or self._lsd_ws.numel() < nbytes:
             self._lsd_ws = None
             self._lsd_ws = torch.empty(int(nbytes * 1.05) + 1024, dtype=torch.uint8, device=device)
+            # a fresh allocation may reuse the address of the freed one: the library must not trust remembered padding
+            if self._lsd_handle is not None:
+                _cabi.lib().lsd_workspace_invalidate(self._lsd_handle.ptr)
         return self._lsd_ws
 
     # ------------------------------------------------------------------ forward
