@@ -89,39 +89,174 @@ def _dist():
     return ws, rank, local
 
 
-def cpu_reference_run(steps: int, warmup: int, sample_windows: int):
-    """The reference algorithm (oracle port of LipSyncModel.forward, fp32) on all host cores: windows/s."""
+CPU_SWEEP = (1, 4, 8, 16)
+
+
+def cpu_reference_sweep(steps: int, warmup: int, batches=CPU_SWEEP):
+    """The reference algorithm (oracle port of LipSyncModel.forward, fp32, torch CPU, all host threads) per BASELINE.md §4:
+    `warmup` untimed + `steps` timed forwards at every B of the sweep; per B the best and the median time; the reported
+    throughput is the best over B of B / best_time (the most favourable figure for the baseline)."""
     import lipsync_b200 as lb
     from oracle import lipsync_oracle as orc
     torch.set_num_threads(os.cpu_count() or 1)
     sd = lb.make_synthetic_state_dict(0)
-    video, audio = lb.synthetic_windows(1, sample_windows)
-    for _ in range(warmup):
-        orc.forward(sd, video[:1], audio[:1])
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        orc.forward(sd, video, audio)
-    dt = time.perf_counter() - t0
-    return steps * sample_windows / dt, dt / steps * 1e3, torch.get_num_threads()
+    video, audio = lb.synthetic_windows(1, max(batches))
+    per_b = {}
+    for b in batches:
+        v, a = video[:b], audio[:b]
+        for _ in range(warmup):
+            orc.forward(sd, v, a)
+        ts = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            orc.forward(sd, v, a)
+            ts.append(time.perf_counter() - t0)
+        ts.sort()
+        per_b[b] = {"best_ms": ts[0] * 1e3, "median_ms": ts[len(ts) // 2] * 1e3,
+                    "windows_per_s_best": b / ts[0], "windows_per_s_median": b / ts[len(ts) // 2]}
+    best_b = max(per_b, key=lambda b: per_b[b]["windows_per_s_best"])
+    return per_b, best_b, torch.get_num_threads()
+
+
+def _cpu_baseline_record(per_b, best_b, cores, steps, warmup):
+    r = per_b[best_b]
+    return {"value": r["windows_per_s_best"], "unit": "windows/s", "cores": cores, "kind": "port",
+            "median_value": r["windows_per_s_median"], "best_batch": best_b,
+            "single_window_ms_best": per_b[min(per_b)]["best_ms"], "single_window_ms_median": per_b[min(per_b)]["median_ms"],
+            "per_batch": {str(b): v for b, v in per_b.items()},
+            "sample": (f"{warmup} warm-up + {steps} timed forwards at each B in {list(per_b)} (canonical windows, fp32, torch CPU, "
+                       f"{cores} threads) through the CPU restatement of LipSyncModel.forward (oracle/, pinned on the real reference's "
+                       "goldens; /root/reference does not exist on the GPU box); value = best B / best time")}
 
 
 def run_reference(args, out=sys.stdout):
     ws, rank, _ = _dist()
     if rank != 0:
         return
-    sample = 4
-    steps = max(1, min(args.steps, 3))
-    wps, ms, cores = cpu_reference_run(steps, min(args.warmup, 1), sample)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    per_b, best_b, cores = cpu_reference_sweep(steps, warmup)
+    rec = _cpu_baseline_record(per_b, best_b, cores, steps, warmup)
     line = {
-        "impl": "reference", "metric": "windows_per_sec", "value": wps, "unit": "windows/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": "windows_per_sec", "value": rec["value"], "unit": "windows/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": per_b[best_b]["best_ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference is pure Python/PyTorch; timed through the CPU oracle port of LipSyncModel.forward"},
-        "cpu_baseline": {"value": wps, "unit": "windows/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} steps x {sample} canonical windows, fp32, torch CPU, all host threads"},
-        "e2e": {"value": wps, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": WORKLOAD, "sample_batch": best_b,
+                   "note": ("a step of this arm is ONE forward over a bounded sample of the workload (B in {1,4,8,16} canonical windows, the "
+                            "best B is reported), not the 64-window batch: the reference is pure Python/PyTorch and is timed through the "
+                            "CPU restatement of LipSyncModel.forward on all host threads")},
+        "cpu_baseline": rec,
+        "e2e": {"value": rec["value"], "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), file=out, flush=True)
+
+
+def eager_gpu_run(dev, batch: int, steps: int, warmup: int):
+    """PyTorch eager on the same B200 (cuDNN / cuBLAS under bf16 autocast, channels_last_3d video): the only other GPU
+    implementation of this model.  A stated baseline: the same restated forward the CPU arm runs, moved to
+    the GPU — not part of the product path."""
+    import lipsync_b200 as lb
+    from oracle import lipsync_oracle as orc
+    sd = {k: (v.to(dev).contiguous(memory_format=torch.channels_last_3d) if v.dim() == 5 else v.to(dev))
+          for k, v in lb.make_synthetic_state_dict(0).items()}
+    v, a = lb.synthetic_windows(1, 4)
+    v = v.repeat(batch // 4 + 1, 1, 1, 1, 1)[:batch].to(dev).contiguous(memory_format=torch.channels_last_3d)
+    a = a.repeat(batch // 4 + 1, 1, 1, 1)[:batch].to(dev)
+    res = {}
+    for name, ctx in (("bf16_autocast", lambda: torch.autocast("cuda", dtype=torch.bfloat16)),
+                      ("fp16_autocast", lambda: torch.autocast("cuda", dtype=torch.float16))):
+        try:
+            with torch.no_grad(), ctx():
+                for _ in range(warmup):
+                    orc.forward(sd, v, a)
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    orc.forward(sd, v, a)
+                e1.record()
+                torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / steps
+            res[name] = {"windows_per_s": batch / ms * 1e3, "ms_per_step": ms}
+        except Exception as exc:  # noqa: BLE001  (a baseline leg must never take the bench line down)
+            res[name] = {"error": f"{type(exc).__name__}: {str(exc)[:160]}"}
+    res["what"] = (f"torch {torch.__version__} eager, cuDNN/cuBLAS, B={batch}, inputs resident, {steps} steps after {warmup} warm-ups; "
+                   "same weights and inputs as the main arm")
+    return res
+
+
+def latency_probe(pred, lb, iters: int = 30):
+    """Wall-clock latency of the reference-shaped single-window calls (host numpy in, python float out; every call includes
+    its H2D copy and the D2H read of the result): `_infer_confidence` (predictor.py:212-244, B=1) and
+    `_temporal_smoothed_confidence` (predictor.py:295-331: one full window + three half windows)."""
+    import numpy as np
+    v, a = lb.synthetic_windows(7, 1)
+    v, a = v[0].numpy(), a[0].numpy()
+    out = {}
+    for name, fn in (("infer_confidence_ms", lambda: pred._infer_confidence(v, a)),
+                     ("temporal_smoothed_confidence_ms", lambda: pred._temporal_smoothed_confidence(v, a))):
+        for _ in range(5):
+            fn()
+        ts = []
+        for _ in range(iters):
+            t0 = time.perf_counter()
+            fn()
+            ts.append((time.perf_counter() - t0) * 1e3)
+        ts.sort()
+        out[name] = {"best": ts[0], "median": ts[len(ts) // 2]}
+    out["graphs"] = bool(getattr(pred, "use_cuda_graphs", False))
+    out["what"] = "wall clock around the public call on host numpy inputs, B=1 (and 1+3 windows), after 5 warm-ups"
+    return out
+
+
+def long_video_probe(pred, lb, ws, rank, dev, n_windows: int):
+    """BASELINE.json configs[4]: `n_windows` sliding windows (stride 8) of ONE synthetic uint8 track, contiguous block partition
+    over the ranks (strong scaling), windows built on the device, one all-gather of the fp32 logits, SHA-256 of the gathered
+    logits (identical across shardings).  The track is resident in HBM (rank-local span)."""
+    import hashlib
+    import torch.distributed as dist
+    stride, T = 8, 32
+    n_frames = stride * (n_windows - 1) + T + 16
+    lo, hi = lb.partition_windows(n_windows, ws, rank)
+    f_lo, f_hi = stride * lo, stride * max(hi - 1, lo) + T
+    g = torch.Generator(device=dev).manual_seed(5)
+    track = torch.empty(f_hi - f_lo, 96, 96, 3, dtype=torch.uint8, device=dev)
+    blk = 4096
+    for f0 in range(0, n_frames, blk):          # same random stream on every rank -> identical track across shardings
+        chunk = torch.randint(0, 256, (min(blk, n_frames - f0), 96, 96, 3), dtype=torch.uint8, device=dev, generator=g)
+        a, b = max(f0, f_lo), min(f0 + chunk.shape[0], f_hi)
+        if b > a:
+            track[a - f_lo:b - f_lo] = chunk[a - f0:b - f0]
+    del chunk
+    ta_full = int(n_frames / 15 * 100)
+    gm = torch.Generator().manual_seed(6)
+    mel = (-80.0 * torch.rand(1, 80, ta_full, generator=gm)).to(dev)
+    starts_abs = [stride * i for i in range(lo, hi)]
+
+    def score_range(_lo, _hi):
+        return pred.score_track_logits(track, [s - f_lo for s in starts_abs], mel, n_frames, audio_starts_from=starts_abs)
+
+    def run():
+        return pred.score_windows_sharded(n_windows, score_range, ws, rank)
+
+    run()
+    torch.cuda.synchronize(dev)
+    if ws > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    logits = run()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if ws > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    lg = logits.cpu()
+    del track
+    return {"windows": n_windows, "n_gpus": ws, "scaling": "strong", "ms": ms, "windows_per_s": n_windows / ms * 1e3,
+            "logits_sha256_16": hashlib.sha256(lg.numpy().tobytes()).hexdigest()[:16], "fake_votes": int((lg < 0).sum()),
+            "what": "uint8 track resident in HBM (rank-local span), windows built on the device, batches pipelined, one all-gather of fp32 logits"}
 
 
 def _claim_stdout():
@@ -143,6 +278,9 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-gpu", action="store_true")
+    ap.add_argument("--no-config5", action="store_true")
+    ap.add_argument("--config5-windows", type=int, default=10000)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args, out)
@@ -169,7 +307,11 @@ def main():
     pred = lb.Predictor(model, batch_size=B)
 
     # synthetic inputs (host, pinned) and their device-resident copies; distinct data per rank
-    vh, ah = lb.synthetic_windows(100 + rank, 4)
+    # (video values are k/255 for integer k, exactly what the reference's window builder produces from uint8 mouth crops:
+    #  astype(float32) / 255.0, video.py:552-556 — timing does not depend on the values, the e2e transport does)
+    _, ah = lb.synthetic_windows(100 + rank, 4)
+    gv = torch.Generator().manual_seed(100 + rank)
+    vh = torch.randint(0, 256, (4, 3, 32, 96, 96), dtype=torch.uint8, generator=gv).to(torch.float32) / 255.0
     vh = vh.repeat(B // 4 + 1, 1, 1, 1, 1)[:B].contiguous().pin_memory()
     ah = ah.repeat(B // 4 + 1, 1, 1, 1)[:B].contiguous().pin_memory()
     vd, ad = vh.to(dev), ah.to(dev)
@@ -191,10 +333,14 @@ def main():
         if ws > 1:
             dist.all_gather_into_tensor(gathered, local_logits.view(-1))
 
+    e2e_h2d_bytes, e2e_transport = [0], ["fp32"]
+
     def run_e2e(steps):
         """Public API on HOST buffers: Predictor.score_batches uploads every step's windows from pinned host memory
         (copy stream, overlapped with the previous step's scoring) and reads every step's logits back."""
         outs = pred.score_batches((vh, ah) for _ in range(steps))
+        e2e_h2d_bytes[0] = int(getattr(pred, "last_h2d_bytes_per_batch", vh.numel() * 4 + ah.numel() * 4))
+        e2e_transport[0] = getattr(pred, "last_transport", "fp32")
         if ws > 1:
             last = outs[-1].to(dev)
             dist.all_gather_into_tensor(gathered_e2e, last)
@@ -283,16 +429,32 @@ def main():
     ms, launches, prof, clocks = timed(step_resident, K, profile=True, finalize=gather_resident)
     ms_e2e, _, _, _ = timed(run_e2e, K, whole=True)
     ms_trk, _, _, _ = timed(run_e2e_track, K, whole=True)
+    # sustained: the same resident step back to back for >= ~1.5 s (the K-step region above lasts ~60 ms: a burst figure, taken
+    # before the 1000 W power cap pulls the SM clock down)
+    k_sus = max(K, int(1500.0 / max(ms / K, 0.05)))
+    if ws > 1:
+        local_logits = torch.empty(1, B, dtype=torch.float32, device=dev)     # (the sustained run keeps only the last batch)
+    ms_sus, _, _, clocks_sus = timed(step_resident, k_sus)
     value = ws * B * K / (ms / 1e3)
     e2e = ws * B * K / (ms_e2e / 1e3)
     e2e_trk = ws * B * K / (ms_trk / 1e3)
+
+    # latency of the reference-shaped single-window calls (predictor.py:212-244, 295-331): host numpy in, python float out
+    lat = None
+    if args.precision == "bf16":
+        lat = latency_probe(pred, lb)
+    # BASELINE.json configs[4]: 10 000 sliding windows of one uint8 track, sharded over the ranks (strong scaling)
+    c5 = None
+    if not args.no_config5:
+        c5 = long_video_probe(pred, lb, ws, rank, dev, args.config5_windows)
 
     if rank == 0:
         peaks, peak_src = _peaks()
         kern_ms, kern_n, kern_flops = prof
         # dominant kernel class: the implicit-GEMM convolution/linear kernel (tensor-bound on the bf16 path)
         achieved = (kern_flops / max(kern_n, 1)) / ((kern_ms / max(kern_n, 1)) * 1e-3) / 1e12 if kern_n else 0.0
-        peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+        peak = float(peaks.get("bf16_tflops", 1590.0))                       # burst: the timed region lasts ~60 ms at full clocks
+        peak_sus = float(peaks.get("bf16_tflops_sustained", peak))
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
@@ -304,28 +466,43 @@ def main():
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "precision": args.precision,
                        "l2": "inputs (226 MB fp32 video per step) exceed the 126 MB L2; no explicit flush",
+                       "timed_region": f"{K} steps = {ms:.0f} ms: burst conditions (see `sustained` for >= 1.5 s back to back)",
                        "parallelism": f"dp{ws} (independent windows; all-gather of fp32 logits only)"},
             "gpu_launches": launches,
             "clocks": clocks,
+            "sustained": {"value": ws * B * k_sus / (ms_sus / 1e3), "unit": "windows/s", "steps": k_sus, "ms_per_step": ms_sus / k_sus,
+                          "seconds": ms_sus / 1e3, "clocks": clocks_sus},
             "e2e": {"value": e2e, "unit": "windows/s", "ms_per_step": ms_e2e / K,
-                    "h2d_bytes_per_step": vh.numel() * 4 + ah.numel() * 4, "d2h_bytes_per_step": (ws if ws > 1 else 1) * B * 4,
-                    "api": "Predictor.score_batches on pinned host fp32 windows (per step: H2D of the windows on a copy stream, forward, D2H of the logits)"},
+                    "h2d_bytes_per_step": e2e_h2d_bytes[0], "d2h_bytes_per_step": (ws if ws > 1 else 1) * B * 4,
+                    "api": ("Predictor.score_batches on pinned host fp32 windows (per step: exact-uint8 detection + packing on the host "
+                            "threads when the windows are u8/255 as video.py:552-556 produces them, H2D on a copy stream, forward, D2H "
+                            "of the logits)"),
+                    "transport": e2e_transport[0]},
             "e2e_track_u8": {"value": e2e_trk, "unit": "windows/s", "ms_per_step": ms_trk / K,
                              "h2d_bytes_per_step": track_h.numel() + mel_h.numel() * 4, "d2h_bytes_per_step": B * 4,
                              "api": "Predictor.score_track_logits on a pinned host uint8 mouth-crop track (windows built on the device, lsd_score_windows)"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
-                         "kernel": ("umma_conv_kernel, the 9 launches of the 3-D conv visual encoder (stem + layer1-4: 26.77 of the 31.29 "
+                         "peak_sustained": peak_sus, "frac_of_sustained": achieved / peak_sus,
+                         "traffic": traffic,
+                         "traffic_source": "static: per-launch dram__bytes_read+write from the committed ncu --set full capture (profiles/traffic.json), not measured in this run",
+                         "peak_source": f"{peak_src} bf16_tflops (burst: kernels timed in a {ms:.0f} ms region at full clocks)",
+                         "kernel": ("umma_conv_kernel, the launches of the 3-D conv visual encoder (stem + layer1-4: 26.77 of the 31.29 "
                                     "GFLOP per window); CUDA events on the launch stream"
                                     if args.precision == "bf16" else "conv_f32_kernel (all launches, CUDA events on the launch stream)"),
                          "kernel_ms_per_step": kern_ms / K, "kernel_launches_per_step": kern_n / K,
                          "kernel_share_of_step": kern_ms / ms,
-                         "whole_model_tflops": FLOP_PER_WINDOW * B * K / (ms / 1e3) / 1e12},
+                         "whole_model_tflops": FLOP_PER_WINDOW * B * K / (ms / 1e3) / 1e12,
+                         "whole_model_frac": FLOP_PER_WINDOW * B * K / (ms / 1e3) / 1e12 / peak},
         }
+        if lat is not None:
+            line["latency"] = lat
+        if c5 is not None:
+            line["config5"] = c5
         if ws == 1 and not args.no_cpu_baseline:
-            wps, cms, cores = cpu_reference_run(2, 1, 4)
-            line["cpu_baseline"] = {"value": wps, "unit": "windows/s", "cores": cores, "kind": "port",
-                                    "sample": "2 steps x 4 canonical windows through the CPU oracle port (fp32 torch, all host threads)"}
+            per_b, best_b, cores = cpu_reference_sweep(10, 3)
+            line["cpu_baseline"] = _cpu_baseline_record(per_b, best_b, cores, 10, 3)
+        if ws == 1 and not args.no_eager_gpu and args.precision == "bf16":
+            line["eager_gpu"] = eager_gpu_run(dev, B, 5, 3)
         print(json.dumps(line), file=out, flush=True)
     if ws > 1:
         dist.barrier()

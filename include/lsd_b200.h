@@ -175,6 +175,12 @@ int lsd_vad_mask(lsd_handle* h, const float* energy, int n_frames, float thresho
 int lsd_stage_info(lsd_handle* h, const char* name, size_t* offset_bytes, int64_t* numel, int* dtype);
 int lsd_stage_count(lsd_handle* h);
 const char* lsd_stage_name(lsd_handle* h, int i);
+/* Activation tensor of the last tensor-core (BF16) lsd_forward, kept in the workspace in the padded planar bf16 layout
+ * (DESIGN.md §4), converted to fp32 channels-last (N, T, H_full, W_full, C) for per-stage parity tests.  Names: "x1" (stem +
+ * pool), "y1".."y4" (visual_encoder.layer1..4; y1..y3 are parity-split: pass the full-resolution extent), "ya4" (+ "ya4_lo":
+ * audio_encoder.layer4), "hf_f" / "hf_b" (high-frequency branch), "art_b", "artd_b" (artifact branch). */
+int lsd_planar_stage_read(lsd_handle* h, const char* name, const char* name_lo_or_null, const void* workspace, float* out,
+                          int64_t out_elems, int H_full, int W_full, void* stream);
 /* Number of kernels this library launched on behalf of the handle since creation. */
 int64_t lsd_launch_count(lsd_handle* h);
 /* Roofline instrumentation (bench.py): while enabled, every launch of the dominant kernel class (the implicit-GEMM

@@ -854,6 +854,25 @@ static int token_path_bf16(const BCtx& b, const Shapes& s) {
     fp.vec = h->tokf_vec;
     fp.B = B; fp.NT = NT;
     tok_fused_geometry(NT, fp.SL, fp.G);
+    if (getenv("LSD_TOKF_TRACE")) {
+      // debug: phase timestamps of CTA 0 (MMA warp: [start, issue-end] per MMA phase; compute warp 0: [accumulator arrival,
+      // hand-over] per compute phase); prints after a sync, never enabled in timed runs
+      static long long* dbuf = nullptr;
+      if (!dbuf) cudaMalloc(&dbuf, 384 * sizeof(long long));
+      cudaMemsetAsync(dbuf, 0, 384 * sizeof(long long), st);
+      fp.dbg = dbuf;
+      launch_tok_fused(fp, st);
+      std::vector<long long> hv(384);
+      cudaMemcpyAsync(hv.data(), dbuf, 384 * sizeof(long long), cudaMemcpyDeviceToHost, st);
+      cudaStreamSynchronize(st);
+      const long long t0 = hv[192];
+      fprintf(stderr, "[tokf] compute phases (wait-return, hand-over) cycles from start:");
+      for (int i = 0; i < 96 && hv[192 + 2 * i + 1]; ++i) fprintf(stderr, " (%lld,%lld)", hv[192 + 2 * i] - t0, hv[192 + 2 * i + 1] - t0);
+      fprintf(stderr, "\n[tokf] mma phases (start, issue-end):");
+      for (int i = 0; i < 96 && hv[2 * i + 1]; ++i) fprintf(stderr, " (%lld,%lld)", hv[2 * i] - t0, hv[2 * i + 1] - t0);
+      fprintf(stderr, "\n");
+      return 0;
+    }
     launch_tok_fused(fp, st);
     return 0;
   }
@@ -903,6 +922,15 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   build_plan(s, P);
   if (P.f32.cursor > ws_bytes) return lsd_fail(h, LSD_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", P.f32.cursor, ws_bytes);
   h->stages = P.f32.stages;
+  h->planar_stages.clear();
+  for (const auto& kv : P.pb) {
+    const PBuf& b = kv.second;
+    PlanarStage ps;
+    ps.off = b.off; ps.C = b.C; ps.sets = b.sets; ps.plane_stride = b.plane_stride; ps.set_stride = b.set_stride; ps.origin = b.origin;
+    ps.N = b.g.N; ps.T = b.g.T; ps.H = b.g.H; ps.W = b.g.W; ps.ot = b.g.ot; ps.oh = b.g.oh; ps.hp_extra = b.g.HP - b.g.H - b.g.oh;
+    ps.ow = b.g.ow; ps.wp_extra = b.g.RW - b.g.W - b.g.ow;
+    h->planar_stages[kv.first] = ps;
+  }
   int rc0 = 0;
   if ((rc0 = ws_prepare(h, s, P, ws, ws_bytes, st, pipe_parity == 1 ? 1 : 0))) return rc0;
   BCtx b{h, ws, &P, st};
@@ -1057,6 +1085,29 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   }
   if (pipe_parity >= 0) cudaEventRecord(h->ev_tail_done[pipe_parity], st);
   }
+  return 0;
+}
+
+// Introspection (tests): a planar bf16 buffer of the last tensor-core forward -> fp32 channels-last (N, T, Hf, Wf, C).
+// Parity-split buffers (4 plane sets) are re-interleaved: (Hf, Wf) is the full-resolution extent; h-parity-only splits (the
+// stride-(2,1) audio layers) have Wf equal to the plane width.  name_lo: optional low part of a (hi, lo) pair, added in.
+int planar_stage_read(lsd_handle* h, const char* name, const char* name_lo, const char* ws, float* out, int64_t out_elems, int Hf, int Wf,
+                      cudaStream_t st) {
+  auto it = h->planar_stages.find(name);
+  if (it == h->planar_stages.end()) return lsd_fail(h, LSD_ERR_ARG, "unknown planar stage %s", name);
+  const PlanarStage& ps = it->second;
+  const PlanarStage* pl = nullptr;
+  if (name_lo && *name_lo) {
+    auto il = h->planar_stages.find(name_lo);
+    if (il == h->planar_stages.end()) return lsd_fail(h, LSD_ERR_ARG, "unknown planar stage %s", name_lo);
+    pl = &il->second;
+  }
+  const UcGeom g = make_geom_ex(ps.N, ps.T, ps.H, ps.W, ps.ot, ps.oh, ps.hp_extra, ps.ow, ps.wp_extra);
+  if (ps.sets == 1) { Hf = ps.H; Wf = ps.W; }
+  if ((int64_t)ps.N * ps.T * Hf * Wf * ps.C != out_elems) return lsd_fail(h, LSD_ERR_SHAPE, "stage %s holds %lld elements", name, (long long)ps.N * ps.T * Hf * Wf * ps.C);
+  const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(ws + ps.off) + ps.origin;
+  const __nv_bfloat16* xlo = pl ? reinterpret_cast<const __nv_bfloat16*>(ws + pl->off) + pl->origin : nullptr;
+  launch_unpack_planar_any(x, xlo, ps.plane_stride, ps.set_stride, g, ps.C, ps.sets, Hf, Wf, out, st);
   return 0;
 }
 

@@ -591,6 +591,17 @@ extern "C" int lsd_vad_mask(lsd_handle* h, const float* energy, int n_frames, fl
 // ================================================================================================
 // Introspection
 // ================================================================================================
+extern "C" int lsd_planar_stage_read(lsd_handle* h, const char* name, const char* name_lo_or_null, const void* workspace, float* out,
+                                     int64_t out_elems, int H_full, int W_full, void* stream) {
+  if (!h || !name || !workspace || !out) return lsd_fail(h, LSD_ERR_ARG, "lsd_planar_stage_read: null argument");
+  ENTER_DEVICE(h);
+  int rc = planar_stage_read(h, name, name_lo_or_null, reinterpret_cast<const char*>(workspace), out, out_elems, H_full, W_full,
+                             reinterpret_cast<cudaStream_t>(stream));
+  if (rc) return rc;
+  CUDA_OK(h, cudaGetLastError());
+  return LSD_OK;
+}
+
 extern "C" int lsd_workspace_invalidate(lsd_handle* h) {
   if (!h) return LSD_ERR_ARG;
   h->ws_sig[0].ptr = nullptr; h->ws_sig[1].ptr = nullptr;

@@ -47,6 +47,13 @@ struct Prof {             // CUDA-event brackets around the dominant kernel clas
   }
 };
 
+struct PlanarStage {      // planar bf16 buffer of the last tensor-core forward (introspection: lsd_planar_stage_read)
+  size_t off = 0;
+  int C = 0, sets = 1;
+  int64_t plane_stride = 0, set_stride = 0, origin = 0;
+  int N = 0, T = 0, H = 0, W = 0, ot = 0, oh = 0, hp_extra = 0, ow = 0, wp_extra = 0;
+};
+
 struct WsSig { const void* ptr = nullptr; size_t bytes = 0; int shape[6] = {0, 0, 0, 0, 0, 0}; };
 
 struct lsd_handle {
@@ -72,6 +79,7 @@ struct lsd_handle {
   cudaStream_t tail_stream = nullptr;
   cudaEvent_t ev_front[2] = {nullptr, nullptr}, ev_tail_done[2] = {nullptr, nullptr};
   std::vector<Stage> stages;
+  std::map<std::string, PlanarStage> planar_stages;
   std::vector<int32_t> idx_host;
   Prof prof;
   cudaStream_t side_stream = nullptr;      // artifact branch runs here, concurrently with the token path
@@ -120,3 +128,5 @@ int score_batch_bf16(lsd_handle* h, const uint8_t* track, int n_frames, const in
                      const float* mel_full, int Ta_full, int nb, int T, int H, int W, int F, int Ta, float* logits,
                      char* ws, size_t ws_bytes, cudaStream_t st, int pipe_parity = -1);
 int ensure_pipeline(lsd_handle* h);
+int planar_stage_read(lsd_handle* h, const char* name, const char* name_lo, const char* ws, float* out, int64_t out_elems, int Hf, int Wf,
+                      cudaStream_t st);

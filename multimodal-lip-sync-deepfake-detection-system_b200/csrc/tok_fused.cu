@@ -127,8 +127,11 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tok_fused_kernel(const __grid_c
     const uint64_t desc_hi = ((uint64_t)8 << 32) | ((uint64_t)1 << 46);   // SBO = 128 B, descriptor version 1
     uint32_t par_c = 0;
     int ws = 0;                                                           // weight stages consumed so far
-    auto wait_cmp = [&]() { mbar_wait(&bar_cmp, par_c); par_c ^= 1u; tc_fence_after(); };
-    auto done = [&]() { mma_commit_pred(&bar_mma, leader); };
+    // debug (p.dbg != nullptr, CTA 0): clock64 at the start and at the issue-end of every MMA phase
+    long long* dbg = (p.dbg && blockIdx.x == 0 && lane == 0) ? reinterpret_cast<long long*>(p.dbg) : nullptr;
+    int dbg_n = 0;
+    auto wait_cmp = [&]() { mbar_wait(&bar_cmp, par_c); par_c ^= 1u; tc_fence_after(); if (dbg && dbg_n < 96) dbg[2 * dbg_n] = clock64(); };
+    auto done = [&]() { mma_commit_pred(&bar_mma, leader); if (dbg && dbg_n < 96) { dbg[2 * dbg_n + 1] = clock64(); ++dbg_n; } };
     auto desc = [&](uint32_t byte_addr, uint32_t lbo_bytes) -> uint64_t {
       return desc_hi | (uint64_t)(((lbo_bytes >> 4) & 0x3FFFu) << 16) | (uint64_t)((byte_addr >> 4) & 0x3FFFu);
     };
@@ -215,12 +218,17 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tok_fused_kernel(const __grid_c
     const uint32_t row16 = (uint32_t)row * 16u;
     float* grow = p.tok + ((size_t)(valid ? win : 0) * p.NT + (valid ? lrow : 0)) * TF_D;
     uint32_t par_m = 0;
-    auto wait_mma = [&]() { mbar_wait(&bar_mma, par_m); par_m ^= 1u; tc_fence_after(); };
+    // debug (p.dbg != nullptr, CTA 0, warp 0): clock64 when an accumulator arrives and when the compute phase hands over
+    long long* dbg = (p.dbg && blockIdx.x == 0 && warp == 0 && lane == 0) ? reinterpret_cast<long long*>(p.dbg) + 192 : nullptr;
+    int dbg_n = 0;
+    if (dbg) dbg[0] = clock64();
+    auto wait_mma = [&]() { mbar_wait(&bar_mma, par_m); par_m ^= 1u; tc_fence_after(); if (dbg && dbg_n < 96) dbg[2 * dbg_n] = clock64(); };
     auto done = [&]() {
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_cmp);
+      if (dbg && dbg_n < 96) { dbg[2 * dbg_n + 1] = clock64(); ++dbg_n; }
     };
     const float* cum_all = p.vec + (size_t)TF_LAYERS * TF_VEC_LAYER;
 

@@ -39,7 +39,7 @@ struct TokFusedP {
   const float* vec;           // device: per layer [ln1_g 256 | ln1_b 256 | ln2_g 256 | ln2_b 256 | qkv_bias 768 (packed order) | ff1_bias 1024],
                               //         then (2*TF_LAYERS + 1) cumulative bias vectors of 256 (see tok_fused.cu)
   int B, NT, SL, G;           // windows, tokens per window (T+1), row slot per window (32 or 64), windows per CTA
-  float* dbg;                 // optional debug dump (tests): see tok_fused.cu
+  void* dbg;                  // optional (LSD_TOKF_TRACE): 384 x int64 of phase timestamps of CTA 0, see tok_fused.cu
 };
 constexpr int TF_VEC_LAYER = 4 * 256 + 768 + 1024;
 

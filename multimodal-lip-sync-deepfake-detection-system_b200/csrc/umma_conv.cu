@@ -618,6 +618,44 @@ void launch_unpack_planar(const __nv_bfloat16* x, int64_t plane_stride, UcGeom g
   count_launch();
 }
 
+// Introspection: any planar buffer (plain, or parity-split with 4 plane sets) -> fp32 channels-last (N, T, Hf, Wf, C)
+__global__ void unpack_planar_any_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ xlo, int64_t plane_stride,
+                                         int64_t set_stride, UcGeom g, int C, int sets, int Hf, int Wf, float* __restrict__ y, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int nch = C / 8;
+  const int chunk = (int)(i % nch);
+  int64_t r = i / nch;
+  const int64_t row = r;
+  const int w = (int)(r % Wf); r /= Wf;
+  const int h = (int)(r % Hf); r /= Hf;
+  const int t = (int)(r % g.T);
+  const int n = (int)(r / g.T);
+  int64_t src;
+  if (sets == 1) src = uc_flat(g, n, t, h, w) * 8;
+  else if (Wf == g.W) src = (int64_t)((h & 1) * 2) * set_stride + uc_flat(g, n, t, h >> 1, w) * 8;          // h-parity split
+  else src = (int64_t)((h & 1) * 2 + (w & 1)) * set_stride + uc_flat(g, n, t, h >> 1, w >> 1) * 8;          // (h, w)-parity split
+  src += (int64_t)chunk * plane_stride;
+  float f[8];
+  unpack8(*reinterpret_cast<const uint4*>(x + src), f);
+  if (xlo) {
+    float fl[8];
+    unpack8(*reinterpret_cast<const uint4*>(xlo + src), fl);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] += fl[e];
+  }
+  float4* o = reinterpret_cast<float4*>(y + row * C + chunk * 8);
+  o[0] = make_float4(f[0], f[1], f[2], f[3]);
+  o[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+void launch_unpack_planar_any(const __nv_bfloat16* x, const __nv_bfloat16* xlo, int64_t plane_stride, int64_t set_stride, UcGeom g, int C, int sets,
+                              int Hf, int Wf, float* y, cudaStream_t s) {
+  const int64_t total = (int64_t)g.N * g.T * Hf * Wf * (C / 8);
+  if (total == 0) return;
+  unpack_planar_any_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, xlo, plane_stride, set_stride, g, C, sets, Hf, Wf, y, total);
+  count_launch();
+}
+
 // Deterministic mean: one block per (row, chunk); threads stride over the row's positions, fixed-order tree in shared memory.
 __global__ void planar_mean_kernel(const __nv_bfloat16* __restrict__ x, int64_t plane_stride, UcGeom g, float* __restrict__ y, int ld,
                                    int per_window) {

@@ -133,6 +133,9 @@ void launch_pack_planar(const float* x, __nv_bfloat16* y, int64_t plane_stride, 
                         int parity, cudaStream_t s);
 // padded planar bf16 (plain) -> fp32 channels-last rows (valid positions only)
 void launch_unpack_planar(const __nv_bfloat16* x, int64_t plane_stride, UcGeom g, int C, float* y, int ld, cudaStream_t s);
+// introspection: plain or parity-split planar buffer (+ optional low part) -> fp32 channels-last (N, T, Hf, Wf, C)
+void launch_unpack_planar_any(const __nv_bfloat16* x, const __nv_bfloat16* xlo, int64_t plane_stride, int64_t set_stride, UcGeom g, int C, int sets,
+                              int Hf, int Wf, float* y, cudaStream_t s);
 // mean over `group` consecutive valid positions -> fp32 y[(row) * ld + c]; per_window != 0: one row per window (mean over T*H*W),
 // else one row per (n,t) (mean over H*W).
 void launch_planar_mean(const __nv_bfloat16* x, int64_t plane_stride, UcGeom g, int C, float* y, int ld, int per_window, cudaStream_t s);

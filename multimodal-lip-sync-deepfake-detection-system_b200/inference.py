@@ -21,6 +21,7 @@ import numpy as np
 import torch
 
 from . import _cabi
+from . import aggregate as _agg
 from .model import LipSyncModel
 
 
@@ -173,38 +174,13 @@ class Predictor:
 
     # ------------------------------------------------------------------ aggregation helpers (host numpy, as the reference)
     def _robust_confidence(self, confidences: List[float]) -> float:
-        if not confidences:
-            return 0.5
-        arr = np.asarray(confidences, dtype=np.float32)
-        if self.confidence_smoothing == "none":
-            return float(arr.mean())
-        if self.confidence_smoothing == "median":
-            return float(np.median(arr))
-        n = int(arr.size)
-        k = int(n * self.trim_ratio)
-        if k <= 0 or (2 * k) >= n:
-            return float(arr.mean())
-        arr_sorted = np.sort(arr)
-        return float(arr_sorted[k: n - k].mean())
+        """predictor.py:246-260 (single implementation: `lipsync_b200.aggregate._robust`)."""
+        return _agg._robust(confidences, self.confidence_smoothing, self.trim_ratio)
 
     def _speech_weighted_confidence(self, confidences: List[float], speaking_scores: List[float],
                                     vad_weights: Optional[List[float]] = None) -> float:
-        if not confidences:
-            return 0.5
-        if len(confidences) != len(speaking_scores):
-            return self._robust_confidence(confidences)
-        conf = np.asarray(confidences, dtype=np.float32)
-        speech = np.clip(np.asarray(speaking_scores, dtype=np.float32), 0.0, 1.0)
-        if vad_weights is not None and len(vad_weights) == len(confidences):
-            vad_arr = np.clip(np.asarray(vad_weights, dtype=np.float32), 0.0, 1.0)
-            combined_speech = 0.7 * vad_arr + 0.3 * speech
-        else:
-            combined_speech = speech
-        weights = np.clip(0.2 + 0.8 * combined_speech, 0.2, 1.0)
-        denom = float(weights.sum())
-        if denom <= 1e-8:
-            return self._robust_confidence(confidences)
-        return float(np.dot(conf, weights) / denom)
+        """predictor.py:262-293 (single implementation: `lipsync_b200.aggregate._speech_weighted`)."""
+        return _agg._speech_weighted(confidences, speaking_scores, vad_weights, self.confidence_smoothing, self.trim_ratio)
 
     @staticmethod
     def _smoothing_windows(t_v: int, t_a: int) -> Tuple[List[Tuple[int, int, int, int]], List[Tuple[int, int]]]:

@@ -304,6 +304,16 @@ class LipSyncModel(nn.Module):
         esz = 4 if dt.value == _cabi.LSD_F32 else 2
         return self._lsd_ws[off.value: off.value + numel.value * esz].view(tdt)
 
+    def planar_stage(self, name: str, shape, lo: Optional[str] = None) -> Tensor:
+        """fp32 channels-last copy `(N, T, H, W, C)` of a planar bf16 activation buffer of the last tensor-core forward
+        (`lsd_planar_stage_read`); `lo`: name of the low part of a (hi, lo) pair."""
+        h = self._lsd_handle
+        out = torch.empty(tuple(int(x) for x in shape), dtype=torch.float32, device=self._lsd_ws.device)
+        rc = _cabi.lib().lsd_planar_stage_read(h.ptr, name.encode(), lo.encode() if lo else None, self._lsd_ws.data_ptr(), out.data_ptr(),
+                                               out.numel(), int(shape[2]), int(shape[3]), torch.cuda.current_stream(out.device).cuda_stream)
+        _cabi.check(h.ptr, rc)
+        return out
+
     def stage_names(self):
         h = self._lsd_handle
         L = _cabi.lib()

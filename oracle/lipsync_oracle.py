@@ -131,7 +131,7 @@ def lerp_tokens(a: Tensor, t_out: int) -> Tensor:
     if t_in == t_out:
         return a
     scale = t_in / t_out
-    idx = torch.arange(t_out, dtype=torch.float32)
+    idx = torch.arange(t_out, dtype=torch.float32, device=a.device)
     src = ((idx + 0.5) * scale - 0.5).clamp_(min=0.0)
     i0 = src.floor().to(torch.int64).clamp_(max=t_in - 1)
     i1 = (i0 + 1).clamp_(max=t_in - 1)
