@@ -853,7 +853,7 @@ static int token_path_bf16(const BCtx& b, const Shapes& s) {
     fp.layer_bytes = h->tokf_layer_bytes;
     fp.vec = h->tokf_vec;
     fp.B = B; fp.NT = NT;
-    tok_fused_geometry(NT, fp.SL, fp.G);
+    tok_fused_geometry(NT, fp.SL, fp.G, fp.KW);
     if (getenv("LSD_TOKF_TRACE")) {
       // debug: phase timestamps of CTA 0 (MMA warp: [start, issue-end] per MMA phase; compute warp 0: [accumulator arrival,
       // hand-over] per compute phase); prints after a sync, never enabled in timed runs

@@ -35,19 +35,21 @@ using namespace umma;
 
 namespace {
 
-constexpr int TF_THREADS = 320;
-constexpr int TF_RING = 3;
+constexpr int TF_CWARPS = 16;                        // compute warps: 4 per TMEM lane quarter
+constexpr int TF_THREADS = (TF_CWARPS + 2) * 32;     // + weight producer + MMA issuer
+constexpr int TF_RING = 5;
 constexpr uint32_t PLANE = 2048;                     // one 8-channel plane of a 128-row operand
 constexpr uint32_t OFF_ALN = 0;                      // LayerNorm output, K = 256: 32 planes
 constexpr uint32_t OFF_QK = 65536;                   // Q0 K0 Q1 K1: 4 planes each (hd = 32); aliased by ATT (K = 64: 8 planes) after S
-constexpr uint32_t OFF_VT = OFF_QK + 32768;          // V^T of the two heads: [key plane (14)][32 hd rows][8 keys], 8 KB per head
-constexpr uint32_t OFF_P = OFF_VT + 16384;           // P of the two heads, K = 112 keys: 14 planes each; aliased by the FF chunk (K = 128)
-constexpr uint32_t P_HEAD = 14 * PLANE;
+constexpr uint32_t OFF_VT = OFF_QK + 32768;          // V^T of the two heads: [key plane (16)][32 hd rows][8 keys], 8 KB per head
+constexpr uint32_t OFF_P = OFF_VT + 16384;           // P of the two heads, keys relative to the row's own window: <= 8 planes (16 KB) each
+constexpr uint32_t P_HEAD = 8 * PLANE;
+constexpr uint32_t OFF_FF = OFF_VT;                  // GELU'd FF chunk (K = 128: 16 planes = 32 KB) aliases V^T + the first P buffer
+constexpr uint32_t OFF_RED = OFF_P;                  // LayerNorm partial sums (4 KB) alias P
 constexpr uint32_t OFF_RING = OFF_P + 2 * P_HEAD;
 constexpr uint32_t TF_SMEM = OFF_RING + TF_RING * TF_SLOT_BYTES;
-static_assert(2 * P_HEAD >= 16 * PLANE, "the FF chunk operand must fit in the P region");
+static_assert(OFF_RING - OFF_FF >= 16 * PLANE, "the FF chunk operand must fit in the V^T + P region");
 static_assert(TF_SMEM <= 225 * 1024, "shared-memory budget");
-constexpr int KEYS = 112;                            // key extent of S / P / V^T (7 K16 steps)
 constexpr uint32_t X_COL = 0, ACC_COL = 256;
 
 __host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
@@ -75,11 +77,33 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void st_shared_u16(uint32_t addr, unsigned short v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory"); }
+__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory"); return v; }
 // 8 consecutive fp32 -> one 16-byte fp16 row piece of a plane
 __device__ __forceinline__ void st_plane8(uint32_t addr, const float* v) {
   st_shared_v4(addr, pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// v[0..32) += p[0..32)  (p 16-byte aligned, read-only parameters: vector loads through the read-only path)
+__device__ __forceinline__ void add32(float* v, const float* p) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p) + e);
+    v[4 * e] += t.x; v[4 * e + 1] += t.y; v[4 * e + 2] += t.z; v[4 * e + 3] += t.w;
+  }
+}
+// Exact-erf GELU (approximate='none', temporal.py:39-49 / nn.TransformerEncoderLayer activation="gelu") with erf from
+// Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7): two MUFU (rcp, ex2) + 8 FMA instead of erff's ~30 instructions — the FFN
+// epilogue (1024 activations per token and layer) was the largest compute phase of the kernel.  The result is rounded to fp16.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float w = poly * t * __expf(-z * z);          // = 1 - erf(|x| / sqrt 2) = erfc
+  return 0.5f * x * (x >= 0.f ? 2.0f - w : w);         // 1 + erf(x / sqrt 2), without cancellation for x < 0
+}
 
 }  // namespace
 
@@ -89,20 +113,22 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tok_fused_kernel(const __grid_c
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sbase = smem_u32(smem);
+  constexpr int W_PROD = TF_CWARPS, W_MMA = TF_CWARPS + 1;
 
   if (tid == 0) {
     for (int i = 0; i < TF_RING; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     mbar_init(&bar_mma, 1);
-    mbar_init(&bar_cmp, 8);
+    mbar_init(&bar_cmp, TF_CWARPS);
     fence_barrier_init();
   }
-  if (warp == 9) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
+  if (warp == W_MMA) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  const int G = p.G, SL = p.SL, KW = p.KW;
 
-  if (warp == 8) {
+  if (warp == W_PROD) {
     // ------------------------------------------------------------------ weight producer (one lane)
     if (lane == 0) {
       const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w);
@@ -121,7 +147,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tok_fused_kernel(const __grid_c
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == W_MMA) {
     // ------------------------------------------------------------------ MMA issuer (whole warp runs the loop, one lane issues)
     const uint32_t leader = elect_one() ? 1u : 0u;
     const uint64_t desc_hi = ((uint64_t)8 << 32) | ((uint64_t)1 << 46);   // SBO = 128 B, descriptor version 1
@@ -154,29 +180,35 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tok_fused_kernel(const __grid_c
       }
     };
     const uint32_t X = tmem + X_COL, ACC = tmem + ACC_COL;
-    // S_h = Q_h K_h^T for the two heads of the pair (hd = 32: two K16 steps), 112 key columns each
+    // S_{h,slot} = Q_h K_{h,slot}^T: all 128 query rows against the KW keys of window `slot` (rows of other windows produce
+    // values nobody reads); hd = 32: two K16 steps.  Score tile of (h, slot) at ACC + h*128 + slot*SL.
     auto mma_scores = [&]() {
-      const uint32_t idesc = idesc_f16(128, KEYS);
+      const uint32_t idesc = idesc_f16(128, KW);
 #pragma unroll 1
       for (int h = 0; h < 2; ++h)
 #pragma unroll 1
-        for (int j = 0; j < 2; ++j) {
-          const uint64_t da = desc(sbase + OFF_QK + (uint32_t)(2 * h) * 8192u + (uint32_t)j * 2u * PLANE, PLANE);
-          const uint64_t db = desc(sbase + OFF_QK + (uint32_t)(2 * h + 1) * 8192u + (uint32_t)j * 2u * PLANE, PLANE);
-          mma_bf16_ss_pred(ACC + (uint32_t)h * 128u, da, db, idesc, j ? 1u : 0u, leader);
-        }
+        for (int sl = 0; sl < G; ++sl)
+#pragma unroll 1
+          for (int j = 0; j < 2; ++j) {
+            const uint64_t da = desc(sbase + OFF_QK + (uint32_t)(2 * h) * 8192u + (uint32_t)j * 2u * PLANE, PLANE);
+            const uint64_t db = desc(sbase + OFF_QK + (uint32_t)(2 * h + 1) * 8192u + (uint32_t)j * 2u * PLANE + (uint32_t)(sl * SL) * 16u, PLANE);
+            mma_bf16_ss_pred(ACC + (uint32_t)(h * 128 + sl * SL), da, db, idesc, j ? 1u : 0u, leader);
+          }
     };
-    // O_h = P_h V_h (K = 112 keys: seven K16 steps), B = V^T: [key plane][32 hd rows][8 keys]
+    // O_{h,slot} = P_h V_{h,slot}: P holds, for every row, the probabilities over the keys of the row's OWN window (K = KW), so
+    // the product with window `slot`'s V is meaningful for that window's rows only; O of (h, slot) at ACC + (h*G + slot)*32.
     auto mma_pv = [&]() {
       const uint32_t idesc = idesc_f16(128, 32);
 #pragma unroll 1
       for (int h = 0; h < 2; ++h)
 #pragma unroll 1
-        for (int j = 0; j < KEYS / 16; ++j) {
-          const uint64_t da = desc(sbase + OFF_P + (uint32_t)h * P_HEAD + (uint32_t)j * 2u * PLANE, PLANE);
-          const uint64_t db = desc(sbase + OFF_VT + (uint32_t)h * 8192u + (uint32_t)j * 1024u, 512u);
-          mma_bf16_ss_pred(ACC + (uint32_t)h * 32u, da, db, idesc, j ? 1u : 0u, leader);
-        }
+        for (int sl = 0; sl < G; ++sl)
+#pragma unroll 1
+          for (int j = 0; j < KW / 16; ++j) {
+            const uint64_t da = desc(sbase + OFF_P + (uint32_t)h * P_HEAD + (uint32_t)j * 2u * PLANE, PLANE);
+            const uint64_t db = desc(sbase + OFF_VT + (uint32_t)h * 8192u + (uint32_t)(sl * SL / 8 + 2 * j) * 512u, 512u);
+            mma_bf16_ss_pred(ACC + (uint32_t)((h * G + sl) * 32), da, db, idesc, j ? 1u : 0u, leader);
+          }
     };
     for (int l = 0; l < TF_LAYERS; ++l) {
       for (int hp = 0; hp < 4; ++hp) {
@@ -197,22 +229,22 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tok_fused_kernel(const __grid_c
       // ---- FFN: chunks of 128 hidden channels
       for (int c = 0; c < 8; ++c) {
         wait_cmp();                                                       // LN2 output (c = 0) / GELU'd chunk c-1
-        if (c > 0) gemm_w(sbase + OFF_P, 256, 8, 2, X, 1u);               // X += h_{c-1} @ W2[:, 128(c-1) : 128c]^T
+        if (c > 0) gemm_w(sbase + OFF_FF, 256, 8, 2, X, 1u);              // X += h_{c-1} @ W2[:, 128(c-1) : 128c]^T
         gemm_w(sbase + OFF_ALN, 128, 16, 4, ACC, 0u);                     // h_c = LN2 @ W1[128c : 128c+128]^T
         done();
       }
       wait_cmp();
-      gemm_w(sbase + OFF_P, 256, 8, 2, X, 1u);
+      gemm_w(sbase + OFF_FF, 256, 8, 2, X, 1u);
       done();
     }
   } else {
-    // ------------------------------------------------------------------ compute warps
-    const int q = warp & 3, hf = warp >> 2;
+    // ------------------------------------------------------------------ compute warps: lane quarter q, column quarter cq
+    const int q = warp & 3, cq = warp >> 2;
     const int row = q * 32 + lane;
-    const int slot = (q * 32) / p.SL;
-    const int lrow = row - slot * p.SL;
-    const int win = blockIdx.x * p.G + slot;
-    const bool valid = slot < p.G && win < p.B && lrow < p.NT;
+    const int slot = (q * 32) / SL;
+    const int lrow = row - slot * SL;
+    const int win = blockIdx.x * G + slot;
+    const bool valid = slot < G && win < p.B && lrow < p.NT;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
     const uint32_t X = lane_base + X_COL, ACC = lane_base + ACC_COL;
     const uint32_t row16 = (uint32_t)row * 16u;
@@ -230,10 +262,12 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tok_fused_kernel(const __grid_c
       if (lane == 0) mbar_arrive(&bar_cmp);
       if (dbg && dbg_n < 96) { dbg[2 * dbg_n + 1] = clock64(); ++dbg_n; }
     };
+    auto quarter_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory"); };   // the four warps of this lane quarter
     const float* cum_all = p.vec + (size_t)TF_LAYERS * TF_VEC_LAYER;
 
-    // X <- tok rows (this warp's half of the columns); rows outside the batch are zero
-    for (int c0 = hf * 128; c0 < hf * 128 + 128; c0 += 32) {
+    // X <- tok rows (this warp's 64 columns); rows outside the batch are zero
+#pragma unroll 1
+    for (int c0 = cq * 64; c0 < cq * 64 + 64; c0 += 32) {
       float v[32];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -243,43 +277,41 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tok_fused_kernel(const __grid_c
       tmem_st32(X + (uint32_t)c0, v);
     }
     tmem_st_wait();
-    tc_fence_before();
-    // both warps of a lane quarter must have stored their halves before either reads full rows
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    tc_fence_after();
 
-    // LayerNorm of (X + cum) -> A_ln (fp16 planes); both warps of a quarter compute the row statistics, each writes its half
+    // LayerNorm of (X + cum) -> A_ln (fp16 planes).  A warp holds its 64 columns of the row in registers; the row statistics
+    // are combined across the four warps of the lane quarter through shared memory in a fixed order (two-pass variance).
     auto layer_norm = [&](const float* cum, const float* g, const float* b) {
-      float sum = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < TF_D; c0 += 32) {
-        float v[32];
-        tmem_ld32(X + (uint32_t)c0, v);
-        tmem_ld_wait();
+      const int c0 = cq * 64;
+      float v[64];
+      tmem_ld32(X + (uint32_t)c0, v);
+      tmem_ld32(X + (uint32_t)c0 + 32u, v + 32);
+      tmem_ld_wait();
+      add32(v, cum + c0);
+      add32(v + 32, cum + c0 + 32);
+      float s = 0.f;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) sum += v[e] + __ldg(cum + c0 + e);
+      for (int e = 0; e < 64; ++e) s += v[e];
+      const uint32_t red = sbase + OFF_RED + (uint32_t)row * 4u;           // [2][4 cq][128 rows] floats
+      st_shared_f32(red + (uint32_t)cq * 512u, s);
+      quarter_sync();
+      const float mu = ((ld_shared_f32(red) + ld_shared_f32(red + 512u)) + (ld_shared_f32(red + 1024u) + ld_shared_f32(red + 1536u))) * (1.0f / TF_D);
+      float d2 = 0.f;
+#pragma unroll
+      for (int e = 0; e < 64; ++e) { v[e] -= mu; d2 = fmaf(v[e], v[e], d2); }
+      st_shared_f32(red + 2048u + (uint32_t)cq * 512u, d2);
+      quarter_sync();
+      const float var = ((ld_shared_f32(red + 2048u) + ld_shared_f32(red + 2560u)) + (ld_shared_f32(red + 3072u) + ld_shared_f32(red + 3584u))) * (1.0f / TF_D);
+      const float rstd = valid ? 1.0f / sqrtf(var + 1e-5f) : 0.f;          // rows outside the batch: zeros
+#pragma unroll
+      for (int e4 = 0; e4 < 16; ++e4) {
+        const float4 gg = __ldg(reinterpret_cast<const float4*>(g + c0) + e4), bb = __ldg(reinterpret_cast<const float4*>(b + c0) + e4);
+        v[4 * e4] = valid ? fmaf(v[4 * e4] * rstd, gg.x, bb.x) : 0.f;
+        v[4 * e4 + 1] = valid ? fmaf(v[4 * e4 + 1] * rstd, gg.y, bb.y) : 0.f;
+        v[4 * e4 + 2] = valid ? fmaf(v[4 * e4 + 2] * rstd, gg.z, bb.z) : 0.f;
+        v[4 * e4 + 3] = valid ? fmaf(v[4 * e4 + 3] * rstd, gg.w, bb.w) : 0.f;
       }
-      const float mu = sum * (1.0f / TF_D);
-      float var = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < TF_D; c0 += 32) {
-        float v[32];
-        tmem_ld32(X + (uint32_t)c0, v);
-        tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) { const float d = v[e] + __ldg(cum + c0 + e) - mu; var = fmaf(d, d, var); }
-      }
-      const float rstd = 1.0f / sqrtf(var * (1.0f / TF_D) + 1e-5f);
-#pragma unroll 1
-      for (int c0 = hf * 128; c0 < hf * 128 + 128; c0 += 32) {
-        float v[32];
-        tmem_ld32(X + (uint32_t)c0, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) v[e] = valid ? (v[e] + __ldg(cum + c0 + e) - mu) * rstd * __ldg(g + c0 + e) + __ldg(b + c0 + e) : 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) st_plane8(sbase + OFF_ALN + (uint32_t)(c0 / 8 + j) * PLANE + row16, v + 8 * j);
-      }
+      for (int j = 0; j < 8; ++j) st_plane8(sbase + OFF_ALN + (uint32_t)(c0 / 8 + j) * PLANE + row16, v + 8 * j);
     };
 
     for (int l = 0; l < TF_LAYERS; ++l) {
@@ -288,85 +320,74 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tok_fused_kernel(const __grid_c
       layer_norm(cum_all + (size_t)(2 * l) * TF_D, lv, lv + 256);
       done();
       const float* qkv_b = lv + 1024;
+      float inv_sum = 0.f;
       for (int hp = 0; hp < 4; ++hp) {
-        // ---- Q|K|V epilogue of head 2hp + hf: +bias, Q scaled by 1/sqrt(32), fp16 planes; V transposed (B operand of P V)
+        // ---- Q|K|V epilogue: six 32-column blocks [Q0 K0 V0 Q1 K1 V1] of the accumulator; +bias, Q scaled by 1/sqrt(32), fp16
+        // planes; V transposed (B operand of P V).  cq 0: Q0 K0, cq 1: Q1 K1, cq 2: V0, cq 3: V1 (the transposing blocks alone).
         wait_mma();
         {
-          const float* hb = qkv_b + hp * 192 + hf * 96;
+          const int b0 = cq == 0 ? 0 : (cq == 1 ? 3 : (cq == 2 ? 2 : 5));
+          const int nb = cq < 2 ? 2 : 1;
 #pragma unroll 1
-          for (int part = 0; part < 3; ++part) {
+          for (int bi = 0; bi < nb; ++bi) {
+            const int blk = b0 + bi, head = blk / 3, part = blk - head * 3;
             float v[32];
-            tmem_ld32(ACC + (uint32_t)(hf * 96 + part * 32), v);
+            tmem_ld32(ACC + (uint32_t)(blk * 32), v);
             tmem_ld_wait();
-            const float sc = part == 0 ? 0.17677669529663688f : 1.0f;
+            add32(v, qkv_b + hp * 192 + blk * 32);
+            const float sc = !valid ? 0.f : (part == 0 ? 0.17677669529663688f : 1.0f);
 #pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = valid ? (v[e] + __ldg(hb + part * 32 + e)) * sc : 0.f;
+            for (int e = 0; e < 32; ++e) v[e] *= sc;
             if (part < 2) {
-              const uint32_t base = sbase + OFF_QK + (uint32_t)(2 * hf + part) * 8192u + row16;
+              const uint32_t base = sbase + OFF_QK + (uint32_t)(2 * head + part) * 8192u + row16;
 #pragma unroll
               for (int j = 0; j < 4; ++j) st_plane8(base + (uint32_t)j * PLANE, v + 8 * j);
-            } else if (row < KEYS) {
-              const uint32_t base = sbase + OFF_VT + (uint32_t)hf * 8192u + (uint32_t)(row >> 3) * 512u + (uint32_t)(row & 7) * 2u;
+            } else {
+              const uint32_t base = sbase + OFF_VT + (uint32_t)head * 8192u + (uint32_t)(row >> 3) * 512u + (uint32_t)(row & 7) * 2u;
 #pragma unroll
               for (int d = 0; d < 32; ++d) st_shared_u16(base + (uint32_t)d * 16u, __half_as_ushort(__float2half_rn(v[d])));
             }
           }
         }
         done();
-        // ---- softmax over this window's keys (columns slot*SL .. +NT of the score tile), un-normalised P -> fp16 planes
+        // ---- softmax over the row's own window (score columns slot*SL .. +NT of head cq), un-normalised P -> fp16 planes,
+        // keys relative to the window; one TMEM pass (NT <= 64 values per row in registers)
         wait_mma();
-        float inv_sum = 0.f;
-        {
-          const uint32_t S = ACC + (uint32_t)(hf * 128 + slot * p.SL);
+        if (cq < 2) {
+          const uint32_t S = ACC + (uint32_t)(cq * 128 + slot * SL);
+          float v[64];
+          tmem_ld32(S, v);
+          if (p.NT > 32) tmem_ld32(S + 32u, v + 32);
+          tmem_ld_wait();
           float mx = -INFINITY;
-#pragma unroll 1
-          for (int c0 = 0; c0 < p.NT; c0 += 32) {
-            float v[32];
-            tmem_ld32(S + (uint32_t)c0, v);
-            tmem_ld_wait();
 #pragma unroll
-            for (int e = 0; e < 32; ++e) if (c0 + e < p.NT) mx = fmaxf(mx, v[e]);
-          }
+          for (int e = 0; e < 64; ++e) if (e < p.NT) mx = fmaxf(mx, v[e]);
           float sum = 0.f;
-          const uint32_t pbase = sbase + OFF_P + (uint32_t)hf * P_HEAD + row16;
-          const int kp0 = (slot * p.SL) >> 3;                             // first key plane of this window
-          int written_lo = kp0, written_hi = kp0;
-#pragma unroll 1
-          for (int c0 = 0; c0 < p.NT; c0 += 32) {
-            float v[32];
-            tmem_ld32(S + (uint32_t)c0, v);
-            tmem_ld_wait();
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const float pe = (valid && c0 + e < p.NT) ? __expf(v[e] - mx) : 0.f;
-              // the row sum is taken over the fp16-rounded probabilities the tensor core will multiply with V
-              const float pr = __half2float(__float2half_rn(pe));
-              sum += pr;
-              v[e] = pr;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int kp = kp0 + (c0 >> 3) + j;
-              if (kp < KEYS / 8) st_plane8(pbase + (uint32_t)kp * PLANE, v + 8 * j);
-            }
-            written_hi = kp0 + (c0 >> 3) + 4;
+          for (int e = 0; e < 64; ++e) {
+            const float pe = (valid && e < p.NT) ? __expf(v[e] - mx) : 0.f;
+            // the row sum is taken over the fp16-rounded probabilities the tensor core multiplies with V
+            const float pr = __half2float(__float2half_rn(pe));
+            sum += pr;
+            v[e] = pr;
           }
-          const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          for (int kp = 0; kp < KEYS / 8; ++kp)
-            if (kp < written_lo || kp >= written_hi) st_plane8(pbase + (uint32_t)kp * PLANE, z);
+          const uint32_t pbase = sbase + OFF_P + (uint32_t)cq * P_HEAD + row16;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (8 * j < KW) st_plane8(pbase + (uint32_t)j * PLANE, v + 8 * j);
           inv_sum = (valid && sum > 0.f) ? 1.0f / sum : 0.f;
         }
         done();
-        // ---- attention output of head 2hp + hf: (P V) / rowsum -> planes 4hf..4hf+3 of the K = 64 operand (aliases Q/K)
+        // ---- attention output of head 2hp + cq: (P V) / rowsum -> planes 4cq..4cq+3 of the K = 64 operand (aliases Q/K)
         wait_mma();
-        {
+        if (cq < 2) {
           float v[32];
-          tmem_ld32(ACC + (uint32_t)(hf * 32), v);
+          tmem_ld32(ACC + (uint32_t)((cq * G + slot) * 32), v);
           tmem_ld_wait();
 #pragma unroll
           for (int e = 0; e < 32; ++e) v[e] *= inv_sum;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) st_plane8(sbase + OFF_QK + (uint32_t)(4 * hf + j) * PLANE + row16, v + 8 * j);
+          for (int j = 0; j < 4; ++j) st_plane8(sbase + OFF_QK + (uint32_t)(4 * cq + j) * PLANE + row16, v + 8 * j);
         }
         done();
       }
@@ -374,56 +395,52 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tok_fused_kernel(const __grid_c
       wait_mma();
       layer_norm(cum_all + (size_t)(2 * l + 1) * TF_D, lv + 512, lv + 768);
       done();
-      // ---- FFN chunks: GELU(acc + b1) -> fp16 planes of the K = 128 operand (this warp: 64 of the 128 columns)
+      // ---- FFN chunks: GELU(acc + b1) -> fp16 planes of the K = 128 operand (this warp: 32 of the 128 columns)
       const float* b1 = lv + 1024 + 768;
       for (int c = 0; c < 8; ++c) {
         wait_mma();
-#pragma unroll 1
-        for (int c0 = hf * 64; c0 < hf * 64 + 64; c0 += 32) {
+        {
           float v[32];
-          tmem_ld32(ACC + (uint32_t)c0, v);
+          tmem_ld32(ACC + (uint32_t)(cq * 32), v);
           tmem_ld_wait();
+          add32(v, b1 + c * 128 + cq * 32);
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = valid ? gelu_erf(v[e] + __ldg(b1 + c * 128 + c0 + e)) : 0.f;
+          for (int e = 0; e < 32; ++e) v[e] = valid ? gelu_fast(v[e]) : 0.f;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) st_plane8(sbase + OFF_P + (uint32_t)(c0 / 8 + j) * PLANE + row16, v + 8 * j);
+          for (int j = 0; j < 4; ++j) st_plane8(sbase + OFF_FF + (uint32_t)(cq * 4 + j) * PLANE + row16, v + 8 * j);
         }
         done();
       }
     }
     // ---- tok <- X + total bias
     wait_mma();
-    {
+    if (valid) {
       const float* cum = cum_all + (size_t)(2 * TF_LAYERS) * TF_D;
 #pragma unroll 1
-      for (int c0 = hf * 128; c0 < hf * 128 + 128; c0 += 32) {
+      for (int c0 = cq * 64; c0 < cq * 64 + 64; c0 += 32) {
         float v[32];
         tmem_ld32(X + (uint32_t)c0, v);
         tmem_ld_wait();
-        if (valid) {
+        add32(v, cum + c0);
 #pragma unroll
-          for (int e = 0; e < 8; ++e)
-            *reinterpret_cast<float4*>(grow + c0 + 4 * e) = make_float4(v[4 * e] + __ldg(cum + c0 + 4 * e), v[4 * e + 1] + __ldg(cum + c0 + 4 * e + 1),
-                                                                        v[4 * e + 2] + __ldg(cum + c0 + 4 * e + 2), v[4 * e + 3] + __ldg(cum + c0 + 4 * e + 3));
-        }
+        for (int e = 0; e < 8; ++e) *reinterpret_cast<float4*>(grow + c0 + 4 * e) = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem, 512);
+  if (warp == W_MMA) tmem_dealloc(tmem, 512);
 }
 
 cudaError_t tok_fused_device_init() {
   return cudaFuncSetAttribute(tok_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TF_SMEM);
 }
 
-// Row slot per window: a multiple of 32 (a warp's rows belong to one window) and of 16 (a window's keys start on a K16 step).
-// The key extent of the score tile is KEYS = 112 columns: (G - 1) * SL + NT must fit.
-void tok_fused_geometry(int NT, int& SL, int& G) {
+// Row slot per window: a multiple of 32 (a warp's rows belong to one window).  KW = key extent per window (multiple of 16).
+void tok_fused_geometry(int NT, int& SL, int& G, int& KW) {
   SL = NT <= 32 ? 32 : 64;
   G = 128 / SL;
-  while (G > 1 && (G - 1) * SL + NT > KEYS) --G;
+  KW = (NT + 15) / 16 * 16;
 }
 bool tok_fused_supported(int NT) { return NT >= 1 && NT <= 64; }
 

@@ -38,14 +38,14 @@ struct TokFusedP {
   uint32_t layer_bytes;       // bytes of one layer image
   const float* vec;           // device: per layer [ln1_g 256 | ln1_b 256 | ln2_g 256 | ln2_b 256 | qkv_bias 768 (packed order) | ff1_bias 1024],
                               //         then (2*TF_LAYERS + 1) cumulative bias vectors of 256 (see tok_fused.cu)
-  int B, NT, SL, G;           // windows, tokens per window (T+1), row slot per window (32 or 64), windows per CTA
+  int B, NT, SL, G, KW;       // windows, tokens per window (T+1), row slot per window (32 or 64), windows per CTA, keys per window (16-multiple)
   void* dbg;                  // optional (LSD_TOKF_TRACE): 384 x int64 of phase timestamps of CTA 0, see tok_fused.cu
 };
 constexpr int TF_VEC_LAYER = 4 * 256 + 768 + 1024;
 
 cudaError_t tok_fused_device_init();
 bool tok_fused_supported(int NT);
-void tok_fused_geometry(int NT, int& SL, int& G);
+void tok_fused_geometry(int NT, int& SL, int& G, int& KW);
 void launch_tok_fused(const TokFusedP& p, cudaStream_t s);
 
 }  // namespace lsd

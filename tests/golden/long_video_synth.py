@@ -27,7 +27,7 @@ _S["two_tracks_clear_winner"] = _spec(11, _sp, [0.9, 0.6], {"0": _confs(1, _n_ch
 _S["two_tracks_close_scores"] = _spec(12, _sp, [0.8, 0.8], {"0": _confs(3, _n_chunks(_sp[0]), 0.74, 0.01), "1": _confs(4, _n_chunks(_sp[1]), 0.72, 0.01)})
 _S["two_tracks_conf_gap_small_selection_clear"] = _spec(13, _sp, [0.95, 0.30], {"0": _confs(5, _n_chunks(_sp[0]), 0.66, 0.01), "1": _confs(6, _n_chunks(_sp[1]), 0.62, 0.01)})
 _sp3 = [(0, 200), (40, 176), (96, 200)]
-_S["three_tracks_turn_taking"] = _spec(14, _sp3, [0.7, 0.7, 0.7], {"0": _confs(7, _n_chunks(_sp3[0]), 0.55, 0.15), "1": _confs(8, _n_chunks(_sp3[1]), 0.60, 0.15),
+_S["three_tracks_turn_taking"] = _spec(14, _sp3, [0.7, 0.5, 0.9], {"0": _confs(7, _n_chunks(_sp3[0]), 0.55, 0.15), "1": _confs(8, _n_chunks(_sp3[1]), 0.60, 0.15),
                                                                      "2": _confs(9, _n_chunks(_sp3[2]), 0.58, 0.15)})
 _S["two_tracks_fake_winner"] = _spec(15, _sp, [0.9, 0.5], {"0": _confs(10, _n_chunks(_sp[0]), 0.12, 0.03), "1": _confs(11, _n_chunks(_sp[1]), 0.20, 0.03)})
 _S["two_tracks_static_mouth"] = _spec(16, _sp, [0.9, 0.5], {"0": _confs(12, _n_chunks(_sp[0]), 0.40, 0.03), "1": _confs(13, _n_chunks(_sp[1]), 0.20, 0.03)}, motion=(0.0, 6.0))
