@@ -204,6 +204,7 @@ def latency_probe(pred, lb, iters: int = 30):
         ts.sort()
         out[name] = {"best": ts[0], "median": ts[len(ts) // 2]}
     out["graphs"] = bool(getattr(pred, "use_cuda_graphs", False))
+    out["graph_captures"] = int(getattr(pred, "graph_captures", 0))
     out["what"] = "wall clock around the public call on host numpy inputs, B=1 (and 1+3 windows), after 5 warm-ups"
     return out
 
@@ -335,12 +336,16 @@ def main():
 
     e2e_h2d_bytes, e2e_transport = [0], ["fp32"]
 
-    def run_e2e(steps):
+    pred_f32 = lb.Predictor(model, batch_size=B, host_transport="fp32")
+
+    def run_e2e(steps, p=None):
         """Public API on HOST buffers: Predictor.score_batches uploads every step's windows from pinned host memory
         (copy stream, overlapped with the previous step's scoring) and reads every step's logits back."""
-        outs = pred.score_batches((vh, ah) for _ in range(steps))
-        e2e_h2d_bytes[0] = int(getattr(pred, "last_h2d_bytes_per_batch", vh.numel() * 4 + ah.numel() * 4))
-        e2e_transport[0] = getattr(pred, "last_transport", "fp32")
+        p = pred if p is None else p
+        outs = p.score_batches((vh, ah) for _ in range(steps))
+        if p is pred:
+            e2e_h2d_bytes[0] = int(p.last_h2d_bytes_per_batch)
+            e2e_transport[0] = p.last_transport
         if ws > 1:
             last = outs[-1].to(dev)
             dist.all_gather_into_tensor(gathered_e2e, last)
@@ -428,6 +433,7 @@ def main():
 
     ms, launches, prof, clocks = timed(step_resident, K, profile=True, finalize=gather_resident)
     ms_e2e, _, _, _ = timed(run_e2e, K, whole=True)
+    ms_e2e_f32, _, _, _ = timed(lambda n: run_e2e(n, pred_f32), K, whole=True)
     ms_trk, _, _, _ = timed(run_e2e_track, K, whole=True)
     # sustained: the same resident step back to back for >= ~1.5 s (the K-step region above lasts ~60 ms: a burst figure, taken
     # before the 1000 W power cap pulls the SM clock down)
@@ -477,7 +483,10 @@ def main():
                     "api": ("Predictor.score_batches on pinned host fp32 windows (per step: exact-uint8 detection + packing on the host "
                             "threads when the windows are u8/255 as video.py:552-556 produces them, H2D on a copy stream, forward, D2H "
                             "of the logits)"),
-                    "transport": e2e_transport[0]},
+                    "transport": e2e_transport[0], "host_pack_threads": pred.host_pack_threads},
+            "e2e_fp32_upload": {"value": ws * B * K / (ms_e2e_f32 / 1e3), "unit": "windows/s", "ms_per_step": ms_e2e_f32 / K,
+                                "h2d_bytes_per_step": vh.numel() * 4 + ah.numel() * 4, "d2h_bytes_per_step": (ws if ws > 1 else 1) * B * 4,
+                                "api": "the same call with host_transport='fp32' (windows cross PCIe as fp32: round 1's e2e)"},
             "e2e_track_u8": {"value": e2e_trk, "unit": "windows/s", "ms_per_step": ms_trk / K,
                              "h2d_bytes_per_step": track_h.numel() + mel_h.numel() * 4, "d2h_bytes_per_step": B * 4,
                              "api": "Predictor.score_track_logits on a pinned host uint8 mouth-crop track (windows built on the device, lsd_score_windows)"},

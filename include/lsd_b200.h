@@ -175,6 +175,22 @@ int lsd_vad_mask(lsd_handle* h, const float* energy, int n_frames, float thresho
 int lsd_stage_info(lsd_handle* h, const char* name, size_t* offset_bytes, int64_t* numel, int* dtype);
 int lsd_stage_count(lsd_handle* h);
 const char* lsd_stage_name(lsd_handle* h, int i);
+/* ---- host-side transport helper (no GPU work; needs no handle) -------------------------------------------------- */
+/* The reference builds float windows from uint8 mouth crops as astype(float32) / 255.0 (app/preprocessing/video.py:552-556), so
+ * the pixels of a window given to _run_chunked_inference (predictor.py:554-580) are exactly fl(k / 255.0f), k in 0..255.  This
+ * call verifies that for all n values of `src` (by redoing the division) while writing the k's to `dst`, on `threads` host
+ * threads (0 = all).  Returns 1 when every value qualified (dst complete: ship it as LSD_U8 in the same layout — the device
+ * normalisation reproduces the fp32 values bit for bit), 0 when some value did not (dst undefined: ship the fp32 values),
+ * LSD_ERR_ARG on null pointers. */
+int lsd_host_pack_u8_exact(const float* src, uint8_t* dst, int64_t n, int threads);
+
+/* CUDA-graph support.  lsd_forward may be captured into a CUDA graph (cudaStreamBeginCapture on `stream`; the internal side
+ * streams join the capture through events) once a plain call with the same arguments has run: the first call of a shape
+ * allocates and uploads its stage programs, which is not capturable.  A captured graph bakes in device addresses owned by the
+ * handle (packed weights, stage programs); lsd_state_generation() changes whenever those are invalidated (lsd_load_weights,
+ * stage-program arena recycled) — re-capture when it differs from the value read at capture time. */
+int64_t lsd_state_generation(lsd_handle* h);
+
 /* Activation tensor of the last tensor-core (BF16) lsd_forward, kept in the workspace in the padded planar bf16 layout
  * (DESIGN.md §4), converted to fp32 channels-last (N, T, H_full, W_full, C) for per-stage parity tests.  Names: "x1" (stem +
  * pool), "y1".."y4" (visual_encoder.layer1..4; y1..y3 are parity-split: pass the full-resolution extent), "ya4" (+ "ya4_lo":

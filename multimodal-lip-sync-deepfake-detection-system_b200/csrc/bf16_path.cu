@@ -511,6 +511,7 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
         cudaDeviceSynchronize();
         c.h->prog_cache.clear();
         c.h->prog_cursor = 0;
+        ++c.h->generation;   // captured CUDA graphs hold addresses of the old programs
       }
       std::vector<UcStageDesc> host((size_t)p.nst_tile);
       umma_conv_build_program(p, host.data());
@@ -996,9 +997,35 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
     launch_planar_mean2(bs.org(pb["hf_b"]), pb["hf_b"].plane_stride, hf.g, 64, comb + 384, 448, 1, none, sst);
     g_tl.mark(sst, "S:hf3");
   }
-  RUN("visual_encoder.stem", a_.in = &xs; a_.og = xs.g; a_.act = ACT_RELU; a_.yp = &so);
-  g_tl.mark(st, "M:stem");
-  launch_planar_maxpool(b.org(so), so.plane_stride, so.g, b.org(x1), x1.plane_stride, x1.g, 64, st);
+  // Stem + max-pool.  LSD_STEM_CHUNK=n (tuning knob, default 0 = one pass over the whole batch) runs them in sub-batches of n
+  // windows so that the stem output of a sub-batch (11 MB per window) is still in the 126 MB L2 when the max-pool reads it and the
+  // 640 MB stem output of a B=64 step never makes the round trip through HBM.  Measured at B=64: 20.7k windows/s in one pass,
+  // 19.1k with n=7, 19.7k with n=15 — the stem is tensor-bound, not HBM-bound, and the extra wave tails and launches of the
+  // sub-batches cost more than the saved DRAM traffic.  Sub-batch views share the buffers' plane strides; only the first position moves.
+  {
+    int chunk = 0;
+    if (const char* e = getenv("LSD_STEM_CHUNK")) chunk = atoi(e);
+    if (chunk <= 0 || chunk >= B) {
+      RUN("visual_encoder.stem", a_.in = &xs; a_.og = xs.g; a_.act = ACT_RELU; a_.yp = &so);
+      g_tl.mark(st, "M:stem");
+      launch_planar_maxpool(b.org(so), so.plane_stride, so.g, b.org(x1), x1.plane_stride, x1.g, 64, st);
+    } else {
+      auto view = [&](const PBuf& full, int n0, int nb) {
+        PBuf v = full;
+        v.g = make_geom_ex(nb, full.g.T, full.g.H, full.g.W, full.g.ot, full.g.oh, full.g.HP - full.g.H - full.g.oh, full.g.ow,
+                           full.g.RW - full.g.W - full.g.ow);
+        v.origin = full.origin + (int64_t)n0 * full.g.TS * full.g.SL * 8;
+        return v;
+      };
+      for (int n0 = 0; n0 < B; n0 += chunk) {
+        const int nb = std::min(chunk, B - n0);
+        const PBuf xs_v = view(xs, n0, nb), so_v = view(so, n0, nb), x1_v = view(x1, n0, nb);
+        RUN("visual_encoder.stem", a_.in = &xs_v; a_.og = xs_v.g; a_.act = ACT_RELU; a_.yp = &so_v);
+        launch_planar_maxpool(b.org(so_v), so_v.plane_stride, so_v.g, b.org(x1_v), x1_v.plane_stride, x1_v.g, 64, st);
+      }
+      g_tl.mark(st, "M:stem");
+    }
+  }
   g_tl.mark(st, "M:maxpool");
   // ---- residual stages (visual_encoder.py:81-87, 133-152)
   if ((rc = res_stage_umma(b, "visual_encoder.layer1", x1, pb["l1a"], pb["y1"], false, UC_Y_PARITY))) return rc;
@@ -1032,13 +1059,33 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   RUNS("art.td3", a_.in = &pb["artd_a"]; a_.og = dl.g; a_.act = ACT_RELU; a_.yp = &pb["artd_b"]);
   launch_planar_mean2(bs.org(pb["artd_b"]), pb["artd_b"].plane_stride, dl.g, 64, comb + 320, 448, 1, none, sst);
   g_tl.mark(sst, "S:td_delta");
-  // high-frequency branch: Conv3d 3->32 s(1,2,2) on the laplacian pixel rows (Toeplitz K), Conv3d 32->64 s(1,2,2) planar
+  // high-frequency branch: Conv3d 3->32 s(1,2,2) on the laplacian pixel rows (Toeplitz K), Conv3d 32->64 s(1,2,2) planar.
+  // It depends on nothing but the laplacian rows, so in the tail it runs on a second side stream NEXT TO the
+  // temporal-inconsistency convolutions instead of behind them (LSD_HF_SERIAL=1 restores the single side stream): both
+  // chains are capped at half of the SMs, and the token path's small grids fit in between.
   if (!hf_early) {
-    RUNS("art.hf0", a_.in = &xl; a_.og = xl.g; a_.act = ACT_RELU; a_.yp = &hf);
-    g_tl.mark(sst, "S:hf0");
-    RUNS("art.hf3", a_.in = &hf; a_.og = hf.g; a_.act = ACT_RELU; a_.yp = &pb["hf_b"]);
-    launch_planar_mean2(bs.org(pb["hf_b"]), pb["hf_b"].plane_stride, hf.g, 64, comb + 384, 448, 1, none, sst);
-    g_tl.mark(sst, "S:hf3");
+    const bool hf_par = getenv("LSD_HF_SERIAL") == nullptr && pipe_parity < 0;
+    cudaStream_t hst = sst;
+    if (hf_par) {
+      if (!h->side2_stream) {
+        if (cudaStreamCreateWithFlags(&h->side2_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming) != cudaSuccess)
+          return lsd_fail(h, LSD_ERR_CUDA, "second side stream creation failed");
+      }
+      hst = h->side2_stream;
+      cudaStreamWaitEvent(hst, h->ev_fork, 0);
+    }
+    BCtx bh = bs;
+    bh.st = hst;
+    if (const char* e = getenv("LSD_HF_CTAS")) bh.max_ctas = atoi(e);
+    RUNC(bh, "art.hf0", a_.in = &xl; a_.og = xl.g; a_.act = ACT_RELU; a_.yp = &hf);
+    g_tl.mark(hst, "S:hf0");
+    RUNC(bh, "art.hf3", a_.in = &hf; a_.og = hf.g; a_.act = ACT_RELU; a_.yp = &pb["hf_b"]);
+    launch_planar_mean2(bh.org(pb["hf_b"]), pb["hf_b"].plane_stride, hf.g, 64, comb + 384, 448, 1, none, hst);
+    g_tl.mark(hst, "S:hf3");
+    if (hf_par) {                       // fold the second side stream back into the first: ev_join then covers both
+      cudaEventRecord(h->ev_join2, hst);
+      cudaStreamWaitEvent(sst, h->ev_join2, 0);
+    }
   }
   }
   cudaEventRecord(h->ev_join, sst);

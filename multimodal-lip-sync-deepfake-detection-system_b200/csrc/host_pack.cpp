@@ -1,0 +1,184 @@
+// Host-side transport helper (no GPU work, plain C++ compiled by the host compiler): lossless fp32 -> uint8 packing of
+// window pixels for the H2D copy.
+//
+// The reference builds its float windows from uint8 mouth crops as `astype(np.float32) / 255.0` (app/preprocessing/video.py:552-556),
+// so every pixel of a window handed to `_run_chunked_inference` is exactly fl(k / 255.0f) for an integer k in [0, 255].  Such a
+// window can cross PCIe as k (one byte instead of four): the device normalisation of uint8 input reproduces fl(k / 255.0f) bit
+// for bit (umma_conv.cu: video_rows, tests/test_host_logic.py), so the logits do not change.  lsd_host_pack_u8_exact() verifies the
+// property for every value (by redoing the reference's division) while it packs, and reports failure for anything else — the
+// caller then ships the fp32 values as before.
+#include <immintrin.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <cstdint>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "../../include/lsd_b200.h"
+
+namespace {
+
+constexpr int64_t CHUNK = 1 << 18;   // elements per work item (1 MB of fp32)
+
+bool pack_scalar(const float* s, uint8_t* d, int64_t n) {
+  bool ok = true;
+  for (int64_t i = 0; i < n; ++i) {
+    const float x = s[i];
+    const float t = x * 255.0f;
+    int k = (t >= 0.0f && t <= 255.5f) ? (int)__builtin_lrintf(t) : 0;
+    if (k > 255) k = 255;
+    const float back = (float)k / 255.0f;
+    ok &= (__builtin_memcmp(&back, &x, 4) == 0);   // bit pattern: false for NaN, -0.0 and anything that is not exactly fl(k/255)
+    d[i] = (uint8_t)k;
+  }
+  return ok;
+}
+
+// fl(k / 255.0f) without the divider: q0 = k * fl(1/255), one Newton step on the exact residual.  Verified against the division for
+// all 256 values of k before it is used (newton_ok()).
+inline float div255_newton(float k) {
+  const float r = 1.0f / 255.0f;
+  const float q0 = k * r;
+  const float e = __builtin_fmaf(-q0, 255.0f, k);
+  return __builtin_fmaf(e, r, q0);
+}
+bool newton_ok() {
+  for (int k = 0; k < 256; ++k) {
+    const float a = div255_newton((float)k), b = (float)k / 255.0f;
+    if (__builtin_memcmp(&a, &b, 4) != 0) return false;
+  }
+  return true;
+}
+
+template <bool NEWTON>
+__attribute__((target("avx2,fma"))) bool pack_avx2(const float* s, uint8_t* d, int64_t n) {
+  const __m256 c255 = _mm256_set1_ps(255.0f), rcp = _mm256_set1_ps(1.0f / 255.0f);
+  const __m256i perm = _mm256_setr_epi32(0, 4, 1, 5, 2, 6, 3, 7);
+  const __m256i hi = _mm256_set1_epi32(255);
+  __m256i bad = _mm256_setzero_si256();
+  int64_t i = 0;
+  for (; i + 32 <= n; i += 32) {
+    __m256i k[4];
+#pragma GCC unroll 4
+    for (int j = 0; j < 4; ++j) {
+      const __m256 x = _mm256_loadu_ps(s + i + 8 * j);
+      k[j] = _mm256_cvtps_epi32(_mm256_mul_ps(x, c255));                  // round to nearest (NaN / overflow -> INT_MIN)
+      const __m256 kf = _mm256_cvtepi32_ps(k[j]);
+      __m256 back;
+      if (NEWTON) {
+        const __m256 q0 = _mm256_mul_ps(kf, rcp);
+        back = _mm256_fmadd_ps(_mm256_fnmadd_ps(q0, c255, kf), rcp, q0);
+      } else {
+        back = _mm256_div_ps(kf, c255);                                   // the reference's own operation
+      }
+      bad = _mm256_or_si256(bad, _mm256_xor_si256(_mm256_castps_si256(back), _mm256_castps_si256(x)));   // bit patterns differ
+      bad = _mm256_or_si256(bad, _mm256_cmpgt_epi32(k[j], hi));
+      bad = _mm256_or_si256(bad, _mm256_cmpgt_epi32(_mm256_setzero_si256(), k[j]));
+    }
+    const __m256i p01 = _mm256_packus_epi32(k[0], k[1]);   // per 128-bit lane: k0[0:4] k1[0:4] | k0[4:8] k1[4:8]
+    const __m256i p23 = _mm256_packus_epi32(k[2], k[3]);
+    const __m256i p = _mm256_packus_epi16(p01, p23);       // lane 0: k0[0:4] k1[0:4] k2[0:4] k3[0:4], lane 1: the upper halves
+    _mm256_storeu_si256(reinterpret_cast<__m256i*>(d + i), _mm256_permutevar8x32_epi32(p, perm));
+  }
+  bool ok = _mm256_testz_si256(bad, bad) != 0;
+  if (i < n) ok &= pack_scalar(s + i, d + i, n - i);
+  return ok;
+}
+
+bool pack_range(const float* s, uint8_t* d, int64_t n) {
+  static const bool have_avx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("fma");
+  static const bool newton = newton_ok();
+  if (!have_avx2) return pack_scalar(s, d, n);
+  return newton ? pack_avx2<true>(s, d, n) : pack_avx2<false>(s, d, n);
+}
+
+// A small persistent pool: thread creation (~30 us each) would otherwise be a visible part of a 1-2 ms job.
+class Pool {
+ public:
+  static Pool& get() { static Pool p; return p; }
+
+  bool run(const float* src, uint8_t* dst, int64_t n, int threads) {
+    std::lock_guard<std::mutex> serial(run_mu_);    // one job at a time
+    const int64_t items = (n + CHUNK - 1) / CHUNK;
+    int want = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    if (want < 1) want = 1;
+    if (want > 64) want = 64;
+    if ((int64_t)want > items) want = (int)items;
+    src_ = src; dst_ = dst; n_ = n; items_ = items;
+    next_.store(0, std::memory_order_relaxed);
+    ok_.store(true, std::memory_order_relaxed);
+    const int helpers = want - 1;
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      while ((int)workers_.size() < helpers) workers_.emplace_back([this, id = (int)workers_.size()] { worker(id); });
+      active_ = helpers;
+      pending_ = helpers;
+      ++gen_;
+    }
+    if (helpers > 0) cv_.notify_all();
+    work();
+    if (helpers > 0) {
+      std::unique_lock<std::mutex> lk(mu_);
+      done_cv_.wait(lk, [this] { return pending_ == 0; });
+    }
+    return ok_.load(std::memory_order_relaxed);
+  }
+
+ private:
+  Pool() = default;
+  ~Pool() {
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  void work() {
+    for (;;) {
+      if (!ok_.load(std::memory_order_relaxed)) return;       // another chunk already failed: stop early
+      const int64_t it = next_.fetch_add(1, std::memory_order_relaxed);
+      if (it >= items_) return;
+      const int64_t lo = it * CHUNK, len = (lo + CHUNK <= n_) ? CHUNK : n_ - lo;
+      if (!pack_range(src_ + lo, dst_ + lo, len)) ok_.store(false, std::memory_order_relaxed);
+    }
+  }
+  void worker(int id) {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return stop_ || (gen_ != seen && id < active_); });
+        if (stop_) return;
+        seen = gen_;
+      }
+      work();
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        if (--pending_ == 0) done_cv_.notify_one();
+      }
+    }
+  }
+
+  std::mutex run_mu_, mu_;
+  std::condition_variable cv_, done_cv_;
+  std::vector<std::thread> workers_;
+  uint64_t gen_ = 0;
+  int active_ = 0, pending_ = 0;
+  bool stop_ = false;
+  const float* src_ = nullptr;
+  uint8_t* dst_ = nullptr;
+  int64_t n_ = 0, items_ = 0;
+  std::atomic<int64_t> next_{0};
+  std::atomic<bool> ok_{true};
+};
+
+}  // namespace
+
+extern "C" int lsd_host_pack_u8_exact(const float* src, uint8_t* dst, int64_t n, int threads) {
+  if (n < 0 || (n > 0 && (!src || !dst))) return LSD_ERR_ARG;
+  if (n == 0) return 1;
+  return Pool::get().run(src, dst, n, threads) ? 1 : 0;
+}

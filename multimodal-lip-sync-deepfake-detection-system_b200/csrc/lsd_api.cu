@@ -104,6 +104,8 @@ extern "C" void lsd_destroy(lsd_handle* h) {
   if (h->ev_lm_clips) cudaEventDestroy(h->ev_lm_clips);
   for (cudaEvent_t e : h->prof.ev) cudaEventDestroy(e);
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
+  if (h->side2_stream) cudaStreamDestroy(h->side2_stream);
+  if (h->ev_join2) cudaEventDestroy(h->ev_join2);
   for (int i = 0; i < 2; ++i) {
     if (h->tok_stream[i]) cudaStreamDestroy(h->tok_stream[i]);
     if (h->ev_tok_join[i]) cudaEventDestroy(h->ev_tok_join[i]);
@@ -325,6 +327,7 @@ extern "C" int lsd_load_weights(lsd_handle* h, const lsd_tensor* tensors, int n)
   int rc = pack_bf16_weights(h, L.arena);
   if (rc != 0) return rc;
   h->loaded = true;
+  ++h->generation;
   return LSD_OK;
 }
 
@@ -601,6 +604,8 @@ extern "C" int lsd_planar_stage_read(lsd_handle* h, const char* name, const char
   CUDA_OK(h, cudaGetLastError());
   return LSD_OK;
 }
+
+extern "C" int64_t lsd_state_generation(lsd_handle* h) { return h ? h->generation : -1; }
 
 extern "C" int lsd_workspace_invalidate(lsd_handle* h) {
   if (!h) return LSD_ERR_ARG;

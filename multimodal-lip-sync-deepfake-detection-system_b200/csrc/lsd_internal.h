@@ -84,10 +84,13 @@ struct lsd_handle {
   Prof prof;
   cudaStream_t side_stream = nullptr;      // artifact branch runs here, concurrently with the token path
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_start = nullptr, ev_audio = nullptr;
+  cudaStream_t side2_stream = nullptr;     // high-frequency branch, next to the temporal-inconsistency convolutions on side_stream
+  cudaEvent_t ev_join2 = nullptr;
   // independent pieces of the token path (the two attention directions, the three multi-scale branches) run side by side
   cudaStream_t tok_stream[2] = {nullptr, nullptr};
   cudaEvent_t ev_tok_fork = nullptr, ev_tok_join[2] = {nullptr, nullptr};
   int64_t launches0 = 0;
+  int64_t generation = 0;                  // bumped whenever device addresses baked into earlier launches become stale (see lsd_state_generation)
   // stage programs of the tcgen05 launches (umma_conv.cuh): built on the host once per (layer, shapes, workspace), cached here
   char* prog_arena = nullptr;
   size_t prog_cap = 0, prog_cursor = 0;

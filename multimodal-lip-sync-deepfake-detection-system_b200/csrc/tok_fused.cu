@@ -282,36 +282,51 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tok_fused_kernel(const __grid_c
     // are combined across the four warps of the lane quarter through shared memory in a fixed order (two-pass variance).
     auto layer_norm = [&](const float* cum, const float* g, const float* b) {
       const int c0 = cq * 64;
-      float v[64];
-      tmem_ld32(X + (uint32_t)c0, v);
-      tmem_ld32(X + (uint32_t)c0 + 32u, v + 32);
-      tmem_ld_wait();
-      add32(v, cum + c0);
-      add32(v + 32, cum + c0 + 32);
-      float s = 0.f;
-#pragma unroll
-      for (int e = 0; e < 64; ++e) s += v[e];
       const uint32_t red = sbase + OFF_RED + (uint32_t)row * 4u;           // [2][4 cq][128 rows] floats
+      float s = 0.f;
+#pragma unroll 1
+      for (int c = c0; c < c0 + 64; c += 32) {
+        float v[32];
+        tmem_ld32(X + (uint32_t)c, v);
+        tmem_ld_wait();
+        add32(v, cum + c);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) s += v[e];
+      }
       st_shared_f32(red + (uint32_t)cq * 512u, s);
       quarter_sync();
       const float mu = ((ld_shared_f32(red) + ld_shared_f32(red + 512u)) + (ld_shared_f32(red + 1024u) + ld_shared_f32(red + 1536u))) * (1.0f / TF_D);
       float d2 = 0.f;
+#pragma unroll 1
+      for (int c = c0; c < c0 + 64; c += 32) {
+        float v[32];
+        tmem_ld32(X + (uint32_t)c, v);
+        tmem_ld_wait();
+        add32(v, cum + c);
 #pragma unroll
-      for (int e = 0; e < 64; ++e) { v[e] -= mu; d2 = fmaf(v[e], v[e], d2); }
+        for (int e = 0; e < 32; ++e) { const float d = v[e] - mu; d2 = fmaf(d, d, d2); }
+      }
       st_shared_f32(red + 2048u + (uint32_t)cq * 512u, d2);
       quarter_sync();
       const float var = ((ld_shared_f32(red + 2048u) + ld_shared_f32(red + 2560u)) + (ld_shared_f32(red + 3072u) + ld_shared_f32(red + 3584u))) * (1.0f / TF_D);
       const float rstd = valid ? 1.0f / sqrtf(var + 1e-5f) : 0.f;          // rows outside the batch: zeros
+#pragma unroll 1
+      for (int c = c0; c < c0 + 64; c += 32) {
+        float v[32];
+        tmem_ld32(X + (uint32_t)c, v);
+        tmem_ld_wait();
+        add32(v, cum + c);
 #pragma unroll
-      for (int e4 = 0; e4 < 16; ++e4) {
-        const float4 gg = __ldg(reinterpret_cast<const float4*>(g + c0) + e4), bb = __ldg(reinterpret_cast<const float4*>(b + c0) + e4);
-        v[4 * e4] = valid ? fmaf(v[4 * e4] * rstd, gg.x, bb.x) : 0.f;
-        v[4 * e4 + 1] = valid ? fmaf(v[4 * e4 + 1] * rstd, gg.y, bb.y) : 0.f;
-        v[4 * e4 + 2] = valid ? fmaf(v[4 * e4 + 2] * rstd, gg.z, bb.z) : 0.f;
-        v[4 * e4 + 3] = valid ? fmaf(v[4 * e4 + 3] * rstd, gg.w, bb.w) : 0.f;
+        for (int e4 = 0; e4 < 8; ++e4) {
+          const float4 gg = __ldg(reinterpret_cast<const float4*>(g + c) + e4), bb = __ldg(reinterpret_cast<const float4*>(b + c) + e4);
+          v[4 * e4] = valid ? fmaf((v[4 * e4] - mu) * rstd, gg.x, bb.x) : 0.f;
+          v[4 * e4 + 1] = valid ? fmaf((v[4 * e4 + 1] - mu) * rstd, gg.y, bb.y) : 0.f;
+          v[4 * e4 + 2] = valid ? fmaf((v[4 * e4 + 2] - mu) * rstd, gg.z, bb.z) : 0.f;
+          v[4 * e4 + 3] = valid ? fmaf((v[4 * e4 + 3] - mu) * rstd, gg.w, bb.w) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) st_plane8(sbase + OFF_ALN + (uint32_t)(c / 8 + j) * PLANE + row16, v + 8 * j);
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) st_plane8(sbase + OFF_ALN + (uint32_t)(c0 / 8 + j) * PLANE + row16, v + 8 * j);
     };
 
     for (int l = 0; l < TF_LAYERS; ++l) {
@@ -355,26 +370,34 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tok_fused_kernel(const __grid_c
         wait_mma();
         if (cq < 2) {
           const uint32_t S = ACC + (uint32_t)(cq * 128 + slot * SL);
-          float v[64];
-          tmem_ld32(S, v);
-          if (p.NT > 32) tmem_ld32(S + 32u, v + 32);
-          tmem_ld_wait();
           float mx = -INFINITY;
+#pragma unroll 1
+          for (int c0 = 0; c0 < p.NT; c0 += 32) {
+            float v[32];
+            tmem_ld32(S + (uint32_t)c0, v);
+            tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 64; ++e) if (e < p.NT) mx = fmaxf(mx, v[e]);
-          float sum = 0.f;
-#pragma unroll
-          for (int e = 0; e < 64; ++e) {
-            const float pe = (valid && e < p.NT) ? __expf(v[e] - mx) : 0.f;
-            // the row sum is taken over the fp16-rounded probabilities the tensor core multiplies with V
-            const float pr = __half2float(__float2half_rn(pe));
-            sum += pr;
-            v[e] = pr;
+            for (int e = 0; e < 32; ++e) if (c0 + e < p.NT) mx = fmaxf(mx, v[e]);
           }
+          float sum = 0.f;
           const uint32_t pbase = sbase + OFF_P + (uint32_t)cq * P_HEAD + row16;
+#pragma unroll 1
+          for (int c0 = 0; c0 < KW; c0 += 32) {
+            float v[32];
+            tmem_ld32(S + (uint32_t)c0, v);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (8 * j < KW) st_plane8(pbase + (uint32_t)j * PLANE, v + 8 * j);
+            for (int e = 0; e < 32; ++e) {
+              const float pe = (valid && c0 + e < p.NT) ? __expf(v[e] - mx) : 0.f;
+              // the row sum is taken over the fp16-rounded probabilities the tensor core multiplies with V
+              const float pr = __half2float(__float2half_rn(pe));
+              sum += pr;
+              v[e] = pr;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (c0 + 8 * j < KW) st_plane8(pbase + (uint32_t)(c0 / 8 + j) * PLANE, v + 8 * j);
+          }
           inv_sum = (valid && sum > 0.f) ? 1.0f / sum : 0.f;
         }
         done();
@@ -414,7 +437,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tok_fused_kernel(const __grid_c
     }
     // ---- tok <- X + total bias
     wait_mma();
-    if (valid) {
+    if (__any_sync(0xffffffffu, valid)) {     // warp-uniform: tcgen05.ld is .sync.aligned, only the stores are per row
       const float* cum = cum_all + (size_t)(2 * TF_LAYERS) * TF_D;
 #pragma unroll 1
       for (int c0 = cq * 64; c0 < cq * 64 + 64; c0 += 32) {
@@ -422,8 +445,10 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tok_fused_kernel(const __grid_c
         tmem_ld32(X + (uint32_t)c0, v);
         tmem_ld_wait();
         add32(v, cum + c0);
+        if (valid) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) *reinterpret_cast<float4*>(grow + c0 + 4 * e) = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+          for (int e = 0; e < 8; ++e) *reinterpret_cast<float4*>(grow + c0 + 4 * e) = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+        }
       }
     }
   }

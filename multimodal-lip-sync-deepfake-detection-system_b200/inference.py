@@ -15,6 +15,8 @@ Video decode, face tracking, VAD and the gate/verdict block of `_predict_long_vi
 from __future__ import annotations
 
 import ctypes as C
+import os
+import time
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -69,6 +71,10 @@ class Predictor:
         chunk_size: int = 32,
         chunk_stride: int = 8,
         batch_size: int = 64,
+        use_cuda_graphs: bool = True,
+        graph_max_batch: int = 8,
+        host_transport: str = "auto",
+        host_pack_threads: Optional[int] = None,
     ) -> None:
         self.model = model
         self.device = device if device is not None else (model._device() if model is not None else torch.device("cpu"))
@@ -87,6 +93,25 @@ class Predictor:
         self.chunk_size = int(chunk_size)
         self.chunk_stride = int(chunk_stride)
         self.batch_size = int(max(1, batch_size))
+        #: small host batches (the B=1 calls of `_infer_confidence`, the 1+3 windows of `_temporal_smoothed_confidence`) replay a
+        #: captured CUDA graph (H2D copies + the ~60 launches of the forward + D2H) instead of enqueueing launch by launch
+        self.use_cuda_graphs = bool(use_cuda_graphs)
+        self.graph_max_batch = int(graph_max_batch)
+        self._graphs = {}
+        self.graph_captures = 0      # how many graphs this predictor captured (a rising count under steady shapes = re-capture churn)
+        #: how fp32 host windows cross PCIe in `score_batches`: "u8" packs windows whose pixels are exactly k/255 (what
+        #: video.py:552-556 produces) to one byte per pixel on the host threads (`lsd_host_pack_u8_exact`: verified value by value,
+        #: logits bit-identical), "fp32" copies them as they are, "auto" packs when the first batch qualifies and the host packs
+        #: faster than PCIe would move the fp32 bytes
+        if host_transport not in ("auto", "u8", "fp32"):
+            raise ValueError(f"host_transport must be 'auto', 'u8' or 'fp32', got {host_transport!r}")
+        self.host_transport = host_transport
+        if host_pack_threads is None:
+            local_ws = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+            host_pack_threads = max(1, min(32, (os.cpu_count() or 1) // local_ws))
+        self.host_pack_threads = int(host_pack_threads)
+        self.last_transport = "fp32"
+        self.last_h2d_bytes_per_batch = 0
 
     # ------------------------------------------------------------------ calibration (predictor.py:226-244)
     def _calibrate(self, logit_val: float) -> float:
@@ -104,6 +129,9 @@ class Predictor:
     def _infer_logits(self, visuals: Sequence[np.ndarray], audios: Sequence[np.ndarray]) -> List[float]:
         """Batched forward over host windows of one common shape, `batch_size` windows per launch."""
         n = len(visuals)
+        if (self.use_cuda_graphs and 0 < n <= self.graph_max_batch and self.model is not None and self.device.type == "cuda"
+                and self.model._precision() == _cabi.LSD_PREC_BF16):
+            return self._infer_logits_graph(visuals, audios)
 
         def gen():
             for i0 in range(0, n, self.batch_size):
@@ -115,6 +143,64 @@ class Predictor:
         for t in self.score_batches(gen()):
             out.extend(float(x) for x in t.tolist())
         return out
+
+    # ------------------------------------------------------------------ CUDA-graph path for small host batches
+    def _infer_logits_graph(self, visuals: Sequence[np.ndarray], audios: Sequence[np.ndarray]) -> List[float]:
+        """`len(visuals) <= graph_max_batch` host windows of one shape -> logits, through a CUDA graph captured once per
+        (batch, shapes, dtype): pinned staging -> H2D -> `lsd_forward` (all of its streams) -> D2H.  Same kernels, same
+        numerics as the launch-by-launch path (tests compare them bitwise)."""
+        m = self.model
+        dev = self.device
+        v = np.stack(visuals)
+        a = np.stack(audios)
+        dt = torch.float16 if self.use_half_precision else torch.float32
+        with m._lsd_lock:
+            key = (v.shape, a.shape, dt, m.state_generation())
+            ent = self._graphs.get(key)
+            if ent is None:
+                for k in [k for k in self._graphs if k[3] != key[3]]:      # stale generations
+                    del self._graphs[k]
+                ent = self._graphs[key] = self._capture_graph(v.shape, a.shape, dt)
+                self.graph_captures += 1
+            vh, ah, oh, graph = ent["vh"], ent["ah"], ent["oh"], ent["graph"]
+            vh.copy_(torch.from_numpy(v))
+            ah.copy_(torch.from_numpy(a))
+            graph.replay()
+            torch.cuda.current_stream(dev).synchronize()
+            return [float(x) for x in oh.tolist()]
+
+    def _capture_graph(self, vshape, ashape, dt):
+        m = self.model
+        dev = self.device
+        B, _, T, H, W = vshape
+        F_, Ta = ashape[2], ashape[3]
+        ent = {
+            "vh": torch.empty(vshape, dtype=dt).pin_memory(), "ah": torch.empty(ashape, dtype=dt).pin_memory(),
+            "vd": torch.empty(vshape, dtype=dt, device=dev), "ad": torch.empty(ashape, dtype=dt, device=dev),
+            "od": torch.empty(B, dtype=torch.float32, device=dev), "oh": torch.empty(B, dtype=torch.float32).pin_memory(),
+            "ws": torch.empty(m.workspace_bytes(B, T, H, W, F_, Ta) + 1024, dtype=torch.uint8, device=dev),   # private: its padding persists
+        }
+        ent["vh"].zero_()
+        ent["ah"].zero_()
+
+        def body():
+            ent["vd"].copy_(ent["vh"], non_blocking=True)
+            ent["ad"].copy_(ent["ah"], non_blocking=True)
+            m.forward_into(ent["vd"], ent["ad"], ent["od"], ent["ws"])
+            ent["oh"].copy_(ent["od"], non_blocking=True)
+
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):       # the first call of a shape uploads stage programs and zeroes the padding: not capturable
+                body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            body()
+        ent["graph"] = g
+        return ent
 
     def score_batches(self, batches) -> List[torch.Tensor]:
         """Pipelined scoring of a sequence of HOST batches `(visual (B,3,T,H,W), audio (B,1,F,Ta))` (torch CPU tensors, ideally
@@ -138,10 +224,53 @@ class Predictor:
         slots, ready, free = self._slot_cache
         outs: List[torch.Tensor] = []
         pool, pool_off = None, 0
-        for k, (vh, ah) in enumerate(batches):
+        stage = getattr(self, "_u8_stage", None)
+        if stage is None:
+            stage = self._u8_stage = [None] * NS
+        L = _cabi.lib()
+        state = {"mode": "fp32" if self.use_half_precision else self.host_transport}
+
+        def prepare(k, vh, ah):
+            """Host side of batch k (runs one batch ahead of the enqueue loop, on a helper thread: the pack releases the GIL)."""
             s = k % NS
             if self.use_half_precision:
                 vh, ah = vh.half(), ah.half()
+            transport = "fp32"
+            if state["mode"] != "fp32" and vh.dtype == torch.float32 and vh.device.type == "cpu" and vh.is_contiguous():
+                if stage[s] is None or stage[s].shape != vh.shape:
+                    stage[s] = torch.empty(vh.shape, dtype=torch.uint8).pin_memory()
+                elif k >= NS:
+                    ready[s].synchronize()    # the H2D copy that last read this staging buffer (batch k - NS) has finished
+                t0 = time.perf_counter()
+                ok = L.lsd_host_pack_u8_exact(vh.data_ptr(), stage[s].data_ptr(), vh.numel(), self.host_pack_threads)
+                dt = time.perf_counter() - t0
+                if ok == 1:
+                    if state["mode"] == "auto" and k >= 1:
+                        # keep packing only when it beats the copy it saves (fp32 bytes at ~50 GB/s of PCIe gen5 x16); decided on
+                        # the second batch: the first one also pays for starting the pack threads
+                        state["mode"] = "u8" if dt < vh.numel() * 4 / 50e9 else "fp32"
+                    vh = stage[s]
+                    transport = "u8 (host-packed, exact)"
+                else:
+                    state["mode"] = "fp32"       # not k/255 data: stop checking for the rest of this call
+            return vh, ah, transport
+
+        it = iter(batches)
+        first = next(it, None)
+        if first is None:
+            return outs
+        if getattr(self, "_prep_pool", None) is None:
+            import concurrent.futures
+            self._prep_pool = concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix="lsd-pack")
+        fut = self._prep_pool.submit(prepare, 0, *first)
+        k = 0
+        while fut is not None:
+            vh, ah, transport = fut.result()
+            nxt = next(it, None)
+            fut = self._prep_pool.submit(prepare, k + 1, *nxt) if nxt is not None else None
+            s = k % NS
+            self.last_transport = transport        # of the last batch shipped
+            self.last_h2d_bytes_per_batch = vh.numel() * vh.element_size() + ah.numel() * ah.element_size()
             if slots[s] is None or slots[s][0].shape != vh.shape or slots[s][0].dtype != vh.dtype or slots[s][1].shape != ah.shape:
                 slots[s] = (torch.empty(vh.shape, dtype=vh.dtype, device=dev), torch.empty(ah.shape, dtype=ah.dtype, device=dev))
                 free[s].record(comp)
@@ -162,6 +291,7 @@ class Predictor:
             pool_off += nb
             host.copy_(logits.float(), non_blocking=True)
             outs.append(host)
+            k += 1
         comp.synchronize()
         return outs
 

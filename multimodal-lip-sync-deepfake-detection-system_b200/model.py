@@ -236,6 +236,33 @@ class LipSyncModel(nn.Module):
             return logits
         return logits, {k: v.to(out_dtype) for k, v in aux_t.items()}
 
+    def forward_into(self, visual: Tensor, audio: Tensor, logits: Tensor, workspace: Tensor) -> None:
+        """Allocation-free forward for CUDA-graph capture: device `visual (B,3,T,H,W)` / `audio (B,1,F,T_a)` (contiguous),
+        fp32 device `logits (B,)`, caller-owned `workspace` (uint8, >= `workspace_bytes(...)`), current stream."""
+        B, _, T, H, W = visual.shape
+        F_, Ta = int(audio.shape[2]), int(audio.shape[3])
+        dev = self._device()
+        with self._lsd_lock:
+            h = self._ensure_handle(dev)
+            rc = _cabi.lib().lsd_forward(h.ptr, visual.data_ptr(), _DTYPES[visual.dtype], _cabi.LSD_NCDHW, audio.data_ptr(), _DTYPES[audio.dtype],
+                                         int(B), int(T), int(H), int(W), F_, Ta, self._precision(), logits.data_ptr(), None,
+                                         workspace.data_ptr(), workspace.numel(), torch.cuda.current_stream(dev).cuda_stream)
+            _cabi.check(h.ptr, rc)
+
+    def workspace_bytes(self, B: int, T: int, H: int, W: int, F_: int, Ta: int) -> int:
+        with self._lsd_lock:
+            h = self._ensure_handle(self._device())
+            need = _cabi.lib().lsd_workspace_bytes(h.ptr, int(B), int(T), int(H), int(W), int(F_), int(Ta), self._precision())
+        if need == 0:
+            _cabi.check(h.ptr, _cabi.LSD_ERR_SHAPE)
+        return int(need)
+
+    def state_generation(self) -> int:
+        """Changes whenever device addresses a captured CUDA graph may hold became stale (`lsd_state_generation`)."""
+        with self._lsd_lock:
+            h = self._ensure_handle(self._device())
+            return int(_cabi.lib().lsd_state_generation(h.ptr))
+
     @torch.no_grad()
     def predict(self, visual: Tensor, audio: Tensor) -> Tensor:
         self.eval()

@@ -536,3 +536,51 @@ def test_fused_transformer_matches_layer_chain(model, seed0_sd):
     with torch.no_grad():
         ch_ref = orc.temporal(seed0_sd, orc.cross_modal(seed0_sd, v[:5, :16], a[:5, :8]))
     assert _rel(ch.cpu(), ch_ref) <= 2e-3
+
+
+def test_cuda_graph_small_batch_path_bitwise(model):
+    """`_infer_confidence` / `_temporal_smoothed_confidence` (predictor.py:212-244, 295-331) replay a captured CUDA graph for
+    small host batches: same kernels, so the logits equal the launch-by-launch path bit for bit, also after the graph has been
+    replayed with other data and after other shapes went through the handle."""
+    model.compute_precision = "bf16"
+    pg = lb.Predictor(model, use_cuda_graphs=True)
+    pn = lb.Predictor(model, use_cuda_graphs=False)
+    v, a = lb.synthetic_windows(3, 6)
+    vs, as_ = [x.numpy() for x in v], [x.numpy() for x in a]
+    for lo, n in ((0, 1), (1, 1), (0, 4), (2, 4), (5, 1)):
+        assert pg._infer_logits(vs[lo:lo + n], as_[lo:lo + n]) == pn._infer_logits(vs[lo:lo + n], as_[lo:lo + n]), (lo, n)
+    model(v.cuda(), a.cuda())                                   # other shapes through the shared handle in between
+    r1, c1, s1 = pg._temporal_smoothed_confidence(vs[0], as_[0])
+    r2, c2, s2 = pn._temporal_smoothed_confidence(vs[0], as_[0])
+    assert c1 == c2 and r1 == r2 and s1 == s2
+    assert len(pg._graphs) == 3                                  # (1 window), (4 windows), (3 half windows)
+
+
+def test_score_batches_u8_transport_bitwise(model):
+    """`Predictor.score_batches` on host fp32 windows (the `_run_chunked_inference` contract, predictor.py:554-580): windows whose
+    pixels are exactly uint8 / 255.0 (video.py:552-556) cross PCIe as bytes and give the same logits, bit for bit, as the fp32
+    upload and as a plain forward; windows that are not (here: one pixel nudged by an ulp) fall back to the fp32 upload."""
+    model.compute_precision = "bf16"
+    g = torch.Generator().manual_seed(5)
+    _, a = lb.synthetic_windows(9, 10)
+    v = torch.randint(0, 256, (10, 3, 32, 96, 96), dtype=torch.uint8, generator=g).to(torch.float32) / 255.0
+    batches = [(v[0:4].contiguous(), a[0:4].contiguous()), (v[4:8].contiguous(), a[4:8].contiguous()),
+               (v[6:10].contiguous(), a[6:10].contiguous()), (v[2:6].contiguous(), a[2:6].contiguous()), (v[8:10].contiguous(), a[8:10].contiguous())]
+    ref = [model(vb.cuda(), ab.cuda()).float().cpu() for vb, ab in batches]
+    p_u8 = lb.Predictor(model, host_transport="u8")
+    p_f32 = lb.Predictor(model, host_transport="fp32")
+    out_u8 = [t.clone() for t in p_u8.score_batches(batches)]
+    assert p_u8.last_transport.startswith("u8") and p_u8.last_h2d_bytes_per_batch == 2 * 3 * 32 * 96 * 96 + 2 * 80 * 128 * 4
+    out_f32 = [t.clone() for t in p_f32.score_batches(batches)]
+    assert p_f32.last_transport == "fp32"
+    for r, x, y in zip(ref, out_u8, out_f32):
+        assert torch.equal(r, x) and torch.equal(r, y)
+    # not k/255 data: detected, shipped as fp32, still identical to the plain forward
+    v2 = v.clone()
+    v2[5, 1, 7, 3, 2] = torch.nextafter(v2[5, 1, 7, 3, 2], torch.tensor(2.0))
+    b2 = [(v2[0:4].contiguous(), a[0:4].contiguous()), (v2[4:8].contiguous(), a[4:8].contiguous()), (v2[6:10].contiguous(), a[6:10].contiguous())]
+    ref2 = [model(vb.cuda(), ab.cuda()).float().cpu() for vb, ab in b2]
+    out2 = [t.clone() for t in p_u8.score_batches(b2)]
+    assert p_u8.last_transport == "fp32"
+    for r, x in zip(ref2, out2):
+        assert torch.equal(r, x)

@@ -167,3 +167,28 @@ def test_u8_normalisation_formula_is_exact():
     r = (np.float64(-255.0) * q.astype(np.float64) + i.astype(np.float64)).astype(np.float32)          # fmaf(-255, q, i)
     out = (r.astype(np.float64) * np.float64(c) + q.astype(np.float64)).astype(np.float32)              # fmaf(r, c, q)
     assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+
+
+def test_host_pack_u8_exact():
+    """`lsd_host_pack_u8_exact` (host threads, no GPU): packs fp32 pixels that are exactly uint8 / 255.0 (video.py:552-556) to
+    bytes and refuses anything else — including -0.0, NaN, out-of-range and one-ulp-off values, at any position (vector body,
+    scalar tail, any work item)."""
+    from lipsync_b200 import _cabi
+    L = _cabi.lib()
+    rng = np.random.default_rng(0)
+    for n, threads in ((0, 1), (1, 1), (31, 2), (256, 0), (1237, 3), (3 * (1 << 18) + 77, 4)):
+        k = rng.integers(0, 256, n, dtype=np.uint8)
+        if n >= 256:
+            k[:256] = np.arange(256)
+        x = k.astype(np.float32) / 255.0
+        d = np.full(n, 7, np.uint8)
+        assert L.lsd_host_pack_u8_exact(x.ctypes.data, d.ctypes.data, n, threads) == 1
+        assert np.array_equal(d, k)
+        if n == 0:
+            continue
+        for bad in (0.5, float(np.nextafter(np.float32(1 / 255), np.float32(1))), -1 / 255, 256 / 255, float("nan"), float("inf"), -0.0, 1e30, -1e30):
+            for pos in {0, n // 2, n - 1}:
+                y = x.copy()
+                y[pos] = bad
+                assert L.lsd_host_pack_u8_exact(y.ctypes.data, d.ctypes.data, n, threads) == 0, (n, bad, pos)
+    assert L.lsd_host_pack_u8_exact(None, None, 5, 1) == _cabi.LSD_ERR_ARG
