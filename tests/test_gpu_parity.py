@@ -584,3 +584,28 @@ def test_score_batches_u8_transport_bitwise(model):
     assert p_u8.last_transport == "fp32"
     for r, x in zip(ref2, out2):
         assert torch.equal(r, x)
+
+
+def test_preprocessed_validation_driver(model, seed0_sd, tmp_path):
+    """The reference's preprocessed-mode evaluator (scripts/validate_pipeline.py:382-525) on this backend: confidences equal
+    sigmoid(model(batch)) of the same batches bit for bit, decisions equal the fp32 oracle's, files are written."""
+    model.compute_precision = "bf16"
+    v, a = lb.synthetic_windows(21, 7)
+    labels = torch.tensor([1, 0, 1, 1, 0, 0, 1])
+
+    class DS:
+        def __len__(self):
+            return 7
+
+        def get_item(self, idx, train_mode_override=False):
+            return (None if idx == 2 else (v[idx], a[idx], labels[idx].float()))
+
+    res = lb.run_preprocessed_validation(DS(), lb.Predictor(model), output_dir=str(tmp_path), batch_size=4)
+    keep = [0, 1, 3, 4, 5, 6]
+    assert [r["sample_idx"] for r in res["rows"]] == keep
+    direct = torch.cat([model(v[[0, 1, 3]].cuda(), a[[0, 1, 3]].cuda()), model(v[[4, 5, 6]].cuda(), a[[4, 5, 6]].cuda())]).float().cpu()
+    conf = torch.tensor([r["confidence"] for r in res["rows"]], dtype=torch.float64)
+    assert torch.equal(conf, torch.sigmoid(direct).double())
+    ref = orc.forward(seed0_sd, v[keep], a[keep])
+    assert [r["predicted_label"] for r in res["rows"]] == [0 if float(torch.sigmoid(x)) >= 0.5 else 1 for x in ref]
+    assert res["metrics"]["total_samples"] == 6 and (tmp_path / "predictions.csv").is_file() and (tmp_path / "metrics.json").is_file()
