@@ -2,6 +2,7 @@
 // orchestration that runs the 3-D residual stages, the artifact-detector convolutions and the high-frequency
 // back end on it.  Host-side only.
 #include "forward_common.h"
+#include "tok_front.cuh"
 #include "tok_fused.cuh"
 #include "token_kernels.cuh"
 #include "umma_conv.cuh"
@@ -679,6 +680,49 @@ static int pack_tok_fused(lsd_handle* h, const std::vector<float>& f32) {
   return 0;
 }
 
+// Weight stream and vectors of the fused token-path front (tok_front.cu), in the order of tok_front.cuh.
+static int pack_tok_front(lsd_handle* h, const std::vector<float>& f32) {
+  std::vector<__half> w;
+  w.reserve((size_t)TFR_K16_TOTAL * 16 * 256);
+  // one (256 x 16*k16) block, packed [k16][2 planes][256][8]; get(ci, co) = weight of input channel ci, output channel co
+  auto emit = [&](int k16, auto&& get) {
+    for (int k = 0; k < k16; ++k)
+      for (int pl = 0; pl < 2; ++pl)
+        for (int n = 0; n < 256; ++n)
+          for (int e = 0; e < 8; ++e) w.push_back(__float2half_rn(get(k * 16 + pl * 8 + e, n)));
+  };
+  const ConvP &o0 = h->convs.at("cross.v2a.out"), &o1 = h->convs.at("cross.a2v.out"), &g0 = h->convs.at("cross.gate0"),
+              &fu = h->convs.at("cross.fuse"), &pp = h->convs.at("temporal.pre_scale_proj");
+  for (const ConvP* o : {&o0, &o1})
+    for (int hp = 0; hp < 4; ++hp) emit(4, [&](int ci, int co) { return f32[o->w_off + (size_t)(64 * hp + ci) * 256 + co]; });
+  emit(32, [&](int ci, int co) { return f32[g0.w_off + (size_t)ci * 256 + co]; });
+  emit(16, [&](int ci, int co) { return f32[fu.w_off + (size_t)ci * 256 + co]; });
+  const int ks[3] = {3, 5, 7};
+  for (int b = 0; b < 3; ++b) {
+    const ConvP& c = h->convs.at("temporal.branch_k" + std::to_string(ks[b]));
+    for (int j = 0; j < ks[b]; ++j)     // BN scale folded into the weights, shift added in the epilogue
+      emit(16, [&](int ci, int co) { return f32[c.w_off + ((size_t)j * 256 + ci) * 256 + co] * (c.has_scale ? f32[c.scale_off + co] : 1.0f); });
+    emit(16, [&](int ci, int co) { return f32[pp.w_off + (size_t)(256 * b + ci) * 256 + co]; });
+  }
+  if (w.size() != (size_t)TFR_N_STAGES * TFR_STAGE_BYTES / sizeof(__half)) return lsd_fail(h, LSD_ERR_WEIGHTS, "pack_tok_front: stream size mismatch");
+  std::vector<float> vec(TFR_V_TOTAL, 0.f);
+  auto cp = [&](int dst, size_t src, int n) { memcpy(vec.data() + dst, &f32[src], (size_t)n * sizeof(float)); };
+  cp(TFR_V_BO0, o0.shift_off, 256); cp(TFR_V_BO1, o1.shift_off, 256); cp(TFR_V_BG0, g0.shift_off, 256);
+  cp(TFR_V_WG2, h->vecs.at("cross.gate2.w"), 256); cp(TFR_V_BG2, h->vecs.at("cross.gate2.b"), 1);
+  cp(TFR_V_BF, fu.shift_off, 256);
+  cp(TFR_V_SH3, h->convs.at("temporal.branch_k3").shift_off, 256); cp(TFR_V_SH5, h->convs.at("temporal.branch_k5").shift_off, 256);
+  cp(TFR_V_SH7, h->convs.at("temporal.branch_k7").shift_off, 256);
+  cp(TFR_V_BP, pp.shift_off, 256); cp(TFR_V_CLS, h->vecs.at("temporal.cls"), 256);
+  for (void* q : {(void*)h->tokfr_w, (void*)h->tokfr_vec}) if (q) cudaFree(q);
+  h->tokfr_w = nullptr; h->tokfr_vec = nullptr;
+  cudaError_t e = cudaMalloc(&h->tokfr_w, w.size() * sizeof(__half));
+  if (e == cudaSuccess) e = cudaMemcpy(h->tokfr_w, w.data(), w.size() * sizeof(__half), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&h->tokfr_vec, vec.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(h->tokfr_vec, vec.data(), vec.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return lsd_fail(h, LSD_ERR_CUDA, "pack_tok_front: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 int pack_bf16_weights(lsd_handle* h, const std::vector<float>& f32_arena) {
   Packer P{h, f32_arena, {}, {}};
   h->blayers.clear();
@@ -730,7 +774,8 @@ int pack_bf16_weights(lsd_handle* h, const std::vector<float>& f32_arena) {
   if (e == cudaSuccess) e = cudaMalloc(&h->bbias, P.bias.size() * 4);
   if (e == cudaSuccess) e = cudaMemcpy(h->bbias, P.bias.data(), P.bias.size() * 4, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) return lsd_fail(h, LSD_ERR_CUDA, "pack_bf16_weights: %s", cudaGetErrorString(e));
-  return pack_tok_fused(h, f32_arena);
+  if (int rc = pack_tok_fused(h, f32_arena)) return rc;
+  return pack_tok_front(h, f32_arena);
 }
 
 void make_plan_bf16(lsd_handle* h, int B, int T, int H, int W, int F, int Ta, std::vector<Stage>& stages, size_t& bytes) {
@@ -817,6 +862,43 @@ static int token_path_bf16(const BCtx& b, const Shapes& s) {
   RUNC(b1, "cross.in_a", a_.in = &pbf("aint_p"); a_.in_lo = &pbf("aint_p_lo"); a_.og = gt; a_.y32 = pa; a_.y32_ld = 768);
   RUN("cross.in_v", a_.in = &pbf("vemb_p"); a_.in_lo = &pbf("vemb_p_lo"); a_.og = gt; a_.y32 = pv; a_.y32_ld = 768);
   join(1);
+  g_tl.mark(st, "T:inproj");
+  float* tok = b.f("tok");
+  // ---- attention core, output projections, gated fusion, multi-scale branches, pre_scale_proj, CLS row: one fused launch
+  // (tok_front.cu); LSD_TOK_FRONT=0 (debug / A-B tests) or more than 61 tokens per window fall back to the launch-by-launch chain
+  const char* front_env = getenv("LSD_TOK_FRONT");
+  const bool front_off = front_env && atoi(front_env) == 0;
+  if (!front_off && tok_front_supported(T)) {
+    TokFrontP fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.pv = pv; fp.pa = pa; fp.v_emb = b.f("v_emb"); fp.a_int = b.f("a_int");
+    fp.gi = gi; fp.fused = b.f("fused"); fp.tok = tok;
+    fp.w = reinterpret_cast<const __half*>(h->tokfr_w);
+    fp.vec = h->tokfr_vec;
+    fp.B = B; fp.T = T;
+    tok_front_geometry(T, fp.SL, fp.G, fp.KW);
+    if (getenv("LSD_TOKF_TRACE")) {
+      // debug: phase timestamps of CTA 0 (compute warp 0: start, then [hand-over, next accumulator arrival] per phase; MMA warp:
+      // [phase start, issue end]); prints after a sync, never enabled in timed runs
+      static long long* dbuf = nullptr;
+      if (!dbuf) cudaMalloc(&dbuf, 256 * sizeof(long long));
+      cudaMemsetAsync(dbuf, 0, 256 * sizeof(long long), st);
+      fp.dbg = dbuf;
+      launch_tok_front(fp, st);
+      std::vector<long long> hv(256);
+      cudaMemcpyAsync(hv.data(), dbuf, 256 * sizeof(long long), cudaMemcpyDeviceToHost, st);
+      cudaStreamSynchronize(st);
+      const long long t0 = hv[128];
+      fprintf(stderr, "[tokfront] compute (start=0) then (hand-over, next arrival):");
+      for (int i = 0; i < 63 && hv[128 + 2 * i + 1]; ++i) fprintf(stderr, " (%lld,%lld)", hv[128 + 2 * i + 1] - t0, hv[128 + 2 * i + 2] ? hv[128 + 2 * i + 2] - t0 : 0);
+      fprintf(stderr, "\n[tokfront] mma phases (start, issue-end):");
+      for (int i = 0; i < 64 && hv[2 * i + 1]; ++i) fprintf(stderr, " (%lld,%lld)", hv[2 * i] - t0, hv[2 * i + 1] - t0);
+      fprintf(stderr, "\n");
+      fp.dbg = nullptr;
+    } else
+    launch_tok_front(fp, st);
+    g_tl.mark(st, "T:cross");
+  } else {
   fork(1);
   launch_mha_core_p(pv, 768, pa + 256, 768, pa + 512, 768, B, T, T, 8, pout(b, pbf("att1_p"), &pbf("att1_p_lo")), st);  // v2a: Q=v, K/V=a
   RUN("cross.v2a.out", a_.in = &pbf("att1_p"); a_.in_lo = &pbf("att1_p_lo"); a_.og = gt; a_.res32 = b.f("v_emb"); a_.res32_ld = 256; a_.y32 = gi; a_.y32_ld = 512;
@@ -830,7 +912,6 @@ static int token_path_bf16(const BCtx& b, const Shapes& s) {
   RUN("cross.fuse", a_.in = &pbf("blend_p"); a_.in_lo = &pbf("blend_p_lo"); a_.og = gt; a_.act = ACT_RELU; a_.y32 = b.f("fused"); a_.y32_ld = 256; a_.yp = &pbf("fused_p"); a_.yp_lo = &pbf("fused_p_lo"));
   // ---- temporal transformer (temporal.py:79-111)
   g_tl.mark(st, "T:cross");
-  float* tok = b.f("tok");
   fork(2);
   RUNC(b1, "temporal.branch_k5", a_.in = &pbf("fused_p"); a_.in_lo = &pbf("fused_p_lo"); a_.og = gt; a_.act = ACT_GELU; a_.yp = &pbf("mscat_p"); a_.yp_lo = &pbf("mscat_p_lo"); a_.y_plane_off = 32);
   RUNC(b2, "temporal.branch_k3", a_.in = &pbf("fused_p"); a_.in_lo = &pbf("fused_p_lo"); a_.og = gt; a_.act = ACT_GELU; a_.yp = &pbf("mscat_p"); a_.yp_lo = &pbf("mscat_p_lo"); a_.y_plane_off = 0);
@@ -840,6 +921,7 @@ static int token_path_bf16(const BCtx& b, const Shapes& s) {
   // pre_scale_proj + residual, written straight into token rows 1..T of each window
   RUN("temporal.pre_scale_proj", a_.in = &pbf("mscat_p"); a_.in_lo = &pbf("mscat_p_lo"); a_.og = gt; a_.res32 = b.f("fused"); a_.res32_ld = 256; a_.y32 = tok; a_.y32_ld = 256;
       a_.y32_outer_stride = NT; a_.y32_row_off = 1);
+  }
   // ---- the four encoder layers: one fused launch (tok_fused.cu); LSD_TOK_FUSED=0 (debug / A-B tests) or more than 64 tokens per
   // window fall back to the layer-by-layer GEMM chain
   const char* fused_env = getenv("LSD_TOK_FUSED");

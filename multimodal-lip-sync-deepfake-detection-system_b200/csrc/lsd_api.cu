@@ -11,6 +11,7 @@
 #include <cstring>
 
 #include "forward_common.h"
+#include "tok_front.cuh"
 #include "tok_fused.cuh"
 #include "umma_conv.cuh"
 using namespace lsd;
@@ -81,6 +82,7 @@ extern "C" int lsd_create(lsd_handle** out, int device) {
   if (rc == 0) {
     cudaError_t ce = lsd::umma_conv_device_init();
     if (ce == cudaSuccess) ce = lsd::tok_fused_device_init();
+    if (ce == cudaSuccess) ce = lsd::tok_front_device_init();
     if (ce != cudaSuccess) rc = lsd_fail(h, LSD_ERR_CUDA, "lsd_create: kernel attribute setup: %s", cudaGetErrorString(ce));
   }
   if (rc != 0) { g_create_error = h->err; delete h; return rc; }
@@ -94,6 +96,8 @@ extern "C" void lsd_destroy(lsd_handle* h) {
   if (h->warena) cudaFree(h->warena);
   if (h->barena) cudaFree(h->barena);
   if (h->bbias) cudaFree(h->bbias);
+  if (h->tokfr_w) cudaFree(h->tokfr_w);
+  if (h->tokfr_vec) cudaFree(h->tokfr_vec);
   if (h->tokf_w) cudaFree(h->tokf_w);
   if (h->tokf_stage_bytes) cudaFree(h->tokf_stage_bytes);
   if (h->tokf_vec) cudaFree(h->tokf_vec);

@@ -67,6 +67,8 @@ struct lsd_handle {
   std::map<std::string, size_t> vecs;      // small fp32 vectors (offsets into warena)
   float* bbias = nullptr;                  // fp32 biases of the bf16 layers
   // fused temporal-transformer kernel (tok_fused.cu): fp16 weight stream, per-layer stage sizes, small fp32 vectors
+  void* tokfr_w = nullptr;                 // fused token-path front (tok_front.cu): packed fp16 weight stream + fp32 vectors
+  float* tokfr_vec = nullptr;
   void* tokf_w = nullptr;
   uint32_t* tokf_stage_bytes = nullptr;
   float* tokf_vec = nullptr;

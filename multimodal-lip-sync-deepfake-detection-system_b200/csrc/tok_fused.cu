@@ -27,18 +27,19 @@
 #include <cstdio>
 
 #include "lsd_kernels.h"
+#include "tok_common.cuh"
 #include "umma.cuh"
 
 namespace lsd {
 
 using namespace umma;
+using namespace tokc;
 
 namespace {
 
 constexpr int TF_CWARPS = 16;                        // compute warps: 4 per TMEM lane quarter
 constexpr int TF_THREADS = (TF_CWARPS + 2) * 32;     // + weight producer + MMA issuer
 constexpr int TF_RING = 5;
-constexpr uint32_t PLANE = 2048;                     // one 8-channel plane of a 128-row operand
 constexpr uint32_t OFF_ALN = 0;                      // LayerNorm output, K = 256: 32 planes
 constexpr uint32_t OFF_QK = 65536;                   // Q0 K0 Q1 K1: 4 planes each (hd = 32); aliased by ATT (K = 64: 8 planes) after S
 constexpr uint32_t OFF_VT = OFF_QK + 32768;          // V^T of the two heads: [key plane (16)][32 hd rows][8 keys], 8 KB per head
@@ -52,64 +53,11 @@ static_assert(OFF_RING - OFF_FF >= 16 * PLANE, "the FF chunk operand must fit in
 static_assert(TF_SMEM <= 225 * 1024, "shared-memory budget");
 constexpr uint32_t X_COL = 0, ACC_COL = 256;
 
-__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
-  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);   // D = f32, A = B = f16, K-major, dense
-}
-
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
-  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
-      "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
-      "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-  const __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<const uint32_t*>(&h);
-}
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ void st_shared_u16(uint32_t addr, unsigned short v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory"); }
-__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
-__device__ __forceinline__ float ld_shared_f32(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory"); return v; }
-// 8 consecutive fp32 -> one 16-byte fp16 row piece of a plane
-__device__ __forceinline__ void st_plane8(uint32_t addr, const float* v) {
-  st_shared_v4(addr, pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-}
-// v[0..32) += p[0..32)  (p 16-byte aligned, read-only parameters: vector loads through the read-only path)
-__device__ __forceinline__ void add32(float* v, const float* p) {
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(p) + e);
-    v[4 * e] += t.x; v[4 * e + 1] += t.y; v[4 * e + 2] += t.z; v[4 * e + 3] += t.w;
-  }
-}
-// Exact-erf GELU (approximate='none', temporal.py:39-49 / nn.TransformerEncoderLayer activation="gelu") with erf from
-// Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7): two MUFU (rcp, ex2) + 8 FMA instead of erff's ~30 instructions — the FFN
-// epilogue (1024 activations per token and layer) was the largest compute phase of the kernel.  The result is rounded to fp16.
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float w = poly * t * __expf(-z * z);          // = 1 - erf(|x| / sqrt 2) = erfc
-  return 0.5f * x * (x >= 0.f ? 2.0f - w : w);         // 1 + erf(x / sqrt 2), without cancellation for x < 0
-}
-
 }  // namespace
 
 __global__ void __launch_bounds__(TF_THREADS, 1) tok_fused_kernel(const __grid_constant__ TokFusedP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t w_full[TF_RING], w_empty[TF_RING], bar_mma, bar_cmp;
+  __shared__ uint64_t w_full[TF_RING], w_empty[TF_RING], bar_mma, bar_cmp, bar_f1[2], bar_gd[2];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sbase = smem_u32(smem);
@@ -119,6 +67,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tok_fused_kernel(const __grid_c
     for (int i = 0; i < TF_RING; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     mbar_init(&bar_mma, 1);
     mbar_init(&bar_cmp, TF_CWARPS);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_f1[i], 1); mbar_init(&bar_gd[i], TF_CWARPS); }
     fence_barrier_init();
   }
   if (warp == W_MMA) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
@@ -151,7 +100,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tok_fused_kernel(const __grid_c
     // ------------------------------------------------------------------ MMA issuer (whole warp runs the loop, one lane issues)
     const uint32_t leader = elect_one() ? 1u : 0u;
     const uint64_t desc_hi = ((uint64_t)8 << 32) | ((uint64_t)1 << 46);   // SBO = 128 B, descriptor version 1
-    uint32_t par_c = 0;
+    uint32_t par_c = 0, par_g[2] = {0u, 0u};
     int ws = 0;                                                           // weight stages consumed so far
     // debug (p.dbg != nullptr, CTA 0): clock64 at the start and at the issue-end of every MMA phase
     long long* dbg = (p.dbg && blockIdx.x == 0 && lane == 0) ? reinterpret_cast<long long*>(p.dbg) : nullptr;
@@ -226,30 +175,47 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tok_fused_kernel(const __grid_c
       wait_cmp();                                                         // attention output of the last pair
       gemm_w(sbase + OFF_QK, 256, 4, 2, X, 1u);
       done();
-      // ---- FFN: chunks of 128 hidden channels
+      // ---- FFN, software-pipelined over chunks of 128 hidden channels: FF1 of chunk c+2 and FF2 of chunk c are issued while the
+      // compute warps apply the GELU to chunk c+1 (two accumulator halves, two GELU'd operands; the barriers of the two halves
+      // alternate, so neither side can run more than one completed phase ahead of the other)
+      wait_cmp();                                                         // LN2 output
+      gemm_w(sbase + OFF_ALN, 128, 16, 4, ACC, 0u);                       // h_0 = LN2 @ W1[0:128]^T
+      mma_commit_pred(&bar_f1[0], leader);
+      gemm_w(sbase + OFF_ALN, 128, 16, 4, ACC + 128u, 0u);                // h_1
+      mma_commit_pred(&bar_f1[1], leader);
       for (int c = 0; c < 8; ++c) {
-        wait_cmp();                                                       // LN2 output (c = 0) / GELU'd chunk c-1
-        if (c > 0) gemm_w(sbase + OFF_FF, 256, 8, 2, X, 1u);              // X += h_{c-1} @ W2[:, 128(c-1) : 128c]^T
-        gemm_w(sbase + OFF_ALN, 128, 16, 4, ACC, 0u);                     // h_c = LN2 @ W1[128c : 128c+128]^T
-        done();
+        const int hb = c & 1;
+        mbar_wait(&bar_gd[hb], par_g[hb]); par_g[hb] ^= 1u; tc_fence_after();            // GELU'd chunk c in operand hb, accumulator half hb read
+        gemm_w(sbase + (hb ? OFF_FF : OFF_QK), 256, 8, 2, X, 1u);         // X += h_c @ W2[:, 128c : 128c+128]^T
+        if (c + 2 < 8) {
+          gemm_w(sbase + OFF_ALN, 128, 16, 4, ACC + (uint32_t)hb * 128u, 0u);   // h_{c+2}
+          mma_commit_pred(&bar_f1[hb], leader);
+        }
       }
-      wait_cmp();
-      gemm_w(sbase + OFF_FF, 256, 8, 2, X, 1u);
       done();
     }
   } else {
     // ------------------------------------------------------------------ compute warps: lane quarter q, column quarter cq
+    // Tile row (= TMEM lane) -> token: a window owns 4/G lane quarters and its tokens are interleaved over them (token = lane *
+    // (4/G) + quarter in window).  A warp can only read the TMEM lanes of quarter (warp % 4), and warp w issues on scheduler w % 4,
+    // so with a window's tokens in consecutive rows the quarters that hold a slot's unused rows (31 of 64 at NT = 33) would leave
+    // their schedulers idle while the others do all the elementwise work; interleaved, every scheduler gets the same share, and a
+    // warp's rows still belong to ONE window (the TMEM address of a tcgen05.ld must be warp-uniform).  Operand rows that are
+    // indexed by KEY (K, V^T) are stored in canonical order (krow): the score / P V tiles of a window then are contiguous column
+    // ranges, whatever the order of the query rows.
     const int q = warp & 3, cq = warp >> 2;
     const int row = q * 32 + lane;
-    const int slot = (q * 32) / SL;
-    const int lrow = row - slot * SL;
+    const int QW = 4 / G;
+    const int slot = q / QW;
+    const int lrow = lane * QW + (q - slot * QW);
+    const int krow = slot * SL + lrow;
     const int win = blockIdx.x * G + slot;
     const bool valid = slot < G && win < p.B && lrow < p.NT;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
     const uint32_t X = lane_base + X_COL, ACC = lane_base + ACC_COL;
     const uint32_t row16 = (uint32_t)row * 16u;
     float* grow = p.tok + ((size_t)(valid ? win : 0) * p.NT + (valid ? lrow : 0)) * TF_D;
-    uint32_t par_m = 0;
+    uint32_t par_m = 0, par_f[2] = {0u, 0u};
     // debug (p.dbg != nullptr, CTA 0, warp 0): clock64 when an accumulator arrives and when the compute phase hands over
     long long* dbg = (p.dbg && blockIdx.x == 0 && warp == 0 && lane == 0) ? reinterpret_cast<long long*>(p.dbg) + 192 : nullptr;
     int dbg_n = 0;
@@ -354,11 +320,11 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tok_fused_kernel(const __grid_c
 #pragma unroll
             for (int e = 0; e < 32; ++e) v[e] *= sc;
             if (part < 2) {
-              const uint32_t base = sbase + OFF_QK + (uint32_t)(2 * head + part) * 8192u + row16;
+              const uint32_t base = sbase + OFF_QK + (uint32_t)(2 * head + part) * 8192u + (part == 0 ? row16 : (uint32_t)krow * 16u);
 #pragma unroll
               for (int j = 0; j < 4; ++j) st_plane8(base + (uint32_t)j * PLANE, v + 8 * j);
             } else {
-              const uint32_t base = sbase + OFF_VT + (uint32_t)head * 8192u + (uint32_t)(row >> 3) * 512u + (uint32_t)(row & 7) * 2u;
+              const uint32_t base = sbase + OFF_VT + (uint32_t)head * 8192u + (uint32_t)(krow >> 3) * 512u + (uint32_t)(krow & 7) * 2u;
 #pragma unroll
               for (int d = 0; d < 32; ++d) st_shared_u16(base + (uint32_t)d * 16u, __half_as_ushort(__float2half_rn(v[d])));
             }
@@ -418,21 +384,26 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tok_fused_kernel(const __grid_c
       wait_mma();
       layer_norm(cum_all + (size_t)(2 * l + 1) * TF_D, lv + 512, lv + 768);
       done();
-      // ---- FFN chunks: GELU(acc + b1) -> fp16 planes of the K = 128 operand (this warp: 32 of the 128 columns)
+      // ---- FFN chunks: GELU(acc + b1) -> fp16 planes of the K = 128 operand (this warp: 32 of the 128 columns); accumulator half
+      // and operand buffer alternate with the chunk (see the MMA warp)
       const float* b1 = lv + 1024 + 768;
       for (int c = 0; c < 8; ++c) {
-        wait_mma();
+        const int hb = c & 1;
+        mbar_wait(&bar_f1[hb], par_f[hb]); par_f[hb] ^= 1u; tc_fence_after();
         {
           float v[32];
-          tmem_ld32(ACC + (uint32_t)(cq * 32), v);
+          tmem_ld32(ACC + (uint32_t)(hb * 128 + cq * 32), v);
           tmem_ld_wait();
           add32(v, b1 + c * 128 + cq * 32);
 #pragma unroll
           for (int e = 0; e < 32; ++e) v[e] = valid ? gelu_fast(v[e]) : 0.f;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) st_plane8(sbase + OFF_FF + (uint32_t)(cq * 4 + j) * PLANE + row16, v + 8 * j);
+          for (int j = 0; j < 4; ++j) st_plane8(sbase + (hb ? OFF_FF : OFF_QK) + (uint32_t)(cq * 4 + j) * PLANE + row16, v + 8 * j);
         }
-        done();
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_gd[hb]);
       }
     }
     // ---- tok <- X + total bias

@@ -14,8 +14,8 @@ constexpr int TF_SLOT_BYTES = 16384;      // largest weight-ring stage
 
 // One stage of the weight stream = `kps` K16 steps of a (N x K) block, packed [k16][2 planes][N][8] fp16.
 // Order of the blocks of one layer (host packer and device issue loop walk the same list, see tf_layer_blocks):
-//   QKV(0), OUT(0), QKV(1), OUT(1), QKV(2), OUT(2), QKV(3), OUT(3), FF1(0), FF2(0), FF1(1), ..., FF1(7), FF2(7)
-// where the device issues OUT(hp-1) together with QKV(hp) and FF2(c-1) together with FF1(c).
+//   QKV(0), OUT(0), QKV(1), OUT(1), QKV(2), OUT(2), QKV(3), OUT(3), FF1(0), FF1(1), FF2(0), FF1(2), FF2(1), ..., FF1(7), FF2(6), FF2(7)
+// where the device issues OUT(hp-1) together with QKV(hp), and FF2(c) together with FF1(c+2) while the GELU of chunk c+1 runs.
 struct TfBlock { int kind, idx, N, k16, kps; };   // kind: 0 QKV, 1 OUT, 2 FF1, 3 FF2
 inline void tf_layer_blocks(std::vector<TfBlock>& out) {
   out.clear();
@@ -24,9 +24,12 @@ inline void tf_layer_blocks(std::vector<TfBlock>& out) {
     out.push_back({1, hp, 256, 4, 2});    // out_proj columns, K = the 64 attention channels of this head pair
   }
   // (stream order: the device consumes QKV(hp) before OUT(hp); OUT(hp) is issued in the same MMA phase as QKV(hp+1))
+  // FFN, software-pipelined: FF1(0), FF1(1), then FF2(c) followed by FF1(c+2)
+  out.push_back({2, 0, 128, 16, 4});      // linear1 rows 128c..128c+127; K = 256
+  out.push_back({2, 1, 128, 16, 4});
   for (int c = 0; c < 8; ++c) {
-    out.push_back({2, c, 128, 16, 4});    // linear1 rows 128c..128c+127; K = 256
     out.push_back({3, c, 256, 8, 2});     // linear2 all rows, K = hidden 128c..128c+127
+    if (c + 2 < 8) out.push_back({2, c + 2, 128, 16, 4});
   }
 }
 

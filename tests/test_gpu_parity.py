@@ -509,33 +509,46 @@ def test_workspace_padding_survives_shape_changes(model):
     assert torch.equal(first, again)
 
 
-def test_fused_transformer_matches_layer_chain(model, seed0_sd):
-    """tok_fused.cu (one launch, fp16 operands) against the layer-by-layer GEMM chain (split-bf16, LSD_TOK_FUSED=0) and the
-    oracle, and bitwise independence of a window from its slot / co-tenants in the CTA."""
+def test_fused_token_kernels_match_layer_chain(model, seed0_sd):
+    """tok_front.cu + tok_fused.cu (two launches, fp16 operands) against the launch-by-launch GEMM chain (split-bf16,
+    LSD_TOK_FRONT=0 / LSD_TOK_FUSED=0) and the oracle — fused tokens (CrossModalAttention.forward, fusion_module.py:54-87) and
+    CLS output (TemporalTransformer.forward, temporal.py:79-111) — and bitwise independence of a window from its slot /
+    co-tenants in the CTA."""
     import os
     model.compute_precision = "bf16"
     g = torch.Generator().manual_seed(4)
     v = torch.randn(7, 32, 256, generator=g)
     a = torch.randn(7, 16, 256, generator=g)
     with torch.no_grad():
-        cls_ref = orc.temporal(seed0_sd, orc.cross_modal(seed0_sd, v, a))
+        f_ref = orc.cross_modal(seed0_sd, v, a)
+        cls_ref = orc.temporal(seed0_sd, f_ref)
+    res = {}
     try:
-        os.environ["LSD_TOK_FUSED"] = "0"
-        _, c_chain = model.fuse_tokens(v.cuda(), a.cuda())
-        os.environ["LSD_TOK_FUSED"] = "1"
-        _, c_fused = model.fuse_tokens(v.cuda(), a.cuda())
+        for front, fused in (("0", "0"), ("1", "0"), ("0", "1"), ("1", "1")):
+            os.environ["LSD_TOK_FRONT"], os.environ["LSD_TOK_FUSED"] = front, fused
+            f, c = model.fuse_tokens(v.cuda(), a.cuda())
+            res[front + fused] = (f.cpu(), c.cpu())
     finally:
+        os.environ.pop("LSD_TOK_FRONT", None)
         os.environ.pop("LSD_TOK_FUSED", None)
-    assert _rel(c_chain.cpu(), cls_ref) <= 2e-4
-    assert _rel(c_fused.cpu(), cls_ref) <= 2e-3
+    assert _rel(res["00"][0], f_ref) <= 5e-5 and _rel(res["00"][1], cls_ref) <= 2e-4          # chain
+    assert _rel(res["10"][0], f_ref) <= 1e-3 and _rel(res["10"][1], cls_ref) <= 1e-3          # fused front alone
+    assert torch.equal(res["01"][0], res["00"][0]) and _rel(res["01"][1], cls_ref) <= 2e-3    # fused transformer alone
+    assert torch.equal(res["11"][0], res["10"][0]) and _rel(res["11"][1], cls_ref) <= 2e-3    # both (the default)
+    f_all, c_all = model.fuse_tokens(v.cuda(), a.cuda())
+    assert torch.equal(f_all.cpu(), res["11"][0]) and torch.equal(c_all.cpu(), res["11"][1])
     for i in range(7):
-        _, ci = model.fuse_tokens(v[i:i + 1].cuda(), a[i:i + 1].cuda())
-        assert torch.equal(ci[0], c_fused[i])
-    # half windows: 17 tokens per window, three windows per CTA
-    _, ch = model.fuse_tokens(v[:5, :16].cuda(), a[:5, :8].cuda())
-    with torch.no_grad():
-        ch_ref = orc.temporal(seed0_sd, orc.cross_modal(seed0_sd, v[:5, :16], a[:5, :8]))
-    assert _rel(ch.cpu(), ch_ref) <= 2e-3
+        fi, ci = model.fuse_tokens(v[i:i + 1].cuda(), a[i:i + 1].cuda())
+        assert torch.equal(ci[0], c_all[i]) and torch.equal(fi[0], f_all[i])
+    # half windows (16 + 1 tokens: four windows per CTA) and other lengths (slot 64 with 40 tokens, slot 32 with 29)
+    for n, t, ta in ((5, 16, 8), (3, 40, 20), (3, 29, 16)):
+        g2 = torch.Generator().manual_seed(100 + t)
+        v2, a2 = torch.randn(n, t, 256, generator=g2), torch.randn(n, ta, 256, generator=g2)
+        fh, ch = model.fuse_tokens(v2.cuda(), a2.cuda())
+        with torch.no_grad():
+            fh_ref = orc.cross_modal(seed0_sd, v2, a2)
+            ch_ref = orc.temporal(seed0_sd, fh_ref)
+        assert _rel(fh.cpu(), fh_ref) <= 1e-3 and _rel(ch.cpu(), ch_ref) <= 2e-3, (n, t, ta)
 
 
 def test_cuda_graph_small_batch_path_bitwise(model):
