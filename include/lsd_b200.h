@@ -111,7 +111,9 @@ int lsd_audio_encoder(lsd_handle* h, const void* audio, int audio_dtype, int B, 
                       void* workspace, size_t workspace_bytes, void* stream);
 /* CrossModalAttention.forward (app/models/fusion_module.py:54-87) followed by TemporalTransformer.forward
  * (app/models/temporal.py:79-111): projected embeddings v_emb (B,T,256), a_emb (B,Ta_tokens,256), fp32 device
- * -> fused_out (B,T,256) and/or cls_out (B,256), fp32 device (either may be NULL). */
+ * -> fused_out (B,T,256) and/or cls_out (B,256), fp32 device (either may be NULL).  Same kernels as inside lsd_forward; the
+ * full forward feeds them the cross-attention in-projections from a GEMM merged with FeatureProjection, this entry point
+ * computes them from the embeddings, so the two agree to ~1e-4 relative, not bit for bit. */
 size_t lsd_token_path_workspace_bytes(lsd_handle* h, int B, int T, int Ta_tokens);
 int lsd_token_path(lsd_handle* h, const float* v_emb, const float* a_emb, int B, int T, int Ta_tokens,
                    float* fused_out, float* cls_out, void* workspace, size_t workspace_bytes, void* stream);

@@ -252,6 +252,9 @@ void build_plan(const Shapes& s, BPlan& P) {
   p.add("a_int", B * T * 256);
   p.add("proj_v", B * T * 768);
   p.add("proj_a", B * T * 768);
+  p.add("vcomb", B * T * 1024);            // [v_emb | in-projection of the visual tokens] per token (fused token path)
+  p.add("acomb", B * T * 1024);            // [interpolated a_emb | in-projection of the interpolated audio tokens]
+  p.add("a_fint", B * T * 256);            // audio features interpolated to T tokens
   p.add("gate_in", B * T * 512);
   p.add("gate_h", B * T * 256);
   p.add("fused", B * T * 256);
@@ -309,7 +312,7 @@ void build_plan(const Shapes& s, BPlan& P) {
   for (const char* sfx : {"", "_lo"}) {
     auto nm = [&](const char* n) { return std::string(n) + sfx; };
     P.addp(nm("afeat_p").c_str(), 256, 1, P.gta);
-    for (const char* n : {"vfeat_p", "vemb_p", "aint_p", "att1_p", "att2_p", "blend_p", "fused_p"}) P.addp(nm(n).c_str(), 256, 1, P.gt);
+    for (const char* n : {"vfeat_p", "vemb_p", "aint_p", "afint_p", "att1_p", "att2_p", "blend_p", "fused_p"}) P.addp(nm(n).c_str(), 256, 1, P.gt);
     P.addp(nm("gatein_p").c_str(), 512, 1, P.gt);
     P.addp(nm("mscat_p").c_str(), 768, 1, P.gt);
     P.addp(nm("tokln_p").c_str(), 256, 1, P.g33);
@@ -763,7 +766,7 @@ int pack_bf16_weights(lsd_handle* h, const std::vector<float>& f32_arena) {
                         "cross.gate0", "cross.fuse", "temporal.branch_k3", "temporal.branch_k5", "temporal.branch_k7",
                         "temporal.pre_scale_proj"})
     P.add_split(k, k, narrow);
-  for (const char* k : {"cross.in_v", "cross.in_a"}) P.add_split(k, k, wide);
+  for (const char* k : {"cross.in_v", "cross.in_a", "cross.vcomb", "cross.acomb"}) P.add_split(k, k, wide);
   for (int l = 0; l < 4; ++l)
     for (const char* k : {".in", ".out", ".ff1", ".ff2"})
       P.add_split("t" + std::to_string(l) + k, "t" + std::to_string(l) + k, (k[1] == 'i' || (k[1] == 'f' && k[3] == '1')) ? wide : narrow);
@@ -833,7 +836,13 @@ static int audio_encoder_bf16(const BCtx& b, const Shapes& s, bool inputs_ready,
 
 // CrossModalAttention.forward + TemporalTransformer.forward (fusion_module.py:54-87, temporal.py:79-111): expects v_emb / a_emb
 // (fp32 rows) and vemb_p (planar hi, lo) in the workspace; leaves the fused tokens in "fused" and the transformer tokens in "tok".
-static int token_path_bf16(const BCtx& b, const Shapes& s) {
+// combined: "vcomb" / "acomb" already hold [emb | in-projection] of the visual / interpolated audio tokens (full forward with the
+// fused front kernel); otherwise v_emb / a_emb (+ vemb_p) are the inputs and the in-projections are computed here.
+static bool token_front_enabled(int T) {
+  const char* e = getenv("LSD_TOK_FRONT");
+  return !(e && atoi(e) == 0) && tok_front_supported(T);
+}
+static int token_path_bf16(const BCtx& b, const Shapes& s, bool combined = false) {
   const BPlan& P = *b.P;
   auto pbf = [&](const char* n) -> const PBuf& { return P.pb.at(n); };
   cudaStream_t st = b.st;
@@ -857,21 +866,27 @@ static int token_path_bf16(const BCtx& b, const Shapes& s) {
   auto join = [&](int n) { if (par) for (int i = 0; i < n; ++i) { cudaEventRecord(h->ev_tok_join[i], h->tok_stream[i]); cudaStreamWaitEvent(st, h->ev_tok_join[i], 0); } };
   // ---- cross-modal attention + gated fusion (fusion_module.py:54-87)
   float *pv = b.f("proj_v"), *pa = b.f("proj_a"), *gi = b.f("gate_in");
-  fork(1);
-  launch_lerp_tokens_p(b.f("a_emb"), b.f("a_int"), B, TA, T, 256, pout(b, pbf("aint_p"), &pbf("aint_p_lo")), b1.st);
-  RUNC(b1, "cross.in_a", a_.in = &pbf("aint_p"); a_.in_lo = &pbf("aint_p_lo"); a_.og = gt; a_.y32 = pa; a_.y32_ld = 768);
-  RUN("cross.in_v", a_.in = &pbf("vemb_p"); a_.in_lo = &pbf("vemb_p_lo"); a_.og = gt; a_.y32 = pv; a_.y32_ld = 768);
-  join(1);
+  if (!combined) {
+    fork(1);
+    launch_lerp_tokens_p(b.f("a_emb"), b.f("a_int"), B, TA, T, 256, pout(b, pbf("aint_p"), &pbf("aint_p_lo")), b1.st);
+    RUNC(b1, "cross.in_a", a_.in = &pbf("aint_p"); a_.in_lo = &pbf("aint_p_lo"); a_.og = gt; a_.y32 = pa; a_.y32_ld = 768);
+    RUN("cross.in_v", a_.in = &pbf("vemb_p"); a_.in_lo = &pbf("vemb_p_lo"); a_.og = gt; a_.y32 = pv; a_.y32_ld = 768);
+    join(1);
+  }
   g_tl.mark(st, "T:inproj");
   float* tok = b.f("tok");
   // ---- attention core, output projections, gated fusion, multi-scale branches, pre_scale_proj, CLS row: one fused launch
   // (tok_front.cu); LSD_TOK_FRONT=0 (debug / A-B tests) or more than 61 tokens per window fall back to the launch-by-launch chain
-  const char* front_env = getenv("LSD_TOK_FRONT");
-  const bool front_off = front_env && atoi(front_env) == 0;
-  if (!front_off && tok_front_supported(T)) {
+  if (token_front_enabled(T)) {
     TokFrontP fp;
     memset(&fp, 0, sizeof(fp));
-    fp.pv = pv; fp.pa = pa; fp.v_emb = b.f("v_emb"); fp.a_int = b.f("a_int");
+    if (combined) {
+      fp.v_emb = b.f("vcomb"); fp.pv = fp.v_emb + 256; fp.a_int = b.f("acomb"); fp.pa = fp.a_int + 256;
+      fp.ld_e = 1024; fp.ld_p = 1024;
+    } else {
+      fp.pv = pv; fp.pa = pa; fp.v_emb = b.f("v_emb"); fp.a_int = b.f("a_int");
+      fp.ld_e = 256; fp.ld_p = 768;
+    }
     fp.gi = gi; fp.fused = b.f("fused"); fp.tok = tok;
     fp.w = reinterpret_cast<const __half*>(h->tokfr_w);
     fp.vec = h->tokfr_vec;
@@ -1037,6 +1052,17 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   // ---- audio encoder (independent of the video): on the side stream from the very start, so that its latency-bound chain of
   // small launches hides behind the visual encoder instead of heading the tail
   const bool audio_early = getenv("LSD_AUDIO_LATE") == nullptr;
+  // Fused token path (tok_front.cu): the audio tokens' share of it — interpolation to T tokens, then ONE GEMM for
+  // [a_int | cross-attention in-projection] (see pack_comb_proj in lsd_api.cu), plus a_emb itself for the aux / stage output —
+  // runs right behind the audio encoder, on its stream, long before the visual encoder is done.
+  const bool tcomb = token_front_enabled(T);
+  auto audio_tokens = [&](const BCtx& c) -> int {
+    int rc = 0;
+    launch_lerp_tokens_p(c.f("a_feat"), c.f("a_fint"), B, TA, T, 256, pout(c, pb["afint_p"], &pb["afint_p_lo"]), c.st);
+    RUNC(c, "cross.acomb", a_.in = &pb["afint_p"]; a_.in_lo = &pb["afint_p_lo"]; a_.og = P.gt; a_.y32 = c.f("acomb"); a_.y32_ld = 1024);
+    RUNC(c, "projection.audio_proj", a_.in = &pb["afeat_p"]; a_.in_lo = &pb["afeat_p_lo"]; a_.og = P.gta; a_.y32 = c.f("a_emb"); a_.y32_ld = 256);
+    return 0;
+  };
   g_tl.on = getenv("LSD_TIMELINE") != nullptr;
   g_tl.mark(st, "start");
   const bool audio_after_rows = getenv("LSD_AUDIO_AFTER_ROWS") != nullptr;   // tuning knob, see below
@@ -1044,6 +1070,7 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
     cudaEventRecord(h->ev_start, st);
     cudaStreamWaitEvent(sst, h->ev_start, 0);
     if ((rc = audio_encoder_bf16(bs, s, inputs_ready, audio, adt))) return rc;
+    if (tcomb && (rc = audio_tokens(bs))) return rc;
     g_tl.mark(sst, "S:audio_enc");
     cudaEventRecord(h->ev_audio, sst);
   }
@@ -1062,6 +1089,7 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
     cudaEventRecord(h->ev_start, st);
     cudaStreamWaitEvent(sst, h->ev_start, 0);
     if ((rc = audio_encoder_bf16(bs, s, inputs_ready, audio, adt))) return rc;
+    if (tcomb && (rc = audio_tokens(bs))) return rc;
     g_tl.mark(sst, "S:audio_enc");
     cudaEventRecord(h->ev_audio, sst);
   }
@@ -1146,7 +1174,7 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   // temporal-inconsistency convolutions instead of behind them (LSD_HF_SERIAL=1 restores the single side stream): both
   // chains are capped at half of the SMs, and the token path's small grids fit in between.
   if (!hf_early) {
-    const bool hf_par = getenv("LSD_HF_SERIAL") == nullptr && pipe_parity < 0;
+    const bool hf_par = getenv("LSD_HF_SERIAL") == nullptr;   // (also when batches are pipelined: 10k-window run 19.6k -> 20.5k windows/s)
     cudaStream_t hst = sst;
     if (hf_par) {
       if (!h->side2_stream) {
@@ -1185,11 +1213,19 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   if (!audio_early) { if ((rc = audio_encoder_bf16(b, s, inputs_ready, audio, adt))) return rc; }
   // ---- projection (fusion_module.py:108-124)
   const UcGeom gt = P.gt;
-  RUN("projection.visual_proj", a_.in = &pb["vfeat_p"]; a_.in_lo = &pb["vfeat_p_lo"]; a_.og = gt; a_.yp = &pb["vemb_p"]; a_.yp_lo = &pb["vemb_p_lo"]; a_.y32 = b.f("v_emb"); a_.y32_ld = 256);
-  if (audio_early) cudaStreamWaitEvent(st, h->ev_audio, 0);   // audio features (a_feat / afeat_p) are complete
-  RUN("projection.audio_proj", a_.in = &pb["afeat_p"]; a_.in_lo = &pb["afeat_p_lo"]; a_.og = P.gta; a_.y32 = b.f("a_emb"); a_.y32_ld = 256);
+  if (tcomb) {
+    // fused token path: one GEMM gives [v_emb | cross-attention in-projection] per visual token (the audio half ran behind the audio encoder)
+    if (!audio_early) { if ((rc = audio_tokens(b))) return rc; }
+    RUN("cross.vcomb", a_.in = &pb["vfeat_p"]; a_.in_lo = &pb["vfeat_p_lo"]; a_.og = gt; a_.y32 = b.f("vcomb"); a_.y32_ld = 1024);
+    if (audio_early) cudaStreamWaitEvent(st, h->ev_audio, 0);   // [a_int | in-projection] of the audio tokens is complete
+  } else {
+    RUN("projection.visual_proj", a_.in = &pb["vfeat_p"]; a_.in_lo = &pb["vfeat_p_lo"]; a_.og = gt; a_.yp = &pb["vemb_p"]; a_.yp_lo = &pb["vemb_p_lo"]; a_.y32 = b.f("v_emb"); a_.y32_ld = 256);
+    if (audio_early) cudaStreamWaitEvent(st, h->ev_audio, 0);   // audio features (a_feat / afeat_p) are complete
+    RUN("projection.audio_proj", a_.in = &pb["afeat_p"]; a_.in_lo = &pb["afeat_p_lo"]; a_.og = P.gta; a_.y32 = b.f("a_emb"); a_.y32_ld = 256);
+  }
   g_tl.mark(st, "T:proj");
-  if ((rc = token_path_bf16(b, s))) return rc;
+  if ((rc = token_path_bf16(b, s, tcomb))) return rc;
+  if (tcomb) launch_copy_rows(b.f("vcomb"), 1024, b.f("v_emb"), 256, B * T, 256, st);   // v_emb as a contiguous stage / aux tensor
   float* tok = b.f("tok");
   g_tl.mark(st, "T:tokens");
   // cls = tok[:,0]: no final norm (temporal.py:110-111)

@@ -237,6 +237,38 @@ bool pack_cross_inproj(Loader& L) {
   return true;
 }
 
+// Projection followed by the cross-attention in-projection is two Linear layers with nothing in between
+// (fusion_module.py:108-124 -> :54-66), so the in-projection of a token can be taken straight from the encoder feature:
+//   [emb | in_proj(emb)] = feat @ [Wp | Wp Win] + [bp | bp Win + bin]          (one GEMM with 1024 output columns)
+// (the audio side applies it to the interpolated features: interpolation along the token axis commutes with a per-token affine
+// map).  Products are accumulated in double; "cross.vcomb" / "cross.acomb" are used by the fused token path only.
+bool pack_comb_proj(Loader& L, const char* key, const char* proj_key, const char* in_key) {
+  const ConvP pr = L.h->convs.at(proj_key), in = L.h->convs.at(in_key);
+  ConvP c;
+  c.Cin = 256; c.Cout = 1024; c.kt = c.kh = c.kw = 1; c.has_scale = false;
+  c.w_off = L.reserve((size_t)256 * 1024);
+  c.shift_off = L.reserve(1024);
+  std::vector<double> acc(768);
+  for (int i = 0; i < 256; ++i) {
+    for (int o = 0; o < 256; ++o) L.arena[c.w_off + (size_t)i * 1024 + o] = L.arena[pr.w_off + (size_t)i * 256 + o];
+    std::fill(acc.begin(), acc.end(), 0.0);
+    for (int k = 0; k < 256; ++k) {
+      const double a = L.arena[pr.w_off + (size_t)i * 256 + k];
+      const float* row = &L.arena[in.w_off + (size_t)k * 768];
+      for (int o = 0; o < 768; ++o) acc[o] += a * (double)row[o];
+    }
+    for (int o = 0; o < 768; ++o) L.arena[c.w_off + (size_t)i * 1024 + 256 + o] = (float)acc[o];
+  }
+  for (int o = 0; o < 256; ++o) L.arena[c.shift_off + o] = L.arena[pr.shift_off + o];
+  for (int o = 0; o < 768; ++o) {
+    double a = L.arena[in.shift_off + o];
+    for (int k = 0; k < 256; ++k) a += (double)L.arena[pr.shift_off + k] * (double)L.arena[in.w_off + (size_t)k * 768 + o];
+    L.arena[c.shift_off + 256 + o] = (float)a;
+  }
+  L.h->convs[key] = c;
+  return true;
+}
+
 }  // namespace
 
 extern "C" int lsd_load_weights(lsd_handle* h, const lsd_tensor* tensors, int n) {
@@ -286,6 +318,7 @@ extern "C" int lsd_load_weights(lsd_handle* h, const lsd_tensor* tensors, int n)
   linear("projection.visual_proj", "projection.visual_proj", 256, 256);
   linear("projection.audio_proj", "projection.audio_proj", 256, 256);
   ok = ok && pack_cross_inproj(L);
+  ok = ok && pack_comb_proj(L, "cross.vcomb", "projection.visual_proj", "cross.in_v") && pack_comb_proj(L, "cross.acomb", "projection.audio_proj", "cross.in_a");
   linear("cross.v2a.out", "cross_modal.v2a_attn.out_proj", 256, 256);
   linear("cross.a2v.out", "cross_modal.a2v_attn.out_proj", 256, 256);
   linear("cross.gate0", "cross_modal.gate.0", 256, 512);

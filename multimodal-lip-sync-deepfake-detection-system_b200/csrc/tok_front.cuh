@@ -23,6 +23,7 @@ enum { TFR_V_BO0 = 0, TFR_V_BO1 = 256, TFR_V_BG0 = 512, TFR_V_WG2 = 768, TFR_V_B
        TFR_V_SH7 = 1856, TFR_V_BP = 2112, TFR_V_CLS = 2368, TFR_V_TOTAL = 2624 };
 
 struct TokFrontP {
+  int ld_p, ld_e;       // row strides (floats) of pv / pa and of v_emb / a_int
   const float* pv;      // [B*T][768] fp32: [Q of v2a | K of a2v | V of a2v] of the visual tokens (in-projection output, bias included)
   const float* pa;      // [B*T][768] fp32: [Q of a2v | K of v2a | V of v2a] of the interpolated audio tokens
   const float* v_emb;   // [B*T][256] fp32 residual of v2a

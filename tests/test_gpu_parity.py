@@ -290,16 +290,19 @@ def test_audio_encoder_subpath(model, seed0_sd):
 
 def test_token_path_subpath(model, seed0_sd):
     """lsd_token_path (CrossModalAttention + TemporalTransformer, fusion_module.py:54-87 / temporal.py:79-111) fed with the
-    projected embeddings of a full forward reproduces that forward's fused tokens and CLS output bitwise, and matches the
-    oracle's `fused` / `cls` within the bf16-route budget."""
+    projected embeddings of a full forward reproduces that forward's fused tokens and CLS output, and matches the oracle's
+    `fused` / `cls` within the bf16-route budget."""
     model.compute_precision = "bf16"
     video, audio = lb.synthetic_windows(1, 3)
     inter = {}
     orc.forward(seed0_sd, video, audio, inter=inter)
     _, aux = model(video.cuda(), audio.cuda(), return_aux=True)
     fused, cls = model.fuse_tokens(aux["visual_tokens"], aux["audio_tokens"])
-    assert torch.equal(fused, aux["fused_tokens"])
-    assert torch.equal(cls, aux["cls_output"])
+    # (same kernels; the full forward takes the cross-attention in-projections from the GEMM it merged with the feature
+    #  projection — lsd_api.cu: pack_comb_proj —, the sub-path computes them from the embeddings: equal up to fp32 re-association
+    #  in front of the fp16 operand rounding)
+    assert _rel(fused, aux["fused_tokens"]) <= 1e-3
+    assert _rel(cls, aux["cls_output"]) <= 1e-3
     f2, c2 = model.fuse_tokens(inter["v_emb"].cuda(), inter["a_emb"].cuda())
     assert _rel(f2.cpu(), inter["fused"]) <= 2e-3
     assert _rel(c2.cpu(), inter["cls"]) <= 2e-3
