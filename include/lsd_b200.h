@@ -185,6 +185,13 @@ const char* lsd_stage_name(lsd_handle* h, int i);
  * normalisation reproduces the fp32 values bit for bit), 0 when some value did not (dst undefined: ship the fp32 values),
  * LSD_ERR_ARG on null pointers. */
 int lsd_host_pack_u8_exact(const float* src, uint8_t* dst, int64_t n, int threads);
+/* The same in two steps, for callers that enqueue GPU work for batch k while the host threads pack batch k+1: _begin starts the
+ * job on `threads` pool threads and returns LSD_OK at once (LSD_ERR_ARG: bad arguments, or a job is already in flight — one at a
+ * time per process); _end waits for it and returns 1 / 0 like lsd_host_pack_u8_exact.  src and dst must stay valid in between. */
+int lsd_host_pack_u8_begin(const float* src, uint8_t* dst, int64_t n, int threads);
+int lsd_host_pack_u8_end(void);
+/* Duration of the last finished pack job, first thread started .. last thread done, in milliseconds. */
+double lsd_host_pack_last_ms(void);
 
 /* CUDA-graph support.  lsd_forward may be captured into a CUDA graph (cudaStreamBeginCapture on `stream`; the internal side
  * streams join the capture through events) once a plain call with the same arguments has run: the first call of a shape

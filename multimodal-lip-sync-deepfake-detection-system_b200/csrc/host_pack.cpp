@@ -10,6 +10,7 @@
 #include <immintrin.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdint>
 #include <mutex>
@@ -99,8 +100,10 @@ class Pool {
  public:
   static Pool& get() { static Pool p; return p; }
 
-  bool run(const float* src, uint8_t* dst, int64_t n, int threads) {
-    std::lock_guard<std::mutex> serial(run_mu_);    // one job at a time
+  // Starts a job on `threads` pool threads and returns; the caller does not take part (it goes on enqueueing GPU work).
+  bool begin(const float* src, uint8_t* dst, int64_t n, int threads) {
+    std::unique_lock<std::mutex> lk(mu_);
+    if (busy_) return false;
     const int64_t items = (n + CHUNK - 1) / CHUNK;
     int want = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
     if (want < 1) want = 1;
@@ -109,22 +112,26 @@ class Pool {
     src_ = src; dst_ = dst; n_ = n; items_ = items;
     next_.store(0, std::memory_order_relaxed);
     ok_.store(true, std::memory_order_relaxed);
-    const int helpers = want - 1;
-    {
-      std::unique_lock<std::mutex> lk(mu_);
-      while ((int)workers_.size() < helpers) workers_.emplace_back([this, id = (int)workers_.size()] { worker(id); });
-      active_ = helpers;
-      pending_ = helpers;
-      ++gen_;
-    }
-    if (helpers > 0) cv_.notify_all();
-    work();
-    if (helpers > 0) {
-      std::unique_lock<std::mutex> lk(mu_);
-      done_cv_.wait(lk, [this] { return pending_ == 0; });
-    }
+    while ((int)workers_.size() < want) workers_.emplace_back([this, id = (int)workers_.size()] { worker(id); });
+    active_ = want;
+    pending_ = want;
+    busy_ = true;
+    t_begin_ = std::chrono::steady_clock::now();
+    ++gen_;
+    lk.unlock();
+    cv_.notify_all();
+    return true;
+  }
+  // Waits for the job started by begin(); true when every value qualified.
+  bool end() {
+    std::unique_lock<std::mutex> lk(mu_);
+    if (!busy_) return false;
+    done_cv_.wait(lk, [this] { return pending_ == 0; });
+    busy_ = false;
     return ok_.load(std::memory_order_relaxed);
   }
+  bool run(const float* src, uint8_t* dst, int64_t n, int threads) { return begin(src, dst, n, threads) && end(); }
+  double last_ms() { std::unique_lock<std::mutex> lk(mu_); return last_ms_; }
 
  private:
   Pool() = default;
@@ -157,17 +164,22 @@ class Pool {
       work();
       {
         std::unique_lock<std::mutex> lk(mu_);
-        if (--pending_ == 0) done_cv_.notify_one();
+        if (--pending_ == 0) {
+          last_ms_ = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin_).count();
+          done_cv_.notify_one();
+        }
       }
     }
   }
 
-  std::mutex run_mu_, mu_;
+  std::mutex mu_;
   std::condition_variable cv_, done_cv_;
   std::vector<std::thread> workers_;
   uint64_t gen_ = 0;
   int active_ = 0, pending_ = 0;
-  bool stop_ = false;
+  bool stop_ = false, busy_ = false;
+  std::chrono::steady_clock::time_point t_begin_;
+  double last_ms_ = 0.0;
   const float* src_ = nullptr;
   uint8_t* dst_ = nullptr;
   int64_t n_ = 0, items_ = 0;
@@ -180,5 +192,15 @@ class Pool {
 extern "C" int lsd_host_pack_u8_exact(const float* src, uint8_t* dst, int64_t n, int threads) {
   if (n < 0 || (n > 0 && (!src || !dst))) return LSD_ERR_ARG;
   if (n == 0) return 1;
-  return Pool::get().run(src, dst, n, threads) ? 1 : 0;
+  if (!Pool::get().begin(src, dst, n, threads)) return LSD_ERR_ARG;     // another job is in flight
+  return Pool::get().end() ? 1 : 0;
 }
+
+extern "C" int lsd_host_pack_u8_begin(const float* src, uint8_t* dst, int64_t n, int threads) {
+  if (n <= 0 || !src || !dst) return LSD_ERR_ARG;
+  return Pool::get().begin(src, dst, n, threads) ? LSD_OK : LSD_ERR_ARG;
+}
+
+extern "C" int lsd_host_pack_u8_end(void) { return Pool::get().end() ? 1 : 0; }
+
+extern "C" double lsd_host_pack_last_ms(void) { return Pool::get().last_ms(); }

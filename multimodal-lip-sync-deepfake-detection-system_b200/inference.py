@@ -230,68 +230,75 @@ class Predictor:
         L = _cabi.lib()
         state = {"mode": "fp32" if self.use_half_precision else self.host_transport}
 
-        def prepare(k, vh, ah):
-            """Host side of batch k (runs one batch ahead of the enqueue loop, on a helper thread: the pack releases the GIL)."""
+        def start(k, vh, ah):
+            """Host side of batch k, first half: starts the uint8 pack on the library's host threads (the call returns at once;
+            this thread goes on to enqueue batch k-1).  No Python helper thread: a second Python thread that makes CUDA calls was
+            measured to slow every later single-window call of the process by ~1 ms."""
             s = k % NS
             if self.use_half_precision:
                 vh, ah = vh.half(), ah.half()
-            transport = "fp32"
-            if state["mode"] != "fp32" and vh.dtype == torch.float32 and vh.device.type == "cpu" and vh.is_contiguous():
+            if state["mode"] != "fp32" and vh.dtype == torch.float32 and vh.device.type == "cpu" and vh.is_contiguous() and vh.numel() > 0:
                 if stage[s] is None or stage[s].shape != vh.shape:
                     stage[s] = torch.empty(vh.shape, dtype=torch.uint8).pin_memory()
                 elif k >= NS:
                     ready[s].synchronize()    # the H2D copy that last read this staging buffer (batch k - NS) has finished
-                t0 = time.perf_counter()
-                ok = L.lsd_host_pack_u8_exact(vh.data_ptr(), stage[s].data_ptr(), vh.numel(), self.host_pack_threads)
-                dt = time.perf_counter() - t0
-                if ok == 1:
-                    if state["mode"] == "auto" and k >= 1:
-                        # keep packing only when it beats the copy it saves (fp32 bytes at ~50 GB/s of PCIe gen5 x16); decided on
-                        # the second batch: the first one also pays for starting the pack threads
-                        state["mode"] = "u8" if dt < vh.numel() * 4 / 50e9 else "fp32"
-                    vh = stage[s]
-                    transport = "u8 (host-packed, exact)"
-                else:
-                    state["mode"] = "fp32"       # not k/255 data: stop checking for the rest of this call
-            return vh, ah, transport
+                if L.lsd_host_pack_u8_begin(vh.data_ptr(), stage[s].data_ptr(), vh.numel(), self.host_pack_threads) == _cabi.LSD_OK:
+                    return (k, vh, ah, s)
+            return (k, vh, ah, None)
+
+        def finish(st):
+            k, vh, ah, s = st
+            if s is None:
+                return vh, ah, "fp32"
+            ok = L.lsd_host_pack_u8_end()
+            if ok == 1:
+                if state["mode"] == "auto" and k >= 1:
+                    # keep packing only when it beats the copy it saves (fp32 bytes at ~50 GB/s of PCIe gen5 x16); decided on
+                    # the second batch: the first one also pays for starting the pack threads
+                    state["mode"] = "u8" if L.lsd_host_pack_last_ms() * 1e-3 < vh.numel() * 4 / 50e9 else "fp32"
+                return stage[s], ah, "u8 (host-packed, exact)"
+            state["mode"] = "fp32"               # not k/255 data: stop checking for the rest of this call
+            return vh, ah, "fp32"
 
         it = iter(batches)
         first = next(it, None)
         if first is None:
             return outs
-        if getattr(self, "_prep_pool", None) is None:
-            import concurrent.futures
-            self._prep_pool = concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix="lsd-pack")
-        fut = self._prep_pool.submit(prepare, 0, *first)
+        st = start(0, *first)
         k = 0
-        while fut is not None:
-            vh, ah, transport = fut.result()
-            nxt = next(it, None)
-            fut = self._prep_pool.submit(prepare, k + 1, *nxt) if nxt is not None else None
-            s = k % NS
-            self.last_transport = transport        # of the last batch shipped
-            self.last_h2d_bytes_per_batch = vh.numel() * vh.element_size() + ah.numel() * ah.element_size()
-            if slots[s] is None or slots[s][0].shape != vh.shape or slots[s][0].dtype != vh.dtype or slots[s][1].shape != ah.shape:
-                slots[s] = (torch.empty(vh.shape, dtype=vh.dtype, device=dev), torch.empty(ah.shape, dtype=ah.dtype, device=dev))
+        try:
+            while st is not None:
+                vh, ah, transport = finish(st)                                  # batch k is packed (or goes as it is)
+                nxt = next(it, None)
+                st = start(k + 1, *nxt) if nxt is not None else None            # batch k+1 is being packed while batch k is enqueued
+                s = k % NS
+                self.last_transport = transport        # of the last batch shipped
+                self.last_h2d_bytes_per_batch = vh.numel() * vh.element_size() + ah.numel() * ah.element_size()
+                if slots[s] is None or slots[s][0].shape != vh.shape or slots[s][0].dtype != vh.dtype or slots[s][1].shape != ah.shape:
+                    slots[s] = (torch.empty(vh.shape, dtype=vh.dtype, device=dev), torch.empty(ah.shape, dtype=ah.dtype, device=dev))
+                    free[s].record(comp)
+                with torch.cuda.stream(copy):
+                    copy.wait_event(free[s])          # the forward that last read this slot has finished
+                    slots[s][0].copy_(vh, non_blocking=True)
+                    slots[s][1].copy_(ah, non_blocking=True)
+                    ready[s].record(copy)
+                comp.wait_event(ready[s])
+                logits = m(slots[s][0], slots[s][1])
                 free[s].record(comp)
-            with torch.cuda.stream(copy):
-                copy.wait_event(free[s])          # the forward that last read this slot has finished
-                slots[s][0].copy_(vh, non_blocking=True)
-                slots[s][1].copy_(ah, non_blocking=True)
-                ready[s].record(copy)
-            comp.wait_event(ready[s])
-            logits = m(slots[s][0], slots[s][1])
-            free[s].record(comp)
-            # logits come back through one pinned block per 256 batches (a pinned allocation per step costs ~0.1-0.4 ms)
-            nb = int(logits.numel())
-            if pool is None or pool_off + nb > pool.numel():
-                pool = torch.empty(max(256 * nb, 4096), dtype=torch.float32, pin_memory=True)
-                pool_off = 0
-            host = pool[pool_off:pool_off + nb].view(logits.shape)
-            pool_off += nb
-            host.copy_(logits.float(), non_blocking=True)
-            outs.append(host)
-            k += 1
+                # logits come back through one pinned block per 256 batches (a pinned allocation per step costs ~0.1-0.4 ms)
+                nb = int(logits.numel())
+                if pool is None or pool_off + nb > pool.numel():
+                    pool = torch.empty(max(256 * nb, 4096), dtype=torch.float32, pin_memory=True)
+                    pool_off = 0
+                host = pool[pool_off:pool_off + nb].view(logits.shape)
+                pool_off += nb
+                host.copy_(logits.float(), non_blocking=True)
+                outs.append(host)
+                k += 1
+        except BaseException:
+            if st is not None and st[3] is not None:
+                L.lsd_host_pack_u8_end()         # never leave a pack job in flight behind an error
+            raise
         comp.synchronize()
         return outs
 

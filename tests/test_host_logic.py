@@ -192,3 +192,25 @@ def test_host_pack_u8_exact():
                 y[pos] = bad
                 assert L.lsd_host_pack_u8_exact(y.ctypes.data, d.ctypes.data, n, threads) == 0, (n, bad, pos)
     assert L.lsd_host_pack_u8_exact(None, None, 5, 1) == _cabi.LSD_ERR_ARG
+
+
+def test_host_pack_u8_begin_end():
+    """Two-step form of the pack (the scoring loop enqueues batch k while the host threads pack batch k+1): one job at a time,
+    same results as the blocking call."""
+    from lipsync_b200 import _cabi
+    L = _cabi.lib()
+    rng = np.random.default_rng(1)
+    n = 2 * (1 << 18) + 13
+    k = rng.integers(0, 256, n, dtype=np.uint8)
+    x = k.astype(np.float32) / 255.0
+    d = np.zeros(n, np.uint8)
+    assert L.lsd_host_pack_u8_end() == 0                                               # nothing in flight
+    assert L.lsd_host_pack_u8_begin(x.ctypes.data, d.ctypes.data, n, 3) == _cabi.LSD_OK
+    assert L.lsd_host_pack_u8_begin(x.ctypes.data, d.ctypes.data, n, 3) == _cabi.LSD_ERR_ARG      # busy
+    assert L.lsd_host_pack_u8_exact(x.ctypes.data, d.ctypes.data, n, 3) == _cabi.LSD_ERR_ARG      # busy
+    assert L.lsd_host_pack_u8_end() == 1 and np.array_equal(d, k)
+    assert L.lsd_host_pack_last_ms() > 0.0
+    x[n - 2] = 0.3
+    assert L.lsd_host_pack_u8_begin(x.ctypes.data, d.ctypes.data, n, 0) == _cabi.LSD_OK and L.lsd_host_pack_u8_end() == 0
+    assert L.lsd_host_pack_u8_begin(None, d.ctypes.data, n, 1) == _cabi.LSD_ERR_ARG
+    assert L.lsd_host_pack_u8_exact(x.ctypes.data, d.ctypes.data, n, 2) == 0           # the pool is free again
