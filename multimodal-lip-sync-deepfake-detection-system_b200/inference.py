@@ -102,13 +102,17 @@ class Predictor:
         #: how fp32 host windows cross PCIe in `score_batches`: "u8" packs windows whose pixels are exactly k/255 (what
         #: video.py:552-556 produces) to one byte per pixel on the host threads (`lsd_host_pack_u8_exact`: verified value by value,
         #: logits bit-identical), "fp32" copies them as they are, "auto" packs when the first batch qualifies and the host packs
-        #: faster than PCIe would move the fp32 bytes
+        #: clearly faster than PCIe would move the fp32 bytes (re-checked on every batch)
         if host_transport not in ("auto", "u8", "fp32"):
             raise ValueError(f"host_transport must be 'auto', 'u8' or 'fp32', got {host_transport!r}")
         self.host_transport = host_transport
         if host_pack_threads is None:
             local_ws = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
-            host_pack_threads = max(1, min(32, (os.cpu_count() or 1) // local_ws))
+            try:
+                cpus = len(os.sched_getaffinity(0))
+            except (AttributeError, OSError):
+                cpus = os.cpu_count() or 1
+            host_pack_threads = max(1, min(32, cpus // local_ws))
         self.host_pack_threads = int(host_pack_threads)
         self.last_transport = "fp32"
         self.last_h2d_bytes_per_batch = 0
@@ -252,10 +256,13 @@ class Predictor:
                 return vh, ah, "fp32"
             ok = L.lsd_host_pack_u8_end()
             if ok == 1:
-                if state["mode"] == "auto" and k >= 1:
-                    # keep packing only when it beats the copy it saves (fp32 bytes at ~50 GB/s of PCIe gen5 x16); decided on
-                    # the second batch: the first one also pays for starting the pack threads
-                    state["mode"] = "u8" if L.lsd_host_pack_last_ms() * 1e-3 < vh.numel() * 4 / 50e9 else "fp32"
+                if state["mode"] == "auto" and k >= 1 and L.lsd_host_pack_last_ms() * 1e-3 > 0.6 * vh.numel() * 4 / 50e9:
+                    # "auto" keeps packing only while the pack is clearly faster than the copy it saves (fp32 bytes at ~50 GB/s
+                    # of PCIe gen5 x16).  Measured: 16 host threads for one GPU pack a 64-window batch in 2.2 ms against 4.6 ms of
+                    # copy (14.9k -> 20.6k windows/s); 12 threads per GPU on a 2-GPU box need 4.1 ms and gain nothing — the pack
+                    # moves MORE host-DRAM bytes than the copy, so with every GPU of a box fed this way the fp32 copy wins.
+                    # (Checked from the second batch on: the first one also pays for starting the pack threads.)
+                    state["mode"] = "fp32"
                 return stage[s], ah, "u8 (host-packed, exact)"
             state["mode"] = "fp32"               # not k/255 data: stop checking for the rest of this call
             return vh, ah, "fp32"
