@@ -485,11 +485,18 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
   for (int gi = 0; gi < p.ngroups; ++gi)
     p.nst_tile += ((p.groups[gi].k16 + p.kpack - 1) / p.kpack) * (p.groups[gi].band_end - p.groups[gi].band_begin);
   const uint32_t prog_bytes = (uint32_t)p.nst_tile * (uint32_t)umma_conv_stage_desc_bytes();
-  const uint32_t budget = 211u * 1024u;   // one persistent CTA per SM owns the whole shared memory
+  uint32_t budget = 211u * 1024u;   // one persistent CTA per SM owns the whole shared memory
+  uint32_t pool_bytes = 0;
+  if (p.y_mode == UC_Y_POOL) {     // fused max-pool: output ring + per-position table behind the stage program
+    p.pool_ring = (uint32_t)(p.MT * 128 + 128);
+    uc_magic(p.pool_ring, p.pool_mR, p.pool_sR);
+    pool_bytes = (uint32_t)umma_conv_pool_smem_bytes(p.MT) + 128u;
+    budget -= pool_bytes;
+  }
   if (prog_bytes + 2 * stage > budget) return lsd_fail(c.h, LSD_ERR_UNSUPPORTED, "%s: stage program of %u bytes does not fit", name.c_str(), prog_bytes);
   int stages = (int)((budget - prog_bytes) / stage);
   stages = std::max(2, std::min(stages, 8));
-  if ((size_t)stages * stage + prog_bytes + 1024 > 223u * 1024u) return lsd_fail(c.h, LSD_ERR_UNSUPPORTED, "%s: stage of %u bytes does not fit", name.c_str(), stage);
+  if ((size_t)stages * stage + prog_bytes + pool_bytes + 1024 > 223u * 1024u) return lsd_fail(c.h, LSD_ERR_UNSUPPORTED, "%s: stage of %u bytes does not fit", name.c_str(), stage);
   p.stages = stages;
   double kflop = 0;
   for (const BGroup& G : L.groups) kflop += (double)G.taps_total * G.Cin;
@@ -533,7 +540,7 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
   // visual encoder by ~20 us per forward (CTAs delayed by the side stream's kernels take fewer tiles) but every one-tile
   // token-path launch pays the claim + counter re-arm (~1 us each), a net +2 % per step.
   static const bool dyn_tiles = getenv("LSD_UMMA_DYNAMIC") != nullptr;
-  if (dyn_tiles) {
+  if (dyn_tiles && p.y_mode != UC_Y_POOL) {   // (the fused max-pool walks contiguous position ranges)
     constexpr int kMaxLayers = 512;
     if (!c.h->tile_ctr_arena) {
       if (cudaMalloc(&c.h->tile_ctr_arena, kMaxLayers * 16 * sizeof(unsigned)) != cudaSuccess ||
@@ -1115,7 +1122,18 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   {
     int chunk = 0;
     if (const char* e = getenv("LSD_STEM_CHUNK")) chunk = atoi(e);
-    if (chunk <= 0 || chunk >= B) {
+    // LSD_STEM_POOL_FUSE=1: the max-pool rides in the stem's epilogue (UC_Y_POOL, umma_conv.cu): the 10 MB per window of stem
+    // output never leave the SM (DRAM traffic of stem + pool 1.6 GB -> 0.32 GB per 64 windows), same bits as the two-kernel path.
+    // Off by default: the stem is bound by the shared-memory read port (N = 64 MMAs), and the pooling pass reads its 3x3
+    // neighbourhoods through the same port — measured at B=64: stem 696 k -> 1 102 k cycles (708 k with the pooling reads skipped),
+    // which cancels the 0.21 ms of the separate max-pool kernel at burst clocks (2.880 vs 2.875 ms per step; +1.3 % under the
+    // power cap, where the saved DRAM traffic buys clock).
+    static const bool fuse_env = getenv("LSD_STEM_POOL_FUSE") && atoi(getenv("LSD_STEM_POOL_FUSE")) != 0;
+    const bool fuse_pool = fuse_env && !(xs.g.H & 1) && !(xs.g.W & 1) && x1.g.H * 2 == xs.g.H && x1.g.W * 2 == xs.g.W && 2 * xs.g.RW + 2 <= 128;
+    if (fuse_pool && (chunk <= 0 || chunk >= B)) {
+      RUN("visual_encoder.stem", a_.in = &xs; a_.og = xs.g; a_.act = ACT_RELU; a_.yp = &x1; a_.y_mode = UC_Y_POOL);
+      g_tl.mark(st, "M:stem");
+    } else if (chunk <= 0 || chunk >= B) {
       RUN("visual_encoder.stem", a_.in = &xs; a_.og = xs.g; a_.act = ACT_RELU; a_.yp = &so);
       g_tl.mark(st, "M:stem");
       launch_planar_maxpool(b.org(so), so.plane_stride, so.g, b.org(x1), x1.plane_stride, x1.g, 64, st);

@@ -103,8 +103,12 @@ constexpr int UC_PROD_WARPS = 4, UC_MMA_WARP0 = 4, UC_MMA_WARPS = 4, UC_EPI_WARP
 // GENERIC = false: lean epilogue of the convolution layers (bias, ReLU/none, optional bf16 residual, planar / parity-split bf16
 // store).  GENERIC = true: everything (fp32 rows in/out, split-bf16 hi/lo outputs and residuals, GELU) for the audio encoder and
 // the token-path GEMMs.  Two instantiations keep each one small enough for the instruction cache.
-template <bool GENERIC>
+// MODE 2 (y_mode == UC_Y_POOL): the lean epilogue with the 3x3 / stride-2 max-pool of the stem fused in.  Every CTA then owns one
+// contiguous range of positions (tiles pbase, pbase + S, ... instead of the grid-strided walk), so that the rows a pooled output
+// needs from the previous tile are still in this CTA's shared-memory ring; ranges start 2 rows + 2 positions early (halo, 0.3 %).
+template <int MODE>
 __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_constant__ UmmaConvP p) {
+  constexpr bool GENERIC = MODE == 1, POOL = MODE == 2;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2];
   __shared__ uint64_t tq_full[UC_TQ], tq_empty[UC_TQ];   // tile queue (dynamic tile scheduling, see below)
@@ -119,6 +123,18 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
   const int num_tiles = (int)((p.g.P_total + S - 1) / S);
   const int slice = blockIdx.y, ch0 = slice * p.Cout;
   const uint32_t buf_cols = (uint32_t)(p.MT * p.Cout);
+  // tile walk: tile_first, tile_first + tile_step, ... < tile_end; tile i covers positions pbase + i*S .. + S
+  int tile_first = blockIdx.x, tile_step = gridDim.x, tile_end = num_tiles;
+  int64_t pbase = 0, emit_lo = 0, emit_hi = 0;      // POOL: this CTA writes the pooled outputs whose last input position is in [emit_lo, emit_hi)
+  if constexpr (POOL) {
+    const int64_t per = (p.g.P_total + gridDim.x - 1) / gridDim.x;
+    emit_lo = min((int64_t)blockIdx.x * per, p.g.P_total);
+    emit_hi = min(emit_lo + per, p.g.P_total);
+    pbase = max((int64_t)0, emit_lo - (2 * p.g.RW + 2));
+    tile_first = 0; tile_step = 1;
+    tile_end = emit_hi > emit_lo ? (int)((emit_hi - pbase + S - 1) / S) : 0;
+  }
+  const int tile_start = tile_first < tile_end ? tile_first : -1;   // (-1: nothing to do for this CTA)
 
   const int n_issuers = p.issuers;          // MMA-issuing warps (M-tiles are independent accumulators), chosen on the host
   if (tid == 0) {
@@ -166,10 +182,10 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
     const uint64_t slice64 = (uint64_t)slice;
     int k = 0;                                              // global stage counter at the start of the tile
     int seq = 0;
-    for (int tile = blockIdx.x; tile >= 0; k += p.nst_tile) {
+    for (int tile = tile_start; tile >= 0; k += p.nst_tile) {
       unsigned claim = 0;
       if (dyn && warp == 0 && lane == 0) claim = atomicAdd(p.tile_ctr + slice, 1u);   // (consumed after this tile's stages are issued)
-      const uint64_t p0_bytes = (uint64_t)tile * (uint64_t)S * 16u;
+      const uint64_t p0_bytes = ((uint64_t)pbase + (uint64_t)tile * (uint64_t)S) * 16u;
       // first stage of this tile owned by this warp: si = (warp - k) mod 4
       for (int si = ((warp - k) % npw + npw) % npw; si < p.nst_tile; si += npw) {
         const int kk = k + si;
@@ -198,8 +214,8 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
       // next tile
       ++seq;
       if (!dyn) {
-        tile += gridDim.x;
-        if (tile >= num_tiles) tile = -1;
+        tile += tile_step;
+        if (tile >= tile_end) tile = -1;
       } else if (warp == 0) {
         int nt = 0;
         if (lane == 0) {
@@ -235,7 +251,7 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
     uint32_t ph = 0;
     // (the loop must stay provably warp-uniform for the descriptor arithmetic to live in uniform registers: "another tile?" is
     // taken from a warp vote, which ptxas treats as uniform, not from the per-thread value read from the queue)
-    for (int tile = blockIdx.x; tile < num_tiles; ++lt, tile = dyn ? (__any_sync(0xffffffffu, tq_read(lt) >= 0) ? 0 : num_tiles) : tile + (int)gridDim.x) {
+    for (int tile = tile_first; tile < tile_end; ++lt, tile = dyn ? (__any_sync(0xffffffffu, tq_read(lt) >= 0) ? 0 : tile_end) : tile + tile_step) {
       const int buf = p.nbuf == 2 ? (lt & 1) : 0;
       const uint32_t use = p.nbuf == 2 ? ((uint32_t)lt >> 1) : (uint32_t)lt;   // how many times this buffer was used before
       const uint32_t tb = tmem_base + (uint32_t)buf * buf_cols + (uint32_t)(mt_lo * p.Cout);
@@ -305,11 +321,15 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
     const float act_lo = p.act == ACT_RELU ? 0.0f : -INFINITY;   // ReLU as one FMNMX; GELU (token GEMMs only) branches once per chunk
     const int rowt = quarter * 32 + lane;
     int lt = 0;
-    for (int tile = blockIdx.x; tile >= 0; ++lt, tile = dyn ? tq_read(lt) : (tile + (int)gridDim.x < num_tiles ? tile + (int)gridDim.x : -1)) {
+    // POOL: ring of the last pool_ring positions ([slot][8 chunks of 8 channels], chunk index XOR-swizzled with the slot) and, per
+    // tile position, (pooled destination position or -1, ring slot)
+    uint8_t* const ring = smem + (size_t)p.stages * stage_bytes + (((size_t)p.nst_tile * sizeof(UcStageDesc) + 127) & ~(size_t)127);
+    int2* const pool_dst = reinterpret_cast<int2*>(ring + (size_t)p.pool_ring * 128u);
+    for (int tile = tile_start; tile >= 0; ++lt, tile = dyn ? tq_read(lt) : (tile + tile_step < tile_end ? tile + tile_step : -1)) {
       const int buf = p.nbuf == 2 ? (lt & 1) : 0;
       const uint32_t use = p.nbuf == 2 ? ((uint32_t)lt >> 1) : (uint32_t)lt;
       const uint32_t tb = tmem_base + (uint32_t)buf * buf_cols + ((uint32_t)(quarter * 32) << 16);
-      const int64_t P0 = (int64_t)tile * S;
+      const int64_t P0 = pbase + (int64_t)tile * S;
       mbar_wait(&tfull_bar[buf], use & 1u);
       tc_fence_after();
       if (dbg && warp == UC_EPI_WARP0 && lane == 0 && lt == 0) p.dbg[4] = clock64();   // first accumulator complete
@@ -319,7 +339,7 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
       // (the lean epilogue works in 32-column steps: with a single M-tile the columns are split only if both halves are whole
       // steps, otherwise the first warp of the quarter takes all of them)
       const bool split_c = !split_m && (GENERIC || (p.Cout & 63) == 0);
-      const int m_end = (!split_m && !split_c && half == 1) ? 0 : p.MT;
+      const int m_end = (!split_m && (!split_c || POOL) && half == 1) ? 0 : p.MT;   // (POOL: a thread takes all 64 columns of its position)
       for (int m = split_m ? half : 0; m < m_end; m += split_m ? 2 : 1) {
         const int64_t P = P0 + (int64_t)m * 128 + rowt;
         int n = 0, t = 0, h = 0, w = 0;
@@ -334,7 +354,35 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
         const bool store_planar = ((p.y_mode == UC_Y_PLAIN && inrange) || (p.y_mode >= UC_Y_PARITY && valid)) && !(p.skip & 4);   // (skip bit 2: timing experiment)
         // this warp's columns: [half*Cout/2, (half+1)*Cout/2), or all of them when the warps split the M-tiles
         const int cbeg = split_c ? half * (p.Cout >> 1) : 0, cend = split_c ? cbeg + (p.Cout >> 1) : p.Cout;
-        if constexpr (!GENERIC) {
+        if constexpr (POOL) {
+          // bias + ReLU + pad mask as in the lean path, but the packed words go to the ring; the thread also records whether its
+          // position is the last input (odd h, odd w) of a pooled output this CTA owns, and where that output lives
+          const uint32_t rel = (uint32_t)(P - pbase);
+          const uint32_t slot = rel - uc_div(rel, p.pool_mR, p.pool_sR) * p.pool_ring;
+          const bool emit = valid && (h & 1) && (w & 1) && P >= emit_lo && P < emit_hi;
+          pool_dst[m * 128 + rowt] = make_int2(emit ? (int)uc_flat(p.g2, n, t, h >> 1, w >> 1) : -1, (int)slot);
+          uint8_t* const rrow = ring + (size_t)slot * 128u;
+          const uint32_t sw = slot & 7u;
+          const uint32_t vmask = valid ? 0xffffffffu : 0u;
+          uint32_t ta = tb + (uint32_t)(m * p.Cout);
+#pragma unroll 1
+          for (int c = 0; c < 64; c += 32, ta += 32) {
+            float v[32];
+            float4 b[8];
+            tmem_ld32(ta, v);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) b[q] = *reinterpret_cast<const float4*>(&bias_s[c + 4 * q]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { v[4 * q] += b[q].x; v[4 * q + 1] += b[q].y; v[4 * q + 2] += b[q].z; v[4 * q + 3] += b[q].w; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 o = pack8_relu(v + 8 * q);
+              o.x &= vmask; o.y &= vmask; o.z &= vmask; o.w &= vmask;
+              if (!(p.skip & 32)) *reinterpret_cast<uint4*>(rrow + ((((uint32_t)(c >> 3) + q) ^ sw) << 4)) = o;   // (skip bits 4-6: timing experiments)
+            }
+          }
+        } else if constexpr (!GENERIC) {
           // lean path (Cout % 32 == 0, checked on the host): 32 columns per step.  One 32-column TMEM load, the bias (shared
           // memory) and the residual (global) are fetched before the single wait, the activation rides on the bf16 conversion
           // (cvt.rn.relu), pads are zeroed by a mask on the packed words.  ~110 instructions per step instead of ~450: the stem and
@@ -465,6 +513,34 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      if constexpr (POOL) {
+        // the tile's outputs are in the ring: pooled outputs whose last input lies in this tile are complete.  One thread per
+        // (position, 8-channel chunk), positions fastest (coalesced 16-byte stores into the destination plane).
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int etid = tid - UC_EPI_WARP0 * 32;
+        const int RW = p.g.RW, R = (int)p.pool_ring, sS = 31 - __clz(S);
+        for (int idx = etid; idx < ((p.skip & 16) ? 0 : S * 8); idx += UC_EPI_WARPS * 32) {
+          const int pos = idx & (S - 1), q = idx >> sS;
+          const int2 d = pool_dst[pos];
+          if (d.x < 0) continue;
+          __nv_bfloat162 mx[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) mx[e] = __floats2bfloat162_rn(0.0f, 0.0f);
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int bb = 0; bb < 3; ++bb) {
+              int sn = d.y - a * RW - bb;
+              sn += sn < 0 ? R : 0;
+              const uint4 r = *reinterpret_cast<const uint4*>(ring + (size_t)sn * 128u + (((uint32_t)q ^ ((uint32_t)sn & 7u)) << 4));
+              const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) mx[e] = __hmax2(mx[e], rb[e]);
+            }
+          *reinterpret_cast<uint4*>(p.y + (int64_t)((ch0 >> 3) + q) * p.y_plane_stride + (int64_t)d.x * 8) = *reinterpret_cast<const uint4*>(mx);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // the next tile's outputs overwrite the oldest ring slots
+      }
       if (dbg && warp == UC_EPI_WARP0 && lane == 0 && lt == 0) p.dbg[5] = clock64();   // first epilogue done
     }
   }
@@ -522,9 +598,13 @@ void umma_conv_build_program(const UmmaConvP& p, UcStageDesc* out) {
 }
 
 size_t umma_conv_smem_bytes(const UmmaConvP& p) {
-  return (size_t)p.stages * (p.a_stage_bytes + p.w_stage_bytes) + (size_t)p.nst_tile * sizeof(UcStageDesc) + 1024;
+  size_t b = (size_t)p.stages * (p.a_stage_bytes + p.w_stage_bytes) + (size_t)p.nst_tile * sizeof(UcStageDesc) + 1024;
+  if (p.y_mode == UC_Y_POOL) b += 128 + umma_conv_pool_smem_bytes(p.MT);
+  return b;
 }
 int umma_conv_stage_desc_bytes() { return (int)sizeof(UcStageDesc); }
+// UC_Y_POOL: ring of (tile + 128) positions x 64 channels bf16 + one int2 per tile position
+size_t umma_conv_pool_smem_bytes(int MT) { return (size_t)(MT * 128 + 128) * 128u + (size_t)MT * 128 * sizeof(int2); }
 
 static bool uc_is_generic(const UmmaConvP& p) {
   return p.y32 || p.res32 || p.ylo || p.res_lo || p.act == ACT_GELU || p.y_mode == UC_Y_NONE || (p.Cout & 31);   // (the lean epilogue works in 32-column steps)
@@ -534,14 +614,20 @@ const char* umma_conv_config_error(const UmmaConvP& p) {
   if (p.res && p.res32) return "bf16 and fp32 residuals are mutually exclusive";
   if (uc_is_generic(p) && (p.Cout & 63)) return "the generic epilogue needs a column slice that is a multiple of 64";
   if (p.MT / p.issuers > 4 || p.MT % p.issuers) return "unsupported M-tiles per issuing warp";
+  if (p.y_mode == UC_Y_POOL) {
+    if (uc_is_generic(p) || p.res || p.act != ACT_RELU || p.Cout != 64 || p.tile_ctr) return "fused max-pool needs the lean epilogue, ReLU, 64 columns and the static tile walk";
+    if ((p.g.H & 1) || (p.g.W & 1) || p.g2.H * 2 != p.g.H || p.g2.W * 2 != p.g.W || 2 * p.g.RW + 2 > 128) return "fused max-pool: unsupported geometry";
+    if (p.pool_ring != (uint32_t)(p.MT * 128 + 128) || (p.MT & (p.MT - 1))) return "fused max-pool: ring size mismatch";
+  }
   return nullptr;
 }
 
 // Function attributes are per device: lsd_create calls this once with the handle's device current.
 cudaError_t umma_conv_device_init() {
   // the opt-in limit (227 KB) covers static + dynamic shared memory; ~3.7 KB is static (barriers, bias, band / group tables)
-  cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024);
   if (e == cudaSuccess) e = video_rows_device_init();
   return e;
 }
@@ -555,8 +641,9 @@ void launch_umma_conv(const UmmaConvP& p, int n_slices, cudaStream_t s, int num_
   int gx = (budget + n_slices - 1) / n_slices;
   gx = gx < 1 ? 1 : (gx > tiles ? tiles : gx);
   const bool generic = uc_is_generic(p);
-  if (generic) umma_conv_kernel<true><<<dim3(gx, n_slices), UC_THREADS, umma_conv_smem_bytes(p), s>>>(p);
-  else umma_conv_kernel<false><<<dim3(gx, n_slices), UC_THREADS, umma_conv_smem_bytes(p), s>>>(p);
+  if (generic) umma_conv_kernel<1><<<dim3(gx, n_slices), UC_THREADS, umma_conv_smem_bytes(p), s>>>(p);
+  else if (p.y_mode == UC_Y_POOL) umma_conv_kernel<2><<<dim3(gx, n_slices), UC_THREADS, umma_conv_smem_bytes(p), s>>>(p);
+  else umma_conv_kernel<0><<<dim3(gx, n_slices), UC_THREADS, umma_conv_smem_bytes(p), s>>>(p);
   count_launch();
 }
 

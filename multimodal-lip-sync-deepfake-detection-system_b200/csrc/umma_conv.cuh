@@ -40,7 +40,10 @@ struct UcGroup {              // taps that share one K extent (main conv; option
 };
 
 // bf16 planar output modes (an fp32 row output can be produced in addition to, or instead of, the planar one)
-enum UcOut { UC_Y_NONE = 0, UC_Y_PLAIN = 1, UC_Y_PARITY = 2, UC_Y_PARITY_H = 3 };
+// UC_Y_POOL: the epilogue keeps the bf16 outputs of the last positions in a shared-memory ring and writes only the
+// 3x3 / stride-2 / pad-1 max-pool over (H, W) of them (plain layout, geometry g2 = (N, T, H/2, W/2)) — the stem + MaxPool3d of
+// visual_encoder.py:113-129 in one launch.  Needs ReLU (zero pads stand for the -inf padding), even H and W, 64 columns, one slice.
+enum UcOut { UC_Y_NONE = 0, UC_Y_PLAIN = 1, UC_Y_PARITY = 2, UC_Y_PARITY_H = 3, UC_Y_POOL = 4 };
 
 // Padded flat geometry:  P = ((n*TS + t + ot)*HP + h + oh)*RW + w + ow,  SL = HP*RW.
 // Standard activation geometry: one shared zero slab / row / column (TS=T+1, ot=1, HP=H+1, oh=1, RW=W+1, ow=1).
@@ -110,6 +113,10 @@ struct UmmaConvP {
   int skip;                   // debug (LSD_UMMA_SKIP): bit 0 = no A copies, bit 1 = no W copies — timing experiments only
   int kpack;                  // k16 chunks per pipeline stage (small-K-step layers amortise the mbarrier round trip)
   uint32_t a_stage_bytes, w_stage_bytes, tmem_cols;
+  // UC_Y_POOL: ring of pool_ring positions (tile positions + 128 >= tile + 2 rows + 2) behind the stage program; division by
+  // pool_ring as multiply + shift (uc_magic)
+  uint32_t pool_ring, pool_mR;
+  int pool_sR, pool_pad_;
   UcGeom g;                   // output geometry (== input geometry of every band)
   UcGeom g2;                  // UC_Y_PARITY*: destination geometry of each parity plane set
   UcGroup groups[UC_MAX_GROUPS];
@@ -118,6 +125,7 @@ struct UmmaConvP {
 
 size_t umma_conv_smem_bytes(const UmmaConvP& p);
 int umma_conv_stage_desc_bytes();
+size_t umma_conv_pool_smem_bytes(int MT);   // UC_Y_POOL: shared memory behind the stage program (ring + per-position table)
 // host: expand the stage program of a launch (same arithmetic the kernel used to do per stage)
 void umma_conv_build_program(const UmmaConvP& p, UcStageDesc* out);
 // nullptr if the kernel supports this parameter block, else the reason (callers turn it into an error code instead of launching)

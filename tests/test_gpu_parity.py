@@ -402,7 +402,8 @@ def test_bf16_odd_shapes_against_oracle(model, seed0_sd, shape):
 
 def test_scheduling_knobs_do_not_change_logits(model):
     """The scheduling variants of the tcgen05 kernel (dynamic tile claims, side-stream SM share, artifact branch placement, audio
-    fork point) only move work between CTAs and streams: logits must be bit-identical to the default schedule.  The knobs are read
+    fork point) only move work between CTAs and streams, and the stem's fused max-pool epilogue (LSD_STEM_POOL_FUSE=1) computes the same maxima
+    as the separate max-pool kernel: logits must be bit-identical to the default schedule.  The knobs are read
     from the environment inside the library (the first one once per process), so each variant runs in a fresh interpreter."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -414,7 +415,8 @@ def test_scheduling_knobs_do_not_change_logits(model):
             "print('DIGEST', hashlib.sha256(out.numpy().tobytes()).hexdigest())\n") % root
     digests = {}
     for name, env in {"default": {}, "dynamic_tiles": {"LSD_UMMA_DYNAMIC": "1"}, "side_all_sms": {"LSD_SIDE_CTAS": "148"},
-                      "hf_early": {"LSD_HF_EARLY": "1"}, "audio_after_rows": {"LSD_AUDIO_AFTER_ROWS": "1"}}.items():
+                      "hf_early": {"LSD_HF_EARLY": "1"}, "audio_after_rows": {"LSD_AUDIO_AFTER_ROWS": "1"},
+                      "stem_pool_fused": {"LSD_STEM_POOL_FUSE": "1"}}.items():
         r = subprocess.run([sys.executable, "-c", code], env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, (name, r.stderr[-2000:])
         digests[name] = [l for l in r.stdout.splitlines() if l.startswith("DIGEST")][-1]
