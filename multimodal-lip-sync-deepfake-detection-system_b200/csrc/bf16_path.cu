@@ -113,21 +113,26 @@ struct Packer {
   }
   // Toeplitz packing: K index k = c*16 + kc*8 + e  <->  pixel j = k/4 of the row window, channel k%4; kw = j - 1.
   // dup_lo: single-channel input stored as (hi, lo) bf16 pair in channels 0/1 -> both channels carry the channel-0 weight
-  void add_toeplitz(const std::string& name, const std::string& key, int kpix, int dw_units, bool dup_lo = false) {
+  // halves: the weights are packed as two slices of Cout/2 columns (CTA pairs stage one half each)
+  void add_toeplitz(const std::string& name, const std::string& key, int kpix, int dw_units, bool dup_lo = false, bool halves = false) {
     const ConvP& c = h->convs.at(key);
     BLayer L;
     L.Cout = c.Cout;
     L.ntile = c.Cout;
+    L.halves = halves;
     L.groups.push_back(make_group_toeplitz(c, kpix, dw_units));
     BGroup& g = L.groups[0];
     g.w_off = w.size();
     const float* W = &f32[c.w_off];
     const float* sc = c.has_scale ? &f32[c.scale_off] : nullptr;
+    const int nsl = halves ? 2 : 1, ncol = c.Cout / nsl;
+    g.slice_stride = (size_t)g.k16 * g.taps_total * ncol * 16;
+    for (int sl = 0; sl < nsl; ++sl)
     for (int ch = 0; ch < g.k16; ++ch)
       for (const BBand& b : g.bands)
         for (const BTap& t : b.taps)
           for (int kc = 0; kc < 2; ++kc)
-            for (int n = 0; n < c.Cout; ++n)
+            for (int n = sl * ncol; n < (sl + 1) * ncol; ++n)
               for (int e = 0; e < 8; ++e) {
                 const int k = ch * 16 + kc * 8 + e, j = k / 4, kw = j - 1;
                 int ci = k % 4;
@@ -146,13 +151,14 @@ struct Packer {
   }
   // split: every K group is issued three times (hi*hi, lo*hi, hi*lo), see add_split
   void add(const std::string& name, const std::string& key, int sh, int sw, const std::string& ds_key = "", int ntile = 0, bool split = false,
-           bool merge_kt = false) {
+           bool merge_kt = false, bool halves = false) {
     const ConvP& c = h->convs.at(key);
     BLayer L;
     L.Cout = c.Cout;
     L.ntile = ntile > 0 ? ntile : c.Cout;
+    L.halves = halves;   // (single-group layers only)
     L.groups.push_back(make_group(c, sh, sw, merge_kt));
-    pack_group(L.groups[0], c, L.ntile);
+    pack_group(L.groups[0], c, halves ? L.ntile / 2 : L.ntile);
     if (split) {
       BGroup g1 = L.groups[0]; g1.src = 2;
       BGroup g2 = make_group(c, sh, sw, merge_kt);
@@ -366,6 +372,8 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
   const int slices = L.Cout / L.ntile;
   p.act = a.act;
   p.g = og;
+  p.cta2 = L.halves ? 1 : 0;
+  if (a.y_mode == UC_Y_POOL && p.cta2) return lsd_fail(c.h, LSD_ERR_UNSUPPORTED, "%s: the fused max-pool does not run on CTA pairs (LSD_UMMA_CTA2=0)", name.c_str());
   if (a.yp) {
     p.y_mode = a.y_mode >= 0 ? a.y_mode : (a.yp->sets == 4 ? UC_Y_PARITY : UC_Y_PLAIN);
     p.y = c.org(*a.yp) + (int64_t)a.y_plane_off * a.yp->plane_stride;
@@ -463,7 +471,7 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
   }
   p.nbands = nb;
   // K chunks per stage: Toeplitz layers share one row region for all chunks; small planar stages are packed up to ~24 KB
-  const int w_chunk = max_taps * L.ntile * 32;
+  const int w_chunk = max_taps * (L.halves ? L.ntile / 2 : L.ntile) * 32;   // (CTA pairs stage half of the columns per CTA)
   if (any_toeplitz) p.kpack = min_k16;
   else {
     // A stage costs its issuing warp ~300-450 cycles of barrier / descriptor bookkeeping whatever it carries: with 24 KB stages the
@@ -540,7 +548,7 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
   // visual encoder by ~20 us per forward (CTAs delayed by the side stream's kernels take fewer tiles) but every one-tile
   // token-path launch pays the claim + counter re-arm (~1 us each), a net +2 % per step.
   static const bool dyn_tiles = getenv("LSD_UMMA_DYNAMIC") != nullptr;
-  if (dyn_tiles && p.y_mode != UC_Y_POOL) {   // (the fused max-pool walks contiguous position ranges)
+  if (dyn_tiles && p.y_mode != UC_Y_POOL && !p.cta2) {   // (the fused max-pool walks contiguous position ranges)
     constexpr int kMaxLayers = 512;
     if (!c.h->tile_ctr_arena) {
       if (cudaMalloc(&c.h->tile_ctr_arena, kMaxLayers * 16 * sizeof(unsigned)) != cudaSuccess ||
@@ -737,6 +745,7 @@ int pack_bf16_weights(lsd_handle* h, const std::vector<float>& f32_arena) {
   Packer P{h, f32_arena, {}, {}};
   h->blayers.clear();
   const int vstr[4] = {1, 2, 2, 2};
+  const bool cta2 = !(getenv("LSD_UMMA_CTA2") && atoi(getenv("LSD_UMMA_CTA2")) == 0);
   for (int l = 1; l <= 4; ++l) {
     const std::string p = "visual_encoder.layer" + std::to_string(l);
     const int s = vstr[l - 1];
@@ -744,11 +753,14 @@ int pack_bf16_weights(lsd_handle* h, const std::vector<float>& f32_arena) {
     // twice the MMA time per refill (4 M-tiles per weight stage instead of 2), measured 15-18 % faster than one 256-column slice.
     int nt = l >= 3 ? 128 : 0;
     if (const char* e = getenv(l == 3 ? "LSD_UMMA_NT3" : (l == 4 ? "LSD_UMMA_NT4" : "LSD_UMMA_NTX"))) nt = atoi(e);   // tuning knob
-    P.add(p + ".conv1", p + ".conv1", s, s, "", nt, false, /*merge_kt=*/l >= 2);   // 12x12 / 6x6 / 3x3 maps: one band per parity set
+    // CTA pairs (cta_group::2) for the Cout = 64 layers — stem and layer1, bound by the shared-memory read port — LSD_UMMA_CTA2=0 turns
+    // them off; the accumulation order is the same, so are the bits.
+    const bool pairs = cta2 && l == 1;
+    P.add(p + ".conv1", p + ".conv1", s, s, "", nt, false, /*merge_kt=*/l >= 2, pairs);   // 12x12 / 6x6 / 3x3 maps: one band per parity set
     P.ds_sh = 2; P.ds_sw = 2;
-    P.add(p + ".conv2", p + ".conv2", 1, 1, l == 1 ? "" : p + ".downsample", nt);
+    P.add(p + ".conv2", p + ".conv2", 1, 1, l == 1 ? "" : p + ".downsample", nt, false, false, pairs);
   }
-  P.add_toeplitz("visual_encoder.stem", "visual_encoder.stem", 8, 0);  // 7 taps in w -> 8-pixel window starting at 2*wo-4
+  P.add_toeplitz("visual_encoder.stem", "visual_encoder.stem", 8, 0, false, cta2);  // 7 taps in w -> 8-pixel window starting at 2*wo-4
   P.add_toeplitz("art.hf0", "art.hf0", 4, 1);                          // 3 taps in w -> 4-pixel window starting at 2*wo-2
   P.add("art.td0", "art.td0", 1, 1);
   P.add("art.td3", "art.td3", 1, 1);
@@ -1122,14 +1134,14 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   {
     int chunk = 0;
     if (const char* e = getenv("LSD_STEM_CHUNK")) chunk = atoi(e);
-    // LSD_STEM_POOL_FUSE=1: the max-pool rides in the stem's epilogue (UC_Y_POOL, umma_conv.cu): the 10 MB per window of stem
+    // LSD_STEM_POOL_FUSE=1 (with LSD_UMMA_CTA2=0: the fused epilogue is not built for CTA pairs): the max-pool rides in the stem's epilogue (UC_Y_POOL, umma_conv.cu): the 10 MB per window of stem
     // output never leave the SM (DRAM traffic of stem + pool 1.6 GB -> 0.32 GB per 64 windows), same bits as the two-kernel path.
     // Off by default: the stem is bound by the shared-memory read port (N = 64 MMAs), and the pooling pass reads its 3x3
     // neighbourhoods through the same port — measured at B=64: stem 696 k -> 1 102 k cycles (708 k with the pooling reads skipped),
     // which cancels the 0.21 ms of the separate max-pool kernel at burst clocks (2.880 vs 2.875 ms per step; +1.3 % under the
     // power cap, where the saved DRAM traffic buys clock).
     static const bool fuse_env = getenv("LSD_STEM_POOL_FUSE") && atoi(getenv("LSD_STEM_POOL_FUSE")) != 0;
-    const bool fuse_pool = fuse_env && !(xs.g.H & 1) && !(xs.g.W & 1) && x1.g.H * 2 == xs.g.H && x1.g.W * 2 == xs.g.W && 2 * xs.g.RW + 2 <= 128;
+    const bool fuse_pool = fuse_env && !h->blayers.at("visual_encoder.stem").halves && !(xs.g.H & 1) && !(xs.g.W & 1) && x1.g.H * 2 == xs.g.H && x1.g.W * 2 == xs.g.W && 2 * xs.g.RW + 2 <= 128;
     if (fuse_pool && (chunk <= 0 || chunk >= B)) {
       RUN("visual_encoder.stem", a_.in = &xs; a_.og = xs.g; a_.act = ACT_RELU; a_.yp = &x1; a_.y_mode = UC_Y_POOL);
       g_tl.mark(st, "M:stem");

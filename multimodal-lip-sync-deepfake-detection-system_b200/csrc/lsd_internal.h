@@ -24,7 +24,7 @@ struct Stage {            // named intermediate of the last forward (byte offset
 struct BTap { int orig, dt, dh, dw; };                       // original tap index + input shift (in the band's plane set)
 struct BBand { int set; std::vector<BTap> taps; };
 struct BGroup { std::vector<BBand> bands; int Cin = 0, taps_total = 0, k16 = 0, toeplitz = 0, src = 0; size_t w_off = 0, slice_stride = 0; };  // src: 0 main input, 1 downsample input, 2 low part of the main input  // w_off: bf16 elements into barena
-struct BLayer { std::vector<BGroup> groups; int Cout = 0, ntile = 0; size_t bias_off = 0; };            // bias_off: floats into bbias
+struct BLayer { std::vector<BGroup> groups; int Cout = 0, ntile = 0; size_t bias_off = 0; bool halves = false; };  // halves: weights packed as two ntile/2-column slices (CTA pairs)            // bias_off: floats into bbias
 
 struct Prof {             // CUDA-event brackets around the dominant kernel class (lsd_profile_*)
   int want = 0;           // 0 off, 1 fp32 conv kernel, 2 tcgen05 conv kernel

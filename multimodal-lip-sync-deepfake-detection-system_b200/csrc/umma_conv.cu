@@ -106,11 +106,18 @@ constexpr int UC_PROD_WARPS = 4, UC_MMA_WARP0 = 4, UC_MMA_WARPS = 4, UC_EPI_WARP
 // MODE 2 (y_mode == UC_Y_POOL): the lean epilogue with the 3x3 / stride-2 max-pool of the stem fused in.  Every CTA then owns one
 // contiguous range of positions (tiles pbase, pbase + S, ... instead of the grid-strided walk), so that the rows a pooled output
 // needs from the previous tile are still in this CTA's shared-memory ring; ranges start 2 rows + 2 positions early (halo, 0.3 %).
+#define UC_MMA(...) do { if constexpr (CTA2) mma2_bf16_ss_pred(__VA_ARGS__); else mma_bf16_ss_pred(__VA_ARGS__); } while (0)
+#define UC_COMMIT(...) do { if constexpr (CTA2) mma2_commit_pred(__VA_ARGS__); else mma_commit_pred(__VA_ARGS__); } while (0)
 template <int MODE>
 __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_constant__ UmmaConvP p) {
-  constexpr bool GENERIC = MODE == 1, POOL = MODE == 2;
+  // MODE 3 (p.cta2): the lean epilogue on CTA pairs (cluster of 2, tcgen05 cta_group::2).  The two CTAs of a pair take the tiles
+  // 2j and 2j+1 (own A rows, own accumulator, own epilogue) but each stages only HALF of the weight columns; the leader's MMA
+  // (M = 256) reads both halves.  A 64-column MMA then reads 4 KB of A + 1 KB of B from each SM's shared memory instead of 4 + 2:
+  // 40 instead of 48 cycles of the 128 B/cycle read port that bounds the Cout = 64 layers (stem, layer1).
+  constexpr bool GENERIC = MODE == 1, POOL = MODE == 2, CTA2 = MODE == 3;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2];
+  __shared__ uint64_t full2_bar[8], tempty2_bar[2];      // CTA2, leader's copies used: peer's stage landed / peer's epilogue drained
   __shared__ uint64_t tq_full[UC_TQ], tq_empty[UC_TQ];   // tile queue (dynamic tile scheduling, see below)
   __shared__ int tq_tile[UC_TQ];
   __shared__ uint32_t tmem_base_s;
@@ -121,7 +128,9 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
   const int S = p.MT * 128;
   const uint32_t stage_bytes = p.a_stage_bytes + p.w_stage_bytes;
   const int num_tiles = (int)((p.g.P_total + S - 1) / S);
+  const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
   const int slice = blockIdx.y, ch0 = slice * p.Cout;
+  const int bcols = CTA2 ? p.Cout >> 1 : p.Cout;         // weight columns in this CTA's shared memory
   const uint32_t buf_cols = (uint32_t)(p.MT * p.Cout);
   // tile walk: tile_first, tile_first + tile_step, ... < tile_end; tile i covers positions pbase + i*S .. + S
   int tile_first = blockIdx.x, tile_step = gridDim.x, tile_end = num_tiles;
@@ -134,17 +143,28 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
     tile_first = 0; tile_step = 1;
     tile_end = emit_hi > emit_lo ? (int)((emit_hi - pbase + S - 1) / S) : 0;
   }
+  if constexpr (CTA2) {   // the walk runs over tile PAIRS; this CTA's tile of pair j is 2j + rank (the last pair may repeat the last tile)
+    tile_first = blockIdx.x >> 1; tile_step = gridDim.x >> 1; tile_end = (num_tiles + 1) >> 1;
+  }
+  auto tile_p0 = [&](int tile) -> int64_t {
+    if constexpr (CTA2) return (int64_t)min(2 * tile + (int)cta_rank, num_tiles - 1) * S;
+    return pbase + (int64_t)tile * S;
+  };
   const int tile_start = tile_first < tile_end ? tile_first : -1;   // (-1: nothing to do for this CTA)
 
   const int n_issuers = p.issuers;          // MMA-issuing warps (M-tiles are independent accumulators), chosen on the host
   if (tid == 0) {
     for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], n_issuers); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], n_issuers); mbar_init(&tempty_bar[i], UC_EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], n_issuers); mbar_init(&tempty_bar[i], UC_EPI_WARPS); mbar_init(&tempty2_bar[i], UC_EPI_WARPS); }
+    for (int i = 0; i < p.stages; ++i) mbar_init(&full2_bar[i], 1);
     // queue readers: the producer warps other than warp 0, the MMA issuers, the epilogue warps
     for (int i = 0; i < UC_TQ; ++i) { mbar_init(&tq_full[i], 1); mbar_init(&tq_empty[i], (uint32_t)(min(UC_PROD_WARPS, p.stages) - 1 + n_issuers + UC_EPI_WARPS)); }
     fence_barrier_init();
   }
-  if (warp == UC_EPI_WARP0) { tmem_alloc(&tmem_base_s, p.tmem_cols); tmem_relinquish(); }
+  if (warp == UC_EPI_WARP0) {
+    if constexpr (CTA2) { tmem_alloc2(&tmem_base_s, p.tmem_cols); tmem_relinquish2(); }
+    else { tmem_alloc(&tmem_base_s, p.tmem_cols); tmem_relinquish(); }
+  }
   for (int i = tid; i < p.Cout; i += UC_THREADS) bias_s[i] = p.bias ? p.bias[ch0 + i] : 0.0f;
   // stage program -> shared memory (one 16-byte piece per thread)
   UcStageDesc* prog = reinterpret_cast<UcStageDesc*>(smem + (size_t)p.stages * stage_bytes);
@@ -154,7 +174,8 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
     for (int i = tid; i < p.nst_tile * 4; i += UC_THREADS) pdst[i] = psrc[i];
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();   // (the peer's barriers are initialised before anything arrives on them remotely)
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   if (dbg && tid == 0) p.dbg[1] = clock64();   // prologue done
@@ -179,13 +200,13 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
     const int npw = min(UC_PROD_WARPS, p.stages);
     if (warp >= npw) goto done;
     const uint32_t smem_base = smem_u32(smem);
-    const uint64_t slice64 = (uint64_t)slice;
+    const uint64_t slice64 = CTA2 ? (uint64_t)cta_rank : (uint64_t)slice;   // (CTA2: the packed weights hold the two column halves as slices)
     int k = 0;                                              // global stage counter at the start of the tile
     int seq = 0;
     for (int tile = tile_start; tile >= 0; k += p.nst_tile) {
       unsigned claim = 0;
       if (dyn && warp == 0 && lane == 0) claim = atomicAdd(p.tile_ctr + slice, 1u);   // (consumed after this tile's stages are issued)
-      const uint64_t p0_bytes = ((uint64_t)pbase + (uint64_t)tile * (uint64_t)S) * 16u;
+      const uint64_t p0_bytes = (uint64_t)tile_p0(tile) * 16u;
       // first stage of this tile owned by this warp: si = (warp - k) mod 4
       for (int si = ((warp - k) % npw + npw) % npw; si < p.nst_tile; si += npw) {
         const int kk = k + si;
@@ -234,6 +255,22 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
   } else if (warp < UC_MMA_WARP0 + UC_MMA_WARPS) {
     // ------------------------------------------------ MMA issuers (whole warp runs the loop; one elected lane issues)
     if (warp - UC_MMA_WARP0 >= n_issuers) goto done;
+    if constexpr (CTA2) {
+      if (cta_rank != 0) {
+        // peer CTA: no MMAs are issued here.  One warp relays "this CTA's stage has landed" to the leader's full2 barrier.
+        if (warp != UC_MMA_WARP0) goto done;
+        int stage = 0;
+        uint32_t ph = 0;
+        for (int tile = tile_first; tile < tile_end; tile += tile_step)
+          for (int si = 0; si < p.nst_tile; ++si) {
+            mbar_wait(&full_bar[stage], ph);
+            if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&full2_bar[stage]), 0u));
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; ph ^= 1u; }
+          }
+        goto done;
+      }
+    }
     // (the warp index as a value ptxas knows to be warp-uniform: everything derived from it — TMEM column, M-tile offset of the A
     // descriptor — then lives in uniform registers; derived from threadIdx.x it cost an R2UR.BROADCAST per operand per MMA)
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
@@ -241,11 +278,11 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
     const int mt_lo = (warp_u - UC_MMA_WARP0) * mt_n;
     // One thread feeds the tensor core: keep the per-instruction work to a few 32-bit adds.  A descriptor is
     // (constant high part) | (start address >> 4); tap / M-tile / K-chunk offsets are added in 16-byte units.
-    const uint32_t idesc = idesc_bf16(128, p.Cout);
+    const uint32_t idesc = idesc_bf16(CTA2 ? 256 : 128, p.Cout);
     const uint32_t smem_base = smem_u32(smem);
     const uint64_t desc_hi64 = ((uint64_t)8 << 32) | ((uint64_t)1 << 46);          // high word: SBO = 128 B, descriptor version 1
-    const uint32_t b_lbo = (uint32_t)p.Cout << 16;                                 // LBO(B) = Cout * 16 B
-    const uint32_t tap_w = (uint32_t)p.Cout * 2u;                                  // Cout * 32 B per tap, in 16 B units
+    const uint32_t b_lbo = (uint32_t)bcols << 16;                                  // LBO(B) = (staged) Cout * 16 B
+    const uint32_t tap_w = (uint32_t)bcols * 2u;                                   // Cout * 32 B per tap, in 16 B units
     const uint32_t leader = elect_one() ? 1u : 0u;                                 // the lane that issues (fixed for the whole kernel)
     int stage = 0, lt = 0, dbg_it = 0;
     uint32_t ph = 0;
@@ -256,6 +293,7 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
       const uint32_t use = p.nbuf == 2 ? ((uint32_t)lt >> 1) : (uint32_t)lt;   // how many times this buffer was used before
       const uint32_t tb = tmem_base + (uint32_t)buf * buf_cols + (uint32_t)(mt_lo * p.Cout);
       mbar_wait(&tempty_bar[buf], (use & 1u) ^ 1u);   // epilogue has drained this accumulator buffer
+      if constexpr (CTA2) mbar_wait_cluster(&tempty2_bar[buf], (use & 1u) ^ 1u);   // ... and so has the peer's
       tc_fence_after();
       uint32_t acc = 0;
       // The loop nest reads the parameter block with warp-uniform indices (uniform constant loads) and runs on every lane;
@@ -273,6 +311,7 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
             const uint32_t a_chunk = bd.toeplitz ? 2u : 2u * unitsA;
             const uint32_t w_chunk = (uint32_t)ntaps * tap_w;
             mbar_wait(&full_bar[stage], ph);
+            if constexpr (CTA2) mbar_wait_cluster(&full2_bar[stage], ph);   // the peer's A rows and weight half have landed too
             tc_fence_after();
             if (dbg && warp == UC_MMA_WARP0 && lane == 0 && acc == 0 && lt == 0) p.dbg[2] = clock64();   // first stage landed
             if (dbg && warp == UC_MMA_WARP0 && lane == 0 && lt == 0 && dbg_it < 24) p.dbg[8 + dbg_it++] = clock64();
@@ -284,8 +323,8 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
 #pragma unroll 1
               for (int j = 0; j < nc; ++j, at += a_chunk, wj += w_chunk) {
                 const uint64_t da = desc_hi64 | (uint64_t)at, db = desc_hi64 | (uint64_t)wj;
-                mma_bf16_ss_pred(tb, da, db, idesc, acc, leader);
-                if (mt_n > 1) mma_bf16_ss_pred(tb + (uint32_t)p.Cout, da + 128u, db, idesc, acc, leader);
+                UC_MMA(tb, da, db, idesc, acc, leader);
+                if (mt_n > 1) UC_MMA(tb + (uint32_t)p.Cout, da + 128u, db, idesc, acc, leader);
                 acc = 1u;
               }
             } else
@@ -296,22 +335,22 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
               for (int tp = 0; tp < ntaps; ++tp) {   // (not unrolled: the kernel must stay inside the instruction cache)
                 const uint32_t at = aj + (uint32_t)bd.rel[tp];
                 const uint64_t da = desc_hi64 | (uint64_t)at, db = desc_hi64 | (uint64_t)wj;
-                mma_bf16_ss_pred(tb, da, db, idesc, acc, leader);
-                if (mt_n > 1) mma_bf16_ss_pred(tb + (uint32_t)p.Cout, da + 128u, db, idesc, acc, leader);
+                UC_MMA(tb, da, db, idesc, acc, leader);
+                if (mt_n > 1) UC_MMA(tb + (uint32_t)p.Cout, da + 128u, db, idesc, acc, leader);
                 if (mt_n > 2) {
-                  mma_bf16_ss_pred(tb + 2u * (uint32_t)p.Cout, da + 256u, db, idesc, acc, leader);
-                  mma_bf16_ss_pred(tb + 3u * (uint32_t)p.Cout, da + 384u, db, idesc, acc, leader);
+                  UC_MMA(tb + 2u * (uint32_t)p.Cout, da + 256u, db, idesc, acc, leader);
+                  UC_MMA(tb + 3u * (uint32_t)p.Cout, da + 384u, db, idesc, acc, leader);
                 }
                 acc = 1u;
                 wj += tap_w;
               }
             }
-            mma_commit_pred(&empty_bar[stage], leader);  // frees the stage once the MMAs that read it have completed
+            UC_COMMIT(&empty_bar[stage], leader);  // frees the stage once the MMAs that read it have completed
             if (++stage == p.stages) { stage = 0; ph ^= 1u; }
           }
         }
       }
-      mma_commit_pred(&tfull_bar[buf], leader);   // accumulator of this tile complete -> epilogue
+      UC_COMMIT(&tfull_bar[buf], leader);   // accumulator of this tile complete -> epilogue
       if (dbg && warp == UC_MMA_WARP0 && lane == 0 && lt == 0) p.dbg[3] = clock64();   // all MMAs of the first tile issued
     }
   } else {
@@ -329,7 +368,7 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
       const int buf = p.nbuf == 2 ? (lt & 1) : 0;
       const uint32_t use = p.nbuf == 2 ? ((uint32_t)lt >> 1) : (uint32_t)lt;
       const uint32_t tb = tmem_base + (uint32_t)buf * buf_cols + ((uint32_t)(quarter * 32) << 16);
-      const int64_t P0 = pbase + (int64_t)tile * S;
+      const int64_t P0 = tile_p0(tile);
       mbar_wait(&tfull_bar[buf], use & 1u);
       tc_fence_after();
       if (dbg && warp == UC_EPI_WARP0 && lane == 0 && lt == 0) p.dbg[4] = clock64();   // first accumulator complete
@@ -512,7 +551,10 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
       // all TMEM reads of this warp are complete (wait::ld above): hand the buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      if (lane == 0) {
+        if (CTA2 && cta_rank != 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty2_bar[buf]), 0u));
+        else mbar_arrive(&tempty_bar[buf]);
+      }
       if constexpr (POOL) {
         // the tile's outputs are in the ring: pooled outputs whose last input lies in this tile are complete.  One thread per
         // (position, 8-channel chunk), positions fastest (coalesced 16-byte stores into the destination plane).
@@ -546,8 +588,12 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
   }
 done:
   tc_fence_before();
-  __syncthreads();
-  if (warp == UC_EPI_WARP0) tmem_dealloc(tmem_base, p.tmem_cols);
+  if constexpr (CTA2) cluster_sync_all();   // (both CTAs are done with the pair's tensor memory and barriers)
+  else __syncthreads();
+  if (warp == UC_EPI_WARP0) {
+    if constexpr (CTA2) tmem_dealloc2(tmem_base, p.tmem_cols);
+    else tmem_dealloc(tmem_base, p.tmem_cols);
+  }
   if (dyn && tid == 0) {
     // every claim of this CTA has completed (its queue saw the end marker): the last CTA of the launch re-arms the counters
     __threadfence();
@@ -563,6 +609,7 @@ done:
 
 void umma_conv_build_program(const UmmaConvP& p, UcStageDesc* out) {
   const int S = p.MT * 128;
+  const int bcols = p.cta2 ? p.Cout / 2 : p.Cout;   // weight columns one CTA stages
   int s = 0;
   for (int gi = 0; gi < p.ngroups; ++gi) {
     const UcGroup& g = p.groups[gi];
@@ -571,7 +618,7 @@ void umma_conv_build_program(const UmmaConvP& p, UcStageDesc* out) {
       for (int b = g.band_begin; b < g.band_end; ++b, ++s) {
         const UcBand& bd = p.bands[b];
         UcStageDesc d;
-        const uint32_t bytesW = (uint32_t)bd.ntaps * (uint32_t)p.Cout * 32u;
+        const uint32_t bytesW = (uint32_t)bd.ntaps * (uint32_t)bcols * 32u;
         d.bytesA = bd.toeplitz ? (uint32_t)(S + bd.len_extra + 1 + 2 * (nc - 1)) * 16u : (uint32_t)(S + bd.len_extra) * 16u;
         uint32_t n_a = bd.toeplitz ? 1u : 2u * (uint32_t)nc;   // Toeplitz: the K chunks are 32-byte shifts of one row region
         // single-band groups (Linear layers): the weights of consecutive K chunks are contiguous -> one copy
@@ -587,9 +634,9 @@ void umma_conv_build_program(const UmmaConvP& p, UcStageDesc* out) {
         d.chunk_stride_b = (uint64_t)bd.chunk_stride * 2u;
         d.plane_stride_b = (uint64_t)bd.plane_stride * 2u;
         // weight piece j of the stage is the packed block [chunk c0 + j][taps of this band]: pieces are taps_total * Cout * 32 B apart
-        d.w_src = reinterpret_cast<uint64_t>(p.w + g.w_off + ((int64_t)c0 * g.taps_total + bd.tap_begin) * (int64_t)p.Cout * 16);
+        d.w_src = reinterpret_cast<uint64_t>(p.w + g.w_off + ((int64_t)c0 * g.taps_total + bd.tap_begin) * (int64_t)bcols * 16);
         d.w_slice_stride_b = (uint64_t)g.slice_stride * 2u;
-        d.w_src_step = (uint32_t)g.taps_total * (uint32_t)p.Cout * 32u;
+        d.w_src_step = (uint32_t)g.taps_total * (uint32_t)bcols * 32u;
         d.counts = n_a | (n_w << 8) | ((uint32_t)b << 16) | ((uint32_t)nc << 24);
         out[s] = d;
       }
@@ -614,6 +661,7 @@ const char* umma_conv_config_error(const UmmaConvP& p) {
   if (p.res && p.res32) return "bf16 and fp32 residuals are mutually exclusive";
   if (uc_is_generic(p) && (p.Cout & 63)) return "the generic epilogue needs a column slice that is a multiple of 64";
   if (p.MT / p.issuers > 4 || p.MT % p.issuers) return "unsupported M-tiles per issuing warp";
+  if (p.cta2 && (uc_is_generic(p) || p.y_mode == UC_Y_POOL || (p.Cout & 31) || p.tile_ctr)) return "CTA pairs need the lean epilogue, a multiple of 32 columns and the static tile walk";
   if (p.y_mode == UC_Y_POOL) {
     if (uc_is_generic(p) || p.res || p.act != ACT_RELU || p.Cout != 64 || p.tile_ctr) return "fused max-pool needs the lean epilogue, ReLU, 64 columns and the static tile walk";
     if ((p.g.H & 1) || (p.g.W & 1) || p.g2.H * 2 != p.g.H || p.g2.W * 2 != p.g.W || 2 * p.g.RW + 2 > 128) return "fused max-pool: unsupported geometry";
@@ -628,6 +676,7 @@ cudaError_t umma_conv_device_init() {
   cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_conv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024);
   if (e == cudaSuccess) e = video_rows_device_init();
   return e;
 }
@@ -641,6 +690,25 @@ void launch_umma_conv(const UmmaConvP& p, int n_slices, cudaStream_t s, int num_
   int gx = (budget + n_slices - 1) / n_slices;
   gx = gx < 1 ? 1 : (gx > tiles ? tiles : gx);
   const bool generic = uc_is_generic(p);
+  if (p.cta2) {
+    // CTA pairs: an even grid of clusters of 2 (one pair per TPC), each pair walking tile pairs
+    if (n_slices != 1) { fprintf(stderr, "umma_conv: CTA pairs take one column slice\n"); abort(); }
+    const int pairs = (tiles + 1) / 2;
+    int gp = budget / 2;
+    gp = gp < 1 ? 1 : (gp > pairs ? pairs : gp);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * gp, 1, 1);
+    cfg.blockDim = dim3(UC_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = umma_conv_smem_bytes(p);
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, umma_conv_kernel<3>, p);
+    count_launch();
+    return;
+  }
   if (generic) umma_conv_kernel<1><<<dim3(gx, n_slices), UC_THREADS, umma_conv_smem_bytes(p), s>>>(p);
   else if (p.y_mode == UC_Y_POOL) umma_conv_kernel<2><<<dim3(gx, n_slices), UC_THREADS, umma_conv_smem_bytes(p), s>>>(p);
   else umma_conv_kernel<0><<<dim3(gx, n_slices), UC_THREADS, umma_conv_smem_bytes(p), s>>>(p);

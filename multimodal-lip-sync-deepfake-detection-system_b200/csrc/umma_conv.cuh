@@ -116,7 +116,8 @@ struct UmmaConvP {
   // UC_Y_POOL: ring of pool_ring positions (tile positions + 128 >= tile + 2 rows + 2) behind the stage program; division by
   // pool_ring as multiply + shift (uc_magic)
   uint32_t pool_ring, pool_mR;
-  int pool_sR, pool_pad_;
+  int pool_sR;
+  int cta2;                   // 1: CTA pairs (cluster of 2, tcgen05 cta_group::2): the packed weights hold two column halves as slices
   UcGeom g;                   // output geometry (== input geometry of every band)
   UcGeom g2;                  // UC_Y_PARITY*: destination geometry of each parity plane set
   UcGroup groups[UC_MAX_GROUPS];

@@ -1,0 +1,14 @@
+#!/bin/bash
+# CTA pairs (cta_group::2) for the Cout=64 layers: bitwise check against single-CTA MMAs, then timing
+cat > /tmp/dig.py <<'PY'
+import sys; sys.path.insert(0, '/root/repo')
+import torch, hashlib, lipsync_b200 as lb
+m = lb.LipSyncModel(); m.load_state_dict(lb.make_synthetic_state_dict(0)); m.to('cuda:0').eval(); m.compute_precision = 'bf16'
+v, a = lb.synthetic_windows(33, 5)
+out = m(v.cuda(), a.cuda()).float().cpu()
+torch.cuda.synchronize()
+print('DIGEST', hashlib.sha256(out.numpy().tobytes()).hexdigest()[:16], out.tolist())
+PY
+echo "--- cta2 off"; LSD_UMMA_CTA2=0 timeout 120 python /tmp/dig.py 2>&1 | tail -2
+echo "--- cta2 on";  timeout 120 python /tmp/dig.py 2>&1 | tail -4
+echo "rc=$?"
