@@ -494,13 +494,12 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
     p.nst_tile += ((p.groups[gi].k16 + p.kpack - 1) / p.kpack) * (p.groups[gi].band_end - p.groups[gi].band_begin);
   const uint32_t prog_bytes = (uint32_t)p.nst_tile * (uint32_t)umma_conv_stage_desc_bytes();
   uint32_t budget = 211u * 1024u;   // one persistent CTA per SM owns the whole shared memory
-  uint32_t pool_bytes = 0;
   if (p.y_mode == UC_Y_POOL) {     // fused max-pool: output ring + per-position table behind the stage program
     p.pool_ring = (uint32_t)(p.MT * 128 + 128);
     uc_magic(p.pool_ring, p.pool_mR, p.pool_sR);
-    pool_bytes = (uint32_t)umma_conv_pool_smem_bytes(p.MT) + 128u;
-    budget -= pool_bytes;
   }
+  const uint32_t pool_bytes = (uint32_t)umma_conv_extra_smem_bytes(p);   // bias operand tiles of the lean epilogue (+ the max-pool ring)
+  budget -= pool_bytes;
   if (prog_bytes + 2 * stage > budget) return lsd_fail(c.h, LSD_ERR_UNSUPPORTED, "%s: stage program of %u bytes does not fit", name.c_str(), prog_bytes);
   int stages = (int)((budget - prog_bytes) / stage);
   stages = std::max(2, std::min(stages, 8));

@@ -166,6 +166,30 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
     else { tmem_alloc(&tmem_base_s, p.tmem_cols); tmem_relinquish(); }
   }
   for (int i = tid; i < p.Cout; i += UC_THREADS) bias_s[i] = p.bias ? p.bias[ch0 + i] : 0.0f;
+  // Lean instantiations: the bias enters the accumulator through ONE extra MMA per M-tile instead of 8 shared-memory loads + 32
+  // additions per epilogue step (the epilogue warps, not the tensor pipe, bounded the stem and the residual convolutions once the
+  // CTA pairs had shortened the MMAs).  A = 128 rows x (1, 1, 1, 0, ...) (both K halves alias the same 2 KB: LBO = 0),
+  // B = per column (hi, mid, lo, 0, ...) with b = hi + mid + lo in bf16 parts (24 mantissa bits: exact), second K half zero.
+  uint8_t* const bias_a = smem + (size_t)p.stages * stage_bytes + (((size_t)p.nst_tile * sizeof(UcStageDesc) + 127) & ~(size_t)127);
+  uint8_t* const bias_b = bias_a + 2048;
+  uint8_t* const lean_end = bias_b + (size_t)bcols * 32u;
+  if constexpr (!GENERIC) {
+    for (int i = tid; i < 128; i += UC_THREADS) reinterpret_cast<uint4*>(bias_a)[i] = make_uint4(0x3F803F80u, 0x00003F80u, 0u, 0u);
+    for (int i = tid; i < 2 * bcols; i += UC_THREADS) {
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if (i < bcols && p.bias) {
+        const float b = p.bias[ch0 + (int)cta_rank * bcols + i];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+        const float r1 = b - __bfloat162float(hi);
+        const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+        o.x = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(mid) << 16);
+        o.y = (uint32_t)__bfloat16_as_ushort(lo);
+      }
+      reinterpret_cast<uint4*>(bias_b)[i] = o;
+    }
+    fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's operand reads
+  }
   // stage program -> shared memory (one 16-byte piece per thread)
   UcStageDesc* prog = reinterpret_cast<UcStageDesc*>(smem + (size_t)p.stages * stage_bytes);
   {
@@ -296,6 +320,18 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
       if constexpr (CTA2) mbar_wait_cluster(&tempty2_bar[buf], (use & 1u) ^ 1u);   // ... and so has the peer's
       tc_fence_after();
       uint32_t acc = 0;
+      if constexpr (!GENERIC) {
+        // accumulators start as the bias (overwrite: accumulate = 0)
+        const uint64_t da = desc_hi64 | (uint64_t)(smem_u32(bias_a) >> 4);                   // LBO = 0
+        const uint64_t db = desc_hi64 | (uint64_t)((smem_u32(bias_b) >> 4) | b_lbo);
+        UC_MMA(tb, da, db, idesc, 0u, leader);
+        if (mt_n > 1) UC_MMA(tb + (uint32_t)p.Cout, da, db, idesc, 0u, leader);
+        if (mt_n > 2) {
+          UC_MMA(tb + 2u * (uint32_t)p.Cout, da, db, idesc, 0u, leader);
+          UC_MMA(tb + 3u * (uint32_t)p.Cout, da, db, idesc, 0u, leader);
+        }
+        acc = 1u;
+      }
       // The loop nest reads the parameter block with warp-uniform indices (uniform constant loads) and runs on every lane;
       // only the MMA / commit instructions are predicated on the elected lane, so the descriptor arithmetic stays in uniform
       // registers instead of being moved there (R2UR) for every instruction.
@@ -362,7 +398,7 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
     int lt = 0;
     // POOL: ring of the last pool_ring positions ([slot][8 chunks of 8 channels], chunk index XOR-swizzled with the slot) and, per
     // tile position, (pooled destination position or -1, ring slot)
-    uint8_t* const ring = smem + (size_t)p.stages * stage_bytes + (((size_t)p.nst_tile * sizeof(UcStageDesc) + 127) & ~(size_t)127);
+    uint8_t* const ring = lean_end;
     int2* const pool_dst = reinterpret_cast<int2*>(ring + (size_t)p.pool_ring * 128u);
     for (int tile = tile_start; tile >= 0; ++lt, tile = dyn ? tq_read(lt) : (tile + tile_step < tile_end ? tile + tile_step : -1)) {
       const int buf = p.nbuf == 2 ? (lt & 1) : 0;
@@ -407,13 +443,8 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
 #pragma unroll 1
           for (int c = 0; c < 64; c += 32, ta += 32) {
             float v[32];
-            float4 b[8];
             tmem_ld32(ta, v);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) b[q] = *reinterpret_cast<const float4*>(&bias_s[c + 4 * q]);
-            tmem_ld_wait();
-#pragma unroll
-            for (int q = 0; q < 8; ++q) { v[4 * q] += b[q].x; v[4 * q + 1] += b[q].y; v[4 * q + 2] += b[q].z; v[4 * q + 3] += b[q].w; }
+            tmem_ld_wait();          // (the bias is already in the accumulator)
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               uint4 o = pack8_relu(v + 8 * q);
@@ -432,23 +463,17 @@ __global__ void __launch_bounds__(UC_THREADS, 1) umma_conv_kernel(const __grid_c
           const bool has_res = p.res != nullptr;   // (warp-uniform)
           const bool relu = p.act == ACT_RELU;
           const uint32_t vmask = valid ? 0xffffffffu : 0u;
-          const float* bp = &bias_s[cbeg];
           uint32_t ta = tb + (uint32_t)(m * p.Cout + cbeg);
 #pragma unroll 1
-          for (int c = cbeg; c < cend; c += 32, yp += 4 * yps, rp += 4 * rps, bp += 32, ta += 32) {
+          for (int c = cbeg; c < cend; c += 32, yp += 4 * yps, rp += 4 * rps, ta += 32) {
             float v[32];
-            float4 b[8];
             uint4 rr[4];
-            tmem_ld32(ta, v);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) b[q] = *reinterpret_cast<const float4*>(bp + 4 * q);
+            tmem_ld32(ta, v);        // (the bias is already in the accumulator: see the MMA issuer)
             if (has_res) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) rr[q] = valid ? *reinterpret_cast<const uint4*>(rp + q * rps) : make_uint4(0, 0, 0, 0);
             }
             tmem_ld_wait();
-#pragma unroll
-            for (int q = 0; q < 8; ++q) { v[4 * q] += b[q].x; v[4 * q + 1] += b[q].y; v[4 * q + 2] += b[q].z; v[4 * q + 3] += b[q].w; }
             if (has_res) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -646,12 +671,19 @@ void umma_conv_build_program(const UmmaConvP& p, UcStageDesc* out) {
 
 size_t umma_conv_smem_bytes(const UmmaConvP& p) {
   size_t b = (size_t)p.stages * (p.a_stage_bytes + p.w_stage_bytes) + (size_t)p.nst_tile * sizeof(UcStageDesc) + 1024;
-  if (p.y_mode == UC_Y_POOL) b += 128 + umma_conv_pool_smem_bytes(p.MT);
-  return b;
+  return b + umma_conv_extra_smem_bytes(p);
 }
 int umma_conv_stage_desc_bytes() { return (int)sizeof(UcStageDesc); }
 // UC_Y_POOL: ring of (tile + 128) positions x 64 channels bf16 + one int2 per tile position
 size_t umma_conv_pool_smem_bytes(int MT) { return (size_t)(MT * 128 + 128) * 128u + (size_t)MT * 128 * sizeof(int2); }
+static bool uc_is_generic(const UmmaConvP& p);
+// shared memory behind the stage program: the bias operand tiles of the lean instantiations (+ the max-pool ring)
+size_t umma_conv_extra_smem_bytes(const UmmaConvP& p) {
+  if (uc_is_generic(p)) return 0;
+  size_t b = 128 + 2048 + (size_t)(p.cta2 ? p.Cout / 2 : p.Cout) * 32u;
+  if (p.y_mode == UC_Y_POOL) b += 128 + umma_conv_pool_smem_bytes(p.MT);
+  return b;
+}
 
 static bool uc_is_generic(const UmmaConvP& p) {
   return p.y32 || p.res32 || p.ylo || p.res_lo || p.act == ACT_GELU || p.y_mode == UC_Y_NONE || (p.Cout & 31);   // (the lean epilogue works in 32-column steps)

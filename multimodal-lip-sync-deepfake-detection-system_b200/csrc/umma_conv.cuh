@@ -126,6 +126,7 @@ struct UmmaConvP {
 
 size_t umma_conv_smem_bytes(const UmmaConvP& p);
 int umma_conv_stage_desc_bytes();
+size_t umma_conv_extra_smem_bytes(const UmmaConvP& p);   // behind the stage program: bias operand tiles (lean epilogue) + max-pool ring
 size_t umma_conv_pool_smem_bytes(int MT);   // UC_Y_POOL: shared memory behind the stage program (ring + per-position table)
 // host: expand the stage program of a launch (same arithmetic the kernel used to do per stage)
 void umma_conv_build_program(const UmmaConvP& p, UcStageDesc* out);
