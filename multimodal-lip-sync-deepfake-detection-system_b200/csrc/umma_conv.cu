@@ -1034,11 +1034,48 @@ __global__ void __launch_bounds__(256) planar_maxpool_bf16_kernel(const __nv_bfl
   }
 }
 
+// Same result, one thread per pooled position: nine independent predicated 16-byte loads (the 3x3 window; neighbours' re-reads hit
+// L1), no shuffles, no idle lanes at the store.  The warp-per-row version above was bound by its dependent load -> shuffle chain
+// (209 us for the 811 MB of the stem's max-pool at B=64: 3.9 TB/s).
+__global__ void __launch_bounds__(192) planar_maxpool_direct_kernel(const __nv_bfloat16* __restrict__ x, int64_t xs, UcGeom gi,
+                                                                    __nv_bfloat16* __restrict__ y, int64_t ys, UcGeom go) {
+  const int frame = blockIdx.x, chunk = blockIdx.y;
+  const int n = frame / go.T, t = frame - n * go.T;
+  const uint4* xc = reinterpret_cast<const uint4*>(x + (int64_t)chunk * xs + uc_flat(gi, n, t, 0, 0) * 8);
+  uint4* yc = reinterpret_cast<uint4*>(y + (int64_t)chunk * ys + uc_flat(go, n, t, 0, 0) * 8);
+  const uint32_t NINF2 = 0xFF80FF80u;                                   // (-inf, -inf) in bf16
+  const int total = go.H * go.W;
+  for (int o = threadIdx.x; o < total; o += blockDim.x) {
+    const int h = o / go.W, w = o - h * go.W;
+    uint4 v[9];
+#pragma unroll
+    for (int dh = 0; dh < 3; ++dh)
+#pragma unroll
+      for (int dw = 0; dw < 3; ++dw) {
+        const int hi = 2 * h - 1 + dh, wi = 2 * w - 1 + dw;
+        v[dh * 3 + dw] = ((unsigned)hi < (unsigned)gi.H && (unsigned)wi < (unsigned)gi.W) ? xc[hi * gi.RW + wi] : make_uint4(NINF2, NINF2, NINF2, NINF2);
+      }
+    uint32_t* m = reinterpret_cast<uint32_t*>(&v[0]);
+#pragma unroll
+    for (int k = 1; k < 9; ++k) {
+      const uint32_t* r = reinterpret_cast<const uint32_t*>(&v[k]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat162 q = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&m[e]), *reinterpret_cast<const __nv_bfloat162*>(&r[e]));
+        m[e] = *reinterpret_cast<const uint32_t*>(&q);
+      }
+    }
+    yc[h * go.RW + w] = v[0];
+  }
+}
+
 void launch_planar_maxpool(const __nv_bfloat16* x, int64_t x_plane_stride, UcGeom gi, __nv_bfloat16* y, int64_t y_plane_stride, UcGeom go,
                            int C, cudaStream_t s, const __nv_bfloat16* xlo, __nv_bfloat16* ylo) {
   const int frames = go.N * go.T;
   if (frames == 0 || go.H * go.W == 0) return;
-  if (!xlo && !ylo) planar_maxpool_bf16_kernel<<<dim3((unsigned)frames, (unsigned)(C / 8)), 256, 0, s>>>(x, x_plane_stride, gi, y, y_plane_stride, go);
+  static const bool warp_rows = getenv("LSD_POOL_WARP_ROWS") != nullptr;   // (the previous kernel, for comparison)
+  if (!xlo && !ylo && !warp_rows) planar_maxpool_direct_kernel<<<dim3((unsigned)frames, (unsigned)(C / 8)), 192, 0, s>>>(x, x_plane_stride, gi, y, y_plane_stride, go);
+  else if (!xlo && !ylo) planar_maxpool_bf16_kernel<<<dim3((unsigned)frames, (unsigned)(C / 8)), 256, 0, s>>>(x, x_plane_stride, gi, y, y_plane_stride, go);
   else planar_maxpool_kernel<<<dim3((unsigned)frames, (unsigned)(C / 8)), 256, 0, s>>>(x, x_plane_stride, gi, y, y_plane_stride, go, xlo, ylo);
   count_launch();
 }

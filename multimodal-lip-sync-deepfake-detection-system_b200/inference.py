@@ -233,6 +233,8 @@ class Predictor:
             stage = self._u8_stage = [None] * NS
         L = _cabi.lib()
         state = {"mode": "fp32" if self.use_half_precision else self.host_transport}
+        if state["mode"] == "auto" and getattr(self, "_auto_prefers_fp32", False):
+            state["mode"] = "fp32"       # an earlier call on this predictor measured the pack slower than the copy (busy host / several GPUs)
 
         def start(k, vh, ah):
             """Host side of batch k, first half: starts the uint8 pack on the library's host threads (the call returns at once;
@@ -269,6 +271,7 @@ class Predictor:
                     recent.append(L.lsd_host_pack_last_ms())
                     if len(recent) >= 3 and min(recent[-3:]) * 1e-3 + 0.4e-3 > vh.numel() * 4 / 52e9:
                         state["mode"] = "fp32"
+                        self._auto_prefers_fp32 = True     # remembered for the later calls of this predictor
                 return stage[s], ah, "u8 (host-packed, exact)"
             state["mode"] = "fp32"               # not k/255 data: stop checking for the rest of this call
             return vh, ah, "fp32"

@@ -416,7 +416,8 @@ def test_scheduling_knobs_do_not_change_logits(model):
     digests = {}
     for name, env in {"default": {}, "dynamic_tiles": {"LSD_UMMA_DYNAMIC": "1"}, "side_all_sms": {"LSD_SIDE_CTAS": "148"},
                       "hf_early": {"LSD_HF_EARLY": "1"}, "audio_after_rows": {"LSD_AUDIO_AFTER_ROWS": "1"},
-                      "stem_pool_fused": {"LSD_STEM_POOL_FUSE": "1", "LSD_UMMA_CTA2": "0"}, "no_cta_pairs": {"LSD_UMMA_CTA2": "0"}}.items():
+                      "stem_pool_fused": {"LSD_STEM_POOL_FUSE": "1", "LSD_UMMA_CTA2": "0"}, "no_cta_pairs": {"LSD_UMMA_CTA2": "0"},
+                      "pool_warp_rows": {"LSD_POOL_WARP_ROWS": "1"}}.items():
         r = subprocess.run([sys.executable, "-c", code], env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, (name, r.stderr[-2000:])
         digests[name] = [l for l in r.stdout.splitlines() if l.startswith("DIGEST")][-1]
