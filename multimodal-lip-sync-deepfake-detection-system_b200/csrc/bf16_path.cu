@@ -742,6 +742,7 @@ static int pack_tok_front(lsd_handle* h, const std::vector<float>& f32) {
 
 int pack_bf16_weights(lsd_handle* h, const std::vector<float>& f32_arena) {
   Packer P{h, f32_arena, {}, {}};
+  memcpy(h->lapw_host, &f32_arena[h->convs.at("art.lap").w_off], sizeof(h->lapw_host));   // (video_rows takes them by value)
   h->blayers.clear();
   const int vstr[4] = {1, 2, 2, 2};
   const bool cta2 = !(getenv("LSD_UMMA_CTA2") && atoi(getenv("LSD_UMMA_CTA2")) == 0);
@@ -1096,9 +1097,9 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   const PBuf &xs = pb["xs"], &xl = pb["xl"], &so = pb["s_out"], &x1 = pb["x1"];
   const float* lapw = h->warena + h->convs.at("art.lap").w_off;
   // (vstarts: the uint8 track is read in place, window n = frames vstarts[n] .. vstarts[n]+T-1 — no fp32 window copy)
-  if (vstarts) launch_video_rows(video, vdt, vlayout, lapw, b.org(xs), b.org(xl), xs.set_stride, xs.g, s.H, s.W, st, h->num_sms, vstarts, n_frames);
-  else if (inputs_ready) launch_video_rows(b.f("vid"), LSD_F32, LSD_NDHWC, lapw, b.org(xs), b.org(xl), xs.set_stride, xs.g, s.H, s.W, st, h->num_sms);
-  else launch_video_rows(video, vdt, vlayout, lapw, b.org(xs), b.org(xl), xs.set_stride, xs.g, s.H, s.W, st, h->num_sms);
+  if (vstarts) launch_video_rows(video, vdt, vlayout, lapw, h->lapw_host, b.org(xs), b.org(xl), xs.set_stride, xs.g, s.H, s.W, st, h->num_sms, vstarts, n_frames);
+  else if (inputs_ready) launch_video_rows(b.f("vid"), LSD_F32, LSD_NDHWC, lapw, h->lapw_host, b.org(xs), b.org(xl), xs.set_stride, xs.g, s.H, s.W, st, h->num_sms);
+  else launch_video_rows(video, vdt, vlayout, lapw, h->lapw_host, b.org(xs), b.org(xl), xs.set_stride, xs.g, s.H, s.W, st, h->num_sms);
   g_tl.mark(st, "M:video_rows");
   // (LSD_AUDIO_AFTER_ROWS=1 forks the audio encoder after video_rows instead: that kernel then takes 158 us instead of 262 — it
   // walks its tiles with a static stride, so side-stream kernels holding SMs at its start delay it — but the audio encoder's chain of

@@ -62,6 +62,7 @@ struct lsd_handle {
   std::string err;
   bool loaded = false;
   float* warena = nullptr;                 // fp32 packed weights
+  float lapw_host[81] = {0};               // host copy of the 3->3 laplacian conv weights [tap][ci][co]: passed to video_rows by value
   void* barena = nullptr;                  // bf16 UMMA-packed weights
   std::map<std::string, ConvP> convs;
   std::map<std::string, size_t> vecs;      // small fp32 vectors (offsets into warena)

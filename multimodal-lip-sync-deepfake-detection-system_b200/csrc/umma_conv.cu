@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "lsd_kernels.h"
 #include "umma.cuh"
@@ -1246,21 +1247,20 @@ template <> __device__ __forceinline__ void vr_load4_lut<uint8_t>(const uint8_t*
 template <typename T> __device__ __forceinline__ float vr_norm_lut(T x, const float*) { return vr_norm<T>((float)x); }
 template <> __device__ __forceinline__ float vr_norm_lut<uint8_t>(uint8_t x, const float* lut) { return lut ? lut[x] : vr_u8_norm((float)x); }
 
+struct VrLapW { float w[81]; };   // [tap][ci][co], passed by value: the FFMAs take their weights from the constant bank
 template <typename T, int LAYOUT>
-__global__ void __launch_bounds__(VR2_THREADS, 2) video_rows_tma_kernel(const T* __restrict__ video, const int32_t* __restrict__ starts, int n_frames,
-                                                                    const float* __restrict__ lapw, __nv_bfloat16* __restrict__ xs,
+__global__ void __launch_bounds__(VR2_THREADS, 3) video_rows_tma_kernel(const T* __restrict__ video, const int32_t* __restrict__ starts, int n_frames,
+                                                                    const __grid_constant__ VrLapW LW, __nv_bfloat16* __restrict__ xs,
                                                                     __nv_bfloat16* __restrict__ xl, int64_t set_stride, UcGeom g, int Tn, int H, int W,
                                                                     int bands, int num_tiles) {
   extern __shared__ __align__(128) uint8_t vr_smem[];
   __shared__ uint64_t full_bar[VR2_STAGES];
-  __shared__ float lw[81];
   const float* lut = nullptr;   // (the table variant — 256 entries of i / 255.0f in shared memory — was bank-conflict-bound)
   const int tid = threadIdx.x;
   const int row_elems = LAYOUT == 0 ? W : 3 * W;                       // elements of one image row in one staged piece
   const int plane_elems = (VR2_ROWS + 2) * row_elems;                  // one staged piece (all rows of the band + halo)
   const uint32_t stage_bytes = (uint32_t)((LAYOUT == 0 ? 3 : 1) * plane_elems * (int)sizeof(T));
   const uint32_t stage_pitch = (stage_bytes + 127u) & ~127u;
-  if (tid < 81) lw[tid] = lapw[tid];
   if (tid == 0) {
     for (int i = 0; i < VR2_STAGES; ++i) mbar_init(&full_bar[i], 1);
     fence_barrier_init();
@@ -1362,7 +1362,7 @@ __global__ void __launch_bounds__(VR2_THREADS, 2) video_rows_tma_kernel(const T*
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
             const int wi = ((kh * 3 + kw) * 3 + ci) * 3;
-            const float w0 = lw[wi], w1 = lw[wi + 1], w2 = lw[wi + 2];
+            const float w0 = LW.w[wi], w1 = LW.w[wi + 1], w2 = LW.w[wi + 2];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               acc[q][0] = fmaf(w0, x[ci][q + kw], acc[q][0]);
@@ -1405,7 +1405,7 @@ bool video_rows_bulk_ok(const void* video, int dtype, int layout, int W) {
   return (W % 4 == 0) && (row_bytes % 16 == 0) && (reinterpret_cast<uintptr_t>(video) % 16 == 0) && stage * VR2_STAGES <= 96 * 1024;
 }
 
-void launch_video_rows(const void* video, int dtype, int layout, const float* lapw, __nv_bfloat16* xs, __nv_bfloat16* xl,
+void launch_video_rows(const void* video, int dtype, int layout, const float* lapw, const float* lapw_host, __nv_bfloat16* xs, __nv_bfloat16* xl,
                        int64_t set_stride, UcGeom g, int H, int W, cudaStream_t s, int num_sms, const int32_t* starts, int n_frames) {
   const size_t esz = dtype == 0 ? 4 : (dtype == 3 ? 1 : 2);
   const size_t row_bytes = (size_t)W * esz * (layout == 0 ? 1 : 3);
@@ -1415,11 +1415,13 @@ void launch_video_rows(const void* video, int dtype, int layout, const float* la
     const int64_t tiles = (int64_t)g.N * g.T * bands;
     if (tiles == 0) return;
     const size_t smem = stage * VR2_STAGES;
-    const int64_t per_sm = 2;   // 128 registers x 256 threads: two resident blocks per SM
+    VrLapW lw;
+    memcpy(lw.w, lapw_host, sizeof(lw.w));
+    const int64_t per_sm = stage * VR2_STAGES * 3 <= 200 * 1024 ? 3 : 2;   // 80 registers x 256 threads, <= 62 KB of stages: three resident blocks per SM
     const unsigned grid = (unsigned)std::min<int64_t>(tiles, per_sm * num_sms);
 #define VRT(TT, LL)                                                                                                             \
   do {                                                                                                                          \
-    video_rows_tma_kernel<TT, LL><<<grid, VR2_THREADS, smem, s>>>(reinterpret_cast<const TT*>(video), starts, n_frames, lapw, xs, xl,    \
+    video_rows_tma_kernel<TT, LL><<<grid, VR2_THREADS, smem, s>>>(reinterpret_cast<const TT*>(video), starts, n_frames, lw, xs, xl,    \
                                                                   set_stride, g, g.T, H, W, bands, (int)tiles);               \
   } while (0)
     if (layout == 0) {

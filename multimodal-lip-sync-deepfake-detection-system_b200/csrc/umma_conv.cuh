@@ -161,7 +161,9 @@ void launch_planar_maxpool(const __nv_bfloat16* x, int64_t x_plane_stride, UcGeo
 // 2 pixels), pixel p of a row at element offset (p + 4) * 4, channels (r, g, b, 0).
 // starts != nullptr (interleaved tracks, bulk-copy path only — check video_rows_bulk_ok): window n reads frames
 // starts[n] .. starts[n]+T-1 of an n_frames-long track instead of frames n*T .. n*T+T-1.
-void launch_video_rows(const void* video, int dtype, int layout, const float* lapw, __nv_bfloat16* xs, __nv_bfloat16* xl,
+// lapw_host: the same 81 weights on the host; the bulk-copy kernel takes them by value (constant-bank FFMA operands instead of 81
+// shared-memory loads per 4 pixels).
+void launch_video_rows(const void* video, int dtype, int layout, const float* lapw, const float* lapw_host, __nv_bfloat16* xs, __nv_bfloat16* xl,
                        int64_t set_stride, UcGeom g, int H, int W, cudaStream_t s, int num_sms, const int32_t* starts = nullptr, int n_frames = 0);
 bool video_rows_bulk_ok(const void* video, int dtype, int layout, int W);
 
