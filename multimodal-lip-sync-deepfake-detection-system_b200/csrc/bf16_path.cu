@@ -6,6 +6,7 @@
 #include "tok_fused.cuh"
 #include "token_kernels.cuh"
 #include "umma_conv.cuh"
+#include "stem_ring.cuh"
 
 #include <cuda_fp16.h>
 
@@ -593,6 +594,83 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
   return 0;
 }
 
+// Stem through the temporal-ring kernel (stem_ring.cu): xs (pixel rows, 2 parity sets) -> so (plain planar, 64 channels), same geometry.
+int run_stem_ring(const BCtx& c, const PBuf& xs, const PBuf& so) {
+  lsd_handle* h = c.h;
+  const UcGeom& g = xs.g;
+  if (g.P_total >= ((int64_t)1 << 31) - 4096) return lsd_fail(h, LSD_ERR_SHAPE, "stem: more than 2^31 padded positions in one launch (reduce the batch)");
+  const BLayer& L = h->blayers.at("visual_encoder.stem");
+  StemRingP p;
+  memset(&p, 0, sizeof(p));
+  p.xs[0] = c.org(xs);
+  p.xs[1] = c.org(xs) + xs.set_stride;
+  p.w = reinterpret_cast<const __nv_bfloat16*>(h->barena) + h->stem_ring_w_off;
+  p.bias = h->bbias + L.bias_off;
+  p.y = c.org(so);
+  p.y_plane_stride = so.plane_stride;
+  p.g = g;
+  // parity set 0: kernel rows 1, 3, 5 (dh = -1, 0, 1); set 1: rows 0, 2, 4, 6 (dh = -2 .. 1); K chunks are 2-position shifts
+  p.ntap[0] = 3; p.ntap[1] = 4;
+  for (int t = 0; t < 4; ++t) { p.rel[0][t] = t * g.RW; p.rel[1][t] = t * g.RW; }
+  p.start[0] = -g.RW; p.start[1] = -2 * g.RW;
+  p.units[0] = 128 + 2 * g.RW + 3; p.units[1] = 128 + 3 * g.RW + 3;
+  if ((int64_t)(2 * g.RW + 3) * 8 > xs.origin) return lsd_fail(h, LSD_ERR_UNSUPPORTED, "stem: guard zone too small");
+  // step table: (column chunk, t) outputs numbered column-major, cut into equal contiguous ranges, one per accumulator slot
+  const int T = g.T, CH = (g.SL + 127) / 128;
+  const int64_t G = (int64_t)g.N * CH * T;
+  const int budget = (c.max_ctas > 0 && c.max_ctas < h->num_sms) ? c.max_ctas : h->num_sms;
+  uint64_t key = 1469598103934665603ull;
+  for (uint64_t v : {(uint64_t)g.N, (uint64_t)T, (uint64_t)g.SL, (uint64_t)g.TS, (uint64_t)g.ot, (uint64_t)budget}) { key ^= v; key *= 1099511628211ull; key ^= key >> 29; }
+  auto it = h->ring_tabs.find(key);
+  if (it == h->ring_tabs.end()) {
+    int grid = budget;
+    int64_t Lr = (G + 2 * (int64_t)grid - 1) / (2 * (int64_t)grid);
+    if (Lr < 8) { Lr = 8; grid = (int)((G + 2 * Lr - 1) / (2 * Lr)); }
+    if (grid < 1) grid = 1;
+    std::vector<std::vector<SrStep>> lists((size_t)2 * grid);
+    size_t nsteps = 0;
+    for (int sg = 0; sg < 2 * grid; ++sg) {
+      int64_t g0 = (int64_t)sg * Lr;
+      const int64_t g1 = std::min(G, g0 + Lr);
+      while (g0 < g1) {
+        const int64_t col = g0 / T;
+        const int ta = (int)(g0 % T), tb = (int)std::min<int64_t>(T, ta + (g1 - g0));
+        const int n = (int)(col / CH), sp = (int)(col % CH);
+        const int t_first = std::max(ta - 1, 0);
+        for (int t_in = t_first; t_in <= tb; ++t_in) {
+          SrStep st;
+          st.in_pos = (int32_t)(((int64_t)n * g.TS + t_in + g.ot) * g.SL + (int64_t)sp * 128);
+          const int t_out = t_in - 1;
+          st.out_pos = (t_out >= ta && t_out < tb) ? (int32_t)(((int64_t)n * g.TS + t_out + g.ot) * g.SL + (int64_t)sp * 128) : -1;
+          st.flags = 1 | (t_in == t_first ? 2 : 0);
+          st.valid = std::min(128, g.SL - sp * 128);
+          lists[sg].push_back(st);
+        }
+        g0 += tb - ta;
+      }
+      nsteps = std::max(nsteps, lists[sg].size());
+    }
+    std::vector<SrStep> flat((size_t)2 * grid * nsteps);
+    memset(flat.data(), 0, flat.size() * sizeof(SrStep));
+    for (int sg = 0; sg < 2 * grid; ++sg) std::copy(lists[sg].begin(), lists[sg].end(), flat.begin() + (size_t)sg * nsteps);
+    lsd_handle::RingTab tab;
+    tab.nsteps = (int)nsteps; tab.grid = grid;
+    // cache miss only (first forward of a shape): blocking copy, visible to every stream afterwards
+    if (cudaMalloc(&tab.dev, std::max<size_t>(flat.size(), 1) * sizeof(SrStep)) != cudaSuccess ||
+        cudaMemcpy(tab.dev, flat.data(), flat.size() * sizeof(SrStep), cudaMemcpyHostToDevice) != cudaSuccess)
+      return lsd_fail(h, LSD_ERR_CUDA, "stem: step table upload failed");
+    it = h->ring_tabs.emplace(key, tab).first;
+  }
+  p.steps = reinterpret_cast<const SrStep*>(it->second.dev);
+  p.nsteps = it->second.nsteps;
+  if (stem_ring_smem_bytes(p) > 223u * 1024u) return lsd_fail(h, LSD_ERR_UNSUPPORTED, "stem: rows too wide for the ring kernel");
+  const ConvP& cp = h->convs.at("visual_encoder.stem");
+  h->prof.begin(c.st, 2.0 * (double)g.N * g.T * g.H * g.W * 64.0 * (double)cp.kt * cp.kh * cp.kw * cp.Cin, 2);
+  launch_stem_ring(p, it->second.grid, c.st);
+  h->prof.end(c.st);
+  return 0;
+}
+
 #define RUN(name, ...)                            \
   do {                                            \
     UArgs a_;                                     \
@@ -761,6 +839,31 @@ int pack_bf16_weights(lsd_handle* h, const std::vector<float>& f32_arena) {
     P.add(p + ".conv2", p + ".conv2", 1, 1, l == 1 ? "" : p + ".downsample", nt, false, false, pairs);
   }
   P.add_toeplitz("visual_encoder.stem", "visual_encoder.stem", 8, 0, false, cta2);  // 7 taps in w -> 8-pixel window starting at 2*wo-4
+  {
+    // the same weights for the temporal-ring kernel (stem_ring.cu): per (parity set, kernel row) tap and K chunk one block
+    // [2 K halves][192 = 3 temporal taps x 64 columns][8]; column block j holds the weights of temporal tap dt = j - 1
+    const ConvP& c = h->convs.at("visual_encoder.stem");
+    h->stem_ring_w_off = 0;
+    if (c.kt == 3 && c.kh == 7 && c.kw == 7 && c.Cin == 3 && c.Cout == 64) {
+      h->stem_ring_w_off = P.w.size();
+      const float* W = &f32_arena[c.w_off];
+      const float* sc = c.has_scale ? &f32_arena[c.scale_off] : nullptr;
+      for (int set = 0; set < 2; ++set)
+        for (int b = 0; b < 7; ++b) {
+          if (((b - 3) & 1) != set) continue;          // rows of this parity set, in ascending dh
+          for (int ch = 0; ch < 2; ++ch)
+            for (int kc = 0; kc < 2; ++kc)
+              for (int n = 0; n < 192; ++n)
+                for (int e = 0; e < 8; ++e) {
+                  const int k = ch * 16 + kc * 8 + e, j = k / 4, kw = j - 1, ci = k % 4, a = n / 64, co = n % 64;
+                  float v = 0.f;
+                  if (ci < 3 && kw >= 0 && kw < 7) v = W[((size_t)((a * 7 + b) * 7 + kw) * 3 + ci) * 64 + co] * (sc ? sc[co] : 1.0f);
+                  P.w.push_back(f2bf(v));
+                }
+        }
+      while (P.w.size() % 64) P.w.push_back(0);
+    }
+  }
   P.add_toeplitz("art.hf0", "art.hf0", 4, 1);                          // 3 taps in w -> 4-pixel window starting at 2*wo-2
   P.add("art.td0", "art.td0", 1, 1);
   P.add("art.td3", "art.td3", 1, 1);
@@ -1142,7 +1245,15 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
     // power cap, where the saved DRAM traffic buys clock).
     static const bool fuse_env = getenv("LSD_STEM_POOL_FUSE") && atoi(getenv("LSD_STEM_POOL_FUSE")) != 0;
     const bool fuse_pool = fuse_env && !h->blayers.at("visual_encoder.stem").halves && !(xs.g.H & 1) && !(xs.g.W & 1) && x1.g.H * 2 == xs.g.H && x1.g.W * 2 == xs.g.W && 2 * xs.g.RW + 2 <= 128;
-    if (fuse_pool && (chunk <= 0 || chunk >= B)) {
+    // Default: the temporal-ring kernel (stem_ring.cu: the three temporal taps as one N = 192 MMA); LSD_STEM_RING=0 keeps the flat
+    // shift-GEMM launch (CTA pairs).  The summation order differs between the two, the bits of a given route do not depend on the batch.
+    static const bool ring_env = !(getenv("LSD_STEM_RING") && atoi(getenv("LSD_STEM_RING")) == 0);
+    const bool ring = ring_env && h->stem_ring_w_off != 0 && !fuse_env && (chunk <= 0 || chunk >= B) && 128 + 3 * xs.g.RW + 3 <= 640;
+    if (ring) {
+      if ((rc = run_stem_ring(b, xs, so))) return rc;
+      g_tl.mark(st, "M:stem");
+      launch_planar_maxpool(b.org(so), so.plane_stride, so.g, b.org(x1), x1.plane_stride, x1.g, 64, st);
+    } else if (fuse_pool && (chunk <= 0 || chunk >= B)) {
       RUN("visual_encoder.stem", a_.in = &xs; a_.og = xs.g; a_.act = ACT_RELU; a_.yp = &x1; a_.y_mode = UC_Y_POOL);
       g_tl.mark(st, "M:stem");
     } else if (chunk <= 0 || chunk >= B) {

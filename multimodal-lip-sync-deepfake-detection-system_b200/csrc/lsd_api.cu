@@ -13,6 +13,7 @@
 #include "forward_common.h"
 #include "tok_front.cuh"
 #include "tok_fused.cuh"
+#include "stem_ring.cuh"
 #include "umma_conv.cuh"
 using namespace lsd;
 
@@ -82,6 +83,7 @@ extern "C" int lsd_create(lsd_handle** out, int device) {
   if (rc == 0) {
     cudaError_t ce = lsd::umma_conv_device_init();
     if (ce == cudaSuccess) ce = lsd::tok_fused_device_init();
+    if (ce == cudaSuccess) ce = lsd::stem_ring_device_init();
     if (ce == cudaSuccess) ce = lsd::tok_front_device_init();
     if (ce != cudaSuccess) rc = lsd_fail(h, LSD_ERR_CUDA, "lsd_create: kernel attribute setup: %s", cudaGetErrorString(ce));
   }
@@ -103,6 +105,7 @@ extern "C" void lsd_destroy(lsd_handle* h) {
   if (h->tokf_vec) cudaFree(h->tokf_vec);
   if (h->mel_tables) cudaFree(h->mel_tables);
   if (h->prog_arena) cudaFree(h->prog_arena);
+  for (auto& kv : h->ring_tabs) if (kv.second.dev) cudaFree(kv.second.dev);
   if (h->tile_ctr_arena) cudaFree(h->tile_ctr_arena);
   if (h->lm_clips) cudaFree(h->lm_clips);
   if (h->ev_lm_clips) cudaEventDestroy(h->ev_lm_clips);

@@ -98,6 +98,10 @@ struct lsd_handle {
   char* prog_arena = nullptr;
   size_t prog_cap = 0, prog_cursor = 0;
   std::unordered_map<uint64_t, const void*> prog_cache;
+  // temporal-ring stem (stem_ring.cu): packed N = 192 weights inside barena, step tables per (batch, frames, geometry)
+  size_t stem_ring_w_off = 0;              // bf16 elements into barena; 0 = not packed
+  struct RingTab { void* dev = nullptr; int nsteps = 0, grid = 0; };
+  std::unordered_map<uint64_t, RingTab> ring_tabs;
   // tile counters of the tcgen05 launches (dynamic tile scheduling): 16 words per layer name, zero whenever the layer is not
   // running (the last CTA of a launch resets them); launches of one layer are always ordered on one stream
   unsigned* tile_ctr_arena = nullptr;

@@ -418,10 +418,38 @@ def test_scheduling_knobs_do_not_change_logits(model):
                       "hf_early": {"LSD_HF_EARLY": "1"}, "audio_after_rows": {"LSD_AUDIO_AFTER_ROWS": "1"},
                       "stem_pool_fused": {"LSD_STEM_POOL_FUSE": "1", "LSD_UMMA_CTA2": "0"}, "no_cta_pairs": {"LSD_UMMA_CTA2": "0"},
                       "pool_warp_rows": {"LSD_POOL_WARP_ROWS": "1"}}.items():
-        r = subprocess.run([sys.executable, "-c", code], env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
+        # (LSD_STEM_RING=0: all variants run the flat shift-GEMM stem — the temporal-ring stem sums in a different order, it is
+        #  compared with a tolerance in test_stem_ring_matches_flat_stem)
+        r = subprocess.run([sys.executable, "-c", code], env={**os.environ, "LSD_STEM_RING": "0", **env}, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, (name, r.stderr[-2000:])
         digests[name] = [l for l in r.stdout.splitlines() if l.startswith("DIGEST")][-1]
     assert len(set(digests.values())) == 1, digests
+
+
+def test_stem_ring_matches_flat_stem(model):
+    """The default stem (stem_ring.cu: three temporal taps as one N = 192 MMA over a TMEM ring of accumulators) against the flat
+    shift-GEMM stem (LSD_STEM_RING=0): same bf16 operands, different fp32 summation order -> logits within a fraction of the bf16
+    budget, for the canonical window, half windows (T=16) and a single frame (T=1: first step is also the last), in a fresh
+    interpreter per route (the knob is read once per process)."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import torch, json, lipsync_b200 as lb\n"
+            "m = lb.LipSyncModel(); m.load_state_dict(lb.make_synthetic_state_dict(0)); m.to('cuda:0').eval(); m.compute_precision = 'bf16'\n"
+            "v, a = lb.synthetic_windows(41, 7)\n"
+            "out = {}\n"
+            "out['full'] = m(v.cuda(), a.cuda()).float().cpu().tolist()\n"
+            "out['half'] = m(v[:, :, 8:24].contiguous().cuda(), a[..., 32:96].contiguous().cuda()).float().cpu().tolist()\n"
+            "out['one'] = m(v[:3, :, :1].contiguous().cuda(), a[:3].cuda()).float().cpu().tolist()\n"
+            "print('OUT', json.dumps(out))\n") % root
+    res = {}
+    for name, env in {"ring": {}, "flat": {"LSD_STEM_RING": "0"}}.items():
+        r = subprocess.run([sys.executable, "-c", code], env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, (name, r.stderr[-2000:])
+        res[name] = json.loads([l for l in r.stdout.splitlines() if l.startswith("OUT")][-1][4:])
+    for k in res["ring"]:
+        d = np.abs(np.asarray(res["ring"][k]) - np.asarray(res["flat"][k])).max()
+        assert d <= 5e-3, (k, d, res["ring"][k], res["flat"][k])
 
 
 def test_temporal_smoothed_confidence_values_match_oracle(model, seed0_sd):
