@@ -640,10 +640,9 @@ int run_stem_ring(const BCtx& c, const PBuf& xs, const PBuf& so) {
         for (int t_in = t_first; t_in <= tb; ++t_in) {
           SrStep st;
           st.in_pos = (int32_t)(((int64_t)n * g.TS + t_in + g.ot) * g.SL + (int64_t)sp * 128);
-          const int t_out = t_in - 1;
-          st.out_pos = (t_out >= ta && t_out < tb) ? (int32_t)(((int64_t)n * g.TS + t_out + g.ot) * g.SL + (int64_t)sp * 128) : -1;
-          st.flags = 1 | (t_in == t_first ? 2 : 0);
-          st.valid = std::min(128, g.SL - sp * 128);
+          const int t_out = t_in - 1;   // the output slab that completes with this step: stored when it belongs to this range
+          st.flags = SR_ACTIVE | (t_in == t_first ? SR_FIRST : 0u) | ((t_out >= ta && t_out < tb) ? SR_STORE : 0u) |
+                     ((uint32_t)std::min(128, g.SL - sp * 128) << 8);
           lists[sg].push_back(st);
         }
         g0 += tb - ta;
@@ -663,9 +662,31 @@ int run_stem_ring(const BCtx& c, const PBuf& xs, const PBuf& so) {
   }
   p.steps = reinterpret_cast<const SrStep*>(it->second.dev);
   p.nsteps = it->second.nsteps;
-  if (stem_ring_smem_bytes(p) > 223u * 1024u) return lsd_fail(h, LSD_ERR_UNSUPPORTED, "stem: rows too wide for the ring kernel");
+  p.nst = 6;
+  if (const char* e = getenv("LSD_SR_SKIP")) p.skip = atoi(e);   // timing experiments only
+  while (p.nst > 3 && stem_ring_smem_bytes(p) > 223u * 1024u) --p.nst;    // a long step table (large batches) takes ring stages
+  if (stem_ring_smem_bytes(p) > 223u * 1024u) return lsd_fail(h, LSD_ERR_UNSUPPORTED, "stem: batch too large for the ring kernel (LSD_STEM_RING=0)");
   const ConvP& cp = h->convs.at("visual_encoder.stem");
   h->prof.begin(c.st, 2.0 * (double)g.N * g.T * g.H * g.W * 64.0 * (double)cp.kt * cp.kh * cp.kw * cp.Cin, 2);
+  if (getenv("LSD_SR_TRACE")) {
+    // debug: clock64 stamps of CTA 0, steps 16..47 (producer: stage free / copies issued; MMA slot 0: stage landed / accumulator
+    // block free / step issued; epilogue warp 4: accumulator complete / block handed back); prints after a sync
+    static long long* dbuf = nullptr;
+    if (!dbuf) cudaMalloc(&dbuf, 4 * 32 * 2 * sizeof(long long));
+    cudaMemsetAsync(dbuf, 0, 4 * 32 * 2 * sizeof(long long), c.st);
+    p.dbg = dbuf;
+    launch_stem_ring(p, it->second.grid, c.st);
+    long long hv[4 * 32 * 2];
+    cudaMemcpyAsync(hv, dbuf, sizeof(hv), cudaMemcpyDeviceToHost, c.st);
+    cudaStreamSynchronize(c.st);
+    const long long t0 = hv[0];
+    for (int k = 0; k < 32; ++k)
+      fprintf(stderr, "[sr] step %2d | prod free %7lld issued %7lld | mma landed %7lld blockfree %7lld issued %7lld | epi complete %7lld back %7lld\n", k + 16,
+              hv[(0 * 32 + k) * 2] - t0, hv[(0 * 32 + k) * 2 + 1] - t0, hv[(1 * 32 + k) * 2] - t0, hv[(1 * 32 + k) * 2 + 1] - t0,
+              hv[(2 * 32 + k) * 2] - t0, hv[(3 * 32 + k) * 2] - t0, hv[(3 * 32 + k) * 2 + 1] - t0);
+    h->prof.end(c.st);
+    return 0;
+  }
   launch_stem_ring(p, it->second.grid, c.st);
   h->prof.end(c.st);
   return 0;
@@ -1187,7 +1208,7 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   };
   g_tl.on = getenv("LSD_TIMELINE") != nullptr;
   g_tl.mark(st, "start");
-  const bool audio_after_rows = getenv("LSD_AUDIO_AFTER_ROWS") != nullptr;   // tuning knob, see below
+  const bool audio_after_rows = getenv("LSD_AUDIO_AFTER_ROWS") && atoi(getenv("LSD_AUDIO_AFTER_ROWS")) != 0;   // tuning knob, see below
   if (audio_early && !audio_after_rows) {
     cudaEventRecord(h->ev_start, st);
     cudaStreamWaitEvent(sst, h->ev_start, 0);
@@ -1204,9 +1225,11 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   else if (inputs_ready) launch_video_rows(b.f("vid"), LSD_F32, LSD_NDHWC, lapw, h->lapw_host, b.org(xs), b.org(xl), xs.set_stride, xs.g, s.H, s.W, st, h->num_sms);
   else launch_video_rows(video, vdt, vlayout, lapw, h->lapw_host, b.org(xs), b.org(xl), xs.set_stride, xs.g, s.H, s.W, st, h->num_sms);
   g_tl.mark(st, "M:video_rows");
-  // (LSD_AUDIO_AFTER_ROWS=1 forks the audio encoder after video_rows instead: that kernel then takes 158 us instead of 262 — it
-  // walks its tiles with a static stride, so side-stream kernels holding SMs at its start delay it — but the audio encoder's chain of
-  // 15 launches, which only gets SMs at the main stream's kernel boundaries, then ends after the visual encoder: no net gain)
+  // (LSD_AUDIO_AFTER_ROWS=1 forks the audio encoder after video_rows instead.  video_rows walks its tiles with a static stride, so
+  // side-stream kernels holding SMs at its start delay it: 267 -> 123 us when it runs alone, and ONE forward is 110 us shorter
+  // (timeline at B=64: head at 2543 instead of 2665 us).  Back to back the early fork wins: scripts/exp_ab.py, 40 / 400 forwards:
+  // 2.69 / 2.86 ms per forward against 2.73 / 2.89 — the audio encoder of forward k+1 then fills the SMs the tail of forward k
+  // leaves idle.  Throughput is the metric, so the early fork stays the default.)
   if (audio_early && audio_after_rows) {
     cudaEventRecord(h->ev_start, st);
     cudaStreamWaitEvent(sst, h->ev_start, 0);

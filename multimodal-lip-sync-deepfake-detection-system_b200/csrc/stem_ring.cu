@@ -33,7 +33,7 @@ using namespace umma;
 
 namespace {
 
-constexpr int SR_THREADS = 384, SR_NST = 6;
+constexpr int SR_THREADS = 384, SR_NST = 6;   // SR_NST: most ring stages (barrier arrays); p.nst are in use
 
 __device__ __forceinline__ uint32_t sr_div(uint32_t n, uint32_t m, int s) { return (uint32_t)(((uint64_t)n * m) >> (31 + s)); }
 __device__ __forceinline__ bool sr_valid(const UcGeom& g, int64_t P) {
@@ -66,7 +66,14 @@ __global__ void __launch_bounds__(SR_THREADS, 1) stem_ring_kernel(const __grid_c
   uint8_t* const ones = smem + SR_WBYTES;          // A of the bias MMA: 128 rows x (1, 1, 1, 0, ...), both K halves alias it (LBO = 0)
   uint8_t* const biasb = ones + 2048;              // B of the bias MMA: [2 K halves][64 columns][8]: (hi, mid, lo) parts of the bias, zeros
   uint8_t* const stages = biasb + 2048;
+  // this CTA's two rows of the step table, behind the stages (a dependent global load per step in every role's loop cost ~700 cycles
+  // of L2 latency per step on the critical path)
+  SrStep* const tab = reinterpret_cast<SrStep*>(stages + (size_t)p.nst * stage_bytes);
 
+  {
+    const uint2* src = reinterpret_cast<const uint2*>(p.steps + (size_t)(2 * blockIdx.x) * (size_t)p.nsteps);
+    for (int i = tid; i < 2 * p.nsteps; i += SR_THREADS) reinterpret_cast<uint2*>(tab)[i] = src[i];
+  }
   if (tid == 0) {
     for (int i = 0; i < SR_NST; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 2); }
     for (int s = 0; s < 2; ++s)
@@ -94,7 +101,9 @@ __global__ void __launch_bounds__(SR_THREADS, 1) stem_ring_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  const SrStep* const st0 = p.steps + (size_t)(2 * blockIdx.x) * (size_t)p.nsteps;
+  const SrStep* const st0 = tab;
+  long long* const dbg = (p.dbg && blockIdx.x == 0 && lane == 0) ? p.dbg : nullptr;
+  auto stamp = [&](int role, int k, int which) { if (dbg && k >= 16 && k < 48) dbg[(role * 32 + (k - 16)) * 2 + which] = clock64(); };
 
   if (warp == 0) {
     // ------------------------------------------------ producer: the weights once, then per step the pixel-row regions of both slots
@@ -107,12 +116,13 @@ __global__ void __launch_bounds__(SR_THREADS, 1) stem_ring_kernel(const __grid_c
     const uint32_t bytes = (uint32_t)p.units[set] * 16u;
     const uint32_t dst0 = smem_u32(stages) + (uint32_t)slot * slot_bytes + (set ? r0 : 0u);
     for (int k = 0; k < p.nsteps; ++k) {
-      const int stage = k % SR_NST;
-      const uint32_t ph = (uint32_t)(k / SR_NST) & 1u;
+      const int stage = k % p.nst;
+      const uint32_t ph = (uint32_t)(k / p.nst) & 1u;
       const SrStep sd = st[k];
-      const bool act = lane < 4 && (sd.flags & 1);
+      const bool act = lane < 4 && (sd.flags & SR_ACTIVE);
       const uint32_t total = __reduce_add_sync(0xffffffffu, act ? bytes : 0u);
       mbar_wait(&empty_bar[stage], ph ^ 1u);
+      stamp(0, k, 0);
       if (lane == 0) mbar_arrive_expect_tx(&full_bar[stage], total);
       __syncwarp();
       if (act) {
@@ -120,6 +130,7 @@ __global__ void __launch_bounds__(SR_THREADS, 1) stem_ring_kernel(const __grid_c
         bulk_s2(dst0 + (uint32_t)stage * stage_bytes, src, bytes, &full_bar[stage]);
       }
       __syncwarp();
+      stamp(0, k, 1);
     }
   } else if (warp == 1 || warp == 2) {
     // ------------------------------------------------ MMA issuer of slot (warp - 1): whole warp runs the loop, one lane issues
@@ -127,74 +138,68 @@ __global__ void __launch_bounds__(SR_THREADS, 1) stem_ring_kernel(const __grid_c
     const SrStep* const st = st0 + (size_t)slot * (size_t)p.nsteps;
     const uint32_t leader = elect_one() ? 1u : 0u;
     const uint64_t desc_hi64 = ((uint64_t)8 << 32) | ((uint64_t)1 << 46);          // SBO = 128 B, descriptor version 1
-    const uint32_t id192 = idesc_bf16(128, 192), id128 = idesc_bf16(128, 128), id64 = idesc_bf16(128, 64);
+    const uint32_t id192 = (p.skip & 8) ? idesc_bf16(128, 64) : idesc_bf16(128, 192), id128 = idesc_bf16(128, 128), id64 = idesc_bf16(128, 64);   // (skip bit 3: timing experiment)
     const uint32_t tb = tmem + (uint32_t)slot * 256u;
     const uint64_t d_ones = desc_hi64 | (uint64_t)(smem_u32(ones) >> 4);                           // LBO = 0
     const uint64_t d_bias = desc_hi64 | (uint64_t)((smem_u32(biasb) >> 4) | (64u << 16));         // LBO = 64 columns x 16 B
     const uint32_t w0 = (smem_u32(wsm) >> 4) | (192u << 16);                                       // LBO = 192 columns x 16 B
     const uint32_t a_slot = (smem_u32(stages) + (uint32_t)slot * slot_bytes) >> 4;
-    // tap tau = (parity set, row): A offset inside the slot's stage, in 16-byte units, with the Toeplitz LBO (16 B) in the high half
-    uint32_t a_off[SR_TAPS];
-#pragma unroll
-    for (int tau = 0; tau < SR_TAPS; ++tau) {
-      const int set = tau < 3 ? 0 : 1, tp = tau < 3 ? tau : tau - 3;
-      a_off[tau] = ((set ? r0 : 0u) >> 4) + (uint32_t)p.rel[set][tp] + (1u << 16);
-    }
     mbar_wait(&wbar, 0u);
     tc_fence_after();
     int q = 0;
     for (int k = 0; k < p.nsteps; ++k) {
-      const int stage = k % SR_NST;
-      const uint32_t ph = (uint32_t)(k / SR_NST) & 1u;
-      const int flags = st[k].flags;
+      const int stage = k % p.nst;
+      const uint32_t ph = (uint32_t)(k / p.nst) & 1u;
+      // (a value ptxas knows to be warp-uniform: everything derived from it — q, the D block, the branches — then stays in uniform
+      //  registers; taken straight from the shared-memory load, every MMA operand went through R2UR moves, ~4 per MMA)
+      const uint32_t flags = __shfl_sync(0xffffffffu, st[k].flags, 0);
       mbar_wait(&full_bar[stage], ph);
       tc_fence_after();
-      if (flags & 1) {
+      if (slot == 0) stamp(1, k, 0);
+      if (flags & SR_ACTIVE) {
         if (q >= 2) { mbar_wait(&tempty[slot][(q - 2) & 3], (uint32_t)((q - 2) >> 2) & 1u); tc_fence_after(); }
-        const uint32_t c = (uint32_t)(-q) & 3u;              // first block of this step's D region: [out(t+1) | out(t) | out(t-1)]
-        if (flags & 2) {
+        if (slot == 0) stamp(1, k, 1);
+        const uint32_t c = (p.skip & 2) ? 0u : ((uint32_t)(-q) & 3u);   // first block of this step's D region: [out(t+1) | out(t) | out(t-1)]
+        if (flags & SR_FIRST) {
           mma_bf16_ss_pred(tb + c * 64u, d_ones, d_bias, id64, 0u, leader);
           mma_bf16_ss_pred(tb + ((c + 1u) & 3u) * 64u, d_ones, d_bias, id64, 0u, leader);
           mma_bf16_ss_pred(tb + ((c + 2u) & 3u) * 64u, d_ones, d_bias, id64, 0u, leader);
         } else {
           mma_bf16_ss_pred(tb + c * 64u, d_ones, d_bias, id64, 0u, leader);
         }
-        // (the seven taps and their two K chunks are unrolled with loop-invariant offsets held in registers: a tap loop that reloads
-        //  its offsets from the parameter block issues one MMA per ~190 cycles, LDCU -> add -> UTCHMMA, and with ONE issuing warp
-        //  per slot that — not the tensor pipe — would pace the kernel)
-        const uint32_t ab = a_slot + (((uint32_t)stage * stage_bytes) >> 4);
-        if (c <= 1u) {
-          const uint32_t td = tb + c * 64u;
-#pragma unroll
-          for (int tau = 0; tau < SR_TAPS; ++tau)
-#pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-              const uint64_t da = desc_hi64 | (uint64_t)(ab + a_off[tau] + 2u * (uint32_t)ch);
-              const uint64_t db = desc_hi64 | (uint64_t)(w0 + (uint32_t)((tau * 2 + ch) * (SR_WBLOCK >> 4)));
-              mma_bf16_ss_pred(td, da, db, id192, 1u, leader);
+        // (descriptors advance by running additions — taps of a parity set are RW positions apart, weight blocks are consecutive — so
+        //  the loop carries no loads and few live uniform registers; an unrolled version with per-tap offsets kept in an array went
+        //  through vector registers and R2UR moves, ~4 per MMA)
+        const uint32_t ab = a_slot + (((uint32_t)stage * stage_bytes) >> 4) + (1u << 16);   // LBO = 16 B (Toeplitz K)
+        const uint32_t rw = (uint32_t)p.g.RW;
+        uint32_t wj = w0;
+#pragma unroll 1
+        for (int set = 0; set < 2; ++set) {
+          uint32_t at = ab + (set ? (r0 >> 4) : 0u);
+          const int nt = set ? 4 : 3;
+#pragma unroll 1
+          for (int tp = 0; tp < nt; ++tp, at += rw, wj += 2u * (uint32_t)(SR_WBLOCK >> 4)) {
+            if ((p.skip & 4) && (set || tp >= 2)) continue;
+            const uint64_t da0 = desc_hi64 | (uint64_t)at, da1 = desc_hi64 | (uint64_t)(at + 2u);
+            const uint64_t db0 = desc_hi64 | (uint64_t)wj, db1 = desc_hi64 | (uint64_t)(wj + (uint32_t)(SR_WBLOCK >> 4));
+            if (c <= 1u) {
+              mma_bf16_ss_pred(tb + c * 64u, da0, db0, id192, 1u, leader);
+              mma_bf16_ss_pred(tb + c * 64u, da1, db1, id192, 1u, leader);
+            } else if (c == 2u) {          // blocks 2, 3, then (wrapped) block 0
+              mma_bf16_ss_pred(tb + 128u, da0, db0, id128, 1u, leader);
+              mma_bf16_ss_pred(tb, da0, db0 + 128u, id64, 1u, leader);
+              mma_bf16_ss_pred(tb + 128u, da1, db1, id128, 1u, leader);
+              mma_bf16_ss_pred(tb, da1, db1 + 128u, id64, 1u, leader);
+            } else {                       // block 3, then (wrapped) blocks 0, 1
+              mma_bf16_ss_pred(tb + 192u, da0, db0, id64, 1u, leader);
+              mma_bf16_ss_pred(tb, da0, db0 + 64u, id128, 1u, leader);
+              mma_bf16_ss_pred(tb + 192u, da1, db1, id64, 1u, leader);
+              mma_bf16_ss_pred(tb, da1, db1 + 64u, id128, 1u, leader);
             }
-        } else if (c == 2u) {          // blocks 2, 3, then (wrapped) block 0
-#pragma unroll
-          for (int tau = 0; tau < SR_TAPS; ++tau)
-#pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-              const uint64_t da = desc_hi64 | (uint64_t)(ab + a_off[tau] + 2u * (uint32_t)ch);
-              const uint64_t db = desc_hi64 | (uint64_t)(w0 + (uint32_t)((tau * 2 + ch) * (SR_WBLOCK >> 4)));
-              mma_bf16_ss_pred(tb + 128u, da, db, id128, 1u, leader);
-              mma_bf16_ss_pred(tb, da, db + 128u, id64, 1u, leader);
-            }
-        } else {                       // block 3, then (wrapped) blocks 0, 1
-#pragma unroll
-          for (int tau = 0; tau < SR_TAPS; ++tau)
-#pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-              const uint64_t da = desc_hi64 | (uint64_t)(ab + a_off[tau] + 2u * (uint32_t)ch);
-              const uint64_t db = desc_hi64 | (uint64_t)(w0 + (uint32_t)((tau * 2 + ch) * (SR_WBLOCK >> 4)));
-              mma_bf16_ss_pred(tb + 192u, da, db, id64, 1u, leader);
-              mma_bf16_ss_pred(tb, da, db + 64u, id128, 1u, leader);
-            }
+          }
         }
         mma_commit_pred(&tfull[slot][q & 3], leader);   // out(t-1) of this slot is complete
+        if (slot == 0) stamp(2, k, 0);
         ++q;
       }
       mma_commit_pred(&empty_bar[stage], leader);       // the stage is free once the MMAs that read it have completed
@@ -207,14 +212,15 @@ __global__ void __launch_bounds__(SR_THREADS, 1) stem_ring_kernel(const __grid_c
     int q = 0;
     for (int k = 0; k < p.nsteps; ++k) {
       const SrStep sd = st[k];
-      if (!(sd.flags & 1)) continue;
+      if (!(sd.flags & SR_ACTIVE)) continue;
       mbar_wait(&tfull[slot][q & 3], (uint32_t)(q >> 2) & 1u);
       tc_fence_after();
-      if (sd.out_pos >= 0) {
+      if (warp == 4) stamp(3, k, 0);
+      if ((sd.flags & SR_STORE) && !(p.skip & 1)) {
         const uint32_t blk = (((uint32_t)(-q) & 3u) + 2u) & 3u;
         const uint32_t ta = tmem + (uint32_t)slot * 256u + blk * 64u + ((uint32_t)(quarter * 32) << 16);
-        const bool store = i < sd.valid;
-        const int64_t P = (int64_t)sd.out_pos + i;
+        const bool store = i < (int)((sd.flags >> 8) & 0xffu);
+        const int64_t P = (int64_t)sd.in_pos - p.g.SL + i;
         const uint32_t vmask = (store && sr_valid(p.g, P)) ? 0xffffffffu : 0u;     // pad positions of the slab are written as zeros
         char* yp = reinterpret_cast<char*>(p.y + P * 8);
         const int64_t yps = p.y_plane_stride * 2;
@@ -236,6 +242,7 @@ __global__ void __launch_bounds__(SR_THREADS, 1) stem_ring_kernel(const __grid_c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[slot][q & 3]);
+      if (warp == 4) stamp(3, k, 1);
       ++q;
     }
   }
@@ -248,7 +255,7 @@ __global__ void __launch_bounds__(SR_THREADS, 1) stem_ring_kernel(const __grid_c
 
 size_t stem_ring_smem_bytes(const StemRingP& p) {
   const size_t r0 = ((size_t)p.units[0] * 16 + 127) & ~size_t(127), r1 = ((size_t)p.units[1] * 16 + 127) & ~size_t(127);
-  return (size_t)SR_WBYTES + 4096 + (size_t)SR_NST * 2 * (r0 + r1) + 1024;
+  return (size_t)SR_WBYTES + 4096 + (size_t)p.nst * 2 * (r0 + r1) + (size_t)2 * p.nsteps * sizeof(SrStep) + 1024;
 }
 
 cudaError_t stem_ring_device_init() {
