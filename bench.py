@@ -495,7 +495,7 @@ def main():
                          "traffic": traffic,
                          "traffic_source": "static: per-launch dram__bytes_read+write from the committed ncu --set full capture (profiles/traffic.json), not measured in this run",
                          "peak_source": f"{peak_src} bf16_tflops (burst: kernels timed in a {ms:.0f} ms region at full clocks)",
-                         "kernel": ("umma_conv_kernel, the launches of the 3-D conv visual encoder (stem + layer1-4: 26.77 of the 31.29 "
+                         "kernel": ("stem_ring_kernel + umma_conv_kernel, the 9 tcgen05 launches of the 3-D conv visual encoder (stem + layer1-4: 26.77 of the 31.29 "
                                     "GFLOP per window); CUDA events on the launch stream"
                                     if args.precision == "bf16" else "conv_f32_kernel (all launches, CUDA events on the launch stream)"),
                          "kernel_ms_per_step": kern_ms / K, "kernel_launches_per_step": kern_n / K,

@@ -672,13 +672,27 @@ int run_stem_ring(const BCtx& c, const PBuf& xs, const PBuf& so) {
     // debug: clock64 stamps of CTA 0, steps 16..47 (producer: stage free / copies issued; MMA slot 0: stage landed / accumulator
     // block free / step issued; epilogue warp 4: accumulator complete / block handed back); prints after a sync
     static long long* dbuf = nullptr;
-    if (!dbuf) cudaMalloc(&dbuf, 4 * 32 * 2 * sizeof(long long));
-    cudaMemsetAsync(dbuf, 0, 4 * 32 * 2 * sizeof(long long), c.st);
+    constexpr int kDbg = 256 + 4 * 160;
+    if (!dbuf) cudaMalloc(&dbuf, kDbg * sizeof(long long));
+    cudaMemsetAsync(dbuf, 0, kDbg * sizeof(long long), c.st);
     p.dbg = dbuf;
     launch_stem_ring(p, it->second.grid, c.st);
-    long long hv[4 * 32 * 2];
+    long long hv[kDbg];
     cudaMemcpyAsync(hv, dbuf, sizeof(hv), cudaMemcpyDeviceToHost, c.st);
     cudaStreamSynchronize(c.st);
+    {
+      long long g0 = INT64_MAX, g1 = 0, cmin = INT64_MAX, cmax = 0, csum = 0, smax = 0;
+      const int nc = std::min(it->second.grid, 160);
+      for (int i = 0; i < nc; ++i) g0 = std::min(g0, hv[256 + 4 * i]);
+      for (int i = 0; i < nc; ++i) {
+        const long long* d = hv + 256 + 4 * i;
+        g1 = std::max(g1, d[1]); smax = std::max(smax, d[0] - g0);
+        const long long cy = d[3] - d[2];
+        cmin = std::min(cmin, cy); cmax = std::max(cmax, cy); csum += cy;
+      }
+      fprintf(stderr, "[sr] %d CTAs x %d steps: kernel span %.1f us (globaltimer), latest CTA start +%.1f us, CTA cycles min %lld avg %lld max %lld\n", nc,
+              p.nsteps, (g1 - g0) / 1e3, smax / 1e3, cmin, csum / nc, cmax);
+    }
     const long long t0 = hv[0];
     for (int k = 0; k < 32; ++k)
       fprintf(stderr, "[sr] step %2d | prod free %7lld issued %7lld | mma landed %7lld blockfree %7lld issued %7lld | epi complete %7lld back %7lld\n", k + 16,

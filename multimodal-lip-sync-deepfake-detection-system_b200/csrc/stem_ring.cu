@@ -103,6 +103,10 @@ __global__ void __launch_bounds__(SR_THREADS, 1) stem_ring_kernel(const __grid_c
   const uint32_t tmem = tmem_base_s;
   const SrStep* const st0 = tab;
   long long* const dbg = (p.dbg && blockIdx.x == 0 && lane == 0) ? p.dbg : nullptr;
+  // (per-CTA span: [256 + 4*cta + {0: globaltimer at start, 1: at end, 2: clock64 at start, 3: at end}])
+  unsigned long long gt0 = 0;
+  long long ck0 = 0;
+  if (p.dbg && tid == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0)); ck0 = clock64(); }
   auto stamp = [&](int role, int k, int which) { if (dbg && k >= 16 && k < 48) dbg[(role * 32 + (k - 16)) * 2 + which] = clock64(); };
 
   if (warp == 0) {
@@ -248,6 +252,12 @@ __global__ void __launch_bounds__(SR_THREADS, 1) stem_ring_kernel(const __grid_c
   }
   tc_fence_before();
   __syncthreads();
+  if (p.dbg && tid == 0 && blockIdx.x < 160) {
+    unsigned long long gt1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+    long long* d = p.dbg + 256 + 4 * blockIdx.x;
+    d[0] = (long long)gt0; d[1] = (long long)gt1; d[2] = ck0; d[3] = clock64();
+  }
   if (warp == 3) tmem_dealloc(tmem, 512);
 }
 

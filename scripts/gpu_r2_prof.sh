@@ -7,7 +7,7 @@ TAG=${1:-r02}
 $T python bench.py --steps 20 --warmup 3 2> gpurun_out/${TAG}_bench.err | tail -n 1 > gpurun_out/${TAG}_bench_n1.json; cut -c1-300 gpurun_out/${TAG}_bench_n1.json
 $T ncu --metrics gpu__time_duration.sum --clock-control none -c 1600 --csv --log-file gpurun_out/${TAG}_launches_bench_py.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-eager-gpu --no-config5 > gpurun_out/${TAG}_ncu_bench.log 2>&1
 $T ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches_traffic_tensorpipe.csv python scripts/run_forward_b64.py > gpurun_out/${TAG}_ncu_traffic.log 2>&1
-LSD_AUDIO_LATE=1 $T ncu --set full --clock-control none --import-source on -k regex:umma_conv_kernel -c 9 -o gpurun_out/${TAG}_prof_umma_encoder -f python scripts/run_forward_b64.py > gpurun_out/${TAG}_ncu_full.log 2>&1
+LSD_AUDIO_LATE=1 $T ncu --set full --clock-control none --import-source on -k "regex:umma_conv_kernel|stem_ring_kernel" -c 9 -o gpurun_out/${TAG}_prof_umma_encoder -f python scripts/run_forward_b64.py > gpurun_out/${TAG}_ncu_full.log 2>&1
 $T ncu --set full --clock-control none --import-source on -k regex:tok_f -c 2 -o gpurun_out/${TAG}_prof_tok -f python scripts/run_forward_b64.py > gpurun_out/${TAG}_ncu_full_tok.log 2>&1
 $T python scripts/audit_configs.py --config 3 > gpurun_out/${TAG}_audit3.json 2>/dev/null
 $T python scripts/audit_configs.py --config 4 > gpurun_out/${TAG}_audit4.json 2>/dev/null; cut -c1-400 gpurun_out/${TAG}_audit4.json
