@@ -274,7 +274,9 @@ void build_plan(const Shapes& s, BPlan& P) {
   const UcGeom g1 = make_geom(Bn, Tn, s.H1, s.W1), g2 = make_geom(Bn, Tn, s.H2, s.W2), g3 = make_geom(Bn, Tn, s.H3, s.W3),
                g4 = make_geom(Bn, Tn, s.H4, s.W4), gd = make_geom(Bn, s.Td, s.H4, s.W4), gh = make_geom(Bn, Tn, s.Hg, s.Wg);
   // bf16 pixel rows of the video and of its per-frame 3->3 "laplacian" conv (h-parity split; 16-byte unit = 2 pixels x 4 ch)
-  const UcGeom gs = make_geom_ex(Bn, Tn, s.Hs, s.Ws, 1, 2, 0, 0, 4);
+  // (row = 2 zero units + W/2 data units: the 2 leading units of the NEXT row are this row's right padding — the 7-tap window of the
+  //  last output reaches one unit past the data — so the row pitch is W/2 + 2, not W/2 + 4: 4 % fewer positions for the stem and hf0)
+  const UcGeom gs = make_geom_ex(Bn, Tn, s.Hs, s.Ws, 1, 2, 0, 0, 2);
   P.addp("xs", 8, 2, gs);
   P.addp("xl", 8, 2, gs);
   P.addp("s_out", 64, 1, gs);    // stem conv output (stem geometry), before the max-pool
