@@ -18,6 +18,10 @@
 using namespace lsd;
 using namespace lsdfw;
 
+// Environment knobs are read once per process (a getenv per knob per launch was ~0.2 ms of host time per forward); the A/B and
+// trace switches that tests and experiments flip inside one process (LSD_TOK_FRONT / LSD_TOK_FUSED, *_TRACE, *_SKIP) stay live.
+#define LSD_ENV(name) ([]() -> const char* { static const char* const v_ = getenv(name); return v_; }())
+
 namespace {
 
 uint16_t f2bf(float f) {
@@ -406,7 +410,7 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
   const int cta_budget = (c.max_ctas > 0 && c.max_ctas < c.h->num_sms) ? c.max_ctas : c.h->num_sms;
   while (p.MT > 1 && ((og.P_total + p.MT * 128 - 1) / (p.MT * 128)) * slices < cta_budget) p.MT /= 2;
   p.nbuf = (p.MT <= mt2 && 2 * p.MT * L.ntile <= 512) ? 2 : 1;  // single buffering only when it buys a larger tile
-  if (const char* e = getenv("LSD_UMMA_NBUF")) {               // tuning knob
+  if (const char* e = LSD_ENV("LSD_UMMA_NBUF")) {               // tuning knob
     const int v = atoi(e);
     if (v == 1) p.nbuf = 1;
     if (v == 2 && 2 * L.ntile <= 512) { p.nbuf = 2; p.MT = std::min(p.MT, mt2); }
@@ -415,7 +419,7 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
   // more than the tensor time of the MMAs it carries for narrow tiles, so the M-tiles of a tap are spread over as many
   // issuing warps as there are M-tiles.
   p.issuers = std::min(p.MT, 4);   // (measured: one issuer for MT = 4 is 6-15 % slower than two on every layer)
-  if (const char* e = getenv("LSD_UMMA_ISSUERS")) { const int v = atoi(e); if (v >= 1 && v <= 4 && v <= p.MT && p.MT % v == 0 && p.MT / v <= 4) p.issuers = v; }   // tuning knob
+  if (const char* e = LSD_ENV("LSD_UMMA_ISSUERS")) { const int v = atoi(e); if (v >= 1 && v <= 4 && v <= p.MT && p.MT % v == 0 && p.MT / v <= 4) p.issuers = v; }   // tuning knob
   uint32_t cols = 32;
   while ((int)cols < p.nbuf * p.MT * L.ntile) cols *= 2;
   p.tmem_cols = cols;
@@ -436,7 +440,7 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
     ug.slice_stride = (int64_t)G.slice_stride;
     int tap_begin = 0;
     int wkb = 40;                                                                        // keep a weight stage <= ~40 KB
-    if (const char* e = getenv("LSD_UMMA_WKB")) wkb = std::max(8, atoi(e));               // tuning knob
+    if (const char* e = LSD_ENV("LSD_UMMA_WKB")) wkb = std::max(8, atoi(e));               // tuning knob
     const int tmax = std::max(1, std::min(UC_MAX_TAPS, (wkb * 1024) / (L.ntile * 32)));
     for (const BBand& b : G.bands) {
       const int nt = (int)b.taps.size();
@@ -485,7 +489,7 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
     bool single_band = true;
     for (int gi = 0; gi < p.ngroups; ++gi) single_band = single_band && (p.groups[gi].band_end - p.groups[gi].band_begin) == 1;
     int stage_kb = single_band ? 64 : 24;
-    if (const char* e = getenv("LSD_UMMA_STAGE_KB")) stage_kb = std::max(8, atoi(e));   // tuning knob
+    if (const char* e = LSD_ENV("LSD_UMMA_STAGE_KB")) stage_kb = std::max(8, atoi(e));   // tuning knob
     p.kpack = std::max(1, std::min(std::min(8, min_k16), (stage_kb * 1024) / (max_a + w_chunk)));
   }
   p.a_stage_bytes = ((uint32_t)(any_toeplitz ? max_a : max_a * p.kpack) + 127u) & ~127u;
@@ -549,7 +553,7 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
   // tile counters of this layer (dynamic tile scheduling, LSD_UMMA_DYNAMIC=1).  Off by default: measured at B=64 it shortens the
   // visual encoder by ~20 us per forward (CTAs delayed by the side stream's kernels take fewer tiles) but every one-tile
   // token-path launch pays the claim + counter re-arm (~1 us each), a net +2 % per step.
-  static const bool dyn_tiles = getenv("LSD_UMMA_DYNAMIC") != nullptr;
+  static const bool dyn_tiles = LSD_ENV("LSD_UMMA_DYNAMIC") != nullptr;
   if (dyn_tiles && p.y_mode != UC_Y_POOL && !p.cta2) {   // (the fused max-pool walks contiguous position ranges)
     constexpr int kMaxLayers = 512;
     if (!c.h->tile_ctr_arena) {
@@ -860,7 +864,7 @@ int pack_bf16_weights(lsd_handle* h, const std::vector<float>& f32_arena) {
   memcpy(h->lapw_host, &f32_arena[h->convs.at("art.lap").w_off], sizeof(h->lapw_host));   // (video_rows takes them by value)
   h->blayers.clear();
   const int vstr[4] = {1, 2, 2, 2};
-  const bool cta2 = !(getenv("LSD_UMMA_CTA2") && atoi(getenv("LSD_UMMA_CTA2")) == 0);
+  const bool cta2 = !(LSD_ENV("LSD_UMMA_CTA2") && atoi(LSD_ENV("LSD_UMMA_CTA2")) == 0);
   for (int l = 1; l <= 4; ++l) {
     const std::string p = "visual_encoder.layer" + std::to_string(l);
     const int s = vstr[l - 1];
@@ -918,9 +922,9 @@ int pack_bf16_weights(lsd_handle* h, const std::vector<float>& f32_arena) {
   // token path GEMMs: 64-column slices so that the small M (B*T rows) still spreads over the SMs; the wide ones (768 / 1024
   // columns) use 128-column slices, which keeps B = 64 (17 M-tiles) inside one wave of CTAs
   int wide = 128;
-  if (const char* e = getenv("LSD_UMMA_NTW")) wide = atoi(e);   // tuning knob
+  if (const char* e = LSD_ENV("LSD_UMMA_NTW")) wide = atoi(e);   // tuning knob
   int narrow = 64;
-  if (const char* e = getenv("LSD_UMMA_NTN")) narrow = atoi(e);   // tuning knob
+  if (const char* e = LSD_ENV("LSD_UMMA_NTN")) narrow = atoi(e);   // tuning knob
   for (const char* k : {"projection.visual_proj", "projection.audio_proj", "cross.v2a.out", "cross.a2v.out",
                         "cross.gate0", "cross.fuse", "temporal.branch_k3", "temporal.branch_k5", "temporal.branch_k7",
                         "temporal.pre_scale_proj"})
@@ -1011,7 +1015,7 @@ static int token_path_bf16(const BCtx& b, const Shapes& s, bool combined = false
   // Independent pieces run side by side on two helper streams (LSD_TOK_SERIAL=1 keeps everything on one stream): the token path is
   // a chain of latency-bound launches, each far too small to fill the SMs it gets.
   lsd_handle* h = b.h;
-  const bool par = getenv("LSD_TOK_SERIAL") == nullptr;
+  const bool par = LSD_ENV("LSD_TOK_SERIAL") == nullptr;
   if (par && !h->tok_stream[0]) {
     for (int i = 0; i < 2; ++i)
       if (cudaStreamCreateWithFlags(&h->tok_stream[i], cudaStreamNonBlocking) != cudaSuccess ||
@@ -1203,14 +1207,14 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   cudaStream_t sst = h->side_stream;
   BCtx bs{h, ws, &P, sst};
   bs.max_ctas = h->num_sms / 2;   // measured at B=64 (re-tuned after the epilogue rewrite): 60 / 74 / 98 / 120 / 148 SMs -> 3.53 / 3.30 / 3.36 / 3.37 / 3.43 ms per step
-  if (const char* e = getenv("LSD_SIDE_CTAS")) bs.max_ctas = atoi(e);   // tuning knob: SMs the side stream may occupy
+  if (const char* e = LSD_ENV("LSD_SIDE_CTAS")) bs.max_ctas = atoi(e);   // tuning knob: SMs the side stream may occupy
   int art_ctas = bs.max_ctas;                                           // ... and during the artifact branch (tail phase)
-  if (const char* e = getenv("LSD_ART_CTAS")) art_ctas = atoi(e);
+  if (const char* e = LSD_ENV("LSD_ART_CTAS")) art_ctas = atoi(e);
   // LSD_MAIN_CTAS (tuning knob): cap the visual-encoder launches and give the audio encoder exactly the SMs they leave free
-  if (const char* e = getenv("LSD_MAIN_CTAS")) { b.max_ctas = atoi(e); bs.max_ctas = h->num_sms - b.max_ctas; }
+  if (const char* e = LSD_ENV("LSD_MAIN_CTAS")) { b.max_ctas = atoi(e); bs.max_ctas = h->num_sms - b.max_ctas; }
   // ---- audio encoder (independent of the video): on the side stream from the very start, so that its latency-bound chain of
   // small launches hides behind the visual encoder instead of heading the tail
-  const bool audio_early = getenv("LSD_AUDIO_LATE") == nullptr;
+  const bool audio_early = LSD_ENV("LSD_AUDIO_LATE") == nullptr;
   // Fused token path (tok_front.cu): the audio tokens' share of it — interpolation to T tokens, then ONE GEMM for
   // [a_int | cross-attention in-projection] (see pack_comb_proj in lsd_api.cu), plus a_emb itself for the aux / stage output —
   // runs right behind the audio encoder, on its stream, long before the visual encoder is done.
@@ -1222,9 +1226,9 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
     RUNC(c, "projection.audio_proj", a_.in = &pb["afeat_p"]; a_.in_lo = &pb["afeat_p_lo"]; a_.og = P.gta; a_.y32 = c.f("a_emb"); a_.y32_ld = 256);
     return 0;
   };
-  g_tl.on = getenv("LSD_TIMELINE") != nullptr;
+  g_tl.on = LSD_ENV("LSD_TIMELINE") != nullptr;
   g_tl.mark(st, "start");
-  const bool audio_after_rows = getenv("LSD_AUDIO_AFTER_ROWS") && atoi(getenv("LSD_AUDIO_AFTER_ROWS")) != 0;   // tuning knob, see below
+  const bool audio_after_rows = LSD_ENV("LSD_AUDIO_AFTER_ROWS") && atoi(LSD_ENV("LSD_AUDIO_AFTER_ROWS")) != 0;   // tuning knob, see below
   if (audio_early && !audio_after_rows) {
     cudaEventRecord(h->ev_start, st);
     cudaStreamWaitEvent(sst, h->ev_start, 0);
@@ -1256,7 +1260,7 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   }
   // The high-frequency branch only needs the laplacian rows: LSD_HF_EARLY=1 (tuning knob) runs it on the side stream right after the
   // audio encoder, next to the visual encoder, instead of in the tail.
-  const bool hf_early = getenv("LSD_HF_EARLY") != nullptr;
+  const bool hf_early = LSD_ENV("LSD_HF_EARLY") != nullptr;
   float* comb = b.f("comb");
   PlanarOut none{nullptr, nullptr, 0, 0, 0, 0};
   const PBuf& hf = pb["hf_f"];
@@ -1275,18 +1279,18 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   // sub-batches cost more than the saved DRAM traffic.  Sub-batch views share the buffers' plane strides; only the first position moves.
   {
     int chunk = 0;
-    if (const char* e = getenv("LSD_STEM_CHUNK")) chunk = atoi(e);
+    if (const char* e = LSD_ENV("LSD_STEM_CHUNK")) chunk = atoi(e);
     // LSD_STEM_POOL_FUSE=1 (with LSD_UMMA_CTA2=0: the fused epilogue is not built for CTA pairs): the max-pool rides in the stem's epilogue (UC_Y_POOL, umma_conv.cu): the 10 MB per window of stem
     // output never leave the SM (DRAM traffic of stem + pool 1.6 GB -> 0.32 GB per 64 windows), same bits as the two-kernel path.
     // Off by default: the stem is bound by the shared-memory read port (N = 64 MMAs), and the pooling pass reads its 3x3
     // neighbourhoods through the same port — measured at B=64: stem 696 k -> 1 102 k cycles (708 k with the pooling reads skipped),
     // which cancels the 0.21 ms of the separate max-pool kernel at burst clocks (2.880 vs 2.875 ms per step; +1.3 % under the
     // power cap, where the saved DRAM traffic buys clock).
-    static const bool fuse_env = getenv("LSD_STEM_POOL_FUSE") && atoi(getenv("LSD_STEM_POOL_FUSE")) != 0;
+    static const bool fuse_env = LSD_ENV("LSD_STEM_POOL_FUSE") && atoi(LSD_ENV("LSD_STEM_POOL_FUSE")) != 0;
     const bool fuse_pool = fuse_env && !h->blayers.at("visual_encoder.stem").halves && !(xs.g.H & 1) && !(xs.g.W & 1) && x1.g.H * 2 == xs.g.H && x1.g.W * 2 == xs.g.W && 2 * xs.g.RW + 2 <= 128;
     // Default: the temporal-ring kernel (stem_ring.cu: the three temporal taps as one N = 192 MMA); LSD_STEM_RING=0 keeps the flat
     // shift-GEMM launch (CTA pairs).  The summation order differs between the two, the bits of a given route do not depend on the batch.
-    static const bool ring_env = !(getenv("LSD_STEM_RING") && atoi(getenv("LSD_STEM_RING")) == 0);
+    static const bool ring_env = !(LSD_ENV("LSD_STEM_RING") && atoi(LSD_ENV("LSD_STEM_RING")) == 0);
     const bool ring = ring_env && h->stem_ring_w_off != 0 && !fuse_env && (chunk <= 0 || chunk >= B) && 128 + 3 * xs.g.RW + 3 <= 640;
     if (ring) {
       if ((rc = run_stem_ring(b, xs, so))) return rc;
@@ -1335,7 +1339,7 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   // output, so they run concurrently with the audio encoder + token path, whose small grids leave most SMs idle.
   cudaEventRecord(h->ev_fork, st);
   cudaStreamWaitEvent(sst, h->ev_fork, 0);
-  const bool skip_art = getenv("LSD_SKIP_ART") != nullptr;   // timing experiment only (garbage logits)
+  const bool skip_art = LSD_ENV("LSD_SKIP_ART") != nullptr;   // timing experiment only (garbage logits)
   bs.max_ctas = art_ctas;
   if (!skip_art) {
   RUNS("art.td0", a_.in = &y4; a_.og = y4.g; a_.act = ACT_RELU; a_.yp = &pb["art_a"]);
@@ -1354,7 +1358,7 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   // temporal-inconsistency convolutions instead of behind them (LSD_HF_SERIAL=1 restores the single side stream): both
   // chains are capped at half of the SMs, and the token path's small grids fit in between.
   if (!hf_early) {
-    const bool hf_par = getenv("LSD_HF_SERIAL") == nullptr;   // (also when batches are pipelined: 10k-window run 19.6k -> 20.5k windows/s)
+    const bool hf_par = LSD_ENV("LSD_HF_SERIAL") == nullptr;   // (also when batches are pipelined: 10k-window run 19.6k -> 20.5k windows/s)
     cudaStream_t hst = sst;
     if (hf_par) {
       if (!h->side2_stream) {
@@ -1366,7 +1370,7 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
     }
     BCtx bh = bs;
     bh.st = hst;
-    if (const char* e = getenv("LSD_HF_CTAS")) bh.max_ctas = atoi(e);
+    if (const char* e = LSD_ENV("LSD_HF_CTAS")) bh.max_ctas = atoi(e);
     RUNC(bh, "art.hf0", a_.in = &xl; a_.og = xl.g; a_.act = ACT_RELU; a_.yp = &hf);
     g_tl.mark(hst, "S:hf0");
     RUNC(bh, "art.hf3", a_.in = &hf; a_.og = hf.g; a_.act = ACT_RELU; a_.yp = &pb["hf_b"]);

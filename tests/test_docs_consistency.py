@@ -18,7 +18,7 @@ def test_readme_knobs_match_sources():
     readme = open(os.path.join(ROOT, "README.md")).read()
     src = _sources()
     documented = set(re.findall(r"LSD_[A-Z0-9_]+", readme))
-    read = set(re.findall(r'getenv\("(LSD_[A-Z0-9_]+)"\)', src))
+    read = set(re.findall(r'(?:getenv|LSD_ENV)\("(LSD_[A-Z0-9_]+)"\)', src))
     assert not sorted(read - documented), f"read by the library but not in README.md: {sorted(read - documented)}"
     stale = sorted(k for k in documented if k not in src)
     assert not stale, f"documented in README.md but gone from the sources: {stale}"
