@@ -601,7 +601,8 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
 }
 
 // Stem through the temporal-ring kernel (stem_ring.cu): xs (pixel rows, 2 parity sets) -> so (plain planar, 64 channels), same geometry.
-int run_stem_ring(const BCtx& c, const PBuf& xs, const PBuf& so) {
+// pool_to != nullptr: the max-pool runs inside the kernel (four pool warps per CTA, see stem_ring.cu) and writes *pool_to.
+int run_stem_ring(const BCtx& c, const PBuf& xs, const PBuf& so, const PBuf* pool_to = nullptr) {
   lsd_handle* h = c.h;
   const UcGeom& g = xs.g;
   if (g.P_total >= ((int64_t)1 << 31) - 4096) return lsd_fail(h, LSD_ERR_SHAPE, "stem: more than 2^31 padded positions in one launch (reduce the batch)");
@@ -626,7 +627,7 @@ int run_stem_ring(const BCtx& c, const PBuf& xs, const PBuf& so) {
   const int64_t G = (int64_t)g.N * CH * T;
   const int budget = (c.max_ctas > 0 && c.max_ctas < h->num_sms) ? c.max_ctas : h->num_sms;
   uint64_t key = 1469598103934665603ull;
-  for (uint64_t v : {(uint64_t)g.N, (uint64_t)T, (uint64_t)g.SL, (uint64_t)g.TS, (uint64_t)g.ot, (uint64_t)budget}) { key ^= v; key *= 1099511628211ull; key ^= key >> 29; }
+  for (uint64_t v : {(uint64_t)g.N, (uint64_t)T, (uint64_t)g.SL, (uint64_t)g.TS, (uint64_t)g.ot, (uint64_t)budget, (uint64_t)(pool_to != nullptr)}) { key ^= v; key *= 1099511628211ull; key ^= key >> 29; }
   auto it = h->ring_tabs.find(key);
   if (it == h->ring_tabs.end()) {
     int grid = budget;
@@ -635,31 +636,64 @@ int run_stem_ring(const BCtx& c, const PBuf& xs, const PBuf& so) {
     if (grid < 1) grid = 1;
     std::vector<std::vector<SrStep>> lists((size_t)2 * grid);
     size_t nsteps = 0;
-    for (int sg = 0; sg < 2 * grid; ++sg) {
-      int64_t g0 = (int64_t)sg * Lr;
-      const int64_t g1 = std::min(G, g0 + Lr);
-      while (g0 < g1) {
-        const int64_t col = g0 / T;
-        const int ta = (int)(g0 % T), tb = (int)std::min<int64_t>(T, ta + (g1 - g0));
-        const int n = (int)(col / CH), sp = (int)(col % CH);
-        const int t_first = std::max(ta - 1, 0);
-        for (int t_in = t_first; t_in <= tb; ++t_in) {
-          SrStep st;
-          st.in_pos = (int32_t)(((int64_t)n * g.TS + t_in + g.ot) * g.SL + (int64_t)sp * 128);
-          const int t_out = t_in - 1;   // the output slab that completes with this step: stored when it belongs to this range
-          st.flags = SR_ACTIVE | (t_in == t_first ? SR_FIRST : 0u) | ((t_out >= ta && t_out < tb) ? SR_STORE : 0u) |
-                     ((uint32_t)std::min(128, g.SL - sp * 128) << 8);
-          lists[sg].push_back(st);
-        }
-        g0 += tb - ta;
+    const int nslots = 2 * grid;
+    // steps of outputs [ta, tb) of column `col` (input slabs max(ta-1, 0) .. tb; the slab completed by a step is stored when it is in range)
+    auto add_range = [&](int sg, int64_t col, int ta, int tb) {
+      const int n = (int)(col / CH), sp = (int)(col % CH);
+      const int t_first = std::max(ta - 1, 0);
+      for (int t_in = t_first; t_in <= tb; ++t_in) {
+        SrStep st;
+        st.in_pos = (int32_t)(((int64_t)n * g.TS + t_in + g.ot) * g.SL + (int64_t)sp * 128);
+        const int t_out = t_in - 1;
+        st.flags = SR_ACTIVE | (t_in == t_first ? SR_FIRST : 0u) | ((t_out >= ta && t_out < tb) ? SR_STORE : 0u) |
+                   ((uint32_t)std::min(128, g.SL - sp * 128) << 8);
+        lists[sg].push_back(st);
       }
-      nsteps = std::max(nsteps, lists[sg].size());
+    };
+    // Inline pooling wants the frames of a window to complete progressively: whole columns are dealt round-robin to the slots in
+    // window-major order (round r: columns r * nslots ..), and only the remaining columns are cut into equal output ranges.
+    const int64_t ncols = (int64_t)g.N * CH;
+    const int64_t rounds = pool_to ? ncols / nslots : 0;
+    std::vector<int> col_round((size_t)ncols, 0);       // step index at which a column's output t completes ~ round * (T + 1) + t
+    for (int64_t r = 0; r < rounds; ++r)
+      for (int sg = 0; sg < nslots; ++sg) { add_range(sg, r * nslots + sg, 0, T); col_round[(size_t)(r * nslots + sg)] = (int)r; }
+    {
+      const int64_t col0 = rounds * nslots, Grem = (ncols - col0) * T;
+      if (pool_to) Lr = (Grem + nslots - 1) / nslots;
+      for (int64_t cc = col0; cc < ncols; ++cc) col_round[(size_t)cc] = (int)rounds;
+      for (int sg = 0; sg < nslots && Lr > 0; ++sg) {
+        int64_t g0 = (int64_t)sg * Lr;
+        const int64_t g1 = std::min(Grem, g0 + Lr);
+        while (g0 < g1) {
+          const int64_t col = col0 + g0 / T;
+          const int ta = (int)(g0 % T), tb = (int)std::min<int64_t>(T, ta + (g1 - g0));
+          add_range(sg, col, ta, tb);
+          g0 += tb - ta;
+        }
+      }
     }
+    for (int sg = 0; sg < nslots; ++sg) nsteps = std::max(nsteps, lists[sg].size());
     std::vector<SrStep> flat((size_t)2 * grid * nsteps);
     memset(flat.data(), 0, flat.size() * sizeof(SrStep));
     for (int sg = 0; sg < 2 * grid; ++sg) std::copy(lists[sg].begin(), lists[sg].end(), flat.begin() + (size_t)sg * nsteps);
     lsd_handle::RingTab tab;
     tab.nsteps = (int)nsteps; tab.grid = grid;
+    if (pool_to) {
+      // frames in expected order of completion (the latest of their columns), dealt round-robin to the CTAs
+      std::vector<std::pair<int64_t, int>> order;
+      for (int n = 0; n < g.N; ++n) {
+        int rmax = 0;
+        for (int sp = 0; sp < CH; ++sp) rmax = std::max(rmax, col_round[(size_t)n * CH + sp]);
+        for (int t = 0; t < T; ++t) order.push_back({(int64_t)rmax * (T + 1) + t, n * T + t});
+      }
+      std::stable_sort(order.begin(), order.end(), [](const std::pair<int64_t, int>& a, const std::pair<int64_t, int>& b) { return a.first < b.first; });
+      tab.nfr = (int)((order.size() + grid - 1) / grid) + 1;
+      std::vector<int> fl((size_t)grid * tab.nfr, -1);
+      for (size_t i = 0; i < order.size(); ++i) fl[(i % grid) * tab.nfr + i / grid] = order[i].second;
+      if (cudaMalloc(&tab.frames, fl.size() * sizeof(int)) != cudaSuccess ||
+          cudaMemcpy(tab.frames, fl.data(), fl.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess)
+        return lsd_fail(h, LSD_ERR_CUDA, "stem: pool list upload failed");
+    }
     // cache miss only (first forward of a shape): blocking copy, visible to every stream afterwards
     if (cudaMalloc(&tab.dev, std::max<size_t>(flat.size(), 1) * sizeof(SrStep)) != cudaSuccess ||
         cudaMemcpy(tab.dev, flat.data(), flat.size() * sizeof(SrStep), cudaMemcpyHostToDevice) != cudaSuccess)
@@ -670,6 +704,22 @@ int run_stem_ring(const BCtx& c, const PBuf& xs, const PBuf& so) {
   p.nsteps = it->second.nsteps;
   p.nst = 6;
   if (const char* e = getenv("LSD_SR_SKIP")) p.skip = atoi(e);   // timing experiments only
+  if (pool_to) {
+    const size_t need = (size_t)g.N * T;
+    if (h->ring_cnt_cap < need) {
+      if (h->ring_cnt) { cudaStreamSynchronize(c.st); cudaFree(h->ring_cnt); h->ring_cnt = nullptr; ++h->generation; }
+      h->ring_cnt_cap = need * 2;
+      if (cudaMalloc(&h->ring_cnt, h->ring_cnt_cap * sizeof(unsigned)) != cudaSuccess) { h->ring_cnt_cap = 0; return lsd_fail(h, LSD_ERR_CUDA, "stem: frame counter allocation failed"); }
+    }
+    cudaMemsetAsync(h->ring_cnt, 0, need * sizeof(unsigned), c.st);
+    p.frame_cnt = h->ring_cnt;
+    p.pool_frames = it->second.frames;
+    p.pool_nfr = it->second.nfr;
+    p.pool_expected = 4 * CH;
+    p.yp = c.org(*pool_to);
+    p.yp_plane_stride = pool_to->plane_stride;
+    p.gp = pool_to->g;
+  }
   while (p.nst > 3 && stem_ring_smem_bytes(p) > 223u * 1024u) --p.nst;    // a long step table (large batches) takes ring stages
   if (stem_ring_smem_bytes(p) > 223u * 1024u) return lsd_fail(h, LSD_ERR_UNSUPPORTED, "stem: batch too large for the ring kernel (LSD_STEM_RING=0)");
   const ConvP& cp = h->convs.at("visual_encoder.stem");
@@ -1292,7 +1342,13 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
     // shift-GEMM launch (CTA pairs).  The summation order differs between the two, the bits of a given route do not depend on the batch.
     static const bool ring_env = !(LSD_ENV("LSD_STEM_RING") && atoi(LSD_ENV("LSD_STEM_RING")) == 0);
     const bool ring = ring_env && h->stem_ring_w_off != 0 && !fuse_env && (chunk <= 0 || chunk >= B) && 128 + 3 * xs.g.RW + 3 <= 640;
-    if (ring) {
+    // LSD_STEM_POOL_INLINE=1: the max-pool done inside the ring kernel by four extra warps per CTA (same bits; measured slower than the
+    // separate launch, see stem_ring.cu)
+    static const bool pool_inline = LSD_ENV("LSD_STEM_POOL_INLINE") && atoi(LSD_ENV("LSD_STEM_POOL_INLINE")) != 0;
+    if (ring && pool_inline && x1.g.H * 2 == xs.g.H && x1.g.W * 2 == xs.g.W) {
+      if ((rc = run_stem_ring(b, xs, so, &x1))) return rc;
+      g_tl.mark(st, "M:stem");
+    } else if (ring) {
       if ((rc = run_stem_ring(b, xs, so))) return rc;
       g_tl.mark(st, "M:stem");
       launch_planar_maxpool(b.org(so), so.plane_stride, so.g, b.org(x1), x1.plane_stride, x1.g, 64, st);

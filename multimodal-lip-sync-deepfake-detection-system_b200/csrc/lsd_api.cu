@@ -105,7 +105,8 @@ extern "C" void lsd_destroy(lsd_handle* h) {
   if (h->tokf_vec) cudaFree(h->tokf_vec);
   if (h->mel_tables) cudaFree(h->mel_tables);
   if (h->prog_arena) cudaFree(h->prog_arena);
-  for (auto& kv : h->ring_tabs) if (kv.second.dev) cudaFree(kv.second.dev);
+  for (auto& kv : h->ring_tabs) { if (kv.second.dev) cudaFree(kv.second.dev); if (kv.second.frames) cudaFree(kv.second.frames); }
+  if (h->ring_cnt) cudaFree(h->ring_cnt);
   if (h->tile_ctr_arena) cudaFree(h->tile_ctr_arena);
   if (h->lm_clips) cudaFree(h->lm_clips);
   if (h->ev_lm_clips) cudaEventDestroy(h->ev_lm_clips);

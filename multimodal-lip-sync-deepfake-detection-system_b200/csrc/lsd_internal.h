@@ -100,7 +100,9 @@ struct lsd_handle {
   std::unordered_map<uint64_t, const void*> prog_cache;
   // temporal-ring stem (stem_ring.cu): packed N = 192 weights inside barena, step tables per (batch, frames, geometry)
   size_t stem_ring_w_off = 0;              // bf16 elements into barena; 0 = not packed
-  struct RingTab { void* dev = nullptr; int nsteps = 0, grid = 0; };
+  struct RingTab { void* dev = nullptr; int nsteps = 0, grid = 0; int* frames = nullptr; int nfr = 0; };   // frames: per-CTA pool lists (inline max-pool)
+  unsigned* ring_cnt = nullptr;            // per-frame completion counters of the inline max-pool (zeroed before every launch)
+  size_t ring_cnt_cap = 0;
   std::unordered_map<uint64_t, RingTab> ring_tabs;
   // tile counters of the tcgen05 launches (dynamic tile scheduling): 16 words per layer name, zero whenever the layer is not
   // running (the last CTA of a launch resets them); launches of one layer are always ordered on one stream

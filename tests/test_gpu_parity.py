@@ -443,10 +443,12 @@ def test_stem_ring_matches_flat_stem(model):
             "out['one'] = m(v[:3, :, :1].contiguous().cuda(), a[:3].cuda()).float().cpu().tolist()\n"
             "print('OUT', json.dumps(out))\n") % root
     res = {}
-    for name, env in {"ring": {}, "flat": {"LSD_STEM_RING": "0"}}.items():
+    for name, env in {"ring": {}, "ring_pool_inline": {"LSD_STEM_POOL_INLINE": "1"}, "flat": {"LSD_STEM_RING": "0"}}.items():
         r = subprocess.run([sys.executable, "-c", code], env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, (name, r.stderr[-2000:])
         res[name] = json.loads([l for l in r.stdout.splitlines() if l.startswith("OUT")][-1][4:])
+    # the max-pool done by the ring kernel's own pool warps (LSD_STEM_POOL_INLINE=1) and by the separate launch give the same bits
+    assert res["ring"] == res["ring_pool_inline"], (res["ring"], res["ring_pool_inline"])
     for k in res["ring"]:
         d = np.abs(np.asarray(res["ring"][k]) - np.asarray(res["flat"][k])).max()
         assert d <= 5e-3, (k, d, res["ring"][k], res["flat"][k])
