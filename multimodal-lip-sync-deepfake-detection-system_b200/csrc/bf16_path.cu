@@ -7,6 +7,7 @@
 #include "token_kernels.cuh"
 #include "umma_conv.cuh"
 #include "stem_ring.cuh"
+#include "conv_ring.cuh"
 
 #include <cuda_fp16.h>
 
@@ -601,28 +602,11 @@ int run_umma(const BCtx& c, const std::string& name, const UArgs& a) {
 }
 
 // Stem through the temporal-ring kernel (stem_ring.cu): xs (pixel rows, 2 parity sets) -> so (plain planar, 64 channels), same geometry.
-// pool_to != nullptr: the max-pool runs inside the kernel (four pool warps per CTA, see stem_ring.cu) and writes *pool_to.
-int run_stem_ring(const BCtx& c, const PBuf& xs, const PBuf& so, const PBuf* pool_to = nullptr) {
+// Step table of the temporal-ring kernels (stem_ring.cu, conv_ring.cu) for geometry g: (column chunk, t) outputs numbered column-major,
+// cut into equal contiguous ranges, one per accumulator slot; cached per (batch, frames, geometry, CTA budget).
+int ring_table(const BCtx& c, const UcGeom& g, bool pool, const lsd_handle::RingTab** out) {
   lsd_handle* h = c.h;
-  const UcGeom& g = xs.g;
-  if (g.P_total >= ((int64_t)1 << 31) - 4096) return lsd_fail(h, LSD_ERR_SHAPE, "stem: more than 2^31 padded positions in one launch (reduce the batch)");
-  const BLayer& L = h->blayers.at("visual_encoder.stem");
-  StemRingP p;
-  memset(&p, 0, sizeof(p));
-  p.xs[0] = c.org(xs);
-  p.xs[1] = c.org(xs) + xs.set_stride;
-  p.w = reinterpret_cast<const __nv_bfloat16*>(h->barena) + h->stem_ring_w_off;
-  p.bias = h->bbias + L.bias_off;
-  p.y = c.org(so);
-  p.y_plane_stride = so.plane_stride;
-  p.g = g;
-  // parity set 0: kernel rows 1, 3, 5 (dh = -1, 0, 1); set 1: rows 0, 2, 4, 6 (dh = -2 .. 1); K chunks are 2-position shifts
-  p.ntap[0] = 3; p.ntap[1] = 4;
-  for (int t = 0; t < 4; ++t) { p.rel[0][t] = t * g.RW; p.rel[1][t] = t * g.RW; }
-  p.start[0] = -g.RW; p.start[1] = -2 * g.RW;
-  p.units[0] = 128 + 2 * g.RW + 3; p.units[1] = 128 + 3 * g.RW + 3;
-  if ((int64_t)(2 * g.RW + 3) * 8 > xs.origin) return lsd_fail(h, LSD_ERR_UNSUPPORTED, "stem: guard zone too small");
-  // step table: (column chunk, t) outputs numbered column-major, cut into equal contiguous ranges, one per accumulator slot
+  const void* pool_to = pool ? (const void*)&g : nullptr;
   const int T = g.T, CH = (g.SL + 127) / 128;
   const int64_t G = (int64_t)g.N * CH * T;
   const int budget = (c.max_ctas > 0 && c.max_ctas < h->num_sms) ? c.max_ctas : h->num_sms;
@@ -700,8 +684,36 @@ int run_stem_ring(const BCtx& c, const PBuf& xs, const PBuf& so, const PBuf* poo
       return lsd_fail(h, LSD_ERR_CUDA, "stem: step table upload failed");
     it = h->ring_tabs.emplace(key, tab).first;
   }
-  p.steps = reinterpret_cast<const SrStep*>(it->second.dev);
-  p.nsteps = it->second.nsteps;
+  *out = &it->second;
+  return 0;
+}
+
+// pool_to != nullptr: the max-pool runs inside the kernel (four pool warps per CTA, see stem_ring.cu) and writes *pool_to.
+int run_stem_ring(const BCtx& c, const PBuf& xs, const PBuf& so, const PBuf* pool_to = nullptr) {
+  lsd_handle* h = c.h;
+  const UcGeom& g = xs.g;
+  if (g.P_total >= ((int64_t)1 << 31) - 4096) return lsd_fail(h, LSD_ERR_SHAPE, "stem: more than 2^31 padded positions in one launch (reduce the batch)");
+  const BLayer& L = h->blayers.at("visual_encoder.stem");
+  StemRingP p;
+  memset(&p, 0, sizeof(p));
+  p.xs[0] = c.org(xs);
+  p.xs[1] = c.org(xs) + xs.set_stride;
+  p.w = reinterpret_cast<const __nv_bfloat16*>(h->barena) + h->stem_ring_w_off;
+  p.bias = h->bbias + L.bias_off;
+  p.y = c.org(so);
+  p.y_plane_stride = so.plane_stride;
+  p.g = g;
+  // parity set 0: kernel rows 1, 3, 5 (dh = -1, 0, 1); set 1: rows 0, 2, 4, 6 (dh = -2 .. 1); K chunks are 2-position shifts
+  p.ntap[0] = 3; p.ntap[1] = 4;
+  for (int t = 0; t < 4; ++t) { p.rel[0][t] = t * g.RW; p.rel[1][t] = t * g.RW; }
+  p.start[0] = -g.RW; p.start[1] = -2 * g.RW;
+  p.units[0] = 128 + 2 * g.RW + 3; p.units[1] = 128 + 3 * g.RW + 3;
+  if ((int64_t)(2 * g.RW + 3) * 8 > xs.origin) return lsd_fail(h, LSD_ERR_UNSUPPORTED, "stem: guard zone too small");
+  const int T = g.T, CH = (g.SL + 127) / 128;
+  const lsd_handle::RingTab* tab = nullptr;
+  if (int trc = ring_table(c, g, pool_to != nullptr, &tab)) return trc;
+  p.steps = reinterpret_cast<const SrStep*>(tab->dev);
+  p.nsteps = tab->nsteps;
   p.nst = 6;
   if (const char* e = getenv("LSD_SR_SKIP")) p.skip = atoi(e);   // timing experiments only
   if (pool_to) {
@@ -713,8 +725,8 @@ int run_stem_ring(const BCtx& c, const PBuf& xs, const PBuf& so, const PBuf* poo
     }
     cudaMemsetAsync(h->ring_cnt, 0, need * sizeof(unsigned), c.st);
     p.frame_cnt = h->ring_cnt;
-    p.pool_frames = it->second.frames;
-    p.pool_nfr = it->second.nfr;
+    p.pool_frames = tab->frames;
+    p.pool_nfr = tab->nfr;
     p.pool_expected = 4 * CH;
     p.yp = c.org(*pool_to);
     p.yp_plane_stride = pool_to->plane_stride;
@@ -732,13 +744,13 @@ int run_stem_ring(const BCtx& c, const PBuf& xs, const PBuf& so, const PBuf* poo
     if (!dbuf) cudaMalloc(&dbuf, kDbg * sizeof(long long));
     cudaMemsetAsync(dbuf, 0, kDbg * sizeof(long long), c.st);
     p.dbg = dbuf;
-    launch_stem_ring(p, it->second.grid, c.st);
+    launch_stem_ring(p, tab->grid, c.st);
     long long hv[kDbg];
     cudaMemcpyAsync(hv, dbuf, sizeof(hv), cudaMemcpyDeviceToHost, c.st);
     cudaStreamSynchronize(c.st);
     {
       long long g0 = INT64_MAX, g1 = 0, cmin = INT64_MAX, cmax = 0, csum = 0, smax = 0;
-      const int nc = std::min(it->second.grid, 160);
+      const int nc = std::min(tab->grid, 160);
       for (int i = 0; i < nc; ++i) g0 = std::min(g0, hv[256 + 4 * i]);
       for (int i = 0; i < nc; ++i) {
         const long long* d = hv + 256 + 4 * i;
@@ -757,7 +769,61 @@ int run_stem_ring(const BCtx& c, const PBuf& xs, const PBuf& so, const PBuf* poo
     h->prof.end(c.st);
     return 0;
   }
-  launch_stem_ring(p, it->second.grid, c.st);
+  launch_stem_ring(p, tab->grid, c.st);
+  h->prof.end(c.st);
+  return 0;
+}
+
+// One 64 -> 64 channel 3x3x3 convolution of layer1 through the temporal-ring kernel (conv_ring.cu): x (plain planar) -> y (plain, or
+// parity-split when y.sets == 4), optional residual (plain), ReLU.  which: 0 = conv1, 1 = conv2.
+int run_conv_ring(const BCtx& c, const std::string& name, int which, const PBuf& x, const PBuf& y, const PBuf* res) {
+  lsd_handle* h = c.h;
+  const UcGeom& g = x.g;
+  if (g.P_total >= ((int64_t)1 << 31) - 4096) return lsd_fail(h, LSD_ERR_SHAPE, "%s: more than 2^31 padded positions in one launch (reduce the batch)", name.c_str());
+  const BLayer& L = h->blayers.at(name);
+  ConvRingP p;
+  memset(&p, 0, sizeof(p));
+  p.x = c.org(x);
+  p.x_plane_stride = x.plane_stride;
+  p.w = reinterpret_cast<const __nv_bfloat16*>(h->barena) + h->l1_ring_w_off[which];
+  p.bias = h->bbias + L.bias_off;
+  if (res) { p.res = c.org(*res); p.res_plane_stride = res->plane_stride; }
+  p.y = c.org(y);
+  p.y_plane_stride = y.plane_stride; p.y_set_stride = y.set_stride;
+  p.y_mode = y.sets == 4 ? UC_Y_PARITY : UC_Y_PLAIN;
+  p.g = g; p.g2 = y.g;
+  p.start = -(g.RW + 1);
+  p.units = 128 + 2 * g.RW + 2;
+  if ((int64_t)(g.RW + 1) * 8 > x.origin) return lsd_fail(h, LSD_ERR_UNSUPPORTED, "%s: guard zone too small", name.c_str());
+  const lsd_handle::RingTab* tab = nullptr;
+  if (int trc = ring_table(c, g, false, &tab)) return trc;
+  p.steps = reinterpret_cast<const SrStep*>(tab->dev);
+  p.nsteps = tab->nsteps;
+  p.nst = 4;
+  if (const char* e = getenv("LSD_SR_SKIP")) p.skip = atoi(e);   // timing experiments only
+  while (p.nst > 1 && conv_ring_smem_bytes(p) > 223u * 1024u) --p.nst;
+  if (conv_ring_smem_bytes(p) > 223u * 1024u) return lsd_fail(h, LSD_ERR_UNSUPPORTED, "%s: rows too wide / batch too large for the ring kernel (LSD_L1_RING=0)", name.c_str());
+  const ConvP& cp = h->convs.at(name);
+  h->prof.begin(c.st, 2.0 * (double)g.N * g.T * g.H * g.W * 64.0 * (double)cp.kt * cp.kh * cp.kw * cp.Cin, 2);
+  if (getenv("LSD_CR_TRACE")) {
+    static long long* dbuf = nullptr;
+    if (!dbuf) cudaMalloc(&dbuf, 4 * 160 * sizeof(long long));
+    cudaMemsetAsync(dbuf, 0, 4 * 160 * sizeof(long long), c.st);
+    p.dbg = dbuf;
+    launch_conv_ring(p, tab->grid, c.st);
+    long long hv[4 * 160];
+    cudaMemcpyAsync(hv, dbuf, sizeof(hv), cudaMemcpyDeviceToHost, c.st);
+    cudaStreamSynchronize(c.st);
+    long long g0 = INT64_MAX, g1 = 0, cmin = INT64_MAX, cmax = 0, csum = 0;
+    const int nc = std::min(tab->grid, 160);
+    for (int i = 0; i < nc; ++i) g0 = std::min(g0, hv[4 * i]);
+    for (int i = 0; i < nc; ++i) { g1 = std::max(g1, hv[4 * i + 1]); const long long cy = hv[4 * i + 3] - hv[4 * i + 2]; cmin = std::min(cmin, cy); cmax = std::max(cmax, cy); csum += cy; }
+    fprintf(stderr, "[cr] %s: %d CTAs x %d steps (nst %d): kernel span %.1f us, CTA cycles min %lld avg %lld max %lld\n", name.c_str(), nc, p.nsteps, p.nst,
+            (g1 - g0) / 1e3, cmin, csum / nc, cmax);
+    h->prof.end(c.st);
+    return 0;
+  }
+  launch_conv_ring(p, tab->grid, c.st);
   h->prof.end(c.st);
   return 0;
 }
@@ -930,6 +996,26 @@ int pack_bf16_weights(lsd_handle* h, const std::vector<float>& f32_arena) {
     P.add(p + ".conv2", p + ".conv2", 1, 1, l == 1 ? "" : p + ".downsample", nt, false, false, pairs);
   }
   P.add_toeplitz("visual_encoder.stem", "visual_encoder.stem", 8, 0, false, cta2);  // 7 taps in w -> 8-pixel window starting at 2*wo-4
+  for (int cv = 0; cv < 2; ++cv) {
+    // layer1's 3x3x3 convolutions for the temporal-ring kernel (conv_ring.cu): per K16 chunk and spatial tap one block
+    // [2 K halves][192 = 3 temporal taps x 64 columns][8]; column block j holds the weights of temporal tap dt = j - 1
+    const ConvP& c = h->convs.at(cv == 0 ? "visual_encoder.layer1.conv1" : "visual_encoder.layer1.conv2");
+    h->l1_ring_w_off[cv] = 0;
+    if (c.kt != 3 || c.kh != 3 || c.kw != 3 || c.Cin != 64 || c.Cout != 64) continue;
+    h->l1_ring_w_off[cv] = P.w.size();
+    const float* W = &f32_arena[c.w_off];
+    const float* sc = c.has_scale ? &f32_arena[c.scale_off] : nullptr;
+    for (int ch = 0; ch < 4; ++ch)
+      for (int b = 0; b < 3; ++b)
+        for (int d = 0; d < 3; ++d)
+          for (int kc = 0; kc < 2; ++kc)
+            for (int n = 0; n < 192; ++n)
+              for (int e = 0; e < 8; ++e) {
+                const int ci = ch * 16 + kc * 8 + e, a = n / 64, co = n % 64;
+                P.w.push_back(f2bf(W[((size_t)((a * 3 + b) * 3 + d) * 64 + ci) * 64 + co] * (sc ? sc[co] : 1.0f)));
+              }
+    while (P.w.size() % 64) P.w.push_back(0);
+  }
   {
     // the same weights for the temporal-ring kernel (stem_ring.cu): per (parity set, kernel row) tap and K chunk one block
     // [2 K halves][192 = 3 temporal taps x 64 columns][8]; column block j holds the weights of temporal tap dt = j - 1
@@ -1378,7 +1464,14 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   }
   g_tl.mark(st, "M:maxpool");
   // ---- residual stages (visual_encoder.py:81-87, 133-152)
-  if ((rc = res_stage_umma(b, "visual_encoder.layer1", x1, pb["l1a"], pb["y1"], false, UC_Y_PARITY))) return rc;
+  {
+    // layer1 (64 -> 64, 24x24 maps): LSD_L1_RING=1 runs its two convolutions through the temporal-ring kernel (conv_ring.cu)
+    static const bool l1_ring = LSD_ENV("LSD_L1_RING") && atoi(LSD_ENV("LSD_L1_RING")) != 0;
+    if (l1_ring && h->l1_ring_w_off[0] && h->l1_ring_w_off[1] && 128 + 2 * x1.g.RW + 2 <= 512) {
+      if ((rc = run_conv_ring(b, "visual_encoder.layer1.conv1", 0, x1, pb["l1a"], nullptr))) return rc;
+      if ((rc = run_conv_ring(b, "visual_encoder.layer1.conv2", 1, pb["l1a"], pb["y1"], &x1))) return rc;
+    } else if ((rc = res_stage_umma(b, "visual_encoder.layer1", x1, pb["l1a"], pb["y1"], false, UC_Y_PARITY))) return rc;
+  }
   g_tl.mark(st, "M:layer1");
   if ((rc = res_stage_umma(b, "visual_encoder.layer2", pb["y1"], pb["l2a"], pb["y2"], true, UC_Y_PARITY))) return rc;
   g_tl.mark(st, "M:layer2");

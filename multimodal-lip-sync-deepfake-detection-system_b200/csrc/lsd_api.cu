@@ -14,6 +14,7 @@
 #include "tok_front.cuh"
 #include "tok_fused.cuh"
 #include "stem_ring.cuh"
+#include "conv_ring.cuh"
 #include "umma_conv.cuh"
 using namespace lsd;
 
@@ -84,6 +85,7 @@ extern "C" int lsd_create(lsd_handle** out, int device) {
     cudaError_t ce = lsd::umma_conv_device_init();
     if (ce == cudaSuccess) ce = lsd::tok_fused_device_init();
     if (ce == cudaSuccess) ce = lsd::stem_ring_device_init();
+    if (ce == cudaSuccess) ce = lsd::conv_ring_device_init();
     if (ce == cudaSuccess) ce = lsd::tok_front_device_init();
     if (ce != cudaSuccess) rc = lsd_fail(h, LSD_ERR_CUDA, "lsd_create: kernel attribute setup: %s", cudaGetErrorString(ce));
   }

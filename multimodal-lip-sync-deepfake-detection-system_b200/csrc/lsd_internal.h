@@ -100,6 +100,7 @@ struct lsd_handle {
   std::unordered_map<uint64_t, const void*> prog_cache;
   // temporal-ring stem (stem_ring.cu): packed N = 192 weights inside barena, step tables per (batch, frames, geometry)
   size_t stem_ring_w_off = 0;              // bf16 elements into barena; 0 = not packed
+  size_t l1_ring_w_off[2] = {0, 0};        // temporal-ring weights of visual_encoder.layer1.conv1 / conv2 (conv_ring.cu); 0 = not packed
   struct RingTab { void* dev = nullptr; int nsteps = 0, grid = 0; int* frames = nullptr; int nfr = 0; };   // frames: per-CTA pool lists (inline max-pool)
   unsigned* ring_cnt = nullptr;            // per-frame completion counters of the inline max-pool (zeroed before every launch)
   size_t ring_cnt_cap = 0;

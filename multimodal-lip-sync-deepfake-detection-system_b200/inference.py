@@ -102,7 +102,7 @@ class Predictor:
         #: how fp32 host windows cross PCIe in `score_batches`: "u8" packs windows whose pixels are exactly k/255 (what
         #: video.py:552-556 produces) to one byte per pixel on the host threads (`lsd_host_pack_u8_exact`: verified value by value,
         #: logits bit-identical), "fp32" copies them as they are, "auto" packs when the first batch qualifies and keeps packing
-        #: unless the pack turns out slower than PCIe would move the fp32 bytes (faster of the last two packs, remembered across calls, see finish())
+        #: unless the pack turns out slower than PCIe would move the fp32 bytes (fastest of the last three packs once four are measured, remembered across calls, see finish())
         if host_transport not in ("auto", "u8", "fp32"):
             raise ValueError(f"host_transport must be 'auto', 'u8' or 'fp32', got {host_transport!r}")
         self.host_transport = host_transport
@@ -244,33 +244,35 @@ class Predictor:
             if self.use_half_precision:
                 vh, ah = vh.half(), ah.half()
             if state["mode"] != "fp32" and vh.dtype == torch.float32 and vh.device.type == "cpu" and vh.is_contiguous() and vh.numel() > 0:
-                if stage[s] is None or stage[s].shape != vh.shape:
+                fresh = stage[s] is None or stage[s].shape != vh.shape
+                if fresh:
                     stage[s] = torch.empty(vh.shape, dtype=torch.uint8).pin_memory()
                 elif k >= NS:
                     ready[s].synchronize()    # the H2D copy that last read this staging buffer (batch k - NS) has finished
                 if L.lsd_host_pack_u8_begin(vh.data_ptr(), stage[s].data_ptr(), vh.numel(), self.host_pack_threads) == _cabi.LSD_OK:
-                    return (k, vh, ah, s)
-            return (k, vh, ah, None)
+                    return (k, vh, ah, s, fresh)
+            return (k, vh, ah, None, False)
 
         def finish(st):
-            k, vh, ah, s = st
+            k, vh, ah, s, fresh = st
             if s is None:
                 return vh, ah, "fp32"
             ok = L.lsd_host_pack_u8_end()
             if ok == 1:
-                if state["mode"] == "auto" and k >= 1:
+                if state["mode"] == "auto" and k >= 1 and not fresh:
                     # "auto" stops packing only when packing is the slower way: a step of the packed pipeline costs about the pack
                     # time + 0.4 ms (packs run one at a time, back to back with the enqueue of the previous batch), a step of the
-                    # fp32 pipeline at least the fp32 bytes at ~52 GB/s of PCIe gen5 x16.  Judged on the faster of the last two
-                    # packs (one slow pack on a busy host must not flip the transport for the rest of the call) and from the second
-                    # batch on (the first also pays for starting the pack threads).  Measured: 16 host threads for one GPU pack a
+                    # fp32 pipeline at least the fp32 bytes at ~52 GB/s of PCIe gen5 x16.  Judged on the fastest of the last three
+                    # packs once four have been measured (a slow pack or two on a busy host must not flip the transport for good),
+                    # not counting the first batch (it also pays for starting the pack threads) nor the first pack into a freshly
+                    # pinned staging buffer.  Measured: 16 host threads for one GPU pack a
                     # 64-window batch in 2.2-3 ms against >= 4.4 ms of copy (14.5k -> 20.6k windows/s); 12 threads per GPU with two
                     # GPUs packing at once need 4.1 ms and the fp32 copy wins by 10 % — the pack moves more host-DRAM bytes than the
                     # copy it saves, so with every GPU of a box fed this way the host memory, not PCIe, is the limit.
                     recent = self.__dict__.setdefault("_pack_ms_hist", [])      # kept across calls: a 3-batch warm-up call decides for the next one
                     recent.append(L.lsd_host_pack_last_ms())
                     del recent[:-8]
-                    if len(recent) >= 2 and min(recent[-2:]) * 1e-3 + 0.4e-3 > vh.numel() * 4 / 52e9:
+                    if len(recent) >= 4 and min(recent[-3:]) * 1e-3 + 0.4e-3 > vh.numel() * 4 / 52e9:
                         state["mode"] = "fp32"
                         self._auto_prefers_fp32 = True     # remembered for the later calls of this predictor
                 return stage[s], ah, "u8 (host-packed, exact)"
