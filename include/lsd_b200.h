@@ -192,6 +192,11 @@ int lsd_host_pack_u8_begin(const float* src, uint8_t* dst, int64_t n, int thread
 int lsd_host_pack_u8_end(void);
 /* Duration of the last finished pack job, first thread started .. last thread done, in milliseconds. */
 double lsd_host_pack_last_ms(void);
+/* The device side of a SPLIT transport: dst[i] = fl(src[i] / 255.0f) for n device bytes, bit for bit what astype(float32) / 255.0
+ * (app/preprocessing/video.py:552-556) gives on the host.  A caller whose host threads pack slower than the GPU scores sends part of
+ * a batch as fp32 over PCIe and the rest packed, expands the packed part next to the fp32 part and scores one fp32 batch.  Asynchronous
+ * on `stream`; n and both pointers must be multiples of 16 (bytes / elements).  Returns LSD_OK or LSD_ERR_ARG / LSD_ERR_CUDA. */
+int lsd_expand_u8(const uint8_t* src, float* dst, int64_t n, void* stream);
 
 /* CUDA-graph support.  lsd_forward may be captured into a CUDA graph (cudaStreamBeginCapture on `stream`; the internal side
  * streams join the capture through events) once a plain call with the same arguments has run: the first call of a shape

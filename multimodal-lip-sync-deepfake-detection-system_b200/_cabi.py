@@ -27,7 +27,7 @@ EXPORTS = [
     "lsd_profile_enable", "lsd_profile_get",
     "lsd_audio_encoder_workspace_bytes", "lsd_audio_encoder", "lsd_token_path_workspace_bytes", "lsd_token_path",
     "lsd_track_motion", "lsd_speech_stats", "lsd_vad_frames", "lsd_frame_energy", "lsd_vad_mask",
-    "lsd_workspace_invalidate", "lsd_planar_stage_read", "lsd_state_generation", "lsd_host_pack_u8_exact", "lsd_host_pack_u8_begin", "lsd_host_pack_u8_end", "lsd_host_pack_last_ms",
+    "lsd_workspace_invalidate", "lsd_planar_stage_read", "lsd_state_generation", "lsd_host_pack_u8_exact", "lsd_host_pack_u8_begin", "lsd_host_pack_u8_end", "lsd_host_pack_last_ms", "lsd_expand_u8",
 ]
 
 
@@ -91,6 +91,7 @@ def lib() -> C.CDLL:
         L.lsd_host_pack_u8_begin.argtypes = [vp, vp, i64, i]; L.lsd_host_pack_u8_begin.restype = i
         L.lsd_host_pack_u8_end.argtypes = []; L.lsd_host_pack_u8_end.restype = i
         L.lsd_host_pack_last_ms.argtypes = []; L.lsd_host_pack_last_ms.restype = C.c_double
+        L.lsd_expand_u8.argtypes = [vp, vp, i64, vp]; L.lsd_expand_u8.restype = i
         L.lsd_planar_stage_read.argtypes = [vp, C.c_char_p, C.c_char_p, vp, vp, i64, i, i, vp]; L.lsd_planar_stage_read.restype = i
         _lib = L
         return L

@@ -1359,7 +1359,8 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
     int rc = 0;
     launch_lerp_tokens_p(c.f("a_feat"), c.f("a_fint"), B, TA, T, 256, pout(c, pb["afint_p"], &pb["afint_p_lo"]), c.st);
     RUNC(c, "cross.acomb", a_.in = &pb["afint_p"]; a_.in_lo = &pb["afint_p_lo"]; a_.og = P.gt; a_.y32 = c.f("acomb"); a_.y32_ld = 1024);
-    RUNC(c, "projection.audio_proj", a_.in = &pb["afeat_p"]; a_.in_lo = &pb["afeat_p_lo"]; a_.og = P.gta; a_.y32 = c.f("a_emb"); a_.y32_ld = 256);
+    // a_emb itself (TA tokens per window) is an aux output only: the token path consumes the interpolated rows above
+    if (aux && aux->audio_tokens) RUNC(c, "projection.audio_proj", a_.in = &pb["afeat_p"]; a_.in_lo = &pb["afeat_p_lo"]; a_.og = P.gta; a_.y32 = c.f("a_emb"); a_.y32_ld = 256);
     return 0;
   };
   g_tl.on = LSD_ENV("LSD_TIMELINE") != nullptr;
@@ -1558,11 +1559,9 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   }
   g_tl.mark(st, "T:proj");
   if ((rc = token_path_bf16(b, s, tcomb))) return rc;
-  if (tcomb) launch_copy_rows(b.f("vcomb"), 1024, b.f("v_emb"), 256, B * T, 256, st);   // v_emb as a contiguous stage / aux tensor
   float* tok = b.f("tok");
   g_tl.mark(st, "T:tokens");
-  // cls = tok[:,0]: no final norm (temporal.py:110-111)
-  launch_copy_rows(tok, (int64_t)NT * 256, comb, 448, B, 256, st);
+  // cls = tok[:,0]: no final norm (temporal.py:110-111); the head reads the CLS rows in place
   cudaStreamWaitEvent(st, h->ev_join, 0);   // artifact features (comb[:, 256:448]) are complete
   // ---- artifact fusion MLP + classification head, fused, fp32 (artifact_detector.py:142-147,180-181; classifier.py:14-34)
   HeadW hw;
@@ -1571,12 +1570,15 @@ static int forward_bf16_impl(lsd_handle* h, const Shapes& s, float* logits, cons
   hw.w0 = cw("art.fuse0"); hw.b0 = cb("art.fuse0"); hw.w2 = cw("art.fuse2"); hw.b2 = cb("art.fuse2");
   hw.wc = cw("head.fc0"); hw.bc = cb("head.fc0");
   hw.lng = b.W("head.ln.w"); hw.lnb = b.W("head.ln.b"); hw.wo = b.W("head.out.w"); hw.bo = b.W("head.out.b");
-  launch_head(comb, hw, logits, B, st);
+  launch_head(tok, (int64_t)NT * 256, comb, hw, logits, B, st);
   g_tl.mark(st, "T:head");
   g_tl.dump();
   if (aux) {
     const size_t tb = (size_t)B * T * 256 * sizeof(float);
-    if (aux->visual_tokens) cudaMemcpyAsync(aux->visual_tokens, b.f("v_emb"), tb, cudaMemcpyDeviceToDevice, st);
+    if (aux->visual_tokens) {
+      if (tcomb) launch_copy_rows(b.f("vcomb"), 1024, aux->visual_tokens, 256, B * T, 256, st);   // v_emb = the first 256 columns of the merged projection
+      else cudaMemcpyAsync(aux->visual_tokens, b.f("v_emb"), tb, cudaMemcpyDeviceToDevice, st);
+    }
     if (aux->audio_tokens) cudaMemcpyAsync(aux->audio_tokens, b.f("a_emb"), (size_t)B * TA * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st);
     if (aux->fused_tokens) cudaMemcpyAsync(aux->fused_tokens, b.f("fused"), tb, cudaMemcpyDeviceToDevice, st);
     if (aux->cls_output) launch_copy_rows(tok, (int64_t)NT * 256, aux->cls_output, 256, B, 256, st);

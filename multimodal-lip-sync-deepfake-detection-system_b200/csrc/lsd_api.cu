@@ -526,6 +526,26 @@ extern "C" int lsd_score_windows(lsd_handle* h, const uint8_t* track, int n_fram
 extern "C" size_t lsd_audio_encoder_workspace_bytes(lsd_handle* h, int B, int F, int Ta) {
   return h ? audio_encoder_bf16_bytes(h, B, F, Ta) : 0;
 }
+// dst[i] = fl(src[i] / 255.0f): IEEE division, the reference's own operation (video.py:552-556); 16 values per thread
+__global__ void expand_u8_kernel(const uint4* __restrict__ src, float4* __restrict__ dst, int64_t n16) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n16) return;
+  const uint4 v = src[i];
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    dst[4 * i + q] = make_float4(__fdiv_rn((float)(w[q] & 0xffu), 255.0f), __fdiv_rn((float)((w[q] >> 8) & 0xffu), 255.0f),
+                                 __fdiv_rn((float)((w[q] >> 16) & 0xffu), 255.0f), __fdiv_rn((float)(w[q] >> 24), 255.0f));
+}
+extern "C" int lsd_expand_u8(const uint8_t* src, float* dst, int64_t n, void* stream) {
+  if (n < 0 || (n > 0 && (!src || !dst)) || (n & 15) || (reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15)) return LSD_ERR_ARG;
+  if (n == 0) return LSD_OK;
+  const int64_t n16 = n / 16;
+  expand_u8_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<float4*>(dst), n16);
+  lsd::count_launch();
+  return cudaGetLastError() == cudaSuccess ? LSD_OK : LSD_ERR_CUDA;
+}
+
 extern "C" int lsd_audio_encoder(lsd_handle* h, const void* audio, int audio_dtype, int B, int F, int Ta, float* feats_out,
                                  void* workspace, size_t workspace_bytes, void* stream) {
   if (!h) return LSD_ERR_ARG;

@@ -75,6 +75,7 @@ class Predictor:
         graph_max_batch: int = 8,
         host_transport: str = "auto",
         host_pack_threads: Optional[int] = None,
+        host_split: bool = False,
     ) -> None:
         self.model = model
         self.device = device if device is not None else (model._device() if model is not None else torch.device("cpu"))
@@ -106,6 +107,11 @@ class Predictor:
         if host_transport not in ("auto", "u8", "fp32"):
             raise ValueError(f"host_transport must be 'auto', 'u8' or 'fp32', got {host_transport!r}")
         self.host_transport = host_transport
+        #: split transport of `score_batches` (opt-in): part of every batch crosses PCIe as fp32 while the host threads pack the rest
+        #: (True: the share follows the measured pack rate; a float in (0, 1) fixes it; logits unchanged, `lsd_expand_u8`).  Off by
+        #: default: measured slower than packing whole batches on one GPU (17.1 k against 22 k windows/s end to end, and unstable —
+        #: the fp32 part and the pack threads read the same host DRAM at once).
+        self.host_split = host_split if isinstance(host_split, float) else bool(host_split)
         if host_pack_threads is None:
             local_ws = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
             try:
@@ -236,6 +242,16 @@ class Predictor:
         if state["mode"] == "auto" and getattr(self, "_auto_prefers_fp32", False):
             state["mode"] = "fp32"       # an earlier call on this predictor measured the pack slower than the copy (busy host / several GPUs)
 
+        def split_count(B):
+            """Windows of a batch that cross PCIe as fp32 while the host threads pack the rest (split transport): a batch costs the
+            pipeline max(PCIe time, pack time), so the fp32 share f equalises  f*t32 + (1-f)*t32/4  and  (1-f)*T + 0.33 ms  (t32: the
+            fp32 bytes of the whole batch at ~52 GB/s, T: the measured pack time of a whole batch).  0 until a pack has been measured."""
+            if not self.host_split or B < 2:
+                return 0
+            if isinstance(self.host_split, float):
+                return int(round(self.host_split * B))
+            return int(round(getattr(self, "_split_frac", 0.0) * B)) if B >= 8 else 0
+
         def start(k, vh, ah):
             """Host side of batch k, first half: starts the uint8 pack on the library's host threads (the call returns at once;
             this thread goes on to enqueue batch k-1).  No Python helper thread: a second Python thread that makes CUDA calls was
@@ -249,35 +265,52 @@ class Predictor:
                     stage[s] = torch.empty(vh.shape, dtype=torch.uint8).pin_memory()
                 elif k >= NS:
                     ready[s].synchronize()    # the H2D copy that last read this staging buffer (batch k - NS) has finished
-                if L.lsd_host_pack_u8_begin(vh.data_ptr(), stage[s].data_ptr(), vh.numel(), self.host_pack_threads) == _cabi.LSD_OK:
-                    return (k, vh, ah, s, fresh)
-            return (k, vh, ah, None, False)
+                B = int(vh.shape[0])
+                wbytes = vh[0].numel()
+                na = min(split_count(B), B - 1) if wbytes % 16 == 0 else 0       # (lsd_expand_u8 works in 16-byte pieces)
+                if L.lsd_host_pack_u8_begin(vh.data_ptr() + 4 * na * wbytes, stage[s].data_ptr(), (B - na) * wbytes, self.host_pack_threads) == _cabi.LSD_OK:
+                    return (k, vh, ah, s, fresh, na)
+            return (k, vh, ah, None, False, 0)
 
         def finish(st):
-            k, vh, ah, s, fresh = st
+            """-> (video to ship, audio, transport label, na): na > 0 = split transport (video is then (fp32 windows, packed rest))."""
+            k, vh, ah, s, fresh, na = st
             if s is None:
-                return vh, ah, "fp32"
+                return vh, ah, "fp32", 0
             ok = L.lsd_host_pack_u8_end()
             if ok == 1:
-                if state["mode"] == "auto" and k >= 1 and not fresh:
-                    # "auto" stops packing only when packing is the slower way: a step of the packed pipeline costs about the pack
-                    # time + 0.4 ms (packs run one at a time, back to back with the enqueue of the previous batch), a step of the
-                    # fp32 pipeline at least the fp32 bytes at ~52 GB/s of PCIe gen5 x16.  Judged on the fastest of the last three
-                    # packs once four have been measured (a slow pack or two on a busy host must not flip the transport for good),
-                    # not counting the first batch (it also pays for starting the pack threads) nor the first pack into a freshly
-                    # pinned staging buffer.  Measured: 16 host threads for one GPU pack a
-                    # 64-window batch in 2.2-3 ms against >= 4.4 ms of copy (14.5k -> 20.6k windows/s); 12 threads per GPU with two
-                    # GPUs packing at once need 4.1 ms and the fp32 copy wins by 10 % — the pack moves more host-DRAM bytes than the
-                    # copy it saves, so with every GPU of a box fed this way the host memory, not PCIe, is the limit.
-                    recent = self.__dict__.setdefault("_pack_ms_hist", [])      # kept across calls: a 3-batch warm-up call decides for the next one
-                    recent.append(L.lsd_host_pack_last_ms())
-                    del recent[:-8]
-                    if len(recent) >= 4 and min(recent[-3:]) * 1e-3 + 0.4e-3 > vh.numel() * 4 / 52e9:
-                        state["mode"] = "fp32"
-                        self._auto_prefers_fp32 = True     # remembered for the later calls of this predictor
-                return stage[s], ah, "u8 (host-packed, exact)"
+                B = int(vh.shape[0])
+                if k >= 1 and not fresh:
+                    # pack time of a whole batch, from this (possibly partial) pack
+                    T = L.lsd_host_pack_last_ms() * 1e-3 * B / max(1, B - na)
+                    t32 = vh.numel() * 4 / 52e9
+                    if self.host_split:
+                        f = (T + 0.33e-3 - t32 / 4) / (0.75 * t32 + T)
+                        f = min(0.6, max(0.0, f))
+                        if f < 0.05:
+                            f = 0.0
+                        self._split_frac = f if not hasattr(self, "_split_frac") else 0.5 * self._split_frac + 0.5 * f
+                    if state["mode"] == "auto":
+                        # "auto" stops packing only when packing is the slower way even so: a step of the packed pipeline costs about
+                        # the pack time + 0.4 ms (packs run one at a time, back to back with the enqueue of the previous batch), a step
+                        # of the fp32 pipeline at least the fp32 bytes at ~52 GB/s of PCIe gen5 x16.  Judged on the fastest of the last
+                        # three whole-batch pack times once four have been measured (a slow pack or two on a busy host must not flip the
+                        # transport for good), not counting the first batch (it also pays for starting the pack threads) nor the first
+                        # pack into a freshly pinned staging buffer.  Measured: 16 host threads for one GPU pack a 64-window batch in
+                        # 2.2-3.5 ms against >= 4.4 ms of copy; 12 threads per GPU with two GPUs packing at once need 4.1 ms and the
+                        # fp32 copy wins by 10 % — the pack moves more host-DRAM bytes than the copy it saves, so with every GPU of a
+                        # box fed this way the host memory, not PCIe, is the limit.
+                        recent = self.__dict__.setdefault("_pack_ms_hist", [])      # kept across calls
+                        recent.append(T * 1e3)
+                        del recent[:-8]
+                        if len(recent) >= 4 and min(recent[-3:]) * 1e-3 + 0.4e-3 > t32 and not self.host_split:
+                            state["mode"] = "fp32"
+                            self._auto_prefers_fp32 = True     # remembered for the later calls of this predictor
+                if na > 0:
+                    return (vh, stage[s]), ah, "u8 + fp32 split (host-packed part exact)", na
+                return stage[s], ah, "u8 (host-packed, exact)", 0
             state["mode"] = "fp32"               # not k/255 data: stop checking for the rest of this call
-            return vh, ah, "fp32"
+            return vh, ah, "fp32", 0
 
         it = iter(batches)
         first = next(it, None)
@@ -285,24 +318,52 @@ class Predictor:
             return outs
         st = start(0, *first)
         k = 0
+        split_slots = getattr(self, "_split_slots", None)
+        if split_slots is None:
+            split_slots = self._split_slots = [None] * NS
         try:
             while st is not None:
-                vh, ah, transport = finish(st)                                  # batch k is packed (or goes as it is)
+                vh, ah, transport, na = finish(st)                              # batch k is packed (or goes as it is)
                 nxt = next(it, None)
                 st = start(k + 1, *nxt) if nxt is not None else None            # batch k+1 is being packed while batch k is enqueued
                 s = k % NS
                 self.last_transport = transport        # of the last batch shipped
-                self.last_h2d_bytes_per_batch = vh.numel() * vh.element_size() + ah.numel() * ah.element_size()
-                if slots[s] is None or slots[s][0].shape != vh.shape or slots[s][0].dtype != vh.dtype or slots[s][1].shape != ah.shape:
-                    slots[s] = (torch.empty(vh.shape, dtype=vh.dtype, device=dev), torch.empty(ah.shape, dtype=ah.dtype, device=dev))
-                    free[s].record(comp)
-                with torch.cuda.stream(copy):
-                    copy.wait_event(free[s])          # the forward that last read this slot has finished
-                    slots[s][0].copy_(vh, non_blocking=True)
-                    slots[s][1].copy_(ah, non_blocking=True)
-                    ready[s].record(copy)
-                comp.wait_event(ready[s])
-                logits = m(slots[s][0], slots[s][1])
+                if na > 0:
+                    # split transport: windows [0, na) cross PCIe as fp32, the rest packed; the packed part is expanded next to the
+                    # fp32 part on the device (lsd_expand_u8: the reference's own astype(float32) / 255.0, bit for bit) and ONE fp32
+                    # batch is scored
+                    v32, v8 = vh
+                    B = int(v32.shape[0])
+                    wbytes = v32[0].numel()
+                    self.last_h2d_bytes_per_batch = 4 * na * wbytes + (B - na) * wbytes + ah.numel() * ah.element_size()
+                    ss = split_slots[s]
+                    if ss is None or ss[0].shape != v32.shape or ss[2].shape != ah.shape:
+                        ss = split_slots[s] = (torch.empty(v32.shape, dtype=torch.float32, device=dev), torch.empty(v32.shape, dtype=torch.uint8, device=dev),
+                                               torch.empty(ah.shape, dtype=ah.dtype, device=dev))
+                        free[s].record(comp)
+                    with torch.cuda.stream(copy):
+                        copy.wait_event(free[s])          # the forward that last read this slot has finished
+                        ss[0][:na].copy_(v32[:na], non_blocking=True)
+                        ss[1][:B - na].copy_(v8[:B - na], non_blocking=True)
+                        ss[2].copy_(ah, non_blocking=True)
+                        ready[s].record(copy)
+                    comp.wait_event(ready[s])
+                    rc = L.lsd_expand_u8(ss[1].data_ptr(), ss[0].data_ptr() + 4 * na * wbytes, (B - na) * wbytes, comp.cuda_stream)
+                    if rc != _cabi.LSD_OK:
+                        raise RuntimeError(f"lsd_expand_u8 failed ({rc})")
+                    logits = m(ss[0], ss[2])
+                else:
+                    self.last_h2d_bytes_per_batch = vh.numel() * vh.element_size() + ah.numel() * ah.element_size()
+                    if slots[s] is None or slots[s][0].shape != vh.shape or slots[s][0].dtype != vh.dtype or slots[s][1].shape != ah.shape:
+                        slots[s] = (torch.empty(vh.shape, dtype=vh.dtype, device=dev), torch.empty(ah.shape, dtype=ah.dtype, device=dev))
+                        free[s].record(comp)
+                    with torch.cuda.stream(copy):
+                        copy.wait_event(free[s])          # the forward that last read this slot has finished
+                        slots[s][0].copy_(vh, non_blocking=True)
+                        slots[s][1].copy_(ah, non_blocking=True)
+                        ready[s].record(copy)
+                    comp.wait_event(ready[s])
+                    logits = m(slots[s][0], slots[s][1])
                 free[s].record(comp)
                 # logits come back through one pinned block per 256 batches (a pinned allocation per step costs ~0.1-0.4 ms)
                 nb = int(logits.numel())

@@ -627,6 +627,12 @@ def test_score_batches_u8_transport_bitwise(model):
     assert p_f32.last_transport == "fp32"
     for r, x, y in zip(ref, out_u8, out_f32):
         assert torch.equal(r, x) and torch.equal(r, y)
+    # split transport (half of every batch as fp32 over PCIe, the rest packed and expanded on the device by lsd_expand_u8): same bits
+    p_split = lb.Predictor(model, host_transport="u8", host_split=0.5)
+    out_split = [t.clone() for t in p_split.score_batches(batches)]
+    assert "split" in p_split.last_transport and p_split.last_h2d_bytes_per_batch == (4 + 1) * 3 * 32 * 96 * 96 + 2 * 80 * 128 * 4
+    for r, x in zip(ref, out_split):
+        assert torch.equal(r, x)
     # not k/255 data: detected, shipped as fp32, still identical to the plain forward
     v2 = v.clone()
     v2[5, 1, 7, 3, 2] = torch.nextafter(v2[5, 1, 7, 3, 2], torch.tensor(2.0))
