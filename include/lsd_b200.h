@@ -185,12 +185,14 @@ const char* lsd_stage_name(lsd_handle* h, int i);
  * normalisation reproduces the fp32 values bit for bit), 0 when some value did not (dst undefined: ship the fp32 values),
  * LSD_ERR_ARG on null pointers. */
 int lsd_host_pack_u8_exact(const float* src, uint8_t* dst, int64_t n, int threads);
-/* The same in two steps, for callers that enqueue GPU work for batch k while the host threads pack batch k+1: _begin starts the
- * job on `threads` pool threads and returns LSD_OK at once (LSD_ERR_ARG: bad arguments, or a job is already in flight — one at a
- * time per process); _end waits for it and returns 1 / 0 like lsd_host_pack_u8_exact.  src and dst must stay valid in between. */
+/* The same in two steps, for callers that enqueue GPU work for batch k while the host threads pack batches k+1 and k+2: _begin
+ * queues the job for `threads` pool threads and returns LSD_OK at once (LSD_ERR_ARG: bad arguments, or two jobs are already in
+ * flight — jobs run in submission order, the threads go from one straight on to the next); _end waits for the OLDEST job in flight
+ * and returns 1 / 0 like lsd_host_pack_u8_exact (0 also when none is in flight).  src and dst must stay valid in between.
+ * lsd_host_pack_u8_exact returns LSD_ERR_ARG while a _begin job is in flight. */
 int lsd_host_pack_u8_begin(const float* src, uint8_t* dst, int64_t n, int threads);
 int lsd_host_pack_u8_end(void);
-/* Duration of the last finished pack job, first thread started .. last thread done, in milliseconds. */
+/* Duration of the pack job the last _end (or _exact) returned, first thread started .. last thread done, in milliseconds. */
 double lsd_host_pack_last_ms(void);
 /* The device side of a SPLIT transport: dst[i] = fl(src[i] / 255.0f) for n device bytes, bit for bit what astype(float32) / 255.0
  * (app/preprocessing/video.py:552-556) gives on the host.  A caller whose host threads pack slower than the GPU scores sends part of

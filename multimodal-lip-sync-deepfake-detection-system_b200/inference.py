@@ -278,6 +278,8 @@ class Predictor:
             if s is None:
                 return vh, ah, "fp32", 0
             ok = L.lsd_host_pack_u8_end()
+            if state["mode"] == "fp32":          # the transport was given up while this batch's pack was queued: drained, shipped as fp32
+                return vh, ah, "fp32", 0
             if ok == 1:
                 B = int(vh.shape[0])
                 if k >= 1 and not fresh:
@@ -292,18 +294,19 @@ class Predictor:
                         self._split_frac = f if not hasattr(self, "_split_frac") else 0.5 * self._split_frac + 0.5 * f
                     if state["mode"] == "auto":
                         # "auto" stops packing only when packing is the slower way even so: a step of the packed pipeline costs about
-                        # the pack time + 0.4 ms (packs run one at a time, back to back with the enqueue of the previous batch), a step
-                        # of the fp32 pipeline at least the fp32 bytes at ~52 GB/s of PCIe gen5 x16.  Judged on the fastest of the last
-                        # three whole-batch pack times once four have been measured (a slow pack or two on a busy host must not flip the
-                        # transport for good), not counting the first batch (it also pays for starting the pack threads) nor the first
-                        # pack into a freshly pinned staging buffer.  Measured: 16 host threads for one GPU pack a 64-window batch in
-                        # 2.2-3.5 ms against >= 4.4 ms of copy; 12 threads per GPU with two GPUs packing at once need 4.1 ms and the
-                        # fp32 copy wins by 10 % — the pack moves more host-DRAM bytes than the copy it saves, so with every GPU of a
-                        # box fed this way the host memory, not PCIe, is the limit.
+                        # the pack time (+ 0.1 ms: the pack jobs of consecutive batches are queued in the library and run back to back),
+                        # a step of the fp32 pipeline at least the fp32 bytes at ~52 GB/s of PCIe gen5 x16.  Judged on the fastest of the
+                        # last three whole-batch pack times once four have been measured (a slow pack or two on a busy host must not
+                        # flip the transport for good), not counting the first batch (it also pays for starting the pack threads) nor
+                        # the first pack into a freshly pinned staging buffer.  Measured (AVX-512 loop, non-temporal stores): 16 host
+                        # threads for one GPU pack a 64-window batch in 2.2 ms against >= 4.4 ms of copy; 12 threads per GPU with two
+                        # GPUs packing at once need 3.3 ms (4.3 - 4.7 ms per step for the fp32 copy there); with 4 threads per GPU
+                        # (eight GPUs fed at once) the pack is the slower way — it moves more host-DRAM bytes than the copy it saves,
+                        # and with every GPU of a box fed this way the host memory, not PCIe, is the limit.
                         recent = self.__dict__.setdefault("_pack_ms_hist", [])      # kept across calls
                         recent.append(T * 1e3)
                         del recent[:-8]
-                        if len(recent) >= 4 and min(recent[-3:]) * 1e-3 + 0.4e-3 > t32 and not self.host_split:
+                        if len(recent) >= 4 and min(recent[-3:]) * 1e-3 + 0.1e-3 > t32 and not self.host_split:
                             state["mode"] = "fp32"
                             self._auto_prefers_fp32 = True     # remembered for the later calls of this predictor
                 if na > 0:
@@ -313,19 +316,26 @@ class Predictor:
             return vh, ah, "fp32", 0
 
         it = iter(batches)
-        first = next(it, None)
-        if first is None:
-            return outs
-        st = start(0, *first)
+        pend = []                       # host side started, not yet shipped: batches k, k+1 (the library queues two pack jobs)
+        started = [0]
+
+        def fill():
+            while len(pend) < 2:
+                nxt = next(it, None)
+                if nxt is None:
+                    return
+                pend.append(start(started[0], *nxt))
+                started[0] += 1
+
+        fill()
         k = 0
         split_slots = getattr(self, "_split_slots", None)
         if split_slots is None:
             split_slots = self._split_slots = [None] * NS
         try:
-            while st is not None:
-                vh, ah, transport, na = finish(st)                              # batch k is packed (or goes as it is)
-                nxt = next(it, None)
-                st = start(k + 1, *nxt) if nxt is not None else None            # batch k+1 is being packed while batch k is enqueued
+            while pend:
+                vh, ah, transport, na = finish(pend.pop(0))                     # batch k is packed (or goes as it is)
+                fill()          # batch k+1 is being packed while batch k is enqueued, the pack of batch k+2 is queued behind it
                 s = k % NS
                 self.last_transport = transport        # of the last batch shipped
                 if na > 0:
@@ -376,8 +386,9 @@ class Predictor:
                 outs.append(host)
                 k += 1
         except BaseException:
-            if st is not None and st[3] is not None:
-                L.lsd_host_pack_u8_end()         # never leave a pack job in flight behind an error
+            for st in pend:
+                if st[3] is not None:
+                    L.lsd_host_pack_u8_end()     # never leave a pack job in flight behind an error
             raise
         comp.synchronize()
         return outs

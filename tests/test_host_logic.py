@@ -192,6 +192,21 @@ def test_host_pack_u8_exact():
                 y[pos] = bad
                 assert L.lsd_host_pack_u8_exact(y.ctypes.data, d.ctypes.data, n, threads) == 0, (n, bad, pos)
     assert L.lsd_host_pack_u8_exact(None, None, 5, 1) == _cabi.LSD_ERR_ARG
+    # destination alignment selects the store flavour of the AVX-512 loop (64-byte aligned: non-temporal): both give the same bytes,
+    # and a misaligned source is fine
+    n = (1 << 18) + 200
+    k = rng.integers(0, 256, n, dtype=np.uint8)
+    xbuf = np.zeros(n + 16, np.float32)
+    dbuf = np.zeros(n + 128, np.uint8)
+    a0 = (-dbuf.ctypes.data) % 64
+    for soff in (0, 3):
+        xs = xbuf[soff:soff + n]
+        xs[:] = k.astype(np.float32) / 255.0
+        for doff in (a0, a0 + 1, a0 + 32):
+            dbuf[:] = 9
+            d = dbuf[doff:doff + n]
+            assert L.lsd_host_pack_u8_exact(xs.ctypes.data, d.ctypes.data, n, 2) == 1
+            assert np.array_equal(d, k) and (dbuf[:doff] == 9).all() and (dbuf[doff + n:] == 9).all()
 
 
 def test_host_pack_u8_begin_end():
@@ -205,11 +220,27 @@ def test_host_pack_u8_begin_end():
     x = k.astype(np.float32) / 255.0
     d = np.zeros(n, np.uint8)
     assert L.lsd_host_pack_u8_end() == 0                                               # nothing in flight
+    # two jobs may be in flight (the scoring loop queues the pack of batch k+2 behind the one of batch k+1); _end returns them in order
+    k2 = rng.integers(0, 256, n, dtype=np.uint8)
+    x2 = k2.astype(np.float32) / 255.0
+    x2[5] = 0.3                                                                        # the second job fails, the first does not
+    d2 = np.zeros(n, np.uint8)
     assert L.lsd_host_pack_u8_begin(x.ctypes.data, d.ctypes.data, n, 3) == _cabi.LSD_OK
-    assert L.lsd_host_pack_u8_begin(x.ctypes.data, d.ctypes.data, n, 3) == _cabi.LSD_ERR_ARG      # busy
+    assert L.lsd_host_pack_u8_begin(x2.ctypes.data, d2.ctypes.data, n, 2) == _cabi.LSD_OK
+    assert L.lsd_host_pack_u8_begin(x.ctypes.data, d.ctypes.data, n, 3) == _cabi.LSD_ERR_ARG      # two in flight: busy
     assert L.lsd_host_pack_u8_exact(x.ctypes.data, d.ctypes.data, n, 3) == _cabi.LSD_ERR_ARG      # busy
     assert L.lsd_host_pack_u8_end() == 1 and np.array_equal(d, k)
     assert L.lsd_host_pack_last_ms() > 0.0
+    assert L.lsd_host_pack_u8_end() == 0
+    assert L.lsd_host_pack_u8_end() == 0                                               # nothing in flight
+    for rep in range(20):                                                              # back-to-back queued jobs with changing thread counts
+        ka = rng.integers(0, 256, n, dtype=np.uint8); kb = rng.integers(0, 256, n, dtype=np.uint8)
+        xa = ka.astype(np.float32) / 255.0; xb = kb.astype(np.float32) / 255.0
+        da = np.zeros(n, np.uint8); db = np.zeros(n, np.uint8)
+        assert L.lsd_host_pack_u8_begin(xa.ctypes.data, da.ctypes.data, n, 1 + rep % 4) == _cabi.LSD_OK
+        assert L.lsd_host_pack_u8_begin(xb.ctypes.data, db.ctypes.data, n, 1 + (rep * 3) % 5) == _cabi.LSD_OK
+        assert L.lsd_host_pack_u8_end() == 1 and np.array_equal(da, ka)
+        assert L.lsd_host_pack_u8_end() == 1 and np.array_equal(db, kb)
     x[n - 2] = 0.3
     assert L.lsd_host_pack_u8_begin(x.ctypes.data, d.ctypes.data, n, 0) == _cabi.LSD_OK and L.lsd_host_pack_u8_end() == 0
     assert L.lsd_host_pack_u8_begin(None, d.ctypes.data, n, 1) == _cabi.LSD_ERR_ARG
