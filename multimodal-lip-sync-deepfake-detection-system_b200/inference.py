@@ -53,6 +53,21 @@ def gather_logits(local: torch.Tensor, n_windows: int, world_size: int, rank: in
     return out[:n_windows]
 
 
+def auto_transport_gives_up_packing(steady_ms: Sequence[float], all_ms: Sequence[float], t32_s: float) -> bool:
+    """The decision of `host_transport="auto"` (a pure function of the measured pack times, unit-tested on CPU): stop packing when
+    packing is the slower way to feed the GPU.  `steady_ms`: whole-batch pack times in ms, oldest first, without the first batch of a
+    call and without first packs into freshly pinned staging buffers; `all_ms`: every pack but the very first of the predictor;
+    `t32_s`: the fp32 bytes of a batch at ~52 GB/s of PCIe gen5 x16, in seconds.
+      * marginal: the fastest of the last three steady packs (once four are measured) + 0.1 ms is slower than the fp32 copy — a slow
+        pack or two on a busy host must not flip the transport for good;
+      * clearly slower: the last two packs of any kind both took more than 1.5 x the fp32 copy (every GPU of a box fed at once: the
+        host DRAM is the limit and the pack moves more of it than the copy it saves — 12 ms against 4.4 ms with eight GPUs) — decided
+        within a three-batch warm-up call instead of five batches into the next one."""
+    if len(steady_ms) >= 4 and min(steady_ms[-3:]) * 1e-3 + 0.1e-3 > t32_s:
+        return True
+    return len(all_ms) >= 2 and min(all_ms[-2:]) * 1e-3 > 1.5 * t32_s
+
+
 class Predictor:
     """Scoring half of the reference Predictor.  `model` is a `lipsync_b200.LipSyncModel` already on a CUDA device."""
 
@@ -282,33 +297,35 @@ class Predictor:
                 return vh, ah, "fp32", 0
             if ok == 1:
                 B = int(vh.shape[0])
-                if k >= 1 and not fresh:
-                    # pack time of a whole batch, from this (possibly partial) pack
-                    T = L.lsd_host_pack_last_ms() * 1e-3 * B / max(1, B - na)
-                    t32 = vh.numel() * 4 / 52e9
-                    if self.host_split:
-                        f = (T + 0.33e-3 - t32 / 4) / (0.75 * t32 + T)
-                        f = min(0.6, max(0.0, f))
-                        if f < 0.05:
-                            f = 0.0
-                        self._split_frac = f if not hasattr(self, "_split_frac") else 0.5 * self._split_frac + 0.5 * f
-                    if state["mode"] == "auto":
-                        # "auto" stops packing only when packing is the slower way even so: a step of the packed pipeline costs about
-                        # the pack time (+ 0.1 ms: the pack jobs of consecutive batches are queued in the library and run back to back),
-                        # a step of the fp32 pipeline at least the fp32 bytes at ~52 GB/s of PCIe gen5 x16.  Judged on the fastest of the
-                        # last three whole-batch pack times once four have been measured (a slow pack or two on a busy host must not
-                        # flip the transport for good), not counting the first batch (it also pays for starting the pack threads) nor
-                        # the first pack into a freshly pinned staging buffer.  Measured (AVX-512 loop, non-temporal stores): 16 host
-                        # threads for one GPU pack a 64-window batch in 2.2 ms against >= 4.4 ms of copy; 12 threads per GPU with two
-                        # GPUs packing at once need 3.3 ms (4.3 - 4.7 ms per step for the fp32 copy there); with 4 threads per GPU
-                        # (eight GPUs fed at once) the pack is the slower way — it moves more host-DRAM bytes than the copy it saves,
-                        # and with every GPU of a box fed this way the host memory, not PCIe, is the limit.
-                        recent = self.__dict__.setdefault("_pack_ms_hist", [])      # kept across calls
-                        recent.append(T * 1e3)
+                d = self.__dict__
+                first_ever = d.setdefault("_pack_jobs_seen", 0) == 0     # the very first pack of this predictor also starts the pack threads
+                d["_pack_jobs_seen"] += 1
+                T_ms = L.lsd_host_pack_last_ms() * B / max(1, B - na)     # pack time of a whole batch, from this (possibly partial) pack
+                t32 = vh.numel() * 4 / 52e9                               # the fp32 bytes at ~52 GB/s of PCIe gen5 x16
+                steady = k >= 1 and not fresh      # not the first batch of a call, not the first pack into a freshly pinned staging buffer
+                if steady and self.host_split:
+                    f = (T_ms * 1e-3 + 0.33e-3 - t32 / 4) / (0.75 * t32 + T_ms * 1e-3)
+                    f = min(0.6, max(0.0, f))
+                    if f < 0.05:
+                        f = 0.0
+                    self._split_frac = f if not hasattr(self, "_split_frac") else 0.5 * self._split_frac + 0.5 * f
+                if state["mode"] == "auto" and not self.host_split:
+                    # "auto" stops packing only when packing is the slower way (auto_transport_gives_up_packing; histories are kept
+                    # across calls, so a three-batch warm-up call can decide for the next one).  Measured (AVX-512 loop, non-temporal
+                    # stores, queued jobs): 16 host threads for one GPU pack a 64-window batch in 2.2 ms against >= 4.4 ms of copy;
+                    # 12 threads per GPU with two GPUs packing at once need 3.3 ms (4.3 - 4.7 ms per step for the fp32 copy there);
+                    # eight GPUs fed at once: ~12 ms per pack whatever the thread count against 6.5 - 9.8 ms per step for the copy —
+                    # the pack moves more host-DRAM bytes than the copy it saves, and there the host memory, not PCIe, is the limit.
+                    every, recent = d.setdefault("_pack_ms_all", []), d.setdefault("_pack_ms_hist", [])
+                    if not first_ever:
+                        every.append(T_ms)
+                        del every[:-8]
+                    if steady:
+                        recent.append(T_ms)
                         del recent[:-8]
-                        if len(recent) >= 4 and min(recent[-3:]) * 1e-3 + 0.1e-3 > t32 and not self.host_split:
-                            state["mode"] = "fp32"
-                            self._auto_prefers_fp32 = True     # remembered for the later calls of this predictor
+                    if auto_transport_gives_up_packing(recent, every, t32):
+                        state["mode"] = "fp32"             # this batch is packed and exact: it still ships packed, the next ones as fp32
+                        self._auto_prefers_fp32 = True     # remembered for the later calls of this predictor
                 if na > 0:
                     return (vh, stage[s]), ah, "u8 + fp32 split (host-packed part exact)", na
                 return stage[s], ah, "u8 (host-packed, exact)", 0

@@ -245,3 +245,19 @@ def test_host_pack_u8_begin_end():
     assert L.lsd_host_pack_u8_begin(x.ctypes.data, d.ctypes.data, n, 0) == _cabi.LSD_OK and L.lsd_host_pack_u8_end() == 0
     assert L.lsd_host_pack_u8_begin(None, d.ctypes.data, n, 1) == _cabi.LSD_ERR_ARG
     assert L.lsd_host_pack_u8_exact(x.ctypes.data, d.ctypes.data, n, 2) == 0           # the pool is free again
+
+
+def test_auto_transport_decision():
+    """`host_transport="auto"` of `Predictor.score_batches` (the `_run_chunked_inference` contract, predictor.py:554-580): the
+    decision to stop packing is a pure function of the measured pack times (measured cases: DESIGN.md §6/§7)."""
+    from lipsync_b200.inference import auto_transport_gives_up_packing as gives_up
+    t32 = 64 * 3 * 32 * 96 * 96 * 4 / 52e9                       # 4.36 ms: a 64-window fp32 batch over PCIe gen5 x16
+    assert not gives_up([], [], t32)                             # nothing measured: keep packing
+    assert not gives_up([2.2, 2.3, 2.5, 2.2], [2.2] * 5, t32)    # one GPU, 16 threads: packing wins
+    assert not gives_up([3.3] * 6, [3.3] * 6, t32)               # two GPUs packing at once, 12 threads each: packing still wins
+    assert gives_up([4.5, 4.6, 4.4, 4.5], [4.5] * 4, t32)        # marginal rule: the fastest of the last three is slower than the copy
+    assert not gives_up([4.5, 4.6, 3.4, 4.5], [4.5] * 4, t32)    # ... one fast pack among them keeps the transport
+    assert not gives_up([4.5, 4.6, 4.4], [4.5] * 3, t32)         # ... and it needs four measurements
+    assert not gives_up([], [12.0], t32)                         # clearly-slower rule needs two packs in a row
+    assert gives_up([], [12.0, 11.5], t32)                       # eight GPUs fed at once: decided inside a three-batch warm-up call
+    assert not gives_up([], [12.0, 3.0], t32)                    # a single outlier does not flip the transport
