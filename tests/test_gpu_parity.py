@@ -644,6 +644,26 @@ def test_score_batches_u8_transport_bitwise(model):
         assert torch.equal(r, x)
 
 
+def test_expand_u8_is_the_reference_division_bitwise():
+    """`lsd_expand_u8`: device bytes -> fl(k / 255.0f), bit for bit the reference's `astype(np.float32) / 255.0` (video.py:552-556)
+    for every k, at any 16-byte-aligned length; misaligned or odd-length arguments are refused."""
+    from lipsync_b200 import _cabi
+    L = _cabi.lib()
+    g = torch.Generator().manual_seed(3)
+    for n in (16, 256, 4096 + 16, 3 * 96 * 96):
+        k = torch.randint(0, 256, (n,), dtype=torch.uint8, generator=g)
+        k[:min(n, 256)] = torch.arange(min(n, 256), dtype=torch.uint8)
+        src = k.cuda()
+        dst = torch.full((n + 4,), -1.0, dtype=torch.float32, device="cuda")
+        assert L.lsd_expand_u8(src.data_ptr(), dst.data_ptr(), n, torch.cuda.current_stream().cuda_stream) == _cabi.LSD_OK
+        exp = torch.from_numpy(k.numpy().astype(np.float32) / 255.0)
+        assert torch.equal(dst[:n].cpu(), exp) and bool((dst[n:] == -1.0).all())
+    assert L.lsd_expand_u8(src.data_ptr(), dst.data_ptr(), 0, None) == _cabi.LSD_OK
+    assert L.lsd_expand_u8(src.data_ptr(), dst.data_ptr(), 24, None) == _cabi.LSD_ERR_ARG
+    assert L.lsd_expand_u8(src.data_ptr() + 1, dst.data_ptr(), 16, None) == _cabi.LSD_ERR_ARG
+    assert L.lsd_expand_u8(None, dst.data_ptr(), 16, None) == _cabi.LSD_ERR_ARG
+
+
 def test_preprocessed_validation_driver(model, seed0_sd, tmp_path):
     """The reference's preprocessed-mode evaluator (scripts/validate_pipeline.py:382-525) on this backend: confidences equal
     sigmoid(model(batch)) of the same batches bit for bit, decisions equal the fp32 oracle's, files are written."""
